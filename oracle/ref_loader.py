@@ -1,0 +1,82 @@
+"""TEST INFRASTRUCTURE ONLY -- loads the *verbatim* reference pieces that can run here.
+
+The reference (wingos80/RL4AFCS, mounted read-only at /root/reference in the build
+container; absent on the GPU box) cannot be imported as a whole: ``objects.py:29``
+imports TensorFlow, ``envs/linear/env.py:2-4`` imports gymnasium + matplotlib, none
+of which are installed.  Two pieces are pure numpy and run unmodified:
+
+* ``Ce500ShortPeriod`` (``envs/linear/env.py:7-264``) -- imported from the file where
+  it lies, with stub ``gymnasium`` / ``matplotlib`` modules registered first;
+* ``RLS`` (``objects.py:439-549``) -- the ``ClassDef`` node is extracted with ``ast``
+  and exec'd with ``{'np': numpy}``.
+
+Nothing is copied into this repo; the source is read from /root/reference at call
+time.  Used by ``oracle/make_golden.py`` and ``tests/test_oracle_vs_reference.py``
+(skipped when /root/reference is absent).  Never imported by the product package.
+"""
+from __future__ import annotations
+
+import ast
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("RL4AFCS_REFERENCE", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "envs", "linear", "env.py"))
+
+
+def _install_stubs() -> None:
+    if "gymnasium" not in sys.modules:
+        gym = types.ModuleType("gymnasium")
+
+        class Env:  # minimal stand-in for gymnasium.Env
+            def reset(self, seed=None, options=None):
+                return None
+
+        gym.Env = Env
+        spaces = types.ModuleType("gymnasium.spaces")
+        spaces.Box = object
+        gym.spaces = spaces
+        sys.modules["gymnasium"] = gym
+        sys.modules["gymnasium.spaces"] = spaces
+    if "matplotlib" not in sys.modules:
+        mpl = types.ModuleType("matplotlib")
+        plt = types.ModuleType("matplotlib.pyplot")
+        mpl.pyplot = plt
+        sys.modules["matplotlib"] = mpl
+        sys.modules["matplotlib.pyplot"] = plt
+
+
+def load_reference_linear_env():
+    """Return the verbatim ``Ce500ShortPeriod`` class (envs/linear/env.py:7)."""
+    if not reference_available():
+        raise FileNotFoundError(f"reference tree not found at {REFERENCE_ROOT}")
+    _install_stubs()
+    import importlib.util
+
+    path = os.path.join(REFERENCE_ROOT, "envs", "linear", "env.py")
+    spec = importlib.util.spec_from_file_location("_rl4afcs_ref_linear_env", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.Ce500ShortPeriod
+
+
+def load_reference_rls():
+    """Return the verbatim ``RLS`` class (objects.py:439-549)."""
+    if not reference_available():
+        raise FileNotFoundError(f"reference tree not found at {REFERENCE_ROOT}")
+    import numpy as np
+
+    path = os.path.join(REFERENCE_ROOT, "objects.py")
+    with open(path, "r", encoding="utf-8") as fh:
+        tree = ast.parse(fh.read(), filename=path)
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == "RLS":
+            ns = {"np": np}
+            code = compile(ast.Module(body=[node], type_ignores=[]), path, "exec")
+            exec(code, ns)
+            return ns["RLS"]
+    raise RuntimeError("class RLS not found in reference objects.py")
