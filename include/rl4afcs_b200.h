@@ -1,0 +1,221 @@
+/* rl4afcs_b200 -- C ABI of the B200-native batched IDHP flight-control engine.
+ *
+ * The reference (wingos80/RL4AFCS) has no FFI on this path: it is a Python object API
+ *   envs/linear/env.py:156,222        Ce500ShortPeriod.step / reset
+ *   objects.py:142-281                Critic / Actor (call, get_weight_update, soft_update)
+ *   objects.py:439-549                RLS (update, F, G, _reset)
+ *   objects.py:551-1004               IDHPsp (train and its helpers)
+ * so the drop-in boundary is the Python package `rl4afcs_b200` (same class / method /
+ * attribute names with a leading batch dimension), and THIS header is the thin native
+ * layer those classes call through ctypes.  Each entry point cites the reference
+ * function(s) it replaces.  INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - caller owns every buffer; nothing here allocates except rl4_sp_episode_host()'s
+ *     context (rl4_ctx_create / rl4_ctx_destroy);
+ *   - device buffers are structure-of-arrays planes  plane[field * stride + agent],
+ *     agent index fastest, `stride` >= n_agents;
+ *   - dtype policy: RL4_FP64 (all double), RL4_FP32 (all float), RL4_MIXED (the reference's
+ *     own mix: network plane float, env/RLS/trace plane double);
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), returns
+ *     0 on success, <0 for an argument error, >0 = cudaError_t; rl4_last_error() gives text;
+ *   - sm_100a only.  There is no CPU fallback: without a B200 the calls fail.
+ */
+#ifndef RL4AFCS_B200_H
+#define RL4AFCS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RL4_ABI_VERSION 1
+
+enum rl4_policy { RL4_FP64 = 0, RL4_FP32 = 1, RL4_MIXED = 2 };
+enum rl4_elig   { RL4_ELIG_NONE = 0, RL4_ELIG_ACCUMULATING = 1, RL4_ELIG_REPLACING = 2 };
+/* plant variants selectable per agent (envs/linear/env.py:127-154) */
+enum rl4_fault  { RL4_FAULT_NONE = 0, RL4_FAULT_INVERT_ELEVATOR = 1, RL4_FAULT_DAMP_ELEVATOR = 2,
+                  RL4_FAULT_SHIFT_CG = 3, RL4_FAULT_COUNT = 4 };
+
+/* ---- state planes of the short-period agent (objects.py:551-1004 loop-carried values) ---- */
+/* env plane (dtype TE): plant state, RLS model, traces, statistics */
+enum rl4_sp_env_field {
+    RL4_SPE_X = 0,          /* [2] env.x == agent x_k            envs/linear/env.py:43,193 */
+    RL4_SPE_XPREV = 2,      /* [2] x_{k-1}                        objects.py:980 */
+    RL4_SPE_THETA = 4,      /* [6] RLS params (3,2) row-major     objects.py:461 */
+    RL4_SPE_COV = 10,       /* [9] RLS Cov (3,3) row-major        objects.py:470 */
+    RL4_SPE_CGRAD_PREV = 19,/* [1] reward_grad[0] of step k-1     objects.py:984 */
+    RL4_SPE_EPS = 20,       /* [2] last RLS innovation            objects.py:537 */
+    RL4_SPE_EPS_NORM = 22,  /* [1]                                objects.py:539 */
+    RL4_SPE_SUM_C = 23,     /* [1] running sum of rewards         functions.py:53 */
+    RL4_SPE_SUM_ABS_E = 24, /* [1] running sum |e| (nMAE numerator; addition of this repo) */
+    RL4_SPE_EA = 25,        /* [8] actor trace E (1,8)            objects.py:236-254 */
+    RL4_SPE_EC_H = 33,      /* [4] critic trace E[0,0:4] == E[1,4:8]   objects.py:161-188 */
+    RL4_SPE_EC_W1R0 = 37,   /* [4] critic trace E[0,8:12] */
+    RL4_SPE_EC_W1R1 = 41,   /* [4] critic trace E[1,8:12] */
+    RL4_SPE_COUNT = 45
+};
+/* net plane (dtype TN): actions, weights, learning rates */
+enum rl4_sp_net_field {
+    RL4_SPN_A = 0,          /* [1] a_k (normalised)               objects.py:933,981 */
+    RL4_SPN_APREV = 1,      /* [1] */
+    RL4_SPN_W1A = 2,        /* [4] actor W1 (1,4)                 objects.py:590 */
+    RL4_SPN_W2A = 6,        /* [4] actor W2 (4,1) */
+    RL4_SPN_W1C = 10,       /* [4] critic W1 (1,4)                objects.py:591 */
+    RL4_SPN_W2C = 14,       /* [8] critic W2 (4,2) row-major */
+    RL4_SPN_W1T = 22,       /* [4] target critic                  objects.py:592 */
+    RL4_SPN_W2T = 26,       /* [8] */
+    RL4_SPN_MPREV = 34,     /* [4] dx1dx0_prev (2,2) row-major    objects.py:985 */
+    RL4_SPN_ETA_A = 38,     /* [1] actor SGD learning rate        objects.py:918 */
+    RL4_SPN_ETA_C = 39,     /* [1] critic SGD learning rate       objects.py:919 */
+    RL4_SPN_COUNT = 40
+};
+/* int plane (int32) */
+enum rl4_sp_int_field {
+    RL4_SPI_COOLDOWN = 0,   /* objects.py:568,809-835 */
+    RL4_SPI_FLAGS = 1,      /* RL4_SPF_* */
+    RL4_SPI_DIVERGED_STEP = 2, /* step whose reward was NaN (objects.py:991), -1 otherwise */
+    RL4_SPI_CONV_STEP = 3,  /* last step with |alpha error| > 0.5 deg (utils.py:350-369), -1 if none */
+    RL4_SPI_COUNT = 4
+};
+enum rl4_sp_flag {
+    RL4_SPF_CHANGED = 1,    /* one-shot RLS reset done            objects.py:838-841 */
+    RL4_SPF_LR_INIT = 2,    /* eta still the python float */
+    RL4_SPF_LAMBDA_LOW = 4, /* gamma_lambda currently = lambda_l*gamma  objects.py:814-832 */
+    RL4_SPF_X_NAN = 8       /* a NaN state was logged             functions.py:162 */
+};
+
+typedef struct rl4_sp_state {
+    void*    env;           /* [RL4_SPE_COUNT][stride] of TE */
+    void*    net;           /* [RL4_SPN_COUNT][stride] of TN */
+    int32_t* ints;          /* [RL4_SPI_COUNT][stride] */
+    int64_t  stride;
+} rl4_sp_state;
+
+/* per-agent hyper-parameter overrides (device pointers, NULL = use the shared scalar) */
+enum rl4_sp_hp {
+    RL4_HP_ETA_A_H = 0, RL4_HP_ETA_A_L, RL4_HP_ETA_C_H, RL4_HP_ETA_C_L,
+    RL4_HP_LAMBDA_H, RL4_HP_LAMBDA_L, RL4_HP_GAMMA, RL4_HP_GAMMA_SQ, RL4_HP_TAU, RL4_HP_KAPPA,
+    RL4_HP_RLS_GAMMA, RL4_HP_RLS_COV0, RL4_HP_ERROR_THRESH_DEG, RL4_HP_REF_AMP,
+    RL4_HP_COUNT
+};
+enum rl4_sp_hpi {
+    RL4_HPI_MULTISTEP = 0, RL4_HPI_WARMUP_STEPS, RL4_HPI_COOLDOWN_STEPS,
+    RL4_HPI_FAULT_STEP, RL4_HPI_FAULT_KIND, RL4_HPI_ELIG_A, RL4_HPI_ELIG_C,
+    RL4_HPI_COUNT
+};
+
+/* Shared configuration: idhp_sp.py:45-52,150-173 and the plant of envs/linear/env.py:66-154.
+ * The plant matrices are computed by the host exactly as the reference does (Python floats). */
+typedef struct rl4_sp_params {
+    double A[RL4_FAULT_COUNT][4];   /* row-major 2x2 per plant variant; variant 0 = nominal */
+    double B[RL4_FAULT_COUNT][2];
+    double dt;
+    double hp[RL4_HP_COUNT];        /* shared scalars, indexed by rl4_sp_hp */
+    int32_t hpi[RL4_HPI_COUNT];     /* shared ints, indexed by rl4_sp_hpi (fault_step < 0: no fault) */
+    int32_t q3_alias;               /* reproduce the x aliasing at k == 1 (reference: 1) */
+    int32_t q7_numpy1;              /* numpy-1.x float32-vs-python-float compare (reference: 1) */
+    const double*  hp_agent[RL4_HP_COUNT];    /* optional per-agent overrides, length n_agents */
+    const int32_t* hpi_agent[RL4_HPI_COUNT];
+} rl4_sp_params;
+
+/* Optional trajectory log: rows for agents [0, n_agents_logged), steps k with
+ * (k - k0) % every == 0, layout  buf[((row * n_fields) + field) * n_agents_logged + agent]. */
+enum rl4_sp_log_level { RL4_LOG_NONE = 0, RL4_LOG_BASIC = 1, RL4_LOG_FULL = 2 };
+enum rl4_sp_log_basic_field {   /* IDHPsp._log objects.py:682-688 */
+    RL4_LB_X = 0 /* [2] */, RL4_LB_A = 2, RL4_LB_C = 3, RL4_LB_REF = 4, RL4_LB_E = 5, RL4_LB_COUNT = 6
+};
+enum rl4_sp_log_full_field {    /* the rest of objects.py:691-726 */
+    RL4_LF_AW1 = 6 /* [4] */, RL4_LF_AW2 = 10 /* [4] */, RL4_LF_CW1 = 14 /* [4] */, RL4_LF_CW2 = 18 /* [8] */,
+    RL4_LF_AE = 26 /* [8] */, RL4_LF_CE = 34 /* [12] h, w1 row0, w1 row1 */,
+    RL4_LF_AGRAD = 46 /* [8] a_all_grad */, RL4_LF_CGRAD = 54 /* [12] c_all_grad */,
+    RL4_LF_PARAMS = 66 /* [6] */, RL4_LF_COV = 72 /* [9] */, RL4_LF_EPS_NORM = 81, RL4_LF_EPS_ABS = 82 /* [2] */,
+    RL4_LF_LAM = 84 /* [2] */, RL4_LF_LAM_T = 86 /* [2] */, RL4_LF_TD = 88 /* [2] */, RL4_LF_DADZ = 90,
+    RL4_LF_M = 91 /* [4] */, RL4_LF_LOSS_GRAD = 95, RL4_LF_COUNT = 96
+};
+typedef struct rl4_sp_log {
+    double* buf;                /* device, may be NULL when level == RL4_LOG_NONE */
+    int32_t level;
+    int32_t every;              /* >= 1 */
+    int64_t n_agents_logged;
+} rl4_sp_log;
+
+/* ---- library ---- */
+int         rl4_abi_version(void);
+const char* rl4_last_error(void);
+/* 0 if `device` is an sm_100 GPU this library can run on */
+int         rl4_device_check(int device);
+
+/* ---- short-period path ---- */
+
+/* IDHPsp.__init__/_setup_networks/_setup_optimizers/_invert_controller + train() prologue
+ * (objects.py:552-615,843-851,911-948) and Ce500ShortPeriod.reset (envs/linear/env.py:222-258):
+ * builds the loop-entry state from x0 [2][stride_in] and initial weights W1a[4], W2a[4],
+ * W1c[4], W2c[8] (each [n][stride_in] planes of double, rounded to the policy's dtypes). */
+int rl4_sp_init(int policy, const rl4_sp_params* p, const double* x0, const double* w1a, const double* w2a,
+                const double* w1c, const double* w2c, int64_t stride_in,
+                rl4_sp_state st, int64_t n_agents, void* stream);
+
+/* IDHPsp.train() hot loop (objects.py:950-1004), steps [k0, k0 + n_steps) for every agent, fused
+ * with env.step (envs/linear/env.py:156-220), Critic/Actor forward + traces (objects.py:151-193,
+ * 226-259), _update_networks (:884-908), RLS.update (:492-543), _adapt_check (:783-841) and the
+ * episode statistics of MC_run_seed (functions.py:39-60).  `ref_base` is a device table with at
+ * least k0 + n_steps samples; the reference signal is hp[REF_AMP] * ref_base[k] (idhp_sp.py:44,174).
+ * `use_traces` = 0 requires elig_a == elig_c == RL4_ELIG_NONE for every agent. */
+int rl4_sp_run(int policy, const rl4_sp_params* p, const double* ref_base, int32_t k0, int32_t n_steps,
+               rl4_sp_state st, int64_t n_agents, int32_t use_traces, rl4_sp_log log, void* stream);
+
+/* Ce500ShortPeriod.step (envs/linear/env.py:156-220) for every agent: step-API form.
+ *   x [2][stride] (TE, in/out), action_deg [stride] (TN; the caller's 20*a, degrees),
+ *   out_reward, out_e, out_reward_grad0 [stride] (TE).  stepp = the env's step counter. */
+int rl4_sp_env_step(int policy, const rl4_sp_params* p, const double* ref_base, int32_t stepp,
+                    void* x, const void* action_deg, void* out_reward, void* out_e, void* out_reward_grad0,
+                    int64_t stride, int64_t n_agents, void* stream);
+
+/* RLS.update (objects.py:492-543): theta [6][stride], cov [9][stride] in/out (TE);
+ * dx0 [2][stride], da0 [stride], dx1 [2][stride] (TE); out eps [2][stride], eps_norm [stride]. */
+int rl4_sp_rls_update(int policy, const rl4_sp_params* p, void* theta, void* cov,
+                      const void* dx0, const void* da0, const void* dx1, void* out_eps, void* out_eps_norm,
+                      int64_t stride, int64_t n_agents, void* stream);
+
+/* Critic.call (objects.py:151-193) / Actor.call (:226-259): forward + trace for every agent.
+ *   z [stride] (TN), w1 [4][stride], w2 [4*n_out][stride] (TN), E planes (TE, in/out),
+ *   out [n_out][stride] (TN), gamma_lambda shared, elig mode shared.
+ *   critic: n_out = 2, E = [12][stride] (h, w1 row0, w1 row1);  actor: n_out = 1, E = [8][stride],
+ *   out_dadz [stride] (TN) may be NULL (objects.py:876-878). */
+int rl4_sp_critic_forward(int policy, const void* z, const void* w1, const void* w2, void* E, void* out_lambda,
+                          double gamma_lambda, int32_t elig, int64_t stride, int64_t n_agents, void* stream);
+int rl4_sp_actor_forward(int policy, const void* z, const void* w1, const void* w2, void* E, void* out_a,
+                         void* out_dadz, double gamma_lambda, int32_t elig, int64_t stride, int64_t n_agents,
+                         void* stream);
+
+/* ---- host-buffer episode (what a reference user calls: IDHPsp(...).train() for a batch) ----
+ * Copies x0 / weights from host memory, runs rl4_sp_init + rl4_sp_run for n_steps on the GPU
+ * and copies the final state planes and statistics back.  Host buffers may be pageable or pinned. */
+typedef struct rl4_ctx rl4_ctx;
+int rl4_ctx_create(int device, int policy, int64_t max_agents, int32_t max_steps, rl4_ctx** out);
+int rl4_ctx_destroy(rl4_ctx* ctx);
+typedef struct rl4_sp_host_io {
+    const double* x0;           /* [2][n] */
+    const double* w1a;          /* [4][n] */
+    const double* w2a;          /* [4][n] */
+    const double* w1c;          /* [4][n] */
+    const double* w2c;          /* [8][n] */
+    const double* ref_base;     /* [n_steps] */
+    void*    out_env;           /* [RL4_SPE_COUNT][n] of TE */
+    void*    out_net;           /* [RL4_SPN_COUNT][n] of TN */
+    int32_t* out_ints;          /* [RL4_SPI_COUNT][n] */
+} rl4_sp_host_io;
+int rl4_sp_episode_host(rl4_ctx* ctx, const rl4_sp_params* p, const rl4_sp_host_io* io,
+                        int64_t n_agents, int32_t n_steps, int32_t use_traces);
+
+/* ---- measurement helpers (bench.py roofline denominators) ---- */
+/* Runs a dependent-FMA micro-kernel (is_double ? DFMA : FFMA) and returns achieved FLOP/s. */
+int rl4_peak_fma(int is_double, double* out_flops_per_s, void* stream);
+/* number of kernel launches issued by this library since load (bench.py "gpu_launches") */
+int64_t rl4_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

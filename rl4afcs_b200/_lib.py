@@ -1,0 +1,115 @@
+"""ctypes binding of librl4afcs_b200.so (include/rl4afcs_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing, fails to load, or the
+device is not an sm_100 GPU, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librl4afcs_b200.so")
+
+# enums of include/rl4afcs_b200.h
+FP64, FP32, MIXED = 0, 1, 2
+POLICY = {"fp64": FP64, "fp32": FP32, "mixed": MIXED}
+ELIG = {None: 0, "none": 0, "accumulating": 1, "replacing": 2}
+FAULT = {None: 0, "none": 0, "invert_elevator": 1, "damp_elevator": 2, "shift_cg": 3}
+FAULT_COUNT = 4
+
+SPE = dict(X=0, XPREV=2, THETA=4, COV=10, CGRAD_PREV=19, EPS=20, EPS_NORM=22, SUM_C=23, SUM_ABS_E=24,
+           EA=25, EC_H=33, EC_W1R0=37, EC_W1R1=41, COUNT=45)
+SPN = dict(A=0, APREV=1, W1A=2, W2A=6, W1C=10, W2C=14, W1T=22, W2T=26, MPREV=34, ETA_A=38, ETA_C=39, COUNT=40)
+SPI = dict(COOLDOWN=0, FLAGS=1, DIVERGED_STEP=2, CONV_STEP=3, COUNT=4)
+SPF = dict(CHANGED=1, LR_INIT=2, LAMBDA_LOW=4, X_NAN=8)
+HP = dict(ETA_A_H=0, ETA_A_L=1, ETA_C_H=2, ETA_C_L=3, LAMBDA_H=4, LAMBDA_L=5, GAMMA=6, GAMMA_SQ=7, TAU=8,
+          KAPPA=9, RLS_GAMMA=10, RLS_COV0=11, ERROR_THRESH_DEG=12, REF_AMP=13, COUNT=14)
+HPI = dict(MULTISTEP=0, WARMUP_STEPS=1, COOLDOWN_STEPS=2, FAULT_STEP=3, FAULT_KIND=4, ELIG_A=5, ELIG_C=6, COUNT=7)
+LOG_NONE, LOG_BASIC, LOG_FULL = 0, 1, 2
+LB = dict(X=0, A=2, C=3, REF=4, E=5, COUNT=6)
+LF = dict(AW1=6, AW2=10, CW1=14, CW2=18, AE=26, CE=34, AGRAD=46, CGRAD=54, PARAMS=66, COV=72, EPS_NORM=81,
+          EPS_ABS=82, LAM=84, LAM_T=86, TD=88, DADZ=90, M=91, LOSS_GRAD=95, COUNT=96)
+
+
+class SpState(ctypes.Structure):
+    _fields_ = [("env", ctypes.c_void_p), ("net", ctypes.c_void_p), ("ints", ctypes.c_void_p),
+                ("stride", ctypes.c_int64)]
+
+
+class SpParams(ctypes.Structure):
+    _fields_ = [
+        ("A", (ctypes.c_double * 4) * FAULT_COUNT),
+        ("B", (ctypes.c_double * 2) * FAULT_COUNT),
+        ("dt", ctypes.c_double),
+        ("hp", ctypes.c_double * HP["COUNT"]),
+        ("hpi", ctypes.c_int32 * HPI["COUNT"]),
+        ("q3_alias", ctypes.c_int32),
+        ("q7_numpy1", ctypes.c_int32),
+        ("hp_agent", ctypes.c_void_p * HP["COUNT"]),
+        ("hpi_agent", ctypes.c_void_p * HPI["COUNT"]),
+    ]
+
+
+class SpLog(ctypes.Structure):
+    _fields_ = [("buf", ctypes.c_void_p), ("level", ctypes.c_int32), ("every", ctypes.c_int32),
+                ("n_agents_logged", ctypes.c_int64)]
+
+
+class SpHostIO(ctypes.Structure):
+    _fields_ = [("x0", ctypes.c_void_p), ("w1a", ctypes.c_void_p), ("w2a", ctypes.c_void_p),
+                ("w1c", ctypes.c_void_p), ("w2c", ctypes.c_void_p), ("ref_base", ctypes.c_void_p),
+                ("out_env", ctypes.c_void_p), ("out_net", ctypes.c_void_p), ("out_ints", ctypes.c_void_p)]
+
+
+EXPORTS = [
+    "rl4_abi_version", "rl4_last_error", "rl4_device_check",
+    "rl4_sp_init", "rl4_sp_run", "rl4_sp_env_step", "rl4_sp_rls_update",
+    "rl4_sp_critic_forward", "rl4_sp_actor_forward",
+    "rl4_ctx_create", "rl4_ctx_destroy", "rl4_sp_episode_host",
+    "rl4_peak_fma", "rl4_launch_count",
+]
+
+_lib = None
+
+
+class Rl4Error(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library; raises when it is absent (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise Rl4Error(f"{LIB_PATH} is missing: build it with `python -m rl4afcs_b200.build` "
+                       "(nvcc, sm_100a). rl4afcs_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+    L.rl4_abi_version.restype = ctypes.c_int
+    L.rl4_last_error.restype = ctypes.c_char_p
+    L.rl4_device_check.argtypes = [ctypes.c_int]
+    L.rl4_sp_init.argtypes = [ctypes.c_int, ctypes.POINTER(SpParams), vp, vp, vp, vp, vp, i64, SpState, i64, vp]
+    L.rl4_sp_run.argtypes = [ctypes.c_int, ctypes.POINTER(SpParams), vp, i32, i32, SpState, i64, i32, SpLog, vp]
+    L.rl4_sp_env_step.argtypes = [ctypes.c_int, ctypes.POINTER(SpParams), vp, i32, vp, vp, vp, vp, vp, i64, i64, vp]
+    L.rl4_sp_rls_update.argtypes = [ctypes.c_int, ctypes.POINTER(SpParams), vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]
+    L.rl4_sp_critic_forward.argtypes = [ctypes.c_int, vp, vp, vp, vp, vp, dbl, i32, i64, i64, vp]
+    L.rl4_sp_actor_forward.argtypes = [ctypes.c_int, vp, vp, vp, vp, vp, vp, dbl, i32, i64, i64, vp]
+    L.rl4_ctx_create.argtypes = [ctypes.c_int, ctypes.c_int, i64, i32, ctypes.POINTER(vp)]
+    L.rl4_ctx_destroy.argtypes = [vp]
+    L.rl4_sp_episode_host.argtypes = [vp, ctypes.POINTER(SpParams), ctypes.POINTER(SpHostIO), i64, i32, i32]
+    L.rl4_peak_fma.argtypes = [ctypes.c_int, ctypes.POINTER(dbl), vp]
+    L.rl4_launch_count.restype = i64
+    for name in EXPORTS:
+        fn = getattr(L, name)
+        if name not in ("rl4_last_error", "rl4_launch_count", "rl4_abi_version"):
+            fn.restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().rl4_last_error().decode("utf-8", "replace")
+        raise Rl4Error(f"{what} failed (rc={rc}): {msg}")

@@ -1,0 +1,105 @@
+// Library plumbing: error text, device check, launch counter, FMA peak micro-benchmark.
+#include "rl4_runtime.h"
+#include "../../include/rl4afcs_b200.h"
+#include <cstdarg>
+#include <cstdio>
+
+namespace rl4 {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launch_count{0};
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what)
+{
+    set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return (int)e;
+}
+
+// 16 independent dependent-FMA chains per thread: enough ILP to saturate the pipe at
+// modest occupancy.  Used only as the measured denominator of the pipe roofline.
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T b)
+{
+    T acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = (T)(threadIdx.x + j) * (T)1e-3;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], a, b);
+    }
+    T s = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += acc[j];
+    if (s == (T)123456789) out[0] = s;   // never true; keeps the chains alive
+}
+
+template <typename T>
+static int run_peak(double* out_flops, cudaStream_t stream)
+{
+    int dev = 0, sms = 0;
+    RL4_CUDA(cudaGetDevice(&dev));
+    RL4_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    T* d = nullptr;
+    RL4_CUDA(cudaMalloc(&d, sizeof(T)));
+    cudaEvent_t e0, e1;
+    RL4_CUDA(cudaEventCreate(&e0));
+    RL4_CUDA(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        RL4_CUDA(cudaEventRecord(e0, stream));
+        fma_peak_kernel<T><<<blocks, threads, 0, stream>>>(d, iters, (T)0.999, (T)1e-3);
+        int rc = check_launch("fma_peak_kernel");
+        if (rc) return rc;
+        RL4_CUDA(cudaEventRecord(e1, stream));
+        RL4_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        RL4_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 16.0 * iters * (double)blocks * threads / (ms * 1e-3);
+        if (rep > 0 && flops > best) best = flops;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *out_flops = best;
+    return 0;
+}
+
+}  // namespace rl4
+
+extern "C" {
+
+int rl4_abi_version(void) { return RL4_ABI_VERSION; }
+
+const char* rl4_last_error(void) { return rl4::g_err; }
+
+int rl4_device_check(int device)
+{
+    cudaDeviceProp prop;
+    RL4_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        rl4::set_error("rl4_device_check: device %d is sm_%d%d; this library is built for sm_100a only and has no fallback",
+                       device, prop.major, prop.minor);
+        return -2;
+    }
+    return 0;
+}
+
+int rl4_peak_fma(int is_double, double* out_flops_per_s, void* stream)
+{
+    RL4_REQUIRE(out_flops_per_s != nullptr, "out_flops_per_s is NULL");
+    return is_double ? rl4::run_peak<double>(out_flops_per_s, (cudaStream_t)stream)
+                     : rl4::run_peak<float>(out_flops_per_s, (cudaStream_t)stream);
+}
+
+int64_t rl4_launch_count(void) { return rl4::g_launch_count.load(); }
+
+}  // extern "C"
