@@ -212,6 +212,10 @@ int rl4_sp_episode_host(rl4_ctx* ctx, const rl4_sp_params* p, const rl4_sp_host_
 /* ---- measurement helpers (bench.py roofline denominators) ---- */
 /* Runs a dependent-FMA micro-kernel (is_double ? DFMA : FFMA) and returns achieved FLOP/s. */
 int rl4_peak_fma(int is_double, double* out_flops_per_s, void* stream);
+/* Test hook: element-wise probe of the arithmetic primitives on device arrays.
+ * op 0: tanh t13 (double)  1: tanh t13 (float)  2: shared-reciprocal division a/b (double)
+ * 3: __ddiv_rn(a, b).  Used by tests/test_gpu_math.py only. */
+int rl4_test_math(int op, const void* a, const void* b, void* out, int64_t n, void* stream);
 /* number of kernel launches issued by this library since load (bench.py "gpu_launches") */
 int64_t rl4_launch_count(void);
 

@@ -106,6 +106,10 @@ def lib() -> ctypes.CDLL:
                              ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]
     L.orc_sp_init.restype = ctypes.c_int
     L.orc_sp_init.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_int64]
+    L.orc_tanh_t13_f64_array.restype = None
+    L.orc_tanh_t13_f64_array.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+    L.orc_tanh_t13_f32_array.restype = None
+    L.orc_tanh_t13_f32_array.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
     L.orc_tanh_t13_f64.restype = ctypes.c_double
     L.orc_tanh_t13_f64.argtypes = [ctypes.c_double]
     L.orc_tanh_t13_f32.restype = ctypes.c_float
@@ -277,7 +281,12 @@ def run(policy: str, cfg: np.ndarray, ref_base: np.ndarray, states: np.ndarray, 
 
 def tanh_t13(x: np.ndarray) -> np.ndarray:
     L = lib()
-    x = np.asarray(x)
+    x = np.ascontiguousarray(x)
     if x.dtype == np.float32:
-        return np.array([L.orc_tanh_t13_f32(float(v)) for v in x.ravel()], dtype=np.float32).reshape(x.shape)
-    return np.array([L.orc_tanh_t13_f64(float(v)) for v in x.ravel()], dtype=np.float64).reshape(x.shape)
+        y = np.empty_like(x)
+        L.orc_tanh_t13_f32_array(_ptr(x), _ptr(y), x.size)
+        return y
+    x = x.astype(np.float64, copy=False)
+    y = np.empty_like(x)
+    L.orc_tanh_t13_f64_array(_ptr(x), _ptr(y), x.size)
+    return y

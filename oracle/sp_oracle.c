@@ -121,6 +121,8 @@ int orc_sp_init(int policy, const orc_sp_cfg* cfgs, int cfg_stride,
     return 0;
 }
 
+void orc_tanh_t13_f64_array(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = orc_t13_f64(x[i]); }
+void orc_tanh_t13_f32_array(const float* x, float* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = orc_t13_f32(x[i]); }
 double orc_tanh_t13_f64(double x) { return orc_t13_f64(x); }
 float  orc_tanh_t13_f32(float x)  { return orc_t13_f32(x); }
 int orc_sizeof_cfg(void)    { return (int)sizeof(orc_sp_cfg); }

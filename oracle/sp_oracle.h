@@ -125,6 +125,8 @@ int orc_sp_init(int policy, const orc_sp_cfg* cfgs, int cfg_stride,
                 orc_sp_state* states, int64_t n_agents);
 
 /* the oracle's tanh variants, exposed for accuracy tests */
+void orc_tanh_t13_f64_array(const double* x, double* y, int64_t n);
+void orc_tanh_t13_f32_array(const float* x, float* y, int64_t n);
 double orc_tanh_t13_f64(double x);
 float  orc_tanh_t13_f32(float x);
 

@@ -67,7 +67,7 @@ EXPORTS = [
     "rl4_sp_init", "rl4_sp_run", "rl4_sp_env_step", "rl4_sp_rls_update",
     "rl4_sp_critic_forward", "rl4_sp_actor_forward",
     "rl4_ctx_create", "rl4_ctx_destroy", "rl4_sp_episode_host",
-    "rl4_peak_fma", "rl4_launch_count",
+    "rl4_peak_fma", "rl4_launch_count", "rl4_test_math",
 ]
 
 _lib = None
@@ -101,6 +101,7 @@ def load() -> ctypes.CDLL:
     L.rl4_sp_episode_host.argtypes = [vp, ctypes.POINTER(SpParams), ctypes.POINTER(SpHostIO), i64, i32, i32]
     L.rl4_peak_fma.argtypes = [ctypes.c_int, ctypes.POINTER(dbl), vp]
     L.rl4_launch_count.restype = i64
+    L.rl4_test_math.argtypes = [ctypes.c_int, vp, vp, vp, i64, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("rl4_last_error", "rl4_launch_count", "rl4_abi_version"):

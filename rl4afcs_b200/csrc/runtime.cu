@@ -1,5 +1,6 @@
 // Library plumbing: error text, device check, launch counter, FMA peak micro-benchmark.
 #include "rl4_runtime.h"
+#include "rl4_math.cuh"
 #include "../../include/rl4afcs_b200.h"
 #include <cstdarg>
 #include <cstdio>
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T
     for (int j = 0; j < 16; ++j) acc[j] = (T)(threadIdx.x + j) * (T)1e-3;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], a, b);
+        for (int j = 0; j < 16; ++j) acc[j] = ::fma(acc[j], a, b);
     }
     T s = 0;
 #pragma unroll
@@ -73,6 +74,20 @@ static int run_peak(double* out_flops, cudaStream_t stream)
     return 0;
 }
 
+// element-wise probes of the arithmetic primitives (tests/test_gpu_math.py)
+__global__ void math_probe_kernel(int op, const void* a, const void* b, void* out, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    switch (op) {
+    case 0: ((double*)out)[i] = tanh_t13(Rn<double>(((const double*)a)[i])).v; break;
+    case 1: ((float*)out)[i] = tanh_t13(Rn<float>(((const float*)a)[i])).v; break;
+    case 2: { const double d = ((const double*)b)[i]; ((double*)out)[i] = div_rn_shared(((const double*)a)[i], d, rcp_refined(d)); break; }
+    case 3: ((double*)out)[i] = __ddiv_rn(((const double*)a)[i], ((const double*)b)[i]); break;
+    default: break;
+    }
+}
+
 }  // namespace rl4
 
 extern "C" {
@@ -98,6 +113,15 @@ int rl4_peak_fma(int is_double, double* out_flops_per_s, void* stream)
     RL4_REQUIRE(out_flops_per_s != nullptr, "out_flops_per_s is NULL");
     return is_double ? rl4::run_peak<double>(out_flops_per_s, (cudaStream_t)stream)
                      : rl4::run_peak<float>(out_flops_per_s, (cudaStream_t)stream);
+}
+
+int rl4_test_math(int op, const void* a, const void* b, void* out, int64_t n, void* stream)
+{
+    RL4_REQUIRE(a && out && n >= 0 && op >= 0 && op <= 3, "bad argument");
+    RL4_REQUIRE(op < 2 || b, "b is NULL");
+    if (n == 0) return 0;
+    rl4::math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(op, a, b, out, n);
+    return rl4::check_launch("math_probe_kernel");
 }
 
 int64_t rl4_launch_count(void) { return rl4::g_launch_count.load(); }

@@ -217,18 +217,27 @@ __device__ __forceinline__ void sp_rls_update(Rn<TE> (&th)[6], Rn<TE> (&cv)[9], 
     xcx = fma(X[1], CX[1], xcx);
     xcx = fma(X[2], CX[2], xcx);
     const E den = rls_gamma + xcx;
+    const TE rden = make_rcp(den.v);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) K[i] = CX[i] / den;              // objects.py:521
+    for (int i = 0; i < 3; ++i) K[i] = div_by(CX[i], den, rden); // objects.py:521
 #pragma unroll
     for (int j = 0; j < 3; ++j) {                                // objects.py:522
         th[j * 2 + 0] = th[j * 2 + 0] + K[j] * eps[0];
         th[j * 2 + 1] = th[j * 2 + 1] + K[j] * eps[1];
     }
+    if (rls_gamma.v == TE(1)) {                                  // x / 1 == x exactly: skip the nine divisions
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
-            cv[i * 3 + j] = (cv[i * 3 + j] - K[i] * CX[j]) / rls_gamma;   // objects.py:529-530
+            for (int j = 0; j < 3; ++j) cv[i * 3 + j] = cv[i * 3 + j] - K[i] * CX[j];
+    } else {
+        const TE rg = make_rcp(rls_gamma.v);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                cv[i * 3 + j] = div_by(cv[i * 3 + j] - K[i] * CX[j], rls_gamma, rg);   // objects.py:529-530
+    }
     eps_norm = sqrt_rn(fma(eps[1], eps[1], eps[0] * eps[0]));    // objects.py:539
 }
 

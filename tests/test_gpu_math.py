@@ -1,0 +1,68 @@
+"""Arithmetic primitives of the kernels vs their CPU statements (through the C-ABI test hook)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _probe(op, a, b=None):
+    from rl4afcs_b200 import _lib
+
+    L = _lib.load()
+    ta = torch.as_tensor(a).cuda()
+    tb = torch.as_tensor(b).cuda() if b is not None else None
+    out = torch.empty_like(ta)
+    _lib.check(L.rl4_test_math(op, ta.data_ptr(), tb.data_ptr() if tb is not None else None, out.data_ptr(),
+                               ta.numel(), None), "rl4_test_math")
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _tanh_inputs(dtype, rng):
+    parts = [rng.uniform(-20, 20, 200000), rng.uniform(-1, 1, 200000), rng.uniform(-1e-2, 1e-2, 200000),
+             10.0 ** rng.uniform(-300 if dtype == np.float64 else -37, -2, 100000),
+             np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 19.0624, 19.0625, 19.07, 9.124, 9.125, 9.2, 1e300, -1e300,
+                       0.17328679, 0.1732868, 0.5198603, 5e-324, 1e-310, -1e-310])]
+    return np.concatenate(parts).astype(dtype)
+
+
+@pytest.mark.parametrize("dtype,op", [(np.float64, 0), (np.float32, 1)])
+def test_device_tanh_t13_equals_oracle_t13_bitwise(oracle, dtype, op):
+    x = _tanh_inputs(dtype, np.random.default_rng(0))
+    if dtype == np.float32:
+        x = x[np.isfinite(x) | np.isnan(x) | np.isinf(x)]
+    got = _probe(op, x)
+    want = oracle.tanh_t13(x)
+    same = (got == want) | (np.isnan(got) & np.isnan(want))
+    assert same.all(), (x[~same][:5], got[~same][:5], want[~same][:5])
+
+
+def test_device_tanh_t13_accuracy_vs_libm():
+    x = _tanh_inputs(np.float64, np.random.default_rng(1))
+    x = x[np.isfinite(x)]
+    got = _probe(0, x)
+    want = np.tanh(x)
+    ulp = np.abs(got - want) / np.maximum(np.spacing(np.abs(want)), 5e-324)
+    assert ulp.max() <= 6.0, ulp.max()      # t13 <= 2.1 ulp of exact, np.tanh <= 3 ulp of libm
+
+
+def test_shared_reciprocal_division_equals_ieee():
+    rng = np.random.default_rng(2)
+    n = 1 << 22
+    a = rng.standard_normal(n) * 10.0 ** rng.uniform(-12, 12, n)
+    b = rng.standard_normal(n) * 10.0 ** rng.uniform(-12, 12, n)
+    # edge ranges: zeros, denormals, huge, inf, nan, exact quotients
+    edge = np.array([0.0, -0.0, 5e-324, 1e-310, 2.0 ** -969, 2.0 ** -970, 1e-300, 1.0, 3.0, 1e300, 1.7e308, np.inf, -np.inf, np.nan])
+    ea, eb = np.meshgrid(edge, edge)
+    a = np.concatenate([a, ea.ravel(), rng.uniform(0, 2 ** 56, 100000)])
+    b = np.concatenate([b, eb.ravel(), rng.uniform(2, 2 ** 56, 100000)])
+    got = _probe(2, a, b)
+    ieee = _probe(3, a, b)
+    with np.errstate(all="ignore"):
+        host = a / b
+    for want in (ieee, host):
+        same = (got == want) | (np.isnan(got) & np.isnan(want))
+        assert same.all(), (a[~same][:5], b[~same][:5], got[~same][:5], want[~same][:5])
