@@ -1,0 +1,114 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz from the reference ITSELF.
+
+Run in the build container (where /root/reference is mounted):
+
+    python -m oracle.make_golden
+
+The reference has no tests and no golden vectors of its own, and its
+TensorFlow agent cannot run here; what CAN run unmodified is `Ce500ShortPeriod`
+(envs/linear/env.py:7-264) and `RLS` (objects.py:439-549).  The fixtures below are the outputs
+of those verbatim classes (numpy 2.3.5, scipy-openblas 0.3.30, x86-64 AVX-512 host):
+
+  sp_env_<fault>.npz     verbatim env driven open-loop by a seeded float32 action sequence
+  sp_rls_<tag>.npz       verbatim RLS driven by seeded regressors (incl. a mid-run _reset())
+  sp_loop_<case>.npz     full IDHP loop: the reference-shaped numpy loop (oracle/sp_numpy.py,
+                         TensorFlow ops restated in float32 numpy) running on the VERBATIM env
+                         and the VERBATIM RLS objects, tanh = t13 (and one case with np.tanh)
+
+The GPU box has no /root/reference: tests there read these files only.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader, sp_c, sp_numpy  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def env_fixture(fault, seed, steps=1500, x0=(0.02, -0.03), kappa=1140):
+    Env = ref_loader.load_reference_linear_env()
+    base, amp = sp_c.default_reference()
+    ref = amp * base
+    env = Env({"state_dim": 2, "action_dim": 1, "x0": np.array(x0, dtype=float).reshape(2, 1), "dt": 0.02,
+               "t_end": 60, "fault_time": 20, "fault_scenario": fault,
+               "reference": {"tracked_state": ["alpha"], "signal": [ref]}})
+    env.kappa = kappa
+    env.reset(seed=0)
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(-1, 1, size=steps).astype(np.float32)
+    xs, cs, es, gs = [], [], [], []
+    for k in range(steps):
+        obs, c, done, _, info = env.step(np.float32(20) * a[k].reshape(1, 1))
+        xs.append(obs.ravel().copy()); cs.append(float(c)); es.append(float(info["e"]))
+        gs.append(info["reward_grad"].ravel().copy())
+    return dict(fault=str(fault), x0=np.array(x0), kappa=kappa, action=a, x=np.array(xs), reward=np.array(cs),
+                e=np.array(es), reward_grad=np.array(gs), A=env.A.copy(), B=env.B.copy())
+
+
+def rls_fixture(gamma, seed, steps=400, reset_at=250):
+    RLS = ref_loader.load_reference_rls()
+    m = RLS({"state_dim": 2, "action_dim": 1, "rls_gamma": gamma, "rls_cov": 10 ** 6})
+    rng = np.random.default_rng(seed)
+    dx0 = rng.normal(size=(steps, 2, 1)) * 1e-3
+    da0 = (rng.normal(size=(steps, 1, 1)) * 1e-2).astype(np.float32)
+    Atrue = np.array([[0.985, 0.0195], [-0.0294, 0.9687]]); Btrue = np.array([[-0.0006], [-0.0469]])
+    dx1 = Atrue @ dx0 + Btrue @ da0.astype(np.float64) + rng.normal(size=(steps, 2, 1)) * 1e-7
+    th, cv, ep, en = [], [], [], []
+    for k in range(steps):
+        if k == reset_at:
+            m._reset()
+        m.update(dx0[k], da0[k], dx1[k])
+        th.append(m.params.ravel().copy()); cv.append(m.Cov.ravel().copy())
+        ep.append(m.epsilon.ravel().copy()); en.append(float(m.eps_norm))
+    return dict(gamma=gamma, reset_at=reset_at, dx0=dx0[:, :, 0], da0=da0[:, 0, 0], dx1=dx1[:, :, 0],
+                theta=np.array(th), cov=np.array(cv), eps=np.array(ep), eps_norm=np.array(en))
+
+
+def loop_fixture(name, *, x0, seed, fault=None, elig=(None, None), ms=2, steps=1100, tanh="t13"):
+    Env = ref_loader.load_reference_linear_env()
+    RLS = ref_loader.load_reference_rls()
+    base, amp = sp_c.default_reference()
+    ic = sp_c.default_idhp_config()
+    ic["multistep"] = ms
+    ic["actor_config"]["elig"], ic["critic_config"]["elig"] = elig
+    env = Env({"state_dim": 2, "action_dim": 1, "x0": np.array(x0, dtype=float).reshape(2, 1), "dt": 0.02,
+               "t_end": 60, "fault_time": 20, "fault_scenario": fault,
+               "reference": {"tracked_state": ["alpha"], "signal": [amp * base]}})
+    w = sp_c.init_weights(1, seed)
+    fn = (lambda a: sp_c.tanh_t13(np.asarray(a))) if tanh == "t13" else np.tanh
+    loop = sp_numpy.IDHPspLoop(env, ic, {k: v[0] for k, v in w.items()}, tanh_fn=fn, rls=RLS(ic["rls_config"]))
+    lg = loop.train(steps)
+    out = dict(x0=np.array(x0, dtype=float), seed=seed, fault=str(fault), elig_a=str(elig[0]), elig_c=str(elig[1]),
+               multistep=ms, steps=steps, tanh=tanh, **{f"w_{k}": v[0] for k, v in w.items()})
+    for k in ("x", "a", "c", "ref", "a_w1", "a_w2", "c_w1", "c_w2", "params", "cov", "eps_norm"):
+        out[k] = lg[k]
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for i, f in enumerate([None, "invert_elevator", "damp_elevator", "shift_cg"]):
+        np.savez_compressed(os.path.join(OUT, f"sp_env_{f or 'none'}.npz"), **env_fixture(f, 100 + i))
+    np.savez_compressed(os.path.join(OUT, "sp_rls_g1.npz"), **rls_fixture(1, 7))
+    np.savez_compressed(os.path.join(OUT, "sp_rls_g0995.npz"), **rls_fixture(0.995, 8))
+    cases = {
+        "default_x0zero": dict(x0=(0, 0), seed=4),                                  # idhp_sp.py as shipped
+        "default_x0rand": dict(x0=(0.02, -0.03), seed=5),                           # exercises Q3
+        "shiftcg_acc_1step": dict(x0=(-0.01, 0.03), seed=7, fault="shift_cg", elig=("accumulating", "accumulating"), ms=0),
+        "invert_replacing": dict(x0=(0.015, 0.01), seed=8, fault="invert_elevator", elig=("replacing", "replacing")),
+        "default_nptanh": dict(x0=(0.02, -0.03), seed=5, tanh="np"),
+    }
+    for name, kw in cases.items():
+        np.savez_compressed(os.path.join(OUT, f"sp_loop_{name}.npz"), **loop_fixture(name, **kw))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -106,6 +106,10 @@ def lib() -> ctypes.CDLL:
                              ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]
     L.orc_sp_init.restype = ctypes.c_int
     L.orc_sp_init.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_int64]
+    L.orc_sp_env_step.restype = ctypes.c_int
+    L.orc_sp_env_step.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 5 + [ctypes.c_int64]
+    L.orc_sp_rls_update.restype = ctypes.c_int
+    L.orc_sp_rls_update.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 7 + [ctypes.c_int64]
     L.orc_tanh_t13_f64_array.restype = None
     L.orc_tanh_t13_f64_array.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
     L.orc_tanh_t13_f32_array.restype = None
@@ -277,6 +281,35 @@ def run(policy: str, cfg: np.ndarray, ref_base: np.ndarray, states: np.ndarray, 
     if rc != 0:
         raise RuntimeError(f"orc_sp_run failed: {rc}")
     return log
+
+
+def env_step(policy: str, cfg: np.ndarray, ref_base, stepp: int, x: np.ndarray, action_deg: np.ndarray):
+    """Step-API env step for n agents: x (n,2) is advanced in place; returns reward, e, reward_grad[0]."""
+    n = x.shape[0]
+    assert x.dtype == np.float64 and x.flags.c_contiguous
+    ref_base = np.ascontiguousarray(ref_base, dtype=np.float64)
+    act = np.ascontiguousarray(action_deg, dtype=np.float64).reshape(n)
+    r, e, g = np.empty(n), np.empty(n), np.empty(n)
+    rc = lib().orc_sp_env_step(POLICY[policy], _ptr(cfg), 0 if cfg.shape[0] == 1 else 1, _ptr(ref_base), stepp,
+                               _ptr(x), _ptr(act), _ptr(r), _ptr(e), _ptr(g), n)
+    if rc != 0:
+        raise RuntimeError(f"orc_sp_env_step failed: {rc}")
+    return r, e, g
+
+
+def rls_update(policy: str, cfg: np.ndarray, theta: np.ndarray, cov: np.ndarray, dx0, da0, dx1):
+    """Step-API RLS update: theta (n,6), cov (n,9) in place; returns eps (n,2), eps_norm (n,)."""
+    n = theta.shape[0]
+    assert theta.dtype == np.float64 and cov.dtype == np.float64 and theta.flags.c_contiguous and cov.flags.c_contiguous
+    dx0 = np.ascontiguousarray(dx0, dtype=np.float64).reshape(n, 2)
+    dx1 = np.ascontiguousarray(dx1, dtype=np.float64).reshape(n, 2)
+    da0 = np.ascontiguousarray(da0, dtype=np.float64).reshape(n)
+    eps, en = np.empty((n, 2)), np.empty(n)
+    rc = lib().orc_sp_rls_update(POLICY[policy], _ptr(cfg), 0 if cfg.shape[0] == 1 else 1, _ptr(theta), _ptr(cov),
+                                 _ptr(dx0), _ptr(da0), _ptr(dx1), _ptr(eps), _ptr(en), n)
+    if rc != 0:
+        raise RuntimeError(f"orc_sp_rls_update failed: {rc}")
+    return eps, en
 
 
 def tanh_t13(x: np.ndarray) -> np.ndarray:

@@ -121,6 +121,30 @@ int orc_sp_init(int policy, const orc_sp_cfg* cfgs, int cfg_stride,
     return 0;
 }
 
+int orc_sp_env_step(int policy, const orc_sp_cfg* cfgs, int cfg_stride, const double* ref_base, int stepp,
+                    double* x, const double* action_deg, double* reward, double* e, double* rg0, int64_t n)
+{
+    if (!cfgs || !ref_base || !x || !action_deg || !reward || !e || !rg0 || n < 0 || stepp < 0) return -1;
+    switch (policy) {
+    case ORC_POLICY_FP64:  env_step_batch_fp64(cfgs, cfg_stride, ref_base, stepp, x, action_deg, reward, e, rg0, n); return 0;
+    case ORC_POLICY_FP32:  env_step_batch_fp32(cfgs, cfg_stride, ref_base, stepp, x, action_deg, reward, e, rg0, n); return 0;
+    case ORC_POLICY_MIXED: env_step_batch_mixed(cfgs, cfg_stride, ref_base, stepp, x, action_deg, reward, e, rg0, n); return 0;
+    default: return -1;
+    }
+}
+
+int orc_sp_rls_update(int policy, const orc_sp_cfg* cfgs, int cfg_stride, double* theta, double* cov, const double* dx0,
+                      const double* da0, const double* dx1, double* eps, double* eps_norm, int64_t n)
+{
+    if (!cfgs || !theta || !cov || !dx0 || !da0 || !dx1 || !eps || !eps_norm || n < 0) return -1;
+    switch (policy) {
+    case ORC_POLICY_FP64:  rls_update_batch_fp64(cfgs, cfg_stride, theta, cov, dx0, da0, dx1, eps, eps_norm, n); return 0;
+    case ORC_POLICY_FP32:  rls_update_batch_fp32(cfgs, cfg_stride, theta, cov, dx0, da0, dx1, eps, eps_norm, n); return 0;
+    case ORC_POLICY_MIXED: rls_update_batch_mixed(cfgs, cfg_stride, theta, cov, dx0, da0, dx1, eps, eps_norm, n); return 0;
+    default: return -1;
+    }
+}
+
 void orc_tanh_t13_f64_array(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = orc_t13_f64(x[i]); }
 void orc_tanh_t13_f32_array(const float* x, float* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = orc_t13_f32(x[i]); }
 double orc_tanh_t13_f64(double x) { return orc_t13_f64(x); }

@@ -124,6 +124,13 @@ int orc_sp_init(int policy, const orc_sp_cfg* cfgs, int cfg_stride,
                 const double* W1c, const double* W2c /* [n][4],[n][4],[n][4],[n][8] */,
                 orc_sp_state* states, int64_t n_agents);
 
+/* Step-API forms of envs/linear/env.py:156-220 and objects.py:492-543 for n agents (AoS:
+ * x [n][2], theta [n][6], cov [n][9], dx0/dx1/eps [n][2]); action_deg is the caller's 20*a. */
+int orc_sp_env_step(int policy, const orc_sp_cfg* cfgs, int cfg_stride, const double* ref_base, int stepp,
+                    double* x, const double* action_deg, double* reward, double* e, double* rg0, int64_t n);
+int orc_sp_rls_update(int policy, const orc_sp_cfg* cfgs, int cfg_stride, double* theta, double* cov, const double* dx0,
+                      const double* da0, const double* dx1, double* eps, double* eps_norm, int64_t n);
+
 /* the oracle's tanh variants, exposed for accuracy tests */
 void orc_tanh_t13_f64_array(const double* x, double* y, int64_t n);
 void orc_tanh_t13_f32_array(const float* x, float* y, int64_t n);

@@ -1,0 +1,65 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/rl4afcs_b200.h declares;
+the product refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "rl4afcs_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rl4_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from rl4afcs_b200 import _lib, build
+
+    build.build()
+    L = _lib.load()
+    names = _declared()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(_lib.EXPORTS) == names
+    assert L.rl4_abi_version() == 1
+
+
+def test_struct_layouts_match_header_constants():
+    from rl4afcs_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "rl4afcs_b200.h")).read()
+    for table, prefix in ((_lib.SPE, "RL4_SPE_"), (_lib.SPN, "RL4_SPN_"), (_lib.SPI, "RL4_SPI_"), (_lib.LF, "RL4_LF_"), (_lib.LB, "RL4_LB_")):
+        for k, v in table.items():
+            m = re.search(prefix + k + r"\s*=\s*(\d+)", hdr)
+            assert m and int(m.group(1)) == v, (prefix, k)
+    for table, enum in ((_lib.HP, "rl4_sp_hp"), (_lib.HPI, "rl4_sp_hpi")):
+        body = re.search(r"enum " + enum + r"\s*\{(.*?)\}", hdr, flags=re.S).group(1)
+        names = [t.strip().split("=")[0].strip() for t in body.split(",") if t.strip()]
+        for i, nm in enumerate(names):
+            key = nm.replace("RL4_HPI_", "").replace("RL4_HP_", "")
+            assert table[key] == i, nm
+    assert ctypes.sizeof(_lib.SpParams) == 8 * (16 + 8 + 1 + 14) + 4 * (7 + 2) + 4 + 8 * (14 + 7)
+
+
+def test_no_cpu_fallback():
+    torch = pytest.importorskip("torch")
+    from rl4afcs_b200 import _lib, sp_engine
+
+    with pytest.raises(_lib.Rl4Error):
+        sp_engine.SpEngine(4, policy="fp64", device="cpu")
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            sp_engine.SpEngine(4, policy="fp64", device="cuda")
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "rl4afcs_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("# oracle", ""), os.path.join(dp, f)

@@ -1,0 +1,56 @@
+"""Live re-check of the oracle against the verbatim reference code (build container only:
+/root/reference is not present on the GPU box, where the committed golden vectors stand in)."""
+import numpy as np
+import pytest
+
+from oracle import ref_loader
+
+pytestmark = pytest.mark.skipif(not ref_loader.reference_available(), reason="/root/reference not mounted")
+
+
+def test_numpy_matmul_order_assumptions():
+    """The term orders the oracle hard-codes are those numpy executes on this host."""
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6"); libm.fma.restype = ctypes.c_double; libm.fma.argtypes = [ctypes.c_double] * 3
+    f = libm.fma
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        A = rng.normal(size=(2, 2)); x = rng.normal(size=(2, 1))
+        y = A @ x
+        assert y[0, 0] == f(A[0, 0], x[0, 0], A[0, 1] * x[1, 0])                       # (2,2)@(2,1): terms 1,0
+        C = rng.normal(size=(3, 3)); X = rng.normal(size=(3, 1))
+        z = C @ X
+        assert z[1, 0] == f(C[1, 2], X[2, 0], f(C[1, 0], X[0, 0], C[1, 1] * X[1, 0]))   # (3,3)@(3,1): 1,0,2
+        P = rng.normal(size=(3, 2))
+        w = P.T @ X
+        assert w[0, 0] == f(P[2, 0], X[2, 0], f(P[1, 0], X[1, 0], P[0, 0] * X[0, 0]))   # transposed lhs: in order
+        d = X.T @ z
+        assert d[0, 0] == f(X[2, 0], z[2, 0], f(X[1, 0], z[1, 0], X[0, 0] * z[0, 0]))
+        assert np.linalg.norm(x) == np.sqrt(f(x[1, 0], x[1, 0], x[0, 0] * x[0, 0]))
+
+
+@pytest.mark.parametrize("seed,fault,elig,ms", [
+    (21, None, (None, None), 2), (22, "damp_elevator", ("accumulating", None), 2), (23, "shift_cg", (None, "replacing"), 0)])
+def test_c_oracle_equals_numpy_loop_on_verbatim_objects(oracle, seed, fault, elig, ms):
+    from oracle import sp_numpy
+
+    Env = ref_loader.load_reference_linear_env(); RLS = ref_loader.load_reference_rls()
+    base, amp = oracle.default_reference()
+    ic = oracle.default_idhp_config(); ic["multistep"] = ms
+    ic["actor_config"]["elig"], ic["critic_config"]["elig"] = elig
+    rng = np.random.default_rng(seed)
+    x0 = np.deg2rad(rng.uniform(-2, 2, size=2))
+    steps = 1300
+    env = Env({"state_dim": 2, "action_dim": 1, "x0": x0.reshape(2, 1).copy(), "dt": 0.02, "t_end": 60, "fault_time": 20,
+               "fault_scenario": fault, "reference": {"tracked_state": ["alpha"], "signal": [amp * base]}})
+    w = oracle.init_weights(1, seed)
+    loop = sp_numpy.IDHPspLoop(env, ic, {k: v[0] for k, v in w.items()},
+                               tanh_fn=lambda a: oracle.tanh_t13(np.asarray(a)), rls=RLS(ic["rls_config"]))
+    lg = loop.train(steps)
+    cfg = oracle.make_cfg(ic, fault_scenario=fault)
+    st = oracle.init_states("mixed", cfg, x0.reshape(1, 2), w)
+    cl = oracle.run("mixed", cfg, base, st, 0, steps, tanh="t13", n_log=1)[0]
+    for k in ("x", "a", "ref", "a_w1", "a_w2", "c_w1", "c_w2", "a_e", "c_e"):
+        assert np.array_equal(lg[k], cl[k], equal_nan=True), k
+    for k in ("params", "cov", "eps_norm"):
+        assert np.array_equal(lg[k][2:], cl[k][2:], equal_nan=True), k
