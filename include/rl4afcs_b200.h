@@ -189,6 +189,12 @@ int rl4_sp_actor_forward(int policy, const void* z, const void* w1, const void* 
                          void* out_dadz, double gamma_lambda, int32_t elig, int64_t stride, int64_t n_agents,
                          void* stream);
 
+/* Critic.get_weight_update (objects.py:195-205): td [2][stride] (TN) times the critic trace E
+ * [12][stride] (TE, cast to TN as TF does); out [12][stride] (TN) = W1_update (1,4) then W2_update
+ * (4,2) row-major.  (Actor.get_weight_update is a plain product loss*E and needs no kernel.) */
+int rl4_sp_critic_weight_update(int policy, const void* td, const void* E, void* out, int64_t stride,
+                                int64_t n_agents, void* stream);
+
 /* ---- host-buffer episode (what a reference user calls: IDHPsp(...).train() for a batch) ----
  * Copies x0 / weights from host memory, runs rl4_sp_init + rl4_sp_run for n_steps on the GPU
  * and copies the final state planes and statistics back.  Host buffers may be pageable or pinned. */

@@ -65,7 +65,7 @@ class SpHostIO(ctypes.Structure):
 EXPORTS = [
     "rl4_abi_version", "rl4_last_error", "rl4_device_check",
     "rl4_sp_init", "rl4_sp_run", "rl4_sp_env_step", "rl4_sp_rls_update",
-    "rl4_sp_critic_forward", "rl4_sp_actor_forward",
+    "rl4_sp_critic_forward", "rl4_sp_actor_forward", "rl4_sp_critic_weight_update",
     "rl4_ctx_create", "rl4_ctx_destroy", "rl4_sp_episode_host",
     "rl4_peak_fma", "rl4_launch_count", "rl4_test_math",
 ]
@@ -96,6 +96,7 @@ def load() -> ctypes.CDLL:
     L.rl4_sp_rls_update.argtypes = [ctypes.c_int, ctypes.POINTER(SpParams), vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]
     L.rl4_sp_critic_forward.argtypes = [ctypes.c_int, vp, vp, vp, vp, vp, dbl, i32, i64, i64, vp]
     L.rl4_sp_actor_forward.argtypes = [ctypes.c_int, vp, vp, vp, vp, vp, vp, dbl, i32, i64, i64, vp]
+    L.rl4_sp_critic_weight_update.argtypes = [ctypes.c_int, vp, vp, vp, i64, i64, vp]
     L.rl4_ctx_create.argtypes = [ctypes.c_int, ctypes.c_int, i64, i32, ctypes.POINTER(vp)]
     L.rl4_ctx_destroy.argtypes = [vp]
     L.rl4_sp_episode_host.argtypes = [vp, ctypes.POINTER(SpParams), ctypes.POINTER(SpHostIO), i64, i32, i32]

@@ -307,6 +307,26 @@ sp_actor_forward_kernel(const TN* __restrict__ z, const TN* __restrict__ w1, con
     if (out_dadz) out_dadz[i] = dadz.v;
 }
 
+// Critic.get_weight_update (objects.py:195-205): td @ E in the tensor dtype; out = [dW1 (4), dW2 (4,2) row-major]
+template <typename TN, typename TE>
+__global__ void __launch_bounds__(256)
+sp_critic_weight_update_kernel(const TN* __restrict__ td, const TE* __restrict__ Eplane, TN* __restrict__ out,
+                               int64_t stride, int64_t n_agents)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_agents) return;
+    using N = Rn<TN>;
+    const N td0 = N(td[i]), td1 = N(td[stride + i]), zero = N(TN(0));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const N eh = cvt<TN>(Rn<TE>(Eplane[j * stride + i]));
+        const N e0 = cvt<TN>(Rn<TE>(Eplane[(4 + j) * stride + i])), e1 = cvt<TN>(Rn<TE>(Eplane[(8 + j) * stride + i]));
+        out[j * stride + i] = fma(td1, e1, td0 * e0).v;                       // W1_update[0][j] = crit_grad[8+j]
+        out[(4 + j * 2 + 0) * stride + i] = fma(td1, zero, td0 * eh).v;       // W2_update[j][0] = crit_grad[j]
+        out[(4 + j * 2 + 1) * stride + i] = fma(td1, eh, td0 * zero).v;       // W2_update[j][1] = crit_grad[4+j]
+    }
+}
+
 // ---- host-side dispatch ------------------------------------------------------------------
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
@@ -456,6 +476,22 @@ int rl4_sp_actor_forward(int policy, const void* z, const void* w1, const void* 
     default: set_error("rl4_sp_actor_forward: unknown policy %d", policy); return -1;
     }
     return check_launch("sp_actor_forward_kernel");
+}
+
+int rl4_sp_critic_weight_update(int policy, const void* td, const void* E, void* out, int64_t stride, int64_t n, void* stream)
+{
+    RL4_REQUIRE(td && E && out, "NULL argument");
+    RL4_REQUIRE(n >= 0 && stride >= n, "bad size");
+    if (n == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = grid_for(n, 256);
+    switch (policy) {
+    case RL4_FP64:  sp_critic_weight_update_kernel<double, double><<<grid, 256, 0, s>>>((const double*)td, (const double*)E, (double*)out, stride, n); break;
+    case RL4_FP32:  sp_critic_weight_update_kernel<float, float><<<grid, 256, 0, s>>>((const float*)td, (const float*)E, (float*)out, stride, n); break;
+    case RL4_MIXED: sp_critic_weight_update_kernel<float, double><<<grid, 256, 0, s>>>((const float*)td, (const double*)E, (float*)out, stride, n); break;
+    default: set_error("rl4_sp_critic_weight_update: unknown policy %d", policy); return -1;
+    }
+    return check_launch("sp_critic_weight_update_kernel");
 }
 
 // ---- host-buffer episode -----------------------------------------------------------------

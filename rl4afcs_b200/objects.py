@@ -1,0 +1,355 @@
+"""Batched, GPU-resident agent objects -- drop-in for objects.py of wingos80/RL4AFCS on the
+short-period path: ``RLS`` (objects.py:439-549), ``Actor`` / ``Critic`` (objects.py:142-281) and
+``IDHPsp`` (objects.py:551-1004).  Same class, method and attribute names; every array gains a
+leading batch axis.  All arithmetic runs in the CUDA kernels behind include/rl4afcs_b200.h; the
+objects are views over the SoA state planes of ``sp_engine.SpEngine``.
+
+``IDHPsp.train()`` is the hot path: ONE fused persistent kernel launch runs the whole episode
+(env step + critic / target / actor + RLS + adaptation + statistics) for every agent.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib, sp_engine
+from ._lib import LB, LF, SPE, SPN
+
+
+# ------------------------------------------------------------------------------------------
+class RLS:
+    """Exponentially weighted recursive least squares on increments (objects.py:439-549)."""
+
+    def __init__(self, config, *, batch: int = 1, device="cuda", dtype: str = "mixed", _engine=None) -> None:
+        self.state_dim = config["state_dim"]
+        self.action_dim = config["action_dim"]
+        assert (self.state_dim, self.action_dim) == (2, 1), "short-period RLS is 2 states + 1 action"
+        self.gamma = config["rls_gamma"]
+        self.init_cov = config["rls_cov"]
+        self._eng = _engine if _engine is not None else sp_engine.SpEngine(batch, policy=dtype, device=device)
+        self.batch = self._eng.n
+        self._eng.set_hp("RLS_GAMMA", self.gamma)
+        self._eng.set_hp("RLS_COV0", self.init_cov)
+        if _engine is None:
+            self._reset()
+        self.eps_norm_hist = [0, 0]
+        self.eps_hist = [np.zeros(self.state_dim)]
+        self.covs = []
+
+    def _reset(self):
+        """Theta <- 0, Cov <- init_cov * I (objects.py:477-482)."""
+        e = self._eng
+        e.env_field("THETA", 6).zero_()
+        cov = e.env_field("COV", 9)
+        cov.zero_()
+        c0 = torch.as_tensor(np.asarray(self.init_cov, dtype=np.float64)).to(e.device).to(e.te)
+        for d in (0, 4, 8):
+            cov[d] = c0
+
+    @property
+    def params(self) -> torch.Tensor:
+        """(B, 3, 2): [F.T; G.T] (objects.py:459-461)."""
+        return self._eng.env_field("THETA", 6).t().reshape(self.batch, 3, 2)
+
+    @property
+    def Cov(self) -> torch.Tensor:
+        return self._eng.env_field("COV", 9).t().reshape(self.batch, 3, 3)
+
+    @property
+    def F(self) -> torch.Tensor:
+        return self.params[:, : self.state_dim, :].transpose(1, 2).clone()
+
+    @property
+    def G(self) -> torch.Tensor:
+        return self.params[:, self.state_dim:, :].transpose(1, 2).clone()
+
+    @property
+    def epsilon(self) -> torch.Tensor:
+        return self._eng.env_field("EPS", 2).t().unsqueeze(-1)
+
+    @property
+    def eps_norm(self) -> torch.Tensor:
+        return self._eng.env_field("EPS_NORM")[0]
+
+    def update(self, dx_t, da_t, dx_t1):
+        """dx_t (B,2,1), da_t (B,1,1), dx_t1 (B,2,1) -> updates params / Cov in place (objects.py:492-543)."""
+        e = self._eng
+        te = e.te
+
+        def plane(v, w):
+            return torch.as_tensor(v, device=e.device).to(te).reshape(self.batch, w).t().contiguous()
+
+        dx0, da0, dx1 = plane(dx_t, 2), plane(da_t, 1), plane(dx_t1, 2)
+        e.set_hp("RLS_GAMMA", self.gamma)
+        with torch.cuda.device(e.device):
+            rc = e.lib.rl4_sp_rls_update(e.policy_id, ctypes.byref(e.params), e.env_field("THETA", 6).data_ptr(),
+                                         e.env_field("COV", 9).data_ptr(), dx0.data_ptr(), da0.data_ptr(), dx1.data_ptr(),
+                                         e.env_field("EPS", 2).data_ptr(), e.env_field("EPS_NORM").data_ptr(),
+                                         e.stride, self.batch, e._stream())
+            _lib.check(rc, "rl4_sp_rls_update")
+        self.eps_hist.append(self.epsilon.clone())
+        self.eps_norm_hist.append(self.eps_norm.clone())
+        self.covs.append(self.Cov.clone())
+
+
+# ------------------------------------------------------------------------------------------
+class _Net:
+    """Common part of Actor / Critic: bias-free in-h-out MLP whose weights live in the net plane
+    (objects.py:39-140).  ``trainable_weights`` = [W1 (B,in,h), W2 (B,h,out)]."""
+
+    _w1, _w2, _n_out = None, None, None
+
+    def __init__(self, in_dim, layers, identity_init=False, std_init=0.01, seed=1, eligibility=None, *,
+                 batch: int = 1, device="cuda", dtype: str = "mixed", _engine=None, _fields=None):
+        sizes = list(layers.keys())
+        acts = list(layers.values())
+        assert in_dim == 1 and sizes[0] == 4 and acts[0] == "tanh", "short-period nets are 1-4-k (objects.py:160,235)"
+        assert sizes[1] == self._n_out
+        self.input_dim = in_dim
+        self.layers_dict = layers
+        self.n_layers = len(layers)
+        self.eligibility = eligibility
+        self.gamma_lambda = 0.0
+        self._eng = _engine if _engine is not None else sp_engine.SpEngine(batch, policy=dtype, device=device)
+        self.batch = self._eng.n
+        if _fields is not None:
+            self._w1, self._w2 = _fields
+        if _engine is None and not identity_init:
+            w = sp_engine.truncated_normal_weights(self.batch, seed, std_init, self._eng.device)
+            key1, key2 = ("W1a", "W2a") if self._n_out == 1 else ("W1c", "W2c")
+            self.set_weights([w[key1].reshape(self.batch, 1, 4), w[key2].reshape(self.batch, 4, self._n_out)])
+        self.xi = [None, None]
+        self.ai = [None, None]
+
+    @property
+    def trainable_weights(self):
+        e = self._eng
+        W1 = e.net_field(self._w1, 4).t().reshape(self.batch, 1, 4)
+        W2 = e.net_field(self._w2, 4 * self._n_out).t().reshape(self.batch, 4, self._n_out)
+        return [W1, W2]
+
+    def set_weights(self, weights):
+        W1, W2 = self.trainable_weights
+        W1.copy_(torch.as_tensor(weights[0], device=W1.device).to(W1.dtype).reshape(W1.shape))
+        W2.copy_(torch.as_tensor(weights[1], device=W2.device).to(W2.dtype).reshape(W2.shape))
+
+    def get_weights(self):
+        return [w.clone() for w in self.trainable_weights]
+
+    def soft_update(self, source_weights, tau):
+        """target <- (1 - tau) * target + tau * source, three separately rounded float ops per weight
+        (objects.py:207-215)."""
+        for tgt, src in zip(self.trainable_weights, source_weights):
+            src = torch.as_tensor(src, device=tgt.device).to(tgt.dtype).reshape(tgt.shape)
+            omt = torch.tensor(1.0 - tau, dtype=torch.float64).to(tgt.dtype)
+            tt = torch.tensor(float(tau), dtype=torch.float64).to(tgt.dtype)
+            tgt.copy_(tgt.mul(omt).add_(src.mul(tt)))
+
+
+class Critic(_Net):
+    """1-4-2 critic estimating the value-function gradient lambda (objects.py:142-215)."""
+    _w1, _w2, _n_out = "W1C", "W2C", 2
+
+    @property
+    def E(self) -> torch.Tensor:
+        """(B, 2, 12) Jacobian trace in the reference's layout (objects.py:160-166)."""
+        e = self._eng
+        out = torch.zeros((self.batch, 2, 12), dtype=e.te, device=e.device)
+        h = e.env_field("EC_H", 4).t()
+        out[:, 0, 0:4] = h
+        out[:, 1, 4:8] = h
+        out[:, 0, 8:12] = e.env_field("EC_W1R0", 4).t()
+        out[:, 1, 8:12] = e.env_field("EC_W1R1", 4).t()
+        return out
+
+    def __call__(self, s):
+        e = self._eng
+        z = torch.as_tensor(s, device=e.device).to(e.tn).reshape(self.batch).contiguous()
+        out = torch.empty((2, e.stride), dtype=e.tn, device=e.device)
+        with torch.cuda.device(e.device):
+            rc = e.lib.rl4_sp_critic_forward(e.policy_id, z.data_ptr(), e.net_field(self._w1, 4).data_ptr(),
+                                             e.net_field(self._w2, 8).data_ptr(), e.env_field("EC_H", 12).data_ptr(),
+                                             out.data_ptr(), float(self.gamma_lambda), _lib.ELIG[self.eligibility],
+                                             e.stride, self.batch, e._stream())
+            _lib.check(rc, "rl4_sp_critic_forward")
+        return out.t().reshape(self.batch, 1, 2)
+
+    call = __call__
+
+    def get_weight_update(self, td_error):
+        """td_error (B,1,2) -> [W1_update (B,1,4), W2_update (B,4,2)] (objects.py:195-205)."""
+        e = self._eng
+        td = torch.as_tensor(td_error, device=e.device).to(e.tn).reshape(self.batch, 2).t().contiguous()
+        out = torch.empty((12, e.stride), dtype=e.tn, device=e.device)
+        with torch.cuda.device(e.device):
+            rc = e.lib.rl4_sp_critic_weight_update(e.policy_id, td.data_ptr(), e.env_field("EC_H", 12).data_ptr(),
+                                                   out.data_ptr(), e.stride, self.batch, e._stream())
+            _lib.check(rc, "rl4_sp_critic_weight_update")
+        return [out[0:4].t().reshape(self.batch, 1, 4), out[4:12].t().reshape(self.batch, 4, 2)]
+
+
+class Actor(_Net):
+    """1-4-1 actor (objects.py:217-281)."""
+    _w1, _w2, _n_out = "W1A", "W2A", 1
+
+    @property
+    def E(self) -> torch.Tensor:
+        return self._eng.env_field("EA", 8).t().reshape(self.batch, 1, 8)
+
+    def __call__(self, s, return_input_gradient: bool = False):
+        e = self._eng
+        z = torch.as_tensor(s, device=e.device).to(e.tn).reshape(self.batch).contiguous()
+        out = torch.empty(self.batch, dtype=e.tn, device=e.device)
+        dadz = torch.empty(self.batch, dtype=e.tn, device=e.device)
+        with torch.cuda.device(e.device):
+            rc = e.lib.rl4_sp_actor_forward(e.policy_id, z.data_ptr(), e.net_field(self._w1, 4).data_ptr(),
+                                            e.net_field(self._w2, 4).data_ptr(), e.env_field("EA", 8).data_ptr(),
+                                            out.data_ptr(), dadz.data_ptr(), float(self.gamma_lambda),
+                                            _lib.ELIG[self.eligibility], e.stride, self.batch, e._stream())
+            _lib.check(rc, "rl4_sp_actor_forward")
+        self.input_gradient = dadz.reshape(self.batch, 1, 1)      # tape.gradient(a, nn_in) (objects.py:876-878)
+        a = out.reshape(self.batch, 1, 1)
+        return (a, self.input_gradient) if return_input_gradient else a
+
+    call = __call__
+
+    def get_weight_update(self, loss):
+        """loss (B,1,1) -> [W1_update (B,1,4), W2_update (B,4,1)] = loss * E (objects.py:261-271)."""
+        e = self._eng
+        g = torch.as_tensor(loss, device=e.device).to(e.tn).reshape(self.batch, 1) * self.E.reshape(self.batch, 8).to(e.tn)
+        return [g[:, 4:8].reshape(self.batch, 1, 4), g[:, 0:4].reshape(self.batch, 4, 1)]
+
+
+# ------------------------------------------------------------------------------------------
+class IDHPsp:
+    """Incremental dual heuristic programming on the short-period model, one agent per batch entry
+    (objects.py:551-1004).
+
+    ``IDHPsp(env, config, verbose=True, seed=1)`` as in the reference; ``env`` is a batched
+    ``rl4afcs_b200.envs.linear.env.Ce500ShortPeriod`` and fixes batch size, device and dtype policy.
+    Every numeric entry of ``config`` may be a per-agent array (hyper-parameter sweeps).  Extra
+    keyword arguments: ``weights`` (dict W1a (B,4), W2a (B,4), W1c (B,4), W2c (B,8); default:
+    TruncatedNormal(sigma) drawn on the device from ``seed``), ``log`` ('full' | 'basic' | None),
+    ``log_agents`` (how many leading agents are logged), ``log_every``.
+    """
+
+    def __init__(self, env, config, verbose=True, seed=1, *, weights=None, log="full", log_agents=None,
+                 log_every: int = 1, ref_amp=None) -> None:
+        self.seed = seed
+        self.gamma = config["gamma"]
+        self.tau = config["tau"]
+        self.ms = config["multistep"]
+        self.warmup_time = config["warmup_time"]
+        self.error_thresh = config["error_thresh"]
+        self.changed = False
+        self.cooldown_1 = 0
+        self.env = env
+        self.env.kappa = config["kappa"]
+        self.config = config
+        self._eng = env._engine
+        self.batch = self._eng.n
+        self.verbose = verbose
+        self.cooldown_timeit = int(np.max(config["cooldown_time"]) / env.dt)
+        sp_engine.apply_idhp_config(self._eng, config, dt=env.dt)
+        if ref_amp is not None:
+            self._eng.set_hp("REF_AMP", ref_amp)
+        self._setup_networks(config, seed, weights)
+        self.log_level = {None: _lib.LOG_NONE, "none": _lib.LOG_NONE, "basic": _lib.LOG_BASIC, "full": _lib.LOG_FULL}[log]
+        self.log_agents = min(self.batch, 64) if log_agents is None else min(int(log_agents), self.batch)
+        self.log_every = int(log_every)
+
+    def _setup_networks(self, config, seed, weights):
+        eng = self._eng
+        kw = dict(_engine=eng)
+        self.hidden_dim = list(config["actor_config"]["layers"].keys())[0]
+        self.actor = Actor(config["in_dims"], config["actor_config"]["layers"], False, config["sigma"], seed,
+                           _first(config["actor_config"]["elig"]), **kw)
+        self.critic = Critic(config["in_dims"], config["critic_config"]["layers"], False, config["sigma"], seed,
+                             _first(config["critic_config"]["elig"]), **kw)
+        self.target_critic = Critic(config["in_dims"], config["critic_config"]["layers"], False, config["sigma"], seed,
+                                    _first(config["critic_config"]["elig"]), _fields=("W1T", "W2T"), **kw)
+        self.lambda_h, self.lambda_l = config["lambda_h"], config["lambda_l"]
+        gl = float(np.ravel(self.gamma)[0] * np.ravel(self.lambda_h)[0])
+        self.actor.gamma_lambda = self.critic.gamma_lambda = self.target_critic.gamma_lambda = gl
+        self.eta_a_h = config["actor_config"]["eta_h"]
+        self.eta_c_h = config["critic_config"]["eta_h"]
+        self.eta_a_l = config["actor_config"]["eta_l"]
+        self.eta_c_l = config["critic_config"]["eta_l"]
+        self.model = RLS(config["rls_config"], _engine=eng)
+        self.n, self.m = self.model.state_dim, self.model.action_dim
+        if weights is None:
+            weights = sp_engine.truncated_normal_weights(self.batch, seed, float(np.ravel(config["sigma"])[0]), eng.device)
+        self._init_weights = weights
+
+    # ---- the hot path ---------------------------------------------------------------------
+    def train(self, n_steps=None):
+        """Runs the whole episode in one fused kernel launch (objects.py:921-1004)."""
+        env, eng = self.env, self._eng
+        steps = int(env.t_end / env.dt) if n_steps is None else int(n_steps)
+        env.reset(seed=self.seed)
+        w = self._init_weights
+        eng.init(torch.as_tensor(env.x0), w["W1a"], w["W2a"], w["W1c"], w["W2c"])
+        self._setup_optimizers()
+        log = eng.run(steps, log_level=self.log_level, log_agents=self.log_agents, log_every=self.log_every)
+        env.stepp = steps
+        env.t = env.dt * steps
+        env.yref_hist = list(env.state_reference[:steps])
+        self._steps = steps
+        self._store_logs(log, steps)
+        return self
+
+    def _setup_optimizers(self):
+        self.eta_a = self.eta_a_h
+        self.eta_c = self.eta_c_h
+
+    def _store_logs(self, log, steps):
+        """Fills the history attributes of IDHPsp._reset_logs/_log (objects.py:617-726); arrays are
+        (logged agents, rows, ...) torch tensors on the device."""
+        if log is None:
+            return
+        lg = log.permute(2, 0, 1)                     # (agents, rows, fields)
+        rows = lg.shape[1]
+        dt = self.env.dt
+        self.t_hist = torch.arange(rows, dtype=torch.float64) * (dt * self.log_every)
+        self.x_hist = lg[:, :, LB["X"]:LB["X"] + 2]
+        self.a_hist = lg[:, :, LB["A"]:LB["A"] + 1]
+        self.s_hist = self.x_hist.to(self._eng.tn).to(torch.float64)
+        self.c_hist = lg[:, :, LB["C"]]
+        self.ref_hist = lg[:, :, LB["REF"]]
+        self.e_hist = lg[:, :, LB["E"]]
+        if self.log_level == _lib.LOG_FULL:
+            self.a_weights_hist1 = lg[:, :, LF["AW1"]:LF["AW1"] + 4]
+            self.a_weights_hist2 = lg[:, :, LF["AW2"]:LF["AW2"] + 4]
+            self.c_weights_hist1 = lg[:, :, LF["CW1"]:LF["CW1"] + 4]
+            self.c_weights_hist2 = lg[:, :, LF["CW2"]:LF["CW2"] + 8]
+            self.a_e_hist = lg[:, :, LF["AE"]:LF["AE"] + 8]
+            ce = torch.zeros(lg.shape[0], rows, 24, dtype=lg.dtype, device=lg.device)
+            ce[:, :, 0:4] = lg[:, :, LF["CE"]:LF["CE"] + 4]
+            ce[:, :, 16:20] = lg[:, :, LF["CE"]:LF["CE"] + 4]
+            ce[:, :, 8:12] = lg[:, :, LF["CE"] + 4:LF["CE"] + 8]
+            ce[:, :, 20:24] = lg[:, :, LF["CE"] + 8:LF["CE"] + 12]
+            self.c_e_hist = ce
+            self.a_all_grad_hist = lg[:, :, LF["AGRAD"]:LF["AGRAD"] + 8]
+            self.c_all_grad_hist = lg[:, :, LF["CGRAD"]:LF["CGRAD"] + 12]
+            self.a_grad_hist = torch.linalg.vector_norm(self.a_all_grad_hist[:, :, 0:4], dim=-1)   # objects.py:706
+            self.c_grad_hist = torch.linalg.vector_norm(self.c_all_grad_hist[:, :, 0:4], dim=-1)   # objects.py:707
+            self.params_hist = lg[:, :, LF["PARAMS"]:LF["PARAMS"] + 6]
+            self.cov_hist = lg[:, :, LF["COV"]:LF["COV"] + 9]
+            self.eps_norm_hist = lg[:, :, LF["EPS_NORM"]]
+            self.eps_hist = lg[:, :, LF["EPS_ABS"]:LF["EPS_ABS"] + 2]
+
+    # ---- episode statistics (functions.py:39-60) ------------------------------------------------
+    def stats(self) -> dict:
+        return self._eng.stats(self._steps)
+
+    @property
+    def diverged(self) -> torch.Tensor:
+        return self._eng.stats(self._steps)["diverged"]
+
+
+def _first(v):
+    if isinstance(v, (list, tuple, np.ndarray)):
+        return v[0]
+    return v

@@ -1,0 +1,169 @@
+"""The reference-facing Python objects (same names as envs/linear/env.py and objects.py of the
+reference, batched) against golden vectors of the VERBATIM reference classes and the oracle."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FAULTS = {"None": None, "invert_elevator": "invert_elevator", "damp_elevator": "damp_elevator", "shift_cg": "shift_cg"}
+ELIG = {"None": None, "accumulating": "accumulating", "replacing": "replacing"}
+
+
+def _ref_signal(oracle):
+    base, amp = oracle.default_reference()
+    return amp * base
+
+
+def _env_config(oracle, x0, fault):
+    return {"state_dim": 2, "action_dim": 1, "x0": x0, "dt": 0.02, "t_end": 60, "fault_time": 20,
+            "fault_scenario": fault, "reference": {"tracked_state": ["alpha"], "signal": [_ref_signal(oracle)]}}
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "sp_env_*.npz"))))
+def test_env_step_equals_verbatim_reference(oracle, path):
+    from rl4afcs_b200.envs.linear.env import Ce500ShortPeriod
+
+    g = np.load(path)
+    B = 5
+    env = Ce500ShortPeriod(_env_config(oracle, g["x0"].reshape(2, 1), FAULTS[str(g["fault"])]), batch=B, dtype="mixed")
+    env.kappa = float(g["kappa"])
+    obs, r, term, trunc, info = env.reset(seed=0)
+    assert info["x"].data_ptr() == env.x.data_ptr() and obs.shape == (B, 2, 1)          # alias, like the reference (Q3)
+    act = torch.as_tensor(g["action"])
+    for k in range(600 if "none" in path else 1500):
+        a = act[k].reshape(1, 1, 1).expand(B, 1, 1).float()
+        obs, reward, term, trunc, info = env.step(torch.tensor(20.0, dtype=torch.float32) * a)
+        x = obs.cpu().numpy()
+        assert np.array_equal(x[:, :, 0], np.broadcast_to(g["x"][k], (B, 2))), k
+        assert np.array_equal(info["e"].cpu().numpy(), np.full(B, g["e"][k])), k
+        assert np.array_equal(info["reward_grad"].cpu().numpy()[:, 0, :], np.broadcast_to(g["reward_grad"][k], (B, 2))), k
+        ulp = np.abs(reward.cpu().numpy() - g["reward"][k]) / np.spacing(abs(g["reward"][k]) + 1e-300)
+        assert (ulp <= 1.0).all(), k                      # reference: e**2 via libm pow
+    assert env.stepp == k + 1 and info["yref"] == _ref_signal(oracle)[k]
+    if FAULTS[str(g["fault"])] is not None:
+        assert np.array_equal(env.A, g["A"]) and np.array_equal(env.B, g["B"])
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "sp_rls_*.npz"))))
+def test_rls_update_equals_verbatim_reference(path):
+    from rl4afcs_b200.objects import RLS
+
+    g = np.load(path)
+    B = 3
+    m = RLS({"state_dim": 2, "action_dim": 1, "rls_gamma": float(g["gamma"]), "rls_cov": 10 ** 6}, batch=B, dtype="mixed")
+    assert m.params.shape == (B, 3, 2) and m.Cov.shape == (B, 3, 3)
+    for k in range(len(g["da0"])):
+        if k == int(g["reset_at"]):
+            m._reset()
+        ex = lambda v, w: torch.as_tensor(v).reshape(1, w, 1).expand(B, w, 1)   # noqa: E731
+        m.update(ex(g["dx0"][k], 2), ex(g["da0"][k:k + 1], 1), ex(g["dx1"][k], 2))
+        assert np.array_equal(m.params.cpu().numpy().reshape(B, 6), np.broadcast_to(g["theta"][k], (B, 6))), k
+        assert np.array_equal(m.Cov.cpu().numpy().reshape(B, 9), np.broadcast_to(g["cov"][k], (B, 9))), k
+        assert np.array_equal(m.epsilon.cpu().numpy().reshape(B, 2), np.broadcast_to(g["eps"][k], (B, 2))), k
+        assert np.array_equal(m.eps_norm.cpu().numpy(), np.full(B, g["eps_norm"][k])), k
+    F, G = m.F.cpu().numpy(), m.G.cpu().numpy()
+    th = g["theta"][-1].reshape(3, 2)
+    assert np.array_equal(F[0], th[:2].T) and np.array_equal(G[0], th[2:].T)
+
+
+@pytest.mark.parametrize("policy", ["mixed", "fp64"])
+@pytest.mark.parametrize("elig", [None, "accumulating", "replacing"])
+def test_actor_critic_calls_equal_oracle(oracle, policy, elig):
+    """Critic.__call__/Actor.__call__ (+ traces, da/dz), get_weight_update and soft_update vs the
+    oracle's per-step log (same inputs)."""
+    from rl4afcs_b200.objects import Actor, Critic
+
+    n, steps = 33, 25
+    ic = oracle.default_idhp_config()
+    ic["actor_config"]["elig"] = ic["critic_config"]["elig"] = elig
+    cfg = oracle.make_cfg(ic)
+    base, amp = oracle.default_reference()
+    rng = np.random.default_rng(5)
+    x0 = np.deg2rad(rng.uniform(-2, 2, size=(n, 2)))
+    w = oracle.init_weights(n, 6)
+    st = oracle.init_states(policy, cfg, x0, w)
+    actor = Actor(1, {4: "tanh", 1: "tanh"}, False, 0.1, 1, elig, batch=n, dtype=policy)
+    critic = Critic(1, {4: "tanh", 2: "linear"}, False, 0.1, 1, elig, batch=n, dtype=policy)
+    target = Critic(1, {4: "tanh", 2: "linear"}, False, 0.1, 1, elig, batch=n, dtype=policy)
+    gl = float(cfg["gamma"][0] * cfg["lambda_h"][0])
+    actor.gamma_lambda = critic.gamma_lambda = gl
+    for k in range(steps):
+        pre = st.copy()
+        lg = oracle.run(policy, cfg, base, st, k, 1, tanh="t13", n_log=n)[:, 0]
+        # load the pre-step weights / traces into the objects
+        actor.set_weights([pre["W1a"].reshape(n, 1, 4), pre["W2a"].reshape(n, 4, 1)])
+        critic.set_weights([pre["W1c"].reshape(n, 1, 4), pre["W2c"].reshape(n, 4, 2)])
+        target.set_weights([pre["W1t"].reshape(n, 1, 4), pre["W2t"].reshape(n, 4, 2)])
+        actor._eng.env_field("EA", 8).copy_(torch.as_tensor(pre["Ea"].T.copy()).to(actor._eng.te))
+        ce = critic._eng.env_field("EC_H", 12)
+        ce[0:4] = torch.as_tensor(pre["Ec"][:, 0:4].T.copy()).to(ce.dtype)
+        ce[4:8] = torch.as_tensor(pre["Ec"][:, 8:12].T.copy()).to(ce.dtype)
+        ce[8:12] = torch.as_tensor(pre["Ec"][:, 20:24].T.copy()).to(ce.dtype)
+        z = torch.as_tensor(lg["e"]).reshape(n, 1, 1)
+        lam = critic(z)
+        a, dadz = actor(z, return_input_gradient=True)
+        assert np.array_equal(lam.double().cpu().numpy().reshape(n, 2), lg["lam"]), k
+        assert np.array_equal(a.double().cpu().numpy().ravel(), lg["a"]), k
+        assert np.array_equal(dadz.double().cpu().numpy().ravel(), lg["dadz"]), k
+        assert np.array_equal(actor.E.double().cpu().numpy().reshape(n, 8), lg["a_e"]), k
+        assert np.array_equal(critic.E.double().cpu().numpy().reshape(n, 24), lg["c_e"]), k
+        if k > 1:
+            W1u, W2u = critic.get_weight_update(torch.as_tensor(lg["td"]).reshape(n, 1, 2))
+            got = torch.cat([W1u.reshape(n, 4), W2u.reshape(n, 8)], dim=1).double().cpu().numpy()
+            assert np.array_equal(got, lg["c_all_grad"]), k
+            W1u, W2u = actor.get_weight_update(torch.as_tensor(lg["loss_grad"]).reshape(n, 1, 1))
+            got = torch.cat([W1u.reshape(n, 4), W2u.reshape(n, 4)], dim=1).double().cpu().numpy()
+            assert np.array_equal(got, lg["a_all_grad"]), k
+            # SGD + Polyak as the reference does them (objects.py:892-895)
+            lr = torch.as_tensor(pre["eta_c"]).to(W1u.dtype).cuda().reshape(n, 1, 1)
+            cw = critic.trainable_weights
+            g = critic.get_weight_update(torch.as_tensor(lg["td"]).reshape(n, 1, 2))
+            cw[0].copy_(cw[0] - lr * g[0]); cw[1].copy_(cw[1] - lr * g[1])
+            target.soft_update(critic.trainable_weights, tau=float(cfg["tau"][0]))
+            assert np.array_equal(cw[0].double().cpu().numpy().reshape(n, 4), st["W1c"]), k
+            assert np.array_equal(target.trainable_weights[1].double().cpu().numpy().reshape(n, 8), st["W2t"]), k
+
+
+@pytest.mark.parametrize("name", ["default_x0zero", "default_x0rand", "shiftcg_acc_1step", "invert_replacing"])
+def test_idhpsp_train_equals_reference_run(oracle, name):
+    """IDHPsp(env, config).train() (BASELINE.json configs[0]: one agent, idhp_sp.py defaults) against the
+    golden loop that ran on the verbatim reference env + RLS."""
+    from rl4afcs_b200.envs.linear.env import Ce500ShortPeriod
+    from rl4afcs_b200.objects import IDHPsp
+
+    g = np.load(os.path.join(GOLD, f"sp_loop_{name}.npz"))
+    ic = oracle.default_idhp_config()
+    ic["multistep"] = int(g["multistep"])
+    ic["actor_config"]["elig"] = ELIG[str(g["elig_a"])]
+    ic["critic_config"]["elig"] = ELIG[str(g["elig_c"])]
+    B = 2
+    env = Ce500ShortPeriod(_env_config(oracle, g["x0"].reshape(2, 1), FAULTS[str(g["fault"])]), batch=B, dtype="mixed")
+    w = {k: np.broadcast_to(g[f"w_{k}"], (B,) + g[f"w_{k}"].shape).copy() for k in ("W1a", "W2a", "W1c", "W2c")}
+    idhp = IDHPsp(env, ic, verbose=0, seed=4, weights=w, log="full", log_agents=B)
+    steps = int(g["steps"])
+    idhp.train(steps)
+    for b in range(B):
+        assert np.array_equal(idhp.x_hist[b].cpu().numpy(), g["x"])
+        assert np.array_equal(idhp.a_hist[b, :, 0].cpu().numpy(), g["a"])
+        assert np.array_equal(idhp.ref_hist[b].cpu().numpy(), g["ref"])
+        assert np.array_equal(idhp.a_weights_hist1[b].cpu().numpy(), g["a_w1"])
+        assert np.array_equal(idhp.a_weights_hist2[b].cpu().numpy(), g["a_w2"])
+        assert np.array_equal(idhp.c_weights_hist1[b].cpu().numpy(), g["c_w1"])
+        assert np.array_equal(idhp.c_weights_hist2[b].cpu().numpy(), g["c_w2"])
+        assert np.array_equal(idhp.params_hist[b, 2:].cpu().numpy(), g["params"][2:])
+        assert np.array_equal(idhp.cov_hist[b, 2:].cpu().numpy(), g["cov"][2:])
+        assert np.array_equal(idhp.eps_norm_hist[b, 2:].cpu().numpy(), g["eps_norm"][2:])
+        c = idhp.c_hist[b].cpu().numpy()
+        nz = np.abs(g["c"]) > 0
+        assert (np.abs(c - g["c"])[nz] / np.spacing(np.abs(g["c"][nz])) <= 1.0).all()
+    # object views after the run
+    assert idhp.actor.trainable_weights[0].shape == (B, 1, 4) and idhp.critic.trainable_weights[1].shape == (B, 4, 2)
+    assert np.array_equal(idhp.model.params[0].cpu().numpy().ravel(), g["params"][-1])
+    s = idhp.stats()
+    assert s["sum_c"].shape == (B,) and not bool(s["diverged"].any())
+    assert env.stepp == steps and len(env.yref_hist) == steps
