@@ -73,16 +73,33 @@ __device__ __forceinline__ void sp_env_step(Rn<TE> (&x)[2], Rn<TN> action_deg, R
     xn[1] = x[1] + xd1 * dt;
 }
 
-// Network.base_call hidden layer (objects.py:111-139) for the scalar input z (Q1):
-// h_j = tanh(z*W1_j), ai0_j = 1 - h_j^2
+// Network.base_call hidden layers (objects.py:111-139) of critic, target critic and actor for the
+// scalar input z (Q1): h_j = tanh(z*W1_j), ai0_j = 1 - h_j^2.  The 12 tanh are one group so that
+// their dependent chains interleave (the three nets are independent).
 template <typename TN>
-__device__ __forceinline__ void sp_hidden(Rn<TN> z, const Rn<TN> (&W1)[4], Rn<TN> (&h)[4], Rn<TN> (&ai0)[4])
+__device__ __forceinline__ void sp_hidden3(Rn<TN> z, const Rn<TN> (&W1c)[4], const Rn<TN> (&W1t)[4], const Rn<TN> (&W1a)[4],
+                                           Rn<TN> (&hc)[4], Rn<TN> (&ht)[4], Rn<TN> (&ha)[4])
+{
+    Rn<TN> pre[12], h[12];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { pre[j] = z * W1c[j]; pre[4 + j] = z * W1t[j]; pre[8 + j] = z * W1a[j]; }
+    tanh_t13_n<12>(pre, h);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { hc[j] = h[j]; ht[j] = h[4 + j]; ha[j] = h[8 + j]; }
+}
+template <typename TN>
+__device__ __forceinline__ void sp_hidden(Rn<TN> z, const Rn<TN> (&W1)[4], Rn<TN> (&h)[4])
+{
+    Rn<TN> pre[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pre[j] = z * W1[j];
+    tanh_t13_n<4>(pre, h);
+}
+template <typename TN>
+__device__ __forceinline__ void sp_ai0(const Rn<TN> (&h)[4], Rn<TN> (&ai0)[4])
 {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        h[j] = tanh_t13(z * W1[j]);
-        ai0[j] = Rn<TN>(TN(1)) - h[j] * h[j];
-    }
+    for (int j = 0; j < 4; ++j) ai0[j] = Rn<TN>(TN(1)) - h[j] * h[j];
 }
 
 // (1,4)@(4,2) linear output layer, in-order FMA chain
@@ -110,13 +127,13 @@ __device__ __forceinline__ Rn<TE> trace_none_or_acc(int elig, Rn<TE> Eold, Rn<TE
 // Critic.call (objects.py:151-193): forward + Jacobian trace.
 // E layout: EcH = E[0,0:4] (== E[1,4:8]), EcR0 = E[0,8:12], EcR1 = E[1,8:12]; other slots are 0.
 template <typename TN, typename TE>
-__device__ __forceinline__ void sp_critic_forward(Rn<TN> z, const Rn<TN> (&W1)[4], const Rn<TN> (&W2)[8],
+__device__ __forceinline__ void sp_critic_forward(Rn<TN> z, const Rn<TN> (&h)[4], const Rn<TN> (&W2)[8],
                                                   Rn<TE> (&EcH)[4], Rn<TE> (&EcR0)[4], Rn<TE> (&EcR1)[4],
                                                   int elig, Rn<TE> gl, Rn<TN> (&lam)[2])
 {
     using E = Rn<TE>;
-    Rn<TN> h[4], ai0[4];
-    sp_hidden(z, W1, h, ai0);
+    Rn<TN> ai0[4];
+    sp_ai0(h, ai0);
     sp_out2(h, W2, lam);
     E gH[4], g0[4], g1[4];
 #pragma unroll
@@ -156,13 +173,13 @@ __device__ __forceinline__ void sp_critic_forward(Rn<TN> z, const Rn<TN> (&W1)[4
 // Actor.call (objects.py:226-259) + d a / d z by reverse-mode autodiff in TF's order
 // (objects.py:876-878): TanhGrad dy*(1-y*y), MatMul grad, TanhGrad, MatMul grad (chain).
 template <typename TN, typename TE>
-__device__ __forceinline__ void sp_actor_forward(Rn<TN> z, const Rn<TN> (&W1)[4], const Rn<TN> (&W2)[4],
+__device__ __forceinline__ void sp_actor_forward(Rn<TN> z, const Rn<TN> (&h)[4], const Rn<TN> (&W1)[4], const Rn<TN> (&W2)[4],
                                                  Rn<TE> (&Ea)[8], int elig, Rn<TE> gl, Rn<TN>& a_next, Rn<TN>& dadz)
 {
     using N = Rn<TN>;
     using E = Rn<TE>;
-    N h[4], ai0[4];
-    sp_hidden(z, W1, h, ai0);
+    N ai0[4];
+    sp_ai0(h, ai0);
     N o = h[0] * W2[0];
 #pragma unroll
     for (int j = 1; j < 4; ++j) o = fma(h[j], W2[j], o);
@@ -217,9 +234,7 @@ __device__ __forceinline__ void sp_rls_update(Rn<TE> (&th)[6], Rn<TE> (&cv)[9], 
     xcx = fma(X[1], CX[1], xcx);
     xcx = fma(X[2], CX[2], xcx);
     const E den = rls_gamma + xcx;
-    const TE rden = make_rcp(den.v);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) K[i] = div_by(CX[i], den, rden); // objects.py:521
+    div_group<3>(CX, den, K);                                    // objects.py:521
 #pragma unroll
     for (int j = 0; j < 3; ++j) {                                // objects.py:522
         th[j * 2 + 0] = th[j * 2 + 0] + K[j] * eps[0];
@@ -231,12 +246,12 @@ __device__ __forceinline__ void sp_rls_update(Rn<TE> (&th)[6], Rn<TE> (&cv)[9], 
 #pragma unroll
             for (int j = 0; j < 3; ++j) cv[i * 3 + j] = cv[i * 3 + j] - K[i] * CX[j];
     } else {
-        const TE rg = make_rcp(rls_gamma.v);
+        E num[9];
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j)
-                cv[i * 3 + j] = div_by(cv[i * 3 + j] - K[i] * CX[j], rls_gamma, rg);   // objects.py:529-530
+            for (int j = 0; j < 3; ++j) num[i * 3 + j] = cv[i * 3 + j] - K[i] * CX[j];
+        div_group<9>(num, rls_gamma, cv);                        // objects.py:529-530
     }
     eps_norm = sqrt_rn(fma(eps[1], eps[1], eps[0] * eps[0]));    // objects.py:539
 }
@@ -274,14 +289,12 @@ __device__ __forceinline__ void sp_agent_step(SpAgent<TN, TE>& s, const rl4_sp_p
         const double lam = (s.flags & RL4_SPF_LAMBDA_LOW) ? hv.hp(RL4_HP_LAMBDA_L) : hv.hp(RL4_HP_LAMBDA_H);
         gl = E(TE(__dmul_rn(lam, hv.hp(RL4_HP_GAMMA))));                // objects.py:602,814-817
     }
-    sp_critic_forward<TN, TE>(z, s.W1c, s.W2c, s.EcH, s.EcR0, s.EcR1, elig_c, gl, o.lam);
-    {
-        N ht[4], ait[4];
-        sp_hidden(z, s.W1t, ht, ait);                                   // objects.py:867 (trace unused, Q16)
-        sp_out2(ht, s.W2t, o.lt);
-    }
+    N hc[4], ht[4], ha[4];
+    sp_hidden3(z, s.W1c, s.W1t, s.W1a, hc, ht, ha);
+    sp_critic_forward<TN, TE>(z, hc, s.W2c, s.EcH, s.EcR0, s.EcR1, elig_c, gl, o.lam);
+    sp_out2(ht, s.W2t, o.lt);                                           // objects.py:867 (trace unused, Q16)
     N a_next;
-    sp_actor_forward<TN, TE>(z, s.W1a, s.W2a, s.Ea, elig_a, gl, a_next, o.dadz);
+    sp_actor_forward<TN, TE>(z, ha, s.W1a, s.W2a, s.Ea, elig_a, gl, a_next, o.dadz);
 
     // F, G of the RLS model BEFORE this step's update (objects.py:874; Q18), in the tensor dtype;
     // dx1dx0 = F + G@dadx with the (2,1) product broadcast over both columns (objects.py:963-964; Q2)
@@ -409,7 +422,9 @@ __device__ __forceinline__ void sp_agent_step(SpAgent<TN, TE>& s, const rl4_sp_p
     s.sumc = s.sumc + o.cost;
     s.sumabse = s.sumabse + abs_rn(o.e);
     {
-        const E aoa_err_deg = sqrt_rn(E(TE(-2)) * (o.cost / kappa)) * E(Consts<TE>::rad2deg());
+        E cq[1] = {o.cost}, cdk[1];
+        div_group<1>(cq, kappa, cdk);
+        const E aoa_err_deg = sqrt_rn(E(TE(-2)) * cdk[0]) * E(Consts<TE>::rad2deg());
         if (aoa_err_deg.v > TE(0.5)) s.conv_step = k;
     }
     if (is_nan(xn[0]) || is_nan(xn[1])) s.flags |= RL4_SPF_X_NAN;

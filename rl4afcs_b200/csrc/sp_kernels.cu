@@ -278,7 +278,9 @@ sp_critic_forward_kernel(const TN* __restrict__ z, const TN* __restrict__ w1, co
     for (int j = 0; j < 4; ++j) { W1[j] = N(w1[j * stride + i]); EcH[j] = E(Eplane[j * stride + i]); EcR0[j] = E(Eplane[(4 + j) * stride + i]); EcR1[j] = E(Eplane[(8 + j) * stride + i]); }
 #pragma unroll
     for (int j = 0; j < 8; ++j) W2[j] = N(w2[j * stride + i]);
-    sp_critic_forward<TN, TE>(N(z[i]), W1, W2, EcH, EcR0, EcR1, elig, E(TE(gamma_lambda)), lam);
+    N h[4];
+    sp_hidden(N(z[i]), W1, h);
+    sp_critic_forward<TN, TE>(N(z[i]), h, W2, EcH, EcR0, EcR1, elig, E(TE(gamma_lambda)), lam);
 #pragma unroll
     for (int j = 0; j < 4; ++j) { Eplane[j * stride + i] = EcH[j].v; Eplane[(4 + j) * stride + i] = EcR0[j].v; Eplane[(8 + j) * stride + i] = EcR1[j].v; }
     out_lambda[i] = lam[0].v; out_lambda[stride + i] = lam[1].v;
@@ -300,7 +302,9 @@ sp_actor_forward_kernel(const TN* __restrict__ z, const TN* __restrict__ w1, con
     for (int j = 0; j < 4; ++j) { W1[j] = N(w1[j * stride + i]); W2[j] = N(w2[j * stride + i]); }
 #pragma unroll
     for (int j = 0; j < 8; ++j) Ea[j] = E(Eplane[j * stride + i]);
-    sp_actor_forward<TN, TE>(N(z[i]), W1, W2, Ea, elig, E(TE(gamma_lambda)), a, dadz);
+    N h[4];
+    sp_hidden(N(z[i]), W1, h);
+    sp_actor_forward<TN, TE>(N(z[i]), h, W1, W2, Ea, elig, E(TE(gamma_lambda)), a, dadz);
 #pragma unroll
     for (int j = 0; j < 8; ++j) Eplane[j * stride + i] = Ea[j].v;
     out_a[i] = a.v;
