@@ -222,6 +222,9 @@ int rl4_peak_fma(int is_double, double* out_flops_per_s, void* stream);
  * op 0: tanh t13 (double)  1: tanh t13 (float)  2: shared-reciprocal division a/b (double)
  * 3: __ddiv_rn(a, b).  Used by tests/test_gpu_math.py only. */
 int rl4_test_math(int op, const void* a, const void* b, void* out, int64_t n, void* stream);
+/* Test hook: exhaustive comparison of the float t13 quotient em/(em+2) with __fdiv_rn over the float
+ * bit patterns [lo_bits, hi_bits); adds the number of mismatches to *device_mismatch_counter. */
+int rl4_test_t13_div_f32(uint32_t lo_bits, uint32_t hi_bits, unsigned long long* device_mismatch_counter, void* stream);
 /* number of kernel launches issued by this library since load (bench.py "gpu_launches") */
 int64_t rl4_launch_count(void);
 

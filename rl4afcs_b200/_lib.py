@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librl4afcs_b200.so")
+LIB_PATH = os.environ.get("RL4AFCS_LIB") or os.path.join(_HERE, "librl4afcs_b200.so")   # override: tuning experiments only
 
 # enums of include/rl4afcs_b200.h
 FP64, FP32, MIXED = 0, 1, 2
@@ -67,7 +67,7 @@ EXPORTS = [
     "rl4_sp_init", "rl4_sp_run", "rl4_sp_env_step", "rl4_sp_rls_update",
     "rl4_sp_critic_forward", "rl4_sp_actor_forward", "rl4_sp_critic_weight_update",
     "rl4_ctx_create", "rl4_ctx_destroy", "rl4_sp_episode_host",
-    "rl4_peak_fma", "rl4_launch_count", "rl4_test_math",
+    "rl4_peak_fma", "rl4_launch_count", "rl4_test_math", "rl4_test_t13_div_f32",
 ]
 
 _lib = None
@@ -103,6 +103,7 @@ def load() -> ctypes.CDLL:
     L.rl4_peak_fma.argtypes = [ctypes.c_int, ctypes.POINTER(dbl), vp]
     L.rl4_launch_count.restype = i64
     L.rl4_test_math.argtypes = [ctypes.c_int, vp, vp, vp, i64, vp]
+    L.rl4_test_t13_div_f32.argtypes = [ctypes.c_uint32, ctypes.c_uint32, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in ("rl4_last_error", "rl4_launch_count", "rl4_abi_version"):

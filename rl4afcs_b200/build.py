@@ -43,10 +43,12 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = None) -> str:
+    """Build the library.  ``extra_flags`` / ``out`` exist for tuning experiments (scripts/)."""
+    out = out or LIB_PATH
+    if not force and out == LIB_PATH and not _stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(_HERE, "build.log")
     with open(log, "w") as fh:
@@ -55,7 +57,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError(f"nvcc failed ({res.returncode}); see {log}\n{res.stderr[-4000:]}")
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":

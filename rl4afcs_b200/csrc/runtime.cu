@@ -88,6 +88,25 @@ __global__ void math_probe_kernel(int op, const void* a, const void* b, void* ou
     }
 }
 
+// exhaustive check of the re-spelled float quotient em/(em+2) against __fdiv_rn for every float
+// bit pattern in [lo, hi): counts mismatches (fast path where its guard accepts, fallback otherwise)
+__global__ void t13_div_f32_exhaustive_kernel(unsigned lo, unsigned hi, unsigned long long* mismatches)
+{
+    unsigned long long bad = 0;
+    const unsigned long long n = (unsigned long long)hi - lo;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float em = __uint_as_float(lo + (unsigned)i);
+        const float den = __fadd_rn(em, 2.0f);
+        bool ok;
+        float q = t13_div_fast(em, den, ok);
+        if (!ok) q = __fdiv_rn(em, den);
+        const float want = __fdiv_rn(em, den);
+        if (__float_as_uint(q) != __float_as_uint(want)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace rl4
 
 extern "C" {
@@ -122,6 +141,13 @@ int rl4_test_math(int op, const void* a, const void* b, void* out, int64_t n, vo
     if (n == 0) return 0;
     rl4::math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(op, a, b, out, n);
     return rl4::check_launch("math_probe_kernel");
+}
+
+int rl4_test_t13_div_f32(uint32_t lo_bits, uint32_t hi_bits, unsigned long long* device_mismatch_counter, void* stream)
+{
+    RL4_REQUIRE(device_mismatch_counter && hi_bits >= lo_bits, "bad argument");
+    rl4::t13_div_f32_exhaustive_kernel<<<148 * 16, 256, 0, (cudaStream_t)stream>>>(lo_bits, hi_bits, device_mismatch_counter);
+    return rl4::check_launch("t13_div_f32_exhaustive_kernel");
 }
 
 int64_t rl4_launch_count(void) { return rl4::g_launch_count.load(); }

@@ -12,6 +12,19 @@
 namespace rl4 {
 
 constexpr int kBlock = 128;
+// minimum resident CTAs per SM requested from ptxas, per dtype policy (tuned on B200, profiles/README.md)
+#ifndef RL4_MINB_FP64
+#define RL4_MINB_FP64 2
+#endif
+#ifndef RL4_MINB_MIXED
+#define RL4_MINB_MIXED 3
+#endif
+#ifndef RL4_MINB_FP32
+#define RL4_MINB_FP32 4
+#endif
+template <typename TN, typename TE> struct MinBlocks { static constexpr int v = RL4_MINB_FP64; };
+template <> struct MinBlocks<float, double> { static constexpr int v = RL4_MINB_MIXED; };
+template <> struct MinBlocks<float, float> { static constexpr int v = RL4_MINB_FP32; };
 
 template <typename T> struct Plane {
     T* base;
@@ -142,7 +155,7 @@ __device__ __forceinline__ void sp_write_log(const rl4_sp_log& lg, int64_t row, 
 }
 
 template <typename TN, typename TE, bool TRACES, int LOG, bool PER_AGENT>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, (MinBlocks<TN, TE>::v))
 sp_run_kernel(const __grid_constant__ rl4_sp_params p, const double* __restrict__ ref_base, int k0, int n_steps,
               const rl4_sp_state st, int64_t n_agents, const rl4_sp_log lg)
 {

@@ -66,3 +66,15 @@ def test_shared_reciprocal_division_equals_ieee():
     for want in (ieee, host):
         same = (got == want) | (np.isnan(got) & np.isnan(want))
         assert same.all(), (a[~same][:5], b[~same][:5], got[~same][:5], want[~same][:5])
+
+
+def test_float_t13_quotient_equals_ieee_for_every_float():
+    """em/(em+2) re-spelled (MUFU.RCP + Newton + correction) == __fdiv_rn for all floats in [0, 2^28]."""
+    from rl4afcs_b200 import _lib
+
+    L = _lib.load()
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    hi = int(np.float32(2.0 ** 28).view(np.uint32)) + 1
+    _lib.check(L.rl4_test_t13_div_f32(0, hi, cnt.data_ptr(), None), "rl4_test_t13_div_f32")
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == 0
