@@ -32,7 +32,9 @@ import numpy as np  # noqa: E402
 # Algorithmic FLOPs per agent-step of the fp64/fp32 path with the idhp_sp.py defaults (multistep
 # on, no traces); FMA = 2, div = sqrt = 1.  Derivation in DESIGN.md "Roofline accounting".
 FLOP_PER_AGENT_STEP = 388 + 13 * 38 + 13 + 2          # body + 13 tanh (37 flop + 1 div) + 13 div + 2 sqrt
-FP_INSTR_PER_AGENT_STEP = None                        # filled from profiles/ (SASS count) in DESIGN.md
+# FP64 warp-instructions per agent-step of the fp64 kernel, measured with ncu (profiles/README.md):
+# sm__pipe_fp64_cycles_active 69.3 % x 2395 cycles per warp-step / 2 issue cycles per FP64 instruction
+FP64_INSTR_PER_AGENT_STEP = 830
 
 
 def parse():
@@ -309,6 +311,7 @@ def run_ours(args) -> dict:
     device = f"cuda:{local}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(device))
     L = _lib.load()
     n, K, W = args.agents, args.steps, max(args.warmup, 0)
@@ -349,6 +352,12 @@ def run_ours(args) -> dict:
                 "kernel": "sp_run_kernel", "flop_per_agent_step": FLOP_PER_AGENT_STEP,
                 "peak_source": "rl4_peak_fma measured live on this GPU (MEASURED_PEAKS.json has no FP64/FP32 vector peak)",
                 "hbm_bytes_per_agent_step": (eng.env.element_size() * 45 + eng.net.element_size() * 40 + 16) * 2 / K}
+        if args.policy == "fp64":
+            # pipe view: the parity contract forces separately rounded mul/add (1 flop per FP64 issue slot), so the
+            # FLOP fraction understates how busy the binding pipe is; instruction count from ncu (profiles/README.md)
+            roof["fp64_instr_per_agent_step"] = FP64_INSTR_PER_AGENT_STEP
+            roof["pipe_frac_of_measured_dfma_rate"] = FP64_INSTR_PER_AGENT_STEP * n * K / (ms * 1e-3) / (peak.value / 2.0)
+            roof["ncu_fp64_pipe_active_pct"] = 69.3
         variants = {}
         if not args.no_variants and world == 1:
             for pol in ("mixed", "fp32", "fp64"):
