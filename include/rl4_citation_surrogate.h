@@ -1,0 +1,198 @@
+/* rl4_citation_surrogate.h -- documented stand-in for the reference's nonlinear aircraft model.
+ *
+ * The reference's plant is `_citation.cp39-win_amd64.pyd` (envs/nonlinear/extended_input/, called at
+ * envs/nonlinear/env.py:210,289-291 through envs/nonlinear/citation.py:62-69): a Simulink-Coder build
+ * of the DASMAT Cessna Citation 500 model, Windows x64, CPython-3.9 ABI, NO source, fixed-step solver
+ * string "ode5".  It cannot be loaded, disassembled into tables, or re-derived here, so NUMERICAL PARITY
+ * WITH THE REFERENCE PLANT IS UNPINNED.  What IS reproduced is its contract:
+ *
+ *   step(u[11]) -> x[12], one fixed step of dt seconds, process-global state in the reference /
+ *   per-agent state here;
+ *   x = [p q r V alpha beta phi theta psi h xe ye]      (envs/nonlinear/env.py:22-26, idhp_nonlin.py:52)
+ *   u = [de da dr, trim de da dr, flap, gear, thr1, thr2, xcg shift]   (idhp_nonlin.py:51, env.py:130,143)
+ *   trimmed straight and level at V = 90 m/s, h = 2000 m, alpha = theta = 0.0576 rad with
+ *   de = -0.02855 rad, throttles 0.55 (idhp_nonlin.py:53-54).
+ *
+ * Model: rigid 6-DOF aeroplane, flat earth, ISA atmosphere, quasi-steady linear-in-derivatives aero
+ * build-up with a quadratic drag polar and a smooth stall (lift saturation + post-stall drag / nose-down moment); stability and control derivatives of the Cessna Ce500 Citation
+ * (TU Delft AE3202 Flight Dynamics lecture notes, Table D-1 -- the same table envs/linear/env.py:68-87
+ * quotes), two fuselage-mounted turbofans lumped into one body-x thrust.  CL0, Cm0 and the static thrust
+ * are solved so that the state above is an exact equilibrium of the model.  Integrators: classical RK4
+ * (BASELINE.json "RK4 dt=0.01") and Dormand-Prince RK5 with fixed step (Simulink's "ode5").
+ *
+ * One definition, plain C, shared by the CUDA kernels (rl4afcs_b200/csrc/nl_kernels.cu) and the CPU
+ * oracle's plant (oracle/nl_oracle.c): there is no reference to restate, so both sides must integrate
+ * the SAME documented model; sin/cos/pow come from the respective math library (CUDA / glibc), hence
+ * plant parity kernel-vs-oracle is a tolerance (1e-12 per step), not bit equality.
+ */
+#ifndef RL4_CITATION_SURROGATE_H
+#define RL4_CITATION_SURROGATE_H
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define RL4_HD __host__ __device__ __forceinline__
+#else
+#define RL4_HD static inline
+#endif
+
+enum { RL4_CIT_NX = 12, RL4_CIT_NU = 11 };
+enum { RL4_CIT_P = 0, RL4_CIT_Q, RL4_CIT_R, RL4_CIT_V, RL4_CIT_ALPHA, RL4_CIT_BETA, RL4_CIT_PHI, RL4_CIT_THETA,
+       RL4_CIT_PSI, RL4_CIT_H, RL4_CIT_XE, RL4_CIT_YE };
+enum { RL4_CIT_INTEGRATOR_RK4 = 0, RL4_CIT_INTEGRATOR_ODE5 = 1 };
+
+typedef struct rl4_cit_params {
+    /* mass and geometry */
+    double m, S, c, b, Ixx, Iyy, Izz, Ixz, g;
+    /* longitudinal derivatives (per rad, rates normalised with c/(2V)) */
+    double CL0, CLa, CLq, CLde, CLflap, al_stall;
+    double CD0, CDk, CDgear, CDflap, CDstall;
+    double Cm0, Cma, Cmq, Cmde, Cmflap, Cmstall;
+    /* lateral-directional derivatives (rates normalised with b/(2V)) */
+    double CYb, CYp, CYr, CYda, CYdr;
+    double Clb, Clp, Clr, Clda, Cldr;
+    double Cnb, Cnp, Cnr, Cnda, Cndr;
+    /* propulsion: T = Tstatic * (rho/rho0)^0.7 * (thr1 + thr2)/2, along body x through the c.g. */
+    double Tstatic;
+} rl4_cit_params;
+
+/* ISA troposphere density */
+RL4_HD double rl4_cit_density(double h)
+{
+    const double T0 = 288.15, lapse = -0.0065, R = 287.05, g0 = 9.80665, rho0 = 1.225;
+    const double Tr = 1.0 + lapse * h / T0;
+    return rho0 * pow(Tr, -(g0 / (lapse * R) + 1.0));
+}
+
+/* xdot = f(x, u) */
+RL4_HD void rl4_cit_deriv(const rl4_cit_params* P, const double* x, const double* u, double* dx)
+{
+    const double p = x[RL4_CIT_P], q = x[RL4_CIT_Q], r = x[RL4_CIT_R];
+    const double V = x[RL4_CIT_V], al = x[RL4_CIT_ALPHA], be = x[RL4_CIT_BETA];
+    const double phi = x[RL4_CIT_PHI], th = x[RL4_CIT_THETA], psi = x[RL4_CIT_PSI], h = x[RL4_CIT_H];
+    const double de = u[0] + u[3], da = u[1] + u[4], dr = u[2] + u[5];
+    const double flap = u[6], gear = u[7], thr = 0.5 * (u[8] + u[9]), dxcg = u[10];
+
+    const double sa = sin(al), ca = cos(al), sb = sin(be), cb = cos(be);
+    const double sphi = sin(phi), cphi = cos(phi), sth = sin(th), cth = cos(th), spsi = sin(psi), cpsi = cos(psi);
+
+    const double rho = rl4_cit_density(h);
+    const double qbar = 0.5 * rho * V * V;
+    const double qS = qbar * P->S;
+    const double ch = P->c / (2.0 * V), bh = P->b / (2.0 * V);
+
+    /* aerodynamic coefficients; lift saturates smoothly beyond alpha_stall (al_e = al / sqrt(1 + (al/al_s)^2)),
+     * the lost incidence (al - al_e) produces extra drag and a nose-down moment: a crude but bounded stall */
+    const double al_e = al / sqrt(1.0 + (al / P->al_stall) * (al / P->al_stall));
+    const double al_x = al - al_e;
+    const double CL = P->CL0 + P->CLa * al_e + P->CLq * (q * ch) + P->CLde * de + P->CLflap * flap;
+    const double CD = P->CD0 + P->CDk * CL * CL + P->CDgear * gear + P->CDflap * flap + P->CDstall * al_x * al_x;
+    const double CY = P->CYb * be + P->CYp * (p * bh) + P->CYr * (r * bh) + P->CYda * da + P->CYdr * dr;
+    const double CX = -CD * ca + CL * sa;                 /* body axes */
+    const double CZ = -CD * sa - CL * ca;
+    /* a c.g. shift dxcg (m, + forward ... sign as the reference's `shift_cg`: input[10] = -0.5) moves the
+     * moment reference: dCm = CZ * dxcg / c, dCn = -CY * dxcg / b */
+    const double Cm = P->Cm0 + P->Cma * al + P->Cmstall * al_x + P->Cmq * (q * ch) + P->Cmde * de + P->Cmflap * flap + CZ * dxcg / P->c;
+    const double Cl = P->Clb * be + P->Clp * (p * bh) + P->Clr * (r * bh) + P->Clda * da + P->Cldr * dr;
+    const double Cn = P->Cnb * be + P->Cnp * (p * bh) + P->Cnr * (r * bh) + P->Cnda * da + P->Cndr * dr - CY * dxcg / P->b;
+
+    const double T = P->Tstatic * pow(rho / 1.225, 0.7) * thr;
+    const double Fx = qS * CX + T, Fy = qS * CY, Fz = qS * CZ;
+    const double L = qS * P->b * Cl, M = qS * P->c * Cm, N = qS * P->b * Cn;
+
+    /* body-axis velocities and their rates */
+    const double ub = V * ca * cb, vb = V * sb, wb = V * sa * cb;
+    const double ud = r * vb - q * wb - P->g * sth + Fx / P->m;
+    const double vd = p * wb - r * ub + P->g * sphi * cth + Fy / P->m;
+    const double wd = q * ub - p * vb + P->g * cphi * cth + Fz / P->m;
+    const double Vd = (ub * ud + vb * vd + wb * wd) / V;
+    const double uw2 = ub * ub + wb * wb;
+
+    /* Euler's equations with Ixz */
+    const double gam = P->Ixx * P->Izz - P->Ixz * P->Ixz;
+    const double Lp = L - (P->Izz - P->Iyy) * q * r + P->Ixz * p * q;
+    const double Np = N - (P->Iyy - P->Ixx) * p * q - P->Ixz * q * r;
+
+    dx[RL4_CIT_P] = (P->Izz * Lp + P->Ixz * Np) / gam;
+    dx[RL4_CIT_Q] = (M - (P->Ixx - P->Izz) * p * r - P->Ixz * (p * p - r * r)) / P->Iyy;
+    dx[RL4_CIT_R] = (P->Ixz * Lp + P->Ixx * Np) / gam;
+    dx[RL4_CIT_V] = Vd;
+    dx[RL4_CIT_ALPHA] = (ub * wd - wb * ud) / uw2;
+    dx[RL4_CIT_BETA] = (vd * V - vb * Vd) / (V * sqrt(uw2));
+    dx[RL4_CIT_PHI] = p + (sth / cth) * (q * sphi + r * cphi);
+    dx[RL4_CIT_THETA] = q * cphi - r * sphi;
+    dx[RL4_CIT_PSI] = (q * sphi + r * cphi) / cth;
+    dx[RL4_CIT_H] = ub * sth - vb * sphi * cth - wb * cphi * cth;
+    dx[RL4_CIT_XE] = ub * cth * cpsi + vb * (sphi * sth * cpsi - cphi * spsi) + wb * (cphi * sth * cpsi + sphi * spsi);
+    dx[RL4_CIT_YE] = ub * cth * spsi + vb * (sphi * sth * spsi + cphi * cpsi) + wb * (cphi * sth * spsi - sphi * cpsi);
+}
+
+/* one fixed step, input held constant over the step (zero-order hold, like Simulink's fixed-step solvers) */
+RL4_HD void rl4_cit_step_rk4(const rl4_cit_params* P, double* x, const double* u, double dt)
+{
+    double k1[12], k2[12], k3[12], k4[12], y[12];
+    int i;
+    rl4_cit_deriv(P, x, u, k1);
+    for (i = 0; i < 12; ++i) y[i] = x[i] + 0.5 * dt * k1[i];
+    rl4_cit_deriv(P, y, u, k2);
+    for (i = 0; i < 12; ++i) y[i] = x[i] + 0.5 * dt * k2[i];
+    rl4_cit_deriv(P, y, u, k3);
+    for (i = 0; i < 12; ++i) y[i] = x[i] + dt * k3[i];
+    rl4_cit_deriv(P, y, u, k4);
+    for (i = 0; i < 12; ++i) x[i] = x[i] + (dt / 6.0) * (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]);
+}
+
+/* Dormand-Prince 5(4) pair, 5th-order solution, fixed step: what Simulink calls ode5 */
+RL4_HD void rl4_cit_step_ode5(const rl4_cit_params* P, double* x, const double* u, double dt)
+{
+    double k1[12], k2[12], k3[12], k4[12], k5[12], k6[12], y[12];
+    int i;
+    rl4_cit_deriv(P, x, u, k1);
+    for (i = 0; i < 12; ++i) y[i] = x[i] + dt * (1.0 / 5.0) * k1[i];
+    rl4_cit_deriv(P, y, u, k2);
+    for (i = 0; i < 12; ++i) y[i] = x[i] + dt * ((3.0 / 40.0) * k1[i] + (9.0 / 40.0) * k2[i]);
+    rl4_cit_deriv(P, y, u, k3);
+    for (i = 0; i < 12; ++i) y[i] = x[i] + dt * ((44.0 / 45.0) * k1[i] - (56.0 / 15.0) * k2[i] + (32.0 / 9.0) * k3[i]);
+    rl4_cit_deriv(P, y, u, k4);
+    for (i = 0; i < 12; ++i)
+        y[i] = x[i] + dt * ((19372.0 / 6561.0) * k1[i] - (25360.0 / 2187.0) * k2[i] + (64448.0 / 6561.0) * k3[i] -
+                            (212.0 / 729.0) * k4[i]);
+    rl4_cit_deriv(P, y, u, k5);
+    for (i = 0; i < 12; ++i)
+        y[i] = x[i] + dt * ((9017.0 / 3168.0) * k1[i] - (355.0 / 33.0) * k2[i] + (46732.0 / 5247.0) * k3[i] +
+                            (49.0 / 176.0) * k4[i] - (5103.0 / 18656.0) * k5[i]);
+    rl4_cit_deriv(P, y, u, k6);
+    for (i = 0; i < 12; ++i)
+        x[i] = x[i] + dt * ((35.0 / 384.0) * k1[i] + (500.0 / 1113.0) * k3[i] + (125.0 / 192.0) * k4[i] -
+                            (2187.0 / 6784.0) * k5[i] + (11.0 / 84.0) * k6[i]);
+}
+
+/* Default parameter set: Ce500 Citation derivatives, with CL0 / Cm0 / Tstatic solved for the trim point
+ * (V, h, alpha = theta, de, throttle) = (90, 2000, 0.0576, -0.02855, 0.55) of idhp_nonlin.py:53-54. */
+RL4_HD void rl4_cit_default_params(rl4_cit_params* P)
+{
+    const double V = 90.0, h = 2000.0, al = 0.0576, de = -0.02855, thr = 0.55;
+    double rho, qS, sa, ca, W, T, CLt, A, B, C, al_e, al_x;
+    P->m = 4547.8; P->S = 24.2; P->c = 2.022; P->b = 13.36; P->g = 9.80665;
+    P->Ixx = P->m * P->b * P->b * 0.012; P->Izz = P->m * P->b * P->b * 0.037; P->Ixz = P->m * P->b * P->b * 0.002;
+    P->Iyy = P->m * P->c * P->c * 0.980;       /* K_Y^2 = Iyy / (m c^2) */
+    P->CLa = 5.16; P->CLq = 3.86; P->CLde = 0.6238; P->CLflap = 0.6; P->al_stall = 0.28;
+    P->CD0 = 0.04; P->CDk = 0.052; P->CDgear = 0.02; P->CDflap = 0.04; P->CDstall = 8.0;
+    P->Cma = -0.43; P->Cmq = -7.04; P->Cmde = -1.553; P->Cmflap = -0.05; P->Cmstall = -6.0;
+    P->CYb = -0.9896; P->CYp = -0.087; P->CYr = 0.43; P->CYda = 0.0; P->CYdr = 0.3037;
+    P->Clb = -0.0772; P->Clp = -0.3444; P->Clr = 0.28; P->Clda = -0.2349; P->Cldr = 0.0286;
+    P->Cnb = 0.1638; P->Cnp = -0.0108; P->Cnr = -0.193; P->Cnda = 0.0286; P->Cndr = -0.1261;
+    /* level trim: T cos(al) = D, L + T sin(al) = W with D = qS (CD0 + k CL^2), L = qS CL:
+     * k/qS * (W - T sa)^2 + qS CD0 - T ca = 0  ->  quadratic in T, smaller root */
+    rho = rl4_cit_density(h); qS = 0.5 * rho * V * V * P->S; sa = sin(al); ca = cos(al); W = P->m * P->g;
+    al_e = al / sqrt(1.0 + (al / P->al_stall) * (al / P->al_stall)); al_x = al - al_e;
+    A = P->CDk / qS * sa * sa; B = -(2.0 * P->CDk / qS * W * sa + ca);
+    C = P->CDk / qS * W * W + qS * (P->CD0 + P->CDstall * al_x * al_x);
+    T = (-B - sqrt(B * B - 4.0 * A * C)) / (2.0 * A);
+    CLt = (W - T * sa) / qS;
+    P->CL0 = CLt - P->CLa * al_e - P->CLde * de;
+    P->Cm0 = -(P->Cma * al + P->Cmstall * al_x + P->Cmde * de);
+    P->Tstatic = T / (pow(rho / 1.225, 0.7) * thr);
+}
+
+#endif

@@ -195,6 +195,109 @@ int rl4_sp_actor_forward(int policy, const void* z, const void* w1, const void* 
 int rl4_sp_critic_weight_update(int policy, const void* td, const void* E, void* out, int64_t stride,
                                 int64_t n_agents, void* stream);
 
+
+/* =====================================================================================
+ * Nonlinear path: Ce500NonLinear (envs/nonlinear/env.py:11-319) + IDHPnonlin (objects.py:1006-1564)
+ * around the documented surrogate plant of include/rl4_citation_surrogate.h (the reference's plant
+ * is a source-less binary; plant parity unpinned).  Policies: RL4_MIXED and RL4_FP64.
+ * ===================================================================================== */
+#include "rl4_citation_surrogate.h"
+
+enum rl4_nl_env_field {        /* env plane, double */
+    RL4_NLE_XFULL = 0,         /* [12] plant state p q r V alpha beta phi theta psi h xe ye   env.py:22-26 */
+    RL4_NLE_XACT = 12,         /* [3] actuator states                                           env.py:71 */
+    RL4_NLE_XLON = 15,         /* [3] x_lon = [alpha theta q]                                   objects.py:1476 */
+    RL4_NLE_XPREVLON = 18,     /* [3] */
+    RL4_NLE_THETA = 21,        /* [12] RLS params (4,3) row-major                               objects.py:461 */
+    RL4_NLE_COV = 33,          /* [16] RLS Cov (4,4) */
+    RL4_NLE_CGRAD_PREV = 49,   /* [1] reward_grad_lon[2] of the previous step                   objects.py:1537 */
+    RL4_NLE_EPS = 50,          /* [3] */
+    RL4_NLE_EPS_NORM = 53,
+    RL4_NLE_RSE = 54,          /* [2] cumulative RSE                                            objects.py:1503-1504 */
+    RL4_NLE_NZ_PEAK = 56,      /* max V q / g0                                                  functions.py:774 */
+    RL4_NLE_ETA_A = 57,        /* self.eta_a / eta_c / lambdaa / gamma_lambda                   objects.py:1252-1281 */
+    RL4_NLE_ETA_C = 58,
+    RL4_NLE_LAMBDAA = 59,
+    RL4_NLE_GL = 60,
+    RL4_NLE_EA = 61,           /* [50] actor trace E (1,50)                                     objects.py:385-392 */
+    RL4_NLE_COUNT = 111
+};
+enum rl4_nl_net_field {        /* net plane, TN */
+    RL4_NLN_S = 0,             /* [4] MDP state s                                               objects.py:1474 */
+    RL4_NLN_SPREV = 4,         /* [4] */
+    RL4_NLN_A = 8, RL4_NLN_APREV = 9,
+    RL4_NLN_W1A = 10,          /* [40] actor W1 (4,10) row-major */
+    RL4_NLN_W2A = 50,          /* [10] */
+    RL4_NLN_W1C = 60,          /* [40] */
+    RL4_NLN_W2C = 100,         /* [30] critic W2 (10,3) row-major */
+    RL4_NLN_W1T = 130,         /* [40] */
+    RL4_NLN_W2T = 170,         /* [30] */
+    RL4_NLN_MPREV = 200,       /* [9] dx1dx0_prev (3,3) */
+    RL4_NLN_LR_A = 209, RL4_NLN_LR_C = 210,   /* optimizer learning rates */
+    RL4_NLN_COUNT = 211
+};
+enum rl4_nl_int_field { RL4_NLI_COOLDOWN = 0, RL4_NLI_DIVERGED_STEP = 1, RL4_NLI_STEPP = 2, RL4_NLI_COUNT = 3 };
+
+typedef struct rl4_nl_state {
+    double*  env;            /* [RL4_NLE_COUNT][stride] */
+    void*    net;            /* [RL4_NLN_COUNT][stride] of TN */
+    int32_t* ints;           /* [RL4_NLI_COUNT][stride] */
+    int64_t  stride;
+} rl4_nl_state;
+
+enum rl4_nl_hp {
+    RL4_NHP_ETA_A_H = 0, RL4_NHP_ETA_A_L, RL4_NHP_ETA_C_H, RL4_NHP_ETA_C_L, RL4_NHP_LAMBDA_H, RL4_NHP_LAMBDA_L,
+    RL4_NHP_GAMMA, RL4_NHP_GAMMA_SQ, RL4_NHP_TAU, RL4_NHP_LR_DECAY, RL4_NHP_RLS_GAMMA, RL4_NHP_RLS_COV0,
+    RL4_NHP_Q_SYM, RL4_NHP_LAMBDA_T, RL4_NHP_LAMBDA_S, RL4_NHP_DAMP_FACTOR, RL4_NHP_CG_SHIFT, RL4_NHP_COUNT
+};
+enum rl4_nl_hpi {
+    RL4_NHPI_MULTISTEP = 0, RL4_NHPI_WARMUP_STEPS, RL4_NHPI_COOLDOWN_STEPS, RL4_NHPI_FAULT_STEP,
+    RL4_NHPI_FAULT_DAMP, RL4_NHPI_FAULT_SAT, RL4_NHPI_ELIG_A, RL4_NHPI_COUNT
+};
+enum rl4_nl_fault_damp { RL4_NL_DAMP_NONE = 0, RL4_NL_DAMP_ELEVATOR, RL4_NL_DAMP_AILERON, RL4_NL_DAMP_RUDDER,
+                         RL4_NL_DAMP_ALL, RL4_NL_SHIFT_CG, RL4_NL_SLOW_ALL };
+enum rl4_nl_fault_sat  { RL4_NL_SAT_NONE = 0, RL4_NL_SAT_ELEVATOR, RL4_NL_SAT_AILERON, RL4_NL_SAT_RUDDER };
+
+typedef struct rl4_nl_params {
+    rl4_cit_params plant;
+    double trim_input[11];          /* idhp_nonlin.py:53 */
+    double dt;
+    double hp[RL4_NHP_COUNT];
+    double noise_std[4];            /* objects.py:1377 */
+    double omega0, omega_slow;      /* envs/nonlinear/env.py:74,145 */
+    double rate_limit;              /* deg2rad(19.7) */
+    double limit_deg[3];            /* 15, 37, 22 */
+    double sat_limit[3];            /* deg2rad(5, 18, 10) */
+    int32_t hpi[RL4_NHPI_COUNT];
+    int32_t integrator;             /* RL4_CIT_INTEGRATOR_* */
+    const double*  hp_agent[RL4_NHP_COUNT];
+    const int32_t* hpi_agent[RL4_NHPI_COUNT];
+} rl4_nl_params;
+
+enum rl4_nl_log_field { RL4_NLL_XFULL = 0 /* [12] */, RL4_NLL_A = 12, RL4_NLL_E_THETA = 13, RL4_NLL_REWARD = 14,
+                        RL4_NLL_SURF = 15 /* [3] action_commanded */, RL4_NLL_COUNT = 18 };
+
+/* Fills *p with the configuration of idhp_nonlin.py:36-54,107-146 and the default surrogate plant (host only). */
+int rl4_nl_default_params(rl4_nl_params* p);
+/* Ce500NonLinear.reset (envs/nonlinear/env.py:258-311: 1000 + 1 plant steps at trim input) and the
+ * IDHPnonlin.train() prologue (objects.py:1466-1488).  Weights: planes of double, W1a [40][stride_in]
+ * ((4,10) row-major), W2a [10], W1c [40], W2c [30] ((10,3) row-major). */
+int rl4_nl_init(int policy, const rl4_nl_params* p, const double* w1a, const double* w2a, const double* w1c,
+                const double* w2c, int64_t stride_in, rl4_nl_state st, int64_t n_agents, void* stream);
+/* IDHPnonlin.train() loop (objects.py:1491-1558) fused with Ce500NonLinear.step (envs/nonlinear/env.py:182-256),
+ * the plant step, Critic_big / Actor_big (objects.py:283-437), RLS.update and _adapt_check (:1212-1290), for steps
+ * [k0, k0+n_steps).  theta_ref: device table (phi / psi references are zero, idhp_nonlin.py:116-117);
+ * noise: device float [n_steps][noise_stride], the N(0,1) draw of tf.random.normal (objects.py:1375) per agent and
+ * step -- an explicit input like the weights (TensorFlow's stream is not reproducible);
+ * log: NULL or RL4_NLL_COUNT fields for the first n_agents_logged agents, layout as rl4_sp_log. */
+int rl4_nl_run(int policy, const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride,
+               int32_t k0, int32_t n_steps, rl4_nl_state st, int64_t n_agents, rl4_sp_log log, void* stream);
+/* Ce500NonLinear.step alone (envs/nonlinear/env.py:182-256): action [3][stride] normalised commands (double),
+ * x_full [12][stride], x_act [3][stride] in/out; out_mdp [4][stride], out_reward, out_e_theta [stride]. */
+int rl4_nl_env_step(const rl4_nl_params* p, const double* theta_ref, int32_t stepp, double* x_full, double* x_act,
+                    const double* action, double* out_mdp, double* out_reward, double* out_e_theta,
+                    int64_t stride, int64_t n_agents, void* stream);
+
 /* ---- host-buffer episode (what a reference user calls: IDHPsp(...).train() for a batch) ----
  * Copies x0 / weights from host memory, runs rl4_sp_init + rl4_sp_run for n_steps on the GPU
  * and copies the final state planes and statistics back.  Host buffers may be pageable or pinned. */

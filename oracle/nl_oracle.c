@@ -1,0 +1,83 @@
+/* TEST INFRASTRUCTURE ONLY -- see nl_oracle.h.  Build: make -C oracle. */
+#include "nl_oracle.h"
+#include "sp_oracle.h"          /* ORC_POLICY_*, ORC_TANH_* */
+#include "sp_oracle_tanh.h"
+#include <math.h>
+#include <string.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+#define TE double
+
+#define TN float
+#define SFX _mixed
+#define N_FMA fmaf
+#define N_SQRT sqrtf
+#define N_T13 orc_t13_f32
+#define N_LIBM_TANH tanhf
+#include "nl_oracle_body.inc"
+#undef TN
+#undef SFX
+#undef N_FMA
+#undef N_SQRT
+#undef N_T13
+#undef N_LIBM_TANH
+
+#define TN double
+#define SFX _fp64
+#define N_FMA fma
+#define N_SQRT sqrt
+#define N_T13 orc_t13_f64
+#define N_LIBM_TANH tanh
+#include "nl_oracle_body.inc"
+
+int orc_nl_default_cfg(orc_nl_cfg* c)
+{
+    if (!c) return -1;
+    memset(c, 0, sizeof(*c));
+    rl4_cit_default_params(&c->plant);
+    const double trim[11] = {-0.02855, 0, 0, 0, 0, 0, 0, 0, 0.55, 0.55, 0};      /* idhp_nonlin.py:53 */
+    memcpy(c->trim_input, trim, sizeof(trim));
+    c->dt = 0.01;                                                                   /* idhp_nonlin.py:36 */
+    c->gamma = 0.6; c->gamma_sq = 0.36; c->tau = 0.02; c->lambda_h = 0.95; c->lambda_l = 0.95; c->lr_decay = 0.998;
+    c->eta_a_h = 35.0; c->eta_a_l = 5.0; c->eta_c_h = 1.4; c->eta_c_l = 0.7;       /* idhp_nonlin.py:123-146 */
+    c->rls_gamma = 1.0; c->rls_cov0 = 1e6; c->Q_sym = 2.0;
+    c->lambda_t = 0.012; c->lambda_s = 0.001;                                       /* objects.py:1383 */
+    c->noise_std[0] = 0.010; c->noise_std[1] = 0.010; c->noise_std[2] = 0.008; c->noise_std[3] = 0.003;
+    c->omega0 = 13.0; c->omega_slow = 6.0; c->rate_limit = 19.7 * (M_PI / 180.0);
+    c->limit_deg[0] = 15.0; c->limit_deg[1] = 37.0; c->limit_deg[2] = 22.0;
+    c->damp_factor = 0.3; c->cg_shift = -0.5;
+    c->sat_limit[0] = 5.0 * (M_PI / 180.0); c->sat_limit[1] = 18.0 * (M_PI / 180.0); c->sat_limit[2] = 10.0 * (M_PI / 180.0);
+    c->multistep = 0; c->warmup_steps = 400; c->cooldown_steps = 200; c->fault_step = -1;
+    c->elig_a = 1; c->fault_damp = 0; c->fault_sat = 0; c->integrator = RL4_CIT_INTEGRATOR_ODE5;
+    return 0;
+}
+
+int orc_nl_init(int policy, const orc_nl_cfg* cfgs, int cfg_stride, const double* W1a, const double* W2a,
+                const double* W1c, const double* W2c, orc_nl_state* st, int64_t n)
+{
+    if (!cfgs || !W1a || !W2a || !W1c || !W2c || !st || n < 0) return -1;
+    for (int64_t i = 0; i < n; ++i) {
+        const orc_nl_cfg* c = cfgs + (cfg_stride ? i : 0);
+        if (policy == ORC_POLICY_MIXED) nl_init_one_mixed(c, W1a + 40 * i, W2a + 10 * i, W1c + 40 * i, W2c + 30 * i, st + i);
+        else if (policy == ORC_POLICY_FP64) nl_init_one_fp64(c, W1a + 40 * i, W2a + 10 * i, W1c + 40 * i, W2c + 30 * i, st + i);
+        else return -1;
+    }
+    return 0;
+}
+
+int orc_nl_run(int policy, int tanh_mode, const orc_nl_cfg* cfgs, int cfg_stride, const double* theta_ref,
+               const float* noise, int k0, int n_steps, orc_nl_state* st, int64_t n, orc_nl_logrow* log, int64_t n_log)
+{
+    if (!cfgs || !theta_ref || !noise || !st || n < 0 || n_steps < 0 || k0 < 0) return -1;
+    if (policy == ORC_POLICY_MIXED) nl_run_mixed(tanh_mode, cfgs, cfg_stride, theta_ref, noise, k0, n_steps, st, n, log, n_log);
+    else if (policy == ORC_POLICY_FP64) nl_run_fp64(tanh_mode, cfgs, cfg_stride, theta_ref, noise, k0, n_steps, st, n, log, n_log);
+    else return -1;
+    return 0;
+}
+
+int orc_nl_sizeof_cfg(void)    { return (int)sizeof(orc_nl_cfg); }
+int orc_nl_sizeof_state(void)  { return (int)sizeof(orc_nl_state); }
+int orc_nl_sizeof_logrow(void) { return (int)sizeof(orc_nl_logrow); }

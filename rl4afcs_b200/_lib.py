@@ -51,6 +51,45 @@ class SpParams(ctypes.Structure):
     ]
 
 
+# ---- nonlinear path ----
+NLE = dict(XFULL=0, XACT=12, XLON=15, XPREVLON=18, THETA=21, COV=33, CGRAD_PREV=49, EPS=50, EPS_NORM=53, RSE=54,
+           NZ_PEAK=56, ETA_A=57, ETA_C=58, LAMBDAA=59, GL=60, EA=61, COUNT=111)
+NLN = dict(S=0, SPREV=4, A=8, APREV=9, W1A=10, W2A=50, W1C=60, W2C=100, W1T=130, W2T=170, MPREV=200, LR_A=209,
+           LR_C=210, COUNT=211)
+NLI = dict(COOLDOWN=0, DIVERGED_STEP=1, STEPP=2, COUNT=3)
+NHP = dict(ETA_A_H=0, ETA_A_L=1, ETA_C_H=2, ETA_C_L=3, LAMBDA_H=4, LAMBDA_L=5, GAMMA=6, GAMMA_SQ=7, TAU=8, LR_DECAY=9,
+           RLS_GAMMA=10, RLS_COV0=11, Q_SYM=12, LAMBDA_T=13, LAMBDA_S=14, DAMP_FACTOR=15, CG_SHIFT=16, COUNT=17)
+NHPI = dict(MULTISTEP=0, WARMUP_STEPS=1, COOLDOWN_STEPS=2, FAULT_STEP=3, FAULT_DAMP=4, FAULT_SAT=5, ELIG_A=6, COUNT=7)
+NL_DAMP = {None: 0, "none": 0, "damp_elevator": 1, "damp_aileron": 2, "damp_rudder": 3, "damp_all": 4, "shift_cg": 5,
+           "slow_all": 6}
+NL_SAT = {None: 0, "none": 0, "saturate_elevator": 1, "saturate_aileron": 2, "saturate_rudder": 3}
+NLL = dict(XFULL=0, A=12, E_THETA=13, REWARD=14, SURF=15, COUNT=18)
+INTEGRATOR = {"rk4": 0, "ode5": 1}
+CIT_FIELDS = ["m", "S", "c", "b", "Ixx", "Iyy", "Izz", "Ixz", "g", "CL0", "CLa", "CLq", "CLde", "CLflap", "al_stall",
+              "CD0", "CDk", "CDgear", "CDflap", "CDstall", "Cm0", "Cma", "Cmq", "Cmde", "Cmflap", "Cmstall",
+              "CYb", "CYp", "CYr", "CYda", "CYdr", "Clb", "Clp", "Clr", "Clda", "Cldr",
+              "Cnb", "Cnp", "Cnr", "Cnda", "Cndr", "Tstatic"]
+
+
+class CitParams(ctypes.Structure):
+    _fields_ = [(f, ctypes.c_double) for f in CIT_FIELDS]
+
+
+class NlState(ctypes.Structure):
+    _fields_ = [("env", ctypes.c_void_p), ("net", ctypes.c_void_p), ("ints", ctypes.c_void_p), ("stride", ctypes.c_int64)]
+
+
+class NlParams(ctypes.Structure):
+    _fields_ = [
+        ("plant", CitParams), ("trim_input", ctypes.c_double * 11), ("dt", ctypes.c_double),
+        ("hp", ctypes.c_double * NHP["COUNT"]), ("noise_std", ctypes.c_double * 4),
+        ("omega0", ctypes.c_double), ("omega_slow", ctypes.c_double), ("rate_limit", ctypes.c_double),
+        ("limit_deg", ctypes.c_double * 3), ("sat_limit", ctypes.c_double * 3),
+        ("hpi", ctypes.c_int32 * NHPI["COUNT"]), ("integrator", ctypes.c_int32),
+        ("hp_agent", ctypes.c_void_p * NHP["COUNT"]), ("hpi_agent", ctypes.c_void_p * NHPI["COUNT"]),
+    ]
+
+
 class SpLog(ctypes.Structure):
     _fields_ = [("buf", ctypes.c_void_p), ("level", ctypes.c_int32), ("every", ctypes.c_int32),
                 ("n_agents_logged", ctypes.c_int64)]
@@ -68,6 +107,7 @@ EXPORTS = [
     "rl4_sp_critic_forward", "rl4_sp_actor_forward", "rl4_sp_critic_weight_update",
     "rl4_ctx_create", "rl4_ctx_destroy", "rl4_sp_episode_host",
     "rl4_peak_fma", "rl4_launch_count", "rl4_test_math", "rl4_test_t13_div_f32",
+    "rl4_nl_init", "rl4_nl_run", "rl4_nl_env_step", "rl4_nl_default_params",
 ]
 
 _lib = None
@@ -103,6 +143,10 @@ def load() -> ctypes.CDLL:
     L.rl4_peak_fma.argtypes = [ctypes.c_int, ctypes.POINTER(dbl), vp]
     L.rl4_launch_count.restype = i64
     L.rl4_test_math.argtypes = [ctypes.c_int, vp, vp, vp, i64, vp]
+    L.rl4_nl_init.argtypes = [ctypes.c_int, ctypes.POINTER(NlParams), vp, vp, vp, vp, i64, NlState, i64, vp]
+    L.rl4_nl_run.argtypes = [ctypes.c_int, ctypes.POINTER(NlParams), vp, vp, i64, i32, i32, NlState, i64, SpLog, vp]
+    L.rl4_nl_env_step.argtypes = [ctypes.POINTER(NlParams), vp, i32, vp, vp, vp, vp, vp, vp, i64, i64, vp]
+    L.rl4_nl_default_params.argtypes = [ctypes.POINTER(NlParams)]
     L.rl4_test_t13_div_f32.argtypes = [ctypes.c_uint32, ctypes.c_uint32, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)

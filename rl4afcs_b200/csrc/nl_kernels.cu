@@ -1,0 +1,572 @@
+// Nonlinear IDHP path (sm_100a): Ce500NonLinear wrapper + surrogate 6-DOF plant + IDHPnonlin agent,
+// fused into one persistent kernel, one aircraft+agent per thread.
+//
+// Round-1 layout: correctness first.  The per-agent state is ~320 scalars (4-10-{1,3} nets, traces,
+// 4x4 RLS covariance, 12 plant states), more than the 255-register budget, so ptxas keeps part of the
+// network weights in thread-local memory (L1-resident); DESIGN.md section 6 discusses the shared-memory
+// / lane-split layout planned for the next round.
+//
+// Arithmetic: built with -fmad=false, FMAs explicit; numpy-side `@` orders as measured for these
+// shapes, TensorFlow-side `@` in-order chains, tanh = t13.
+#include "rl4_math.cuh"
+#include "rl4_runtime.h"
+#include "../../include/rl4afcs_b200.h"
+#include <cstring>
+
+namespace rl4 {
+
+template <bool PER_AGENT>
+struct NlHp {
+    const rl4_nl_params& p;
+    int64_t i;
+    __device__ __forceinline__ double hp(int idx) const {
+        if (PER_AGENT) { const double* a = p.hp_agent[idx]; if (a) return __ldg(a + i); }
+        return p.hp[idx];
+    }
+    __device__ __forceinline__ int hpi(int idx) const {
+        if (PER_AGENT) { const int32_t* a = p.hpi_agent[idx]; if (a) return __ldg(a + i); }
+        return p.hpi[idx];
+    }
+};
+
+template <typename TN> __device__ __forceinline__ TN nfma(TN a, TN b, TN c);
+template <> __device__ __forceinline__ float nfma<float>(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+template <> __device__ __forceinline__ double nfma<double>(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float nsqrt(float a) { return sqrt_rn(Rn<float>(a)).v; }
+__device__ __forceinline__ double nsqrt(double a) { return sqrt_rn(Rn<double>(a)).v; }
+
+// hidden layer of a 4-10-k net (Network.base_call, objects.py:111-139)
+template <typename TN>
+__device__ __forceinline__ void nl_hidden(const TN (&s)[4], const TN* __restrict__ W1, TN (&h)[10])
+{
+    Rn<TN> pre[10], out[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        TN acc = s[0] * W1[j];
+#pragma unroll
+        for (int i = 1; i < 4; ++i) acc = nfma<TN>(s[i], W1[i * 10 + j], acc);
+        pre[j] = Rn<TN>(acc);
+    }
+    tanh_t13_n<10>(pre, out);
+#pragma unroll
+    for (int j = 0; j < 10; ++j) h[j] = out[j].v;
+}
+
+// Actor_big.call (objects.py:374-407): forward + trace update
+template <typename TN>
+__device__ __forceinline__ TN nl_actor(const TN (&s)[4], const TN* __restrict__ W1, const TN* __restrict__ W2, double* __restrict__ Ea,
+                                       int elig, double gl, TN (&h)[10], TN& ai1)
+{
+    nl_hidden<TN>(s, W1, h);
+    TN o = h[0] * W2[0];
+#pragma unroll
+    for (int j = 1; j < 10; ++j) o = nfma<TN>(h[j], W2[j], o);
+    const TN a = tanh_t13(Rn<TN>(o)).v;
+    ai1 = TN(1) - a * a;
+    if (elig == RL4_ELIG_REPLACING) {
+        double ng = 0.0, ne = 0.0;
+        for (int j = 0; j < 10; ++j) { const double g = (double)(ai1 * h[j]); ng = __fma_rn(g, g, ng); ne = __fma_rn(Ea[j], Ea[j], ne); }
+        for (int j = 0; j < 10; ++j) {
+            const TN v = (ai1 * W2[j]) * (TN(1) - h[j] * h[j]);
+            for (int i = 0; i < 4; ++i) { const double g = (double)(v * s[i]); ng = __fma_rn(g, g, ng); ne = __fma_rn(Ea[10 + j * 4 + i], Ea[10 + j * 4 + i], ne); }
+        }
+        const bool take = sqrt_rn(Rn<double>(ng)).v > sqrt_rn(Rn<double>(ne)).v;
+        for (int j = 0; j < 10; ++j) {
+            Ea[j] = take ? (double)(ai1 * h[j]) : Ea[j] * gl;
+            const TN v = (ai1 * W2[j]) * (TN(1) - h[j] * h[j]);
+            for (int i = 0; i < 4; ++i) Ea[10 + j * 4 + i] = take ? (double)(v * s[i]) : Ea[10 + j * 4 + i] * gl;
+        }
+    } else {
+        const bool acc = (elig == RL4_ELIG_ACCUMULATING);
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+            const double g = (double)(ai1 * h[j]);                            // objects.py:385
+            Ea[j] = acc ? (Ea[j] * gl + g) : g;
+            const TN v = (ai1 * W2[j]) * (TN(1) - h[j] * h[j]);               // objects.py:386
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double gi = (double)(v * s[i]);
+                Ea[10 + j * 4 + i] = acc ? (Ea[10 + j * 4 + i] * gl + gi) : gi;
+            }
+        }
+    }
+    return a;
+}
+
+// Ce500NonLinear.step without the agent (envs/nonlinear/env.py:182-256)
+template <bool PER_AGENT>
+__device__ __forceinline__ void nl_env_step(const rl4_nl_params& p, const NlHp<PER_AGENT>& hv, int stepp, double theta_ref_k,
+                                            const double (&act)[3], double (&x)[12], double (&x_act)[3], double (&surf)[3],
+                                            double& e_phi, double& e_th, double& e_psi, double& reward, double& rg2)
+{
+    const int fault_step = hv.hpi(RL4_NHPI_FAULT_STEP);
+    const bool faulted = (fault_step >= 0 && stepp >= fault_step);                 // env.py:132,151
+    const int damp = hv.hpi(RL4_NHPI_FAULT_DAMP), sat = hv.hpi(RL4_NHPI_FAULT_SAT);
+    const double omega = (faulted && damp == RL4_NL_SLOW_ALL && stepp > fault_step) ? p.omega_slow : p.omega0;
+    double eff[11];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) eff[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double hi = p.limit_deg[i], lo = -p.limit_deg[i];
+        double v = act[i] * (hi - lo) / 2.0;                                       // _scale_action env.py:111-124
+        v = v + (hi + lo) / 2.0;
+        const double cmd = v * (3.14159265358979323846 / 180.0);
+        double d = cmd - x_act[i];                                                 // _propagate_surfaces_states env.py:161-180
+        d = d * omega;
+        d = d < -p.rate_limit ? -p.rate_limit : (d > p.rate_limit ? p.rate_limit : d);
+        x_act[i] = x_act[i] + p.dt * d;
+        surf[i] = x_act[i];
+    }
+    if (faulted && sat != RL4_NL_SAT_NONE) {                                       // _saturate_surfaces env.py:150-159
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (sat - 1 == j) { const double L = p.sat_limit[j]; surf[j] = surf[j] < -L ? -L : (surf[j] > L ? L : surf[j]); }
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) eff[i] = surf[i];
+    if (faulted) {                                                                 // _engage_fault env.py:129-148
+        const double f = hv.hp(RL4_NHP_DAMP_FACTOR);
+        if (damp == RL4_NL_DAMP_ELEVATOR || damp == RL4_NL_DAMP_ALL) eff[0] *= f;
+        if (damp == RL4_NL_DAMP_AILERON || damp == RL4_NL_DAMP_ALL) eff[1] *= f;
+        if (damp == RL4_NL_DAMP_RUDDER || damp == RL4_NL_DAMP_ALL) eff[2] *= f;
+        if (damp == RL4_NL_SHIFT_CG) eff[10] = hv.hp(RL4_NHP_CG_SHIFT);
+    }
+    double u[11];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) u[i] = p.trim_input[i] + eff[i];                  // env.py:207-208
+    if (p.integrator == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(&p.plant, x, u, p.dt);
+    else rl4_cit_step_ode5(&p.plant, x, u, p.dt);                                  // env.py:210
+    const double Q = hv.hp(RL4_NHP_Q_SYM);
+    e_phi = x[6] - 0.0; e_th = x[7] - theta_ref_k; e_psi = x[8] - 0.0;            // env.py:215 (state - ref)
+    reward = (-0.5 * Q) * (e_th * e_th);                                           // env.py:218
+    rg2 = (-Q) * e_th;                                                             // env.py:219-220 (q slot)
+}
+
+__device__ __forceinline__ double nl_decay(double a, double b, double c, bool f32)
+{   // objects.py:1235-1243, numpy-1.x promotion: float64 intermediates, network-dtype result
+    double r = b / a;
+    r = c + (1.0 - c) * r;
+    const double a2 = a * (0.998 + (1.0 - 0.998) * b / a);
+    const double v = a2 * r;
+    return f32 ? (double)(float)v : v;
+}
+__device__ __forceinline__ bool nl_isclose(double a, double b) { return fabs(a - b) <= (1e-8 + 1e-5 * fabs(b)); }
+
+template <typename TN, bool PER_AGENT, bool LOG>
+__global__ void __launch_bounds__(128)
+nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict__ theta_ref, const float* __restrict__ noise,
+              int64_t noise_stride, int k0, int n_steps, const rl4_nl_state st, int64_t n_agents, const rl4_sp_log lg)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_agents) return;
+    const NlHp<PER_AGENT> hv{p, i};
+    const int64_t S = st.stride;
+    double* __restrict__ E = st.env + i;
+    TN* __restrict__ Nn = (TN*)st.net + i;
+    int32_t* __restrict__ I = st.ints + i;
+#define EF(f) E[(int64_t)(f) * S]
+#define NF(f) Nn[(int64_t)(f) * S]
+
+    // ---- load ----
+    double x[12], x_act[3], x_lon[3], x_prev_lon[3], th[12], cv[16], Ea[50], eps[3];
+    TN s[4], s_prev[4], W1a[40], W2a[10], W1c[40], W2c[30], W1t[40], W2t[30], Mp[9];
+    for (int j = 0; j < 12; ++j) { x[j] = EF(RL4_NLE_XFULL + j); th[j] = EF(RL4_NLE_THETA + j); }
+    for (int j = 0; j < 3; ++j) { x_act[j] = EF(RL4_NLE_XACT + j); x_lon[j] = EF(RL4_NLE_XLON + j); x_prev_lon[j] = EF(RL4_NLE_XPREVLON + j); eps[j] = EF(RL4_NLE_EPS + j); }
+    for (int j = 0; j < 16; ++j) cv[j] = EF(RL4_NLE_COV + j);
+    for (int j = 0; j < 50; ++j) Ea[j] = EF(RL4_NLE_EA + j);
+    double cgp2 = EF(RL4_NLE_CGRAD_PREV), eps_norm = EF(RL4_NLE_EPS_NORM), rse0 = EF(RL4_NLE_RSE), rse1 = EF(RL4_NLE_RSE + 1);
+    double nz_peak = EF(RL4_NLE_NZ_PEAK), eta_a = EF(RL4_NLE_ETA_A), eta_c = EF(RL4_NLE_ETA_C), lambdaa = EF(RL4_NLE_LAMBDAA), gl = EF(RL4_NLE_GL);
+    for (int j = 0; j < 4; ++j) { s[j] = NF(RL4_NLN_S + j); s_prev[j] = NF(RL4_NLN_SPREV + j); }
+    TN a = NF(RL4_NLN_A), a_prev = NF(RL4_NLN_APREV), lr_a = NF(RL4_NLN_LR_A), lr_c = NF(RL4_NLN_LR_C);
+    for (int j = 0; j < 40; ++j) { W1a[j] = NF(RL4_NLN_W1A + j); W1c[j] = NF(RL4_NLN_W1C + j); W1t[j] = NF(RL4_NLN_W1T + j); }
+    for (int j = 0; j < 10; ++j) W2a[j] = NF(RL4_NLN_W2A + j);
+    for (int j = 0; j < 30; ++j) { W2c[j] = NF(RL4_NLN_W2C + j); W2t[j] = NF(RL4_NLN_W2T + j); }
+    for (int j = 0; j < 9; ++j) Mp[j] = NF(RL4_NLN_MPREV + j);
+    int cooldown = I[(int64_t)RL4_NLI_COOLDOWN * S], diverged_step = I[(int64_t)RL4_NLI_DIVERGED_STEP * S], stepp = I[(int64_t)RL4_NLI_STEPP * S];
+
+    const bool logged = LOG && i < lg.n_agents_logged;
+    const bool f32 = sizeof(TN) == 4;
+    int k = k0;
+    for (; k < k0 + n_steps; ++k) {
+        if (diverged_step >= 0) break;                                             // objects.py:1557
+        const TN a_k = a;
+        // ---- env.step(self._get_action(a))  (objects.py:1497, 1448-1455)
+        const double act[3] = {(double)a_k, 0.0, 0.0};
+        double surf[3], e_phi, e_th, e_psi, reward, rg2;
+        nl_env_step<PER_AGENT>(p, hv, stepp, __ldg(theta_ref + k), act, x, x_act, surf, e_phi, e_th, e_psi, reward, rg2);
+        stepp += 1;
+        const double x_next_lon[3] = {x[4], x[7], x[1]};                           // env.py:231
+        bool nans = false;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) nans |= (x[j] != x[j]);
+        rse0 += nsqrt(e_th * e_th);                                                // env.py:251; objects.py:1503-1504
+        rse1 += nsqrt(e_phi * e_phi + e_psi * e_psi);
+        { const double nz = x[3] * x[1] / 9.80665; if (nz > nz_peak) nz_peak = nz; }
+        TN s_next[4] = {(TN)x[4], (TN)x[7], (TN)x[1], (TN)e_th};                   // env.py:236-238; objects.py:1499
+
+        // ---- _step_networks (objects.py:1292-1348)
+        TN hc[10], ht[10], lam[3], lt[3];
+        nl_hidden<TN>(s_prev, W1c, hc);                                            // critic(s_prev)
+        nl_hidden<TN>(s_next, W1t, ht);                                            // target_critic(s_next)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            TN acc = hc[0] * W2c[q], acc2 = ht[0] * W2t[q];
+#pragma unroll
+            for (int j = 1; j < 10; ++j) { acc = nfma<TN>(hc[j], W2c[j * 3 + q], acc); acc2 = nfma<TN>(ht[j], W2t[j * 3 + q], acc2); }
+            lam[q] = acc; lt[q] = acc2;
+        }
+        const int elig_a = hv.hpi(RL4_NHPI_ELIG_A);
+        TN ha[10], ai1;
+        const TN a_next = nl_actor<TN>(s_prev, W1a, W2a, Ea, elig_a, gl, ha, ai1); // actor(s_prev), trace pass 1
+        TN dads[4];                                                                // tape.gradient(a, s_prev) (objects.py:1323)
+        {
+            const TN g_o = TN(1) * ai1;
+            TN gp[10];
+#pragma unroll
+            for (int j = 0; j < 10; ++j) gp[j] = (g_o * W2a[j]) * (TN(1) - ha[j] * ha[j]);
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+                TN acc = gp[0] * W1a[ii * 10];
+#pragma unroll
+                for (int j = 1; j < 10; ++j) acc = nfma<TN>(gp[j], W1a[ii * 10 + j], acc);
+                dads[ii] = acc;
+            }
+        }
+        TN M[9], Gn[3];                                                            // objects.py:1327-1329
+#pragma unroll
+        for (int ii = 0; ii < 3; ++ii) Gn[ii] = (TN)th[9 + ii];
+#pragma unroll
+        for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) M[ii * 3 + j] = (TN)th[j * 3 + ii] + Gn[ii] * dads[j];
+
+        if (k > 0) {
+            // ---- _update_networks (objects.py:1350-1399)
+            const double gamma_d = hv.hp(RL4_NHP_GAMMA);
+            const TN gam = (TN)gamma_d;
+            const double rg[3] = {0.0, 0.0, rg2};
+            TN td[3];
+            if (hv.hpi(RL4_NHPI_MULTISTEP)) {                                      // objects.py:1360 (Q14)
+                const double gc[3] = {gamma_d * rg[0], gamma_d * rg[1], gamma_d * rg[2]};
+                const TN g2 = (TN)hv.hp(RL4_NHP_GAMMA_SQ);
+                const TN gl3[3] = {g2 * lt[0], g2 * lt[1], g2 * lt[2]};
+                TN V[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { TN acc = gl3[0] * M[j]; acc = nfma<TN>(gl3[1], M[3 + j], acc); acc = nfma<TN>(gl3[2], M[6 + j], acc); V[j] = acc; }
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    double t1 = gc[0] * (double)Mp[j];                             // numpy f64 (1,3)@(3,3)
+                    t1 = __fma_rn(gc[1], (double)Mp[3 + j], t1);
+                    t1 = __fma_rn(gc[2], (double)Mp[6 + j], t1);
+                    TN t2 = V[0] * Mp[j]; t2 = nfma<TN>(V[1], Mp[3 + j], t2); t2 = nfma<TN>(V[2], Mp[6 + j], t2);
+                    const TN cgp = (j == 2) ? (TN)cgp2 : TN(0);
+                    td[j] = ((lam[j] - cgp) - (TN)t1) - t2;
+                }
+            } else {                                                               // objects.py:1362
+                const TN gl3[3] = {gam * lt[0], gam * lt[1], gam * lt[2]};
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    TN acc = gl3[0] * M[j]; acc = nfma<TN>(gl3[1], M[3 + j], acc); acc = nfma<TN>(gl3[2], M[6 + j], acc);
+                    td[j] = (lam[j] - (TN)rg[j]) - acc;
+                }
+            }
+            {   // critic VJP (tape.gradient with output_gradients = td, objects.py:1365) + SGD (:1368)
+                TN dpre[10];
+#pragma unroll
+                for (int j = 0; j < 10; ++j) {
+                    TN dh = td[0] * W2c[j * 3];
+                    dh = nfma<TN>(td[1], W2c[j * 3 + 1], dh);
+                    dh = nfma<TN>(td[2], W2c[j * 3 + 2], dh);
+                    dpre[j] = dh * (TN(1) - hc[j] * hc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 10; ++j)
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) W2c[j * 3 + q] = W2c[j * 3 + q] - lr_c * (hc[j] * td[q]);
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) W1c[ii * 10 + j] = W1c[ii * 10 + j] - lr_c * (s_prev[ii] * dpre[j]);
+            }
+            {   // target soft update (objects.py:1371)
+                const double tau_d = hv.hp(RL4_NHP_TAU);
+                const TN omt = (TN)(1.0 - tau_d), tt = (TN)tau_d;
+#pragma unroll
+                for (int j = 0; j < 40; ++j) W1t[j] = omt * W1t[j] + tt * W1c[j];
+#pragma unroll
+                for (int j = 0; j < 30; ++j) W2t[j] = omt * W2t[j] + tt * W2c[j];
+            }
+            {   // actor (objects.py:1375-1388): one N(0,1) draw, second trace pass at s_random, smoothness terms
+                const TN nz = (TN)__ldg(noise + (int64_t)(k - k0) * noise_stride + i);
+                TN s_rand[4];
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) s_rand[ii] = nz * (TN)p.noise_std[ii] + s_prev[ii];
+                TN hr[10], ai1r;
+                const TN a_random = nl_actor<TN>(s_rand, W1a, W2a, Ea, elig_a, gl, hr, ai1r);
+                const TN dT = a_k - a_next, dS = a_k - a_random;
+                const TN L_T = nsqrt(dT * dT), L_S = nsqrt(dS * dS);
+                TN v[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) v[j] = -((TN)rg[j] + gam * lt[j]);
+                TN acc = v[0] * Gn[0]; acc = nfma<TN>(v[1], Gn[1], acc); acc = nfma<TN>(v[2], Gn[2], acc);
+                const TN loss = (acc + (TN)hv.hp(RL4_NHP_LAMBDA_T) * L_T) + (TN)hv.hp(RL4_NHP_LAMBDA_S) * L_S;
+#pragma unroll
+                for (int j = 0; j < 10; ++j) W2a[j] = W2a[j] - lr_a * (loss * (TN)Ea[j]);      // objects.py:417-427
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) W1a[ii * 10 + j] = W1a[ii * 10 + j] - lr_a * (loss * (TN)Ea[10 + j * 4 + ii]);
+            }
+            {   // RLS, n = 3, m = 1 (objects.py:1521-1524, 492-543)
+                double Xr[4], Y[3];
+#pragma unroll
+                for (int ii = 0; ii < 3; ++ii) { Xr[ii] = x_lon[ii] - x_prev_lon[ii]; Y[ii] = x_next_lon[ii] - x_lon[ii]; }
+                Xr[3] = (double)(a_k - a_prev);
+#pragma unroll
+                for (int ii = 0; ii < 3; ++ii) {                                   // params.T @ X: fma(0,1) + fma(2,3)
+                    const double pred = __dadd_rn(__fma_rn(th[ii], Xr[0], __dmul_rn(th[3 + ii], Xr[1])),
+                                                  __fma_rn(th[6 + ii], Xr[2], __dmul_rn(th[9 + ii], Xr[3])));
+                    eps[ii] = Y[ii] - pred;
+                }
+                Rn<double> CX[4], K[4];
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) {                                   // Cov @ X: (p0+p2)+(p1+p3)
+                    const double p0 = cv[ii * 4] * Xr[0], p1 = cv[ii * 4 + 1] * Xr[1], p2 = cv[ii * 4 + 2] * Xr[2], p3 = cv[ii * 4 + 3] * Xr[3];
+                    CX[ii] = Rn<double>((p0 + p2) + (p1 + p3));
+                }
+                double xcx = Xr[0] * CX[0].v;
+#pragma unroll
+                for (int ii = 1; ii < 4; ++ii) xcx = __fma_rn(Xr[ii], CX[ii].v, xcx);
+                const double rgam = hv.hp(RL4_NHP_RLS_GAMMA);
+                div_group<4>(CX, Rn<double>(rgam + xcx), K);
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+#pragma unroll
+                    for (int ii = 0; ii < 3; ++ii) th[t * 3 + ii] = th[t * 3 + ii] + K[t].v * eps[ii];
+                if (rgam == 1.0) {
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) cv[ii * 4 + j] = cv[ii * 4 + j] - K[ii].v * CX[j].v;
+                } else {
+                    Rn<double> num[16], out[16];
+#pragma unroll
+                    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) num[ii * 4 + j] = Rn<double>(cv[ii * 4 + j] - K[ii].v * CX[j].v);
+                    div_group<16>(num, Rn<double>(rgam), out);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) cv[j] = out[j].v;
+                }
+                eps_norm = nsqrt(__fma_rn(eps[2], eps[2], __fma_rn(eps[1], eps[1], eps[0] * eps[0])));
+            }
+            {   // _adapt_check (objects.py:1212-1290)
+                const bool cond1 = k < hv.hpi(RL4_NHPI_WARMUP_STEPS);
+                if (cooldown > 0) cooldown -= 1;
+                if (!cond1) {
+                    const double dec = hv.hp(RL4_NHP_LR_DECAY);
+                    const double eal = hv.hp(RL4_NHP_ETA_A_L), ecl = hv.hp(RL4_NHP_ETA_C_L), ll = hv.hp(RL4_NHP_LAMBDA_L);
+                    eta_a = nl_isclose(eta_a, eal) ? eal : nl_decay(eta_a, eal, dec, f32);
+                    eta_c = nl_isclose(eta_c, ecl) ? ecl : nl_decay(eta_c, ecl, dec, f32);
+                    lambdaa = nl_isclose(lambdaa, ll) ? ll : nl_decay(lambdaa, ll, dec, f32);
+                }
+                const double lambda_gamma = lambdaa * gamma_d;
+                if ((double)lr_a != eta_a && (double)lr_c != eta_c && cooldown <= 0) {
+                    lr_a = (TN)eta_a; lr_c = (TN)eta_c;
+                    gl = lambda_gamma;
+                    cooldown = hv.hpi(RL4_NHPI_COOLDOWN_STEPS);
+                }
+            }
+        }
+        // ---- shift (objects.py:1530-1538)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s_prev[j] = s[j]; s[j] = s_next[j]; }
+        a_prev = a_k; a = a_next;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { x_prev_lon[j] = x_lon[j]; x_lon[j] = x_next_lon[j]; }
+        cgp2 = rg2;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) Mp[j] = M[j];
+        if (nans) diverged_step = k;
+        if (LOG) {
+            if (logged && (k - k0) % lg.every == 0) {
+                double* b = lg.buf + ((int64_t)((k - k0) / lg.every) * RL4_NLL_COUNT) * lg.n_agents_logged + i;
+                const int64_t L = lg.n_agents_logged;
+                for (int j = 0; j < 12; ++j) b[(int64_t)(RL4_NLL_XFULL + j) * L] = x[j];
+                b[(int64_t)RL4_NLL_A * L] = (double)a_next; b[(int64_t)RL4_NLL_E_THETA * L] = e_th; b[(int64_t)RL4_NLL_REWARD * L] = reward;
+                for (int j = 0; j < 3; ++j) b[(int64_t)(RL4_NLL_SURF + j) * L] = surf[j];
+            }
+        }
+    }
+    if (LOG) {
+        if (logged) {
+            for (; k < k0 + n_steps; ++k) {
+                if ((k - k0) % lg.every) continue;
+                double* b = lg.buf + ((int64_t)((k - k0) / lg.every) * RL4_NLL_COUNT) * lg.n_agents_logged + i;
+                for (int f = 0; f < RL4_NLL_COUNT; ++f) b[(int64_t)f * lg.n_agents_logged] = __longlong_as_double(0x7ff8000000000000LL);
+            }
+        }
+    }
+
+    // ---- store ----
+    for (int j = 0; j < 12; ++j) { EF(RL4_NLE_XFULL + j) = x[j]; EF(RL4_NLE_THETA + j) = th[j]; }
+    for (int j = 0; j < 3; ++j) { EF(RL4_NLE_XACT + j) = x_act[j]; EF(RL4_NLE_XLON + j) = x_lon[j]; EF(RL4_NLE_XPREVLON + j) = x_prev_lon[j]; EF(RL4_NLE_EPS + j) = eps[j]; }
+    for (int j = 0; j < 16; ++j) EF(RL4_NLE_COV + j) = cv[j];
+    for (int j = 0; j < 50; ++j) EF(RL4_NLE_EA + j) = Ea[j];
+    EF(RL4_NLE_CGRAD_PREV) = cgp2; EF(RL4_NLE_EPS_NORM) = eps_norm; EF(RL4_NLE_RSE) = rse0; EF(RL4_NLE_RSE + 1) = rse1;
+    EF(RL4_NLE_NZ_PEAK) = nz_peak; EF(RL4_NLE_ETA_A) = eta_a; EF(RL4_NLE_ETA_C) = eta_c; EF(RL4_NLE_LAMBDAA) = lambdaa; EF(RL4_NLE_GL) = gl;
+    for (int j = 0; j < 4; ++j) { NF(RL4_NLN_S + j) = s[j]; NF(RL4_NLN_SPREV + j) = s_prev[j]; }
+    NF(RL4_NLN_A) = a; NF(RL4_NLN_APREV) = a_prev; NF(RL4_NLN_LR_A) = lr_a; NF(RL4_NLN_LR_C) = lr_c;
+    for (int j = 0; j < 40; ++j) { NF(RL4_NLN_W1A + j) = W1a[j]; NF(RL4_NLN_W1C + j) = W1c[j]; NF(RL4_NLN_W1T + j) = W1t[j]; }
+    for (int j = 0; j < 10; ++j) NF(RL4_NLN_W2A + j) = W2a[j];
+    for (int j = 0; j < 30; ++j) { NF(RL4_NLN_W2C + j) = W2c[j]; NF(RL4_NLN_W2T + j) = W2t[j]; }
+    for (int j = 0; j < 9; ++j) NF(RL4_NLN_MPREV + j) = Mp[j];
+    I[(int64_t)RL4_NLI_COOLDOWN * S] = cooldown; I[(int64_t)RL4_NLI_DIVERGED_STEP * S] = diverged_step; I[(int64_t)RL4_NLI_STEPP * S] = stepp;
+#undef EF
+#undef NF
+}
+
+// Ce500NonLinear.reset + IDHPnonlin prologue
+template <typename TN>
+__global__ void __launch_bounds__(128)
+nl_init_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict__ w1a, const double* __restrict__ w2a,
+               const double* __restrict__ w1c, const double* __restrict__ w2c, int64_t stride_in, const rl4_nl_state st, int64_t n_agents)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_agents) return;
+    const NlHp<true> hv{p, i};
+    const int64_t S = st.stride;
+    double* E = st.env + i;
+    TN* Nn = (TN*)st.net + i;
+    for (int f = 0; f < RL4_NLE_COUNT; ++f) E[(int64_t)f * S] = 0.0;
+    for (int f = 0; f < RL4_NLN_COUNT; ++f) Nn[(int64_t)f * S] = TN(0);
+    // reset: the model's built-in initial state, then 1000 + 1 steps at trim input (env.py:278-291)
+    double x[12] = {0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0};
+    const int n_trim = (int)(10.0 / p.dt) + 1;
+    for (int k = 0; k < n_trim; ++k) {
+        if (p.integrator == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(&p.plant, x, p.trim_input, p.dt);
+        else rl4_cit_step_ode5(&p.plant, x, p.trim_input, p.dt);
+    }
+    for (int j = 0; j < 12; ++j) E[(int64_t)(RL4_NLE_XFULL + j) * S] = x[j];
+    const double c0 = hv.hp(RL4_NHP_RLS_COV0);
+    for (int d = 0; d < 4; ++d) E[(int64_t)(RL4_NLE_COV + d * 5) * S] = c0;
+    E[(int64_t)RL4_NLE_ETA_A * S] = hv.hp(RL4_NHP_ETA_A_H);
+    E[(int64_t)RL4_NLE_ETA_C * S] = hv.hp(RL4_NHP_ETA_C_H);
+    E[(int64_t)RL4_NLE_LAMBDAA * S] = hv.hp(RL4_NHP_LAMBDA_H);
+    E[(int64_t)RL4_NLE_GL * S] = hv.hp(RL4_NHP_GAMMA) * hv.hp(RL4_NHP_LAMBDA_H);
+    for (int j = 0; j < 40; ++j) {
+        const TN wa = (TN)w1a[j * stride_in + i], wc = (TN)w1c[j * stride_in + i];
+        Nn[(int64_t)(RL4_NLN_W1A + j) * S] = wa; Nn[(int64_t)(RL4_NLN_W1C + j) * S] = wc; Nn[(int64_t)(RL4_NLN_W1T + j) * S] = wc;
+    }
+    for (int j = 0; j < 10; ++j) Nn[(int64_t)(RL4_NLN_W2A + j) * S] = (TN)w2a[j * stride_in + i];
+    for (int j = 0; j < 30; ++j) { const TN wc = (TN)w2c[j * stride_in + i]; Nn[(int64_t)(RL4_NLN_W2C + j) * S] = wc; Nn[(int64_t)(RL4_NLN_W2T + j) * S] = wc; }
+    Nn[(int64_t)RL4_NLN_LR_A * S] = (TN)hv.hp(RL4_NHP_ETA_A_H);
+    Nn[(int64_t)RL4_NLN_LR_C * S] = (TN)hv.hp(RL4_NHP_ETA_C_H);
+    st.ints[(int64_t)RL4_NLI_COOLDOWN * S + i] = 0;
+    st.ints[(int64_t)RL4_NLI_DIVERGED_STEP * S + i] = -1;
+    st.ints[(int64_t)RL4_NLI_STEPP * S + i] = 0;
+}
+
+__global__ void __launch_bounds__(128)
+nl_env_step_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict__ theta_ref, int stepp, double* __restrict__ x_full,
+                   double* __restrict__ x_act_p, const double* __restrict__ action, double* __restrict__ out_mdp,
+                   double* __restrict__ out_reward, double* __restrict__ out_e, int64_t S, int64_t n_agents)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_agents) return;
+    const NlHp<true> hv{p, i};
+    double x[12], xa[3], act[3], surf[3], e_phi, e_th, e_psi, reward, rg2;
+    for (int j = 0; j < 12; ++j) x[j] = x_full[j * S + i];
+    for (int j = 0; j < 3; ++j) { xa[j] = x_act_p[j * S + i]; act[j] = action[j * S + i]; }
+    nl_env_step<true>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2);
+    for (int j = 0; j < 12; ++j) x_full[j * S + i] = x[j];
+    for (int j = 0; j < 3; ++j) x_act_p[j * S + i] = xa[j];
+    out_mdp[i] = x[4]; out_mdp[S + i] = x[7]; out_mdp[2 * S + i] = x[1]; out_mdp[3 * S + i] = e_th;
+    out_reward[i] = reward; out_e[i] = e_th;
+}
+
+}  // namespace rl4
+
+using namespace rl4;
+
+extern "C" {
+
+int rl4_nl_default_params(rl4_nl_params* p)
+{
+    RL4_REQUIRE(p != nullptr, "p is NULL");
+    memset(p, 0, sizeof(*p));
+    rl4_cit_default_params(&p->plant);
+    const double trim[11] = {-0.02855, 0, 0, 0, 0, 0, 0, 0, 0.55, 0.55, 0};       // idhp_nonlin.py:53
+    for (int i = 0; i < 11; ++i) p->trim_input[i] = trim[i];
+    p->dt = 0.01;                                                                   // idhp_nonlin.py:36
+    p->hp[RL4_NHP_ETA_A_H] = 35.0; p->hp[RL4_NHP_ETA_A_L] = 5.0; p->hp[RL4_NHP_ETA_C_H] = 1.4; p->hp[RL4_NHP_ETA_C_L] = 0.7;
+    p->hp[RL4_NHP_LAMBDA_H] = 0.95; p->hp[RL4_NHP_LAMBDA_L] = 0.95; p->hp[RL4_NHP_GAMMA] = 0.6; p->hp[RL4_NHP_GAMMA_SQ] = 0.36;
+    p->hp[RL4_NHP_TAU] = 0.02; p->hp[RL4_NHP_LR_DECAY] = 0.998; p->hp[RL4_NHP_RLS_GAMMA] = 1.0; p->hp[RL4_NHP_RLS_COV0] = 1e6;
+    p->hp[RL4_NHP_Q_SYM] = 2.0; p->hp[RL4_NHP_LAMBDA_T] = 0.012; p->hp[RL4_NHP_LAMBDA_S] = 0.001;   // idhp_nonlin.py:123-146; objects.py:1383
+    p->hp[RL4_NHP_DAMP_FACTOR] = 0.3; p->hp[RL4_NHP_CG_SHIFT] = -0.5;              // envs/nonlinear/env.py:135-143
+    p->noise_std[0] = 0.010; p->noise_std[1] = 0.010; p->noise_std[2] = 0.008; p->noise_std[3] = 0.003;   // objects.py:1377
+    const double d2r = 3.14159265358979323846 / 180.0;
+    p->omega0 = 13.0; p->omega_slow = 6.0; p->rate_limit = 19.7 * d2r;             // envs/nonlinear/env.py:74,145,177
+    p->limit_deg[0] = 15.0; p->limit_deg[1] = 37.0; p->limit_deg[2] = 22.0;        // envs/nonlinear/env.py:107-109
+    p->sat_limit[0] = 5.0 * d2r; p->sat_limit[1] = 18.0 * d2r; p->sat_limit[2] = 10.0 * d2r;
+    p->hpi[RL4_NHPI_MULTISTEP] = 0; p->hpi[RL4_NHPI_WARMUP_STEPS] = 400; p->hpi[RL4_NHPI_COOLDOWN_STEPS] = 200;
+    p->hpi[RL4_NHPI_FAULT_STEP] = -1; p->hpi[RL4_NHPI_FAULT_DAMP] = 0; p->hpi[RL4_NHPI_FAULT_SAT] = 0;
+    p->hpi[RL4_NHPI_ELIG_A] = RL4_ELIG_ACCUMULATING;
+    p->integrator = RL4_CIT_INTEGRATOR_ODE5;
+    return 0;
+}
+
+int rl4_nl_init(int policy, const rl4_nl_params* p, const double* w1a, const double* w2a, const double* w1c, const double* w2c,
+                int64_t stride_in, rl4_nl_state st, int64_t n, void* stream)
+{
+    RL4_REQUIRE(p && w1a && w2a && w1c && w2c && st.env && st.net && st.ints, "NULL argument");
+    RL4_REQUIRE(n >= 0 && stride_in >= n && st.stride >= n, "bad size");
+    if (n == 0) return 0;
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (policy == RL4_MIXED) nl_init_kernel<float><<<grid, 128, 0, s>>>(*p, w1a, w2a, w1c, w2c, stride_in, st, n);
+    else if (policy == RL4_FP64) nl_init_kernel<double><<<grid, 128, 0, s>>>(*p, w1a, w2a, w1c, w2c, stride_in, st, n);
+    else { set_error("rl4_nl_init: policy %d not supported on the nonlinear path (mixed or fp64)", policy); return -1; }
+    return check_launch("nl_init_kernel");
+}
+
+int rl4_nl_run(int policy, const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride,
+               int32_t k0, int32_t n_steps, rl4_nl_state st, int64_t n, rl4_sp_log lg, void* stream)
+{
+    RL4_REQUIRE(p && theta_ref && noise && st.env && st.net && st.ints, "NULL argument");
+    RL4_REQUIRE(n >= 0 && st.stride >= n && noise_stride >= n && k0 >= 0 && n_steps >= 0, "bad size");
+    if (lg.level != RL4_LOG_NONE) RL4_REQUIRE(lg.buf && lg.every >= 1 && lg.n_agents_logged >= 0 && lg.n_agents_logged <= n, "bad log descriptor");
+    if (n == 0 || n_steps == 0) return 0;
+    bool per_agent = false;
+    for (int j = 0; j < RL4_NHP_COUNT; ++j) per_agent |= (p->hp_agent[j] != nullptr);
+    for (int j = 0; j < RL4_NHPI_COUNT; ++j) per_agent |= (p->hpi_agent[j] != nullptr);
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool log = lg.level != RL4_LOG_NONE;
+#define RL4_NL_LAUNCH(TN)                                                                                               \
+    do {                                                                                                                \
+        if (log) nl_run_kernel<TN, true, true><<<grid, 128, 0, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg);        \
+        else if (per_agent) nl_run_kernel<TN, true, false><<<grid, 128, 0, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg); \
+        else nl_run_kernel<TN, false, false><<<grid, 128, 0, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg);          \
+    } while (0)
+    if (policy == RL4_MIXED) RL4_NL_LAUNCH(float);
+    else if (policy == RL4_FP64) RL4_NL_LAUNCH(double);
+    else { set_error("rl4_nl_run: policy %d not supported on the nonlinear path (mixed or fp64)", policy); return -1; }
+#undef RL4_NL_LAUNCH
+    return check_launch("nl_run_kernel");
+}
+
+int rl4_nl_env_step(const rl4_nl_params* p, const double* theta_ref, int32_t stepp, double* x_full, double* x_act,
+                    const double* action, double* out_mdp, double* out_reward, double* out_e_theta, int64_t stride,
+                    int64_t n, void* stream)
+{
+    RL4_REQUIRE(p && theta_ref && x_full && x_act && action && out_mdp && out_reward && out_e_theta, "NULL argument");
+    RL4_REQUIRE(n >= 0 && stride >= n && stepp >= 0, "bad size");
+    if (n == 0) return 0;
+    nl_env_step_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*p, theta_ref, stepp, x_full, x_act, action,
+                                                                                        out_mdp, out_reward, out_e_theta, stride, n);
+    return check_launch("nl_env_step_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+"""Device-side engine of the nonlinear path: SoA state planes, parameters, calls into the C-ABI
+(rl4_nl_init / rl4_nl_run / rl4_nl_env_step)."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import NHP, NHPI, NLE, NLI, NLN
+
+
+def theta_reference(t_end=90, dt=0.01):
+    """Pitch-attitude reference of idhp_nonlin.py:36-48 (trim 0.0576 rad + tapered sine sum for 45 s +
+    ramp / hold 15 deg / ramp)."""
+    n = int(t_end / dt)
+    th = 0.0576 + np.zeros(n)
+    th[:4500] += np.deg2rad(5) * np.sin(2 * np.pi * np.linspace(0, 45, 4500) / 15) * (np.linspace(2.0, 0.8, 4500))
+    th[:4500] += np.deg2rad(4) * np.sin(2 * np.pi * np.linspace(0, 45, 4500) / 30) * (np.linspace(2.0, 0.8, 4500))
+    th[5500:6500] += np.deg2rad(1.5) * np.linspace(0, 10, 1000)
+    th[6500:7500] += np.deg2rad(15)
+    th[7500:8500] += np.deg2rad(1.5) * np.linspace(10, 0, 1000)
+    return th
+
+
+def split_fault(name):
+    """Substring matching of envs/nonlinear/env.py:134-158 (if / elif chains), e.g.
+    'damp_elevator_and_saturate_elevator' (idhp_nonlin.py:75) -> (damp kind, saturation kind)."""
+    name = name or "none"
+    damp = sat = 0
+    for key in ("damp_elevator", "damp_aileron", "damp_rudder", "damp_all", "shift_cg", "slow_all"):
+        if key in name:
+            damp = _lib.NL_DAMP[key]
+            break
+    for key in ("saturate_elevator", "saturate_aileron", "saturate_rudder"):
+        if key in name:
+            sat = _lib.NL_SAT[key]
+            break
+    return damp, sat
+
+
+class NlEngine:
+    def __init__(self, n_agents: int, *, policy: str = "mixed", device="cuda"):
+        if policy not in ("mixed", "fp64"):
+            raise _lib.Rl4Error("the nonlinear path supports the 'mixed' and 'fp64' policies")
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.Rl4Error("rl4afcs_b200 runs on B200 GPUs only (no CPU fallback)")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", idx)
+        _lib.check(self.lib.rl4_device_check(idx), "rl4_device_check")
+        self.n = int(n_agents)
+        self.stride = max(self.n, 1)
+        self.policy = policy
+        self.policy_id = _lib.POLICY[policy]
+        self.tn = torch.float32 if policy == "mixed" else torch.float64
+        self.env = torch.zeros((NLE["COUNT"], self.stride), dtype=torch.float64, device=self.device)
+        self.net = torch.zeros((NLN["COUNT"], self.stride), dtype=self.tn, device=self.device)
+        self.ints = torch.zeros((NLI["COUNT"], self.stride), dtype=torch.int32, device=self.device)
+        self.params = _lib.NlParams()
+        _lib.check(self.lib.rl4_nl_default_params(ctypes.byref(self.params)), "rl4_nl_default_params")
+        self._keep = {}
+        self.theta_ref = None
+        self.k = 0
+
+    def set_hp(self, name, value):
+        j = NHP[name]
+        if np.ndim(value) == 0:
+            self.params.hp[j] = float(value); self.params.hp_agent[j] = None; self._keep.pop(("hp", j), None)
+        else:
+            t = torch.as_tensor(np.asarray(value, dtype=np.float64)).to(self.device).contiguous()
+            assert t.numel() == self.n
+            self._keep[("hp", j)] = t; self.params.hp[j] = float(t[0]); self.params.hp_agent[j] = t.data_ptr()
+
+    def set_hpi(self, name, value):
+        j = NHPI[name]
+        if np.ndim(value) == 0:
+            self.params.hpi[j] = int(value); self.params.hpi_agent[j] = None; self._keep.pop(("hpi", j), None)
+        else:
+            t = torch.as_tensor(np.asarray(value, dtype=np.int32)).to(self.device).contiguous()
+            assert t.numel() == self.n
+            self._keep[("hpi", j)] = t; self.params.hpi[j] = int(t[0]); self.params.hpi_agent[j] = t.data_ptr()
+
+    def set_reference(self, theta_ref):
+        self.theta_ref = torch.as_tensor(np.asarray(theta_ref, dtype=np.float64)).to(self.device).contiguous()
+
+    def state_struct(self):
+        return _lib.NlState(self.env.data_ptr(), self.net.data_ptr(), self.ints.data_ptr(), self.stride)
+
+    def env_field(self, name, count=1):
+        o = NLE[name]
+        return self.env[o:o + count, : self.n]
+
+    def net_field(self, name, count=1):
+        o = NLN[name]
+        return self.net[o:o + count, : self.n]
+
+    def int_field(self, name):
+        return self.ints[NLI[name], : self.n]
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def init(self, W1a, W2a, W1c, W2c):
+        """W1a (n,40) [(4,10) row-major], W2a (n,10), W1c (n,40), W2c (n,30) [(10,3) row-major]."""
+        def plane(v, w):
+            t = torch.as_tensor(np.asarray(v, dtype=np.float64) if not torch.is_tensor(v) else v)
+            return t.to(device=self.device, dtype=torch.float64).reshape(self.n, w).t().contiguous()
+        with torch.cuda.device(self.device):
+            a1, a2, c1, c2 = plane(W1a, 40), plane(W2a, 10), plane(W1c, 40), plane(W2c, 30)
+            rc = self.lib.rl4_nl_init(self.policy_id, ctypes.byref(self.params), a1.data_ptr(), a2.data_ptr(), c1.data_ptr(),
+                                      c2.data_ptr(), self.n, self.state_struct(), self.n, self._stream())
+            _lib.check(rc, "rl4_nl_init")
+        self.k = 0
+
+    def run(self, n_steps, noise, *, log_agents=0, log_every=1):
+        """noise: float32 (n_steps, n_agents) N(0,1) draws (objects.py:1375).  Returns the log
+        (rows, fields, log_agents) or None."""
+        assert self.theta_ref is not None and self.theta_ref.numel() >= self.k + n_steps
+        noise = torch.as_tensor(noise, device=self.device).to(torch.float32).contiguous()
+        assert noise.shape == (n_steps, self.n)
+        lg = _lib.SpLog(None, 0, 1, 0)
+        log_t = None
+        if log_agents:
+            log_agents = min(int(log_agents), self.n)
+            rows = (n_steps + log_every - 1) // log_every
+            log_t = torch.zeros((rows, _lib.NLL["COUNT"], log_agents), dtype=torch.float64, device=self.device)
+            lg = _lib.SpLog(log_t.data_ptr(), 1, log_every, log_agents)
+        with torch.cuda.device(self.device):
+            rc = self.lib.rl4_nl_run(self.policy_id, ctypes.byref(self.params), self.theta_ref.data_ptr(), noise.data_ptr(),
+                                     self.n, self.k, n_steps, self.state_struct(), self.n, lg, self._stream())
+            _lib.check(rc, "rl4_nl_run")
+        self.k += n_steps
+        return log_t
+
+    def stats(self):
+        return {"rse": self.env_field("RSE", 2).t().clone(), "nz_peak": self.env_field("NZ_PEAK")[0].clone(),
+                "diverged": self.int_field("DIVERGED_STEP") >= 0}

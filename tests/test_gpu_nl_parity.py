@@ -1,0 +1,135 @@
+"""GPU parity of the nonlinear path (Ce500NonLinear wrapper + surrogate plant + IDHPnonlin) against the CPU
+oracle (oracle/nl_oracle.c: restatement of envs/nonlinear/env.py:60-311 and objects.py:283-437,1006-1564).
+
+The plant integrates with sin/cos/pow of the respective math library (CUDA vs glibc), so kernel-vs-oracle is a
+tolerance test: teacher-forced per step (state re-seeded from the oracle every step) and a short free run.
+The reference's own plant is a source-less binary: plant parity against the reference is unpinned."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from tests import _util_nl  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def nl(oracle):
+    from oracle import nl_c
+    nl_c.lib()
+    return nl_c
+
+
+def _setup(nl, n, policy, *, seed=0, fault=None, fault_time=60, integrator="ode5", elig="accumulating", ms=0, **over):
+    from rl4afcs_b200 import _lib, nl_engine
+
+    cfg = nl.make_cfg(fault=fault, fault_time=fault_time, integrator=integrator, elig_a=elig, multistep=ms, **over)
+    w = nl.init_weights(n, seed)
+    st = nl.init_states(policy, cfg, w, n)
+    eng = nl_engine.NlEngine(n, policy=policy)
+    damp, sat = nl_engine.split_fault(fault)
+    eng.set_hpi("FAULT_DAMP", damp); eng.set_hpi("FAULT_SAT", sat)
+    eng.set_hpi("FAULT_STEP", int(cfg["fault_step"][0]))
+    eng.set_hpi("ELIG_A", _lib.ELIG[elig]); eng.set_hpi("MULTISTEP", 1 if ms else 0)
+    eng.params.integrator = _lib.INTEGRATOR[integrator]
+    for k, v in over.items():
+        eng.set_hp(k.upper(), v)
+    th = nl.theta_reference()
+    eng.set_reference(th)
+    eng.init(w["W1a"], w["W2a"], w["W1c"], w["W2c"])
+    return eng, st, cfg, th
+
+
+@pytest.mark.parametrize("policy", ["mixed", "fp64"])
+def test_reset_and_prologue(nl, policy):
+    eng, st, cfg, th = _setup(nl, 70, policy)
+    got = _util_nl.engine_to_oracle(eng, nl)
+    assert _util_nl.max_rel(got["x_full"], st["x_full"], 1e-3) < 1e-12          # 1001 trim steps of the plant
+    for f in ("W1a", "W2a", "W1c", "W2c", "W1t", "W2t", "cov", "eta_a", "eta_c", "lambdaa", "lr_a", "lr_c", "gl"):
+        assert np.array_equal(got[f], st[f]), f
+    assert np.array_equal(got["diverged_step"], st["diverged_step"])
+
+
+@pytest.mark.parametrize("policy,case", [
+    ("mixed", dict()),                                                           # idhp_nonlin.py defaults
+    ("fp64", dict()),
+    ("mixed", dict(integrator="rk4", elig=None, ms=1)),
+    ("mixed", dict(fault="damp_elevator_and_saturate_elevator", fault_time=2.0, elig="replacing")),
+    ("fp64", dict(fault="shift_cg", fault_time=1.5, ms=1)),
+    ("mixed", dict(fault="slow_all", fault_time=1.0)),
+])
+def test_teacher_forced_steps(nl, policy, case):
+    n, steps = 48, 450
+    eng, st, cfg, th = _setup(nl, n, policy, seed=3, **case)
+    rng = np.random.default_rng(1)
+    noise = rng.standard_normal((steps, n)).astype(np.float32)
+    worst = {}
+    f32 = policy == "mixed"
+    for k in range(steps):
+        _util_nl.oracle_to_engine(st, eng)
+        eng.k = k
+        nl.run(policy, cfg, th, noise[k:k + 1], st, k, 1, tanh="t13")
+        eng.run(1, noise[k:k + 1])
+        got = _util_nl.engine_to_oracle(eng, nl)
+        for f, floor in (("x_full", 1e-3), ("x_act", 1e-4), ("x_lon", 1e-3), ("theta", 1e-4), ("eps", 1e-6), ("rse", 1e-3),
+                         ("eta_a", 1e-3), ("eta_c", 1e-3), ("lambdaa", 1e-3), ("gl", 1e-3)):
+            worst[f] = max(worst.get(f, 0.0), _util_nl.max_rel(got[f], st[f], floor))
+        worst["cov"] = max(worst.get("cov", 0.0), _util_nl.max_rel(got["cov"], st["cov"], np.abs(st["cov"]).max(axis=1, keepdims=True) * 1e-6))
+        for f, floor in (("s", 1e-3), ("a", 1e-3), ("W1a", 1e-2), ("W2a", 1e-2), ("W1c", 1e-2), ("W2c", 1e-2), ("W1t", 1e-2),
+                         ("W2t", 1e-2), ("M_prev", 1e-2), ("Ea", 1e-2), ("lr_a", 1e-3), ("lr_c", 1e-3)):
+            worst[f] = max(worst.get(f, 0.0), _util_nl.max_rel(got[f], st[f], floor))
+        assert np.array_equal(got["cooldown"], st["cooldown"]) and np.array_equal(got["stepp"], st["stepp"]), k
+        assert np.array_equal(got["diverged_step"], st["diverged_step"]), k
+    tol64 = 1e-9
+    tol_net = 5e-6 if f32 else 1e-9       # a last-bit plant difference can flip one float32 rounding of s
+    for f in ("x_full", "x_act", "x_lon", "rse", "eta_a", "eta_c", "lambdaa", "gl"):
+        assert worst[f] < tol64, (f, worst[f])
+    for f in ("theta", "cov", "eps"):
+        assert worst[f] < (1e-4 if f32 else 1e-7), (f, worst[f])
+    for f in ("s", "a", "W1a", "W2a", "W1c", "W2c", "W1t", "W2t", "M_prev", "Ea", "lr_a", "lr_c"):
+        assert worst[f] < tol_net, (f, worst[f])
+
+
+@pytest.mark.parametrize("policy", ["mixed", "fp64"])
+def test_free_run_tracks_oracle_and_chunking_is_exact(nl, policy):
+    n, steps = 64, 600
+    eng, st, cfg, th = _setup(nl, n, policy, seed=5)
+    rng = np.random.default_rng(2)
+    noise = rng.standard_normal((steps, n)).astype(np.float32)
+    olog = nl.run(policy, cfg, th, noise, st, 0, steps, tanh="t13", n_log=n)
+    lg = eng.run(steps, noise, log_agents=n).cpu().numpy()          # (rows, fields, agents)
+    from rl4afcs_b200 import _lib
+    x_gpu = np.transpose(lg[:, _lib.NLL["XFULL"]:_lib.NLL["XFULL"] + 12, :], (2, 0, 1))
+    # early part of the run: still tightly together
+    assert _util_nl.max_rel(x_gpu[:, :200, :9], olog["x_full"][:, :200, :9], 1e-2) < 1e-6
+    got = _util_nl.engine_to_oracle(eng, nl)
+    assert np.array_equal(got["diverged_step"] >= 0, st["diverged_step"] >= 0)
+    # the same run in chunks gives the same bits (resume exactness on the device)
+    eng2, _, _, _ = _setup(nl, n, policy, seed=5)
+    k = 0
+    for chunk in (1, 7, 92, 500):
+        eng2.run(chunk, noise[k:k + chunk]); k += chunk
+    same = lambda u, v: bool(((u == v) | (torch.isnan(u) & torch.isnan(v))).all())   # noqa: E731
+    assert same(eng.env, eng2.env) and same(eng.net, eng2.net) and torch.equal(eng.ints, eng2.ints)
+
+
+def test_agents_learn_to_track_on_the_surrogate(nl):
+    """Sanity of the whole loop on the GPU: with the reference's hyper-parameters (idhp_nonlin.py:123-146) most
+    agents survive the 90 s episode on the surrogate plant and end with a small pitch-tracking error."""
+    n, steps = 256, 9000
+    eng, st, cfg, th = _setup(nl, n, "mixed", seed=8)
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    e_last = None
+    for k0 in range(0, steps, 1500):
+        noise = torch.randn((1500, n), generator=g, device="cuda", dtype=torch.float32)
+        lg = eng.run(1500, noise, log_agents=n)
+        e_last = lg[:, eng_field("E_THETA"), :]
+    alive = ~eng.stats()["diverged"]
+    assert alive.float().mean() > 0.8
+    rms = torch.sqrt((e_last[-1000:] ** 2).mean(dim=0))[alive]
+    assert torch.rad2deg(rms.median()) < 3.0
+
+
+def eng_field(name):
+    from rl4afcs_b200 import _lib
+    return _lib.NLL[name]
