@@ -349,6 +349,167 @@ class IDHPsp:
         return self._eng.stats(self._steps)["diverged"]
 
 
+# ------------------------------------------------------------------------------------------
+class _BigNetView:
+    """Read / write view of a 4-10-k net of the nonlinear agent (Critic_big / Actor_big,
+    objects.py:283-437): ``trainable_weights`` = [W1 (B,4,10), W2 (B,10,k)]."""
+
+    def __init__(self, engine, w1, w2, n_out, eligibility):
+        self._eng, self._w1, self._w2, self._n_out = engine, w1, w2, n_out
+        self.eligibility = eligibility
+        self.batch = engine.n
+
+    @property
+    def trainable_weights(self):
+        e = self._eng
+        return [e.net_field(self._w1, 40).t().reshape(self.batch, 4, 10),
+                e.net_field(self._w2, 10 * self._n_out).t().reshape(self.batch, 10, self._n_out)]
+
+    def get_weights(self):
+        return [w.clone() for w in self.trainable_weights]
+
+    @property
+    def gamma_lambda(self):
+        return self._eng.env_field("GL")[0]
+
+
+class Critic_big(_BigNetView):
+    """4-10-3 critic of the nonlinear task; its gradient comes from autodiff (objects.py:304-305,1365)."""
+
+
+class Actor_big(_BigNetView):
+    """4-10-1 actor with the hand-written Jacobian trace E (1,50) (objects.py:385-392)."""
+
+    @property
+    def E(self) -> torch.Tensor:
+        return self._eng.env_field("EA", 50).t().reshape(self.batch, 1, 50)
+
+
+class _RLSView:
+    """RLS incremental model of the nonlinear agent (n = 3, m = 1): params (B,4,3), Cov (B,4,4)."""
+
+    def __init__(self, engine, config):
+        self._eng = engine
+        self.state_dim, self.action_dim = config["state_dim"], config["action_dim"]
+        self.gamma, self.init_cov = config["rls_gamma"], config["rls_cov"]
+        self.batch = engine.n
+
+    @property
+    def params(self):
+        return self._eng.env_field("THETA", 12).t().reshape(self.batch, 4, 3)
+
+    @property
+    def Cov(self):
+        return self._eng.env_field("COV", 16).t().reshape(self.batch, 4, 4)
+
+    @property
+    def F(self):
+        return self.params[:, :3, :].transpose(1, 2).clone()
+
+    @property
+    def G(self):
+        return self.params[:, 3:, :].transpose(1, 2).clone()
+
+    @property
+    def eps_norm(self):
+        return self._eng.env_field("EPS_NORM")[0]
+
+
+class IDHPnonlin:
+    """IDHP attitude tracking on the nonlinear aircraft, one agent per batch entry (objects.py:1006-1564).
+
+    ``IDHPnonlin(env, config, verbose=True, seed=1)`` as in the reference; ``env`` is a batched
+    ``rl4afcs_b200.envs.nonlinear.env.Ce500NonLinear``.  ``train()`` runs the 9000-step episode in fused kernel
+    launches of ``chunk`` steps; the N(0,1) draw of objects.py:1375 is generated per chunk with torch's Philox
+    generator (or supplied: ``noise=`` (steps, B) float32), the initial weights are TruncatedNormal(sigma) from
+    ``seed`` or ``weights=`` (W1a (B,40), W2a (B,10), W1c (B,40), W2c (B,30)).
+    """
+
+    def __init__(self, env, config, verbose=True, seed=1, *, weights=None, log_agents=None, chunk: int = 1000) -> None:
+        from . import nl_engine  # noqa: F401
+
+        self.seed = seed
+        self.env = env
+        self.config = config
+        self.verbose = verbose
+        self.gamma, self.tau = config["gamma"], config["tau"]
+        self.ms = config["multistep"] > 0 if np.ndim(config["multistep"]) == 0 else None
+        self.warmup_time = config["warmup_time"]
+        self.lr_decay = config["lr_decay"]
+        self._eng = eng = env._engine
+        self.batch = eng.n
+        self.env._set_weight_matrices(config["kappa"])                       # objects.py:1029
+        self.cooldown_timeit = int(config["cooldown_time"] / env.dt)
+        per = lambda v, f: f(v) if np.ndim(v) == 0 else np.asarray([f(x) for x in np.ravel(v)])   # noqa: E731
+        eng.set_hp("GAMMA", config["gamma"]); eng.set_hp("GAMMA_SQ", per(config["gamma"], lambda g: g ** 2))
+        eng.set_hp("TAU", config["tau"]); eng.set_hp("LR_DECAY", config["lr_decay"])
+        eng.set_hp("LAMBDA_H", config["lambda_h"]); eng.set_hp("LAMBDA_L", config["lambda_l"])
+        eng.set_hp("ETA_A_H", config["actor_config"]["eta_h"]); eng.set_hp("ETA_A_L", config["actor_config"]["eta_l"])
+        eng.set_hp("ETA_C_H", config["critic_config"]["eta_h"]); eng.set_hp("ETA_C_L", config["critic_config"]["eta_l"])
+        eng.set_hp("RLS_GAMMA", config["rls_config"]["rls_gamma"]); eng.set_hp("RLS_COV0", config["rls_config"]["rls_cov"])
+        eng.set_hpi("MULTISTEP", per(config["multistep"], lambda m: 1 if m > 0 else 0))
+        eng.set_hpi("WARMUP_STEPS", per(config["warmup_time"], lambda t: int(t / env.dt)))          # objects.py:1222
+        eng.set_hpi("COOLDOWN_STEPS", per(config["cooldown_time"], lambda t: int(t / env.dt)))      # objects.py:1025
+        elig = config["actor_config"]["elig"]
+        eng.set_hpi("ELIG_A", _lib.ELIG[elig] if not isinstance(elig, (list, tuple, np.ndarray))
+                    else np.asarray([_lib.ELIG[e] for e in elig], dtype=np.int32))
+        self.actor = Actor_big(eng, "W1A", "W2A", 1, _first(elig))
+        self.critic = Critic_big(eng, "W1C", "W2C", 3, config["critic_config"]["elig"])
+        self.target_critic = Critic_big(eng, "W1T", "W2T", 3, config["critic_config"]["elig"])
+        self.model = _RLSView(eng, config["rls_config"])
+        self.n, self.m = self.model.state_dim, self.model.action_dim
+        self.s_dim = config["in_dims"]
+        if weights is None:
+            g = torch.Generator(device=eng.device); g.manual_seed(int(seed))
+            sig = float(np.ravel(config["sigma"])[0])
+
+            def draw(w):
+                out = torch.randn((self.batch, w), generator=g, device=eng.device, dtype=torch.float32)
+                bad = out.abs() > 2.0
+                while bool(bad.any()):
+                    out = torch.where(bad, torch.randn((self.batch, w), generator=g, device=eng.device, dtype=torch.float32), out)
+                    bad = out.abs() > 2.0
+                return (out * sig).double()
+            weights = {"W1a": draw(40), "W2a": draw(10), "W1c": draw(40), "W2c": draw(30)}
+        self._init_weights = weights
+        self.log_agents = min(self.batch, 16) if log_agents is None else min(int(log_agents), self.batch)
+        self.chunk = int(chunk)
+
+    def train(self, n_steps=None, noise=None):
+        env, eng = self.env, self._eng
+        steps = int(env.t_end / env.dt) if n_steps is None else int(n_steps)
+        w = self._init_weights
+        eng.init(w["W1a"], w["W2a"], w["W1c"], w["W2c"])                     # env.reset + prologue (objects.py:1466-1488)
+        env.stepp = 0
+        g = torch.Generator(device=eng.device); g.manual_seed(int(self.seed) + 7919)
+        logs, k = [], 0
+        while k < steps:
+            c = min(self.chunk, steps - k)
+            nz = (torch.as_tensor(noise[k:k + c]) if noise is not None
+                  else torch.randn((c, self.batch), generator=g, device=eng.device, dtype=torch.float32))
+            lg = eng.run(c, nz, log_agents=self.log_agents)
+            if lg is not None:
+                logs.append(lg)
+            k += c
+        env.stepp = steps
+        env.t = env.dt * steps
+        self._steps = steps
+        if logs:
+            lg = torch.cat(logs, dim=0).permute(2, 0, 1)                     # (agents, rows, fields)
+            L = _lib.NLL
+            self.log = {"t": (torch.arange(steps, dtype=torch.float64) + 1) * env.dt,     # objects.py:1495 (N12)
+                        "x_full": lg[:, :, L["XFULL"]:L["XFULL"] + 12], "a_cmd": lg[:, :, L["SURF"]:L["SURF"] + 1],
+                        "x": lg[:, :, [L["XFULL"] + 4, L["XFULL"] + 7, L["XFULL"] + 1]],
+                        "e": lg[:, :, L["E_THETA"]:L["E_THETA"] + 1], "a": lg[:, :, L["A"]:L["A"] + 1],
+                        "reward": lg[:, :, L["REWARD"]]}
+        st = eng.stats()
+        self.RSE = [st["rse"][:, 0], st["rse"][:, 1]]                        # objects.py:1488,1503-1504
+        return self
+
+    def stats(self) -> dict:
+        return self._eng.stats()
+
+
 def _first(v):
     if isinstance(v, (list, tuple, np.ndarray)):
         return v[0]

@@ -167,3 +167,45 @@ def test_idhpsp_train_equals_reference_run(oracle, name):
     s = idhp.stats()
     assert s["sum_c"].shape == (B,) and not bool(s["diverged"].any())
     assert env.stepp == steps and len(env.yref_hist) == steps
+
+
+def test_nonlinear_env_and_agent_api(oracle):
+    """Ce500NonLinear.reset/step and IDHPnonlin.train() through the reference-shaped objects
+    (idhp_nonlin.py:107-157), checked against the oracle's free run with the same weights and noise."""
+    from oracle import nl_c
+    from rl4afcs_b200.envs.nonlinear.env import Ce500NonLinear
+    from rl4afcs_b200.objects import IDHPnonlin
+    from tests import _util_nl
+
+    B, steps = 6, 300
+    th = nl_c.theta_reference()
+    trim_input = np.array([-0.02855, 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.55, 0.55, 0])
+    trim_state = np.array([0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0])
+    env_config = {"state_dim": 4, "action_dim": 3, "trim_input": trim_input, "trim_state": trim_state, "dt": 0.01,
+                  "t_end": 90, "total_steps": 9000, "fault_time": 60, "fault_scenario": "none",
+                  "reference": {"tracked_state": ["phi", "theta", "psi"], "signal": [0 * th, th, 0 * th]}}
+    idhp_config = {"gamma": 0.6, "multistep": 0, "lr_decay": 0.998, "lambda_h": 0.95, "lambda_l": 0.95, "kappa": [1, 2, 1],
+                   "cooldown_time": 2.0, "sigma": 0.1, "warmup_time": 4.0, "error_thresh": 1, "tau": 0.02, "in_dims": 4,
+                   "actor_config": {"layers": {10: "tanh", 1: "tanh"}, "eta_h": 35.0, "eta_l": 5.0, "elig": "accumulating"},
+                   "critic_config": {"layers": {10: "tanh", 3: "linear"}, "eta_h": 1.4, "eta_l": 0.7, "elig": 1233},
+                   "rls_config": {"state_dim": 3, "action_dim": 1, "rls_gamma": 1, "rls_cov": 10 ** 6}}
+    env = Ce500NonLinear(env_config, batch=B, dtype="mixed")
+    s, r, term, trunc, info = env.reset()
+    assert s.shape == (B, 4) and float(s.abs().max()) == 0.0 and info["x_full"].shape == (B, 12)
+    assert abs(float(info["x_full"][0, 3]) - 90.0) < 1e-9 and abs(float(info["x_full"][0, 7]) - 0.0576) < 1e-9
+    s, r, _, trunc, info = env.step(np.array([0.1, 0.0, 0.0]))
+    assert s.shape == (B, 4) and r.shape == (B,) and trunc is False and set(info) >= {"nans", "s", "x_full", "x", "e", "RSE", "reward_grad"}
+    assert float(info["action_commanded"][0, 0]) > 0.0           # actuator moved towards +1.5 deg
+
+    w = nl_c.init_weights(B, 8)
+    noise = np.random.default_rng(0).standard_normal((steps, B)).astype(np.float32)
+    idhp = IDHPnonlin(env, idhp_config, seed=8, verbose=0, weights=w, log_agents=B, chunk=128)
+    idhp.train(steps, noise=noise)
+    cfg = nl_c.make_cfg()
+    st = nl_c.init_states("mixed", cfg, w, B)
+    olog = nl_c.run("mixed", cfg, th, noise, st, 0, steps, tanh="t13", n_log=B)
+    assert idhp.log["x_full"].shape == (B, steps, 12)
+    assert _util_nl.max_rel(idhp.log["x_full"].cpu().numpy()[:, :150, :9], olog["x_full"][:, :150, :9], 1e-2) < 1e-6
+    assert idhp.actor.trainable_weights[0].shape == (B, 4, 10) and idhp.critic.trainable_weights[1].shape == (B, 10, 3)
+    assert idhp.actor.E.shape == (B, 1, 50) and idhp.model.params.shape == (B, 4, 3) and idhp.model.Cov.shape == (B, 4, 4)
+    assert idhp.RSE[0].shape == (B,) and bool((idhp.RSE[0] > 0).all())
