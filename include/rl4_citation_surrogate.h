@@ -32,8 +32,10 @@
 
 #if defined(__CUDACC__)
 #define RL4_HD __host__ __device__ __forceinline__
+#define RL4_UNROLL _Pragma("unroll")
 #else
 #define RL4_HD static inline
+#define RL4_UNROLL
 #endif
 
 enum { RL4_CIT_NX = 12, RL4_CIT_NU = 11 };
@@ -64,19 +66,36 @@ RL4_HD double rl4_cit_density(double h)
     return rho0 * pow(Tr, -(g0 / (lapse * R) + 1.0));
 }
 
+#if defined(__CUDA_ARCH__)
+#define RL4_SINCOS(a, s, c) sincos((a), &(s), &(c))
+#else
+#define RL4_SINCOS(a, s, c) do { (s) = sin(a); (c) = cos(a); } while (0)
+#endif
+
+/* Air data frozen over one integration step (zero-order hold like the inputs): density and the thrust
+ * lapse (rho/rho0)^0.7 are evaluated at the altitude at the START of the step; h changes by < 1 m per step. */
+typedef struct rl4_cit_air { double rho, thrust_lapse; } rl4_cit_air;
+RL4_HD rl4_cit_air rl4_cit_airdata(double h)
+{
+    rl4_cit_air a;
+    a.rho = rl4_cit_density(h);
+    a.thrust_lapse = pow(a.rho / 1.225, 0.7);
+    return a;
+}
+
 /* xdot = f(x, u) */
-RL4_HD void rl4_cit_deriv(const rl4_cit_params* P, const double* x, const double* u, double* dx)
+RL4_HD void rl4_cit_deriv(const rl4_cit_params* P, const rl4_cit_air air, const double* x, const double* u, double* dx)
 {
     const double p = x[RL4_CIT_P], q = x[RL4_CIT_Q], r = x[RL4_CIT_R];
     const double V = x[RL4_CIT_V], al = x[RL4_CIT_ALPHA], be = x[RL4_CIT_BETA];
-    const double phi = x[RL4_CIT_PHI], th = x[RL4_CIT_THETA], psi = x[RL4_CIT_PSI], h = x[RL4_CIT_H];
+    const double phi = x[RL4_CIT_PHI], th = x[RL4_CIT_THETA], psi = x[RL4_CIT_PSI];
     const double de = u[0] + u[3], da = u[1] + u[4], dr = u[2] + u[5];
     const double flap = u[6], gear = u[7], thr = 0.5 * (u[8] + u[9]), dxcg = u[10];
 
-    const double sa = sin(al), ca = cos(al), sb = sin(be), cb = cos(be);
-    const double sphi = sin(phi), cphi = cos(phi), sth = sin(th), cth = cos(th), spsi = sin(psi), cpsi = cos(psi);
+    double sa, ca, sb, cb, sphi, cphi, sth, cth, spsi, cpsi;
+    RL4_SINCOS(al, sa, ca); RL4_SINCOS(be, sb, cb); RL4_SINCOS(phi, sphi, cphi); RL4_SINCOS(th, sth, cth); RL4_SINCOS(psi, spsi, cpsi);
 
-    const double rho = rl4_cit_density(h);
+    const double rho = air.rho;
     const double qbar = 0.5 * rho * V * V;
     const double qS = qbar * P->S;
     const double ch = P->c / (2.0 * V), bh = P->b / (2.0 * V);
@@ -96,7 +115,7 @@ RL4_HD void rl4_cit_deriv(const rl4_cit_params* P, const double* x, const double
     const double Cl = P->Clb * be + P->Clp * (p * bh) + P->Clr * (r * bh) + P->Clda * da + P->Cldr * dr;
     const double Cn = P->Cnb * be + P->Cnp * (p * bh) + P->Cnr * (r * bh) + P->Cnda * da + P->Cndr * dr - CY * dxcg / P->b;
 
-    const double T = P->Tstatic * pow(rho / 1.225, 0.7) * thr;
+    const double T = P->Tstatic * air.thrust_lapse * thr;
     const double Fx = qS * CX + T, Fy = qS * CY, Fz = qS * CZ;
     const double L = qS * P->b * Cl, M = qS * P->c * Cm, N = qS * P->b * Cn;
 
@@ -132,13 +151,18 @@ RL4_HD void rl4_cit_step_rk4(const rl4_cit_params* P, double* x, const double* u
 {
     double k1[12], k2[12], k3[12], k4[12], y[12];
     int i;
-    rl4_cit_deriv(P, x, u, k1);
+    const rl4_cit_air air = rl4_cit_airdata(x[RL4_CIT_H]);
+    rl4_cit_deriv(P, air, x, u, k1);
+    RL4_UNROLL
     for (i = 0; i < 12; ++i) y[i] = x[i] + 0.5 * dt * k1[i];
-    rl4_cit_deriv(P, y, u, k2);
+    rl4_cit_deriv(P, air, y, u, k2);
+    RL4_UNROLL
     for (i = 0; i < 12; ++i) y[i] = x[i] + 0.5 * dt * k2[i];
-    rl4_cit_deriv(P, y, u, k3);
+    rl4_cit_deriv(P, air, y, u, k3);
+    RL4_UNROLL
     for (i = 0; i < 12; ++i) y[i] = x[i] + dt * k3[i];
-    rl4_cit_deriv(P, y, u, k4);
+    rl4_cit_deriv(P, air, y, u, k4);
+    RL4_UNROLL
     for (i = 0; i < 12; ++i) x[i] = x[i] + (dt / 6.0) * (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]);
 }
 
@@ -147,21 +171,28 @@ RL4_HD void rl4_cit_step_ode5(const rl4_cit_params* P, double* x, const double* 
 {
     double k1[12], k2[12], k3[12], k4[12], k5[12], k6[12], y[12];
     int i;
-    rl4_cit_deriv(P, x, u, k1);
+    const rl4_cit_air air = rl4_cit_airdata(x[RL4_CIT_H]);
+    rl4_cit_deriv(P, air, x, u, k1);
+    RL4_UNROLL
     for (i = 0; i < 12; ++i) y[i] = x[i] + dt * (1.0 / 5.0) * k1[i];
-    rl4_cit_deriv(P, y, u, k2);
+    rl4_cit_deriv(P, air, y, u, k2);
+    RL4_UNROLL
     for (i = 0; i < 12; ++i) y[i] = x[i] + dt * ((3.0 / 40.0) * k1[i] + (9.0 / 40.0) * k2[i]);
-    rl4_cit_deriv(P, y, u, k3);
+    rl4_cit_deriv(P, air, y, u, k3);
+    RL4_UNROLL
     for (i = 0; i < 12; ++i) y[i] = x[i] + dt * ((44.0 / 45.0) * k1[i] - (56.0 / 15.0) * k2[i] + (32.0 / 9.0) * k3[i]);
-    rl4_cit_deriv(P, y, u, k4);
+    rl4_cit_deriv(P, air, y, u, k4);
+    RL4_UNROLL
     for (i = 0; i < 12; ++i)
         y[i] = x[i] + dt * ((19372.0 / 6561.0) * k1[i] - (25360.0 / 2187.0) * k2[i] + (64448.0 / 6561.0) * k3[i] -
                             (212.0 / 729.0) * k4[i]);
-    rl4_cit_deriv(P, y, u, k5);
+    rl4_cit_deriv(P, air, y, u, k5);
+    RL4_UNROLL
     for (i = 0; i < 12; ++i)
         y[i] = x[i] + dt * ((9017.0 / 3168.0) * k1[i] - (355.0 / 33.0) * k2[i] + (46732.0 / 5247.0) * k3[i] +
                             (49.0 / 176.0) * k4[i] - (5103.0 / 18656.0) * k5[i]);
-    rl4_cit_deriv(P, y, u, k6);
+    rl4_cit_deriv(P, air, y, u, k6);
+    RL4_UNROLL
     for (i = 0; i < 12; ++i)
         x[i] = x[i] + dt * ((35.0 / 384.0) * k1[i] + (500.0 / 1113.0) * k3[i] + (125.0 / 192.0) * k4[i] -
                             (2187.0 / 6784.0) * k5[i] + (11.0 / 84.0) * k6[i]);

@@ -35,9 +35,24 @@ template <> __device__ __forceinline__ double nfma<double>(double a, double b, d
 __device__ __forceinline__ float nsqrt(float a) { return sqrt_rn(Rn<float>(a)).v; }
 __device__ __forceinline__ double nsqrt(double a) { return sqrt_rn(Rn<double>(a)).v; }
 
+#ifndef RL4_NL_BLOCK
+#define RL4_NL_BLOCK 128
+#endif
+#ifndef RL4_NL_MINB
+#define RL4_NL_MINB 1
+#endif
+
+// per-thread arrays kept in shared memory, laid out [element][thread] (conflict-free, no indexing cost):
+// the actor trace E (50 doubles) and the target-critic weights (70 values) are touched once or twice per
+// step, so they are the cheapest state to move out of the 255-register budget
+template <typename T> struct Strided {
+    T* p;
+    __device__ __forceinline__ T& operator[](int j) const { return p[j * RL4_NL_BLOCK]; }
+};
+
 // hidden layer of a 4-10-k net (Network.base_call, objects.py:111-139)
-template <typename TN>
-__device__ __forceinline__ void nl_hidden(const TN (&s)[4], const TN* __restrict__ W1, TN (&h)[10])
+template <typename TN, typename WA>
+__device__ __forceinline__ void nl_hidden(const TN (&s)[4], const WA W1, TN (&h)[10])
 {
     Rn<TN> pre[10], out[10];
 #pragma unroll
@@ -53,8 +68,8 @@ __device__ __forceinline__ void nl_hidden(const TN (&s)[4], const TN* __restrict
 }
 
 // Actor_big.call (objects.py:374-407): forward + trace update
-template <typename TN>
-__device__ __forceinline__ TN nl_actor(const TN (&s)[4], const TN* __restrict__ W1, const TN* __restrict__ W2, double* __restrict__ Ea,
+template <typename TN, typename EA>
+__device__ __forceinline__ TN nl_actor(const TN (&s)[4], const TN* __restrict__ W1, const TN* __restrict__ W2, const EA Ea,
                                        int elig, double gl, TN (&h)[10], TN& ai1)
 {
     nl_hidden<TN>(s, W1, h);
@@ -154,7 +169,7 @@ __device__ __forceinline__ double nl_decay(double a, double b, double c, bool f3
 __device__ __forceinline__ bool nl_isclose(double a, double b) { return fabs(a - b) <= (1e-8 + 1e-5 * fabs(b)); }
 
 template <typename TN, bool PER_AGENT, bool LOG>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(RL4_NL_BLOCK, RL4_NL_MINB)
 nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict__ theta_ref, const float* __restrict__ noise,
               int64_t noise_stride, int k0, int n_steps, const rl4_nl_state st, int64_t n_agents, const rl4_sp_log lg)
 {
@@ -169,8 +184,12 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
 #define NF(f) Nn[(int64_t)(f) * S]
 
     // ---- load ----
-    double x[12], x_act[3], x_lon[3], x_prev_lon[3], th[12], cv[16], Ea[50], eps[3];
-    TN s[4], s_prev[4], W1a[40], W2a[10], W1c[40], W2c[30], W1t[40], W2t[30], Mp[9];
+    extern __shared__ __align__(16) unsigned char nl_smem[];
+    const Strided<double> Ea{reinterpret_cast<double*>(nl_smem) + threadIdx.x};
+    const Strided<TN> W1t{reinterpret_cast<TN*>(nl_smem + sizeof(double) * 50 * RL4_NL_BLOCK) + threadIdx.x};
+    const Strided<TN> W2t{reinterpret_cast<TN*>(nl_smem + sizeof(double) * 50 * RL4_NL_BLOCK) + 40 * RL4_NL_BLOCK + threadIdx.x};
+    double x[12], x_act[3], x_lon[3], x_prev_lon[3], th[12], cv[16], eps[3];
+    TN s[4], s_prev[4], W1a[40], W2a[10], W1c[40], W2c[30], Mp[9];
     for (int j = 0; j < 12; ++j) { x[j] = EF(RL4_NLE_XFULL + j); th[j] = EF(RL4_NLE_THETA + j); }
     for (int j = 0; j < 3; ++j) { x_act[j] = EF(RL4_NLE_XACT + j); x_lon[j] = EF(RL4_NLE_XLON + j); x_prev_lon[j] = EF(RL4_NLE_XPREVLON + j); eps[j] = EF(RL4_NLE_EPS + j); }
     for (int j = 0; j < 16; ++j) cv[j] = EF(RL4_NLE_COV + j);
@@ -207,7 +226,7 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
 
         // ---- _step_networks (objects.py:1292-1348)
         TN hc[10], ht[10], lam[3], lt[3];
-        nl_hidden<TN>(s_prev, W1c, hc);                                            // critic(s_prev)
+        nl_hidden<TN>(s_prev, (const TN*)W1c, hc);                                 // critic(s_prev)
         nl_hidden<TN>(s_next, W1t, ht);                                            // target_critic(s_next)
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
@@ -486,6 +505,29 @@ nl_env_step_kernel(const __grid_constant__ rl4_nl_params p, const double* __rest
     out_reward[i] = reward; out_e[i] = e_th;
 }
 
+template <typename TN, bool PA, bool LOG>
+static int nl_launch_one(const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride, int k0,
+                         int n_steps, rl4_nl_state st, int64_t n, rl4_sp_log lg, unsigned grid, cudaStream_t s)
+{
+    const size_t smem = (sizeof(double) * 50 + sizeof(TN) * 70) * RL4_NL_BLOCK;
+    static bool configured = false;
+    if (!configured) {
+        RL4_CUDA(cudaFuncSetAttribute(nl_run_kernel<TN, PA, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    nl_run_kernel<TN, PA, LOG><<<grid, RL4_NL_BLOCK, smem, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg);
+    return 0;
+}
+
+template <typename TN>
+static int nl_launch(const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride, int k0, int n_steps,
+                     rl4_nl_state st, int64_t n, rl4_sp_log lg, bool log, bool per_agent, unsigned grid, cudaStream_t s)
+{
+    if (log) return nl_launch_one<TN, true, true>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s);
+    if (per_agent) return nl_launch_one<TN, true, false>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s);
+    return nl_launch_one<TN, false, false>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s);
+}
+
 }  // namespace rl4
 
 using namespace rl4;
@@ -541,19 +583,14 @@ int rl4_nl_run(int policy, const rl4_nl_params* p, const double* theta_ref, cons
     bool per_agent = false;
     for (int j = 0; j < RL4_NHP_COUNT; ++j) per_agent |= (p->hp_agent[j] != nullptr);
     for (int j = 0; j < RL4_NHPI_COUNT; ++j) per_agent |= (p->hpi_agent[j] != nullptr);
-    const unsigned grid = (unsigned)((n + 127) / 128);
+    const unsigned grid = (unsigned)((n + RL4_NL_BLOCK - 1) / RL4_NL_BLOCK);
     cudaStream_t s = (cudaStream_t)stream;
     const bool log = lg.level != RL4_LOG_NONE;
-#define RL4_NL_LAUNCH(TN)                                                                                               \
-    do {                                                                                                                \
-        if (log) nl_run_kernel<TN, true, true><<<grid, 128, 0, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg);        \
-        else if (per_agent) nl_run_kernel<TN, true, false><<<grid, 128, 0, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg); \
-        else nl_run_kernel<TN, false, false><<<grid, 128, 0, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg);          \
-    } while (0)
-    if (policy == RL4_MIXED) RL4_NL_LAUNCH(float);
-    else if (policy == RL4_FP64) RL4_NL_LAUNCH(double);
+    int rc = 0;
+    if (policy == RL4_MIXED) rc = nl_launch<float>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, log, per_agent, grid, s);
+    else if (policy == RL4_FP64) rc = nl_launch<double>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, log, per_agent, grid, s);
     else { set_error("rl4_nl_run: policy %d not supported on the nonlinear path (mixed or fp64)", policy); return -1; }
-#undef RL4_NL_LAUNCH
+    if (rc) return rc;
     return check_launch("nl_run_kernel");
 }
 
