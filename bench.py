@@ -341,8 +341,17 @@ def run_ours(args) -> dict:
     device = f"cuda:{local}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device(device))
+        # NCCL prints its version banner on stdout when the communicator is created: keep stdout to the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device(device))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     L = _lib.load()
     n, K, W = args.agents, args.steps, max(args.warmup, 0)
 

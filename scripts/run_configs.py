@@ -31,8 +31,10 @@ world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK"
 torch.cuda.set_device(local)
 dev = f"cuda:{local}"
 if world > 1:
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    dist.init_process_group("nccl", device_id=torch.device(dev))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    sys.stdout.flush(); _saved = os.dup(1); os.dup2(2, 1)          # NCCL's version banner goes to stderr
+    dist.init_process_group("nccl", device_id=torch.device(dev)); dist.barrier(); torch.cuda.synchronize()
+    os.dup2(_saved, 1); os.close(_saved)
 
 
 def timed(fn):
