@@ -171,6 +171,9 @@ class SpEngine:
             t = torch.as_tensor(np.asarray(v, dtype=np.float64) if not torch.is_tensor(v) else v)
             t = t.to(device=self.device, dtype=torch.float64).reshape(self.n, width)
             return t.t().contiguous()
+        if self.n == 0:
+            self.k = 0
+            return
         with torch.cuda.device(self.device):
             px0, pa1, pa2, pc1, pc2 = plane(x0, 2), plane(W1a, 4), plane(W2a, 4), plane(W1c, 4), plane(W2c, 8)
             rc = self.lib.rl4_sp_init(self.policy_id, ctypes.byref(self.params), px0.data_ptr(), pa1.data_ptr(),

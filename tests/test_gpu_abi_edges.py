@@ -1,0 +1,97 @@
+"""Edge cases of the C-ABI on the GPU: empty and ragged batches, stride > n, argument validation, error text."""
+import ctypes
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from tests import _util  # noqa: E402
+
+
+def _engine(oracle, n, policy="mixed"):
+    from rl4afcs_b200 import sp_engine
+
+    eng = sp_engine.SpEngine(n, policy=policy)
+    ic = oracle.default_idhp_config()
+    sp_engine.apply_idhp_config(eng, ic, dt=0.02)
+    base, amp = oracle.default_reference()
+    eng.set_hp("REF_AMP", amp); eng.set_hpi("FAULT_STEP", -1); eng.set_hpi("FAULT_KIND", 0)
+    eng.set_reference(base)
+    return eng, ic, base, amp
+
+
+def test_empty_batch_is_a_no_op(oracle):
+    eng, ic, base, amp = _engine(oracle, 0)
+    eng.init(np.zeros((0, 2)), np.zeros((0, 4)), np.zeros((0, 4)), np.zeros((0, 4)), np.zeros((0, 8)))
+    eng.run(10)
+    assert eng.stats()["sum_c"].numel() == 0
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 127, 129, 1000])
+def test_ragged_batch_sizes(oracle, n):
+    eng, ic, base, amp = _engine(oracle, n, "fp64")
+    rng = np.random.default_rng(n)
+    x0 = np.deg2rad(rng.uniform(-2, 2, size=(n, 2)))
+    w = oracle.init_weights(n, n)
+    eng.init(x0, w["W1a"], w["W2a"], w["W1c"], w["W2c"])
+    eng.run(120)
+    cfg = oracle.make_cfg(ic)
+    st = oracle.init_states("fp64", cfg, x0, w)
+    oracle.run("fp64", cfg, base, st, 0, 120, tanh="t13")
+    got = _util.engine_state_to_oracle(eng, oracle, lambda low: np.where(low, cfg["lambda_l"] * cfg["gamma"], cfg["lambda_h"] * cfg["gamma"]))
+    assert _util.state_mismatches(got, st) == {}
+
+
+def test_stride_larger_than_batch_leaves_padding_untouched(oracle):
+    from rl4afcs_b200 import _lib
+    from rl4afcs_b200._lib import SPE, SPI, SPN
+
+    eng, ic, base, amp = _engine(oracle, 40)
+    L = eng.lib
+    n, stride = 40, 64
+    env = torch.full((SPE["COUNT"], stride), 7.0, dtype=torch.float64, device="cuda")
+    net = torch.full((SPN["COUNT"], stride), 7.0, dtype=torch.float32, device="cuda")
+    ints = torch.full((SPI["COUNT"], stride), 7, dtype=torch.int32, device="cuda")
+    st = _lib.SpState(env.data_ptr(), net.data_ptr(), ints.data_ptr(), stride)
+    z = torch.zeros((8, n), dtype=torch.float64, device="cuda")
+    _lib.check(L.rl4_sp_init(_lib.MIXED, ctypes.byref(eng.params), z.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(),
+                             z.data_ptr(), n, st, n, None), "init")
+    _lib.check(L.rl4_sp_run(_lib.MIXED, ctypes.byref(eng.params), eng.ref_base.data_ptr(), 0, 50, st, n, 0,
+                            _lib.SpLog(None, 0, 1, 0), None), "run")
+    torch.cuda.synchronize()
+    assert bool((env[:, n:] == 7.0).all()) and bool((net[:, n:] == 7.0).all()) and bool((ints[:, n:] == 7).all())
+    assert not bool((env[0, :n] == 7.0).any())
+
+
+def test_argument_validation_and_error_text(oracle):
+    from rl4afcs_b200 import _lib
+
+    eng, ic, base, amp = _engine(oracle, 8)
+    L = eng.lib
+    st = eng.state_struct()
+    nolog = _lib.SpLog(None, 0, 1, 0)
+    assert L.rl4_sp_run(99, ctypes.byref(eng.params), eng.ref_base.data_ptr(), 0, 5, st, 8, 0, nolog, None) == -1
+    assert b"policy" in L.rl4_last_error()
+    assert L.rl4_sp_run(_lib.MIXED, ctypes.byref(eng.params), None, 0, 5, st, 8, 0, nolog, None) == -1
+    bad = _lib.SpState(st.env, st.net, st.ints, 4)           # stride < n
+    assert L.rl4_sp_run(_lib.MIXED, ctypes.byref(eng.params), eng.ref_base.data_ptr(), 0, 5, bad, 8, 0, nolog, None) == -1
+    assert b"stride" in L.rl4_last_error()
+    # traces configured but the trace-free kernel requested
+    eng.set_hpi("ELIG_A", 1)
+    assert L.rl4_sp_run(_lib.MIXED, ctypes.byref(eng.params), eng.ref_base.data_ptr(), 0, 5, st, 8, 0, nolog, None) == -1
+    assert b"elig" in L.rl4_last_error()
+    with pytest.raises(_lib.Rl4Error):
+        _lib.check(-1, "demo")
+    # nonlinear path: fp32 policy is rejected loudly
+    from rl4afcs_b200 import nl_engine
+    with pytest.raises(_lib.Rl4Error):
+        nl_engine.NlEngine(4, policy="fp32")
+
+
+def test_reference_table_bounds_are_checked(oracle):
+    eng, ic, base, amp = _engine(oracle, 4)
+    eng.init(np.zeros((4, 2)), np.zeros((4, 4)), np.zeros((4, 4)), np.zeros((4, 4)), np.zeros((4, 8)))
+    with pytest.raises(AssertionError):
+        eng.run(len(base) + 1)
