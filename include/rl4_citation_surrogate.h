@@ -32,9 +32,13 @@
 
 #if defined(__CUDACC__)
 #define RL4_HD __host__ __device__ __forceinline__
+/* the derivative function is called 4-6 times per step: one out-of-line copy keeps the fused kernel inside the
+ * instruction cache (fully inlined it was 370 KB of SASS and stalled on instruction fetch) */
+#define RL4_HD_NOINLINE __host__ __device__ __forceinline__   /* out-of-line was tried: slower (x, u, k arrays forced to local memory) */
 #define RL4_UNROLL _Pragma("unroll")
 #else
 #define RL4_HD static inline
+#define RL4_HD_NOINLINE static inline
 #define RL4_UNROLL
 #endif
 
@@ -67,7 +71,9 @@ RL4_HD double rl4_cit_density(double h)
 }
 
 #if defined(__CUDA_ARCH__)
-#define RL4_SINCOS(a, s, c) sincos((a), &(s), &(c))
+/* exact-zero shortcut: in symmetric flight (da = dr = 0) beta, phi and psi are identically zero, and
+ * sin(+-0) = +-0, cos(0) = 1 are what sincos returns anyway */
+#define RL4_SINCOS(a, s, c) do { if ((a) == 0.0) { (s) = (a); (c) = 1.0; } else sincos((a), &(s), &(c)); } while (0)
 #else
 #define RL4_SINCOS(a, s, c) do { (s) = sin(a); (c) = cos(a); } while (0)
 #endif
@@ -84,7 +90,7 @@ RL4_HD rl4_cit_air rl4_cit_airdata(double h)
 }
 
 /* xdot = f(x, u) */
-RL4_HD void rl4_cit_deriv(const rl4_cit_params* P, const rl4_cit_air air, const double* x, const double* u, double* dx)
+RL4_HD_NOINLINE void rl4_cit_deriv(const rl4_cit_params* P, const rl4_cit_air air, const double* x, const double* u, double* dx)
 {
     const double p = x[RL4_CIT_P], q = x[RL4_CIT_Q], r = x[RL4_CIT_R];
     const double V = x[RL4_CIT_V], al = x[RL4_CIT_ALPHA], be = x[RL4_CIT_BETA];

@@ -26,6 +26,7 @@ NVCC_FLAGS = [
     "-fmad=false",
     "-Xcompiler", "-fPIC", "-shared",
     "-Xptxas", "-v",
+    "--threads", "4",          # the three translation units compile in parallel
 ]
 
 

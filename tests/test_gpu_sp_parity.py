@@ -215,3 +215,37 @@ def test_fp32_single_step_within_1e4_of_fp64_oracle(oracle):
         for f, scale in (("x", 1e-2), ("a", 1e-2), ("W1a", 1e-2), ("W2a", 1e-2), ("W1c", 1e-2), ("W2c", 1e-2)):
             worst = max(worst, _rel(got[f], st64[f], scale))
     assert worst < 1e-4, worst
+
+
+@pytest.mark.parametrize("policy", ["fp64", "mixed"])
+def test_full_size_batch_by_replication_property(oracle, policy):
+    """BASELINE.json configs[1] size (2^20 agents): agents are independent, so a batch that replicates a 1024-agent
+    block 1024 times must reproduce that block bit for bit at every position (no cross-agent leakage, no
+    position-dependent arithmetic), and the block itself equals the oracle."""
+    from rl4afcs_b200 import sp_engine
+
+    n_small, reps, steps = 1024, 1024, 400
+    n = n_small * reps
+    ic = oracle.default_idhp_config()
+    base, amp = oracle.default_reference()
+    rng = np.random.default_rng(77)
+    x0 = np.deg2rad(rng.uniform(-2, 2, size=(n_small, 2)))
+    w = oracle.init_weights(n_small, 78)
+    cfg = oracle.make_cfg(ic)
+    st = oracle.init_states(policy, cfg, x0, w)
+    oracle.run(policy, cfg, base, st, 0, steps, tanh="t13")
+    eng = sp_engine.SpEngine(n, policy=policy)
+    sp_engine.apply_idhp_config(eng, ic, dt=0.02)
+    eng.set_hp("REF_AMP", amp); eng.set_hpi("FAULT_STEP", -1); eng.set_hpi("FAULT_KIND", 0)
+    eng.set_reference(base)
+    tile = lambda a: torch.as_tensor(a).cuda().repeat(reps, 1)    # noqa: E731
+    eng.init(tile(x0), tile(w["W1a"]), tile(w["W2a"]), tile(w["W1c"]), tile(w["W2c"]))
+    eng.run(steps)
+    for plane in (eng.env, eng.net, eng.ints):
+        v = plane.reshape(plane.shape[0], reps, n_small)
+        same = (v == v[:, :1, :]) | (torch.isnan(v) & torch.isnan(v[:, :1, :])) if plane.is_floating_point() else (v == v[:, :1, :])
+        assert bool(same.all())
+    small = sp_engine.SpEngine(n_small, policy=policy)
+    small.env.copy_(eng.env[:, :n_small]); small.net.copy_(eng.net[:, :n_small]); small.ints.copy_(eng.ints[:, :n_small])
+    got = _util.engine_state_to_oracle(small, oracle, _gl_of(cfg, ic))
+    assert _util.state_mismatches(got, st) == {}
