@@ -517,7 +517,9 @@ struct rl4_ctx {
     int policy;
     int64_t max_agents;
     int32_t max_steps;
-    cudaStream_t stream;
+    static constexpr int kStreams = 4;
+    cudaStream_t streams[kStreams];
+    cudaEvent_t ref_ready;
     double* d_in;        // [22][max_agents] x0(2) w1a(4) w2a(4) w1c(4) w2c(8)
     double* d_ref;       // [max_steps]
     void* d_env;
@@ -538,7 +540,8 @@ int rl4_ctx_create(int device, int policy, int64_t max_agents, int32_t max_steps
     c->device = device; c->policy = policy; c->max_agents = max_agents; c->max_steps = max_steps;
     c->te = (policy == RL4_FP32) ? 4 : 8;
     c->tn = (policy == RL4_FP64) ? 8 : 4;
-    RL4_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < rl4_ctx::kStreams; ++i) RL4_CUDA(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
+    RL4_CUDA(cudaEventCreateWithFlags(&c->ref_ready, cudaEventDisableTiming));
     RL4_CUDA(cudaMalloc(&c->d_in, sizeof(double) * 22 * max_agents));
     RL4_CUDA(cudaMalloc(&c->d_ref, sizeof(double) * max_steps));
     RL4_CUDA(cudaMalloc(&c->d_env, c->te * RL4_SPE_COUNT * max_agents));
@@ -553,11 +556,15 @@ int rl4_ctx_destroy(rl4_ctx* c)
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaFree(c->d_in); cudaFree(c->d_ref); cudaFree(c->d_env); cudaFree(c->d_net); cudaFree(c->d_ints);
-    cudaStreamDestroy(c->stream);
+    for (int i = 0; i < rl4_ctx::kStreams; ++i) cudaStreamDestroy(c->streams[i]);
+    cudaEventDestroy(c->ref_ready);
     delete c;
     return 0;
 }
 
+// The batch is cut into chunks of agents that flow through kStreams streams, so that the H2D copy of chunk
+// c+1, the fused kernel of chunk c and the D2H copy of chunk c-1 overlap (agents are independent; a chunk is just a
+// column range of the SoA planes).  With pinned host buffers the copies are fully asynchronous.
 int rl4_sp_episode_host(rl4_ctx* c, const rl4_sp_params* p, const rl4_sp_host_io* io, int64_t n, int32_t n_steps,
                         int32_t use_traces)
 {
@@ -565,33 +572,43 @@ int rl4_sp_episode_host(rl4_ctx* c, const rl4_sp_params* p, const rl4_sp_host_io
     RL4_REQUIRE(n > 0 && n <= c->max_agents && n_steps > 0 && n_steps <= c->max_steps, "size exceeds the context capacity");
     RL4_REQUIRE(io->x0 && io->w1a && io->w2a && io->w1c && io->w2c && io->ref_base, "NULL input buffer");
     RL4_CUDA(cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
     const int64_t S = c->max_agents;
-    double* d_x0 = c->d_in;
-    double* d_w1a = c->d_in + 2 * S;
-    double* d_w2a = c->d_in + 6 * S;
-    double* d_w1c = c->d_in + 10 * S;
-    double* d_w2c = c->d_in + 14 * S;
-    // host planes are [f][n]; device planes are [f][S]
-    RL4_CUDA(cudaMemcpy2DAsync(d_x0, S * 8, io->x0, n * 8, n * 8, 2, cudaMemcpyHostToDevice, s));
-    RL4_CUDA(cudaMemcpy2DAsync(d_w1a, S * 8, io->w1a, n * 8, n * 8, 4, cudaMemcpyHostToDevice, s));
-    RL4_CUDA(cudaMemcpy2DAsync(d_w2a, S * 8, io->w2a, n * 8, n * 8, 4, cudaMemcpyHostToDevice, s));
-    RL4_CUDA(cudaMemcpy2DAsync(d_w1c, S * 8, io->w1c, n * 8, n * 8, 4, cudaMemcpyHostToDevice, s));
-    RL4_CUDA(cudaMemcpy2DAsync(d_w2c, S * 8, io->w2c, n * 8, n * 8, 8, cudaMemcpyHostToDevice, s));
-    RL4_CUDA(cudaMemcpyAsync(c->d_ref, io->ref_base, sizeof(double) * n_steps, cudaMemcpyHostToDevice, s));
-    rl4_sp_state st{c->d_env, c->d_net, c->d_ints, S};
-    int rc = rl4_sp_init(c->policy, p, d_x0, d_w1a, d_w2a, d_w1c, d_w2c, S, st, n, s);
-    if (rc) return rc;
-    rl4_sp_log lg{nullptr, RL4_LOG_NONE, 1, 0};
-    rc = rl4_sp_run(c->policy, p, c->d_ref, 0, n_steps, st, n, use_traces, lg, s);
-    if (rc) return rc;
-    if (io->out_env)
-        RL4_CUDA(cudaMemcpy2DAsync(io->out_env, n * c->te, c->d_env, S * c->te, n * c->te, RL4_SPE_COUNT, cudaMemcpyDeviceToHost, s));
-    if (io->out_net)
-        RL4_CUDA(cudaMemcpy2DAsync(io->out_net, n * c->tn, c->d_net, S * c->tn, n * c->tn, RL4_SPN_COUNT, cudaMemcpyDeviceToHost, s));
-    if (io->out_ints)
-        RL4_CUDA(cudaMemcpy2DAsync(io->out_ints, n * 4, c->d_ints, S * 4, n * 4, RL4_SPI_COUNT, cudaMemcpyDeviceToHost, s));
-    RL4_CUDA(cudaStreamSynchronize(s));
+    RL4_CUDA(cudaMemcpyAsync(c->d_ref, io->ref_base, sizeof(double) * n_steps, cudaMemcpyHostToDevice, c->streams[0]));
+    RL4_CUDA(cudaEventRecord(c->ref_ready, c->streams[0]));
+    int64_t n_chunks = n / 65536;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > 8) n_chunks = 8;
+    const int64_t per = ((n + n_chunks - 1) / n_chunks + 127) / 128 * 128;
+    const struct { const double* host; int rows; int64_t dev_row; } ins[5] = {
+        {io->x0, 2, 0}, {io->w1a, 4, 2}, {io->w2a, 4, 6}, {io->w1c, 4, 10}, {io->w2c, 8, 14}};
+    int ci = 0;
+    for (int64_t off = 0; off < n; off += per, ++ci) {
+        const int64_t m = (n - off < per) ? (n - off) : per;
+        cudaStream_t s = c->streams[ci % rl4_ctx::kStreams];
+        if (ci % rl4_ctx::kStreams != 0 || ci >= rl4_ctx::kStreams) RL4_CUDA(cudaStreamWaitEvent(s, c->ref_ready, 0));
+        for (const auto& in : ins)   // host planes are [rows][n]; device planes are [rows][S]
+            RL4_CUDA(cudaMemcpy2DAsync(c->d_in + in.dev_row * S + off, S * 8, in.host + off, n * 8, m * 8, in.rows,
+                                       cudaMemcpyHostToDevice, s));
+        rl4_sp_params pc = *p;       // per-agent override arrays follow the chunk
+        for (int j = 0; j < RL4_HP_COUNT; ++j) if (pc.hp_agent[j]) pc.hp_agent[j] += off;
+        for (int j = 0; j < RL4_HPI_COUNT; ++j) if (pc.hpi_agent[j]) pc.hpi_agent[j] += off;
+        rl4_sp_state st{(char*)c->d_env + off * c->te, (char*)c->d_net + off * c->tn, c->d_ints + off, S};
+        int rc = rl4_sp_init(c->policy, &pc, c->d_in + off, c->d_in + 2 * S + off, c->d_in + 6 * S + off, c->d_in + 10 * S + off,
+                             c->d_in + 14 * S + off, S, st, m, s);
+        if (rc) return rc;
+        rl4_sp_log lg{nullptr, RL4_LOG_NONE, 1, 0};
+        rc = rl4_sp_run(c->policy, &pc, c->d_ref, 0, n_steps, st, m, use_traces, lg, s);
+        if (rc) return rc;
+        if (io->out_env)
+            RL4_CUDA(cudaMemcpy2DAsync((char*)io->out_env + off * c->te, n * c->te, st.env, S * c->te, m * c->te, RL4_SPE_COUNT,
+                                       cudaMemcpyDeviceToHost, s));
+        if (io->out_net)
+            RL4_CUDA(cudaMemcpy2DAsync((char*)io->out_net + off * c->tn, n * c->tn, st.net, S * c->tn, m * c->tn, RL4_SPN_COUNT,
+                                       cudaMemcpyDeviceToHost, s));
+        if (io->out_ints)
+            RL4_CUDA(cudaMemcpy2DAsync(io->out_ints + off, n * 4, st.ints, S * 4, m * 4, RL4_SPI_COUNT, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < rl4_ctx::kStreams; ++i) RL4_CUDA(cudaStreamSynchronize(c->streams[i]));
     return 0;
 }
 

@@ -95,3 +95,35 @@ def test_reference_table_bounds_are_checked(oracle):
     eng.init(np.zeros((4, 2)), np.zeros((4, 4)), np.zeros((4, 4)), np.zeros((4, 4)), np.zeros((4, 8)))
     with pytest.raises(AssertionError):
         eng.run(len(base) + 1)
+
+
+@pytest.mark.parametrize("n", [1000, 200000])
+def test_host_buffer_episode_equals_device_path(oracle, n):
+    """rl4_sp_episode_host (chunked, multi-stream H2D / kernels / D2H) returns exactly what init + run produce."""
+    from rl4afcs_b200 import _lib
+    from rl4afcs_b200._lib import SPE, SPI, SPN
+
+    steps = 150
+    eng, ic, base, amp = _engine(oracle, n, "mixed")
+    L = eng.lib
+    rng = np.random.default_rng(3)
+    x0 = np.deg2rad(rng.uniform(-2, 2, size=(n, 2)))
+    w = oracle.init_weights(n, 5)
+    eng.init(x0, w["W1a"], w["W2a"], w["W1c"], w["W2c"])
+    eng.run(steps)
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a.T)).pin_memory()     # noqa: E731  [rows][n]
+    hx0, h1, h2, h3, h4 = pin(x0), pin(w["W1a"]), pin(w["W2a"]), pin(w["W1c"]), pin(w["W2c"])
+    href = torch.as_tensor(base[:steps].copy()).pin_memory()
+    oenv = torch.empty((SPE["COUNT"], n), dtype=torch.float64).pin_memory()
+    onet = torch.empty((SPN["COUNT"], n), dtype=torch.float32).pin_memory()
+    oint = torch.empty((SPI["COUNT"], n), dtype=torch.int32).pin_memory()
+    ctx = ctypes.c_void_p()
+    _lib.check(L.rl4_ctx_create(0, _lib.MIXED, n, steps, ctypes.byref(ctx)), "ctx")
+    io = _lib.SpHostIO(hx0.data_ptr(), h1.data_ptr(), h2.data_ptr(), h3.data_ptr(), h4.data_ptr(), href.data_ptr(),
+                       oenv.data_ptr(), onet.data_ptr(), oint.data_ptr())
+    try:
+        _lib.check(L.rl4_sp_episode_host(ctx, ctypes.byref(eng.params), ctypes.byref(io), n, steps, 0), "episode")
+    finally:
+        L.rl4_ctx_destroy(ctx)
+    eq = lambda u, v: bool(((u == v) | (torch.isnan(u) & torch.isnan(v))).all())   # noqa: E731
+    assert eq(oenv, eng.env[:, :n].cpu()) and eq(onet, eng.net[:, :n].cpu()) and torch.equal(oint, eng.ints[:, :n].cpu())
