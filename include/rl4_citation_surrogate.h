@@ -60,7 +60,16 @@ typedef struct rl4_cit_params {
     double Cnb, Cnp, Cnr, Cnda, Cndr;
     /* propulsion: T = Tstatic * (rho/rho0)^0.7 * (thr1 + thr2)/2, along body x through the c.g. */
     double Tstatic;
+    /* reciprocals used by rl4_cit_deriv, filled by rl4_cit_finalize() */
+    double inv_m, inv_Iyy, inv_gam, inv_al_stall, inv_c, inv_b;
 } rl4_cit_params;
+
+/* derived constants; call after changing m, inertias, al_stall, c or b */
+RL4_HD void rl4_cit_finalize(rl4_cit_params* P)
+{
+    P->inv_m = 1.0 / P->m; P->inv_Iyy = 1.0 / P->Iyy; P->inv_gam = 1.0 / (P->Ixx * P->Izz - P->Ixz * P->Ixz);
+    P->inv_al_stall = 1.0 / P->al_stall; P->inv_c = 1.0 / P->c; P->inv_b = 1.0 / P->b;
+}
 
 /* ISA troposphere density */
 RL4_HD double rl4_cit_density(double h)
@@ -89,7 +98,10 @@ RL4_HD rl4_cit_air rl4_cit_airdata(double h)
     return a;
 }
 
-/* xdot = f(x, u) */
+/* xdot = f(x, u).  Written for the FP64 pipe: sums of products are explicit FMA chains (RL4_FMA = fma() on both
+ * the CUDA and the glibc side), constant denominators are reciprocals precomputed in the parameter block, and the
+ * four state-dependent reciprocals (1/V, 1/sqrt(1+(al/al_s)^2), 1/cos(theta), 1/cos(beta)) are formed once. */
+#define RL4_FMA(a, b, c) fma((a), (b), (c))
 RL4_HD_NOINLINE void rl4_cit_deriv(const rl4_cit_params* P, const rl4_cit_air air, const double* x, const double* u, double* dx)
 {
     const double p = x[RL4_CIT_P], q = x[RL4_CIT_Q], r = x[RL4_CIT_R];
@@ -101,55 +113,62 @@ RL4_HD_NOINLINE void rl4_cit_deriv(const rl4_cit_params* P, const rl4_cit_air ai
     double sa, ca, sb, cb, sphi, cphi, sth, cth, spsi, cpsi;
     RL4_SINCOS(al, sa, ca); RL4_SINCOS(be, sb, cb); RL4_SINCOS(phi, sphi, cphi); RL4_SINCOS(th, sth, cth); RL4_SINCOS(psi, spsi, cpsi);
 
-    const double rho = air.rho;
-    const double qbar = 0.5 * rho * V * V;
-    const double qS = qbar * P->S;
-    const double ch = P->c / (2.0 * V), bh = P->b / (2.0 * V);
+    const double invV = 1.0 / V, inv_cth = 1.0 / cth, inv_cb = 1.0 / cb;
+    const double qS = (0.5 * air.rho * P->S) * (V * V);
+    const double ch = (0.5 * P->c) * invV, bh = (0.5 * P->b) * invV;
+    const double qh = q * ch, ph = p * bh, rh = r * bh;
 
     /* aerodynamic coefficients; lift saturates smoothly beyond alpha_stall (al_e = al / sqrt(1 + (al/al_s)^2)),
      * the lost incidence (al - al_e) produces extra drag and a nose-down moment: a crude but bounded stall */
-    const double al_e = al / sqrt(1.0 + (al / P->al_stall) * (al / P->al_stall));
+    const double an = al * P->inv_al_stall;
+    const double al_e = al / sqrt(RL4_FMA(an, an, 1.0));
     const double al_x = al - al_e;
-    const double CL = P->CL0 + P->CLa * al_e + P->CLq * (q * ch) + P->CLde * de + P->CLflap * flap;
-    const double CD = P->CD0 + P->CDk * CL * CL + P->CDgear * gear + P->CDflap * flap + P->CDstall * al_x * al_x;
-    const double CY = P->CYb * be + P->CYp * (p * bh) + P->CYr * (r * bh) + P->CYda * da + P->CYdr * dr;
-    const double CX = -CD * ca + CL * sa;                 /* body axes */
-    const double CZ = -CD * sa - CL * ca;
-    /* a c.g. shift dxcg (m, + forward ... sign as the reference's `shift_cg`: input[10] = -0.5) moves the
-     * moment reference: dCm = CZ * dxcg / c, dCn = -CY * dxcg / b */
-    const double Cm = P->Cm0 + P->Cma * al + P->Cmstall * al_x + P->Cmq * (q * ch) + P->Cmde * de + P->Cmflap * flap + CZ * dxcg / P->c;
-    const double Cl = P->Clb * be + P->Clp * (p * bh) + P->Clr * (r * bh) + P->Clda * da + P->Cldr * dr;
-    const double Cn = P->Cnb * be + P->Cnp * (p * bh) + P->Cnr * (r * bh) + P->Cnda * da + P->Cndr * dr - CY * dxcg / P->b;
+    const double CL = RL4_FMA(P->CLflap, flap, RL4_FMA(P->CLde, de, RL4_FMA(P->CLq, qh, RL4_FMA(P->CLa, al_e, P->CL0))));
+    const double CD = RL4_FMA(P->CDstall * al_x, al_x, RL4_FMA(P->CDflap, flap, RL4_FMA(P->CDgear, gear, RL4_FMA(P->CDk * CL, CL, P->CD0))));
+    const double CY = RL4_FMA(P->CYdr, dr, RL4_FMA(P->CYda, da, RL4_FMA(P->CYr, rh, RL4_FMA(P->CYp, ph, P->CYb * be))));
+    const double CX = RL4_FMA(CL, sa, -CD * ca);          /* body axes */
+    const double CZ = -RL4_FMA(CL, ca, CD * sa);
+    /* a c.g. shift dxcg (m; the reference's `shift_cg` sets input[10] = -0.5) moves the moment reference:
+     * dCm = CZ * dxcg / c, dCn = -CY * dxcg / b */
+    const double Cm = RL4_FMA(CZ * dxcg, P->inv_c, RL4_FMA(P->Cmflap, flap, RL4_FMA(P->Cmde, de, RL4_FMA(P->Cmq, qh,
+                      RL4_FMA(P->Cmstall, al_x, RL4_FMA(P->Cma, al, P->Cm0))))));
+    const double Cl = RL4_FMA(P->Cldr, dr, RL4_FMA(P->Clda, da, RL4_FMA(P->Clr, rh, RL4_FMA(P->Clp, ph, P->Clb * be))));
+    const double Cn = RL4_FMA(-CY * dxcg, P->inv_b, RL4_FMA(P->Cndr, dr, RL4_FMA(P->Cnda, da, RL4_FMA(P->Cnr, rh,
+                      RL4_FMA(P->Cnp, ph, P->Cnb * be)))));
 
     const double T = P->Tstatic * air.thrust_lapse * thr;
-    const double Fx = qS * CX + T, Fy = qS * CY, Fz = qS * CZ;
-    const double L = qS * P->b * Cl, M = qS * P->c * Cm, N = qS * P->b * Cn;
+    const double ax = RL4_FMA(qS, CX, T) * P->inv_m, ay = (qS * CY) * P->inv_m, az = (qS * CZ) * P->inv_m;   /* specific forces */
+    const double L = (qS * P->b) * Cl, M = (qS * P->c) * Cm, N = (qS * P->b) * Cn;
 
     /* body-axis velocities and their rates */
     const double ub = V * ca * cb, vb = V * sb, wb = V * sa * cb;
-    const double ud = r * vb - q * wb - P->g * sth + Fx / P->m;
-    const double vd = p * wb - r * ub + P->g * sphi * cth + Fy / P->m;
-    const double wd = q * ub - p * vb + P->g * cphi * cth + Fz / P->m;
-    const double Vd = (ub * ud + vb * vd + wb * wd) / V;
-    const double uw2 = ub * ub + wb * wb;
+    const double ud = RL4_FMA(r, vb, RL4_FMA(-q, wb, RL4_FMA(-P->g, sth, ax)));
+    const double vd = RL4_FMA(p, wb, RL4_FMA(-r, ub, RL4_FMA(P->g * sphi, cth, ay)));
+    const double wd = RL4_FMA(q, ub, RL4_FMA(-p, vb, RL4_FMA(P->g * cphi, cth, az)));
+    const double Vd = RL4_FMA(ub, ud, RL4_FMA(vb, vd, wb * wd)) * invV;
+    const double iVc = invV * inv_cb;                      /* 1 / sqrt(u^2 + w^2) */
 
     /* Euler's equations with Ixz */
-    const double gam = P->Ixx * P->Izz - P->Ixz * P->Ixz;
-    const double Lp = L - (P->Izz - P->Iyy) * q * r + P->Ixz * p * q;
-    const double Np = N - (P->Iyy - P->Ixx) * p * q - P->Ixz * q * r;
+    const double Lp = RL4_FMA(P->Ixz * p, q, RL4_FMA(-(P->Izz - P->Iyy) * q, r, L));
+    const double Np = RL4_FMA(-P->Ixz * q, r, RL4_FMA(-(P->Iyy - P->Ixx) * p, q, N));
+    const double qr = RL4_FMA(q, sphi, r * cphi);
 
-    dx[RL4_CIT_P] = (P->Izz * Lp + P->Ixz * Np) / gam;
-    dx[RL4_CIT_Q] = (M - (P->Ixx - P->Izz) * p * r - P->Ixz * (p * p - r * r)) / P->Iyy;
-    dx[RL4_CIT_R] = (P->Ixz * Lp + P->Ixx * Np) / gam;
+    dx[RL4_CIT_P] = RL4_FMA(P->Izz, Lp, P->Ixz * Np) * P->inv_gam;
+    dx[RL4_CIT_Q] = RL4_FMA(-P->Ixz, RL4_FMA(p, p, -r * r), RL4_FMA(-(P->Ixx - P->Izz) * p, r, M)) * P->inv_Iyy;
+    dx[RL4_CIT_R] = RL4_FMA(P->Ixz, Lp, P->Ixx * Np) * P->inv_gam;
     dx[RL4_CIT_V] = Vd;
-    dx[RL4_CIT_ALPHA] = (ub * wd - wb * ud) / uw2;
-    dx[RL4_CIT_BETA] = (vd * V - vb * Vd) / (V * sqrt(uw2));
-    dx[RL4_CIT_PHI] = p + (sth / cth) * (q * sphi + r * cphi);
-    dx[RL4_CIT_THETA] = q * cphi - r * sphi;
-    dx[RL4_CIT_PSI] = (q * sphi + r * cphi) / cth;
-    dx[RL4_CIT_H] = ub * sth - vb * sphi * cth - wb * cphi * cth;
-    dx[RL4_CIT_XE] = ub * cth * cpsi + vb * (sphi * sth * cpsi - cphi * spsi) + wb * (cphi * sth * cpsi + sphi * spsi);
-    dx[RL4_CIT_YE] = ub * cth * spsi + vb * (sphi * sth * spsi + cphi * cpsi) + wb * (cphi * sth * spsi - sphi * cpsi);
+    dx[RL4_CIT_ALPHA] = RL4_FMA(ub, wd, -wb * ud) * (iVc * iVc);
+    dx[RL4_CIT_BETA] = RL4_FMA(vd, V, -vb * Vd) * (invV * iVc);
+    dx[RL4_CIT_PHI] = RL4_FMA(sth * inv_cth, qr, p);
+    dx[RL4_CIT_THETA] = RL4_FMA(q, cphi, -r * sphi);
+    dx[RL4_CIT_PSI] = qr * inv_cth;
+    dx[RL4_CIT_H] = RL4_FMA(ub, sth, -RL4_FMA(vb * sphi, cth, (wb * cphi) * cth));
+    {
+        const double a1 = RL4_FMA(sphi * sth, cpsi, -cphi * spsi), a2 = RL4_FMA(cphi * sth, cpsi, sphi * spsi);
+        const double b1 = RL4_FMA(sphi * sth, spsi, cphi * cpsi), b2 = RL4_FMA(cphi * sth, spsi, -sphi * cpsi);
+        dx[RL4_CIT_XE] = RL4_FMA(ub * cth, cpsi, RL4_FMA(vb, a1, wb * a2));
+        dx[RL4_CIT_YE] = RL4_FMA(ub * cth, spsi, RL4_FMA(vb, b1, wb * b2));
+    }
 }
 
 /* one fixed step, input held constant over the step (zero-order hold, like Simulink's fixed-step solvers) */
@@ -230,6 +249,7 @@ RL4_HD void rl4_cit_default_params(rl4_cit_params* P)
     P->CL0 = CLt - P->CLa * al_e - P->CLde * de;
     P->Cm0 = -(P->Cma * al + P->Cmstall * al_x + P->Cmde * de);
     P->Tstatic = T / (pow(rho / 1.225, 0.7) * thr);
+    rl4_cit_finalize(P);
 }
 
 #endif

@@ -12,7 +12,8 @@ from . import sp_c
 PLANT_FIELDS = ["m", "S", "c", "b", "Ixx", "Iyy", "Izz", "Ixz", "g", "CL0", "CLa", "CLq", "CLde", "CLflap", "al_stall",
                 "CD0", "CDk", "CDgear", "CDflap", "CDstall", "Cm0", "Cma", "Cmq", "Cmde", "Cmflap", "Cmstall",
                 "CYb", "CYp", "CYr", "CYda", "CYdr", "Clb", "Clp", "Clr", "Clda", "Cldr",
-                "Cnb", "Cnp", "Cnr", "Cnda", "Cndr", "Tstatic"]
+                "Cnb", "Cnp", "Cnr", "Cnda", "Cndr", "Tstatic",
+                "inv_m", "inv_Iyy", "inv_gam", "inv_al_stall", "inv_c", "inv_b"]
 PLANT_DTYPE = np.dtype([(f, "f8") for f in PLANT_FIELDS], align=True)
 
 CFG_DTYPE = np.dtype([

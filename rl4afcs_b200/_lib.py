@@ -68,7 +68,8 @@ INTEGRATOR = {"rk4": 0, "ode5": 1}
 CIT_FIELDS = ["m", "S", "c", "b", "Ixx", "Iyy", "Izz", "Ixz", "g", "CL0", "CLa", "CLq", "CLde", "CLflap", "al_stall",
               "CD0", "CDk", "CDgear", "CDflap", "CDstall", "Cm0", "Cma", "Cmq", "Cmde", "Cmflap", "Cmstall",
               "CYb", "CYp", "CYr", "CYda", "CYdr", "Clb", "Clp", "Clr", "Clda", "Cldr",
-              "Cnb", "Cnp", "Cnr", "Cnda", "Cndr", "Tstatic"]
+              "Cnb", "Cnp", "Cnr", "Cnda", "Cndr", "Tstatic",
+              "inv_m", "inv_Iyy", "inv_gam", "inv_al_stall", "inv_c", "inv_b"]
 
 
 class CitParams(ctypes.Structure):
