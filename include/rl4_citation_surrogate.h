@@ -80,9 +80,18 @@ RL4_HD double rl4_cit_density(double h)
 }
 
 #if defined(__CUDA_ARCH__)
-/* exact-zero shortcut: in symmetric flight (da = dr = 0) beta, phi and psi are identically zero, and
- * sin(+-0) = +-0, cos(0) = 1 are what sincos returns anyway */
-#define RL4_SINCOS(a, s, c) do { if ((a) == 0.0) { (s) = (a); (c) = 1.0; } else sincos((a), &(s), &(c)); } while (0)
+/* One out-of-line copy of sincos (values in registers, no pointers): the derivative is inlined 4-6 times per step with
+ * five sincos each, and CUDA's inlined double sincos is ~86 SASS instructions -- that alone was 20 % of the fused
+ * kernel's code and pushed it out of the instruction cache (profiles/README.md).
+ * Exact-zero shortcut: in symmetric flight (da = dr = 0) beta, phi and psi are identically zero, and
+ * sin(+-0) = +-0, cos(0) = 1 are what sincos returns anyway. */
+static __device__ __noinline__ double2 rl4_sincos_ool(double a)
+{
+    double2 r;
+    sincos(a, &r.x, &r.y);
+    return r;
+}
+#define RL4_SINCOS(a, s, c) do { if ((a) == 0.0) { (s) = (a); (c) = 1.0; } else { const double2 sc_ = rl4_sincos_ool(a); (s) = sc_.x; (c) = sc_.y; } } while (0)
 #else
 #define RL4_SINCOS(a, s, c) do { (s) = sin(a); (c) = cos(a); } while (0)
 #endif

@@ -109,7 +109,7 @@ __device__ __forceinline__ TN nl_actor(const TN (&s)[4], const TN* __restrict__ 
 }
 
 // Ce500NonLinear.step without the agent (envs/nonlinear/env.py:182-256)
-template <bool PER_AGENT>
+template <bool PER_AGENT, int INTEG>
 __device__ __forceinline__ void nl_env_step(const rl4_nl_params& p, const NlHp<PER_AGENT>& hv, int stepp, double theta_ref_k,
                                             const double (&act)[3], double (&x)[12], double (&x_act)[3], double (&surf)[3],
                                             double& e_phi, double& e_th, double& e_psi, double& reward, double& rg2)
@@ -150,7 +150,7 @@ __device__ __forceinline__ void nl_env_step(const rl4_nl_params& p, const NlHp<P
     double u[11];
 #pragma unroll
     for (int i = 0; i < 11; ++i) u[i] = p.trim_input[i] + eff[i];                  // env.py:207-208
-    if (p.integrator == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(&p.plant, x, u, p.dt);
+    if (INTEG == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(&p.plant, x, u, p.dt);   // compile-time: one integrator's code per kernel
     else rl4_cit_step_ode5(&p.plant, x, u, p.dt);                                  // env.py:210
     const double Q = hv.hp(RL4_NHP_Q_SYM);
     e_phi = x[6] - 0.0; e_th = x[7] - theta_ref_k; e_psi = x[8] - 0.0;            // env.py:215 (state - ref)
@@ -168,11 +168,12 @@ __device__ __forceinline__ double nl_decay(double a, double b, double c, bool f3
 }
 __device__ __forceinline__ bool nl_isclose(double a, double b) { return fabs(a - b) <= (1e-8 + 1e-5 * fabs(b)); }
 
-template <typename TN, bool PER_AGENT, bool LOG>
+template <typename TN, int INTEG, bool LOG>
 __global__ void __launch_bounds__(RL4_NL_BLOCK, RL4_NL_MINB)
 nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict__ theta_ref, const float* __restrict__ noise,
               int64_t noise_stride, int k0, int n_steps, const rl4_nl_state st, int64_t n_agents, const rl4_sp_log lg)
 {
+    constexpr bool PER_AGENT = true;     // per-agent overrides are a pointer test + load; negligible next to the plant
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_agents) return;
     const NlHp<PER_AGENT> hv{p, i};
@@ -213,7 +214,7 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
         // ---- env.step(self._get_action(a))  (objects.py:1497, 1448-1455)
         const double act[3] = {(double)a_k, 0.0, 0.0};
         double surf[3], e_phi, e_th, e_psi, reward, rg2;
-        nl_env_step<PER_AGENT>(p, hv, stepp, __ldg(theta_ref + k), act, x, x_act, surf, e_phi, e_th, e_psi, reward, rg2);
+        nl_env_step<PER_AGENT, INTEG>(p, hv, stepp, __ldg(theta_ref + k), act, x, x_act, surf, e_phi, e_th, e_psi, reward, rg2);
         stepp += 1;
         const double x_next_lon[3] = {x[4], x[7], x[1]};                           // env.py:231
         bool nans = false;
@@ -498,34 +499,39 @@ nl_env_step_kernel(const __grid_constant__ rl4_nl_params p, const double* __rest
     double x[12], xa[3], act[3], surf[3], e_phi, e_th, e_psi, reward, rg2;
     for (int j = 0; j < 12; ++j) x[j] = x_full[j * S + i];
     for (int j = 0; j < 3; ++j) { xa[j] = x_act_p[j * S + i]; act[j] = action[j * S + i]; }
-    nl_env_step<true>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2);
+    if (p.integrator == RL4_CIT_INTEGRATOR_RK4)
+        nl_env_step<true, RL4_CIT_INTEGRATOR_RK4>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2);
+    else
+        nl_env_step<true, RL4_CIT_INTEGRATOR_ODE5>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2);
     for (int j = 0; j < 12; ++j) x_full[j * S + i] = x[j];
     for (int j = 0; j < 3; ++j) x_act_p[j * S + i] = xa[j];
     out_mdp[i] = x[4]; out_mdp[S + i] = x[7]; out_mdp[2 * S + i] = x[1]; out_mdp[3 * S + i] = e_th;
     out_reward[i] = reward; out_e[i] = e_th;
 }
 
-template <typename TN, bool PA, bool LOG>
+template <typename TN, int INTEG, bool LOG>
 static int nl_launch_one(const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride, int k0,
                          int n_steps, rl4_nl_state st, int64_t n, rl4_sp_log lg, unsigned grid, cudaStream_t s)
 {
     const size_t smem = (sizeof(double) * 50 + sizeof(TN) * 70) * RL4_NL_BLOCK;
     static bool configured = false;
     if (!configured) {
-        RL4_CUDA(cudaFuncSetAttribute(nl_run_kernel<TN, PA, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        RL4_CUDA(cudaFuncSetAttribute(nl_run_kernel<TN, INTEG, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    nl_run_kernel<TN, PA, LOG><<<grid, RL4_NL_BLOCK, smem, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg);
+    nl_run_kernel<TN, INTEG, LOG><<<grid, RL4_NL_BLOCK, smem, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg);
     return 0;
 }
 
 template <typename TN>
 static int nl_launch(const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride, int k0, int n_steps,
-                     rl4_nl_state st, int64_t n, rl4_sp_log lg, bool log, bool per_agent, unsigned grid, cudaStream_t s)
+                     rl4_nl_state st, int64_t n, rl4_sp_log lg, bool log, bool /*per_agent*/, unsigned grid, cudaStream_t s)
 {
-    if (log) return nl_launch_one<TN, true, true>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s);
-    if (per_agent) return nl_launch_one<TN, true, false>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s);
-    return nl_launch_one<TN, false, false>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s);
+    const bool rk4 = (p->integrator == RL4_CIT_INTEGRATOR_RK4);
+    if (log) return rk4 ? nl_launch_one<TN, RL4_CIT_INTEGRATOR_RK4, true>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s)
+                        : nl_launch_one<TN, RL4_CIT_INTEGRATOR_ODE5, true>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s);
+    return rk4 ? nl_launch_one<TN, RL4_CIT_INTEGRATOR_RK4, false>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s)
+               : nl_launch_one<TN, RL4_CIT_INTEGRATOR_ODE5, false>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s);
 }
 
 }  // namespace rl4
