@@ -8,6 +8,7 @@
 //
 // Arithmetic: built with -fmad=false, FMAs explicit; numpy-side `@` orders as measured for these
 // shapes, TensorFlow-side `@` in-order chains, tanh = t13.
+#define RL4_SLOWPATH_OUT_OF_LINE 1
 #include "rl4_math.cuh"
 #include "rl4_runtime.h"
 #include "../../include/rl4afcs_b200.h"
@@ -236,9 +237,29 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
             for (int j = 1; j < 10; ++j) { acc = nfma<TN>(hc[j], W2c[j * 3 + q], acc); acc2 = nfma<TN>(ht[j], W2t[j * 3 + q], acc2); }
             lam[q] = acc; lt[q] = acc2;
         }
+        // actor(s_prev) with trace pass 1 (objects.py:1310) and, for k > 0, actor(s_random) with trace pass 2
+        // (objects.py:1375-1378).  The second pass only needs the actor weights and the trace, which nothing touches in
+        // between, so both passes run back to back through ONE copy of the code (a two-trip loop, not unrolled).
         const int elig_a = hv.hpi(RL4_NHPI_ELIG_A);
-        TN ha[10], ai1;
-        const TN a_next = nl_actor<TN>(s_prev, W1a, W2a, Ea, elig_a, gl, ha, ai1); // actor(s_prev), trace pass 1
+        TN ha[10], ai1 = TN(0), a_next = TN(0), a_random = TN(0);
+        {
+            const TN nz = (TN)__ldg(noise + (int64_t)(k - k0) * noise_stride + i);
+            const int n_pass = (k > 0) ? 2 : 1;
+#pragma unroll 1
+            for (int pass = 0; pass < n_pass; ++pass) {
+                TN sin[4], hh[10], aa1;
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) sin[ii] = pass ? (nz * (TN)p.noise_std[ii] + s_prev[ii]) : s_prev[ii];
+                const TN aout = nl_actor<TN>(sin, W1a, W2a, Ea, elig_a, gl, hh, aa1);
+                if (pass == 0) {
+                    a_next = aout; ai1 = aa1;
+#pragma unroll
+                    for (int j = 0; j < 10; ++j) ha[j] = hh[j];
+                } else {
+                    a_random = aout;
+                }
+            }
+        }
         TN dads[4];                                                                // tape.gradient(a, s_prev) (objects.py:1323)
         {
             const TN g_o = TN(1) * ai1;
@@ -317,13 +338,7 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
 #pragma unroll
                 for (int j = 0; j < 30; ++j) W2t[j] = omt * W2t[j] + tt * W2c[j];
             }
-            {   // actor (objects.py:1375-1388): one N(0,1) draw, second trace pass at s_random, smoothness terms
-                const TN nz = (TN)__ldg(noise + (int64_t)(k - k0) * noise_stride + i);
-                TN s_rand[4];
-#pragma unroll
-                for (int ii = 0; ii < 4; ++ii) s_rand[ii] = nz * (TN)p.noise_std[ii] + s_prev[ii];
-                TN hr[10], ai1r;
-                const TN a_random = nl_actor<TN>(s_rand, W1a, W2a, Ea, elig_a, gl, hr, ai1r);
+            {   // actor (objects.py:1379-1388): smoothness terms, loss, update (the s_random pass ran above)
                 const TN dT = a_k - a_next, dS = a_k - a_random;
                 const TN L_T = nsqrt(dT * dT), L_S = nsqrt(dS * dS);
                 TN v[3];
