@@ -292,6 +292,14 @@ int rl4_nl_init(int policy, const rl4_nl_params* p, const double* w1a, const dou
  * log: NULL or RL4_NLL_COUNT fields for the first n_agents_logged agents, layout as rl4_sp_log. */
 int rl4_nl_run(int policy, const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride,
                int32_t k0, int32_t n_steps, rl4_nl_state st, int64_t n_agents, rl4_sp_log log, void* stream);
+/* Critic_big.call (objects.py:294-339): s [4][stride], w1 [40][stride] ((4,10) row-major), w2 [30][stride] ((10,3)
+ * row-major), all TN; out_lambda [3][stride]. */
+int rl4_nl_critic_forward(int policy, const void* s, void* w1, void* w2, void* out_lambda, int64_t stride,
+                          int64_t n_agents, void* stream);
+/* Actor_big.call (objects.py:374-407) and tape.gradient(a, s) (objects.py:1323): w1 [40][stride], w2 [10][stride] (TN),
+ * E [50][stride] (double, in/out when trace != 0), out_a [stride], out_dads [4][stride] (may be NULL). */
+int rl4_nl_actor_forward(int policy, const void* s, void* w1, void* w2, double* E, void* out_a, void* out_dads,
+                         double gamma_lambda, int32_t elig, int32_t trace, int64_t stride, int64_t n_agents, void* stream);
 /* Ce500NonLinear.step alone (envs/nonlinear/env.py:182-256): action [3][stride] normalised commands (double),
  * x_full [12][stride], x_act [3][stride] in/out; out_mdp [4][stride], out_reward, out_e_theta [stride]. */
 int rl4_nl_env_step(const rl4_nl_params* p, const double* theta_ref, int32_t stepp, double* x_full, double* x_act,

@@ -51,6 +51,13 @@ template <typename T> struct Strided {
     __device__ __forceinline__ T& operator[](int j) const { return p[j * RL4_NL_BLOCK]; }
 };
 
+// element j of a per-agent array stored in a global SoA plane (step-API kernels)
+template <typename T> struct PlaneCol {
+    T* p;
+    int64_t stride;
+    __device__ __forceinline__ T& operator[](int j) const { return p[(int64_t)j * stride]; }
+};
+
 // hidden layer of a 4-10-k net (Network.base_call, objects.py:111-139)
 template <typename TN, typename WA>
 __device__ __forceinline__ void nl_hidden(const TN (&s)[4], const WA W1, TN (&h)[10])
@@ -69,8 +76,8 @@ __device__ __forceinline__ void nl_hidden(const TN (&s)[4], const WA W1, TN (&h)
 }
 
 // Actor_big.call (objects.py:374-407): forward + trace update
-template <typename TN, typename EA>
-__device__ __forceinline__ TN nl_actor(const TN (&s)[4], const TN* __restrict__ W1, const TN* __restrict__ W2, const EA Ea,
+template <typename TN, typename WA, typename EA>
+__device__ __forceinline__ TN nl_actor(const TN (&s)[4], const WA W1, const WA W2, const EA Ea,
                                        int elig, double gl, TN (&h)[10], TN& ai1)
 {
     nl_hidden<TN>(s, W1, h);
@@ -549,6 +556,54 @@ static int nl_launch(const rl4_nl_params* p, const double* theta_ref, const floa
                : nl_launch_one<TN, RL4_CIT_INTEGRATOR_ODE5, false>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s);
 }
 
+// Critic_big.call (objects.py:294-339): forward of the 4-10-3 critic (its trace is never formed, :304-305)
+template <typename TN>
+__global__ void __launch_bounds__(128)
+nl_critic_forward_kernel(const TN* __restrict__ s_in, TN* w1, TN* w2, TN* __restrict__ out_lambda, int64_t S, int64_t n_agents)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_agents) return;
+    TN s[4], h[10];
+    for (int j = 0; j < 4; ++j) s[j] = s_in[j * S + i];
+    nl_hidden<TN>(s, PlaneCol<TN>{w1 + i, S}, h);
+    const PlaneCol<TN> W2{w2 + i, S};
+    for (int q = 0; q < 3; ++q) {
+        TN acc = h[0] * W2[q];
+        for (int j = 1; j < 10; ++j) acc = nfma<TN>(h[j], W2[j * 3 + q], acc);
+        out_lambda[q * S + i] = acc;
+    }
+}
+
+// Actor_big.call (objects.py:374-407) + tape.gradient(a, s) (objects.py:1323)
+template <typename TN>
+__global__ void __launch_bounds__(128)
+nl_actor_forward_kernel(const TN* __restrict__ s_in, TN* w1, TN* w2, double* Eplane, TN* __restrict__ out_a, TN* __restrict__ out_dads,
+                        double gl, int elig, int trace, int64_t S, int64_t n_agents)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_agents) return;
+    TN s[4], h[10], ai1;
+    for (int j = 0; j < 4; ++j) s[j] = s_in[j * S + i];
+    const PlaneCol<TN> W1{w1 + i, S}, W2{w2 + i, S};
+    double Etmp[50];
+    TN a;
+    if (trace) {
+        a = nl_actor<TN>(s, W1, W2, PlaneCol<double>{Eplane + i, S}, elig, gl, h, ai1);
+    } else {
+        for (int j = 0; j < 50; ++j) Etmp[j] = 0.0;
+        a = nl_actor<TN>(s, W1, W2, (double*)Etmp, RL4_ELIG_NONE, gl, h, ai1);
+    }
+    out_a[i] = a;
+    if (out_dads) {
+        const TN g_o = TN(1) * ai1;
+        for (int ii = 0; ii < 4; ++ii) {
+            TN acc = ((g_o * W2[0]) * (TN(1) - h[0] * h[0])) * W1[ii * 10];
+            for (int j = 1; j < 10; ++j) acc = nfma<TN>((g_o * W2[j]) * (TN(1) - h[j] * h[j]), W1[ii * 10 + j], acc);
+            out_dads[ii * S + i] = acc;
+        }
+    }
+}
+
 }  // namespace rl4
 
 using namespace rl4;
@@ -613,6 +668,34 @@ int rl4_nl_run(int policy, const rl4_nl_params* p, const double* theta_ref, cons
     else { set_error("rl4_nl_run: policy %d not supported on the nonlinear path (mixed or fp64)", policy); return -1; }
     if (rc) return rc;
     return check_launch("nl_run_kernel");
+}
+
+int rl4_nl_critic_forward(int policy, const void* s, void* w1, void* w2, void* out_lambda, int64_t stride, int64_t n, void* stream)
+{
+    RL4_REQUIRE(s && w1 && w2 && out_lambda, "NULL argument");
+    RL4_REQUIRE(n >= 0 && stride >= n, "bad size");
+    if (n == 0) return 0;
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (policy == RL4_MIXED) nl_critic_forward_kernel<float><<<grid, 128, 0, st>>>((const float*)s, (float*)w1, (float*)w2, (float*)out_lambda, stride, n);
+    else if (policy == RL4_FP64) nl_critic_forward_kernel<double><<<grid, 128, 0, st>>>((const double*)s, (double*)w1, (double*)w2, (double*)out_lambda, stride, n);
+    else { set_error("rl4_nl_critic_forward: policy %d not supported on the nonlinear path", policy); return -1; }
+    return check_launch("nl_critic_forward_kernel");
+}
+
+int rl4_nl_actor_forward(int policy, const void* s, void* w1, void* w2, double* E, void* out_a, void* out_dads, double gamma_lambda,
+                         int32_t elig, int32_t trace, int64_t stride, int64_t n, void* stream)
+{
+    RL4_REQUIRE(s && w1 && w2 && out_a && (E || !trace), "NULL argument");
+    RL4_REQUIRE(n >= 0 && stride >= n, "bad size");
+    RL4_REQUIRE(elig >= RL4_ELIG_NONE && elig <= RL4_ELIG_REPLACING, "bad elig");
+    if (n == 0) return 0;
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (policy == RL4_MIXED) nl_actor_forward_kernel<float><<<grid, 128, 0, st>>>((const float*)s, (float*)w1, (float*)w2, E, (float*)out_a, (float*)out_dads, gamma_lambda, elig, trace, stride, n);
+    else if (policy == RL4_FP64) nl_actor_forward_kernel<double><<<grid, 128, 0, st>>>((const double*)s, (double*)w1, (double*)w2, E, (double*)out_a, (double*)out_dads, gamma_lambda, elig, trace, stride, n);
+    else { set_error("rl4_nl_actor_forward: policy %d not supported on the nonlinear path", policy); return -1; }
+    return check_launch("nl_actor_forward_kernel");
 }
 
 int rl4_nl_env_step(const rl4_nl_params* p, const double* theta_ref, int32_t stepp, double* x_full, double* x_act,

@@ -376,6 +376,27 @@ class _BigNetView:
 class Critic_big(_BigNetView):
     """4-10-3 critic of the nonlinear task; its gradient comes from autodiff (objects.py:304-305,1365)."""
 
+    def __call__(self, s):
+        """s (B,4) or (B,1,4) -> lambda (B,1,3) (objects.py:294-339; no trace is formed for this net)."""
+        e = self._eng
+        sp = torch.as_tensor(s, device=e.device).to(e.tn).reshape(self.batch, 4).t().contiguous()
+        out = torch.empty((3, e.stride), dtype=e.tn, device=e.device)
+        with torch.cuda.device(e.device):
+            rc = e.lib.rl4_nl_critic_forward(e.policy_id, sp.data_ptr(), e.net_field(self._w1, 40).data_ptr(),
+                                             e.net_field(self._w2, 30).data_ptr(), out.data_ptr(), e.stride, self.batch, e._stream())
+            _lib.check(rc, "rl4_nl_critic_forward")
+        return out[:, : self.batch].t().reshape(self.batch, 1, 3)
+
+    call = __call__
+
+    def soft_update(self, source_weights, tau):
+        """target <- (1 - tau) target + tau source (objects.py:353-361), separately rounded."""
+        for tgt, src in zip(self.trainable_weights, source_weights):
+            src = torch.as_tensor(src, device=tgt.device).to(tgt.dtype).reshape(tgt.shape)
+            omt = torch.tensor(1.0 - tau, dtype=torch.float64).to(tgt.dtype)
+            tt = torch.tensor(float(tau), dtype=torch.float64).to(tgt.dtype)
+            tgt.copy_(tgt.mul(omt).add_(src.mul(tt)))
+
 
 class Actor_big(_BigNetView):
     """4-10-1 actor with the hand-written Jacobian trace E (1,50) (objects.py:385-392)."""
@@ -383,6 +404,31 @@ class Actor_big(_BigNetView):
     @property
     def E(self) -> torch.Tensor:
         return self._eng.env_field("EA", 50).t().reshape(self.batch, 1, 50)
+
+    def __call__(self, s, trace=True, return_input_gradient: bool = False):
+        """s (B,4) -> a (B,1,1); with ``trace`` the Jacobian trace E is updated (objects.py:374-407)."""
+        e = self._eng
+        sp = torch.as_tensor(s, device=e.device).to(e.tn).reshape(self.batch, 4).t().contiguous()
+        out = torch.empty(e.stride, dtype=e.tn, device=e.device)
+        dads = torch.empty((4, e.stride), dtype=e.tn, device=e.device)
+        gl = float(self.gamma_lambda[0]) if torch.is_tensor(self.gamma_lambda) else float(self.gamma_lambda)
+        with torch.cuda.device(e.device):
+            rc = e.lib.rl4_nl_actor_forward(e.policy_id, sp.data_ptr(), e.net_field(self._w1, 40).data_ptr(),
+                                            e.net_field(self._w2, 10).data_ptr(), e.env_field("EA", 50).data_ptr(), out.data_ptr(),
+                                            dads.data_ptr(), gl, _lib.ELIG[self.eligibility], 1 if trace else 0, e.stride,
+                                            self.batch, e._stream())
+            _lib.check(rc, "rl4_nl_actor_forward")
+        self.input_gradient = dads[:, : self.batch].t().clone()                 # tape.gradient(a, s) (objects.py:1323)
+        a = out[: self.batch].reshape(self.batch, 1, 1)
+        return (a, self.input_gradient) if return_input_gradient else a
+
+    call = __call__
+
+    def get_weight_update(self, loss):
+        """loss (B,1,1) -> [W1_update (B,4,10), W2_update (B,10,1)] = loss * E (objects.py:417-427)."""
+        e = self._eng
+        g = torch.as_tensor(loss, device=e.device).to(e.tn).reshape(self.batch, 1) * self.E.reshape(self.batch, 50).to(e.tn)
+        return [g[:, 10:].reshape(self.batch, 10, 4).transpose(1, 2), g[:, 0:10].reshape(self.batch, 10, 1)]
 
 
 class _RLSView:

@@ -133,3 +133,43 @@ def test_agents_learn_to_track_on_the_surrogate(nl):
 def eng_field(name):
     from rl4afcs_b200 import _lib
     return _lib.NLL[name]
+
+
+@pytest.mark.parametrize("policy", ["mixed", "fp64"])
+def test_step_level_actor_big_critic_big(nl, policy):
+    """Critic_big.__call__, Actor_big.__call__ (+ trace, da/ds), get_weight_update, soft_update vs the oracle's
+    per-step log from identical inputs (objects.py:294-339, 374-427)."""
+    from rl4afcs_b200.objects import Actor_big, Critic_big
+    from rl4afcs_b200 import nl_engine
+
+    n, steps = 40, 30
+    eng, st, cfg, th = _setup(nl, n, policy, seed=9)
+    rng = np.random.default_rng(4)
+    noise = rng.standard_normal((steps, n)).astype(np.float32)
+    actor = Actor_big(eng, "W1A", "W2A", 1, "accumulating")
+    critic = Critic_big(eng, "W1C", "W2C", 3, 1233)
+    target = Critic_big(eng, "W1T", "W2T", 3, 1233)
+    for k in range(steps):
+        pre = st.copy()
+        lg = nl.run(policy, cfg, th, noise[k:k + 1], st, k, 1, tanh="t13", n_log=n)[:, 0]
+        _util_nl.oracle_to_engine(pre, eng)                      # objects now see the pre-step weights / trace
+        lam = critic(pre["s_prev"])
+        lam_t = target(lg["s_next"])
+        a, dads = actor(pre["s_prev"], trace=True, return_input_gradient=True)
+        assert np.array_equal(lam.double().cpu().numpy().reshape(n, 3), lg["lam"]), k
+        assert np.array_equal(lam_t.double().cpu().numpy().reshape(n, 3), lg["lam_t"]), k
+        assert np.array_equal(a.double().cpu().numpy().ravel(), lg["a_next"]), k
+        assert np.array_equal(dads.double().cpu().numpy(), lg["dads"]), k
+        if k > 0:
+            # second trace pass at s_random (objects.py:1375-1378), then loss * E
+            s_rand = (torch.as_tensor(noise[k]).cuda().to(eng.tn)[:, None] * torch.as_tensor(cfg["noise_std"][0]).cuda().to(eng.tn)[None, :]
+                      + torch.as_tensor(pre["s_prev"]).cuda().to(eng.tn))
+            a_r = actor(s_rand, trace=True)
+            assert np.array_equal(a_r.double().cpu().numpy().ravel(), lg["a_random"]), k
+            W1u, W2u = actor.get_weight_update(torch.as_tensor(lg["loss_grad"]).reshape(n, 1, 1))
+            lr = torch.as_tensor(pre["lr_a"]).cuda().to(eng.tn)
+            W1, W2 = actor.trainable_weights
+            W1.copy_(W1 - lr[:, None, None] * W1u); W2.copy_(W2 - lr[:, None, None] * W2u)
+            assert np.array_equal(W1.double().cpu().numpy().reshape(n, 40), st["W1a"]), k
+            assert np.array_equal(W2.double().cpu().numpy().reshape(n, 10), st["W2a"]), k
+            assert np.array_equal(actor.E.cpu().numpy().reshape(n, 50), st["Ea"]), k
