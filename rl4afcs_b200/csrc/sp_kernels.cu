@@ -11,7 +11,10 @@
 
 namespace rl4 {
 
-constexpr int kBlock = 128;
+#ifndef RL4_SP_BLOCK
+#define RL4_SP_BLOCK 128
+#endif
+constexpr int kBlock = RL4_SP_BLOCK;
 // minimum resident CTAs per SM requested from ptxas, per dtype policy (tuned on B200, profiles/README.md)
 #ifndef RL4_MINB_FP64
 #define RL4_MINB_FP64 2
