@@ -27,15 +27,38 @@ struct HpView {
     }
 };
 
-template <typename TN, typename TE>
+#ifndef RL4_SP_BLOCK
+#define RL4_SP_BLOCK 128
+#endif
+
+// Small per-agent array that lives either in registers or in shared memory laid out [element][thread]
+// (conflict-free, static element index -> immediate offset).  The fp64 fused kernel keeps the parts of the state
+// that are touched only once or twice per step (target-critic weights, RLS parameters and covariance) in shared
+// memory so that 3 CTAs per SM fit the register file.
+template <typename T, int N, bool SM> struct Arr;
+template <typename T, int N> struct Arr<T, N, false> {
+    Rn<T> a[N];
+    __device__ __forceinline__ Rn<T>& operator[](int j) { return a[j]; }
+    __device__ __forceinline__ const Rn<T>& operator[](int j) const { return a[j]; }
+};
+template <typename T, int N> struct Arr<T, N, true> {
+    Rn<T>* p;
+    __device__ __forceinline__ Rn<T>& operator[](int j) const { return p[j * RL4_SP_BLOCK]; }
+};
+
+template <typename TN, typename TE, bool SM = false>
 struct SpAgent {
     using N = Rn<TN>;
     using E = Rn<TE>;
     // env plane
-    E x[2], xp[2], th[6], cv[9], cgp, eps[2], epsn, sumc, sumabse;
+    E x[2], xp[2], cgp, eps[2], epsn, sumc, sumabse;
+    Arr<TE, 6, SM> th;
+    Arr<TE, 9, SM> cv;
     E Ea[8], EcH[4], EcR0[4], EcR1[4];
     // net plane
-    N a, ap, W1a[4], W2a[4], W1c[4], W2c[8], W1t[4], W2t[8], Mp[4], eta_a, eta_c;
+    N a, ap, W1a[4], W2a[4], W1c[4], W2c[8], Mp[4], eta_a, eta_c;
+    Arr<TN, 4, SM> W1t;
+    Arr<TN, 8, SM> W2t;
     // int plane
     int cooldown, flags, diverged_step, conv_step;
 };
@@ -76,8 +99,8 @@ __device__ __forceinline__ void sp_env_step(Rn<TE> (&x)[2], Rn<TN> action_deg, R
 // Network.base_call hidden layers (objects.py:111-139) of critic, target critic and actor for the
 // scalar input z (Q1): h_j = tanh(z*W1_j), ai0_j = 1 - h_j^2.  The 12 tanh are one group so that
 // their dependent chains interleave (the three nets are independent).
-template <typename TN>
-__device__ __forceinline__ void sp_hidden3(Rn<TN> z, const Rn<TN> (&W1c)[4], const Rn<TN> (&W1t)[4], const Rn<TN> (&W1a)[4],
+template <typename TN, typename W1T>
+__device__ __forceinline__ void sp_hidden3(Rn<TN> z, const Rn<TN> (&W1c)[4], const W1T& W1t, const Rn<TN> (&W1a)[4],
                                            Rn<TN> (&hc)[4], Rn<TN> (&ht)[4], Rn<TN> (&ha)[4])
 {
     Rn<TN> pre[12], h[12];
@@ -103,8 +126,8 @@ __device__ __forceinline__ void sp_ai0(const Rn<TN> (&h)[4], Rn<TN> (&ai0)[4])
 }
 
 // (1,4)@(4,2) linear output layer, in-order FMA chain
-template <typename TN>
-__device__ __forceinline__ void sp_out2(const Rn<TN> (&h)[4], const Rn<TN> (&W2)[8], Rn<TN> (&out)[2])
+template <typename TN, typename W2T>
+__device__ __forceinline__ void sp_out2(const Rn<TN> (&h)[4], const W2T& W2, Rn<TN> (&out)[2])
 {
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -210,8 +233,8 @@ __device__ __forceinline__ void sp_actor_forward(Rn<TN> z, const Rn<TN> (&h)[4],
 }
 
 // RLS.update (objects.py:492-543).  X = [dx0; da0], Y = dx1.
-template <typename TE>
-__device__ __forceinline__ void sp_rls_update(Rn<TE> (&th)[6], Rn<TE> (&cv)[9], const Rn<TE> (&X)[3], const Rn<TE> (&Y)[2],
+template <typename TE, typename TH, typename CV>
+__device__ __forceinline__ void sp_rls_update(TH& th, CV& cv, const Rn<TE> (&X)[3], const Rn<TE> (&Y)[2],
                                               Rn<TE> rls_gamma, Rn<TE> (&eps)[2], Rn<TE>& eps_norm)
 {
     using E = Rn<TE>;
@@ -251,7 +274,10 @@ __device__ __forceinline__ void sp_rls_update(Rn<TE> (&th)[6], Rn<TE> (&cv)[9], 
         for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int j = 0; j < 3; ++j) num[i * 3 + j] = cv[i * 3 + j] - K[i] * CX[j];
-        div_group<9>(num, rls_gamma, cv);                        // objects.py:529-530
+        E quo[9];
+        div_group<9>(num, rls_gamma, quo);                       // objects.py:529-530
+#pragma unroll
+        for (int j = 0; j < 9; ++j) cv[j] = quo[j];
     }
     eps_norm = sqrt_rn(fma(eps[1], eps[1], eps[0] * eps[0]));    // objects.py:539
 }
@@ -259,8 +285,8 @@ __device__ __forceinline__ void sp_rls_update(Rn<TE> (&th)[6], Rn<TE> (&cv)[9], 
 // ---------------------------------------------------------------------------------------
 // One iteration of IDHPsp.train()'s loop body (objects.py:950-992) for one agent.
 // ---------------------------------------------------------------------------------------
-template <typename TN, typename TE, bool TRACES, bool PER_AGENT>
-__device__ __forceinline__ void sp_agent_step(SpAgent<TN, TE>& s, const rl4_sp_params& p, const HpView<PER_AGENT>& hv,
+template <typename TN, typename TE, bool TRACES, bool PER_AGENT, bool SM>
+__device__ __forceinline__ void sp_agent_step(SpAgent<TN, TE, SM>& s, const rl4_sp_params& p, const HpView<PER_AGENT>& hv,
                                               int k, double ref_base_k, SpStepOut<TN, TE>& o)
 {
     using N = Rn<TN>;

@@ -11,13 +11,10 @@
 
 namespace rl4 {
 
-#ifndef RL4_SP_BLOCK
-#define RL4_SP_BLOCK 128
-#endif
 constexpr int kBlock = RL4_SP_BLOCK;
 // minimum resident CTAs per SM requested from ptxas, per dtype policy (tuned on B200, profiles/README.md)
 #ifndef RL4_MINB_FP64
-#define RL4_MINB_FP64 2
+#define RL4_MINB_FP64 3
 #endif
 #ifndef RL4_MINB_MIXED
 #define RL4_MINB_MIXED 3
@@ -25,6 +22,18 @@ constexpr int kBlock = RL4_SP_BLOCK;
 #ifndef RL4_MINB_FP32
 #define RL4_MINB_FP32 4
 #endif
+#ifndef RL4_SMEM_FP64
+#define RL4_SMEM_FP64 1
+#endif
+#ifndef RL4_SMEM_MIXED
+#define RL4_SMEM_MIXED 0
+#endif
+#ifndef RL4_SMEM_FP32
+#define RL4_SMEM_FP32 0
+#endif
+template <typename TN, typename TE> struct UseSmem { static constexpr bool v = RL4_SMEM_FP64; };
+template <> struct UseSmem<float, double> { static constexpr bool v = RL4_SMEM_MIXED; };
+template <> struct UseSmem<float, float> { static constexpr bool v = RL4_SMEM_FP32; };
 template <typename TN, typename TE> struct MinBlocks { static constexpr int v = RL4_MINB_FP64; };
 template <> struct MinBlocks<float, double> { static constexpr int v = RL4_MINB_MIXED; };
 template <> struct MinBlocks<float, float> { static constexpr int v = RL4_MINB_FP32; };
@@ -36,8 +45,8 @@ template <typename T> struct Plane {
     __device__ __forceinline__ void st(int f, int64_t i, Rn<T> v) const { base[(int64_t)f * stride + i] = v.v; }
 };
 
-template <typename TN, typename TE>
-__device__ __forceinline__ void sp_load(SpAgent<TN, TE>& s, const rl4_sp_state& st, int64_t i, bool traces)
+template <typename TN, typename TE, bool SM>
+__device__ __forceinline__ void sp_load(SpAgent<TN, TE, SM>& s, const rl4_sp_state& st, int64_t i, bool traces)
 {
     const Plane<TE> e{(TE*)st.env, st.stride};
     const Plane<TN> n{(TN*)st.net, st.stride};
@@ -78,8 +87,8 @@ __device__ __forceinline__ void sp_load(SpAgent<TN, TE>& s, const rl4_sp_state& 
     s.conv_step = st.ints[(int64_t)RL4_SPI_CONV_STEP * st.stride + i];
 }
 
-template <typename TN, typename TE>
-__device__ __forceinline__ void sp_store(const SpAgent<TN, TE>& s, const rl4_sp_state& st, int64_t i)
+template <typename TN, typename TE, bool SM>
+__device__ __forceinline__ void sp_store(const SpAgent<TN, TE, SM>& s, const rl4_sp_state& st, int64_t i)
 {
     const Plane<TE> e{(TE*)st.env, st.stride};
     const Plane<TN> n{(TN*)st.net, st.stride};
@@ -114,9 +123,9 @@ __device__ __forceinline__ void sp_store(const SpAgent<TN, TE>& s, const rl4_sp_
 }
 
 // One row of IDHPsp._log (objects.py:651-726), SoA over the logged agents.
-template <typename TN, typename TE, int LOG>
+template <typename TN, typename TE, int LOG, bool SM>
 __device__ __forceinline__ void sp_write_log(const rl4_sp_log& lg, int64_t row, int64_t i, int k,
-                                             const SpAgent<TN, TE>& s, const SpStepOut<TN, TE>& o)
+                                             const SpAgent<TN, TE, SM>& s, const SpStepOut<TN, TE>& o)
 {
     const int nf = (LOG == RL4_LOG_FULL) ? RL4_LF_COUNT : RL4_LB_COUNT;
     double* b = lg.buf + (row * nf) * lg.n_agents_logged + i;
@@ -163,18 +172,25 @@ sp_run_kernel(const __grid_constant__ rl4_sp_params p, const double* __restrict_
               const rl4_sp_state st, int64_t n_agents, const rl4_sp_log lg)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr bool SM = UseSmem<TN, TE>::v && (LOG == RL4_LOG_NONE);
+    __shared__ Rn<TE> sm_e[SM ? 15 * kBlock : 1];
+    __shared__ Rn<TN> sm_n[SM ? 12 * kBlock : 1];
     if (i >= n_agents) return;
-    SpAgent<TN, TE> s;
-    sp_load<TN, TE>(s, st, i, TRACES);
+    SpAgent<TN, TE, SM> s;
+    if constexpr (SM) {
+        s.th.p = sm_e + threadIdx.x; s.cv.p = sm_e + 6 * kBlock + threadIdx.x;
+        s.W1t.p = sm_n + threadIdx.x; s.W2t.p = sm_n + 4 * kBlock + threadIdx.x;
+    }
+    sp_load<TN, TE, SM>(s, st, i, TRACES);
     const HpView<PER_AGENT> hv{p, i};
     SpStepOut<TN, TE> o;
     const bool logged = (LOG != RL4_LOG_NONE) && i < lg.n_agents_logged;
     int k = k0;
     for (; k < k0 + n_steps; ++k) {
         if (s.diverged_step >= 0) break;            // the reference left its loop (objects.py:991)
-        sp_agent_step<TN, TE, TRACES, PER_AGENT>(s, p, hv, k, __ldg(ref_base + k), o);
+        sp_agent_step<TN, TE, TRACES, PER_AGENT, SM>(s, p, hv, k, __ldg(ref_base + k), o);
         if (LOG != RL4_LOG_NONE) {
-            if (logged && (k - k0) % lg.every == 0) sp_write_log<TN, TE, LOG>(lg, (k - k0) / lg.every, i, k, s, o);
+            if (logged && (k - k0) % lg.every == 0) sp_write_log<TN, TE, LOG, SM>(lg, (k - k0) / lg.every, i, k, s, o);
         }
     }
     if (LOG != RL4_LOG_NONE) {                      // NaN-fill the rows after a divergence (objects.py:656-679)
@@ -187,7 +203,7 @@ sp_run_kernel(const __grid_constant__ rl4_sp_params p, const double* __restrict_
             }
         }
     }
-    sp_store<TN, TE>(s, st, i);
+    sp_store<TN, TE, SM>(s, st, i);
 }
 
 // IDHPsp.__init__ + train() prologue (objects.py:552-615, 843-851, 911-948); env.reset (env.py:222-258)
@@ -231,7 +247,7 @@ sp_init_kernel(const __grid_constant__ rl4_sp_params p, const double* __restrict
     s.eta_a = N(TN(hv.hp(RL4_HP_ETA_A_H)));                              // objects.py:915-919
     s.eta_c = N(TN(hv.hp(RL4_HP_ETA_C_H)));
     s.cooldown = 0; s.flags = RL4_SPF_LR_INIT; s.diverged_step = -1; s.conv_step = -1;
-    sp_store<TN, TE>(s, st, i);
+    sp_store<TN, TE, false>(s, st, i);
 }
 
 // ---- step-API kernels ----------------------------------------------------------------
