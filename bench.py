@@ -32,9 +32,12 @@ import numpy as np  # noqa: E402
 # Algorithmic FLOPs per agent-step of the fp64/fp32 path with the idhp_sp.py defaults (multistep
 # on, no traces); FMA = 2, div = sqrt = 1.  Derivation in DESIGN.md "Roofline accounting".
 FLOP_PER_AGENT_STEP = 388 + 13 * 38 + 13 + 2          # body + 13 tanh (37 flop + 1 div) + 13 div + 2 sqrt
-# FP64 warp-instructions per agent-step of the fp64 kernel, measured with ncu (profiles/README.md):
-# sm__pipe_fp64_cycles_active 69.3 % x 2395 cycles per warp-step / 2 issue cycles per FP64 instruction
-FP64_INSTR_PER_AGENT_STEP = 830
+# FP64 warp-instructions per agent-step of the fp64 kernel, measured with ncu (profiles/prof_sp_fp64_r01c_raw.csv):
+# sm__pipe_fp64_cycles_active 69.5 % x 2450 cycles per warp-step / 2 issue cycles per FP64 instruction
+FP64_INSTR_PER_AGENT_STEP = 850
+# DRAM traffic of the fused kernel per agent and launch (dram__bytes_read + dram__bytes_write of the same capture,
+# 300.7 MB for 2^18 agents): state planes in once, out once (the trace planes are write-only when traces are off)
+DRAM_BYTES_PER_AGENT_LAUNCH_FP64 = 1147
 
 
 def parse():
@@ -396,7 +399,9 @@ def run_ours(args) -> dict:
             # FLOP fraction understates how busy the binding pipe is; instruction count from ncu (profiles/README.md)
             roof["fp64_instr_per_agent_step"] = FP64_INSTR_PER_AGENT_STEP
             roof["pipe_frac_of_measured_dfma_rate"] = FP64_INSTR_PER_AGENT_STEP * n * K / (ms * 1e-3) / (peak.value / 2.0)
-            roof["ncu_fp64_pipe_active_pct"] = 69.3
+            roof["ncu_fp64_pipe_active_pct"] = 69.5
+            roof["traffic"] = DRAM_BYTES_PER_AGENT_LAUNCH_FP64 * n
+            roof["traffic_note"] = "HBM bytes per launch from ncu (scaled per agent); the kernel is FP64-pipe bound, not HBM bound"
         variants = {}
         if not args.no_variants and world == 1:
             for pol in ("mixed", "fp32", "fp64"):
