@@ -400,6 +400,9 @@ def run_ours(args) -> dict:
             roof["fp64_instr_per_agent_step"] = FP64_INSTR_PER_AGENT_STEP
             roof["pipe_frac_of_measured_dfma_rate"] = FP64_INSTR_PER_AGENT_STEP * n * K / (ms * 1e-3) / (peak.value / 2.0)
             roof["ncu_fp64_pipe_active_pct"] = 69.5
+            # 897 algorithmic FLOP are issued as 850 FP64 instructions (numpy's separately rounded mul / add cannot be
+            # fused), so even a 100 % busy pipe reaches only 897 / (2 * 850) of the DFMA FLOP peak
+            roof["flop_frac_ceiling_under_parity_contract"] = FLOP_PER_AGENT_STEP / (2.0 * FP64_INSTR_PER_AGENT_STEP)
             roof["traffic"] = DRAM_BYTES_PER_AGENT_LAUNCH_FP64 * n
             roof["traffic_note"] = "HBM bytes per launch from ncu (scaled per agent); the kernel is FP64-pipe bound, not HBM bound"
         variants = {}
