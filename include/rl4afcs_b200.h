@@ -214,13 +214,14 @@ enum rl4_nl_env_field {        /* env plane, double */
     RL4_NLE_EPS = 50,          /* [3] */
     RL4_NLE_EPS_NORM = 53,
     RL4_NLE_RSE = 54,          /* [2] cumulative RSE                                            objects.py:1503-1504 */
-    RL4_NLE_NZ_PEAK = 56,      /* max V q / g0                                                  functions.py:774 */
+    RL4_NLE_NZ_PEAK = 56,      /* max |V q / g0|                                                functions.py:774,1050,1055 */
     RL4_NLE_ETA_A = 57,        /* self.eta_a / eta_c / lambdaa / gamma_lambda                   objects.py:1252-1281 */
     RL4_NLE_ETA_C = 58,
     RL4_NLE_LAMBDAA = 59,
     RL4_NLE_GL = 60,
     RL4_NLE_EA = 61,           /* [50] actor trace E (1,50)                                     objects.py:385-392 */
-    RL4_NLE_COUNT = 111
+    RL4_NLE_RSE_FLIGHT = 111,  /* [2] RSE summed over steps >= RL4_NHPI_FLIGHT_STEP only            functions.py:916-917,1038-1039 */
+    RL4_NLE_COUNT = 113
 };
 enum rl4_nl_net_field {        /* net plane, TN */
     RL4_NLN_S = 0,             /* [4] MDP state s                                               objects.py:1474 */
@@ -252,7 +253,9 @@ enum rl4_nl_hp {
 };
 enum rl4_nl_hpi {
     RL4_NHPI_MULTISTEP = 0, RL4_NHPI_WARMUP_STEPS, RL4_NHPI_COOLDOWN_STEPS, RL4_NHPI_FAULT_STEP,
-    RL4_NHPI_FAULT_DAMP, RL4_NHPI_FAULT_SAT, RL4_NHPI_ELIG_A, RL4_NHPI_COUNT
+    RL4_NHPI_FAULT_DAMP, RL4_NHPI_FAULT_SAT, RL4_NHPI_ELIG_A,
+    RL4_NHPI_FLIGHT_STEP,      /* first step of the 'flight' phase of the RSE split (5500)      functions.py:916-917 */
+    RL4_NHPI_COUNT
 };
 enum rl4_nl_fault_damp { RL4_NL_DAMP_NONE = 0, RL4_NL_DAMP_ELEVATOR, RL4_NL_DAMP_AILERON, RL4_NL_DAMP_RUDDER,
                          RL4_NL_DAMP_ALL, RL4_NL_SHIFT_CG, RL4_NL_SLOW_ALL };
@@ -274,8 +277,48 @@ typedef struct rl4_nl_params {
     const int32_t* hpi_agent[RL4_NHPI_COUNT];
 } rl4_nl_params;
 
+/* log.level 1: compact row */
 enum rl4_nl_log_field { RL4_NLL_XFULL = 0 /* [12] */, RL4_NLL_A = 12, RL4_NLL_E_THETA = 13, RL4_NLL_REWARD = 14,
                         RL4_NLL_SURF = 15 /* [3] action_commanded */, RL4_NLL_COUNT = 18 };
+/* log.level 2: every quantity IDHPnonlin._log keeps (objects.py:1083-1176), values as of the END of step k
+ * (after the weight / RLS / learning-rate updates, like the reference's call site objects.py:1541).  'a_elig' and
+ * 'c_elig' of the reference are allocated but never written (all zero) and are not carried; 't' is dt (k + 1). */
+enum rl4_nl_fulllog_field {
+    RL4_NLF_ETA_A = 0,           /* log['eta_a']                                                  */
+    RL4_NLF_XFULL = 1,           /* [12] log['x_full']                                            */
+    RL4_NLF_RSE = 13,            /* [2] per-step RSE (env.py:251)                                 */
+    RL4_NLF_X = 15,              /* [3] x_lon = x_full[4, 7, 1]                                   */
+    RL4_NLF_A_CMD = 18,          /* action_commanded[0]: elevator position after saturation [rad] */
+    RL4_NLF_A_EFF = 19,          /* action_effective[0]: model_input[0] = trim + effective        */
+    RL4_NLF_S = 20,              /* info['s'][0] = alpha (the reference broadcasts it over the 4 columns of log['s']) */
+    RL4_NLF_YREF = 21,           /* info['yref'][1] = theta_ref (broadcast the same way)          */
+    RL4_NLF_E = 22,              /* info['e'][1] = theta error                                    */
+    RL4_NLF_A_W1 = 23,           /* [40] actor W1 (4,10) row-major                                */
+    RL4_NLF_A_W2 = 63,           /* [10]                                                          */
+    RL4_NLF_C_W1 = 73,           /* [40]                                                          */
+    RL4_NLF_C_W2 = 113,          /* [30] (10,3) row-major                                         */
+    RL4_NLF_A_GRAD = 143,        /* [50] actor_loss_grad: W1 (4,10) then W2 (10,1); zero at k = 0 */
+    RL4_NLF_C_GRAD = 193,        /* [70] critic_loss_grad: W1 (4,10) then W2 (10,3); zero at k = 0 */
+    RL4_NLF_RLS_PARAMS = 263,    /* [12] (4,3) row-major                                          */
+    RL4_NLF_RLS_COV = 275,       /* [16]                                                          */
+    RL4_NLF_RLS_EPS = 291,       /* [3]                                                           */
+    RL4_NLF_RLS_EPS_NORM = 294,
+    RL4_NLF_A = 295,             /* a_next (not in the reference's log; convenience)              */
+    RL4_NLF_REWARD = 296,        /* reward_lon                                                    */
+    RL4_NLF_COUNT = 297
+};
+
+/* log.level 3: the per-step quantities MC_test_hparam keeps per repetition (functions.py:1040-1052), light enough
+ * to log EVERY agent of a sweep (88 B per agent-step); n_z follows as V q / g0. */
+enum rl4_nl_mclog_field {
+    RL4_NLM_E = 0,               /* theta error [rad]                 */
+    RL4_NLM_THETA = 1, RL4_NLM_ALPHA = 2, RL4_NLM_Q = 3, RL4_NLM_V = 4, RL4_NLM_H = 5,   /* x_full[7, 4, 1, 3, 9] */
+    RL4_NLM_A_CMD = 6, RL4_NLM_A_EFF = 7,                                                 /* as in level 2         */
+    RL4_NLM_WA_NORM = 8,         /* ||actor W1||_2 (functions.py:1028) */
+    RL4_NLM_WC_NORM = 9,         /* ||critic W1||_2 (functions.py:1030) */
+    RL4_NLM_RLS_EPS = 10,        /* rls eps_norm                       */
+    RL4_NLM_COUNT = 11
+};
 
 /* Fills *p with the configuration of idhp_nonlin.py:36-54,107-146 and the default surrogate plant (host only). */
 int rl4_nl_default_params(rl4_nl_params* p);
@@ -289,7 +332,8 @@ int rl4_nl_init(int policy, const rl4_nl_params* p, const double* w1a, const dou
  * [k0, k0+n_steps).  theta_ref: device table (phi / psi references are zero, idhp_nonlin.py:116-117);
  * noise: device float [n_steps][noise_stride], the N(0,1) draw of tf.random.normal (objects.py:1375) per agent and
  * step -- an explicit input like the weights (TensorFlow's stream is not reproducible);
- * log: NULL or RL4_NLL_COUNT fields for the first n_agents_logged agents, layout as rl4_sp_log. */
+ * log: buf NULL, or level 1 (RL4_NLL_COUNT fields) / 2 (RL4_NLF_COUNT) / 3 (RL4_NLM_COUNT) for the first n_agents_logged
+ * agents, layout as rl4_sp_log; the row of the step whose state turned NaN and every later row are NaN (objects.py:1168-1175). */
 int rl4_nl_run(int policy, const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride,
                int32_t k0, int32_t n_steps, rl4_nl_state st, int64_t n_agents, rl4_sp_log log, void* stream);
 /* Critic_big.call (objects.py:294-339): s [4][stride], w1 [40][stride] ((4,10) row-major), w2 [30][stride] ((10,3)

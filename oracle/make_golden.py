@@ -91,8 +91,44 @@ def loop_fixture(name, *, x0, seed, fault=None, elig=(None, None), ms=2, steps=1
     return out
 
 
+def utils_fixture():
+    """Outputs of the verbatim utils.py functions (samplers with true_random=False, PSD, convergence time, VD_A, KL)."""
+    U = ref_loader.load_reference_utils()
+    rng = np.random.default_rng(21)
+    out = {}
+    c = U.pick_continuous_hparams(7, lambda_hs=[0.3, 0.4], lr_a_hs=[2.5, 4.7], lr_c_hs=[0.45, 0.55], kappas=[1000, 1400],
+                                  cooldown_times=[1.0, 3.0], true_random=False)
+    for k, v in c.items():
+        if v is not None and k != "elig_a":
+            out[f"cont_{k}"] = np.asarray(v, dtype=np.float64)
+    d = U.pick_discrete_hparams(9, lambda_hs=[0.2, 0.3, 0.4], lr_a_hs=[1.0, 2.0, 3.0, 4.0], sigmas=[0.05, 0.1],
+                                elig_a=["accumulating", "replacing"], lr_decays=[0.99, 0.998], true_random=False)
+    for k, v in d.items():
+        if v is not None:
+            out[f"disc_{k}"] = np.asarray(v) if k != "elig_a" else np.asarray([str(e) for e in v])
+    sig = rng.standard_normal((5, 3000)) * 0.05
+    out["psd_in"] = sig
+    out["psd_out"], out["psd_omega"] = U.get_PSD(60, 0.02, sig)
+    one = rng.standard_normal(3500)
+    out["psd1_in"] = one
+    out["psd1_out"], out["psd1_omega"] = U.get_PSD(35, 0.01, one)
+    c_hist = -0.5 * 1200 * (np.deg2rad(3.0) * np.exp(-np.arange(3000) / 300.0) * np.cos(np.arange(3000) / 40.0)) ** 2
+    out["conv_c"] = c_hist
+    out["conv_t"] = np.asarray(U.get_convergence_time(c_hist, 1200, 0.02))
+    X = list(rng.standard_normal(40) + 0.4); Y = list(rng.standard_normal(40)); Z = list(np.round(rng.standard_normal(25), 1))
+    out["vda_X"], out["vda_Y"], out["vda_Z"] = np.asarray(X), np.asarray(Y), np.asarray(Z)
+    out["vda_XY"] = np.asarray(U.VD_A(X, Y)[0]); out["vda_YX"] = np.asarray(U.VD_A(Y, X)[0])
+    out["vda_ZZ"] = np.asarray(U.VD_A(Z, list(np.asarray(Z)[::-1] + 0.1))[0])
+    u = rng.random(30); v = rng.random(30); u[3] = 0.0; v[7] = -1.0
+    out["kl_u"], out["kl_v"], out["kl"] = u, v, np.asarray(U.kl_divergence(u, v))
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "utils_functions.npz"), **utils_fixture())
+    if "--only-utils" in sys.argv:
+        return
     for i, f in enumerate([None, "invert_elevator", "damp_elevator", "shift_cg"]):
         np.savez_compressed(os.path.join(OUT, f"sp_env_{f or 'none'}.npz"), **env_fixture(f, 100 + i))
     np.savez_compressed(os.path.join(OUT, "sp_rls_g1.npz"), **rls_fixture(1, 7))

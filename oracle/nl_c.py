@@ -24,7 +24,7 @@ CFG_DTYPE = np.dtype([
     ("noise_std", "f8", (4,)), ("omega0", "f8"), ("omega_slow", "f8"), ("rate_limit", "f8"),
     ("limit_deg", "f8", (3,)), ("damp_factor", "f8"), ("cg_shift", "f8"), ("sat_limit", "f8", (3,)),
     ("multistep", "i4"), ("warmup_steps", "i4"), ("cooldown_steps", "i4"), ("fault_step", "i4"),
-    ("elig_a", "i4"), ("fault_damp", "i4"), ("fault_sat", "i4"), ("integrator", "i4"),
+    ("elig_a", "i4"), ("fault_damp", "i4"), ("fault_sat", "i4"), ("integrator", "i4"), ("flight_step", "i4"), ("pad", "i4"),
 ], align=True)
 
 STATE_DTYPE = np.dtype([
@@ -34,7 +34,7 @@ STATE_DTYPE = np.dtype([
     ("W1t", "f8", (40,)), ("W2t", "f8", (30,)), ("Ea", "f8", (50,)),
     ("theta", "f8", (12,)), ("cov", "f8", (16,)), ("cgrad_prev", "f8", (3,)), ("M_prev", "f8", (9,)),
     ("eta_a", "f8"), ("eta_c", "f8"), ("lambdaa", "f8"), ("lr_a", "f8"), ("lr_c", "f8"), ("gl", "f8"),
-    ("eps", "f8", (3,)), ("eps_norm", "f8"), ("rse", "f8", (2,)), ("nz_peak", "f8"),
+    ("eps", "f8", (3,)), ("eps_norm", "f8"), ("rse", "f8", (2,)), ("nz_peak", "f8"), ("rse_flight", "f8", (2,)),
     ("cooldown", "i4"), ("diverged_step", "i4"), ("stepp", "i4"), ("pad", "i4"),
 ], align=True)
 
@@ -42,6 +42,9 @@ LOG_DTYPE = np.dtype([
     ("x_full", "f8", (12,)), ("s_next", "f8", (4,)), ("a_next", "f8"), ("reward", "f8"), ("e_theta", "f8"),
     ("lam", "f8", (3,)), ("lam_t", "f8", (3,)), ("td", "f8", (3,)), ("dads", "f8", (4,)), ("M", "f8", (9,)),
     ("loss_grad", "f8"), ("a_random", "f8"), ("surf", "f8", (3,)), ("model_input", "f8", (11,)),
+    ("eta_a", "f8"), ("rse_step", "f8", (2,)), ("yref_theta", "f8"), ("W1a", "f8", (40,)), ("W2a", "f8", (10,)),
+    ("W1c", "f8", (40,)), ("W2c", "f8", (30,)), ("a_grad", "f8", (50,)), ("c_grad", "f8", (70,)), ("theta", "f8", (12,)),
+    ("cov", "f8", (16,)), ("eps", "f8", (3,)), ("eps_norm", "f8"), ("wa_norm", "f8"), ("wc_norm", "f8"),
 ], align=True)
 
 FAULT_DAMP = {None: 0, "none": 0, "damp_elevator": 1, "damp_aileron": 2, "damp_rudder": 3, "damp_all": 4,

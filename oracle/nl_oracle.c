@@ -52,6 +52,7 @@ int orc_nl_default_cfg(orc_nl_cfg* c)
     c->sat_limit[0] = 5.0 * (M_PI / 180.0); c->sat_limit[1] = 18.0 * (M_PI / 180.0); c->sat_limit[2] = 10.0 * (M_PI / 180.0);
     c->multistep = 0; c->warmup_steps = 400; c->cooldown_steps = 200; c->fault_step = -1;
     c->elig_a = 1; c->fault_damp = 0; c->fault_sat = 0; c->integrator = RL4_CIT_INTEGRATOR_ODE5;
+    c->flight_step = 5500;
     return 0;
 }
 

@@ -44,6 +44,7 @@ typedef struct {
     int32_t multistep, warmup_steps, cooldown_steps, fault_step;
     int32_t elig_a;             /* 0 none, 1 accumulating, 2 replacing */
     int32_t fault_damp, fault_sat, integrator;
+    int32_t flight_step, pad;   /* 5500: RSE split of functions.py:916-917,1038-1039 */
 } orc_nl_cfg;
 
 typedef struct {
@@ -62,7 +63,8 @@ typedef struct {
     double gl;                      /* gamma_lambda of actor / critic */
     double eps[3], eps_norm;
     double rse[2];                  /* cumulative RSE, objects.py:1503-1504 */
-    double nz_peak;                 /* max V*q/9.80665, functions.py:774,1050 */
+    double nz_peak;                 /* max |V*q/9.80665|, functions.py:774,1050,1055 */
+    double rse_flight[2];           /* RSE over steps >= flight_step */
     int32_t cooldown, diverged_step, stepp, pad;
 } orc_nl_state;
 
@@ -70,6 +72,9 @@ typedef struct {
 typedef struct {
     double x_full[12], s_next[4], a_next, reward, e_theta, lam[3], lam_t[3], td[3], dads[4], M[9], loss_grad, a_random;
     double surf[3], model_input[11];
+    /* the quantities IDHPnonlin._log keeps (objects.py:1119-1165), as of the end of the step */
+    double eta_a, rse_step[2], yref_theta, W1a[40], W2a[10], W1c[40], W2c[30], a_grad[50], c_grad[70], theta[12], cov[16],
+           eps[3], eps_norm, wa_norm, wc_norm;
 } orc_nl_logrow;
 
 int orc_nl_default_cfg(orc_nl_cfg* c);

@@ -10,6 +10,9 @@ of which are installed.  Two pieces are pure numpy and run unmodified:
 * ``RLS`` (``objects.py:439-549``) -- the ``ClassDef`` node is extracted with ``ast``
   and exec'd with ``{'np': numpy}``.
 
+* ``utils.py`` (samplers, ``get_PSD``, ``get_convergence_time``, ``VD_A``, ``kl_divergence``) -- imported from the
+  file where it lies with the matplotlib stub (scipy is installed).
+
 Nothing is copied into this repo; the source is read from /root/reference at call
 time.  Used by ``oracle/make_golden.py`` and ``tests/test_oracle_vs_reference.py``
 (skipped when /root/reference is absent).  Never imported by the product package.
@@ -80,3 +83,18 @@ def load_reference_rls():
             exec(code, ns)
             return ns["RLS"]
     raise RuntimeError("class RLS not found in reference objects.py")
+
+
+def load_reference_utils():
+    """Return the verbatim ``utils`` module (utils.py: get_PSD :188, samplers :238,:293, get_convergence_time :350,
+    VD_A :391, kl_divergence :436)."""
+    if not reference_available():
+        raise FileNotFoundError(f"reference tree not found at {REFERENCE_ROOT}")
+    _install_stubs()
+    import importlib.util
+
+    path = os.path.join(REFERENCE_ROOT, "utils.py")
+    spec = importlib.util.spec_from_file_location("_rl4afcs_ref_utils", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

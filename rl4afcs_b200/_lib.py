@@ -53,17 +53,25 @@ class SpParams(ctypes.Structure):
 
 # ---- nonlinear path ----
 NLE = dict(XFULL=0, XACT=12, XLON=15, XPREVLON=18, THETA=21, COV=33, CGRAD_PREV=49, EPS=50, EPS_NORM=53, RSE=54,
-           NZ_PEAK=56, ETA_A=57, ETA_C=58, LAMBDAA=59, GL=60, EA=61, COUNT=111)
+           NZ_PEAK=56, ETA_A=57, ETA_C=58, LAMBDAA=59, GL=60, EA=61, RSE_FLIGHT=111, COUNT=113)
 NLN = dict(S=0, SPREV=4, A=8, APREV=9, W1A=10, W2A=50, W1C=60, W2C=100, W1T=130, W2T=170, MPREV=200, LR_A=209,
            LR_C=210, COUNT=211)
 NLI = dict(COOLDOWN=0, DIVERGED_STEP=1, STEPP=2, COUNT=3)
 NHP = dict(ETA_A_H=0, ETA_A_L=1, ETA_C_H=2, ETA_C_L=3, LAMBDA_H=4, LAMBDA_L=5, GAMMA=6, GAMMA_SQ=7, TAU=8, LR_DECAY=9,
            RLS_GAMMA=10, RLS_COV0=11, Q_SYM=12, LAMBDA_T=13, LAMBDA_S=14, DAMP_FACTOR=15, CG_SHIFT=16, COUNT=17)
-NHPI = dict(MULTISTEP=0, WARMUP_STEPS=1, COOLDOWN_STEPS=2, FAULT_STEP=3, FAULT_DAMP=4, FAULT_SAT=5, ELIG_A=6, COUNT=7)
+NHPI = dict(MULTISTEP=0, WARMUP_STEPS=1, COOLDOWN_STEPS=2, FAULT_STEP=3, FAULT_DAMP=4, FAULT_SAT=5, ELIG_A=6, FLIGHT_STEP=7,
+            COUNT=8)
 NL_DAMP = {None: 0, "none": 0, "damp_elevator": 1, "damp_aileron": 2, "damp_rudder": 3, "damp_all": 4, "shift_cg": 5,
            "slow_all": 6}
 NL_SAT = {None: 0, "none": 0, "saturate_elevator": 1, "saturate_aileron": 2, "saturate_rudder": 3}
 NLL = dict(XFULL=0, A=12, E_THETA=13, REWARD=14, SURF=15, COUNT=18)
+# enum rl4_nl_fulllog_field (name -> (offset, width))
+NLF_FIELDS = dict(ETA_A=(0, 1), XFULL=(1, 12), RSE=(13, 2), X=(15, 3), A_CMD=(18, 1), A_EFF=(19, 1), S=(20, 1), YREF=(21, 1),
+                  E=(22, 1), A_W1=(23, 40), A_W2=(63, 10), C_W1=(73, 40), C_W2=(113, 30), A_GRAD=(143, 50), C_GRAD=(193, 70),
+                  RLS_PARAMS=(263, 12), RLS_COV=(275, 16), RLS_EPS=(291, 3), RLS_EPS_NORM=(294, 1), A=(295, 1), REWARD=(296, 1))
+NLF = {k: v[0] for k, v in NLF_FIELDS.items()}
+NLF["COUNT"] = 297
+NLM = dict(E=0, THETA=1, ALPHA=2, Q=3, V=4, H=5, A_CMD=6, A_EFF=7, WA_NORM=8, WC_NORM=9, RLS_EPS=10, COUNT=11)
 INTEGRATOR = {"rk4": 0, "ode5": 1}
 CIT_FIELDS = ["m", "S", "c", "b", "Ixx", "Iyy", "Izz", "Ixz", "g", "CL0", "CLa", "CLq", "CLde", "CLflap", "al_stall",
               "CD0", "CDk", "CDgear", "CDflap", "CDstall", "Cm0", "Cma", "Cmq", "Cmde", "Cmflap", "Cmstall",

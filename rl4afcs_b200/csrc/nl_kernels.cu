@@ -120,7 +120,7 @@ __device__ __forceinline__ TN nl_actor(const TN (&s)[4], const WA W1, const WA W
 template <bool PER_AGENT, int INTEG>
 __device__ __forceinline__ void nl_env_step(const rl4_nl_params& p, const NlHp<PER_AGENT>& hv, int stepp, double theta_ref_k,
                                             const double (&act)[3], double (&x)[12], double (&x_act)[3], double (&surf)[3],
-                                            double& e_phi, double& e_th, double& e_psi, double& reward, double& rg2)
+                                            double& e_phi, double& e_th, double& e_psi, double& reward, double& rg2, double& u0)
 {
     const int fault_step = hv.hpi(RL4_NHPI_FAULT_STEP);
     const bool faulted = (fault_step >= 0 && stepp >= fault_step);                 // env.py:132,151
@@ -158,6 +158,7 @@ __device__ __forceinline__ void nl_env_step(const rl4_nl_params& p, const NlHp<P
     double u[11];
 #pragma unroll
     for (int i = 0; i < 11; ++i) u[i] = p.trim_input[i] + eff[i];                  // env.py:207-208
+    u0 = u[0];
     if (INTEG == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(&p.plant, x, u, p.dt);   // compile-time: one integrator's code per kernel
     else rl4_cit_step_ode5(&p.plant, x, u, p.dt);                                  // env.py:210
     const double Q = hv.hp(RL4_NHP_Q_SYM);
@@ -204,6 +205,8 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
     for (int j = 0; j < 16; ++j) cv[j] = EF(RL4_NLE_COV + j);
     for (int j = 0; j < 50; ++j) Ea[j] = EF(RL4_NLE_EA + j);
     double cgp2 = EF(RL4_NLE_CGRAD_PREV), eps_norm = EF(RL4_NLE_EPS_NORM), rse0 = EF(RL4_NLE_RSE), rse1 = EF(RL4_NLE_RSE + 1);
+    double rse_f0 = EF(RL4_NLE_RSE_FLIGHT), rse_f1 = EF(RL4_NLE_RSE_FLIGHT + 1);
+    const int flight_step = hv.hpi(RL4_NHPI_FLIGHT_STEP);
     double nz_peak = EF(RL4_NLE_NZ_PEAK), eta_a = EF(RL4_NLE_ETA_A), eta_c = EF(RL4_NLE_ETA_C), lambdaa = EF(RL4_NLE_LAMBDAA), gl = EF(RL4_NLE_GL);
     for (int j = 0; j < 4; ++j) { s[j] = NF(RL4_NLN_S + j); s_prev[j] = NF(RL4_NLN_SPREV + j); }
     TN a = NF(RL4_NLN_A), a_prev = NF(RL4_NLN_APREV), lr_a = NF(RL4_NLN_LR_A), lr_c = NF(RL4_NLN_LR_C);
@@ -221,16 +224,22 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
         const TN a_k = a;
         // ---- env.step(self._get_action(a))  (objects.py:1497, 1448-1455)
         const double act[3] = {(double)a_k, 0.0, 0.0};
-        double surf[3], e_phi, e_th, e_psi, reward, rg2;
-        nl_env_step<PER_AGENT, INTEG>(p, hv, stepp, __ldg(theta_ref + k), act, x, x_act, surf, e_phi, e_th, e_psi, reward, rg2);
+        double surf[3], e_phi, e_th, e_psi, reward, rg2, u0;
+        const double yref_k = __ldg(theta_ref + k);
+        nl_env_step<PER_AGENT, INTEG>(p, hv, stepp, yref_k, act, x, x_act, surf, e_phi, e_th, e_psi, reward, rg2, u0);
         stepp += 1;
         const double x_next_lon[3] = {x[4], x[7], x[1]};                           // env.py:231
         bool nans = false;
 #pragma unroll
         for (int j = 0; j < 12; ++j) nans |= (x[j] != x[j]);
-        rse0 += nsqrt(e_th * e_th);                                                // env.py:251; objects.py:1503-1504
-        rse1 += nsqrt(e_phi * e_phi + e_psi * e_psi);
-        { const double nz = x[3] * x[1] / 9.80665; if (nz > nz_peak) nz_peak = nz; }
+        const double rse_k0 = nsqrt(e_th * e_th), rse_k1 = nsqrt(e_phi * e_phi + e_psi * e_psi);   // env.py:251
+        rse0 += rse_k0;                                                            // objects.py:1503-1504
+        rse1 += rse_k1;
+        if (k >= flight_step) { rse_f0 += rse_k0; rse_f1 += rse_k1; }              // functions.py:917,1039
+        // full-log row of this step (level 2): the two loss gradients are written where they are formed
+        double* const fb = (LOG && logged && lg.level == 2 && (k - k0) % lg.every == 0)
+                               ? lg.buf + ((int64_t)((k - k0) / lg.every) * RL4_NLF_COUNT) * lg.n_agents_logged + i : nullptr;
+        { const double nz = fabs(x[3] * x[1] / 9.80665); if (nz > nz_peak) nz_peak = nz; }   // functions.py:774,1055
         TN s_next[4] = {(TN)x[4], (TN)x[7], (TN)x[1], (TN)e_th};                   // env.py:236-238; objects.py:1499
 
         // ---- _step_networks (objects.py:1292-1348)
@@ -336,6 +345,15 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
                 for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
                     for (int j = 0; j < 10; ++j) W1c[ii * 10 + j] = W1c[ii * 10 + j] - lr_c * (s_prev[ii] * dpre[j]);
+                if (LOG) {
+                    if (fb) {                                                      // critic_loss_grad (objects.py:1365,1151-1152)
+                        const int64_t L = lg.n_agents_logged;
+                        for (int ii = 0; ii < 4; ++ii)
+                            for (int j = 0; j < 10; ++j) fb[(int64_t)(RL4_NLF_C_GRAD + ii * 10 + j) * L] = (double)(s_prev[ii] * dpre[j]);
+                        for (int j = 0; j < 10; ++j)
+                            for (int q = 0; q < 3; ++q) fb[(int64_t)(RL4_NLF_C_GRAD + 40 + j * 3 + q) * L] = (double)(hc[j] * td[q]);
+                    }
+                }
             }
             {   // target soft update (objects.py:1371)
                 const double tau_d = hv.hp(RL4_NHP_TAU);
@@ -359,6 +377,14 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
                 for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
                     for (int j = 0; j < 10; ++j) W1a[ii * 10 + j] = W1a[ii * 10 + j] - lr_a * (loss * (TN)Ea[10 + j * 4 + ii]);
+                if (LOG) {
+                    if (fb) {                                                      // actor_loss_grad (objects.py:1387,1154-1155)
+                        const int64_t L = lg.n_agents_logged;
+                        for (int ii = 0; ii < 4; ++ii)
+                            for (int j = 0; j < 10; ++j) fb[(int64_t)(RL4_NLF_A_GRAD + ii * 10 + j) * L] = (double)(loss * (TN)Ea[10 + j * 4 + ii]);
+                        for (int j = 0; j < 10; ++j) fb[(int64_t)(RL4_NLF_A_GRAD + 40 + j) * L] = (double)(loss * (TN)Ea[j]);
+                    }
+                }
             }
             {   // RLS, n = 3, m = 1 (objects.py:1521-1524, 492-543)
                 double Xr[4], Y[3];
@@ -433,20 +459,50 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
         if (nans) diverged_step = k;
         if (LOG) {
             if (logged && (k - k0) % lg.every == 0) {
-                double* b = lg.buf + ((int64_t)((k - k0) / lg.every) * RL4_NLL_COUNT) * lg.n_agents_logged + i;
                 const int64_t L = lg.n_agents_logged;
-                for (int j = 0; j < 12; ++j) b[(int64_t)(RL4_NLL_XFULL + j) * L] = x[j];
-                b[(int64_t)RL4_NLL_A * L] = (double)a_next; b[(int64_t)RL4_NLL_E_THETA * L] = e_th; b[(int64_t)RL4_NLL_REWARD * L] = reward;
-                for (int j = 0; j < 3; ++j) b[(int64_t)(RL4_NLL_SURF + j) * L] = surf[j];
+                const int nf = lg.level >= 3 ? RL4_NLM_COUNT : (lg.level == 2 ? RL4_NLF_COUNT : RL4_NLL_COUNT);
+                double* b = lg.buf + ((int64_t)((k - k0) / lg.every) * nf) * L + i;
+                if (nans) {                                                        // objects.py:1168-1175: this row and all later ones
+                    for (int f = 0; f < nf; ++f) b[(int64_t)f * L] = __longlong_as_double(0x7ff8000000000000LL);
+                } else if (lg.level >= 3) {                                        // functions.py:1040-1052
+                    b[(int64_t)RL4_NLM_E * L] = e_th; b[(int64_t)RL4_NLM_THETA * L] = x[7]; b[(int64_t)RL4_NLM_ALPHA * L] = x[4];
+                    b[(int64_t)RL4_NLM_Q * L] = x[1]; b[(int64_t)RL4_NLM_V * L] = x[3]; b[(int64_t)RL4_NLM_H * L] = x[9];
+                    b[(int64_t)RL4_NLM_A_CMD * L] = surf[0]; b[(int64_t)RL4_NLM_A_EFF * L] = u0;
+                    double na = 0.0, nc = 0.0;
+                    for (int j = 0; j < 40; ++j) { na = __fma_rn((double)W1a[j], (double)W1a[j], na); nc = __fma_rn((double)W1c[j], (double)W1c[j], nc); }
+                    b[(int64_t)RL4_NLM_WA_NORM * L] = nsqrt(na); b[(int64_t)RL4_NLM_WC_NORM * L] = nsqrt(nc);
+                    b[(int64_t)RL4_NLM_RLS_EPS * L] = eps_norm;
+                } else if (lg.level == 2) {
+                    b[(int64_t)RL4_NLF_ETA_A * L] = eta_a;
+                    for (int j = 0; j < 12; ++j) b[(int64_t)(RL4_NLF_XFULL + j) * L] = x[j];
+                    b[(int64_t)RL4_NLF_RSE * L] = rse_k0; b[(int64_t)(RL4_NLF_RSE + 1) * L] = rse_k1;
+                    for (int j = 0; j < 3; ++j) b[(int64_t)(RL4_NLF_X + j) * L] = x_next_lon[j];
+                    b[(int64_t)RL4_NLF_A_CMD * L] = surf[0]; b[(int64_t)RL4_NLF_A_EFF * L] = u0;
+                    b[(int64_t)RL4_NLF_S * L] = x[4]; b[(int64_t)RL4_NLF_YREF * L] = yref_k; b[(int64_t)RL4_NLF_E * L] = e_th;
+                    for (int j = 0; j < 40; ++j) { b[(int64_t)(RL4_NLF_A_W1 + j) * L] = (double)W1a[j]; b[(int64_t)(RL4_NLF_C_W1 + j) * L] = (double)W1c[j]; }
+                    for (int j = 0; j < 10; ++j) b[(int64_t)(RL4_NLF_A_W2 + j) * L] = (double)W2a[j];
+                    for (int j = 0; j < 30; ++j) b[(int64_t)(RL4_NLF_C_W2 + j) * L] = (double)W2c[j];
+                    if (k == 0) for (int j = 0; j < 120; ++j) b[(int64_t)(RL4_NLF_A_GRAD + j) * L] = 0.0;
+                    for (int j = 0; j < 12; ++j) b[(int64_t)(RL4_NLF_RLS_PARAMS + j) * L] = th[j];
+                    for (int j = 0; j < 16; ++j) b[(int64_t)(RL4_NLF_RLS_COV + j) * L] = cv[j];
+                    for (int j = 0; j < 3; ++j) b[(int64_t)(RL4_NLF_RLS_EPS + j) * L] = eps[j];
+                    b[(int64_t)RL4_NLF_RLS_EPS_NORM * L] = eps_norm;
+                    b[(int64_t)RL4_NLF_A * L] = (double)a_next; b[(int64_t)RL4_NLF_REWARD * L] = reward;
+                } else {
+                    for (int j = 0; j < 12; ++j) b[(int64_t)(RL4_NLL_XFULL + j) * L] = x[j];
+                    b[(int64_t)RL4_NLL_A * L] = (double)a_next; b[(int64_t)RL4_NLL_E_THETA * L] = e_th; b[(int64_t)RL4_NLL_REWARD * L] = reward;
+                    for (int j = 0; j < 3; ++j) b[(int64_t)(RL4_NLL_SURF + j) * L] = surf[j];
+                }
             }
         }
     }
     if (LOG) {
         if (logged) {
+            const int nf = lg.level >= 3 ? RL4_NLM_COUNT : (lg.level == 2 ? RL4_NLF_COUNT : RL4_NLL_COUNT);
             for (; k < k0 + n_steps; ++k) {
                 if ((k - k0) % lg.every) continue;
-                double* b = lg.buf + ((int64_t)((k - k0) / lg.every) * RL4_NLL_COUNT) * lg.n_agents_logged + i;
-                for (int f = 0; f < RL4_NLL_COUNT; ++f) b[(int64_t)f * lg.n_agents_logged] = __longlong_as_double(0x7ff8000000000000LL);
+                double* b = lg.buf + ((int64_t)((k - k0) / lg.every) * nf) * lg.n_agents_logged + i;
+                for (int f = 0; f < nf; ++f) b[(int64_t)f * lg.n_agents_logged] = __longlong_as_double(0x7ff8000000000000LL);
             }
         }
     }
@@ -457,6 +513,7 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
     for (int j = 0; j < 16; ++j) EF(RL4_NLE_COV + j) = cv[j];
     for (int j = 0; j < 50; ++j) EF(RL4_NLE_EA + j) = Ea[j];
     EF(RL4_NLE_CGRAD_PREV) = cgp2; EF(RL4_NLE_EPS_NORM) = eps_norm; EF(RL4_NLE_RSE) = rse0; EF(RL4_NLE_RSE + 1) = rse1;
+    EF(RL4_NLE_RSE_FLIGHT) = rse_f0; EF(RL4_NLE_RSE_FLIGHT + 1) = rse_f1;
     EF(RL4_NLE_NZ_PEAK) = nz_peak; EF(RL4_NLE_ETA_A) = eta_a; EF(RL4_NLE_ETA_C) = eta_c; EF(RL4_NLE_LAMBDAA) = lambdaa; EF(RL4_NLE_GL) = gl;
     for (int j = 0; j < 4; ++j) { NF(RL4_NLN_S + j) = s[j]; NF(RL4_NLN_SPREV + j) = s_prev[j]; }
     NF(RL4_NLN_A) = a; NF(RL4_NLN_APREV) = a_prev; NF(RL4_NLN_LR_A) = lr_a; NF(RL4_NLN_LR_C) = lr_c;
@@ -518,13 +575,13 @@ nl_env_step_kernel(const __grid_constant__ rl4_nl_params p, const double* __rest
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_agents) return;
     const NlHp<true> hv{p, i};
-    double x[12], xa[3], act[3], surf[3], e_phi, e_th, e_psi, reward, rg2;
+    double x[12], xa[3], act[3], surf[3], e_phi, e_th, e_psi, reward, rg2, u0;
     for (int j = 0; j < 12; ++j) x[j] = x_full[j * S + i];
     for (int j = 0; j < 3; ++j) { xa[j] = x_act_p[j * S + i]; act[j] = action[j * S + i]; }
     if (p.integrator == RL4_CIT_INTEGRATOR_RK4)
-        nl_env_step<true, RL4_CIT_INTEGRATOR_RK4>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2);
+        nl_env_step<true, RL4_CIT_INTEGRATOR_RK4>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2, u0);
     else
-        nl_env_step<true, RL4_CIT_INTEGRATOR_ODE5>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2);
+        nl_env_step<true, RL4_CIT_INTEGRATOR_ODE5>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2, u0);
     for (int j = 0; j < 12; ++j) x_full[j * S + i] = x[j];
     for (int j = 0; j < 3; ++j) x_act_p[j * S + i] = xa[j];
     out_mdp[i] = x[4]; out_mdp[S + i] = x[7]; out_mdp[2 * S + i] = x[1]; out_mdp[3 * S + i] = e_th;
@@ -631,6 +688,7 @@ int rl4_nl_default_params(rl4_nl_params* p)
     p->hpi[RL4_NHPI_MULTISTEP] = 0; p->hpi[RL4_NHPI_WARMUP_STEPS] = 400; p->hpi[RL4_NHPI_COOLDOWN_STEPS] = 200;
     p->hpi[RL4_NHPI_FAULT_STEP] = -1; p->hpi[RL4_NHPI_FAULT_DAMP] = 0; p->hpi[RL4_NHPI_FAULT_SAT] = 0;
     p->hpi[RL4_NHPI_ELIG_A] = RL4_ELIG_ACCUMULATING;
+    p->hpi[RL4_NHPI_FLIGHT_STEP] = 5500;
     p->integrator = RL4_CIT_INTEGRATOR_ODE5;
     return 0;
 }
@@ -654,7 +712,7 @@ int rl4_nl_run(int policy, const rl4_nl_params* p, const double* theta_ref, cons
 {
     RL4_REQUIRE(p && theta_ref && noise && st.env && st.net && st.ints, "NULL argument");
     RL4_REQUIRE(n >= 0 && st.stride >= n && noise_stride >= n && k0 >= 0 && n_steps >= 0, "bad size");
-    if (lg.level != RL4_LOG_NONE) RL4_REQUIRE(lg.buf && lg.every >= 1 && lg.n_agents_logged >= 0 && lg.n_agents_logged <= n, "bad log descriptor");
+    if (lg.level != RL4_LOG_NONE) RL4_REQUIRE(lg.level >= 1 && lg.level <= 3 && lg.buf && lg.every >= 1 && lg.n_agents_logged >= 0 && lg.n_agents_logged <= n, "bad log descriptor");
     if (n == 0 || n_steps == 0) return 0;
     bool per_agent = false;
     for (int j = 0; j < RL4_NHP_COUNT; ++j) per_agent |= (p->hp_agent[j] != nullptr);

@@ -5,6 +5,8 @@ wingos80/RL4AFCS (plotting and pickling are out of scope).
   MC_run_seed                       functions.py:39-60            (the per-run output dict, for a whole batch)
   MC_run                            functions.py:62-232           (configs x seeds flattened onto the agent axis; returns
                                                                    the metrics dict of functions.py:223-227 per config)
+  MC_test_hparam                    functions.py:931-1060         (nonlinear task: N configs x repetitions in one batch;
+                                                                   returns the per-config log dicts of :1008-1052)
 """
 from __future__ import annotations
 
@@ -13,32 +15,8 @@ import torch
 
 from . import _lib
 from .envs.linear.env import Ce500ShortPeriod
-from .objects import IDHPsp
-
-
-def get_PSD(t_end, dt, array):
-    """Power spectral density |FFT|^2 / t_end of each row, first N/2 bins, and the frequency axis (utils.py:188-236)."""
-    fs = 1 / dt
-    N = int(t_end * fs)
-    upp = int(N / 2)
-    omega = torch.arange(0, upp, 1, dtype=torch.float64) / (N * dt)
-    x = torch.as_tensor(array)
-    if x.ndim == 1:
-        x = x[None]
-    f = torch.fft.fft(x.to(torch.float64), dim=-1)
-    spectra = (f * torch.conj(f)).abs()[..., :upp] / t_end
-    return spectra.squeeze(0) if spectra.shape[0] == 1 else spectra, omega
-
-
-def get_convergence_time(c_hist, kappa, dt):
-    """Time of the last sample whose angle-of-attack error exceeds 0.5 deg (utils.py:350-369); batched over the
-    leading axis.  (The fused kernel computes the same quantity in-register: ``stats()['converged_time']``.)"""
-    c = torch.as_tensor(c_hist, dtype=torch.float64)
-    aoa_error = torch.rad2deg(torch.sqrt(-2 * (c / kappa)))
-    over = aoa_error > 0.5
-    idx = torch.arange(c.shape[-1], device=c.device)
-    last = torch.where(over, idx, torch.full_like(idx, -1)).max(dim=-1).values
-    return last.to(torch.float64) * dt
+from .objects import IDHPnonlin, IDHPsp
+from .utils import get_PSD, get_convergence_time  # noqa: F401  (utils.py:188-236, 350-369)
 
 
 def MC_run_seed(idhp: IDHPsp) -> dict:
@@ -115,3 +93,73 @@ def MC_run(n_configs, configs, env_config, seeds, *, device="cuda", dtype="mixed
                 e = e[~torch.isnan(e)]
                 metrics[c]["avg_PSD_err"] = float(np.around(float(e.mean()), 4)) if e.numel() else float("nan")
     return metrics, idhp
+
+
+_ALGOS = {(0, None): "idhp", (0, "replacing"): "idhprt", (0, "accumulating"): "idhpat",
+          (1, None): "midhp", (1, "replacing"): "midhprt", (1, "accumulating"): "midhpat"}       # functions.py:933,959-972
+
+
+def MC_test_hparam(configs, directory, env, N, repetitions, save=0, show=0, transparency=0.2, *, noise=None, flight_step=5500):
+    """Nonlinear-task Monte-Carlo of functions.py:931-1060: ``N`` hyper-parameter sets (``configs`` = dict of lists with
+    the reference's keys etaah, etaal, etach, etacl, lambda_hs, lambda_ls, seeds, ms, elig) x ``repetitions`` seeds, run
+    as ONE batch of N * repetitions agents (agent index = config * repetitions + seed).
+
+    ``env``: a batched ``Ce500NonLinear`` with ``batch == N * repetitions``.  As in the reference, repetition r of every
+    configuration starts from the same seed-r initial weights and sees the same seed-r noise stream.  ``directory``,
+    ``save``, ``show``, ``transparency`` are accepted for call compatibility (plotting / pickling are out of scope).
+    Returns a list of (algo, idhp_config, log) with log = the dict of functions.py:1008-1021 as torch tensors
+    (angles in degrees, as stored there) plus ``'max_nz'``.
+    """
+    B = N * repetitions
+    assert env.batch == B, f"env.batch must be N * repetitions = {B}"
+    rep = lambda key, conv=float: np.repeat(np.asarray([conv(configs[key][i]) for i in range(N)]), repetitions)   # noqa: E731
+    ms = rep("ms", int)
+    elig = [configs["elig"][i] for i in range(N) for _ in range(repetitions)]
+    n, m, mdp_s_dim = 3, 1, 4
+    idhp_config = {"gamma": 0.6, "multistep": ms, "lr_decay": 0.998, "lambda_h": rep("lambda_hs"), "lambda_l": rep("lambda_ls"),
+                   "kappa": [1, 2, 1], "cooldown_time": 2.0, "sigma": 0.1, "warmup_time": 4, "error_thresh": 1, "tau": 0.02,
+                   "in_dims": mdp_s_dim,
+                   "actor_config": {"layers": {10: "tanh", m: "tanh"}, "eta_h": rep("etaah"), "eta_l": rep("etaal"), "elig": elig},
+                   "critic_config": {"layers": {10: "tanh", n: "linear"}, "eta_h": rep("etach"), "eta_l": rep("etacl"), "elig": 1233},
+                   "rls_config": {"state_dim": n, "action_dim": m, "rls_gamma": 1, "rls_cov": 10 ** 6}}      # functions.py:973-997
+    dev = env.device
+    total_steps = int(env.t_end / env.dt)
+    # seed r -> the same initial weights and noise stream for every configuration (functions.py:1013-1023)
+    g = torch.Generator(device=dev); g.manual_seed(0)
+
+    def draw(w):
+        out = torch.randn((repetitions, w), generator=g, device=dev, dtype=torch.float32)
+        bad = out.abs() > 2.0
+        while bool(bad.any()):
+            out = torch.where(bad, torch.randn((repetitions, w), generator=g, device=dev, dtype=torch.float32), out)
+            bad = out.abs() > 2.0
+        return (out * 0.1).double().repeat(N, 1)
+    weights = {"W1a": draw(40), "W2a": draw(10), "W1c": draw(40), "W2c": draw(30)}
+    if noise is None:
+        noise = torch.randn((total_steps, repetitions), generator=g, device=dev, dtype=torch.float32).repeat(1, N)
+    env._engine.set_hpi("FLIGHT_STEP", int(flight_step))
+    idhp = IDHPnonlin(env, idhp_config, verbose=0, seed=0, weights=weights, log="mc", log_agents=B)
+    idhp.train(noise=noise)
+    st, lg, dt = idhp.stats(), idhp.log, env.dt
+    flight = lg["theta"][:, flight_step:]
+    t_flight = (total_steps - flight_step) * dt                                                 # 35 s (functions.py:1033)
+    theta_PSD, omega = get_PSD(t_flight, dt, torch.rad2deg(flight))
+    Sm = (torch.atleast_2d(theta_PSD) * omega.to(dev)).sum(dim=-1)                              # functions.py:1034
+    nrm = lambda v: v / v.max(dim=-1, keepdim=True).values                                      # noqa: E731
+    full = {"RSE": torch.stack([st["rse"][:, 0] - st["rse_flight"][:, 0], st["rse_flight"][:, 0]], dim=-1),   # :1036-1037
+            "e": torch.rad2deg(lg["e"]), "theta": torch.rad2deg(lg["theta"]), "alpha": torch.rad2deg(lg["alpha"]),
+            "q": torch.rad2deg(lg["q"]), "V": lg["v"], "h": lg["h"], "action_cmd": torch.rad2deg(lg["a_cmd"]),
+            "action_eff": torch.rad2deg(lg["a_eff"]), "n_z": lg["v"] * lg["q"] / 9.80665,
+            "wa_norm": nrm(lg["wa_norm"]), "wc_norm": nrm(lg["wc_norm"]), "Sm": Sm.unsqueeze(-1), "rls_eps": lg["rls_eps"],
+            "max_nz": st["nz_peak"]}
+    out = []
+    for i in range(N):
+        sl = slice(i * repetitions, (i + 1) * repetitions)
+        cfg_i = {**idhp_config, "multistep": int(ms[sl][0]), "lambda_h": float(idhp_config["lambda_h"][sl][0]),
+                 "lambda_l": float(idhp_config["lambda_l"][sl][0]),
+                 "actor_config": {**idhp_config["actor_config"], "eta_h": float(idhp_config["actor_config"]["eta_h"][sl][0]),
+                                  "eta_l": float(idhp_config["actor_config"]["eta_l"][sl][0]), "elig": configs["elig"][i]},
+                 "critic_config": {**idhp_config["critic_config"], "eta_h": float(idhp_config["critic_config"]["eta_h"][sl][0]),
+                                   "eta_l": float(idhp_config["critic_config"]["eta_l"][sl][0])}}
+        out.append((_ALGOS[(int(ms[sl][0]), configs["elig"][i])], cfg_i, {k: v[sl] for k, v in full.items()}))
+    return out

@@ -115,9 +115,9 @@ class NlEngine:
             _lib.check(rc, "rl4_nl_init")
         self.k = 0
 
-    def run(self, n_steps, noise, *, log_agents=0, log_every=1):
+    def run(self, n_steps, noise, *, log_agents=0, log_every=1, log_level=1):
         """noise: float32 (n_steps, n_agents) N(0,1) draws (objects.py:1375).  Returns the log
-        (rows, fields, log_agents) or None."""
+        (rows, fields, log_agents) or None; log_level 1 = compact (_lib.NLL), 2 = full (_lib.NLF), 3 = the MC_test_hparam row (_lib.NLM)."""
         assert self.theta_ref is not None and self.theta_ref.numel() >= self.k + n_steps
         noise = torch.as_tensor(noise, device=self.device).to(torch.float32).contiguous()
         assert noise.shape == (n_steps, self.n)
@@ -126,8 +126,9 @@ class NlEngine:
         if log_agents:
             log_agents = min(int(log_agents), self.n)
             rows = (n_steps + log_every - 1) // log_every
-            log_t = torch.zeros((rows, _lib.NLL["COUNT"], log_agents), dtype=torch.float64, device=self.device)
-            lg = _lib.SpLog(log_t.data_ptr(), 1, log_every, log_agents)
+            nf = {1: _lib.NLL, 2: _lib.NLF, 3: _lib.NLM}[int(log_level)]["COUNT"]
+            log_t = torch.empty((rows, nf, log_agents), dtype=torch.float64, device=self.device)
+            lg = _lib.SpLog(log_t.data_ptr(), int(log_level), log_every, log_agents)
         with torch.cuda.device(self.device):
             rc = self.lib.rl4_nl_run(self.policy_id, ctypes.byref(self.params), self.theta_ref.data_ptr(), noise.data_ptr(),
                                      self.n, self.k, n_steps, self.state_struct(), self.n, lg, self._stream())
@@ -136,5 +137,6 @@ class NlEngine:
         return log_t
 
     def stats(self):
-        return {"rse": self.env_field("RSE", 2).t().clone(), "nz_peak": self.env_field("NZ_PEAK")[0].clone(),
+        return {"rse": self.env_field("RSE", 2).t().clone(), "rse_flight": self.env_field("RSE_FLIGHT", 2).t().clone(),
+                "nz_peak": self.env_field("NZ_PEAK")[0].clone(),
                 "diverged": self.int_field("DIVERGED_STEP") >= 0}

@@ -469,10 +469,18 @@ class IDHPnonlin:
     launches of ``chunk`` steps; the N(0,1) draw of objects.py:1375 is generated per chunk with torch's Philox
     generator (or supplied: ``noise=`` (steps, B) float32), the initial weights are TruncatedNormal(sigma) from
     ``seed`` or ``weights=`` (W1a (B,40), W2a (B,10), W1c (B,40), W2c (B,30)).
+
+    ``log``: "full" = the reference's log dict (objects.py:1083-1176) for the first ``log_agents`` agents, every array
+    with a leading agent axis; "compact" = x_full / a / e / reward / a_cmd only; "mc" = the per-step quantities
+    MC_test_hparam keeps (functions.py:1040-1052), cheap enough for every agent; None = statistics only.
     """
 
-    def __init__(self, env, config, verbose=True, seed=1, *, weights=None, log_agents=None, chunk: int = 1000) -> None:
+    def __init__(self, env, config, verbose=True, seed=1, *, weights=None, log="full", log_agents=None,
+                 chunk: int = 1000) -> None:
         from . import nl_engine  # noqa: F401
+
+        assert log in ("full", "compact", "mc", None)
+        self._log_mode = log
 
         self.seed = seed
         self.env = env
@@ -519,7 +527,10 @@ class IDHPnonlin:
             weights = {"W1a": draw(40), "W2a": draw(10), "W1c": draw(40), "W2c": draw(30)}
         self._init_weights = weights
         self.log_agents = min(self.batch, 16) if log_agents is None else min(int(log_agents), self.batch)
+        if log is None:
+            self.log_agents = 0
         self.chunk = int(chunk)
+        self.hidden_dim_a_lon = self.hidden_dim_c_lon = 10
 
     def train(self, n_steps=None, noise=None):
         env, eng = self.env, self._eng
@@ -533,7 +544,7 @@ class IDHPnonlin:
             c = min(self.chunk, steps - k)
             nz = (torch.as_tensor(noise[k:k + c]) if noise is not None
                   else torch.randn((c, self.batch), generator=g, device=eng.device, dtype=torch.float32))
-            lg = eng.run(c, nz, log_agents=self.log_agents)
+            lg = eng.run(c, nz, log_agents=self.log_agents, log_level={"full": 2, "mc": 3}.get(self._log_mode, 1))
             if lg is not None:
                 logs.append(lg)
             k += c
@@ -542,15 +553,50 @@ class IDHPnonlin:
         self._steps = steps
         if logs:
             lg = torch.cat(logs, dim=0).permute(2, 0, 1)                     # (agents, rows, fields)
-            L = _lib.NLL
-            self.log = {"t": (torch.arange(steps, dtype=torch.float64) + 1) * env.dt,     # objects.py:1495 (N12)
-                        "x_full": lg[:, :, L["XFULL"]:L["XFULL"] + 12], "a_cmd": lg[:, :, L["SURF"]:L["SURF"] + 1],
-                        "x": lg[:, :, [L["XFULL"] + 4, L["XFULL"] + 7, L["XFULL"] + 1]],
-                        "e": lg[:, :, L["E_THETA"]:L["E_THETA"] + 1], "a": lg[:, :, L["A"]:L["A"] + 1],
-                        "reward": lg[:, :, L["REWARD"]]}
+            self._store_logs(lg, steps)
         st = eng.stats()
         self.RSE = [st["rse"][:, 0], st["rse"][:, 1]]                        # objects.py:1488,1503-1504
         return self
+
+    def _store_logs(self, lg, steps):
+        """The log dict of objects.py:1083-1176 with a leading logged-agent axis: log[key] is (agents, N, width)."""
+        env = self.env
+        div = self._eng.int_field("DIVERGED_STEP")[: lg.shape[0]].to(torch.int64)
+        kk = torch.arange(steps, dtype=torch.int64, device=lg.device).unsqueeze(0).expand(lg.shape[0], steps)
+        last = torch.where(div >= 0, div - 1, torch.full_like(div, steps)).unsqueeze(1)
+        t = (torch.minimum(kk, last).to(torch.float64) + 1) * env.dt      # objects.py:1495 (N12); frozen after divergence (:1173-1174)
+        t = torch.where(last < 0, torch.zeros_like(t), t)                    # diverged at step 0: log['t'][-1] of a zero array
+        if self._log_mode == "compact":
+            L = _lib.NLL
+            self.log = {"t": t.unsqueeze(-1), "x_full": lg[:, :, L["XFULL"]:L["XFULL"] + 12],
+                        "a_cmd": lg[:, :, L["SURF"]:L["SURF"] + 1],
+                        "x": lg[:, :, [L["XFULL"] + 4, L["XFULL"] + 7, L["XFULL"] + 1]],
+                        "e": lg[:, :, L["E_THETA"]:L["E_THETA"] + 1], "a": lg[:, :, L["A"]:L["A"] + 1],
+                        "reward": lg[:, :, L["REWARD"]]}
+            return
+        if self._log_mode == "mc":                                           # functions.py:1040-1052, radians / SI
+            M = _lib.NLM
+            self.log = {"t": t.unsqueeze(-1), **{k.lower(): lg[:, :, v] for k, v in M.items() if k != "COUNT"}}
+            return
+        F = _lib.NLF_FIELDS
+
+        def col(name):
+            o, w = F[name]
+            return lg[:, :, o:o + w]
+        nan_like = lambda w: torch.where(torch.isnan(col("ETA_A")), col("ETA_A"), torch.zeros_like(col("ETA_A"))).expand(-1, -1, w)  # noqa: E731
+        self.log = {
+            "eta_a": col("ETA_A"), "t": t.unsqueeze(-1), "x_full": col("XFULL"), "RSE": col("RSE"), "x": col("X"),
+            "a_cmd": col("A_CMD"), "a_eff": col("A_EFF"),
+            "s": col("S").expand(-1, -1, self.s_dim),          # objects.py:1133: info['s'][0] broadcast over the row
+            "yref": col("YREF").expand(-1, -1, self.s_dim),    # objects.py:1134
+            "e": col("E"),
+            "a_weights1": col("A_W1"), "a_weights2": col("A_W2"), "c_weights1": col("C_W1"), "c_weights2": col("C_W2"),
+            "a_grad": col("A_GRAD"), "c_grad": col("C_GRAD"),
+            "a_elig": nan_like(50), "c_elig": nan_like(70),    # allocated, never written by the reference (:1111,1113)
+            "rls_params": col("RLS_PARAMS"), "rls_cov": col("RLS_COV"), "rls_eps_hist": col("RLS_EPS"),
+            "rls_eps_norm": col("RLS_EPS_NORM"),
+            "a": col("A"), "reward": col("REWARD")[:, :, 0],   # not in the reference's dict
+        }
 
     def stats(self) -> dict:
         return self._eng.stats()

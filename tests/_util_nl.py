@@ -4,7 +4,8 @@ import numpy as np
 from rl4afcs_b200._lib import NLE, NLI, NLN
 
 ENV_MAP = [("x_full", "XFULL", 12), ("x_act", "XACT", 3), ("x_lon", "XLON", 3), ("x_prev_lon", "XPREVLON", 3),
-           ("theta", "THETA", 12), ("cov", "COV", 16), ("eps", "EPS", 3), ("rse", "RSE", 2), ("Ea", "EA", 50)]
+           ("theta", "THETA", 12), ("cov", "COV", 16), ("eps", "EPS", 3), ("rse", "RSE", 2), ("Ea", "EA", 50),
+           ("rse_flight", "RSE_FLIGHT", 2)]
 ENV_SCALARS = [("eps_norm", "EPS_NORM"), ("nz_peak", "NZ_PEAK"), ("eta_a", "ETA_A"), ("eta_c", "ETA_C"),
                ("lambdaa", "LAMBDAA"), ("gl", "GL")]
 NET_MAP = [("s", "S", 4), ("s_prev", "SPREV", 4), ("W1a", "W1A", 40), ("W2a", "W2A", 10), ("W1c", "W1C", 40),

@@ -32,7 +32,8 @@ def test_struct_layouts_match_header_constants():
     from rl4afcs_b200 import _lib
 
     hdr = open(os.path.join(ROOT, "include", "rl4afcs_b200.h")).read()
-    for table, prefix in ((_lib.SPE, "RL4_SPE_"), (_lib.SPN, "RL4_SPN_"), (_lib.SPI, "RL4_SPI_"), (_lib.LF, "RL4_LF_"), (_lib.LB, "RL4_LB_")):
+    for table, prefix in ((_lib.SPE, "RL4_SPE_"), (_lib.SPN, "RL4_SPN_"), (_lib.SPI, "RL4_SPI_"), (_lib.LF, "RL4_LF_"), (_lib.LB, "RL4_LB_"),
+                          (_lib.NLL, "RL4_NLL_"), (_lib.NLF, "RL4_NLF_")):
         for k, v in table.items():
             m = re.search(prefix + k + r"\s*=\s*(\d+)", hdr)
             assert m and int(m.group(1)) == v, (prefix, k)

@@ -241,3 +241,87 @@ def test_mc_run_front_end_and_statistics(oracle):
     # and the whole batch against the oracle with the same per-agent configs
     n = 3 * seeds
     assert idhp.x_hist.shape == (n, 3000, 2)
+
+
+def _nl_env_config(th, **over):
+    trim_input = np.array([-0.02855, 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.55, 0.55, 0])
+    trim_state = np.array([0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0])
+    cfg = {"state_dim": 4, "action_dim": 3, "trim_input": trim_input, "trim_state": trim_state, "dt": 0.01,
+           "t_end": 90, "total_steps": 9000, "fault_time": 60, "fault_scenario": "none",
+           "reference": {"tracked_state": ["phi", "theta", "psi"], "signal": [0 * th, th, 0 * th]}}
+    cfg.update(over)
+    return cfg
+
+
+def test_idhpnonlin_full_log_dict(oracle):
+    """The log dict of IDHPnonlin._reset_logs / _log (objects.py:1083-1176): same keys and widths, leading agent axis."""
+    from oracle import nl_c
+    from rl4afcs_b200.envs.nonlinear.env import Ce500NonLinear
+    from rl4afcs_b200.objects import IDHPnonlin
+
+    B, steps = 5, 260
+    th = nl_c.theta_reference()
+    idhp_config = {"gamma": 0.6, "multistep": 1, "lr_decay": 0.998, "lambda_h": 0.95, "lambda_l": 0.95, "kappa": [1, 2, 1],
+                   "cooldown_time": 2.0, "sigma": 0.1, "warmup_time": 1.0, "error_thresh": 1, "tau": 0.02, "in_dims": 4,
+                   "actor_config": {"layers": {10: "tanh", 1: "tanh"}, "eta_h": 35.0, "eta_l": 5.0, "elig": "accumulating"},
+                   "critic_config": {"layers": {10: "tanh", 3: "linear"}, "eta_h": 1.4, "eta_l": 0.7, "elig": 1233},
+                   "rls_config": {"state_dim": 3, "action_dim": 1, "rls_gamma": 1, "rls_cov": 10 ** 6}}
+    env = Ce500NonLinear(_nl_env_config(th), batch=B, dtype="mixed")
+    idhp = IDHPnonlin(env, idhp_config, seed=3, verbose=0, log_agents=B, chunk=100)
+    idhp.train(steps)
+    widths = {"eta_a": 1, "t": 1, "x_full": 12, "RSE": 2, "x": 3, "a_cmd": 1, "a_eff": 1, "s": 4, "yref": 4, "e": 1,
+              "a_weights1": 40, "a_weights2": 10, "c_weights1": 40, "c_weights2": 30, "a_grad": 50, "a_elig": 50,
+              "c_grad": 70, "c_elig": 70, "rls_params": 12, "rls_cov": 16, "rls_eps_hist": 3, "rls_eps_norm": 1}
+    for k, w in widths.items():                                              # objects.py:1094-1119
+        assert tuple(idhp.log[k].shape) == (B, steps, w), (k, idhp.log[k].shape)
+    lg = {k: v.cpu().numpy() for k, v in idhp.log.items()}
+    assert np.allclose(lg["t"][0, :, 0], 0.01 * (np.arange(steps) + 1))                       # N12
+    assert np.array_equal(lg["x"], lg["x_full"][:, :, [4, 7, 1]])
+    assert np.array_equal(lg["s"], np.repeat(lg["x_full"][:, :, 4:5], 4, axis=2))              # objects.py:1133 broadcast quirk
+    assert np.array_equal(lg["yref"][0, :, 0], th[:steps]) and np.array_equal(lg["e"][:, :, 0], lg["x_full"][:, :, 7] - th[:steps])
+    assert np.array_equal(lg["RSE"][:, :, 0], np.sqrt(lg["e"][:, :, 0] ** 2))
+    assert np.allclose(lg["RSE"][:, :, 0].sum(axis=1), idhp.RSE[0].cpu().numpy(), rtol=1e-12)
+    assert not lg["a_elig"].any() and not lg["c_elig"].any() and not lg["a_grad"][:, 0].any()
+    assert lg["a_grad"][:, 5].any() and lg["c_grad"][:, 5].any()
+    # the logged gradient is the SGD step actually taken: W(k) = W(k-1) - lr * grad(k), float32
+    k = 50
+    lr = np.float32(35.0)
+    w_prev, w_now = lg["a_weights2"][:, k - 1].astype(np.float32), lg["a_weights2"][:, k].astype(np.float32)
+    assert np.array_equal(w_now, w_prev - lr * lg["a_grad"][:, k, 40:].astype(np.float32))
+    # learning-rate decay after the warm-up (objects.py:1235-1243): eta_a falls from eta_h towards eta_l
+    assert lg["eta_a"][0, 50, 0] == 35.0 and 5.0 < lg["eta_a"][0, -1, 0] < 35.0
+    # final log row == final state
+    assert np.array_equal(lg["rls_params"][:, -1].reshape(B, 4, 3), idhp.model.params.cpu().numpy())
+    assert np.array_equal(lg["a_weights1"][:, -1].reshape(B, 4, 10), idhp.actor.trainable_weights[0].double().cpu().numpy())
+
+
+def test_mc_test_hparam_front_end(oracle):
+    """MC_test_hparam (functions.py:931-1060): 3 algorithms x 4 repetitions in one batch, short episode."""
+    from oracle import nl_c
+    from rl4afcs_b200 import functions as F
+    from rl4afcs_b200.envs.nonlinear.env import Ce500NonLinear
+
+    N, reps, steps, split = 3, 4, 1200, 700
+    th = nl_c.theta_reference()
+    env = Ce500NonLinear(_nl_env_config(th, t_end=steps * 0.01, total_steps=steps), batch=N * reps, dtype="mixed")
+    configs = {"etaah": [35.0] * N, "etaal": [5.0] * N, "etach": [1.4] * N, "etacl": [0.7] * N, "lambda_hs": [0.95] * N,
+               "lambda_ls": [0.95] * N, "seeds": [0] * N, "ms": [0, 0, 1], "elig": [None, "accumulating", "replacing"]}
+    out = F.MC_test_hparam(configs, "unused/", env, N, reps, save=0, show=0, flight_step=split)
+    assert [o[0] for o in out] == ["idhp", "idhpat", "midhprt"]
+    for algo, cfg, log in out:
+        assert set(log) >= {"RSE", "e", "theta", "alpha", "q", "V", "h", "action_cmd", "action_eff", "n_z", "wa_norm",
+                            "wc_norm", "Sm", "rls_eps"}                       # functions.py:1008-1021
+        assert tuple(log["RSE"].shape) == (reps, 2) and tuple(log["theta"].shape) == (reps, steps) and tuple(log["Sm"].shape) == (reps, 1)
+        e = torch.deg2rad(log["e"])
+        assert torch.allclose(log["RSE"][:, 0], e[:, :split].abs().sum(dim=1), rtol=1e-9)      # :1036
+        assert torch.allclose(log["RSE"][:, 1], e[:, split:].abs().sum(dim=1), rtol=1e-9)      # :1037
+        assert torch.allclose(log["n_z"].abs().max(dim=1).values, log["max_nz"], rtol=1e-12)
+        assert float(log["wa_norm"].max()) == 1.0 and bool((log["Sm"] > 0).all())
+        th_fl = log["theta"][:, split:].cpu().numpy()
+        f = np.fft.fft(th_fl, axis=-1)
+        psd = np.abs(f * np.conj(f) / ((steps - split) * 0.01))[:, :(steps - split) // 2]
+        om = np.arange((steps - split) // 2) / ((steps - split) * 0.01)
+        assert np.allclose(log["Sm"][:, 0].cpu().numpy(), (psd * om).sum(axis=1), rtol=1e-8)   # :1033-1034
+    # repetition r starts from the same weights in every configuration: the first step's action is identical
+    a0 = torch.stack([o[2]["action_cmd"][:, 0] for o in out])
+    assert torch.equal(a0[0], a0[1]) and torch.equal(a0[0], a0[2])

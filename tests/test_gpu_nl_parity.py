@@ -173,3 +173,73 @@ def test_step_level_actor_big_critic_big(nl, policy):
             assert np.array_equal(W1.double().cpu().numpy().reshape(n, 40), st["W1a"]), k
             assert np.array_equal(W2.double().cpu().numpy().reshape(n, 10), st["W2a"]), k
             assert np.array_equal(actor.E.cpu().numpy().reshape(n, 50), st["Ea"]), k
+
+
+_FULL_LOG_MAP = (  # (kernel field, oracle log-row field, relative-error floor, network-side quantity?)
+    ("ETA_A", "eta_a", 1e-3, False), ("XFULL", "x_full", 1e-3, False), ("RSE", "rse_step", 1e-3, False),
+    ("A_CMD", None, 1e-4, False), ("A_EFF", None, 1e-4, False), ("S", None, 1e-3, False), ("YREF", "yref_theta", 1e-3, False),
+    ("E", "e_theta", 1e-4, False), ("A_W1", "W1a", 1e-2, True), ("A_W2", "W2a", 1e-2, True), ("C_W1", "W1c", 1e-2, True),
+    ("C_W2", "W2c", 1e-2, True), ("A_GRAD", "a_grad", 1e-3, True), ("C_GRAD", "c_grad", 1e-3, True),
+    ("RLS_PARAMS", "theta", 1e-4, None), ("RLS_EPS", "eps", 1e-6, None), ("RLS_EPS_NORM", "eps_norm", 1e-6, None),
+    ("A", "a_next", 1e-3, True), ("REWARD", "reward", 1e-4, False))
+
+
+@pytest.mark.parametrize("policy,case", [("mixed", dict()), ("fp64", dict(ms=1, elig=None)),
+                                         ("mixed", dict(fault="damp_elevator_and_saturate_elevator", fault_time=0.5))])
+def test_full_log_rows_teacher_forced(nl, policy, case):
+    """log.level 2 (the layout of IDHPnonlin._log, objects.py:1083-1176) against the oracle's per-step record."""
+    from rl4afcs_b200 import _lib
+
+    n, steps = 24, 160
+    eng, st, cfg, th = _setup(nl, n, policy, seed=11, **case)
+    rng = np.random.default_rng(4)
+    noise = rng.standard_normal((steps, n)).astype(np.float32)
+    f32 = policy == "mixed"
+    worst = {}
+    for k in range(steps):
+        _util_nl.oracle_to_engine(st, eng)
+        eng.k = k
+        olog = nl.run(policy, cfg, th, noise[k:k + 1], st, k, 1, tanh="t13", n_log=n)[:, 0]
+        row = eng.run(1, noise[k:k + 1], log_agents=n, log_level=2)[0].cpu().numpy()      # (fields, agents)
+        assert row.shape == (_lib.NLF["COUNT"], n)
+        for name, oname, floor, _ in _FULL_LOG_MAP:
+            off, w = _lib.NLF_FIELDS[name]
+            got = row[off:off + w].T
+            if name == "A_CMD":
+                want = olog["surf"][:, :1]
+            elif name == "A_EFF":
+                want = olog["model_input"][:, :1]
+            elif name == "S":
+                want = olog["x_full"][:, 4:5]
+            else:
+                want = olog[oname].reshape(n, w)
+            worst[name] = max(worst.get(name, 0.0), _util_nl.max_rel(got, want, floor))
+        off, w = _lib.NLF_FIELDS["X"]
+        assert np.array_equal(row[off:off + w], row[[1 + 4, 1 + 7, 1 + 1]])            # x_lon = x_full[4, 7, 1]
+        off, w = _lib.NLF_FIELDS["RLS_COV"]
+        worst["RLS_COV"] = max(worst.get("RLS_COV", 0.0), _util_nl.max_rel(
+            row[off:off + w].T, olog["cov"], np.abs(olog["cov"]).max(axis=1, keepdims=True) * 1e-6))
+        if k == 0:
+            off, w = _lib.NLF_FIELDS["A_GRAD"]
+            assert not row[off:off + 120].any()                                       # objects.py:1149: untouched at i = 0
+    for name, _, _, net in _FULL_LOG_MAP:
+        tol = (5e-6 if f32 else 1e-9) if net else ((1e-4 if f32 else 1e-7) if net is None else 1e-9)
+        assert worst[name] < tol, (name, worst[name])
+    assert worst["RLS_COV"] < (1e-4 if f32 else 1e-7)
+
+
+def test_full_log_nan_rows_after_divergence(nl):
+    """objects.py:1168-1175: the row of the step whose plant state turned NaN, and every later row, are NaN."""
+    from rl4afcs_b200 import _lib
+
+    n, steps = 8, 12
+    eng, st, cfg, th = _setup(nl, n, "mixed", seed=2)
+    noise = np.zeros((steps, n), dtype=np.float32)
+    eng.run(4, noise[:4])
+    eng.env_field("XFULL", 12)[3, 5] = float("nan")                                  # agent 5: airspeed becomes NaN
+    lg = eng.run(8, noise[4:], log_agents=n, log_level=2).cpu().numpy()              # (rows, fields, agents)
+    assert np.isnan(lg[:, :, 5]).all()
+    assert not np.isnan(lg[:, :, [0, 1, 2, 3, 4, 6, 7]]).any()
+    assert int(eng.int_field("DIVERGED_STEP")[5]) == 4
+    lg1 = eng.run(2, np.zeros((2, n), dtype=np.float32), log_agents=n, log_level=1).cpu().numpy()
+    assert lg1.shape[1] == _lib.NLL["COUNT"] and np.isnan(lg1[:, :, 5]).all()
