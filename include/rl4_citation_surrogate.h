@@ -22,13 +22,16 @@
  *
  * One definition, plain C, shared by the CUDA kernels (rl4afcs_b200/csrc/nl_kernels.cu) and the CPU
  * oracle's plant (oracle/nl_oracle.c): there is no reference to restate, so both sides must integrate
- * the SAME documented model; sin/cos/pow come from the respective math library (CUDA / glibc), hence
- * plant parity kernel-vs-oracle is a tolerance (1e-12 per step), not bit equality.
+ * the SAME documented model.  It is written with IEEE basic operations only (+, -, *, /, sqrt, fma): sine / cosine
+ * are the polynomial kernels below, the ISA power laws are binomial series whose coefficients sit in the parameter
+ * block -- no libm / CUDA math-library call is left, so kernel and oracle produce the SAME BITS.
  */
 #ifndef RL4_CITATION_SURROGATE_H
 #define RL4_CITATION_SURROGATE_H
 
 #include <math.h>
+#include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define RL4_HD __host__ __device__ __forceinline__
@@ -42,7 +45,7 @@
 #define RL4_UNROLL
 #endif
 
-enum { RL4_CIT_NX = 12, RL4_CIT_NU = 11 };
+enum { RL4_CIT_NX = 12, RL4_CIT_NU = 11, RL4_CIT_NPOLY = 21 };
 enum { RL4_CIT_P = 0, RL4_CIT_Q, RL4_CIT_R, RL4_CIT_V, RL4_CIT_ALPHA, RL4_CIT_BETA, RL4_CIT_PHI, RL4_CIT_THETA,
        RL4_CIT_PSI, RL4_CIT_H, RL4_CIT_XE, RL4_CIT_YE };
 enum { RL4_CIT_INTEGRATOR_RK4 = 0, RL4_CIT_INTEGRATOR_ODE5 = 1 };
@@ -62,55 +65,125 @@ typedef struct rl4_cit_params {
     double Tstatic;
     /* reciprocals used by rl4_cit_deriv, filled by rl4_cit_finalize() */
     double inv_m, inv_Iyy, inv_gam, inv_al_stall, inv_c, inv_b;
+    /* ISA troposphere as binomial series in zeta = lapse h / T0, filled by rl4_cit_finalize():
+     * rho / rho0 = (1 + zeta)^n_rho = sum rho_poly[k] zeta^k,  thrust lapse (rho / rho0)^0.7 = sum lapse_poly[k] zeta^k */
+    double zeta_per_m;
+    double rho_poly[RL4_CIT_NPOLY], lapse_poly[RL4_CIT_NPOLY];
 } rl4_cit_params;
+
+#define RL4_FMA(a, b, c) fma((a), (b), (c))
+#ifndef RL4_SINCOS_OUT_OF_LINE
+#define RL4_SINCOS_OUT_OF_LINE 1   /* measured: fp64 kernel +27 %, mixed kernel -0.7 % against the inlined form */
+#endif
 
 /* derived constants; call after changing m, inertias, al_stall, c or b */
 RL4_HD void rl4_cit_finalize(rl4_cit_params* P)
 {
+    const double T0 = 288.15, lapse = -0.0065, R = 287.05, g0 = 9.80665;
+    const double n_rho = -(g0 / (lapse * R) + 1.0);       /* 4.2559 */
+    const double n_lapse = 0.7 * n_rho;
+    int k;
     P->inv_m = 1.0 / P->m; P->inv_Iyy = 1.0 / P->Iyy; P->inv_gam = 1.0 / (P->Ixx * P->Izz - P->Ixz * P->Ixz);
     P->inv_al_stall = 1.0 / P->al_stall; P->inv_c = 1.0 / P->c; P->inv_b = 1.0 / P->b;
+    P->zeta_per_m = lapse / T0;
+    P->rho_poly[0] = 1.0; P->lapse_poly[0] = 1.0;
+    for (k = 1; k < RL4_CIT_NPOLY; ++k) {                  /* generalised binomial coefficients C(n, k) */
+        P->rho_poly[k] = P->rho_poly[k - 1] * (n_rho - (double)(k - 1)) / (double)k;
+        P->lapse_poly[k] = P->lapse_poly[k - 1] * (n_lapse - (double)(k - 1)) / (double)k;
+    }
 }
 
-/* ISA troposphere density */
-RL4_HD double rl4_cit_density(double h)
-{
-    const double T0 = 288.15, lapse = -0.0065, R = 287.05, g0 = 9.80665, rho0 = 1.225;
-    const double Tr = 1.0 + lapse * h / T0;
-    return rho0 * pow(Tr, -(g0 / (lapse * R) + 1.0));
-}
-
+/* sin and cos from IEEE basic operations: Cody-Waite reduction by pi/2 with two FMAs (k = nearest integer to
+ * a * 2/pi via the 1.5 * 2^52 shift), then the classical minimax kernels on [-pi/4, pi/4] (coefficients of the
+ * fdlibm __kernel_sin / __kernel_cos polynomials), < 1.5 ulp for the angles of flight.  The same expression tree on
+ * CUDA (-fmad=false, explicit FMAs) and on the host (-ffp-contract=off, fma()) gives the same bits. */
+#define RL4_SC_LIST(X) \
+    X(6.36619772367581382433e-01)  /* 0: 2/pi            */ \
+    X(6755399441055744.0)          /* 1: 1.5 * 2^52      */ \
+    X(1.57079632679489655800e+00)  /* 2: pi/2 high       */ \
+    X(6.12323399573676603587e-17)  /* 3: pi/2 low        */ \
+    X(-1.66666666666666324348e-01) /* 4..9: S1..S6       */ \
+    X(8.33333333332248946124e-03)  \
+    X(-1.98412698298579493134e-04) \
+    X(2.75573137070700676789e-06)  \
+    X(-2.50507602534068634195e-08) \
+    X(1.58969099521155010221e-10)  \
+    X(4.16666666666666019037e-02)  /* 10..15: C1..C6     */ \
+    X(-1.38888888888741095749e-03) \
+    X(2.48015872894767294178e-05)  \
+    X(-2.75573143513906633035e-07) \
+    X(2.08757232129817482790e-09)  \
+    X(-1.13596475577881948265e-11)
+#define RL4_SC_ELEM(v) v,
+#if defined(__CUDACC__)
+static __constant__ double rl4_sc_dev[16] = { RL4_SC_LIST(RL4_SC_ELEM) };   /* constant bank: an FMA operand, no moves */
+#endif
+static const double rl4_sc_host[16] = { RL4_SC_LIST(RL4_SC_ELEM) };
 #if defined(__CUDA_ARCH__)
-/* One out-of-line copy of sincos (values in registers, no pointers): the derivative is inlined 4-6 times per step with
- * five sincos each, and CUDA's inlined double sincos is ~86 SASS instructions -- that alone was 20 % of the fused
- * kernel's code and pushed it out of the instruction cache (profiles/README.md).
- * Exact-zero shortcut: in symmetric flight (da = dr = 0) beta, phi and psi are identically zero, and
- * sin(+-0) = +-0, cos(0) = 1 are what sincos returns anyway. */
-static __device__ __noinline__ double2 rl4_sincos_ool(double a)
+#define RL4_SC(i) rl4_sc_dev[i]
+#define RL4_LOINT(t) __double2loint(t)
+#else
+#define RL4_SC(i) rl4_sc_host[i]
+static inline int rl4_loint_host(double t) { int64_t b; memcpy(&b, &t, sizeof b); return (int)(uint32_t)(uint64_t)b; }
+#define RL4_LOINT(t) rl4_loint_host(t)
+#endif
+
+RL4_HD void rl4_sincos(double a, double* s, double* c)
 {
-    double2 r;
-    sincos(a, &r.x, &r.y);
-    return r;
+    const double t = RL4_FMA(a, RL4_SC(0), RL4_SC(1));
+    const double kd = t - RL4_SC(1);
+    const int k = RL4_LOINT(t);
+    double r = RL4_FMA(-kd, RL4_SC(2), a);
+    r = RL4_FMA(-kd, RL4_SC(3), r);
+    {
+        const double z = r * r;
+        double ps = RL4_FMA(z, RL4_SC(9), RL4_SC(8)), pc = RL4_FMA(z, RL4_SC(15), RL4_SC(14));
+        ps = RL4_FMA(z, ps, RL4_SC(7)); pc = RL4_FMA(z, pc, RL4_SC(13));
+        ps = RL4_FMA(z, ps, RL4_SC(6)); pc = RL4_FMA(z, pc, RL4_SC(12));
+        ps = RL4_FMA(z, ps, RL4_SC(5)); pc = RL4_FMA(z, pc, RL4_SC(11));
+        ps = RL4_FMA(z, ps, RL4_SC(4)); pc = RL4_FMA(z, pc, RL4_SC(10));
+        {
+            const double sn = RL4_FMA(r * z, ps, r);
+            const double cs = RL4_FMA(z * z, pc, RL4_FMA(z, -0.5, 1.0));
+            const double S = (k & 1) ? cs : sn, C = (k & 1) ? sn : cs;
+            *s = (k & 2) ? -S : S;
+            *c = ((k + 1) & 2) ? -C : C;
+        }
+    }
 }
+/* Exact-zero shortcut (part of the definition, applied on both sides): sin(+-0) = +-0, cos(0) = 1.  In symmetric
+ * flight (da = dr = 0) beta, phi and psi are identically zero, so three of the five evaluations per derivative are
+ * skipped by a warp-uniform branch in the pitch-tracking task. */
+#if defined(__CUDA_ARCH__) && RL4_SINCOS_OUT_OF_LINE
+/* one out-of-line copy, values in registers (the derivative is inlined 4-6 times per step with five call sites each) */
+static __device__ __noinline__ double2 rl4_sincos_ool(double a) { double2 r; rl4_sincos(a, &r.x, &r.y); return r; }
 #define RL4_SINCOS(a, s, c) do { if ((a) == 0.0) { (s) = (a); (c) = 1.0; } else { const double2 sc_ = rl4_sincos_ool(a); (s) = sc_.x; (c) = sc_.y; } } while (0)
 #else
-#define RL4_SINCOS(a, s, c) do { (s) = sin(a); (c) = cos(a); } while (0)
+#define RL4_SINCOS(a, s, c) do { if ((a) == 0.0) { (s) = (a); (c) = 1.0; } else { rl4_sincos((a), &(s), &(c)); } } while (0)
 #endif
 
 /* Air data frozen over one integration step (zero-order hold like the inputs): density and the thrust
- * lapse (rho/rho0)^0.7 are evaluated at the altitude at the START of the step; h changes by < 1 m per step. */
+ * lapse (rho/rho0)^0.7 are evaluated at the altitude at the START of the step; h changes by < 1 m per step.
+ * The series are exact to 1e-16 relative from -2 km to 11 km (|zeta| < 0.25, 21 terms). */
 typedef struct rl4_cit_air { double rho, thrust_lapse; } rl4_cit_air;
-RL4_HD rl4_cit_air rl4_cit_airdata(double h)
+RL4_HD rl4_cit_air rl4_cit_airdata(const rl4_cit_params* P, double h)
 {
     rl4_cit_air a;
-    a.rho = rl4_cit_density(h);
-    a.thrust_lapse = pow(a.rho / 1.225, 0.7);
+    const double zeta = P->zeta_per_m * h;
+    double pr = P->rho_poly[RL4_CIT_NPOLY - 1], pl = P->lapse_poly[RL4_CIT_NPOLY - 1];
+    int k;
+    RL4_UNROLL
+    for (k = RL4_CIT_NPOLY - 2; k >= 0; --k) { pr = RL4_FMA(pr, zeta, P->rho_poly[k]); pl = RL4_FMA(pl, zeta, P->lapse_poly[k]); }
+    a.rho = 1.225 * pr;
+    a.thrust_lapse = pl;
     return a;
 }
+/* ISA troposphere density */
+RL4_HD double rl4_cit_density(const rl4_cit_params* P, double h) { return rl4_cit_airdata(P, h).rho; }
 
 /* xdot = f(x, u).  Written for the FP64 pipe: sums of products are explicit FMA chains (RL4_FMA = fma() on both
- * the CUDA and the glibc side), constant denominators are reciprocals precomputed in the parameter block, and the
+ * the CUDA and the host side), constant denominators are reciprocals precomputed in the parameter block, and the
  * four state-dependent reciprocals (1/V, 1/sqrt(1+(al/al_s)^2), 1/cos(theta), 1/cos(beta)) are formed once. */
-#define RL4_FMA(a, b, c) fma((a), (b), (c))
 RL4_HD_NOINLINE void rl4_cit_deriv(const rl4_cit_params* P, const rl4_cit_air air, const double* x, const double* u, double* dx)
 {
     const double p = x[RL4_CIT_P], q = x[RL4_CIT_Q], r = x[RL4_CIT_R];
@@ -180,24 +253,26 @@ RL4_HD_NOINLINE void rl4_cit_deriv(const rl4_cit_params* P, const rl4_cit_air ai
     }
 }
 
-/* one fixed step, input held constant over the step (zero-order hold, like Simulink's fixed-step solvers) */
+/* one fixed step, input held constant over the step (zero-order hold, like Simulink's fixed-step solvers);
+ * stage combinations are explicit FMA chains (one rounding per term) */
 RL4_HD void rl4_cit_step_rk4(const rl4_cit_params* P, double* x, const double* u, double dt)
 {
     double k1[12], k2[12], k3[12], k4[12], y[12];
     int i;
-    const rl4_cit_air air = rl4_cit_airdata(x[RL4_CIT_H]);
+    const rl4_cit_air air = rl4_cit_airdata(P, x[RL4_CIT_H]);
+    const double hdt = 0.5 * dt, dt6 = dt / 6.0;
     rl4_cit_deriv(P, air, x, u, k1);
     RL4_UNROLL
-    for (i = 0; i < 12; ++i) y[i] = x[i] + 0.5 * dt * k1[i];
+    for (i = 0; i < 12; ++i) y[i] = RL4_FMA(hdt, k1[i], x[i]);
     rl4_cit_deriv(P, air, y, u, k2);
     RL4_UNROLL
-    for (i = 0; i < 12; ++i) y[i] = x[i] + 0.5 * dt * k2[i];
+    for (i = 0; i < 12; ++i) y[i] = RL4_FMA(hdt, k2[i], x[i]);
     rl4_cit_deriv(P, air, y, u, k3);
     RL4_UNROLL
-    for (i = 0; i < 12; ++i) y[i] = x[i] + dt * k3[i];
+    for (i = 0; i < 12; ++i) y[i] = RL4_FMA(dt, k3[i], x[i]);
     rl4_cit_deriv(P, air, y, u, k4);
     RL4_UNROLL
-    for (i = 0; i < 12; ++i) x[i] = x[i] + (dt / 6.0) * (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]);
+    for (i = 0; i < 12; ++i) x[i] = RL4_FMA(dt6, RL4_FMA(2.0, k2[i] + k3[i], k1[i] + k4[i]), x[i]);
 }
 
 /* Dormand-Prince 5(4) pair, 5th-order solution, fixed step: what Simulink calls ode5 */
@@ -205,31 +280,33 @@ RL4_HD void rl4_cit_step_ode5(const rl4_cit_params* P, double* x, const double* 
 {
     double k1[12], k2[12], k3[12], k4[12], k5[12], k6[12], y[12];
     int i;
-    const rl4_cit_air air = rl4_cit_airdata(x[RL4_CIT_H]);
+    const rl4_cit_air air = rl4_cit_airdata(P, x[RL4_CIT_H]);
+    const double dt5 = dt * (1.0 / 5.0);
     rl4_cit_deriv(P, air, x, u, k1);
     RL4_UNROLL
-    for (i = 0; i < 12; ++i) y[i] = x[i] + dt * (1.0 / 5.0) * k1[i];
+    for (i = 0; i < 12; ++i) y[i] = RL4_FMA(dt5, k1[i], x[i]);
     rl4_cit_deriv(P, air, y, u, k2);
     RL4_UNROLL
-    for (i = 0; i < 12; ++i) y[i] = x[i] + dt * ((3.0 / 40.0) * k1[i] + (9.0 / 40.0) * k2[i]);
+    for (i = 0; i < 12; ++i) y[i] = RL4_FMA(dt, RL4_FMA(9.0 / 40.0, k2[i], (3.0 / 40.0) * k1[i]), x[i]);
     rl4_cit_deriv(P, air, y, u, k3);
     RL4_UNROLL
-    for (i = 0; i < 12; ++i) y[i] = x[i] + dt * ((44.0 / 45.0) * k1[i] - (56.0 / 15.0) * k2[i] + (32.0 / 9.0) * k3[i]);
+    for (i = 0; i < 12; ++i)
+        y[i] = RL4_FMA(dt, RL4_FMA(32.0 / 9.0, k3[i], RL4_FMA(-56.0 / 15.0, k2[i], (44.0 / 45.0) * k1[i])), x[i]);
     rl4_cit_deriv(P, air, y, u, k4);
     RL4_UNROLL
     for (i = 0; i < 12; ++i)
-        y[i] = x[i] + dt * ((19372.0 / 6561.0) * k1[i] - (25360.0 / 2187.0) * k2[i] + (64448.0 / 6561.0) * k3[i] -
-                            (212.0 / 729.0) * k4[i]);
+        y[i] = RL4_FMA(dt, RL4_FMA(-212.0 / 729.0, k4[i], RL4_FMA(64448.0 / 6561.0, k3[i],
+                           RL4_FMA(-25360.0 / 2187.0, k2[i], (19372.0 / 6561.0) * k1[i]))), x[i]);
     rl4_cit_deriv(P, air, y, u, k5);
     RL4_UNROLL
     for (i = 0; i < 12; ++i)
-        y[i] = x[i] + dt * ((9017.0 / 3168.0) * k1[i] - (355.0 / 33.0) * k2[i] + (46732.0 / 5247.0) * k3[i] +
-                            (49.0 / 176.0) * k4[i] - (5103.0 / 18656.0) * k5[i]);
+        y[i] = RL4_FMA(dt, RL4_FMA(-5103.0 / 18656.0, k5[i], RL4_FMA(49.0 / 176.0, k4[i], RL4_FMA(46732.0 / 5247.0, k3[i],
+                           RL4_FMA(-355.0 / 33.0, k2[i], (9017.0 / 3168.0) * k1[i])))), x[i]);
     rl4_cit_deriv(P, air, y, u, k6);
     RL4_UNROLL
     for (i = 0; i < 12; ++i)
-        x[i] = x[i] + dt * ((35.0 / 384.0) * k1[i] + (500.0 / 1113.0) * k3[i] + (125.0 / 192.0) * k4[i] -
-                            (2187.0 / 6784.0) * k5[i] + (11.0 / 84.0) * k6[i]);
+        x[i] = RL4_FMA(dt, RL4_FMA(11.0 / 84.0, k6[i], RL4_FMA(-2187.0 / 6784.0, k5[i], RL4_FMA(125.0 / 192.0, k4[i],
+                           RL4_FMA(500.0 / 1113.0, k3[i], (35.0 / 384.0) * k1[i])))), x[i]);
 }
 
 /* Default parameter set: Ce500 Citation derivatives, with CL0 / Cm0 / Tstatic solved for the trim point
@@ -237,7 +314,7 @@ RL4_HD void rl4_cit_step_ode5(const rl4_cit_params* P, double* x, const double* 
 RL4_HD void rl4_cit_default_params(rl4_cit_params* P)
 {
     const double V = 90.0, h = 2000.0, al = 0.0576, de = -0.02855, thr = 0.55;
-    double rho, qS, sa, ca, W, T, CLt, A, B, C, al_e, al_x;
+    double rho, lapse, qS, sa, ca, W, T, CLt, A, B, C, al_e, al_x;
     P->m = 4547.8; P->S = 24.2; P->c = 2.022; P->b = 13.36; P->g = 9.80665;
     P->Ixx = P->m * P->b * P->b * 0.012; P->Izz = P->m * P->b * P->b * 0.037; P->Ixz = P->m * P->b * P->b * 0.002;
     P->Iyy = P->m * P->c * P->c * 0.980;       /* K_Y^2 = Iyy / (m c^2) */
@@ -249,7 +326,12 @@ RL4_HD void rl4_cit_default_params(rl4_cit_params* P)
     P->Cnb = 0.1638; P->Cnp = -0.0108; P->Cnr = -0.193; P->Cnda = 0.0286; P->Cndr = -0.1261;
     /* level trim: T cos(al) = D, L + T sin(al) = W with D = qS (CD0 + k CL^2), L = qS CL:
      * k/qS * (W - T sa)^2 + qS CD0 - T ca = 0  ->  quadratic in T, smaller root */
-    rho = rl4_cit_density(h); qS = 0.5 * rho * V * V * P->S; sa = sin(al); ca = cos(al); W = P->m * P->g;
+    rl4_cit_finalize(P);                                   /* atmosphere tables are needed by the trim solve */
+    {
+        const rl4_cit_air air = rl4_cit_airdata(P, h);
+        rho = air.rho; lapse = air.thrust_lapse;
+    }
+    qS = 0.5 * rho * V * V * P->S; rl4_sincos(al, &sa, &ca); W = P->m * P->g;
     al_e = al / sqrt(1.0 + (al / P->al_stall) * (al / P->al_stall)); al_x = al - al_e;
     A = P->CDk / qS * sa * sa; B = -(2.0 * P->CDk / qS * W * sa + ca);
     C = P->CDk / qS * W * W + qS * (P->CD0 + P->CDstall * al_x * al_x);
@@ -257,7 +339,7 @@ RL4_HD void rl4_cit_default_params(rl4_cit_params* P)
     CLt = (W - T * sa) / qS;
     P->CL0 = CLt - P->CLa * al_e - P->CLde * de;
     P->Cm0 = -(P->Cma * al + P->Cmstall * al_x + P->Cmde * de);
-    P->Tstatic = T / (pow(rho / 1.225, 0.7) * thr);
+    P->Tstatic = T / (lapse * thr);
     rl4_cit_finalize(P);
 }
 

@@ -375,7 +375,8 @@ int rl4_sp_episode_host(rl4_ctx* ctx, const rl4_sp_params* p, const rl4_sp_host_
 int rl4_peak_fma(int is_double, double* out_flops_per_s, void* stream);
 /* Test hook: element-wise probe of the arithmetic primitives on device arrays.
  * op 0: tanh t13 (double)  1: tanh t13 (float)  2: shared-reciprocal division a/b (double)
- * 3: __ddiv_rn(a, b).  Used by tests/test_gpu_math.py only. */
+ * 3: __ddiv_rn(a, b)  4 / 5: rl4_sincos sine / cosine  6 / 7: ISA density / thrust lapse at altitude a (b = device copy
+ * of an rl4_cit_params).  Used by tests/test_gpu_math.py only. */
 int rl4_test_math(int op, const void* a, const void* b, void* out, int64_t n, void* stream);
 /* Test hook: exhaustive comparison of the float t13 quotient em/(em+2) with __fdiv_rn over the float
  * bit patterns [lo_bits, hi_bits); adds the number of mismatches to *device_mismatch_counter. */

@@ -14,7 +14,8 @@ PLANT_FIELDS = ["m", "S", "c", "b", "Ixx", "Iyy", "Izz", "Ixz", "g", "CL0", "CLa
                 "CYb", "CYp", "CYr", "CYda", "CYdr", "Clb", "Clp", "Clr", "Clda", "Cldr",
                 "Cnb", "Cnp", "Cnr", "Cnda", "Cndr", "Tstatic",
                 "inv_m", "inv_Iyy", "inv_gam", "inv_al_stall", "inv_c", "inv_b"]
-PLANT_DTYPE = np.dtype([(f, "f8") for f in PLANT_FIELDS], align=True)
+PLANT_DTYPE = np.dtype([(f, "f8") for f in PLANT_FIELDS] + [("zeta_per_m", "f8"), ("rho_poly", "f8", (21,)),
+                        ("lapse_poly", "f8", (21,))], align=True)
 
 CFG_DTYPE = np.dtype([
     ("plant", PLANT_DTYPE), ("trim_input", "f8", (11,)), ("dt", "f8"),

@@ -81,4 +81,10 @@ int orc_nl_run(int policy, int tanh_mode, const orc_nl_cfg* cfgs, int cfg_stride
 
 int orc_nl_sizeof_cfg(void)    { return (int)sizeof(orc_nl_cfg); }
 int orc_nl_sizeof_state(void)  { return (int)sizeof(orc_nl_state); }
+/* element-wise probes of the plant's deterministic elementary functions (tests) */
+void orc_cit_sincos(const double* a, double* s, double* c, int64_t n) { for (int64_t i = 0; i < n; ++i) rl4_sincos(a[i], s + i, c + i); }
+void orc_cit_air(const rl4_cit_params* P, const double* h, double* rho, double* lapse, int64_t n)
+{
+    for (int64_t i = 0; i < n; ++i) { const rl4_cit_air a = rl4_cit_airdata(P, h[i]); rho[i] = a.rho; lapse[i] = a.thrust_lapse; }
+}
 int orc_nl_sizeof_logrow(void) { return (int)sizeof(orc_nl_logrow); }

@@ -80,8 +80,13 @@ CIT_FIELDS = ["m", "S", "c", "b", "Ixx", "Iyy", "Izz", "Ixz", "g", "CL0", "CLa",
               "inv_m", "inv_Iyy", "inv_gam", "inv_al_stall", "inv_c", "inv_b"]
 
 
+CIT_NPOLY = 21
+
+
 class CitParams(ctypes.Structure):
-    _fields_ = [(f, ctypes.c_double) for f in CIT_FIELDS]
+    _fields_ = [(f, ctypes.c_double) for f in CIT_FIELDS] + [("zeta_per_m", ctypes.c_double),
+                                                              ("rho_poly", ctypes.c_double * CIT_NPOLY),
+                                                              ("lapse_poly", ctypes.c_double * CIT_NPOLY)]
 
 
 class NlState(ctypes.Structure):

@@ -1,10 +1,10 @@
 // Nonlinear IDHP path (sm_100a): Ce500NonLinear wrapper + surrogate 6-DOF plant + IDHPnonlin agent,
 // fused into one persistent kernel, one aircraft+agent per thread.
 //
-// Round-1 layout: correctness first.  The per-agent state is ~320 scalars (4-10-{1,3} nets, traces,
-// 4x4 RLS covariance, 12 plant states), more than the 255-register budget, so ptxas keeps part of the
-// network weights in thread-local memory (L1-resident); DESIGN.md section 6 discusses the shared-memory
-// / lane-split layout planned for the next round.
+// The per-agent state (~1.7 KB mixed / 2.6 KB fp64: 4-10-{1,3} nets, traces, 4x4 RLS covariance, 12 plant states)
+// exceeds the 255-register budget: the actor trace and the target critic live in shared memory, ptxas keeps the rest
+// in registers + ~1.3 KB of local memory.  256 agents per SM fill the register file and 174 KB of shared memory;
+// DESIGN.md section 9 has the capacity analysis and the measured alternatives (RL4_NL_SMEM_* / RL4_NL_BLOCK below).
 //
 // Arithmetic: built with -fmad=false, FMAs explicit; numpy-side `@` orders as measured for these
 // shapes, TensorFlow-side `@` in-order chains, tanh = t13.
@@ -42,6 +42,14 @@ __device__ __forceinline__ double nsqrt(double a) { return sqrt_rn(Rn<double>(a)
 #ifndef RL4_NL_MINB
 #define RL4_NL_MINB 1
 #endif
+#ifndef RL4_NL_SMEM_RLS
+#define RL4_NL_SMEM_RLS 0       // RLS parameters (12) and covariance (16) in shared memory instead of registers
+#endif
+#ifndef RL4_NL_SMEM_ACTOR
+#define RL4_NL_SMEM_ACTOR 0     // actor weights (50) in shared memory instead of registers
+#endif
+constexpr int kNlSmemDoubles = 50 + (RL4_NL_SMEM_RLS ? 28 : 0);
+constexpr int kNlSmemNet = 70 + (RL4_NL_SMEM_ACTOR ? 50 : 0);
 
 // per-thread arrays kept in shared memory, laid out [element][thread] (conflict-free, no indexing cost):
 // the actor trace E (50 doubles) and the target-critic weights (70 values) are touched once or twice per
@@ -195,11 +203,26 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
 
     // ---- load ----
     extern __shared__ __align__(16) unsigned char nl_smem[];
-    const Strided<double> Ea{reinterpret_cast<double*>(nl_smem) + threadIdx.x};
-    const Strided<TN> W1t{reinterpret_cast<TN*>(nl_smem + sizeof(double) * 50 * RL4_NL_BLOCK) + threadIdx.x};
-    const Strided<TN> W2t{reinterpret_cast<TN*>(nl_smem + sizeof(double) * 50 * RL4_NL_BLOCK) + 40 * RL4_NL_BLOCK + threadIdx.x};
+    // layout: doubles first ([Ea 50][th 12 + cv 16 when RL4_NL_SMEM_RLS]), then TN ([W1t 40][W2t 30][W1a 40 + W2a 10 when RL4_NL_SMEM_ACTOR])
+    double* const sm_d = reinterpret_cast<double*>(nl_smem) + threadIdx.x;
+    TN* const sm_n = reinterpret_cast<TN*>(nl_smem + sizeof(double) * kNlSmemDoubles * RL4_NL_BLOCK) + threadIdx.x;
+    const Strided<double> Ea{sm_d};
+    const Strided<TN> W1t{sm_n};
+    const Strided<TN> W2t{sm_n + 40 * RL4_NL_BLOCK};
+#if RL4_NL_SMEM_RLS
+    const Strided<double> th{sm_d + 50 * RL4_NL_BLOCK};
+    const Strided<double> cv{sm_d + 62 * RL4_NL_BLOCK};
+    double x[12], x_act[3], x_lon[3], x_prev_lon[3], eps[3];
+#else
     double x[12], x_act[3], x_lon[3], x_prev_lon[3], th[12], cv[16], eps[3];
+#endif
+#if RL4_NL_SMEM_ACTOR
+    const Strided<TN> W1a{sm_n + 70 * RL4_NL_BLOCK};
+    const Strided<TN> W2a{sm_n + 110 * RL4_NL_BLOCK};
+    TN s[4], s_prev[4], W1c[40], W2c[30], Mp[9];
+#else
     TN s[4], s_prev[4], W1a[40], W2a[10], W1c[40], W2c[30], Mp[9];
+#endif
     for (int j = 0; j < 12; ++j) { x[j] = EF(RL4_NLE_XFULL + j); th[j] = EF(RL4_NLE_THETA + j); }
     for (int j = 0; j < 3; ++j) { x_act[j] = EF(RL4_NLE_XACT + j); x_lon[j] = EF(RL4_NLE_XLON + j); x_prev_lon[j] = EF(RL4_NLE_XPREVLON + j); eps[j] = EF(RL4_NLE_EPS + j); }
     for (int j = 0; j < 16; ++j) cv[j] = EF(RL4_NLE_COV + j);
@@ -592,7 +615,7 @@ template <typename TN, int INTEG, bool LOG>
 static int nl_launch_one(const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride, int k0,
                          int n_steps, rl4_nl_state st, int64_t n, rl4_sp_log lg, unsigned grid, cudaStream_t s)
 {
-    const size_t smem = (sizeof(double) * 50 + sizeof(TN) * 70) * RL4_NL_BLOCK;
+    const size_t smem = (sizeof(double) * kNlSmemDoubles + sizeof(TN) * kNlSmemNet) * RL4_NL_BLOCK;
     static bool configured = false;
     if (!configured) {
         RL4_CUDA(cudaFuncSetAttribute(nl_run_kernel<TN, INTEG, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -84,6 +84,17 @@ __global__ void math_probe_kernel(int op, const void* a, const void* b, void* ou
     case 1: ((float*)out)[i] = tanh_t13(Rn<float>(((const float*)a)[i])).v; break;
     case 2: { const double d = ((const double*)b)[i]; ((double*)out)[i] = div_rn_shared(((const double*)a)[i], d, rcp_refined(d)); break; }
     case 3: ((double*)out)[i] = __ddiv_rn(((const double*)a)[i], ((const double*)b)[i]); break;
+    case 4: case 5: {   // the surrogate plant's sine / cosine (include/rl4_citation_surrogate.h)
+        double sn, cs;
+        rl4_sincos(((const double*)a)[i], &sn, &cs);
+        ((double*)out)[i] = (op == 4) ? sn : cs;
+        break;
+    }
+    case 6: case 7: {   // ISA density / thrust lapse series of the default plant at altitude a[i]; b = rl4_cit_params on the device
+        const rl4_cit_air air = rl4_cit_airdata((const rl4_cit_params*)b, ((const double*)a)[i]);
+        ((double*)out)[i] = (op == 6) ? air.rho : air.thrust_lapse;
+        break;
+    }
     default: break;
     }
 }
@@ -136,8 +147,8 @@ int rl4_peak_fma(int is_double, double* out_flops_per_s, void* stream)
 
 int rl4_test_math(int op, const void* a, const void* b, void* out, int64_t n, void* stream)
 {
-    RL4_REQUIRE(a && out && n >= 0 && op >= 0 && op <= 3, "bad argument");
-    RL4_REQUIRE(op < 2 || b, "b is NULL");
+    RL4_REQUIRE(a && out && n >= 0 && op >= 0 && op <= 7, "bad argument");
+    RL4_REQUIRE(!((op == 2 || op == 3 || op == 6 || op == 7) && !b), "second operand is NULL");
     if (n == 0) return 0;
     rl4::math_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(op, a, b, out, n);
     return rl4::check_launch("math_probe_kernel");

@@ -78,3 +78,52 @@ def test_float_t13_quotient_equals_ieee_for_every_float():
     _lib.check(L.rl4_test_t13_div_f32(0, hi, cnt.data_ptr(), None), "rl4_test_t13_div_f32")
     torch.cuda.synchronize()
     assert int(cnt.item()) == 0
+
+
+def test_plant_sincos_and_atmosphere_equal_oracle_bitwise(oracle):
+    """The surrogate plant's sine / cosine and ISA series (include/rl4_citation_surrogate.h) are IEEE basic operations
+    only: device == host bit for bit, and accurate (sin / cos < 2 ulp of libm; density == ISA power law to 1e-15)."""
+    import ctypes
+
+    from oracle import nl_c
+    from rl4afcs_b200 import _lib
+
+    L = nl_c.lib()
+    vp = ctypes.c_void_p
+    L.orc_cit_sincos.argtypes = [vp, vp, vp, ctypes.c_int64]
+    L.orc_cit_air.argtypes = [vp, vp, vp, vp, ctypes.c_int64]
+    rng = np.random.default_rng(3)
+    a = np.concatenate([rng.uniform(-0.8, 0.8, 300000), rng.uniform(-10, 10, 300000), rng.uniform(-1e4, 1e4, 100000),
+                        rng.standard_normal(1000) * 1e12, [0.0, -0.0, np.pi / 4, np.pi / 2, np.pi, 1e-300, 0.0576, np.inf, np.nan]])
+    s, c = np.empty_like(a), np.empty_like(a)
+    L.orc_cit_sincos(a.ctypes.data, s.ctypes.data, c.ctypes.data, a.size)
+    lib = _lib.load()
+    d_a = torch.as_tensor(a).cuda()
+    out = torch.empty_like(d_a)
+    for op, want in ((4, s), (5, c)):
+        _lib.check(lib.rl4_test_math(op, d_a.data_ptr(), None, out.data_ptr(), a.size, None), "rl4_test_math")
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), fin)                              # inf / nan inputs give nan on both sides
+        bad = np.flatnonzero(got[fin].view(np.uint64) != want[fin].view(np.uint64))
+        assert bad.size == 0, (op, a[fin][bad[:5]], got[fin][bad[:5]], want[fin][bad[:5]])
+    small = np.abs(a) <= 1e4
+    with np.errstate(invalid="ignore"):
+        assert np.max(np.abs(s[small] - np.sin(a[small])) / np.spacing(np.abs(np.sin(a[small])) + 1e-300)) <= 2.0
+        assert np.max(np.abs(c[small] - np.cos(a[small])) / np.spacing(np.abs(np.cos(a[small])) + 1e-300)) <= 2.0
+    # atmosphere
+    cfg = nl_c.make_cfg()
+    plant = np.ascontiguousarray(cfg["plant"][:1])
+    h = np.concatenate([rng.uniform(-2000, 11000, 200000), [0.0, 2000.0]])
+    rho, lapse = np.empty_like(h), np.empty_like(h)
+    L.orc_cit_air(plant.ctypes.data, h.ctypes.data, rho.ctypes.data, lapse.ctypes.data, h.size)
+    d_p = torch.as_tensor(plant.view(np.uint8)).cuda()
+    d_h = torch.as_tensor(h).cuda()
+    out = torch.empty_like(d_h)
+    for op, want in ((6, rho), (7, lapse)):
+        _lib.check(lib.rl4_test_math(op, d_h.data_ptr(), d_p.data_ptr(), out.data_ptr(), h.size, None), "rl4_test_math")
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy().view(np.uint64), want.view(np.uint64))
+    isa = 1.225 * (1 - 0.0065 * h / 288.15) ** (9.80665 / (0.0065 * 287.05) - 1)
+    assert np.max(np.abs(rho - isa) / isa) < 2e-15 and np.max(np.abs(lapse - (isa / 1.225) ** 0.7) / lapse) < 2e-15

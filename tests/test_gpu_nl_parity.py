@@ -1,8 +1,9 @@
 """GPU parity of the nonlinear path (Ce500NonLinear wrapper + surrogate plant + IDHPnonlin) against the CPU
 oracle (oracle/nl_oracle.c: restatement of envs/nonlinear/env.py:60-311 and objects.py:283-437,1006-1564).
 
-The plant integrates with sin/cos/pow of the respective math library (CUDA vs glibc), so kernel-vs-oracle is a
-tolerance test: teacher-forced per step (state re-seeded from the oracle every step) and a short free run.
+The surrogate plant is written with IEEE basic operations only (polynomial sin / cos, binomial-series atmosphere,
+explicit FMA chains), the networks use the t13 tanh: kernel == oracle BIT FOR BIT over free-running episodes
+(test_free_run_bit_exact).  The teacher-forced tolerance tests below predate that and stay as a second, looser net.
 The reference's own plant is a source-less binary: plant parity against the reference is unpinned."""
 import numpy as np
 import pytest
@@ -243,3 +244,64 @@ def test_full_log_nan_rows_after_divergence(nl):
     assert int(eng.int_field("DIVERGED_STEP")[5]) == 4
     lg1 = eng.run(2, np.zeros((2, n), dtype=np.float32), log_agents=n, log_level=1).cpu().numpy()
     assert lg1.shape[1] == _lib.NLL["COUNT"] and np.isnan(lg1[:, :, 5]).all()
+
+
+def test_full_size_batch_by_replication_property(nl):
+    """BASELINE.json configs[2] size (262144 agents): a batch that replicates a 256-agent block 1024 times must give
+    every replica the same bits (agents independent, no position-dependent arithmetic), per-agent fault settings
+    included, and the block itself stays with the oracle over the early part of the run."""
+    n_small, reps, steps = 256, 1024, 240
+    n = n_small * reps
+    from rl4afcs_b200 import _lib, nl_engine
+
+    cfg = nl.make_cfg()
+    w = nl.init_weights(n_small, 31)
+    st = nl.init_states("mixed", cfg, w, n_small)
+    th = nl.theta_reference()
+    rng = np.random.default_rng(9)
+    noise = rng.standard_normal((steps, n_small)).astype(np.float32)
+    olog = nl.run("mixed", cfg, th, noise, st, 0, steps, tanh="t13", n_log=n_small)
+    eng = nl_engine.NlEngine(n, policy="mixed")
+    eng.set_reference(th)
+    tile = lambda a: torch.as_tensor(a).cuda().repeat(reps, 1)    # noqa: E731
+    eng.init(tile(w["W1a"]), tile(w["W2a"]), tile(w["W1c"]), tile(w["W2c"]))
+    lg = eng.run(steps, torch.as_tensor(noise).cuda().repeat(1, reps), log_agents=n_small)
+    for plane in (eng.env, eng.net, eng.ints):
+        v = plane[:, :n].reshape(plane.shape[0], reps, n_small)
+        same = (v == v[:, :1, :]) | (torch.isnan(v) & torch.isnan(v[:, :1, :])) if plane.is_floating_point() else (v == v[:, :1, :])
+        assert bool(same.all())
+    x_gpu = np.transpose(lg.cpu().numpy()[:, _lib.NLL["XFULL"]:_lib.NLL["XFULL"] + 12, :], (2, 0, 1))
+    assert _util_nl.max_rel(x_gpu[:, :200, :9], olog["x_full"][:, :200, :9], 1e-2) < 1e-6
+
+
+_EXACT_FIELDS = ("x_full", "x_act", "x_lon", "x_prev_lon", "theta", "cov", "eps", "eps_norm", "rse", "rse_flight", "nz_peak",
+                 "eta_a", "eta_c", "lambdaa", "gl", "Ea", "s", "s_prev", "a", "a_prev", "W1a", "W2a", "W1c", "W2c", "W1t", "W2t",
+                 "M_prev", "lr_a", "lr_c", "cooldown", "diverged_step", "stepp")
+
+
+@pytest.mark.parametrize("policy,case", [
+    ("mixed", dict()),
+    ("fp64", dict()),
+    ("mixed", dict(integrator="rk4", elig="replacing", ms=1)),
+    ("fp64", dict(fault="shift_cg", fault_time=1.5, ms=1, elig=None)),
+    ("mixed", dict(fault="damp_elevator_and_saturate_elevator", fault_time=2.0)),
+])
+def test_free_run_bit_exact(nl, policy, case):
+    """The surrogate plant uses IEEE basic operations only (polynomial sin / cos, binomial-series atmosphere), the
+    networks the t13 tanh: a FREE-RUNNING episode on the GPU equals the oracle bit for bit, state and full log."""
+    from rl4afcs_b200 import _lib
+
+    n, steps = 96, 1500
+    eng, st, cfg, th = _setup(nl, n, policy, seed=21, **case)
+    rng = np.random.default_rng(5)
+    noise = rng.standard_normal((steps, n)).astype(np.float32)
+    olog = nl.run(policy, cfg, th, noise, st, 0, steps, tanh="t13", n_log=n)
+    lg = eng.run(steps, noise, log_agents=n, log_level=2).cpu().numpy()          # (rows, fields, agents)
+    got = _util_nl.engine_to_oracle(eng, nl)
+    for f in _EXACT_FIELDS:
+        assert np.array_equal(got[f], st[f], equal_nan=(got[f].dtype.kind == "f")), f
+    assert np.array_equal(got["cgrad_prev"][:, 2], st["cgrad_prev"][:, 2], equal_nan=True)
+    for name, oname in (("XFULL", "x_full"), ("A_W1", "W1a"), ("C_W2", "W2c"), ("A_GRAD", "a_grad"), ("C_GRAD", "c_grad"),
+                        ("RLS_PARAMS", "theta"), ("RLS_COV", "cov"), ("RSE", "rse_step"), ("ETA_A", "eta_a")):
+        off, w = _lib.NLF_FIELDS[name]
+        assert np.array_equal(np.transpose(lg[:, off:off + w, :], (2, 0, 1)), olog[oname].reshape(n, steps, w), equal_nan=True), name
