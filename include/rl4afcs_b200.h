@@ -336,6 +336,12 @@ int rl4_nl_init(int policy, const rl4_nl_params* p, const double* w1a, const dou
  * agents, layout as rl4_sp_log; the row of the step whose state turned NaN and every later row are NaN (objects.py:1168-1175). */
 int rl4_nl_run(int policy, const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride,
                int32_t k0, int32_t n_steps, rl4_nl_state st, int64_t n_agents, rl4_sp_log log, void* stream);
+/* RLS.update (objects.py:492-543) with the nonlinear task's dimensions (3 states + 1 action): theta [12][stride] ((4,3)
+ * row-major), cov [16][stride] in/out; dx0 [3][stride], da0 [stride], dx1 [3][stride]; out eps [3][stride], eps_norm
+ * [stride]; all double (both policies keep the RLS in float64).  Forgetting factor = p->hp[RL4_NHP_RLS_GAMMA] or its
+ * per-agent override. */
+int rl4_nl_rls_update(const rl4_nl_params* p, double* theta, double* cov, const double* dx0, const double* da0,
+                      const double* dx1, double* out_eps, double* out_eps_norm, int64_t stride, int64_t n_agents, void* stream);
 /* Critic_big.call (objects.py:294-339): s [4][stride], w1 [40][stride] ((4,10) row-major), w2 [30][stride] ((10,3)
  * row-major), all TN; out_lambda [3][stride]. */
 int rl4_nl_critic_forward(int policy, const void* s, void* w1, void* w2, void* out_lambda, int64_t stride,

@@ -91,6 +91,26 @@ def loop_fixture(name, *, x0, seed, fault=None, elig=(None, None), ms=2, steps=1
     return out
 
 
+def rls3_fixture(gamma, seed, steps=400, reset_at=250):
+    """Verbatim RLS (objects.py:439-549) with the nonlinear task's dimensions: 3 states + 1 action."""
+    RLS = ref_loader.load_reference_rls()
+    m = RLS({"state_dim": 3, "action_dim": 1, "rls_gamma": gamma, "rls_cov": 10 ** 6})
+    rng = np.random.default_rng(seed)
+    dx0 = rng.normal(size=(steps, 3, 1)) * 1e-3
+    da0 = (rng.normal(size=(steps, 1, 1)) * 1e-2).astype(np.float32)
+    Atrue = np.array([[0.99, 0.0, 0.0098], [0.0, 1.0, 0.01], [-0.016, 0.0, 0.984]]); Btrue = np.array([[-0.0003], [0.0], [-0.033]])
+    dx1 = Atrue @ dx0 + Btrue @ da0.astype(np.float64) + rng.normal(size=(steps, 3, 1)) * 1e-7
+    th, cv, ep, en = [], [], [], []
+    for k in range(steps):
+        if k == reset_at:
+            m._reset()
+        m.update(dx0[k], da0[k], dx1[k])
+        th.append(m.params.ravel().copy()); cv.append(m.Cov.ravel().copy())
+        ep.append(m.epsilon.ravel().copy()); en.append(float(m.eps_norm))
+    return dict(gamma=gamma, reset_at=reset_at, dx0=dx0[:, :, 0], da0=da0[:, 0, 0], dx1=dx1[:, :, 0],
+                theta=np.array(th), cov=np.array(cv), eps=np.array(ep), eps_norm=np.array(en))
+
+
 def utils_fixture():
     """Outputs of the verbatim utils.py functions (samplers with true_random=False, PSD, convergence time, VD_A, KL)."""
     U = ref_loader.load_reference_utils()
@@ -127,6 +147,8 @@ def utils_fixture():
 def main():
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, "utils_functions.npz"), **utils_fixture())
+    np.savez_compressed(os.path.join(OUT, "nl_rls_g1.npz"), **rls3_fixture(1, 17))
+    np.savez_compressed(os.path.join(OUT, "nl_rls_g0998.npz"), **rls3_fixture(0.998, 18))
     if "--only-utils" in sys.argv:
         return
     for i, f in enumerate([None, "invert_elevator", "damp_elevator", "shift_cg"]):

@@ -150,3 +150,16 @@ def run(policy, cfg, theta_ref, noise, states, k0, n_steps, *, tanh="libm", n_lo
     if rc:
         raise RuntimeError(f"orc_nl_run failed: {rc}")
     return log
+
+
+def rls_update(gamma, theta, cov, dx0, da0, dx1):
+    """Step-level RLS.update, n = 3, m = 1 (objects.py:492-543); theta (n,12) and cov (n,16) are updated in place."""
+    L = lib()
+    L.orc_nl_rls_update.argtypes = [ctypes.c_double] + [ctypes.c_void_p] * 7 + [ctypes.c_int64]
+    n = theta.shape[0]
+    dx0 = np.ascontiguousarray(np.broadcast_to(dx0, (n, 3)), dtype=np.float64)
+    dx1 = np.ascontiguousarray(np.broadcast_to(dx1, (n, 3)), dtype=np.float64)
+    da0 = np.ascontiguousarray(np.broadcast_to(np.asarray(da0, dtype=np.float64).reshape(-1), (n,)), dtype=np.float64)
+    eps, en = np.zeros((n, 3)), np.zeros(n)
+    L.orc_nl_rls_update(float(gamma), _ptr(theta), _ptr(cov), _ptr(dx0), _ptr(da0), _ptr(dx1), _ptr(eps), _ptr(en), n)
+    return eps, en

@@ -9,6 +9,40 @@
 #define M_PI 3.14159265358979323846
 #endif
 
+/* RLS.update for n = 3, m = 1 (objects.py:492-543).  numpy `@` orders measured for these shapes (header of
+ * nl_oracle.h): params.T @ X -> fma(a0,b0,a1*b1) + fma(a2,b2,a3*b3); Cov @ X -> (p0+p2)+(p1+p3) with rounded products;
+ * X.T @ (Cov X) and the norm -> in-order FMA chains. */
+static void orc_rls3_core(double* th, double* cv, const double* Xr, const double* Y, double gamma, double* eps, double* eps_norm)
+{
+    double pred[3], CX[4], K[4];
+    for (int i = 0; i < 3; ++i)
+        pred[i] = fma(th[0 * 3 + i], Xr[0], th[1 * 3 + i] * Xr[1]) + fma(th[2 * 3 + i], Xr[2], th[3 * 3 + i] * Xr[3]);
+    for (int i = 0; i < 3; ++i) eps[i] = Y[i] - pred[i];
+    for (int i = 0; i < 4; ++i) {
+        const double p0 = cv[i * 4 + 0] * Xr[0], p1 = cv[i * 4 + 1] * Xr[1], p2 = cv[i * 4 + 2] * Xr[2], p3 = cv[i * 4 + 3] * Xr[3];
+        CX[i] = (p0 + p2) + (p1 + p3);
+    }
+    double xcx = Xr[0] * CX[0];
+    for (int i = 1; i < 4; ++i) xcx = fma(Xr[i], CX[i], xcx);
+    const double den = gamma + xcx;
+    for (int i = 0; i < 4; ++i) K[i] = CX[i] / den;
+    for (int t = 0; t < 4; ++t)
+        for (int i = 0; i < 3; ++i) th[t * 3 + i] = th[t * 3 + i] + K[t] * eps[i];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) cv[i * 4 + j] = (cv[i * 4 + j] - K[i] * CX[j]) / gamma;
+    *eps_norm = sqrt(fma(eps[2], eps[2], fma(eps[1], eps[1], eps[0] * eps[0])));
+}
+
+/* step-level form: theta [n][12], cov [n][16], dx0 [n][3], da0 [n], dx1 [n][3] -> eps [n][3], eps_norm [n] */
+void orc_nl_rls_update(double gamma, double* theta, double* cov, const double* dx0, const double* da0, const double* dx1,
+                       double* eps, double* eps_norm, int64_t n)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        const double Xr[4] = {dx0[i * 3], dx0[i * 3 + 1], dx0[i * 3 + 2], da0[i]};
+        orc_rls3_core(theta + i * 12, cov + i * 16, Xr, dx1 + i * 3, gamma, eps + i * 3, eps_norm + i);
+    }
+}
+
 #define TE double
 
 #define TN float

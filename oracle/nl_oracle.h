@@ -86,6 +86,8 @@ int orc_nl_init(int policy, const orc_nl_cfg* cfgs, int cfg_stride, const double
 int orc_nl_run(int policy, int tanh_mode, const orc_nl_cfg* cfgs, int cfg_stride, const double* theta_ref,
                const float* noise, int k0, int n_steps, orc_nl_state* st, int64_t n,
                orc_nl_logrow* log, int64_t n_log);
+void orc_nl_rls_update(double gamma, double* theta, double* cov, const double* dx0, const double* da0, const double* dx1,
+                       double* eps, double* eps_norm, int64_t n);
 void orc_cit_sincos(const double* a, double* s, double* c, int64_t n);
 void orc_cit_air(const rl4_cit_params* P, const double* h, double* rho, double* lapse, int64_t n);
 int orc_nl_sizeof_cfg(void);

@@ -120,7 +120,7 @@ EXPORTS = [
     "rl4_sp_init", "rl4_sp_run", "rl4_sp_env_step", "rl4_sp_rls_update",
     "rl4_sp_critic_forward", "rl4_sp_actor_forward", "rl4_sp_critic_weight_update",
     "rl4_ctx_create", "rl4_ctx_destroy", "rl4_sp_episode_host",
-    "rl4_peak_fma", "rl4_launch_count", "rl4_test_math", "rl4_test_t13_div_f32",
+    "rl4_nl_rls_update", "rl4_peak_fma", "rl4_launch_count", "rl4_test_math", "rl4_test_t13_div_f32",
     "rl4_nl_init", "rl4_nl_run", "rl4_nl_env_step", "rl4_nl_default_params", "rl4_nl_critic_forward", "rl4_nl_actor_forward",
 ]
 
@@ -161,6 +161,7 @@ def load() -> ctypes.CDLL:
     L.rl4_nl_run.argtypes = [ctypes.c_int, ctypes.POINTER(NlParams), vp, vp, i64, i32, i32, NlState, i64, SpLog, vp]
     L.rl4_nl_env_step.argtypes = [ctypes.POINTER(NlParams), vp, i32, vp, vp, vp, vp, vp, vp, i64, i64, vp]
     L.rl4_nl_default_params.argtypes = [ctypes.POINTER(NlParams)]
+    L.rl4_nl_rls_update.argtypes = [ctypes.POINTER(NlParams), vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]
     L.rl4_nl_critic_forward.argtypes = [ctypes.c_int, vp, vp, vp, vp, i64, i64, vp]
     L.rl4_nl_actor_forward.argtypes = [ctypes.c_int, vp, vp, vp, vp, vp, vp, dbl, i32, i32, i64, i64, vp]
     L.rl4_test_t13_div_f32.argtypes = [ctypes.c_uint32, ctypes.c_uint32, vp, vp]

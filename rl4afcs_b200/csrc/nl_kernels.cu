@@ -124,6 +124,50 @@ __device__ __forceinline__ TN nl_actor(const TN (&s)[4], const WA W1, const WA W
     return a;
 }
 
+// RLS.update for n = 3, m = 1 (objects.py:492-543); numpy `@` orders as measured for these shapes:
+// params.T @ X -> fma(a0,b0,a1*b1) + fma(a2,b2,a3*b3); Cov @ X -> (p0+p2)+(p1+p3) with rounded products
+template <typename TH, typename CV>
+__device__ __forceinline__ void nl_rls_update(TH& th, CV& cv, const double (&Xr)[4], const double (&Y)[3], double rgam,
+                                              double (&eps)[3], double& eps_norm)
+{
+#pragma unroll
+    for (int ii = 0; ii < 3; ++ii) {
+        const double pred = __dadd_rn(__fma_rn(th[ii], Xr[0], __dmul_rn(th[3 + ii], Xr[1])),
+                                      __fma_rn(th[6 + ii], Xr[2], __dmul_rn(th[9 + ii], Xr[3])));
+        eps[ii] = Y[ii] - pred;
+    }
+    Rn<double> CX[4], K[4];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+        const double p0 = cv[ii * 4] * Xr[0], p1 = cv[ii * 4 + 1] * Xr[1], p2 = cv[ii * 4 + 2] * Xr[2], p3 = cv[ii * 4 + 3] * Xr[3];
+        CX[ii] = Rn<double>((p0 + p2) + (p1 + p3));
+    }
+    double xcx = Xr[0] * CX[0].v;
+#pragma unroll
+    for (int ii = 1; ii < 4; ++ii) xcx = __fma_rn(Xr[ii], CX[ii].v, xcx);
+    div_group<4>(CX, Rn<double>(rgam + xcx), K);
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int ii = 0; ii < 3; ++ii) th[t * 3 + ii] = th[t * 3 + ii] + K[t].v * eps[ii];
+    if (rgam == 1.0) {
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) cv[ii * 4 + j] = cv[ii * 4 + j] - K[ii].v * CX[j].v;
+    } else {
+        Rn<double> num[16], out[16];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) num[ii * 4 + j] = Rn<double>(cv[ii * 4 + j] - K[ii].v * CX[j].v);
+        div_group<16>(num, Rn<double>(rgam), out);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) cv[j] = out[j].v;
+    }
+    eps_norm = nsqrt(__fma_rn(eps[2], eps[2], __fma_rn(eps[1], eps[1], eps[0] * eps[0])));
+}
+
 // Ce500NonLinear.step without the agent (envs/nonlinear/env.py:182-256)
 template <bool PER_AGENT, int INTEG>
 __device__ __forceinline__ void nl_env_step(const rl4_nl_params& p, const NlHp<PER_AGENT>& hv, int stepp, double theta_ref_k,
@@ -414,43 +458,7 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
 #pragma unroll
                 for (int ii = 0; ii < 3; ++ii) { Xr[ii] = x_lon[ii] - x_prev_lon[ii]; Y[ii] = x_next_lon[ii] - x_lon[ii]; }
                 Xr[3] = (double)(a_k - a_prev);
-#pragma unroll
-                for (int ii = 0; ii < 3; ++ii) {                                   // params.T @ X: fma(0,1) + fma(2,3)
-                    const double pred = __dadd_rn(__fma_rn(th[ii], Xr[0], __dmul_rn(th[3 + ii], Xr[1])),
-                                                  __fma_rn(th[6 + ii], Xr[2], __dmul_rn(th[9 + ii], Xr[3])));
-                    eps[ii] = Y[ii] - pred;
-                }
-                Rn<double> CX[4], K[4];
-#pragma unroll
-                for (int ii = 0; ii < 4; ++ii) {                                   // Cov @ X: (p0+p2)+(p1+p3)
-                    const double p0 = cv[ii * 4] * Xr[0], p1 = cv[ii * 4 + 1] * Xr[1], p2 = cv[ii * 4 + 2] * Xr[2], p3 = cv[ii * 4 + 3] * Xr[3];
-                    CX[ii] = Rn<double>((p0 + p2) + (p1 + p3));
-                }
-                double xcx = Xr[0] * CX[0].v;
-#pragma unroll
-                for (int ii = 1; ii < 4; ++ii) xcx = __fma_rn(Xr[ii], CX[ii].v, xcx);
-                const double rgam = hv.hp(RL4_NHP_RLS_GAMMA);
-                div_group<4>(CX, Rn<double>(rgam + xcx), K);
-#pragma unroll
-                for (int t = 0; t < 4; ++t)
-#pragma unroll
-                    for (int ii = 0; ii < 3; ++ii) th[t * 3 + ii] = th[t * 3 + ii] + K[t].v * eps[ii];
-                if (rgam == 1.0) {
-#pragma unroll
-                    for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) cv[ii * 4 + j] = cv[ii * 4 + j] - K[ii].v * CX[j].v;
-                } else {
-                    Rn<double> num[16], out[16];
-#pragma unroll
-                    for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) num[ii * 4 + j] = Rn<double>(cv[ii * 4 + j] - K[ii].v * CX[j].v);
-                    div_group<16>(num, Rn<double>(rgam), out);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) cv[j] = out[j].v;
-                }
-                eps_norm = nsqrt(__fma_rn(eps[2], eps[2], __fma_rn(eps[1], eps[1], eps[0] * eps[0])));
+                nl_rls_update(th, cv, Xr, Y, hv.hp(RL4_NHP_RLS_GAMMA), eps, eps_norm);
             }
             {   // _adapt_check (objects.py:1212-1290)
                 const bool cond1 = k < hv.hpi(RL4_NHPI_WARMUP_STEPS);
@@ -611,6 +619,26 @@ nl_env_step_kernel(const __grid_constant__ rl4_nl_params p, const double* __rest
     out_reward[i] = reward; out_e[i] = e_th;
 }
 
+// RLS.update (objects.py:492-543) for n = 3, m = 1: step-API form, planes of double
+__global__ void __launch_bounds__(128)
+nl_rls_update_kernel(double rgam, const double* __restrict__ rgam_agent, double* theta, double* cov, const double* __restrict__ dx0,
+                     const double* __restrict__ da0, const double* __restrict__ dx1, double* __restrict__ out_eps,
+                     double* __restrict__ out_eps_norm, int64_t S, int64_t n_agents)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_agents) return;
+    double th[12], cv[16], Xr[4], Y[3], eps[3], eps_norm;
+    for (int j = 0; j < 12; ++j) th[j] = theta[j * S + i];
+    for (int j = 0; j < 16; ++j) cv[j] = cov[j * S + i];
+    for (int j = 0; j < 3; ++j) { Xr[j] = dx0[j * S + i]; Y[j] = dx1[j * S + i]; }
+    Xr[3] = da0[i];
+    nl_rls_update(th, cv, Xr, Y, rgam_agent ? __ldg(rgam_agent + i) : rgam, eps, eps_norm);
+    for (int j = 0; j < 12; ++j) theta[j * S + i] = th[j];
+    for (int j = 0; j < 16; ++j) cov[j * S + i] = cv[j];
+    for (int j = 0; j < 3; ++j) out_eps[j * S + i] = eps[j];
+    out_eps_norm[i] = eps_norm;
+}
+
 template <typename TN, int INTEG, bool LOG>
 static int nl_launch_one(const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride, int k0,
                          int n_steps, rl4_nl_state st, int64_t n, rl4_sp_log lg, unsigned grid, cudaStream_t s)
@@ -749,6 +777,17 @@ int rl4_nl_run(int policy, const rl4_nl_params* p, const double* theta_ref, cons
     else { set_error("rl4_nl_run: policy %d not supported on the nonlinear path (mixed or fp64)", policy); return -1; }
     if (rc) return rc;
     return check_launch("nl_run_kernel");
+}
+
+int rl4_nl_rls_update(const rl4_nl_params* p, double* theta, double* cov, const double* dx0, const double* da0, const double* dx1,
+                      double* out_eps, double* out_eps_norm, int64_t stride, int64_t n, void* stream)
+{
+    RL4_REQUIRE(p && theta && cov && dx0 && da0 && dx1 && out_eps && out_eps_norm, "NULL argument");
+    RL4_REQUIRE(n >= 0 && stride >= n, "bad size");
+    if (n == 0) return 0;
+    nl_rls_update_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        p->hp[RL4_NHP_RLS_GAMMA], p->hp_agent[RL4_NHP_RLS_GAMMA], theta, cov, dx0, da0, dx1, out_eps, out_eps_norm, stride, n);
+    return check_launch("nl_rls_update_kernel");
 }
 
 int rl4_nl_critic_forward(int policy, const void* s, void* w1, void* w2, void* out_lambda, int64_t stride, int64_t n, void* stream)

@@ -22,10 +22,18 @@ from ._lib import LB, LF, SPE, SPN
 class RLS:
     """Exponentially weighted recursive least squares on increments (objects.py:439-549)."""
 
+    def __new__(cls, config, *, batch: int = 1, device="cuda", dtype: str = "mixed", _engine=None):
+        if (config["state_dim"], config["action_dim"]) == (3, 1) and _engine is None:      # the nonlinear task's dimensions
+            from . import nl_engine
+            view = _RLSView(nl_engine.NlEngine(batch, policy=dtype, device=device), config)
+            view._reset()
+            return view
+        return super().__new__(cls)
+
     def __init__(self, config, *, batch: int = 1, device="cuda", dtype: str = "mixed", _engine=None) -> None:
         self.state_dim = config["state_dim"]
         self.action_dim = config["action_dim"]
-        assert (self.state_dim, self.action_dim) == (2, 1), "short-period RLS is 2 states + 1 action"
+        assert (self.state_dim, self.action_dim) == (2, 1), "RLS supports the reference's two shapes: (2, 1) and (3, 1)"
         self.gamma = config["rls_gamma"]
         self.init_cov = config["rls_cov"]
         self._eng = _engine if _engine is not None else sp_engine.SpEngine(batch, policy=dtype, device=device)
@@ -432,13 +440,29 @@ class Actor_big(_BigNetView):
 
 
 class _RLSView:
-    """RLS incremental model of the nonlinear agent (n = 3, m = 1): params (B,4,3), Cov (B,4,4)."""
+    """RLS incremental model with the nonlinear task's dimensions (n = 3, m = 1; objects.py:439-549): params (B,4,3),
+    Cov (B,4,4) are views of the agent's state planes, ``update`` / ``_reset`` are the step-level calls
+    (``rl4_nl_rls_update``).  Created by ``IDHPnonlin`` (shares its engine) or by ``RLS(config)`` with state_dim = 3."""
 
     def __init__(self, engine, config):
         self._eng = engine
         self.state_dim, self.action_dim = config["state_dim"], config["action_dim"]
+        assert (self.state_dim, self.action_dim) == (3, 1)
         self.gamma, self.init_cov = config["rls_gamma"], config["rls_cov"]
         self.batch = engine.n
+        self.eps_norm_hist = [0, 0]                       # objects.py:472-474
+        self.eps_hist = [np.zeros(self.state_dim)]
+        self.covs = []
+
+    def _reset(self):
+        """Theta <- 0, Cov <- init_cov * I (objects.py:477-482)."""
+        e = self._eng
+        e.env_field("THETA", 12).zero_()
+        cov = e.env_field("COV", 16)
+        cov.zero_()
+        c0 = torch.as_tensor(np.asarray(self.init_cov, dtype=np.float64)).to(e.device)
+        for d in (0, 5, 10, 15):
+            cov[d] = c0
 
     @property
     def params(self):
@@ -457,8 +481,31 @@ class _RLSView:
         return self.params[:, 3:, :].transpose(1, 2).clone()
 
     @property
+    def epsilon(self):
+        return self._eng.env_field("EPS", 3).t().unsqueeze(-1)
+
+    @property
     def eps_norm(self):
         return self._eng.env_field("EPS_NORM")[0]
+
+    def update(self, dx_t, da_t, dx_t1):
+        """dx_t (B,3,1), da_t (B,1,1), dx_t1 (B,3,1) -> updates params / Cov in place (objects.py:492-543)."""
+        e = self._eng
+
+        def plane(v, w):
+            return torch.as_tensor(v, device=e.device).to(torch.float64).reshape(self.batch, w).t().contiguous()
+
+        dx0, da0, dx1 = plane(dx_t, 3), plane(da_t, 1), plane(dx_t1, 3)
+        e.set_hp("RLS_GAMMA", self.gamma)
+        with torch.cuda.device(e.device):
+            rc = e.lib.rl4_nl_rls_update(ctypes.byref(e.params), e.env_field("THETA", 12).data_ptr(),
+                                         e.env_field("COV", 16).data_ptr(), dx0.data_ptr(), da0.data_ptr(), dx1.data_ptr(),
+                                         e.env_field("EPS", 3).data_ptr(), e.env_field("EPS_NORM").data_ptr(),
+                                         e.stride, self.batch, e._stream())
+            _lib.check(rc, "rl4_nl_rls_update")
+        self.eps_hist.append(self.epsilon.clone())
+        self.eps_norm_hist.append(self.eps_norm.clone())
+        self.covs.append(self.Cov.clone())
 
 
 class IDHPnonlin:

@@ -325,3 +325,26 @@ def test_mc_test_hparam_front_end(oracle):
     # repetition r starts from the same weights in every configuration: the first step's action is identical
     a0 = torch.stack([o[2]["action_cmd"][:, 0] for o in out])
     assert torch.equal(a0[0], a0[1]) and torch.equal(a0[0], a0[2])
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "nl_rls_*.npz"))))
+def test_rls3_update_equals_verbatim_reference(path):
+    """RLS with the nonlinear task's dimensions (3 states + 1 action), step-level: bit for bit the VERBATIM reference
+    class (objects.py:439-549) on the golden sequence, reset included."""
+    from rl4afcs_b200.objects import RLS
+
+    g = np.load(path)
+    B = 3
+    m = RLS({"state_dim": 3, "action_dim": 1, "rls_gamma": float(g["gamma"]), "rls_cov": 10 ** 6}, batch=B, dtype="mixed")
+    assert m.params.shape == (B, 4, 3) and m.Cov.shape == (B, 4, 4)
+    for k in range(len(g["da0"])):
+        if k == int(g["reset_at"]):
+            m._reset()
+        ex = lambda v, w: torch.as_tensor(v).reshape(1, w, 1).expand(B, w, 1)   # noqa: E731
+        m.update(ex(g["dx0"][k], 3), ex(g["da0"][k:k + 1], 1), ex(g["dx1"][k], 3))
+        assert np.array_equal(m.params.cpu().numpy().reshape(B, 12), np.broadcast_to(g["theta"][k], (B, 12))), k
+        assert np.array_equal(m.Cov.cpu().numpy().reshape(B, 16), np.broadcast_to(g["cov"][k], (B, 16))), k
+        assert np.array_equal(m.epsilon.cpu().numpy().reshape(B, 3), np.broadcast_to(g["eps"][k], (B, 3))), k
+        assert np.array_equal(m.eps_norm.cpu().numpy(), np.full(B, g["eps_norm"][k])), k
+    th = g["theta"][-1].reshape(4, 3)
+    assert np.array_equal(m.F.cpu().numpy()[0], th[:3].T) and np.array_equal(m.G.cpu().numpy()[0], th[3:].T)
