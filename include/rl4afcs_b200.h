@@ -351,10 +351,12 @@ int rl4_nl_critic_forward(int policy, const void* s, void* w1, void* w2, void* o
 int rl4_nl_actor_forward(int policy, const void* s, void* w1, void* w2, double* E, void* out_a, void* out_dads,
                          double gamma_lambda, int32_t elig, int32_t trace, int64_t stride, int64_t n_agents, void* stream);
 /* Ce500NonLinear.step alone (envs/nonlinear/env.py:182-256): action [3][stride] normalised commands (double),
- * x_full [12][stride], x_act [3][stride] in/out; out_mdp [4][stride], out_reward, out_e_theta [stride]. */
+ * x_full [12][stride], x_act [3][stride] in/out; out_mdp [4][stride], out_reward (longitudinal), out_e_theta [stride];
+ * out_surf [3][stride] = info['action_commanded'] (surface positions after saturation), out_eff [3][stride] =
+ * info['action_effective'] (model_input[:3]); either may be NULL. */
 int rl4_nl_env_step(const rl4_nl_params* p, const double* theta_ref, int32_t stepp, double* x_full, double* x_act,
-                    const double* action, double* out_mdp, double* out_reward, double* out_e_theta,
-                    int64_t stride, int64_t n_agents, void* stream);
+                    const double* action, double* out_mdp, double* out_reward, double* out_e_theta, double* out_surf,
+                    double* out_eff, int64_t stride, int64_t n_agents, void* stream);
 
 /* ---- host-buffer episode (what a reference user calls: IDHPsp(...).train() for a batch) ----
  * Copies x0 / weights from host memory, runs rl4_sp_init + rl4_sp_run for n_steps on the GPU

@@ -111,6 +111,42 @@ def rls3_fixture(gamma, seed, steps=400, reset_at=250):
                 theta=np.array(th), cov=np.array(cv), eps=np.array(ep), eps_norm=np.array(en))
 
 
+def nl_env_fixture(fault, seed, steps=700, fault_time=3.0, integrator="ode5"):
+    """VERBATIM Ce500NonLinear wrapper (envs/nonlinear/env.py:11-319) around the surrogate plant: reset + `steps` steps
+    with smooth random three-surface commands; everything the wrapper returns is recorded."""
+    from oracle import nl_c
+    Env, stub = ref_loader.load_reference_nonlinear_env(integrator)
+    th = nl_c.theta_reference()
+    trim_input = np.array([-0.02855, 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.55, 0.55, 0])
+    trim_state = np.array([0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0])
+    env_config = {"state_dim": 4, "action_dim": 3, "trim_input": trim_input, "trim_state": trim_state, "dt": 0.01,
+                  "t_end": 90, "total_steps": 9000, "fault_time": fault_time, "fault_scenario": fault,
+                  "reference": {"tracked_state": ["phi", "theta", "psi"], "signal": [0 * th, th, 0 * th]}}
+    env = Env(env_config)
+    env._set_weight_matrices([1, 2, 1])                    # objects.py:1029 with idhp_nonlin.py's kappa
+    s0, r0, _, _, info0 = env.reset()
+    rng = np.random.default_rng(seed)
+    t = np.arange(steps) * 0.01
+    acts = np.stack([0.5 * np.sin(2 * np.pi * t / 3.1 + rng.uniform(0, 6)) + 0.2 * rng.standard_normal(steps),
+                     0.15 * np.sin(2 * np.pi * t / 2.3 + rng.uniform(0, 6)) + 0.05 * rng.standard_normal(steps),
+                     0.10 * np.sin(2 * np.pi * t / 4.7 + rng.uniform(0, 6)) + 0.05 * rng.standard_normal(steps)], axis=1)
+    acts = np.clip(acts, -1, 1)
+    out = {k: [] for k in ("x_full", "s", "reward", "e", "RSE", "a_cmd", "a_eff", "rg_lon", "rg_lat", "x_lon", "x_lat", "nans", "t")}
+    for k in range(steps):
+        s, r, term, trunc, info = env.step(acts[k].copy())
+        assert term is None and trunc is False
+        out["x_full"].append(np.array(info["x_full"])); out["s"].append(np.array(s)); out["reward"].append(np.array(r).reshape(2))
+        out["e"].append(np.array(info["e"])); out["RSE"].append(np.array(info["RSE"], dtype=np.float64))
+        out["a_cmd"].append(np.array(info["action_commanded"])); out["a_eff"].append(np.array(info["action_effective"]))
+        out["rg_lon"].append(np.array(info["reward_grad"][0]).ravel()); out["rg_lat"].append(np.array(info["reward_grad"][1]).ravel())
+        out["x_lon"].append(info["x"][0].ravel()); out["x_lat"].append(info["x"][1].ravel())
+        out["nans"].append(bool(info["nans"])); out["t"].append(info["t"])
+    res = {k: np.array(v) for k, v in out.items()}
+    res.update(actions=acts, fault=str(fault), fault_time=fault_time, integrator=integrator, x_reset=np.array(info0["x_full"]),
+               theta_ref=th[:steps], kappa=np.array([1, 2, 1]))
+    return res
+
+
 def utils_fixture():
     """Outputs of the verbatim utils.py functions (samplers with true_random=False, PSD, convergence time, VD_A, KL)."""
     U = ref_loader.load_reference_utils()
@@ -149,6 +185,9 @@ def main():
     np.savez_compressed(os.path.join(OUT, "utils_functions.npz"), **utils_fixture())
     np.savez_compressed(os.path.join(OUT, "nl_rls_g1.npz"), **rls3_fixture(1, 17))
     np.savez_compressed(os.path.join(OUT, "nl_rls_g0998.npz"), **rls3_fixture(0.998, 18))
+    for i, (f, integ) in enumerate([("none", "ode5"), ("damp_elevator_and_saturate_elevator", "ode5"), ("shift_cg", "rk4"),
+                                    ("slow_all", "ode5"), ("damp_all", "ode5"), ("saturate_aileron", "rk4")]):
+        np.savez_compressed(os.path.join(OUT, f"nl_env_{f}.npz"), **nl_env_fixture(f, 200 + i, integrator=integ))
     if "--only-utils" in sys.argv:
         return
     for i, f in enumerate([None, "invert_elevator", "damp_elevator", "shift_cg"]):

@@ -163,3 +163,16 @@ def rls_update(gamma, theta, cov, dx0, da0, dx1):
     eps, en = np.zeros((n, 3)), np.zeros(n)
     L.orc_nl_rls_update(float(gamma), _ptr(theta), _ptr(cov), _ptr(dx0), _ptr(da0), _ptr(dx1), _ptr(eps), _ptr(en), n)
     return eps, en
+
+
+def env_step(cfg, theta_ref_k, act, x_full, x_act, stepp):
+    """One Ce500NonLinear.step without the agent (envs/nonlinear/env.py:182-256) for ONE aircraft; x_full (12,) and
+    x_act (3,) are updated in place.  Returns dict(surf, u, e, reward)."""
+    L = lib()
+    L.orc_nl_env_step.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                  ctypes.c_int32] + [ctypes.c_void_p] * 4
+    act = np.ascontiguousarray(act, dtype=np.float64)
+    surf, u, e, r = np.zeros(3), np.zeros(11), np.zeros(3), np.zeros(1)
+    L.orc_nl_env_step(_ptr(cfg), float(theta_ref_k), _ptr(act), _ptr(x_full), _ptr(x_act), int(stepp), _ptr(surf), _ptr(u),
+                      _ptr(e), _ptr(r))
+    return dict(surf=surf, u=u, e=e, reward=float(r[0]))

@@ -43,6 +43,69 @@ void orc_nl_rls_update(double gamma, double* theta, double* cov, const double* d
     }
 }
 
+/* Ce500NonLinear.step without the agent (envs/nonlinear/env.py:182-256): action scaling (:111-124), rate-limited
+ * actuators (:161-180), saturation faults (:150-159), damping / c.g. / slow-actuator faults (:127-148), plant step (:210),
+ * errors and the longitudinal reward (:215-220).  stepp is the env's counter BEFORE the step. */
+typedef struct { double surf[3], u[11], e[3], reward, rg2; } orc_nl_envout;
+static void orc_nl_env_core(const orc_nl_cfg* c, double theta_ref_k, const double* act, double* x_full, double* x_act,
+                            int32_t stepp, orc_nl_envout* o)
+{
+    const double dt = c->dt;
+    const int faulted = (c->fault_step >= 0 && stepp >= c->fault_step);           /* env.py:132,151 */
+    double cmd[3];
+    for (int i = 0; i < 3; ++i) {                                                 /* _scale_action env.py:111-124 */
+        const double hi = c->limit_deg[i], lo = -c->limit_deg[i];
+        double v = act[i] * (hi - lo) / 2.0;
+        v = v + (hi + lo) / 2.0;
+        cmd[i] = v * (M_PI / 180.0);
+    }
+    const double omega = (faulted && c->fault_damp == ORC_NL_SLOW_ALL && stepp > c->fault_step) ? c->omega_slow
+                         : c->omega0;   /* slow_all takes effect from the step AFTER it is first engaged (env.py:145 runs after :205) */
+    for (int i = 0; i < 3; ++i) {                                                 /* _propagate_surfaces_states env.py:161-180 */
+        double d = cmd[i] - x_act[i];
+        d = d * omega;
+        d = d < -c->rate_limit ? -c->rate_limit : (d > c->rate_limit ? c->rate_limit : d);
+        x_act[i] = x_act[i] + dt * d;
+        o->surf[i] = x_act[i];
+    }
+    if (faulted && c->fault_sat != ORC_NL_SAT_NONE) {                             /* _saturate_surfaces env.py:150-159 */
+        const int j = c->fault_sat - 1;
+        const double L = c->sat_limit[j];
+        o->surf[j] = o->surf[j] < -L ? -L : (o->surf[j] > L ? L : o->surf[j]);
+    }
+    double eff[11] = {0};
+    for (int i = 0; i < 3; ++i) eff[i] = o->surf[i];
+    if (faulted) {                                                                /* _engage_fault env.py:129-148 */
+        switch (c->fault_damp) {
+        case ORC_NL_DAMP_ELEVATOR: eff[0] *= c->damp_factor; break;
+        case ORC_NL_DAMP_AILERON:  eff[1] *= c->damp_factor; break;
+        case ORC_NL_DAMP_RUDDER:   eff[2] *= c->damp_factor; break;
+        case ORC_NL_DAMP_ALL:      for (int i = 0; i < 3; ++i) eff[i] *= c->damp_factor; break;
+        case ORC_NL_SHIFT_CG:      eff[10] = c->cg_shift; break;
+        default: break;
+        }
+    }
+    for (int i = 0; i < 11; ++i) o->u[i] = c->trim_input[i] + eff[i];             /* env.py:207-208 */
+    if (c->integrator == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(&c->plant, x_full, o->u, dt);
+    else rl4_cit_step_ode5(&c->plant, x_full, o->u, dt);                           /* env.py:210 */
+    o->e[0] = x_full[6] - 0.0; o->e[1] = x_full[7] - theta_ref_k; o->e[2] = x_full[8] - 0.0;   /* env.py:215 (state - ref) */
+    o->reward = (-0.5 * c->Q_sym) * (o->e[1] * o->e[1]);                           /* env.py:218 */
+    o->rg2 = (-c->Q_sym) * o->e[1];
+}
+
+/* test exports: one env step / one bare plant step / the plant's built-in initial state */
+void orc_nl_env_step(const orc_nl_cfg* c, double theta_ref_k, const double* act, double* x_full, double* x_act, int32_t stepp,
+                     double* surf, double* u, double* e, double* reward)
+{
+    orc_nl_envout o;
+    orc_nl_env_core(c, theta_ref_k, act, x_full, x_act, stepp, &o);
+    memcpy(surf, o.surf, sizeof o.surf); memcpy(u, o.u, sizeof o.u); memcpy(e, o.e, sizeof o.e); *reward = o.reward;
+}
+void orc_cit_plant_step(const rl4_cit_params* P, double* x, const double* u, double dt, int integrator)
+{
+    if (integrator == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(P, x, u, dt); else rl4_cit_step_ode5(P, x, u, dt);
+}
+
 #define TE double
 
 #define TN float

@@ -10,6 +10,10 @@ of which are installed.  Two pieces are pure numpy and run unmodified:
 * ``RLS`` (``objects.py:439-549``) -- the ``ClassDef`` node is extracted with ``ast``
   and exec'd with ``{'np': numpy}``.
 
+* ``Ce500NonLinear`` (``envs/nonlinear/env.py:11-319``), the WRAPPER only -- imported from the file where it lies with a
+  stand-in for its ``extended_input.citation`` module (the reference's plant is a source-less Windows binary): the
+  stand-in's ``initialize / step / terminate`` drive the documented surrogate plant through the C oracle, so the
+  verbatim action scaling, actuator, fault, reward and MDP-state code runs unmodified around it.
 * ``utils.py`` (samplers, ``get_PSD``, ``get_convergence_time``, ``VD_A``, ``kl_divergence``) -- imported from the
   file where it lies with the matplotlib stub (scipy is installed).
 
@@ -98,3 +102,52 @@ def load_reference_utils():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod
+
+
+def load_reference_nonlinear_env(integrator: str = "ode5"):
+    """Return (verbatim ``Ce500NonLinear`` class, plant stand-in module).  envs/nonlinear/env.py:5-9 imports
+    ``extended_input.citation`` -- a SWIG wrapper of a Windows DLL -- so a stand-in module with the same three functions
+    (envs/nonlinear/citation.py:62-69: ``initialize()``, ``step(cmd) -> state[12]``, ``terminate()``; process-global
+    state like the original) is registered first; it integrates the surrogate plant of
+    include/rl4_citation_surrogate.h with the C oracle."""
+    if not reference_available():
+        raise FileNotFoundError(f"reference tree not found at {REFERENCE_ROOT}")
+    _install_stubs()
+    import ctypes
+    import importlib.util
+
+    import numpy as np
+
+    from . import nl_c
+
+    L = nl_c.lib()
+    L.orc_cit_plant_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_int]
+    plant = np.ascontiguousarray(nl_c.make_cfg()["plant"][:1])
+    stub = types.ModuleType("extended_input.citation")
+    stub._x = None
+    stub._integrator = nl_c.INTEGRATOR[integrator]
+    stub.dt = 0.01
+
+    def initialize():
+        stub._x = np.array([0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0], dtype=np.float64)   # built-in initial state
+
+    def step(cmd):
+        u = np.ascontiguousarray(cmd, dtype=np.float64)
+        assert u.shape == (11,)
+        L.orc_cit_plant_step(plant.ctypes.data, stub._x.ctypes.data, u.ctypes.data, stub.dt, stub._integrator)
+        return stub._x.copy()
+
+    def terminate():
+        stub._x = None
+
+    stub.initialize, stub.step, stub.terminate = initialize, step, terminate
+    pkg = types.ModuleType("extended_input")
+    pkg.citation = stub
+    pkg.__path__ = []
+    sys.modules["extended_input"] = pkg
+    sys.modules["extended_input.citation"] = stub
+    path = os.path.join(REFERENCE_ROOT, "envs", "nonlinear", "env.py")
+    spec = importlib.util.spec_from_file_location("_rl4afcs_ref_nonlinear_env", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.Ce500NonLinear, stub

@@ -159,7 +159,7 @@ def load() -> ctypes.CDLL:
     L.rl4_test_math.argtypes = [ctypes.c_int, vp, vp, vp, i64, vp]
     L.rl4_nl_init.argtypes = [ctypes.c_int, ctypes.POINTER(NlParams), vp, vp, vp, vp, i64, NlState, i64, vp]
     L.rl4_nl_run.argtypes = [ctypes.c_int, ctypes.POINTER(NlParams), vp, vp, i64, i32, i32, NlState, i64, SpLog, vp]
-    L.rl4_nl_env_step.argtypes = [ctypes.POINTER(NlParams), vp, i32, vp, vp, vp, vp, vp, vp, i64, i64, vp]
+    L.rl4_nl_env_step.argtypes = [ctypes.POINTER(NlParams), vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]
     L.rl4_nl_default_params.argtypes = [ctypes.POINTER(NlParams)]
     L.rl4_nl_rls_update.argtypes = [ctypes.POINTER(NlParams), vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]
     L.rl4_nl_critic_forward.argtypes = [ctypes.c_int, vp, vp, vp, vp, i64, i64, vp]

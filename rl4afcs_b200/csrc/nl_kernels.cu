@@ -172,7 +172,7 @@ __device__ __forceinline__ void nl_rls_update(TH& th, CV& cv, const double (&Xr)
 template <bool PER_AGENT, int INTEG>
 __device__ __forceinline__ void nl_env_step(const rl4_nl_params& p, const NlHp<PER_AGENT>& hv, int stepp, double theta_ref_k,
                                             const double (&act)[3], double (&x)[12], double (&x_act)[3], double (&surf)[3],
-                                            double& e_phi, double& e_th, double& e_psi, double& reward, double& rg2, double& u0)
+                                            double& e_phi, double& e_th, double& e_psi, double& reward, double& rg2, double (&ueff)[3])
 {
     const int fault_step = hv.hpi(RL4_NHPI_FAULT_STEP);
     const bool faulted = (fault_step >= 0 && stepp >= fault_step);                 // env.py:132,151
@@ -210,7 +210,7 @@ __device__ __forceinline__ void nl_env_step(const rl4_nl_params& p, const NlHp<P
     double u[11];
 #pragma unroll
     for (int i = 0; i < 11; ++i) u[i] = p.trim_input[i] + eff[i];                  // env.py:207-208
-    u0 = u[0];
+    ueff[0] = u[0]; ueff[1] = u[1]; ueff[2] = u[2];
     if (INTEG == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(&p.plant, x, u, p.dt);   // compile-time: one integrator's code per kernel
     else rl4_cit_step_ode5(&p.plant, x, u, p.dt);                                  // env.py:210
     const double Q = hv.hp(RL4_NHP_Q_SYM);
@@ -291,9 +291,9 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
         const TN a_k = a;
         // ---- env.step(self._get_action(a))  (objects.py:1497, 1448-1455)
         const double act[3] = {(double)a_k, 0.0, 0.0};
-        double surf[3], e_phi, e_th, e_psi, reward, rg2, u0;
+        double surf[3], ueff[3], e_phi, e_th, e_psi, reward, rg2;
         const double yref_k = __ldg(theta_ref + k);
-        nl_env_step<PER_AGENT, INTEG>(p, hv, stepp, yref_k, act, x, x_act, surf, e_phi, e_th, e_psi, reward, rg2, u0);
+        nl_env_step<PER_AGENT, INTEG>(p, hv, stepp, yref_k, act, x, x_act, surf, e_phi, e_th, e_psi, reward, rg2, ueff);
         stepp += 1;
         const double x_next_lon[3] = {x[4], x[7], x[1]};                           // env.py:231
         bool nans = false;
@@ -498,7 +498,7 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
                 } else if (lg.level >= 3) {                                        // functions.py:1040-1052
                     b[(int64_t)RL4_NLM_E * L] = e_th; b[(int64_t)RL4_NLM_THETA * L] = x[7]; b[(int64_t)RL4_NLM_ALPHA * L] = x[4];
                     b[(int64_t)RL4_NLM_Q * L] = x[1]; b[(int64_t)RL4_NLM_V * L] = x[3]; b[(int64_t)RL4_NLM_H * L] = x[9];
-                    b[(int64_t)RL4_NLM_A_CMD * L] = surf[0]; b[(int64_t)RL4_NLM_A_EFF * L] = u0;
+                    b[(int64_t)RL4_NLM_A_CMD * L] = surf[0]; b[(int64_t)RL4_NLM_A_EFF * L] = ueff[0];
                     double na = 0.0, nc = 0.0;
                     for (int j = 0; j < 40; ++j) { na = __fma_rn((double)W1a[j], (double)W1a[j], na); nc = __fma_rn((double)W1c[j], (double)W1c[j], nc); }
                     b[(int64_t)RL4_NLM_WA_NORM * L] = nsqrt(na); b[(int64_t)RL4_NLM_WC_NORM * L] = nsqrt(nc);
@@ -508,7 +508,7 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
                     for (int j = 0; j < 12; ++j) b[(int64_t)(RL4_NLF_XFULL + j) * L] = x[j];
                     b[(int64_t)RL4_NLF_RSE * L] = rse_k0; b[(int64_t)(RL4_NLF_RSE + 1) * L] = rse_k1;
                     for (int j = 0; j < 3; ++j) b[(int64_t)(RL4_NLF_X + j) * L] = x_next_lon[j];
-                    b[(int64_t)RL4_NLF_A_CMD * L] = surf[0]; b[(int64_t)RL4_NLF_A_EFF * L] = u0;
+                    b[(int64_t)RL4_NLF_A_CMD * L] = surf[0]; b[(int64_t)RL4_NLF_A_EFF * L] = ueff[0];
                     b[(int64_t)RL4_NLF_S * L] = x[4]; b[(int64_t)RL4_NLF_YREF * L] = yref_k; b[(int64_t)RL4_NLF_E * L] = e_th;
                     for (int j = 0; j < 40; ++j) { b[(int64_t)(RL4_NLF_A_W1 + j) * L] = (double)W1a[j]; b[(int64_t)(RL4_NLF_C_W1 + j) * L] = (double)W1c[j]; }
                     for (int j = 0; j < 10; ++j) b[(int64_t)(RL4_NLF_A_W2 + j) * L] = (double)W2a[j];
@@ -601,22 +601,25 @@ nl_init_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict
 __global__ void __launch_bounds__(128)
 nl_env_step_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict__ theta_ref, int stepp, double* __restrict__ x_full,
                    double* __restrict__ x_act_p, const double* __restrict__ action, double* __restrict__ out_mdp,
-                   double* __restrict__ out_reward, double* __restrict__ out_e, int64_t S, int64_t n_agents)
+                   double* __restrict__ out_reward, double* __restrict__ out_e, double* __restrict__ out_surf,
+                   double* __restrict__ out_eff, int64_t S, int64_t n_agents)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_agents) return;
     const NlHp<true> hv{p, i};
-    double x[12], xa[3], act[3], surf[3], e_phi, e_th, e_psi, reward, rg2, u0;
+    double x[12], xa[3], act[3], surf[3], ueff[3], e_phi, e_th, e_psi, reward, rg2;
     for (int j = 0; j < 12; ++j) x[j] = x_full[j * S + i];
     for (int j = 0; j < 3; ++j) { xa[j] = x_act_p[j * S + i]; act[j] = action[j * S + i]; }
     if (p.integrator == RL4_CIT_INTEGRATOR_RK4)
-        nl_env_step<true, RL4_CIT_INTEGRATOR_RK4>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2, u0);
+        nl_env_step<true, RL4_CIT_INTEGRATOR_RK4>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2, ueff);
     else
-        nl_env_step<true, RL4_CIT_INTEGRATOR_ODE5>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2, u0);
+        nl_env_step<true, RL4_CIT_INTEGRATOR_ODE5>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2, ueff);
     for (int j = 0; j < 12; ++j) x_full[j * S + i] = x[j];
     for (int j = 0; j < 3; ++j) x_act_p[j * S + i] = xa[j];
     out_mdp[i] = x[4]; out_mdp[S + i] = x[7]; out_mdp[2 * S + i] = x[1]; out_mdp[3 * S + i] = e_th;
     out_reward[i] = reward; out_e[i] = e_th;
+    if (out_surf) for (int j = 0; j < 3; ++j) out_surf[j * S + i] = surf[j];          // action_commanded (env.py:244)
+    if (out_eff) for (int j = 0; j < 3; ++j) out_eff[j * S + i] = ueff[j];            // action_effective = model_input[:3] (:245)
 }
 
 // RLS.update (objects.py:492-543) for n = 3, m = 1: step-API form, planes of double
@@ -819,14 +822,14 @@ int rl4_nl_actor_forward(int policy, const void* s, void* w1, void* w2, double* 
 }
 
 int rl4_nl_env_step(const rl4_nl_params* p, const double* theta_ref, int32_t stepp, double* x_full, double* x_act,
-                    const double* action, double* out_mdp, double* out_reward, double* out_e_theta, int64_t stride,
-                    int64_t n, void* stream)
+                    const double* action, double* out_mdp, double* out_reward, double* out_e_theta, double* out_surf,
+                    double* out_eff, int64_t stride, int64_t n, void* stream)
 {
     RL4_REQUIRE(p && theta_ref && x_full && x_act && action && out_mdp && out_reward && out_e_theta, "NULL argument");
     RL4_REQUIRE(n >= 0 && stride >= n && stepp >= 0, "bad size");
     if (n == 0) return 0;
     nl_env_step_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*p, theta_ref, stepp, x_full, x_act, action,
-                                                                                        out_mdp, out_reward, out_e_theta, stride, n);
+                                                                                        out_mdp, out_reward, out_e_theta, out_surf, out_eff, stride, n);
     return check_launch("nl_env_step_kernel");
 }
 

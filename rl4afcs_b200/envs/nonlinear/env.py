@@ -111,34 +111,45 @@ class Ce500NonLinear:
         return MDP_state, torch.zeros((self.batch, 2, 1, 1), dtype=torch.float64, device=self.device), None, None, info
 
     def step(self, action):
-        """action: normalised surface commands in [-1, 1], shape (B, 3) (or (3,) broadcast)."""
+        """action: normalised surface commands in [-1, 1], shape (B, 3) (or (3,) broadcast).  Returns the reference's
+        tuple (envs/nonlinear/env.py:182-256): MDP_state (B,4), reward (B,2,1,1) = [longitudinal, lateral], None, False,
+        info."""
         eng = self._engine
         act = torch.as_tensor(action, device=self.device, dtype=torch.float64)
         if act.ndim == 1:
             act = act.reshape(1, 3).expand(self.batch, 3)
         act_p = act.t().contiguous()
-        mdp = torch.empty((4, self.batch), dtype=torch.float64, device=self.device)
-        reward = torch.empty(self.batch, dtype=torch.float64, device=self.device)
-        e_th = torch.empty_like(reward)
-        with torch.cuda.device(self.device):
+        B, dev = self.batch, self.device
+        mdp = torch.empty((4, B), dtype=torch.float64, device=dev)
+        reward_lon = torch.empty(B, dtype=torch.float64, device=dev)
+        e_th = torch.empty_like(reward_lon)
+        surf = torch.empty((3, B), dtype=torch.float64, device=dev)
+        eff = torch.empty((3, B), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
             rc = eng.lib.rl4_nl_env_step(ctypes.byref(eng.params), eng.theta_ref.data_ptr(), self.stepp,
                                          eng.env_field("XFULL", 12).data_ptr(), eng.env_field("XACT", 3).data_ptr(),
-                                         act_p.data_ptr(), mdp.data_ptr(), reward.data_ptr(), e_th.data_ptr(),
-                                         eng.stride, self.batch, eng._stream())
+                                         act_p.data_ptr(), mdp.data_ptr(), reward_lon.data_ptr(), e_th.data_ptr(),
+                                         surf.data_ptr(), eff.data_ptr(), eng.stride, B, eng._stream())
             _lib.check(rc, "rl4_nl_env_step")
         ref = [r[self.stepp] for r in self.state_reference]
         self.stepp += 1
         self.t += self.dt
         st = self.state
-        err = torch.stack([st[:, 6] - ref[0], e_th, st[:, 8] - ref[2]], dim=1)
-        rg_lon = torch.zeros((self.batch, 1, 3), dtype=torch.float64, device=self.device)
+        err = torch.stack([st[:, 6] - ref[0], e_th, st[:, 8] - ref[2]], dim=1)                # env.py:215 (state - ref)
+        rg_lon = torch.zeros((B, 1, 3), dtype=torch.float64, device=dev)
         rg_lon[:, 0, 2] = -self.Q_sym * e_th                                            # env.py:219-220
+        k0, k2 = float(self.Q_asym[0, 0]), float(self.Q_asym[1, 1])
+        reward_lat = (-0.5 * err[:, 0]) * k0 * err[:, 0] + (-0.5 * err[:, 2]) * k2 * err[:, 2]   # env.py:224 (lateral MDP, unused by IDHPnonlin)
+        rg_lat = torch.zeros((B, 1, 4), dtype=torch.float64, device=dev)
+        rg_lat[:, 0, 2] = -(k0 * err[:, 0])                                             # env.py:225-226, 254
+        rg_lat[:, 0, 3] = -(k2 * err[:, 2])
         MDP_state = mdp.t()
+        reward = torch.stack([reward_lon, reward_lat], dim=1).reshape(B, 2, 1, 1)
         info = {"nans": bool(torch.isnan(st).any()), "s": MDP_state, "yref": ref,
-                "action_commanded": eng.env_field("XACT", 3).t(), "rates": st[:, 6:9], "t": self.t, "x_full": st,
+                "action_commanded": surf.t(), "action_effective": eff.t(), "rates": st[:, 6:9], "t": self.t, "x_full": st,
                 "x": [st[:, [4, 7, 1]].unsqueeze(-1), st[:, [6, 5, 0, 2]].unsqueeze(-1)], "e": err,
                 "RSE": [torch.sqrt(e_th * e_th), torch.sqrt(err[:, 0] ** 2 + err[:, 2] ** 2)],
-                "reward_grad": [rg_lon, None]}
+                "reward_grad": [rg_lon, rg_lat]}
         return MDP_state, reward, None, False, info
 
     def render(self, mode="human"):

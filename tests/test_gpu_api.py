@@ -194,7 +194,7 @@ def test_nonlinear_env_and_agent_api(oracle):
     assert s.shape == (B, 4) and float(s.abs().max()) == 0.0 and info["x_full"].shape == (B, 12)
     assert abs(float(info["x_full"][0, 3]) - 90.0) < 1e-9 and abs(float(info["x_full"][0, 7]) - 0.0576) < 1e-9
     s, r, _, trunc, info = env.step(np.array([0.1, 0.0, 0.0]))
-    assert s.shape == (B, 4) and r.shape == (B,) and trunc is False and set(info) >= {"nans", "s", "x_full", "x", "e", "RSE", "reward_grad"}
+    assert s.shape == (B, 4) and r.shape == (B, 2, 1, 1) and trunc is False and set(info) >= {"nans", "s", "x_full", "x", "e", "RSE", "reward_grad"}
     assert float(info["action_commanded"][0, 0]) > 0.0           # actuator moved towards +1.5 deg
 
     w = nl_c.init_weights(B, 8)
@@ -348,3 +348,32 @@ def test_rls3_update_equals_verbatim_reference(path):
         assert np.array_equal(m.eps_norm.cpu().numpy(), np.full(B, g["eps_norm"][k])), k
     th = g["theta"][-1].reshape(4, 3)
     assert np.array_equal(m.F.cpu().numpy()[0], th[:3].T) and np.array_equal(m.G.cpu().numpy()[0], th[3:].T)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "nl_env_*.npz"))))
+def test_nonlinear_env_equals_verbatim_reference_wrapper(path):
+    """Ce500NonLinear.reset / step on the GPU against the VERBATIM wrapper class run around the same surrogate plant
+    (tests/golden/nl_env_*.npz): every returned quantity over 700 steps, six fault scenarios, both integrators."""
+    from rl4afcs_b200.envs.nonlinear.env import Ce500NonLinear
+
+    g = np.load(path)
+    B = 3
+    th_full = np.zeros(9000); th_full[: len(g["theta_ref"])] = g["theta_ref"]
+    env = Ce500NonLinear(_nl_env_config(th_full, fault_scenario=str(g["fault"]), fault_time=float(g["fault_time"])), batch=B,
+                         dtype="mixed", integrator=str(g["integrator"]))
+    env._set_weight_matrices([int(k) for k in g["kappa"]])
+    s, r, term, trunc, info = env.reset()
+    assert np.array_equal(info["x_full"].cpu().numpy(), np.broadcast_to(g["x_reset"], (B, 12)))
+    ulp = lambda a, b, n=2: bool(np.all(np.abs(a - b) <= n * np.spacing(np.maximum(np.abs(a), np.abs(b)))))   # noqa: E731
+    for k in range(len(g["actions"])):
+        s, r, term, trunc, info = env.step(g["actions"][k])
+        same = lambda t, want: np.array_equal(t.cpu().numpy(), np.broadcast_to(want, (B,) + np.shape(want)))   # noqa: E731
+        assert same(info["x_full"], g["x_full"][k]) and same(s, g["s"][k]) and same(info["e"], g["e"][k]), k
+        assert same(info["action_commanded"], g["a_cmd"][k]) and same(info["action_effective"], g["a_eff"][k]), k
+        assert same(info["x"][0][:, :, 0], g["x_lon"][k]) and same(info["x"][1][:, :, 0], g["x_lat"][k]), k
+        assert same(info["reward_grad"][0][:, 0], g["rg_lon"][k]), k
+        assert np.allclose(info["reward_grad"][1][:, 0].cpu().numpy(), g["rg_lat"][k], rtol=0, atol=0), k
+        rr = r.cpu().numpy().reshape(B, 2)
+        assert ulp(rr[:, 0], g["reward"][k, 0]) and ulp(rr[:, 1], g["reward"][k, 1], 4), k
+        assert ulp(info["RSE"][0].cpu().numpy(), g["RSE"][k, 0]) and ulp(info["RSE"][1].cpu().numpy(), g["RSE"][k, 1], 4), k
+        assert info["nans"] == bool(g["nans"][k]) and abs(info["t"] - g["t"][k]) < 1e-12
