@@ -71,23 +71,34 @@ def rls_fixture(gamma, seed, steps=400, reset_at=250):
 
 
 def loop_fixture(name, *, x0, seed, fault=None, elig=(None, None), ms=2, steps=1100, tanh="t13"):
+    """The VERBATIM agent: objects.py's IDHPsp / Actor / Critic / RLS classes (executed on the TensorFlow stand-in of
+    oracle/tf_shim.py) driving the verbatim Ce500ShortPeriod; only the initial weights are injected."""
     Env = ref_loader.load_reference_linear_env()
-    RLS = ref_loader.load_reference_rls()
+    O, tf = ref_loader.load_reference_objects()
     base, amp = sp_c.default_reference()
     ic = sp_c.default_idhp_config()
     ic["multistep"] = ms
     ic["actor_config"]["elig"], ic["critic_config"]["elig"] = elig
+    t_end = steps * 0.02
+    assert int(t_end / 0.02) == steps
     env = Env({"state_dim": 2, "action_dim": 1, "x0": np.array(x0, dtype=float).reshape(2, 1), "dt": 0.02,
-               "t_end": 60, "fault_time": 20, "fault_scenario": fault,
+               "t_end": t_end, "fault_time": 20, "fault_scenario": fault,
                "reference": {"tracked_state": ["alpha"], "signal": [amp * base]}})
     w = sp_c.init_weights(1, seed)
-    fn = (lambda a: sp_c.tanh_t13(np.asarray(a))) if tanh == "t13" else np.tanh
-    loop = sp_numpy.IDHPspLoop(env, ic, {k: v[0] for k, v in w.items()}, tanh_fn=fn, rls=RLS(ic["rls_config"]))
-    lg = loop.train(steps)
+    tf.set_tanh((lambda a: sp_c.tanh_t13(np.asarray(a, dtype=np.float32))) if tanh == "t13" else (lambda a: np.tanh(a)))
+    idhp = O.IDHPsp(env, ic, verbose=False, seed=seed)
+    idhp.actor.set_weights([w["W1a"][0].reshape(1, 4), w["W2a"][0].reshape(4, 1)])
+    idhp.critic.set_weights([w["W1c"][0].reshape(1, 4), w["W2c"][0].reshape(4, 2)])
+    idhp.train()
+    tf.set_tanh(None)
     out = dict(x0=np.array(x0, dtype=float), seed=seed, fault=str(fault), elig_a=str(elig[0]), elig_c=str(elig[1]),
                multistep=ms, steps=steps, tanh=tanh, **{f"w_{k}": v[0] for k, v in w.items()})
-    for k in ("x", "a", "c", "ref", "a_w1", "a_w2", "c_w1", "c_w2", "params", "cov", "eps_norm"):
-        out[k] = lg[k]
+    f64 = lambda v, w_: np.asarray(v, dtype=np.float64).reshape(steps, w_) if w_ else np.asarray(v, dtype=np.float64).reshape(steps)   # noqa: E731
+    out.update(x=f64(idhp.x_hist, 2), a=f64(idhp.a_hist, 0), c=f64(idhp.c_hist, 0), ref=f64(idhp.ref_hist, 0),
+               a_w1=f64(idhp.a_weights_hist1, 4), a_w2=f64(idhp.a_weights_hist2, 4), c_w1=f64(idhp.c_weights_hist1, 4),
+               c_w2=f64(idhp.c_weights_hist2, 8), params=f64(idhp.params_hist, 6), cov=f64(idhp.cov_hist, 9),
+               eps_norm=f64(idhp.eps_norm_hist, 0), a_e=f64(idhp.a_e_hist, 8), c_e=f64(idhp.c_e_hist, 24),
+               a_all_grad=f64(idhp.a_all_grad_hist, 8), c_all_grad=f64(idhp.c_all_grad_hist, 12))
     return out
 
 

@@ -49,6 +49,22 @@ def _install_stubs() -> None:
         gym.spaces = spaces
         sys.modules["gymnasium"] = gym
         sys.modules["gymnasium.spaces"] = spaces
+    if "tqdm" not in sys.modules or not getattr(sys.modules["tqdm"], "_rl4_stub", False):
+        tq = types.ModuleType("tqdm")
+
+        class tqdm:  # silent stand-in: iterable with set_description
+            def __init__(self, it=None, **kw):
+                self._it = it
+
+            def __iter__(self):
+                return iter(self._it)
+
+            def set_description(self, *a, **k):
+                pass
+
+        tq.tqdm = tqdm
+        tq._rl4_stub = True
+        sys.modules["tqdm"] = tq
     if "matplotlib" not in sys.modules:
         mpl = types.ModuleType("matplotlib")
         plt = types.ModuleType("matplotlib.pyplot")
@@ -151,3 +167,25 @@ def load_reference_nonlinear_env(integrator: str = "ode5"):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod.Ce500NonLinear, stub
+
+
+def load_reference_objects():
+    """Return the verbatim ``objects`` module (objects.py: Network, Critic, Actor, Critic_big, Actor_big, RLS, IDHPsp,
+    IDHPnonlin) executed on the TensorFlow stand-in of oracle/tf_shim.py (TensorFlow itself cannot be installed here).
+    The stand-in supplies only the arithmetic of the TF ops (DESIGN.md section 3 contract); every line of control flow,
+    call order, aliasing and numpy-side arithmetic is the reference's own."""
+    if not reference_available():
+        raise FileNotFoundError(f"reference tree not found at {REFERENCE_ROOT}")
+    _install_stubs()
+    import importlib.util
+
+    from . import tf_shim
+
+    tf_shim.install()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)              # objects.py does `from utils import *`
+    path = os.path.join(REFERENCE_ROOT, "objects.py")
+    spec = importlib.util.spec_from_file_location("_rl4afcs_ref_objects", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, tf_shim

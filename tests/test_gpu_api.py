@@ -131,8 +131,8 @@ def test_actor_critic_calls_equal_oracle(oracle, policy, elig):
 
 @pytest.mark.parametrize("name", ["default_x0zero", "default_x0rand", "shiftcg_acc_1step", "invert_replacing"])
 def test_idhpsp_train_equals_reference_run(oracle, name):
-    """IDHPsp(env, config).train() (BASELINE.json configs[0]: one agent, idhp_sp.py defaults) against the
-    golden loop that ran on the verbatim reference env + RLS."""
+    """IDHPsp(env, config).train() (BASELINE.json configs[0]: one agent, idhp_sp.py defaults) against golden runs of the
+    VERBATIM reference agent (objects.py's IDHPsp on the TensorFlow stand-in, verbatim env + RLS; oracle/make_golden.py)."""
     from rl4afcs_b200.envs.linear.env import Ce500ShortPeriod
     from rl4afcs_b200.objects import IDHPsp
 
@@ -155,6 +155,9 @@ def test_idhpsp_train_equals_reference_run(oracle, name):
         assert np.array_equal(idhp.a_weights_hist2[b].cpu().numpy(), g["a_w2"])
         assert np.array_equal(idhp.c_weights_hist1[b].cpu().numpy(), g["c_w1"])
         assert np.array_equal(idhp.c_weights_hist2[b].cpu().numpy(), g["c_w2"])
+        assert np.array_equal(idhp.a_e_hist[b].cpu().numpy(), g["a_e"]) and np.array_equal(idhp.c_e_hist[b].cpu().numpy(), g["c_e"])
+        assert np.array_equal(idhp.a_all_grad_hist[b].cpu().numpy(), g["a_all_grad"])
+        assert np.array_equal(idhp.c_all_grad_hist[b].cpu().numpy(), g["c_all_grad"])
         assert np.array_equal(idhp.params_hist[b, 2:].cpu().numpy(), g["params"][2:])
         assert np.array_equal(idhp.cov_hist[b, 2:].cpu().numpy(), g["cov"][2:])
         assert np.array_equal(idhp.eps_norm_hist[b, 2:].cpu().numpy(), g["eps_norm"][2:])

@@ -54,3 +54,49 @@ def test_c_oracle_equals_numpy_loop_on_verbatim_objects(oracle, seed, fault, eli
         assert np.array_equal(lg[k], cl[k], equal_nan=True), k
     for k in ("params", "cov", "eps_norm"):
         assert np.array_equal(lg[k][2:], cl[k][2:], equal_nan=True), k
+
+
+@pytest.mark.parametrize("seed,fault,elig,ms,tanh,steps", [
+    (31, None, (None, None), 2, "t13", 3000),                                   # full default episode: LR switch, RLS reset
+    (32, "damp_elevator", ("accumulating", None), 0, "libm", 1300),
+    (33, "invert_elevator", ("replacing", "accumulating"), 2, "t13", 1300),
+])
+def test_c_oracle_equals_verbatim_idhpsp_on_tf_standin(oracle, seed, fault, elig, ms, tanh, steps):
+    """The reference's OWN agent code -- objects.py's IDHPsp.train(), Actor / Critic call and trace code, RLS,
+    _adapt_check, _log -- executed unmodified on the TensorFlow stand-in (oracle/tf_shim.py supplies only the arithmetic
+    of the TF ops) around the verbatim Ce500ShortPeriod, against the C oracle: every logged quantity
+    bit for bit (the reward to 1 ulp: `e**2` is libm pow in the reference).  numpy >= 2 here, so Q7 is off."""
+    O, tf = ref_loader.load_reference_objects()
+    Env = ref_loader.load_reference_linear_env()
+    base, amp = oracle.default_reference()
+    ic = oracle.default_idhp_config(); ic["multistep"] = ms
+    ic["actor_config"]["elig"], ic["critic_config"]["elig"] = elig
+    rng = np.random.default_rng(seed)
+    x0 = np.deg2rad(rng.uniform(-2, 2, size=2))
+    fault_time = 8.0
+    env = Env({"state_dim": 2, "action_dim": 1, "x0": x0.reshape(2, 1).copy(), "dt": 0.02, "t_end": steps * 0.02,
+               "fault_time": fault_time, "fault_scenario": fault, "reference": {"tracked_state": ["alpha"], "signal": [amp * base]}})
+    assert int(env.t_end / env.dt) == steps
+    tf.set_tanh((lambda a: oracle.tanh_t13(np.asarray(a, dtype=np.float32))) if tanh == "t13" else None)
+    try:
+        idhp = O.IDHPsp(env, ic, verbose=False, seed=seed)                      # weights drawn by the stand-in's initializer
+        w = {"W1a": idhp.actor.get_weights()[0].reshape(1, 4).astype(np.float64), "W2a": idhp.actor.get_weights()[1].reshape(1, 4).astype(np.float64),
+             "W1c": idhp.critic.get_weights()[0].reshape(1, 4).astype(np.float64), "W2c": idhp.critic.get_weights()[1].reshape(1, 8).astype(np.float64)}
+        idhp.train()
+    finally:
+        tf.set_tanh(None)
+    cfg = oracle.make_cfg(ic, fault_time=fault_time, fault_scenario=fault, q7_numpy1=0)
+    st = oracle.init_states("mixed", cfg, x0.reshape(1, 2), w)
+    cl = oracle.run("mixed", cfg, base, st, 0, steps, tanh=tanh, n_log=1)[0]
+    ref = {"x": idhp.x_hist, "a": idhp.a_hist.reshape(-1), "ref": idhp.ref_hist, "a_w1": idhp.a_weights_hist1, "a_w2": idhp.a_weights_hist2,
+           "c_w1": idhp.c_weights_hist1, "c_w2": idhp.c_weights_hist2, "a_e": idhp.a_e_hist, "c_e": idhp.c_e_hist,
+           "a_all_grad": idhp.a_all_grad_hist, "c_all_grad": idhp.c_all_grad_hist}
+    for k, v in ref.items():
+        assert np.array_equal(np.asarray(v, dtype=np.float64).reshape(cl[k].shape), cl[k], equal_nan=True), k
+    for k, v in (("params", idhp.params_hist), ("cov", idhp.cov_hist), ("eps_norm", idhp.eps_norm_hist)):
+        assert np.array_equal(np.asarray(v, dtype=np.float64).reshape(cl[k].shape)[2:], cl[k][2:], equal_nan=True), k   # objects.py:704
+    c_ref = np.asarray(idhp.c_hist, dtype=np.float64)
+    assert np.all(np.abs(c_ref - cl["c"]) <= 2 * np.spacing(np.abs(c_ref)))      # pow(e, 2) vs e * e, then * kappa
+    # final object state == final oracle state
+    assert np.array_equal(idhp.model.params.ravel(), st["theta"][0]) and np.array_equal(idhp.model.Cov.ravel(), st["cov"][0])
+    assert np.array_equal(idhp.target_critic.get_weights()[1].ravel().astype(np.float64), st["W2t"][0])
