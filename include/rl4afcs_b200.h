@@ -237,7 +237,9 @@ enum rl4_nl_net_field {        /* net plane, TN */
     RL4_NLN_LR_A = 209, RL4_NLN_LR_C = 210,   /* optimizer learning rates */
     RL4_NLN_COUNT = 211
 };
-enum rl4_nl_int_field { RL4_NLI_COOLDOWN = 0, RL4_NLI_DIVERGED_STEP = 1, RL4_NLI_STEPP = 2, RL4_NLI_COUNT = 3 };
+enum rl4_nl_int_field { RL4_NLI_COOLDOWN = 0, RL4_NLI_DIVERGED_STEP = 1, RL4_NLI_STEPP = 2,
+                        RL4_NLI_PYFLOAT_MASK = 3,   /* NUMPY2 mode: bit 0/1/2 set while eta_a / eta_c / lambdaa is a python float */
+                        RL4_NLI_COUNT = 4 };
 
 typedef struct rl4_nl_state {
     double*  env;            /* [RL4_NLE_COUNT][stride] */
@@ -255,6 +257,9 @@ enum rl4_nl_hpi {
     RL4_NHPI_MULTISTEP = 0, RL4_NHPI_WARMUP_STEPS, RL4_NHPI_COOLDOWN_STEPS, RL4_NHPI_FAULT_STEP,
     RL4_NHPI_FAULT_DAMP, RL4_NHPI_FAULT_SAT, RL4_NHPI_ELIG_A,
     RL4_NHPI_FLIGHT_STEP,      /* first step of the 'flight' phase of the RSE split (5500)      functions.py:916-917 */
+    RL4_NHPI_NUMPY2,           /* _adapt_check promotion rules (objects.py:1235-1284): 0 = numpy 1.x value-based casting (the
+                                * reference's era: float64 intermediates), 1 = NEP 50 / numpy >= 2 (python floats are weak:
+                                * float32 arithmetic once eta / lambda have become float32 arrays) */
     RL4_NHPI_COUNT
 };
 enum rl4_nl_fault_damp { RL4_NL_DAMP_NONE = 0, RL4_NL_DAMP_ELEVATOR, RL4_NL_DAMP_AILERON, RL4_NL_DAMP_RUDDER,

@@ -158,6 +158,54 @@ def nl_env_fixture(fault, seed, steps=700, fault_time=3.0, integrator="ode5"):
     return res
 
 
+def nl_loop_fixture(seed, *, fault="none", fault_time=60, integrator="ode5", elig="accumulating", ms=0, steps=600, warmup=1.5,
+                    lambda_l=0.8):
+    """The VERBATIM nonlinear agent: objects.py's IDHPnonlin / Actor_big / Critic_big / RLS on the TensorFlow stand-in,
+    driving the verbatim Ce500NonLinear wrapper around the surrogate plant.  numpy >= 2 here, so `_adapt_check` follows
+    NEP 50 (oracle / kernel flag numpy2 = 1).  A short warm-up puts the learning-rate decay inside the run."""
+    from oracle import nl_c
+    O, tf = ref_loader.load_reference_objects()
+    Env, stub = ref_loader.load_reference_nonlinear_env(integrator)
+    th = nl_c.theta_reference()
+    trim_input = np.array([-0.02855, 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.55, 0.55, 0])
+    trim_state = np.array([0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0])
+    env_config = {"state_dim": 4, "action_dim": 3, "trim_input": trim_input, "trim_state": trim_state, "dt": 0.01,
+                  "t_end": steps * 0.01, "total_steps": steps, "fault_time": fault_time, "fault_scenario": fault,
+                  "reference": {"tracked_state": ["phi", "theta", "psi"], "signal": [0 * th, th, 0 * th]}}
+    assert int(env_config["t_end"] / 0.01) == steps
+    idhp_config = {"gamma": 0.6, "multistep": ms, "lr_decay": 0.998, "lambda_h": 0.95, "lambda_l": lambda_l, "kappa": [1, 2, 1],
+                   "cooldown_time": 2.0, "sigma": 0.1, "warmup_time": warmup, "error_thresh": 1, "tau": 0.02, "in_dims": 4,
+                   "actor_config": {"layers": {10: "tanh", 1: "tanh"}, "eta_h": 35.0, "eta_l": 5.0, "elig": elig},
+                   "critic_config": {"layers": {10: "tanh", 3: "linear"}, "eta_h": 1.4, "eta_l": 0.7, "elig": 1233},
+                   "rls_config": {"state_dim": 3, "action_dim": 1, "rls_gamma": 1, "rls_cov": 10 ** 6}}     # idhp_nonlin.py:123-146
+    noise = np.random.default_rng(seed).standard_normal(steps).astype(np.float32)
+    tf.set_tanh(lambda v: sp_c.tanh_t13(np.asarray(v, dtype=np.float32)))
+    tf.set_noise(noise[1:])                       # objects.py:1375 draws inside `if step > 0`
+    try:
+        env = Env(env_config)
+        idhp = O.IDHPnonlin(env, idhp_config, verbose=False, seed=seed)
+        w = nl_c.init_weights(1, seed)
+        idhp.actor.set_weights([w["W1a"][0].reshape(4, 10), w["W2a"][0].reshape(10, 1)])
+        idhp.critic.set_weights([w["W1c"][0].reshape(4, 10), w["W2c"][0].reshape(10, 3)])
+        idhp.train()
+    finally:
+        tf.set_tanh(None); tf.set_noise(None)
+    L = idhp.log
+    out = dict(seed=seed, fault=str(fault), fault_time=fault_time, integrator=integrator, elig=str(elig), multistep=ms, steps=steps,
+               warmup=warmup, lambda_l=lambda_l, noise=noise, theta_ref=th[:steps], **{f"w_{k}": v[0] for k, v in w.items()})
+    for k in ("eta_a", "t", "x_full", "RSE", "x", "a_cmd", "a_eff", "s", "yref", "e", "a_weights2", "c_weights2", "a_grad",
+              "rls_params", "rls_eps_hist", "rls_eps_norm"):
+        out[f"log_{k}"] = np.asarray(L[k], dtype=np.float64)
+    for k in ("a_weights1", "c_weights1", "c_grad", "rls_cov"):                    # wide: every 10th row + the last
+        out[f"log10_{k}"] = np.asarray(L[k], dtype=np.float64)[9::10]
+    out["a_elig_nonzero"] = bool(np.any(L["a_elig"])) or bool(np.any(L["c_elig"]))
+    out["final_E"] = np.asarray(idhp.actor.E, dtype=np.float64).ravel()
+    out["final_W1t"] = idhp.target_critic.get_weights()[0].ravel().astype(np.float64)
+    out["final_W2t"] = idhp.target_critic.get_weights()[1].ravel().astype(np.float64)
+    out["RSE_total"] = np.asarray(idhp.RSE, dtype=np.float64)
+    return out
+
+
 def utils_fixture():
     """Outputs of the verbatim utils.py functions (samplers with true_random=False, PSD, convergence time, VD_A, KL)."""
     U = ref_loader.load_reference_utils()
@@ -199,6 +247,10 @@ def main():
     for i, (f, integ) in enumerate([("none", "ode5"), ("damp_elevator_and_saturate_elevator", "ode5"), ("shift_cg", "rk4"),
                                     ("slow_all", "ode5"), ("damp_all", "ode5"), ("saturate_aileron", "rk4")]):
         np.savez_compressed(os.path.join(OUT, f"nl_env_{f}.npz"), **nl_env_fixture(f, 200 + i, integrator=integ))
+    nl_cases = {"default": dict(seed=41), "ms_notrace_rk4": dict(seed=42, ms=1, elig=None, integrator="rk4"),
+                "replacing_fault": dict(seed=43, elig="replacing", fault="damp_elevator_and_saturate_elevator", fault_time=3.0)}
+    for name, kw in nl_cases.items():
+        np.savez_compressed(os.path.join(OUT, f"nl_loop_{name}.npz"), **nl_loop_fixture(**kw))
     if "--only-utils" in sys.argv:
         return
     for i, f in enumerate([None, "invert_elevator", "damp_elevator", "shift_cg"]):

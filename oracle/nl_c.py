@@ -25,7 +25,7 @@ CFG_DTYPE = np.dtype([
     ("noise_std", "f8", (4,)), ("omega0", "f8"), ("omega_slow", "f8"), ("rate_limit", "f8"),
     ("limit_deg", "f8", (3,)), ("damp_factor", "f8"), ("cg_shift", "f8"), ("sat_limit", "f8", (3,)),
     ("multistep", "i4"), ("warmup_steps", "i4"), ("cooldown_steps", "i4"), ("fault_step", "i4"),
-    ("elig_a", "i4"), ("fault_damp", "i4"), ("fault_sat", "i4"), ("integrator", "i4"), ("flight_step", "i4"), ("pad", "i4"),
+    ("elig_a", "i4"), ("fault_damp", "i4"), ("fault_sat", "i4"), ("integrator", "i4"), ("flight_step", "i4"), ("numpy2", "i4"),
 ], align=True)
 
 STATE_DTYPE = np.dtype([
@@ -36,7 +36,7 @@ STATE_DTYPE = np.dtype([
     ("theta", "f8", (12,)), ("cov", "f8", (16,)), ("cgrad_prev", "f8", (3,)), ("M_prev", "f8", (9,)),
     ("eta_a", "f8"), ("eta_c", "f8"), ("lambdaa", "f8"), ("lr_a", "f8"), ("lr_c", "f8"), ("gl", "f8"),
     ("eps", "f8", (3,)), ("eps_norm", "f8"), ("rse", "f8", (2,)), ("nz_peak", "f8"), ("rse_flight", "f8", (2,)),
-    ("cooldown", "i4"), ("diverged_step", "i4"), ("stepp", "i4"), ("pad", "i4"),
+    ("cooldown", "i4"), ("diverged_step", "i4"), ("stepp", "i4"), ("pyfloat_mask", "i4"),
 ], align=True)
 
 LOG_DTYPE = np.dtype([

@@ -44,7 +44,9 @@ typedef struct {
     int32_t multistep, warmup_steps, cooldown_steps, fault_step;
     int32_t elig_a;             /* 0 none, 1 accumulating, 2 replacing */
     int32_t fault_damp, fault_sat, integrator;
-    int32_t flight_step, pad;   /* 5500: RSE split of functions.py:916-917,1038-1039 */
+    int32_t flight_step;        /* 5500: RSE split of functions.py:916-917,1038-1039 */
+    int32_t numpy2;             /* 0: numpy 1.x value-based promotion in _adapt_check (the reference's era, what the kernels
+                                 * implement); 1: NEP 50 (numpy >= 2, what the verbatim code does in this container) */
 } orc_nl_cfg;
 
 typedef struct {
@@ -65,7 +67,8 @@ typedef struct {
     double rse[2];                  /* cumulative RSE, objects.py:1503-1504 */
     double nz_peak;                 /* max |V*q/9.80665|, functions.py:774,1050,1055 */
     double rse_flight[2];           /* RSE over steps >= flight_step */
-    int32_t cooldown, diverged_step, stepp, pad;
+    int32_t cooldown, diverged_step, stepp;
+    int32_t pyfloat_mask;           /* numpy2 mode: bit 0/1/2 set while eta_a / eta_c / lambdaa is still a python float */
 } orc_nl_state;
 
 /* per-step record for tests */

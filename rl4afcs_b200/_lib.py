@@ -56,11 +56,11 @@ NLE = dict(XFULL=0, XACT=12, XLON=15, XPREVLON=18, THETA=21, COV=33, CGRAD_PREV=
            NZ_PEAK=56, ETA_A=57, ETA_C=58, LAMBDAA=59, GL=60, EA=61, RSE_FLIGHT=111, COUNT=113)
 NLN = dict(S=0, SPREV=4, A=8, APREV=9, W1A=10, W2A=50, W1C=60, W2C=100, W1T=130, W2T=170, MPREV=200, LR_A=209,
            LR_C=210, COUNT=211)
-NLI = dict(COOLDOWN=0, DIVERGED_STEP=1, STEPP=2, COUNT=3)
+NLI = dict(COOLDOWN=0, DIVERGED_STEP=1, STEPP=2, PYFLOAT_MASK=3, COUNT=4)
 NHP = dict(ETA_A_H=0, ETA_A_L=1, ETA_C_H=2, ETA_C_L=3, LAMBDA_H=4, LAMBDA_L=5, GAMMA=6, GAMMA_SQ=7, TAU=8, LR_DECAY=9,
            RLS_GAMMA=10, RLS_COV0=11, Q_SYM=12, LAMBDA_T=13, LAMBDA_S=14, DAMP_FACTOR=15, CG_SHIFT=16, COUNT=17)
 NHPI = dict(MULTISTEP=0, WARMUP_STEPS=1, COOLDOWN_STEPS=2, FAULT_STEP=3, FAULT_DAMP=4, FAULT_SAT=5, ELIG_A=6, FLIGHT_STEP=7,
-            COUNT=8)
+            NUMPY2=8, COUNT=9)
 NL_DAMP = {None: 0, "none": 0, "damp_elevator": 1, "damp_aileron": 2, "damp_rudder": 3, "damp_all": 4, "shift_cg": 5,
            "slow_all": 6}
 NL_SAT = {None: 0, "none": 0, "saturate_elevator": 1, "saturate_aileron": 2, "saturate_rudder": 3}

@@ -227,6 +227,23 @@ __device__ __forceinline__ double nl_decay(double a, double b, double c, bool f3
     const double v = a2 * r;
     return f32 ? (double)(float)v : v;
 }
+// the same under NEP 50 (numpy >= 2): once `a` is a 0-d float32 array the python-float operands are weak -> float32
+// arithmetic with the constants rounded to float32 first; while `a` is still a python float it is float64 arithmetic
+__device__ __forceinline__ double nl_decay_np2(double a, double b, double c, bool a_is_pyfloat)
+{
+    if (a_is_pyfloat) {
+        double r = b / a;
+        r = c + (1.0 - c) * r;
+        const double a2 = a * (0.998 + (1.0 - 0.998) * b / a);
+        return (double)(float)(a2 * r);
+    }
+    const float af = (float)a;
+    float r = __fdiv_rn((float)b, af);
+    r = __fadd_rn((float)c, __fmul_rn((float)(1.0 - c), r));
+    const float q = __fdiv_rn((float)((1.0 - 0.998) * b), af);
+    const float a2 = __fmul_rn(af, __fadd_rn((float)0.998, q));
+    return (double)__fmul_rn(a2, r);
+}
 __device__ __forceinline__ bool nl_isclose(double a, double b) { return fabs(a - b) <= (1e-8 + 1e-5 * fabs(b)); }
 
 template <typename TN, int INTEG, bool LOG>
@@ -282,6 +299,7 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
     for (int j = 0; j < 30; ++j) { W2c[j] = NF(RL4_NLN_W2C + j); W2t[j] = NF(RL4_NLN_W2T + j); }
     for (int j = 0; j < 9; ++j) Mp[j] = NF(RL4_NLN_MPREV + j);
     int cooldown = I[(int64_t)RL4_NLI_COOLDOWN * S], diverged_step = I[(int64_t)RL4_NLI_DIVERGED_STEP * S], stepp = I[(int64_t)RL4_NLI_STEPP * S];
+    int pyfloat_mask = I[(int64_t)RL4_NLI_PYFLOAT_MASK * S];
 
     const bool logged = LOG && i < lg.n_agents_logged;
     const bool f32 = sizeof(TN) == 4;
@@ -463,15 +481,27 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
             {   // _adapt_check (objects.py:1212-1290)
                 const bool cond1 = k < hv.hpi(RL4_NHPI_WARMUP_STEPS);
                 if (cooldown > 0) cooldown -= 1;
+                const bool np2 = f32 && hv.hpi(RL4_NHPI_NUMPY2) != 0;
                 if (!cond1) {
                     const double dec = hv.hp(RL4_NHP_LR_DECAY);
                     const double eal = hv.hp(RL4_NHP_ETA_A_L), ecl = hv.hp(RL4_NHP_ETA_C_L), ll = hv.hp(RL4_NHP_LAMBDA_L);
-                    eta_a = nl_isclose(eta_a, eal) ? eal : nl_decay(eta_a, eal, dec, f32);
-                    eta_c = nl_isclose(eta_c, ecl) ? ecl : nl_decay(eta_c, ecl, dec, f32);
-                    lambdaa = nl_isclose(lambdaa, ll) ? ll : nl_decay(lambdaa, ll, dec, f32);
+                    if (!np2) {
+                        eta_a = nl_isclose(eta_a, eal) ? eal : nl_decay(eta_a, eal, dec, f32);
+                        eta_c = nl_isclose(eta_c, ecl) ? ecl : nl_decay(eta_c, ecl, dec, f32);
+                        lambdaa = nl_isclose(lambdaa, ll) ? ll : nl_decay(lambdaa, ll, dec, f32);
+                    } else {
+                        if (nl_isclose(eta_a, eal)) { eta_a = eal; pyfloat_mask |= 1; } else { eta_a = nl_decay_np2(eta_a, eal, dec, pyfloat_mask & 1); pyfloat_mask &= ~1; }
+                        if (nl_isclose(eta_c, ecl)) { eta_c = ecl; pyfloat_mask |= 2; } else { eta_c = nl_decay_np2(eta_c, ecl, dec, pyfloat_mask & 2); pyfloat_mask &= ~2; }
+                        if (nl_isclose(lambdaa, ll)) { lambdaa = ll; pyfloat_mask |= 4; } else { lambdaa = nl_decay_np2(lambdaa, ll, dec, pyfloat_mask & 4); pyfloat_mask &= ~4; }
+                    }
                 }
-                const double lambda_gamma = lambdaa * gamma_d;
-                if ((double)lr_a != eta_a && (double)lr_c != eta_c && cooldown <= 0) {
+                double lambda_gamma = lambdaa * gamma_d;
+                bool differ = ((double)lr_a != eta_a && (double)lr_c != eta_c);
+                if (np2) {                                                         // weak python floats: float32 product / comparisons
+                    if (!(pyfloat_mask & 4)) lambda_gamma = (double)__fmul_rn((float)lambdaa, (float)gamma_d);
+                    differ = ((float)lr_a != (float)eta_a && (float)lr_c != (float)eta_c);
+                }
+                if (differ && cooldown <= 0) {
                     lr_a = (TN)eta_a; lr_c = (TN)eta_c;
                     gl = lambda_gamma;
                     cooldown = hv.hpi(RL4_NHPI_COOLDOWN_STEPS);
@@ -553,6 +583,7 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
     for (int j = 0; j < 30; ++j) { NF(RL4_NLN_W2C + j) = W2c[j]; NF(RL4_NLN_W2T + j) = W2t[j]; }
     for (int j = 0; j < 9; ++j) NF(RL4_NLN_MPREV + j) = Mp[j];
     I[(int64_t)RL4_NLI_COOLDOWN * S] = cooldown; I[(int64_t)RL4_NLI_DIVERGED_STEP * S] = diverged_step; I[(int64_t)RL4_NLI_STEPP * S] = stepp;
+    I[(int64_t)RL4_NLI_PYFLOAT_MASK * S] = pyfloat_mask;
 #undef EF
 #undef NF
 }
@@ -596,6 +627,7 @@ nl_init_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict
     st.ints[(int64_t)RL4_NLI_COOLDOWN * S + i] = 0;
     st.ints[(int64_t)RL4_NLI_DIVERGED_STEP * S + i] = -1;
     st.ints[(int64_t)RL4_NLI_STEPP * S + i] = 0;
+    st.ints[(int64_t)RL4_NLI_PYFLOAT_MASK * S + i] = 7;
 }
 
 __global__ void __launch_bounds__(128)
@@ -743,6 +775,7 @@ int rl4_nl_default_params(rl4_nl_params* p)
     p->hpi[RL4_NHPI_FAULT_STEP] = -1; p->hpi[RL4_NHPI_FAULT_DAMP] = 0; p->hpi[RL4_NHPI_FAULT_SAT] = 0;
     p->hpi[RL4_NHPI_ELIG_A] = RL4_ELIG_ACCUMULATING;
     p->hpi[RL4_NHPI_FLIGHT_STEP] = 5500;
+    p->hpi[RL4_NHPI_NUMPY2] = 0;
     p->integrator = RL4_CIT_INTEGRATOR_ODE5;
     return 0;
 }

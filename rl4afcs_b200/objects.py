@@ -517,13 +517,16 @@ class IDHPnonlin:
     generator (or supplied: ``noise=`` (steps, B) float32), the initial weights are TruncatedNormal(sigma) from
     ``seed`` or ``weights=`` (W1a (B,40), W2a (B,10), W1c (B,40), W2c (B,30)).
 
+    ``numpy2``: the float32 / float64 promotion rules `_adapt_check` (objects.py:1235-1284) runs under -- False = numpy 1.x
+    value-based casting (the reference's era, default), True = NEP 50 (what the verbatim code does under numpy >= 2).
+
     ``log``: "full" = the reference's log dict (objects.py:1083-1176) for the first ``log_agents`` agents, every array
     with a leading agent axis; "compact" = x_full / a / e / reward / a_cmd only; "mc" = the per-step quantities
     MC_test_hparam keeps (functions.py:1040-1052), cheap enough for every agent; None = statistics only.
     """
 
     def __init__(self, env, config, verbose=True, seed=1, *, weights=None, log="full", log_agents=None,
-                 chunk: int = 1000) -> None:
+                 chunk: int = 1000, numpy2: bool = False) -> None:
         from . import nl_engine  # noqa: F401
 
         assert log in ("full", "compact", "mc", None)
@@ -549,6 +552,7 @@ class IDHPnonlin:
         eng.set_hp("ETA_C_H", config["critic_config"]["eta_h"]); eng.set_hp("ETA_C_L", config["critic_config"]["eta_l"])
         eng.set_hp("RLS_GAMMA", config["rls_config"]["rls_gamma"]); eng.set_hp("RLS_COV0", config["rls_config"]["rls_cov"])
         eng.set_hpi("MULTISTEP", per(config["multistep"], lambda m: 1 if m > 0 else 0))
+        eng.set_hpi("NUMPY2", 1 if numpy2 else 0)        # _adapt_check promotion rules: numpy 1.x (reference era) or NEP 50
         eng.set_hpi("WARMUP_STEPS", per(config["warmup_time"], lambda t: int(t / env.dt)))          # objects.py:1222
         eng.set_hpi("COOLDOWN_STEPS", per(config["cooldown_time"], lambda t: int(t / env.dt)))      # objects.py:1025
         elig = config["actor_config"]["elig"]

@@ -30,6 +30,7 @@ def engine_to_oracle(eng, nl_c):
     st["cooldown"] = ints[NLI["COOLDOWN"]]
     st["diverged_step"] = ints[NLI["DIVERGED_STEP"]]
     st["stepp"] = ints[NLI["STEPP"]]
+    st["pyfloat_mask"] = ints[NLI["PYFLOAT_MASK"]]
     return st
 
 
@@ -52,6 +53,7 @@ def oracle_to_engine(st, eng):
     ints[NLI["COOLDOWN"]] = st["cooldown"]
     ints[NLI["DIVERGED_STEP"]] = st["diverged_step"]
     ints[NLI["STEPP"]] = st["stepp"]
+    ints[NLI["PYFLOAT_MASK"]] = st["pyfloat_mask"]
     eng.env[:, :n] = torch.as_tensor(env).to(eng.device)
     eng.net[:, :n] = torch.as_tensor(net).to(eng.net.dtype).to(eng.device)
     eng.ints[:, :n] = torch.as_tensor(ints).to(eng.device)

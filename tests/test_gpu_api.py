@@ -380,3 +380,39 @@ def test_nonlinear_env_equals_verbatim_reference_wrapper(path):
         assert ulp(rr[:, 0], g["reward"][k, 0]) and ulp(rr[:, 1], g["reward"][k, 1], 4), k
         assert ulp(info["RSE"][0].cpu().numpy(), g["RSE"][k, 0]) and ulp(info["RSE"][1].cpu().numpy(), g["RSE"][k, 1], 4), k
         assert info["nans"] == bool(g["nans"][k]) and abs(info["t"] - g["t"][k]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["default", "ms_notrace_rk4", "replacing_fault"])
+def test_idhpnonlin_train_equals_verbatim_reference_run(name):
+    """IDHPnonlin(env, config).train() on the GPU against golden runs of the VERBATIM nonlinear agent (objects.py's
+    IDHPnonlin / Actor_big / Critic_big / RLS on the TensorFlow stand-in, verbatim Ce500NonLinear wrapper, surrogate plant;
+    oracle/make_golden.py::nl_loop_fixture): the full log dict bit for bit, `_adapt_check` under NEP 50 like the fixture."""
+    from rl4afcs_b200.envs.nonlinear.env import Ce500NonLinear
+    from rl4afcs_b200.objects import IDHPnonlin
+
+    g = np.load(os.path.join(GOLD, f"nl_loop_{name}.npz"))
+    steps, B = int(g["steps"]), 2
+    th = np.zeros(9000); th[:steps] = g["theta_ref"]
+    elig = {"None": None}.get(str(g["elig"]), str(g["elig"]))
+    env = Ce500NonLinear(_nl_env_config(th, fault_scenario=str(g["fault"]), fault_time=float(g["fault_time"]), t_end=steps * 0.01,
+                                        total_steps=steps), batch=B, dtype="mixed", integrator=str(g["integrator"]))
+    idhp_config = {"gamma": 0.6, "multistep": int(g["multistep"]), "lr_decay": 0.998, "lambda_h": 0.95, "lambda_l": float(g["lambda_l"]),
+                   "kappa": [1, 2, 1], "cooldown_time": 2.0, "sigma": 0.1, "warmup_time": float(g["warmup"]), "error_thresh": 1,
+                   "tau": 0.02, "in_dims": 4,
+                   "actor_config": {"layers": {10: "tanh", 1: "tanh"}, "eta_h": 35.0, "eta_l": 5.0, "elig": elig},
+                   "critic_config": {"layers": {10: "tanh", 3: "linear"}, "eta_h": 1.4, "eta_l": 0.7, "elig": 1233},
+                   "rls_config": {"state_dim": 3, "action_dim": 1, "rls_gamma": 1, "rls_cov": 10 ** 6}}
+    w = {k: np.broadcast_to(g[f"w_{k}"], (B,) + g[f"w_{k}"].shape).copy() for k in ("W1a", "W2a", "W1c", "W2c")}
+    idhp = IDHPnonlin(env, idhp_config, seed=1, verbose=0, weights=w, log="full", log_agents=B, chunk=250, numpy2=True)
+    idhp.train(steps, noise=np.repeat(g["noise"][:, None], B, axis=1))
+    lg = {k: v.cpu().numpy() for k, v in idhp.log.items()}
+    for b in range(B):
+        for k in ("eta_a", "x_full", "RSE", "x", "a_cmd", "a_eff", "s", "yref", "e", "a_weights2", "c_weights2", "a_grad",
+                  "rls_params", "rls_eps_hist", "rls_eps_norm"):
+            assert np.array_equal(lg[k][b], g[f"log_{k}"], equal_nan=True), k
+        for k in ("a_weights1", "c_weights1", "c_grad", "rls_cov"):
+            assert np.array_equal(lg[k][b][9::10], g[f"log10_{k}"], equal_nan=True), k
+        assert np.allclose(lg["t"][b], g["log_t"], rtol=0, atol=1e-12)
+        assert np.array_equal(idhp.actor.E[b].cpu().numpy().ravel(), g["final_E"])
+        assert np.array_equal(idhp.target_critic.trainable_weights[1][b].double().cpu().numpy().ravel(), g["final_W2t"])
+        assert np.allclose(float(idhp.RSE[0][b]), g["RSE_total"][0], rtol=1e-14)

@@ -1,5 +1,7 @@
 """Live re-check of the oracle against the verbatim reference code (build container only:
 /root/reference is not present on the GPU box, where the committed golden vectors stand in)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -100,3 +102,29 @@ def test_c_oracle_equals_verbatim_idhpsp_on_tf_standin(oracle, seed, fault, elig
     # final object state == final oracle state
     assert np.array_equal(idhp.model.params.ravel(), st["theta"][0]) and np.array_equal(idhp.model.Cov.ravel(), st["cov"][0])
     assert np.array_equal(idhp.target_critic.get_weights()[1].ravel().astype(np.float64), st["W2t"][0])
+
+
+@pytest.mark.parametrize("seed,kw", [
+    (51, dict(steps=1300, warmup=2.0)),                                                    # decay + two LR hand-overs
+    (52, dict(steps=700, warmup=1.0, ms=1, elig=None, integrator="rk4", fault="shift_cg", fault_time=2.0)),
+    (53, dict(steps=700, warmup=1.0, elig="replacing", fault="slow_all", fault_time=2.5)),
+])
+def test_c_oracle_equals_verbatim_idhpnonlin_on_tf_standin(oracle, seed, kw):
+    """Live form of tests/test_oracle_golden.py::test_nl_full_loop_matches_verbatim_idhpnonlin: the verbatim IDHPnonlin
+    (TensorFlow stand-in, verbatim env wrapper, surrogate plant) is run here and compared with the C oracle."""
+    from oracle import make_golden as mg
+    from oracle import nl_c
+    from tests.test_oracle_golden import _NL_LOG10_MAP, _NL_LOG_MAP, _nl_loop_cfg, _oracle_nl_view
+
+    g = mg.nl_loop_fixture(seed, **kw)
+    steps = int(g["steps"])
+    g = {k: np.asarray(v) for k, v in g.items()}
+    cfg = _nl_loop_cfg(nl_c, g)
+    w = {k: g[f"w_{k}"][None] for k in ("W1a", "W2a", "W1c", "W2c")}
+    st = nl_c.init_states("mixed", cfg, w, 1)
+    olog = nl_c.run("mixed", cfg, g["theta_ref"], g["noise"].reshape(steps, 1), st, 0, steps, tanh="t13", n_log=1)[0]
+    for key, oname in _NL_LOG_MAP:
+        assert np.array_equal(g[f"log_{key}"], _oracle_nl_view(olog, oname), equal_nan=True), key
+    for key, oname in _NL_LOG10_MAP:
+        assert np.array_equal(g[f"log10_{key}"], _oracle_nl_view(olog, oname)[9::10], equal_nan=True), key
+    assert np.array_equal(g["final_E"], st["Ea"][0], equal_nan=True)        # case 52 diverges: NaN convention included
