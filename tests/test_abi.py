@@ -64,3 +64,32 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.replace("# oracle", ""), os.path.join(dp, f)
+
+
+def test_nl_default_params_equal_oracle_defaults(oracle):
+    """rl4_nl_default_params (host-only C entry point) == the oracle's default configuration, which
+    tests/test_oracle_vs_reference.py pins to the verbatim idhp_nonlin.py; the plant block (trim solve, atmosphere
+    series, reciprocals) must come out bit-identical from nvcc's host pass and from gcc."""
+    from oracle import nl_c
+    from rl4afcs_b200 import _lib
+
+    L = _lib.load()
+    p = _lib.NlParams()
+    assert L.rl4_nl_default_params(ctypes.byref(p)) == 0
+    cfg = nl_c.make_cfg()[0]
+    for f in nl_c.PLANT_FIELDS + ["zeta_per_m"]:
+        assert getattr(p.plant, f) == cfg["plant"][f], f
+    assert list(p.plant.rho_poly) == list(cfg["plant"]["rho_poly"]) and list(p.plant.lapse_poly) == list(cfg["plant"]["lapse_poly"])
+    assert list(p.trim_input) == list(cfg["trim_input"]) and p.dt == cfg["dt"]
+    hp = _lib.NHP
+    for key, name in (("ETA_A_H", "eta_a_h"), ("ETA_A_L", "eta_a_l"), ("ETA_C_H", "eta_c_h"), ("ETA_C_L", "eta_c_l"),
+                      ("LAMBDA_H", "lambda_h"), ("LAMBDA_L", "lambda_l"), ("GAMMA", "gamma"), ("GAMMA_SQ", "gamma_sq"), ("TAU", "tau"),
+                      ("LR_DECAY", "lr_decay"), ("RLS_GAMMA", "rls_gamma"), ("RLS_COV0", "rls_cov0"), ("Q_SYM", "Q_sym"),
+                      ("LAMBDA_T", "lambda_t"), ("LAMBDA_S", "lambda_s"), ("DAMP_FACTOR", "damp_factor"), ("CG_SHIFT", "cg_shift")):
+        assert p.hp[hp[key]] == cfg[name], key
+    assert list(p.noise_std) == list(cfg["noise_std"]) and p.omega0 == cfg["omega0"] and p.omega_slow == cfg["omega_slow"]
+    assert p.rate_limit == cfg["rate_limit"] and list(p.limit_deg) == list(cfg["limit_deg"]) and list(p.sat_limit) == list(cfg["sat_limit"])
+    hi = _lib.NHPI
+    assert p.hpi[hi["WARMUP_STEPS"]] == cfg["warmup_steps"] and p.hpi[hi["COOLDOWN_STEPS"]] == cfg["cooldown_steps"]
+    assert p.hpi[hi["MULTISTEP"]] == cfg["multistep"] and p.hpi[hi["ELIG_A"]] == cfg["elig_a"] and p.hpi[hi["FAULT_STEP"]] == cfg["fault_step"]
+    assert p.hpi[hi["FLIGHT_STEP"]] == cfg["flight_step"] == 5500 and p.hpi[hi["NUMPY2"]] == 0 and p.integrator == cfg["integrator"]

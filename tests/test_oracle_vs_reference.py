@@ -128,3 +128,54 @@ def test_c_oracle_equals_verbatim_idhpnonlin_on_tf_standin(oracle, seed, kw):
     for key, oname in _NL_LOG10_MAP:
         assert np.array_equal(g[f"log10_{key}"], _oracle_nl_view(olog, oname)[9::10], equal_nan=True), key
     assert np.array_equal(g["final_E"], st["Ea"][0], equal_nan=True)        # case 52 diverges: NaN convention included
+
+
+def _driver_namespace(script, prefer_else_of=("MC",)):
+    """Executes only the plain assignments of a reference driver's `if __name__ == '__main__':` block (descending into the
+    single-run branch of `if MC:`), skipping everything that needs TensorFlow / the environments / plotting."""
+    import ast
+
+    src = open(os.path.join(ref_loader.REFERENCE_ROOT, script)).read()
+    tree = ast.parse(src)
+    ns = {"np": np, "NO_TRACE": None, "A_TRACE": "accumulating", "R_TRACE": "replacing", "timeit": __import__("timeit")}
+
+    def run(stmts):
+        for st in stmts:
+            if isinstance(st, (ast.Assign, ast.AugAssign)):
+                try:
+                    exec(compile(ast.Module(body=[st], type_ignores=[]), script, "exec"), ns)
+                except Exception:
+                    pass
+            elif isinstance(st, ast.If):
+                name = st.test.id if isinstance(st.test, ast.Name) else None
+                run(st.orelse if name in prefer_else_of else st.body)
+    for node in tree.body:
+        if isinstance(node, ast.If) and isinstance(node.test, ast.Compare):
+            run(node.body)
+    return ns
+
+
+def test_default_configurations_equal_the_verbatim_drivers(oracle):
+    """idhp_sp.py / idhp_nonlin.py: the shipped single-run configurations and reference signals, evaluated from the
+    driver sources themselves, equal the defaults the oracle, the C-ABI (`rl4_nl_default_params`) and bench.py use."""
+    from oracle import nl_c
+
+    sp = _driver_namespace("idhp_sp.py")
+    assert sp["idhp_config"] == oracle.default_idhp_config()
+    base, amp = oracle.default_reference()
+    assert np.array_equal(sp["ref"], amp * base)                                            # idhp_sp.py:41-44,174
+    assert sp["env_config"]["dt"] == 0.02 and sp["env_config"]["t_end"] == 60 and sp["env_config"]["fault_time"] == 20
+    assert not sp["env_config"]["x0"].any() and sp["seed"] == 4
+
+    nlns = _driver_namespace("idhp_nonlin.py")
+    assert np.array_equal(nlns["theta_ref"], nl_c.theta_reference())                        # idhp_nonlin.py:40-48
+    ic, cfg = nlns["idhp_config"], nl_c.make_cfg()[0]
+    assert np.array_equal(nlns["trim_input"], cfg["trim_input"]) and nlns["env_config"]["dt"] == cfg["dt"]
+    for key, val in (("gamma", ic["gamma"]), ("tau", ic["tau"]), ("lambda_h", ic["lambda_h"]), ("lambda_l", ic["lambda_l"]),
+                     ("lr_decay", ic["lr_decay"]), ("eta_a_h", ic["actor_config"]["eta_h"]), ("eta_a_l", ic["actor_config"]["eta_l"]),
+                     ("eta_c_h", ic["critic_config"]["eta_h"]), ("eta_c_l", ic["critic_config"]["eta_l"]),
+                     ("rls_gamma", ic["rls_config"]["rls_gamma"]), ("rls_cov0", ic["rls_config"]["rls_cov"]), ("Q_sym", ic["kappa"][1])):
+        assert cfg[key] == val, key
+    assert cfg["multistep"] == (1 if ic["multistep"] > 0 else 0) and cfg["elig_a"] == oracle.ELIG[ic["actor_config"]["elig"]]
+    assert cfg["warmup_steps"] == int(ic["warmup_time"] / 0.01) and cfg["cooldown_steps"] == int(ic["cooldown_time"] / 0.01)
+    assert nlns["env_config"]["fault_time"] == 60 and nlns["env_config"]["fault_scenario"] == "none" and nlns["seed"] == 8
