@@ -102,6 +102,8 @@ enum rl4_sp_hp {
 enum rl4_sp_hpi {
     RL4_HPI_MULTISTEP = 0, RL4_HPI_WARMUP_STEPS, RL4_HPI_COOLDOWN_STEPS,
     RL4_HPI_FAULT_STEP, RL4_HPI_FAULT_KIND, RL4_HPI_ELIG_A, RL4_HPI_ELIG_C,
+    RL4_HPI_TRACKED_Q,          /* 0: tracked_state 'alpha' (idhp_sp.py:175), 1: 'q' (envs/linear/env.py:180-184); the reward
+                                 * gradient stays in the alpha slot either way (Q4) */
     RL4_HPI_COUNT
 };
 

@@ -70,7 +70,7 @@ def rls_fixture(gamma, seed, steps=400, reset_at=250):
                 theta=np.array(th), cov=np.array(cv), eps=np.array(ep), eps_norm=np.array(en))
 
 
-def loop_fixture(name, *, x0, seed, fault=None, elig=(None, None), ms=2, steps=1100, tanh="t13"):
+def loop_fixture(name, *, x0, seed, fault=None, elig=(None, None), ms=2, steps=1100, tanh="t13", tracked="alpha"):
     """The VERBATIM agent: objects.py's IDHPsp / Actor / Critic / RLS classes (executed on the TensorFlow stand-in of
     oracle/tf_shim.py) driving the verbatim Ce500ShortPeriod; only the initial weights are injected."""
     Env = ref_loader.load_reference_linear_env()
@@ -83,7 +83,7 @@ def loop_fixture(name, *, x0, seed, fault=None, elig=(None, None), ms=2, steps=1
     assert int(t_end / 0.02) == steps
     env = Env({"state_dim": 2, "action_dim": 1, "x0": np.array(x0, dtype=float).reshape(2, 1), "dt": 0.02,
                "t_end": t_end, "fault_time": 20, "fault_scenario": fault,
-               "reference": {"tracked_state": ["alpha"], "signal": [amp * base]}})
+               "reference": {"tracked_state": [tracked], "signal": [amp * base]}})
     w = sp_c.init_weights(1, seed)
     tf.set_tanh((lambda a: sp_c.tanh_t13(np.asarray(a, dtype=np.float32))) if tanh == "t13" else (lambda a: np.tanh(a)))
     idhp = O.IDHPsp(env, ic, verbose=False, seed=seed)
@@ -92,7 +92,7 @@ def loop_fixture(name, *, x0, seed, fault=None, elig=(None, None), ms=2, steps=1
     idhp.train()
     tf.set_tanh(None)
     out = dict(x0=np.array(x0, dtype=float), seed=seed, fault=str(fault), elig_a=str(elig[0]), elig_c=str(elig[1]),
-               multistep=ms, steps=steps, tanh=tanh, **{f"w_{k}": v[0] for k, v in w.items()})
+               multistep=ms, steps=steps, tanh=tanh, tracked=tracked, **{f"w_{k}": v[0] for k, v in w.items()})
     f64 = lambda v, w_: np.asarray(v, dtype=np.float64).reshape(steps, w_) if w_ else np.asarray(v, dtype=np.float64).reshape(steps)   # noqa: E731
     out.update(x=f64(idhp.x_hist, 2), a=f64(idhp.a_hist, 0), c=f64(idhp.c_hist, 0), ref=f64(idhp.ref_hist, 0),
                a_w1=f64(idhp.a_weights_hist1, 4), a_w2=f64(idhp.a_weights_hist2, 4), c_w1=f64(idhp.c_weights_hist1, 4),
@@ -263,6 +263,7 @@ def main():
         "shiftcg_acc_1step": dict(x0=(-0.01, 0.03), seed=7, fault="shift_cg", elig=("accumulating", "accumulating"), ms=0),
         "invert_replacing": dict(x0=(0.015, 0.01), seed=8, fault="invert_elevator", elig=("replacing", "replacing")),
         "default_nptanh": dict(x0=(0.02, -0.03), seed=5, tanh="np"),
+        "trackq_damp": dict(x0=(0.01, -0.02), seed=9, fault="damp_elevator", tracked="q"),      # envs/linear/env.py:180-184
     }
     for name, kw in cases.items():
         np.savez_compressed(os.path.join(OUT, f"sp_loop_{name}.npz"), **loop_fixture(name, **kw))

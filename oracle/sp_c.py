@@ -30,7 +30,7 @@ CFG_DTYPE = np.dtype(
         ("eta_a_h", "f8"), ("eta_a_l", "f8"), ("eta_c_h", "f8"), ("eta_c_l", "f8"),
         ("rls_gamma", "f8"), ("rls_cov0", "f8"), ("error_thresh_deg", "f8"), ("ref_amp", "f8"),
         ("multistep", "i4"), ("warmup_steps", "i4"), ("cooldown_steps", "i4"), ("fault_step", "i4"),
-        ("elig_a", "i4"), ("elig_c", "i4"), ("q3_alias", "i4"), ("q7_numpy1", "i4"),
+        ("elig_a", "i4"), ("elig_c", "i4"), ("q3_alias", "i4"), ("q7_numpy1", "i4"), ("tracked_q", "i4"), ("pad", "i4"),
     ],
     align=True,
 )
@@ -192,7 +192,7 @@ def default_idhp_config() -> dict:
 
 
 def make_cfg(idhp_config=None, *, dt=0.02, fault_time=20, fault_scenario=None, ref_amp=None,
-             q3_alias=1, q7_numpy1=1, n=1) -> np.ndarray:
+             q3_alias=1, q7_numpy1=1, tracked_q=0, n=1) -> np.ndarray:
     """Build ``n`` identical orc_sp_cfg records from reference-style config dicts."""
     ic = default_idhp_config() if idhp_config is None else idhp_config
     k = ce500_coeffs()
@@ -223,6 +223,7 @@ def make_cfg(idhp_config=None, *, dt=0.02, fault_time=20, fault_scenario=None, r
     cfg["elig_c"] = ELIG[ic["critic_config"]["elig"]]
     cfg["q3_alias"] = q3_alias
     cfg["q7_numpy1"] = q7_numpy1
+    cfg["tracked_q"] = tracked_q
     return cfg
 
 

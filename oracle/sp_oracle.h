@@ -56,6 +56,8 @@ typedef struct {
     int32_t elig_a, elig_c; /* ORC_ELIG_* */
     int32_t q3_alias;       /* x aliasing at k == 1 (reference behaviour = 1) */
     int32_t q7_numpy1;      /* numpy-1.x value-based compare of f32 lr vs python float */
+    int32_t tracked_q;      /* 0: tracked_state 'alpha', 1: 'q'   envs/linear/env.py:180-184 */
+    int32_t pad;
 } orc_sp_cfg;
 
 /* Loop-carried per-agent state.  All values are stored as doubles; under the fp32 /

@@ -25,7 +25,8 @@ SPI = dict(COOLDOWN=0, FLAGS=1, DIVERGED_STEP=2, CONV_STEP=3, COUNT=4)
 SPF = dict(CHANGED=1, LR_INIT=2, LAMBDA_LOW=4, X_NAN=8)
 HP = dict(ETA_A_H=0, ETA_A_L=1, ETA_C_H=2, ETA_C_L=3, LAMBDA_H=4, LAMBDA_L=5, GAMMA=6, GAMMA_SQ=7, TAU=8,
           KAPPA=9, RLS_GAMMA=10, RLS_COV0=11, ERROR_THRESH_DEG=12, REF_AMP=13, COUNT=14)
-HPI = dict(MULTISTEP=0, WARMUP_STEPS=1, COOLDOWN_STEPS=2, FAULT_STEP=3, FAULT_KIND=4, ELIG_A=5, ELIG_C=6, COUNT=7)
+HPI = dict(MULTISTEP=0, WARMUP_STEPS=1, COOLDOWN_STEPS=2, FAULT_STEP=3, FAULT_KIND=4, ELIG_A=5, ELIG_C=6, TRACKED_Q=7,
+           COUNT=8)
 LOG_NONE, LOG_BASIC, LOG_FULL = 0, 1, 2
 LB = dict(X=0, A=2, C=3, REF=4, E=5, COUNT=6)
 LF = dict(AW1=6, AW2=10, CW1=14, CW2=18, AE=26, CE=34, AGRAD=46, CGRAD=54, PARAMS=66, COV=72, EPS_NORM=81,

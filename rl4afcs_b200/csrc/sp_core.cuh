@@ -78,14 +78,16 @@ struct SpStepOut {
 // ---------------------------------------------------------------------------------------
 template <typename TN, typename TE>
 __device__ __forceinline__ void sp_env_step(Rn<TE> (&x)[2], Rn<TN> action_deg, Rn<TE> ref, Rn<TE> kappa, Rn<TE> dt,
-                                            const double* __restrict__ A, const double* __restrict__ B,
+                                            const double* __restrict__ A, const double* __restrict__ B, bool tracked_q,
                                             Rn<TE>& e, Rn<TE>& cost, Rn<TE>& rg0, Rn<TE> (&xn)[2])
 {
     using E = Rn<TE>;
     const Rn<TN> u_n = action_deg * Rn<TN>(Consts<TN>::deg2rad());   // env.py:176
     const E u = cvt<TE>(u_n);
-    const E y0 = fma(E(TE(0)), x[1], E(TE(1)) * x[0]) + E(TE(0)) * u;   // env.py:179  C@x + D*action
-    e = ref - y0;                                                     // env.py:183
+    // env.py:179  y = C@x + D*action with C = I, D = 0; env.py:180-184: error = ref - y[0] ('alpha') or ref - y[1] ('q')
+    const E y = tracked_q ? (fma(E(TE(0)), x[0], E(TE(1)) * x[1]) + E(TE(0)) * u)
+                          : (fma(E(TE(0)), x[1], E(TE(1)) * x[0]) + E(TE(0)) * u);
+    e = ref - y;
     cost = (E(TE(-0.5)) * kappa) * (e * e);                           // env.py:187
     rg0 = kappa * (E(TE(-2)) * e);                                    // env.py:189
     const E A00 = E(TE(A[0])), A01 = E(TE(A[1])), A10 = E(TE(A[2])), A11 = E(TE(A[3]));
@@ -303,7 +305,8 @@ __device__ __forceinline__ void sp_agent_step(SpAgent<TN, TE, SM>& s, const rl4_
     const N a_k = s.a;
     o.ref = E(TE(hv.hp(RL4_HP_REF_AMP))) * E(TE(ref_base_k));           // idhp_sp.py:44,174
     E xn[2];
-    sp_env_step<TN, TE>(s.x, N(TN(20)) * a_k, o.ref, kappa, dt, p.A[variant], p.B[variant], o.e, o.cost, o.rg0, xn);
+    sp_env_step<TN, TE>(s.x, N(TN(20)) * a_k, o.ref, kappa, dt, p.A[variant], p.B[variant], hv.hpi(RL4_HPI_TRACKED_Q) != 0,
+                        o.e, o.cost, o.rg0, xn);
     const E rg1 = kappa * E(TE(0));
 
     // ---- _step_networks (objects.py:853-882): critic, target critic, actor on z = [[e]]

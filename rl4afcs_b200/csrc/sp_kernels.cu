@@ -265,7 +265,8 @@ sp_env_step_kernel(const __grid_constant__ rl4_sp_params p, const double* __rest
     const int variant = (fault_step >= 0 && stepp >= fault_step) ? hv.hpi(RL4_HPI_FAULT_KIND) : 0;
     E xs[2] = {E(x[i]), E(x[stride + i])}, xn[2], e, cost, rg0;
     const E ref = E(TE(hv.hp(RL4_HP_REF_AMP))) * E(TE(__ldg(ref_base + stepp)));
-    sp_env_step<TN, TE>(xs, Rn<TN>(action_deg[i]), ref, E(TE(hv.hp(RL4_HP_KAPPA))), E(TE(p.dt)), p.A[variant], p.B[variant], e, cost, rg0, xn);
+    sp_env_step<TN, TE>(xs, Rn<TN>(action_deg[i]), ref, E(TE(hv.hp(RL4_HP_KAPPA))), E(TE(p.dt)), p.A[variant], p.B[variant],
+                        hv.hpi(RL4_HPI_TRACKED_Q) != 0, e, cost, rg0, xn);
     x[i] = xn[0].v; x[stride + i] = xn[1].v;
     out_reward[i] = cost.v; out_e[i] = e.v; out_rg0[i] = rg0.v;
 }

@@ -57,6 +57,7 @@ class Ce500ShortPeriod:
         self._set_fault_params()
         self._engine.set_reference(self.state_reference)
         self._engine.set_hp("REF_AMP", 1.0)                # the signal array already carries its amplitude
+        self._engine.set_hpi("TRACKED_Q", 1 if self.tracked_state == "q" else 0)      # envs/linear/env.py:180-184
         self._write_x(self.x0)
         self.x_hist, self.y_hist, self.yref_hist = [], [], []
 

@@ -39,11 +39,12 @@ def test_struct_layouts_match_header_constants():
             assert m and int(m.group(1)) == v, (prefix, k)
     for table, enum in ((_lib.HP, "rl4_sp_hp"), (_lib.HPI, "rl4_sp_hpi")):
         body = re.search(r"enum " + enum + r"\s*\{(.*?)\}", hdr, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = [t.strip().split("=")[0].strip() for t in body.split(",") if t.strip()]
         for i, nm in enumerate(names):
             key = nm.replace("RL4_HPI_", "").replace("RL4_HP_", "")
             assert table[key] == i, nm
-    assert ctypes.sizeof(_lib.SpParams) == 8 * (16 + 8 + 1 + 14) + 4 * (7 + 2) + 4 + 8 * (14 + 7)
+    assert ctypes.sizeof(_lib.SpParams) == 8 * (16 + 8 + 1 + 14) + 4 * (8 + 2) + 8 * (14 + 8)
 
 
 def test_no_cpu_fallback():

@@ -19,9 +19,9 @@ def _ref_signal(oracle):
     return amp * base
 
 
-def _env_config(oracle, x0, fault):
+def _env_config(oracle, x0, fault, tracked="alpha"):
     return {"state_dim": 2, "action_dim": 1, "x0": x0, "dt": 0.02, "t_end": 60, "fault_time": 20,
-            "fault_scenario": fault, "reference": {"tracked_state": ["alpha"], "signal": [_ref_signal(oracle)]}}
+            "fault_scenario": fault, "reference": {"tracked_state": [tracked], "signal": [_ref_signal(oracle)]}}
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "sp_env_*.npz"))))
@@ -129,7 +129,7 @@ def test_actor_critic_calls_equal_oracle(oracle, policy, elig):
             assert np.array_equal(target.trainable_weights[1].double().cpu().numpy().reshape(n, 8), st["W2t"]), k
 
 
-@pytest.mark.parametrize("name", ["default_x0zero", "default_x0rand", "shiftcg_acc_1step", "invert_replacing"])
+@pytest.mark.parametrize("name", ["default_x0zero", "default_x0rand", "shiftcg_acc_1step", "invert_replacing", "trackq_damp"])
 def test_idhpsp_train_equals_reference_run(oracle, name):
     """IDHPsp(env, config).train() (BASELINE.json configs[0]: one agent, idhp_sp.py defaults) against golden runs of the
     VERBATIM reference agent (objects.py's IDHPsp on the TensorFlow stand-in, verbatim env + RLS; oracle/make_golden.py)."""
@@ -142,7 +142,7 @@ def test_idhpsp_train_equals_reference_run(oracle, name):
     ic["actor_config"]["elig"] = ELIG[str(g["elig_a"])]
     ic["critic_config"]["elig"] = ELIG[str(g["elig_c"])]
     B = 2
-    env = Ce500ShortPeriod(_env_config(oracle, g["x0"].reshape(2, 1), FAULTS[str(g["fault"])]), batch=B, dtype="mixed")
+    env = Ce500ShortPeriod(_env_config(oracle, g["x0"].reshape(2, 1), FAULTS[str(g["fault"])], str(g["tracked"])), batch=B, dtype="mixed")
     w = {k: np.broadcast_to(g[f"w_{k}"], (B,) + g[f"w_{k}"].shape).copy() for k in ("W1a", "W2a", "W1c", "W2c")}
     idhp = IDHPsp(env, ic, verbose=0, seed=4, weights=w, log="full", log_agents=B)
     steps = int(g["steps"])
