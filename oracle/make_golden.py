@@ -206,6 +206,33 @@ def nl_loop_fixture(seed, *, fault="none", fault_time=60, integrator="ode5", eli
     return out
 
 
+def mc_run_seed_fixture(seed=3, steps=3000):
+    """Output dict of the VERBATIM functions.MC_run_seed (functions.py:39-60: IDHPsp run + per-step norms, episode return,
+    convergence time) on the TensorFlow stand-in; the initial weights its IDHPsp drew are recorded as inputs."""
+    import contextlib
+    import io
+
+    Fn = ref_loader.load_reference_functions()
+    O, tf = ref_loader.load_reference_objects()
+    Env = ref_loader.load_reference_linear_env()
+    base, amp = sp_c.default_reference()
+    ic = sp_c.default_idhp_config()
+    env = Env({"state_dim": 2, "action_dim": 1, "x0": np.zeros((2, 1)), "dt": 0.02, "t_end": steps * 0.02, "fault_time": 20,
+               "fault_scenario": None, "reference": {"tracked_state": ["alpha"], "signal": [amp * base]}})
+    tf.set_tanh(lambda a: sp_c.tanh_t13(np.asarray(a, dtype=np.float32)))
+    try:
+        probe = O.IDHPsp(env, ic, verbose=False, seed=seed)       # same seed -> the weights MC_run_seed's own agent will draw
+        w = {"W1a": probe.actor.get_weights()[0].ravel(), "W2a": probe.actor.get_weights()[1].ravel(),
+             "W1c": probe.critic.get_weights()[0].ravel(), "W2c": probe.critic.get_weights()[1].ravel()}
+        with contextlib.redirect_stdout(io.StringIO()):
+            out = Fn.MC_run_seed(seed, env, ic)
+    finally:
+        tf.set_tanh(None)
+    res = {f"out_{k}": np.asarray(v, dtype=np.float64) for k, v in out.items()}
+    res.update(seed=seed, steps=steps, **{f"w_{k}": np.asarray(v, dtype=np.float64) for k, v in w.items()})
+    return res
+
+
 def utils_fixture():
     """Outputs of the verbatim utils.py functions (samplers with true_random=False, PSD, convergence time, VD_A, KL)."""
     U = ref_loader.load_reference_utils()
@@ -247,6 +274,7 @@ def main():
     for i, (f, integ) in enumerate([("none", "ode5"), ("damp_elevator_and_saturate_elevator", "ode5"), ("shift_cg", "rk4"),
                                     ("slow_all", "ode5"), ("damp_all", "ode5"), ("saturate_aileron", "rk4")]):
         np.savez_compressed(os.path.join(OUT, f"nl_env_{f}.npz"), **nl_env_fixture(f, 200 + i, integrator=integ))
+    np.savez_compressed(os.path.join(OUT, "sp_mc_run_seed.npz"), **mc_run_seed_fixture())
     nl_cases = {"default": dict(seed=41), "ms_notrace_rk4": dict(seed=42, ms=1, elig=None, integrator="rk4"),
                 "replacing_fault": dict(seed=43, elig="replacing", fault="damp_elevator_and_saturate_elevator", fault_time=3.0)}
     for name, kw in nl_cases.items():

@@ -69,6 +69,7 @@ def _install_stubs() -> None:
         mpl = types.ModuleType("matplotlib")
         plt = types.ModuleType("matplotlib.pyplot")
         mpl.pyplot = plt
+        plt.rcParams = {}
         sys.modules["matplotlib"] = mpl
         sys.modules["matplotlib.pyplot"] = plt
 
@@ -189,3 +190,18 @@ def load_reference_objects():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod, tf_shim
+
+
+def load_reference_functions():
+    """Return the verbatim ``functions`` module (functions.py: MC_run_seed :39, MC_run :62, MC_test_hparam :931) on the
+    TensorFlow stand-in; its ``from objects import ...`` picks up the verbatim objects.py the same way."""
+    load_reference_objects()                            # installs the stand-in, stubs and sys.path
+    import importlib.util
+
+    if not hasattr(sys.modules["matplotlib.pyplot"], "rcParams"):
+        sys.modules["matplotlib.pyplot"].rcParams = {}
+    path = os.path.join(REFERENCE_ROOT, "functions.py")
+    spec = importlib.util.spec_from_file_location("_rl4afcs_ref_functions", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

@@ -341,8 +341,10 @@ class IDHPsp:
             self.c_e_hist = ce
             self.a_all_grad_hist = lg[:, :, LF["AGRAD"]:LF["AGRAD"] + 8]
             self.c_all_grad_hist = lg[:, :, LF["CGRAD"]:LF["CGRAD"] + 12]
-            self.a_grad_hist = torch.linalg.vector_norm(self.a_all_grad_hist[:, :, 0:4], dim=-1)   # objects.py:706
-            self.c_grad_hist = torch.linalg.vector_norm(self.c_all_grad_hist[:, :, 0:4], dim=-1)   # objects.py:707
+            # objects.py:706-707: np.linalg.norm of the W1 gradient as the network dtype holds it (a float32 norm in the mix)
+            tn = self._eng.tn
+            self.a_grad_hist = torch.linalg.vector_norm(self.a_all_grad_hist[:, :, 0:4].to(tn), dim=-1).to(lg.dtype)
+            self.c_grad_hist = torch.linalg.vector_norm(self.c_all_grad_hist[:, :, 0:4].to(tn), dim=-1).to(lg.dtype)
             self.params_hist = lg[:, :, LF["PARAMS"]:LF["PARAMS"] + 6]
             self.cov_hist = lg[:, :, LF["COV"]:LF["COV"] + 9]
             self.eps_norm_hist = lg[:, :, LF["EPS_NORM"]]

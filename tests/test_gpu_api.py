@@ -416,3 +416,36 @@ def test_idhpnonlin_train_equals_verbatim_reference_run(name):
         assert np.array_equal(idhp.actor.E[b].cpu().numpy().ravel(), g["final_E"])
         assert np.array_equal(idhp.target_critic.trainable_weights[1][b].double().cpu().numpy().ravel(), g["final_W2t"])
         assert np.allclose(float(idhp.RSE[0][b]), g["RSE_total"][0], rtol=1e-14)
+
+
+def test_mc_run_seed_equals_verbatim_reference(oracle):
+    """functions.MC_run_seed for one trained agent against the output dict of the VERBATIM functions.MC_run_seed
+    (functions.py:39-60, run on the TensorFlow stand-in; tests/golden/sp_mc_run_seed.npz): trajectories bit for bit,
+    per-step norms / episode return to rounding, convergence time exactly."""
+    from rl4afcs_b200 import functions as F
+    from rl4afcs_b200.envs.linear.env import Ce500ShortPeriod
+    from rl4afcs_b200.objects import IDHPsp
+
+    g = np.load(os.path.join(GOLD, "sp_mc_run_seed.npz"))
+    steps, B = int(g["steps"]), 2
+    env = Ce500ShortPeriod(_env_config(oracle, np.zeros((2, 1)), None), batch=B, dtype="mixed")
+    w = {k: np.broadcast_to(g[f"w_{k}"], (B,) + g[f"w_{k}"].shape).copy() for k in ("W1a", "W2a", "W1c", "W2c")}
+    idhp = IDHPsp(env, oracle.default_idhp_config(), verbose=0, seed=int(g["seed"]), weights=w, log="full", log_agents=B)
+    idhp.train(steps)
+    out = {k: v.cpu().numpy() for k, v in F.MC_run_seed(idhp).items()}
+    for b in range(B):
+        assert np.array_equal(out["x_array"][b], g["out_x_array"]) and np.array_equal(out["a_array"][b], g["out_a_array"])
+        assert np.array_equal(out["ref_hist"][b], g["out_ref_hist"])
+        nz = np.abs(g["out_c_array"]) > 0
+        assert (np.abs(out["c_array"][b] - g["out_c_array"])[nz] <= 2 * np.spacing(np.abs(g["out_c_array"][nz]))).all()
+        for k in ("wa_array", "wc_array"):
+            assert np.allclose(out[k][b], g[f"out_{k}"], rtol=1e-13, atol=0), k
+        for k in ("a_grad", "c_grad"):                                         # float32 norms (objects.py:706-707)
+            assert np.allclose(out[k][b], g[f"out_{k}"], rtol=5e-7, atol=0), k
+        for k in ("p_array", "cov_array", "eps_array"):                        # logged from step 2 on (objects.py:704)
+            assert np.allclose(out[k][b][2:], g[f"out_{k}"][2:], rtol=1e-13, atol=0), k
+        assert np.isclose(out["sum_c_array"][b], float(g["out_sum_c_array"]), rtol=1e-12)
+        assert out["converged_time"][b] == float(g["out_converged_time"])
+    st = idhp.stats()
+    assert float(st["converged_time"][0]) == float(g["out_converged_time"])     # the in-kernel statistic agrees too
+    assert np.isclose(float(st["sum_c"][0]), float(g["out_sum_c_array"]), rtol=1e-12)
