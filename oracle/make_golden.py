@@ -233,6 +233,61 @@ def mc_run_seed_fixture(seed=3, steps=3000):
     return res
 
 
+def mc_test_hparam_fixture(repetitions=2):
+    """The per-configuration `log` dict the VERBATIM functions.MC_test_hparam (functions.py:931-1060) hands to its plot
+    routine -- two algorithms x `repetitions` full 90 s nonlinear episodes on the TensorFlow stand-in / plant stand-in.
+    Summary numbers in full, trajectories every 25th sample.  Takes a few minutes."""
+    import contextlib
+    import io
+
+    from oracle import nl_c
+    Fn = ref_loader.load_reference_functions()
+    O, tf = ref_loader.load_reference_objects()
+    Env, stub = ref_loader.load_reference_nonlinear_env("ode5")
+    th = nl_c.theta_reference()
+    trim_input = np.array([-0.02855, 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.55, 0.55, 0])
+    trim_state = np.array([0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0])
+    env_config = {"state_dim": 4, "action_dim": 3, "trim_input": trim_input, "trim_state": trim_state, "dt": 0.01,
+                  "t_end": 90, "total_steps": 9000, "fault_time": 60, "fault_scenario": "shift_cg",
+                  "reference": {"tracked_state": ["phi", "theta", "psi"], "signal": [0 * th, th, 0 * th]}}
+    N = 2
+    configs = {"etaah": [35.0, 25.0], "etaal": [5.0, 5.0], "etach": [1.4, 1.0], "etacl": [0.7, 0.5], "lambda_hs": [0.95, 0.9],
+               "lambda_ls": [0.95, 0.8], "seeds": [0, 0], "ms": [0, 1], "elig": ["accumulating", None]}
+    noise = np.random.default_rng(77).standard_normal((repetitions, 9000)).astype(np.float32)
+    captured = []
+    Fn.MC_test_hparam_plot = lambda log, *a, **k: captured.append({kk: np.array(v) for kk, v in log.items()})
+    # the weights seed r draws (Actor_big then Critic_big, each from a fresh initializer with that seed)
+    weights = []
+    for r in range(repetitions):
+        env = Env(env_config)
+        probe = O.IDHPnonlin(env, {"gamma": 0.6, "multistep": 0, "lr_decay": 0.998, "lambda_h": 0.95, "lambda_l": 0.95, "kappa": [1, 2, 1],
+                                   "cooldown_time": 2.0, "sigma": 0.1, "warmup_time": 4, "error_thresh": 1, "tau": 0.02, "in_dims": 4,
+                                   "actor_config": {"layers": {10: "tanh", 1: "tanh"}, "eta_h": 1.0, "eta_l": 1.0, "elig": None},
+                                   "critic_config": {"layers": {10: "tanh", 3: "linear"}, "eta_h": 1.0, "eta_l": 1.0, "elig": 1233},
+                                   "rls_config": {"state_dim": 3, "action_dim": 1, "rls_gamma": 1, "rls_cov": 10 ** 6}}, verbose=False, seed=r)
+        weights.append({"W1a": probe.actor.get_weights()[0].ravel(), "W2a": probe.actor.get_weights()[1].ravel(),
+                        "W1c": probe.critic.get_weights()[0].ravel(), "W2c": probe.critic.get_weights()[1].ravel()})
+    tf.set_tanh(lambda v: sp_c.tanh_t13(np.asarray(v, dtype=np.float32)))
+    # noise stream: config 0 rep 0, rep 1, ..., config 1 rep 0, ... ; each run consumes 8999 draws (steps 1..8999)
+    tf.set_noise(np.concatenate([noise[r, 1:] for _ in range(N) for r in range(repetitions)]))
+    try:
+        env = Env(env_config)
+        with contextlib.redirect_stdout(io.StringIO()):
+            Fn.MC_test_hparam(configs, "unused/", env, N, repetitions, save=0, show=0)
+    finally:
+        tf.set_tanh(None); tf.set_noise(None)
+    out = dict(N=N, repetitions=repetitions, noise=noise, theta_ref=th, fault="shift_cg", fault_time=60,
+               **{f"cfg_{k}": np.array([str(x) for x in v]) if k == "elig" else np.asarray(v) for k, v in configs.items()})
+    for r, w in enumerate(weights):
+        for k, v in w.items():
+            out[f"w{r}_{k}"] = np.asarray(v, dtype=np.float64)
+    for i, lg in enumerate(captured):
+        for k, v in lg.items():
+            out[f"log{i}_{k}"] = v if v.ndim < 2 or v.shape[1] <= 2 else v[:, ::25]
+        out[f"log{i}_max_abs_nz"] = np.max(np.abs(lg["n_z"]), axis=1)
+    return out
+
+
 def utils_fixture():
     """Outputs of the verbatim utils.py functions (samplers with true_random=False, PSD, convergence time, VD_A, KL)."""
     U = ref_loader.load_reference_utils()
@@ -275,6 +330,8 @@ def main():
                                     ("slow_all", "ode5"), ("damp_all", "ode5"), ("saturate_aileron", "rk4")]):
         np.savez_compressed(os.path.join(OUT, f"nl_env_{f}.npz"), **nl_env_fixture(f, 200 + i, integrator=integ))
     np.savez_compressed(os.path.join(OUT, "sp_mc_run_seed.npz"), **mc_run_seed_fixture())
+    if "--skip-slow" not in sys.argv:
+        np.savez_compressed(os.path.join(OUT, "nl_mc_test_hparam.npz"), **mc_test_hparam_fixture())
     nl_cases = {"default": dict(seed=41), "ms_notrace_rk4": dict(seed=42, ms=1, elig=None, integrator="rk4"),
                 "replacing_fault": dict(seed=43, elig="replacing", fault="damp_elevator_and_saturate_elevator", fault_time=3.0)}
     for name, kw in nl_cases.items():

@@ -99,7 +99,8 @@ _ALGOS = {(0, None): "idhp", (0, "replacing"): "idhprt", (0, "accumulating"): "i
           (1, None): "midhp", (1, "replacing"): "midhprt", (1, "accumulating"): "midhpat"}       # functions.py:933,959-972
 
 
-def MC_test_hparam(configs, directory, env, N, repetitions, save=0, show=0, transparency=0.2, *, noise=None, flight_step=5500):
+def MC_test_hparam(configs, directory, env, N, repetitions, save=0, show=0, transparency=0.2, *, noise=None, weights=None,
+                   flight_step=5500, numpy2=False):
     """Nonlinear-task Monte-Carlo of functions.py:931-1060: ``N`` hyper-parameter sets (``configs`` = dict of lists with
     the reference's keys etaah, etaal, etach, etacl, lambda_hs, lambda_ls, seeds, ms, elig) x ``repetitions`` seeds, run
     as ONE batch of N * repetitions agents (agent index = config * repetitions + seed).
@@ -107,6 +108,8 @@ def MC_test_hparam(configs, directory, env, N, repetitions, save=0, show=0, tran
     ``env``: a batched ``Ce500NonLinear`` with ``batch == N * repetitions``.  As in the reference, repetition r of every
     configuration starts from the same seed-r initial weights and sees the same seed-r noise stream.  ``directory``,
     ``save``, ``show``, ``transparency`` are accepted for call compatibility (plotting / pickling are out of scope).
+    ``weights`` (dict of (B, w) arrays) / ``noise`` ((steps, B) float32) replace the internally drawn ones; ``numpy2`` selects the
+    NEP 50 promotion rules in `_adapt_check` (see IDHPnonlin).
     Returns a list of (algo, idhp_config, log) with log = the dict of functions.py:1008-1021 as torch tensors
     (angles in degrees, as stored there) plus ``'max_nz'``.
     """
@@ -134,11 +137,12 @@ def MC_test_hparam(configs, directory, env, N, repetitions, save=0, show=0, tran
             out = torch.where(bad, torch.randn((repetitions, w), generator=g, device=dev, dtype=torch.float32), out)
             bad = out.abs() > 2.0
         return (out * 0.1).double().repeat(N, 1)
-    weights = {"W1a": draw(40), "W2a": draw(10), "W1c": draw(40), "W2c": draw(30)}
+    if weights is None:
+        weights = {"W1a": draw(40), "W2a": draw(10), "W1c": draw(40), "W2c": draw(30)}
     if noise is None:
         noise = torch.randn((total_steps, repetitions), generator=g, device=dev, dtype=torch.float32).repeat(1, N)
     env._engine.set_hpi("FLIGHT_STEP", int(flight_step))
-    idhp = IDHPnonlin(env, idhp_config, verbose=0, seed=0, weights=weights, log="mc", log_agents=B)
+    idhp = IDHPnonlin(env, idhp_config, verbose=0, seed=0, weights=weights, log="mc", log_agents=B, numpy2=numpy2)
     idhp.train(noise=noise)
     st, lg, dt = idhp.stats(), idhp.log, env.dt
     flight = lg["theta"][:, flight_step:]
@@ -149,7 +153,8 @@ def MC_test_hparam(configs, directory, env, N, repetitions, save=0, show=0, tran
     full = {"RSE": torch.stack([st["rse"][:, 0] - st["rse_flight"][:, 0], st["rse_flight"][:, 0]], dim=-1),   # :1036-1037
             "e": torch.rad2deg(lg["e"]), "theta": torch.rad2deg(lg["theta"]), "alpha": torch.rad2deg(lg["alpha"]),
             "q": torch.rad2deg(lg["q"]), "V": lg["v"], "h": lg["h"], "action_cmd": torch.rad2deg(lg["a_cmd"]),
-            "action_eff": torch.rad2deg(lg["a_eff"]), "n_z": lg["v"] * lg["q"] / 9.80665,
+            "action_eff": torch.rad2deg(lg["a_eff"]),
+            "n_z": torch.div(lg["v"] * lg["q"], torch.full_like(lg["v"], 9.80665)),   # a true division (scalar divisors become reciprocal multiplies)
             "wa_norm": nrm(lg["wa_norm"]), "wc_norm": nrm(lg["wc_norm"]), "Sm": Sm.unsqueeze(-1), "rls_eps": lg["rls_eps"],
             "max_nz": st["nz_peak"]}
     out = []

@@ -449,3 +449,34 @@ def test_mc_run_seed_equals_verbatim_reference(oracle):
     st = idhp.stats()
     assert float(st["converged_time"][0]) == float(g["out_converged_time"])     # the in-kernel statistic agrees too
     assert np.isclose(float(st["sum_c"][0]), float(g["out_sum_c_array"]), rtol=1e-12)
+
+
+def test_mc_test_hparam_equals_verbatim_reference():
+    """functions.MC_test_hparam (2 algorithms x 2 repetitions of the full 90 s nonlinear flight with a c.g.-shift fault,
+    one batch of 4 agents) against the `log` dict the VERBATIM functions.MC_test_hparam produced on the TensorFlow /
+    plant stand-ins (tests/golden/nl_mc_test_hparam.npz): trajectories bit for bit (every 25th sample stored),
+    RSE warm-up / flight, peak n_z, normalised weight norms and the smoothness index to rounding."""
+    from rl4afcs_b200 import functions as F
+    from rl4afcs_b200.envs.nonlinear.env import Ce500NonLinear
+
+    g = np.load(os.path.join(GOLD, "nl_mc_test_hparam.npz"))
+    N, reps = int(g["N"]), int(g["repetitions"])
+    B = N * reps
+    env = Ce500NonLinear(_nl_env_config(g["theta_ref"], fault_scenario=str(g["fault"]), fault_time=float(g["fault_time"])), batch=B,
+                         dtype="mixed")
+    elig = [None if e == "None" else str(e) for e in g["cfg_elig"]]
+    configs = {k: list(g[f"cfg_{k}"]) for k in ("etaah", "etaal", "etach", "etacl", "lambda_hs", "lambda_ls", "seeds", "ms")}
+    configs["elig"] = elig
+    w = {k: np.stack([g[f"w{r}_{k}"] for _ in range(N) for r in range(reps)]) for k in ("W1a", "W2a", "W1c", "W2c")}
+    noise = np.stack([g["noise"][r] for _ in range(N) for r in range(reps)], axis=1)           # (9000, B)
+    out = F.MC_test_hparam(configs, "unused/", env, N, reps, noise=noise, weights=w, numpy2=True)
+    assert [o[0] for o in out] == ["idhpat", "midhp"]
+    for i, (algo, cfg, log) in enumerate(out):
+        lg = {k: v.cpu().numpy() for k, v in log.items()}
+        for k in ("e", "theta", "alpha", "q", "V", "h", "action_cmd", "action_eff", "n_z", "rls_eps"):
+            assert np.array_equal(lg[k][:, ::25], g[f"log{i}_{k}"], equal_nan=True), (algo, k)
+        for k in ("wa_norm", "wc_norm"):
+            assert np.allclose(lg[k][:, ::25], g[f"log{i}_{k}"], rtol=1e-13, atol=0, equal_nan=True), (algo, k)
+        assert np.allclose(lg["RSE"], g[f"log{i}_RSE"], rtol=1e-11, atol=0), algo
+        assert np.allclose(lg["Sm"], g[f"log{i}_Sm"], rtol=1e-9, atol=0), algo
+        assert np.allclose(lg["max_nz"], g[f"log{i}_max_abs_nz"], rtol=1e-15, atol=0), algo
