@@ -233,6 +233,73 @@ def mc_run_seed_fixture(seed=3, steps=3000):
     return res
 
 
+def mc_run_fixture(seeds=10):
+    """`metrics` of the VERBATIM functions.MC_run (functions.py:62-232) for two hyper-parameter sets x 10 seeds of the full
+    short-period episode.  The process pool is replaced by a serial stand-in, pickling / plotting by a capture hook; the
+    weights each seed draws are recorded as inputs.  The second set has a large critic rate so that some seeds (3 of 10) diverge."""
+    import contextlib
+    import io
+
+    Fn = ref_loader.load_reference_functions()
+    O, tf = ref_loader.load_reference_objects()
+    Env = ref_loader.load_reference_linear_env()
+    base, amp = sp_c.default_reference()
+    env_config = {"state_dim": 2, "action_dim": 1, "x0": np.zeros((2, 1)), "dt": 0.02, "t_end": 60, "fault_time": 20,
+                  "fault_scenario": None, "reference": {"tracked_state": ["alpha"], "signal": [amp * base]}}
+    configs = {"lambda_hs": [0.576, 0.6], "lambda_ls": [0.296, 0.2], "kappas": [1140, 800], "cooldown_times": None, "sigmas": None,
+               "warmup_times": None, "elig_a": [None, "accumulating"], "lr_a_hs": [3.55, 4.5], "lr_a_ls": [0.054, 0.05],
+               "lr_c_hs": [0.338, 0.8], "lr_c_ls": None, "multistep": [2, 0]}
+
+    class _Res:
+        def __init__(self, v):
+            self.v = v
+
+        def get(self):
+            return self.v
+
+    class _SerialPool:
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def apply_async(self, fn, args=()):
+            return _Res(fn(*args))
+
+        def close(self):
+            pass
+
+        def join(self):
+            pass
+    captured = []
+    Fn.Pool = _SerialPool
+    Fn.MC_pickling = lambda directory, arrays, idhp_config, metrics, save: captured.append(
+        (dict(metrics), {k: np.array(arrays[k]) for k in ("sum_c_array", "converged_time")}))
+    Fn.MC_plotting = lambda *a, **k: None
+    tf.set_tanh(lambda a: sp_c.tanh_t13(np.asarray(a, dtype=np.float32)))
+    try:
+        env = Env(env_config)
+        ws = []
+        for s_ in range(seeds):
+            probe = O.IDHPsp(env, sp_c.default_idhp_config(), verbose=False, seed=s_)
+            ws.append(np.concatenate([probe.actor.get_weights()[0].ravel(), probe.actor.get_weights()[1].ravel(),
+                                      probe.critic.get_weights()[0].ravel(), probe.critic.get_weights()[1].ravel()]))
+        with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+            Fn.MC_run(2, configs, env, env_config, seeds, 0.3, "unused/", save=False)
+    finally:
+        tf.set_tanh(None)
+    out = dict(seeds=seeds, weights=np.array(ws, dtype=np.float64))          # (seeds, 4 + 4 + 4 + 8)
+    for k, v in configs.items():
+        out[f"cfg_{k}"] = np.array(["None" if x is None else str(x) for x in v]) if (v is not None and k == "elig_a") else (
+            np.asarray(v, dtype=np.float64) if v is not None else np.array("None"))
+    for i, (m, arr) in enumerate(captured):
+        for k, v in m.items():
+            out[f"metrics{i}_{k}"] = np.asarray(v, dtype=np.float64)
+        out[f"arrays{i}_sum_c"] = arr["sum_c_array"]; out[f"arrays{i}_converged_time"] = arr["converged_time"]
+    return out
+
+
 def mc_test_hparam_fixture(repetitions=2):
     """The per-configuration `log` dict the VERBATIM functions.MC_test_hparam (functions.py:931-1060) hands to its plot
     routine -- two algorithms x `repetitions` full 90 s nonlinear episodes on the TensorFlow stand-in / plant stand-in.
@@ -332,6 +399,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "sp_mc_run_seed.npz"), **mc_run_seed_fixture())
     if "--skip-slow" not in sys.argv:
         np.savez_compressed(os.path.join(OUT, "nl_mc_test_hparam.npz"), **mc_test_hparam_fixture())
+        np.savez_compressed(os.path.join(OUT, "sp_mc_run.npz"), **mc_run_fixture())
     nl_cases = {"default": dict(seed=41), "ms_notrace_rk4": dict(seed=42, ms=1, elig=None, integrator="rk4"),
                 "replacing_fault": dict(seed=43, elig="replacing", fault="damp_elevator_and_saturate_elevator", fault_time=3.0)}
     for name, kw in nl_cases.items():

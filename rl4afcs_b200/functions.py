@@ -38,12 +38,14 @@ def MC_run_seed(idhp: IDHPsp) -> dict:
     return out
 
 
-def MC_run(n_configs, configs, env_config, seeds, *, device="cuda", dtype="mixed", base_seed=0, log_agents=0):
+def MC_run(n_configs, configs, env_config, seeds, *, device="cuda", dtype="mixed", base_seed=0, log_agents=0, weights=None):
     """Monte-Carlo over ``n_configs`` hyper-parameter sets x ``seeds`` seeds in ONE batch (functions.py:62-232 ran
     a process pool of 10).  ``configs`` has the reference's keys (lambda_hs, lambda_ls, kappas, cooldown_times, sigmas,
     warmup_times, elig_a, lr_a_hs, lr_a_ls, lr_c_hs, lr_c_ls, multistep), each None or a list per config.
     Returns (metrics per config, idhp): metrics = dict(avg_PSD_err?, avg_c, avg_t, diverged, unsteady_convergence)
-    as functions.py:223-227 (PSD error only when trajectories are logged)."""
+    as functions.py:223-227 (PSD error only when trajectories are logged).  ``weights``: optional dict of (B, w) initial
+    weights (agent index = config * seeds + seed).  Like the reference, ``avg_c`` averages the non-diverged runs while
+    ``avg_t`` averages ALL runs (its second `np.delete`, functions.py:178, filters on an array that no longer has NaNs)."""
     dflt = dict(lambda_hs=0.34, lambda_ls=0.0, kappas=1200, cooldown_times=2.0, sigmas=0.1, warmup_times=3.0, elig_a=None,
                 lr_a_hs=3.0, lr_a_ls=0.05, lr_c_hs=0.5, lr_c_ls=0.0, multistep=0)          # functions.py:75-86
 
@@ -68,7 +70,8 @@ def MC_run(n_configs, configs, env_config, seeds, *, device="cuda", dtype="mixed
                    "rls_config": {"state_dim": env_config["state_dim"], "action_dim": env_config["action_dim"],
                                   "rls_gamma": 1, "rls_cov": 10 ** 6}}
     env = Ce500ShortPeriod(env_config, batch=B, device=device, dtype=dtype)
-    idhp = IDHPsp(env, idhp_config, verbose=0, seed=base_seed, log="full" if log_agents else None, log_agents=log_agents)
+    idhp = IDHPsp(env, idhp_config, verbose=0, seed=base_seed, weights=weights, log="full" if log_agents else None,
+                  log_agents=log_agents)
     idhp.train()
     st = idhp.stats()
     metrics = []
@@ -79,7 +82,7 @@ def MC_run(n_configs, configs, env_config, seeds, *, device="cuda", dtype="mixed
         conv = st["converged_time"][sl]
         m = {"diverged": int(div.sum()), "unsteady_convergence": int((conv > 30).sum()),                # functions.py:161-166
              "avg_c": float(np.around(float(st["sum_c"][sl][ok].mean()) if bool(ok.any()) else np.nan, 4)),
-             "avg_t": float(np.around(float(conv[ok].mean()) if bool(ok.any()) else np.nan, 4))}
+             "avg_t": float(np.around(float(conv.mean()), 4))}                                          # functions.py:178,182
         metrics.append(m)
     if log_agents:
         dt, t_end = env_config["dt"], env_config["t_end"]

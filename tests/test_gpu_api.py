@@ -480,3 +480,36 @@ def test_mc_test_hparam_equals_verbatim_reference():
         assert np.allclose(lg["RSE"], g[f"log{i}_RSE"], rtol=1e-11, atol=0), algo
         assert np.allclose(lg["Sm"], g[f"log{i}_Sm"], rtol=1e-9, atol=0), algo
         assert np.allclose(lg["max_nz"], g[f"log{i}_max_abs_nz"], rtol=1e-15, atol=0), algo
+
+
+def test_mc_run_metrics_equal_verbatim_reference(oracle):
+    """functions.MC_run (2 hyper-parameter sets x 10 seeds in one batch) against the `metrics` dict of the VERBATIM
+    functions.MC_run (functions.py:62-232; process pool replaced by a serial stand-in, tests/golden/sp_mc_run.npz): counts
+    of diverged / late-converging runs, average return over the survivors, average convergence time, PSD error."""
+    from rl4afcs_b200 import functions as F
+
+    g = np.load(os.path.join(GOLD, "sp_mc_run.npz"))
+    seeds, n_cfg = int(g["seeds"]), 2
+    base, amp = oracle.default_reference()
+    env_config = {"state_dim": 2, "action_dim": 1, "x0": np.zeros((2, 1)), "dt": 0.02, "t_end": 60, "fault_time": 20,
+                  "fault_scenario": None, "reference": {"tracked_state": ["alpha"], "signal": [amp * base]}}
+    configs = {}
+    for k in ("lambda_hs", "lambda_ls", "kappas", "cooldown_times", "sigmas", "warmup_times", "lr_a_hs", "lr_a_ls", "lr_c_hs", "lr_c_ls",
+              "multistep"):
+        v = g[f"cfg_{k}"]
+        configs[k] = None if v.ndim == 0 else [float(x) for x in v]
+    configs["multistep"] = [int(x) for x in configs["multistep"]]
+    configs["elig_a"] = [None if e == "None" else str(e) for e in g["cfg_elig_a"]]
+    W = np.tile(g["weights"], (n_cfg, 1))                                    # agent = config * seeds + seed
+    w = {"W1a": W[:, 0:4], "W2a": W[:, 4:8], "W1c": W[:, 8:12], "W2c": W[:, 12:20]}
+    metrics, idhp = F.MC_run(n_cfg, configs, env_config, seeds, dtype="mixed", log_agents=n_cfg * seeds, weights=w)
+    st = idhp.stats()
+    for c in range(n_cfg):
+        m = metrics[c]
+        assert m["diverged"] == int(g[f"metrics{c}_diverged"]) and m["unsteady_convergence"] == int(g[f"metrics{c}_unsteady_convergence"])
+        assert m["avg_c"] == float(g[f"metrics{c}_avg_c"]) and m["avg_t"] == float(g[f"metrics{c}_avg_t"])
+        assert np.isclose(m["avg_PSD_err"], float(g[f"metrics{c}_avg_PSD_err"]), rtol=1e-6)
+        sl = slice(c * seeds, (c + 1) * seeds)
+        assert np.array_equal(st["converged_time"][sl].cpu().numpy(), g[f"arrays{c}_converged_time"])
+        ok = ~st["diverged"][sl].cpu().numpy()
+        assert np.allclose(st["sum_c"][sl].cpu().numpy()[ok], g[f"arrays{c}_sum_c"], rtol=1e-12)
