@@ -85,8 +85,8 @@ __device__ __forceinline__ void sp_env_step(Rn<TE> (&x)[2], Rn<TN> action_deg, R
     const Rn<TN> u_n = action_deg * Rn<TN>(Consts<TN>::deg2rad());   // env.py:176
     const E u = cvt<TE>(u_n);
     // env.py:179  y = C@x + D*action with C = I, D = 0; env.py:180-184: error = ref - y[0] ('alpha') or ref - y[1] ('q')
-    const E y = tracked_q ? (fma(E(TE(0)), x[0], E(TE(1)) * x[1]) + E(TE(0)) * u)
-                          : (fma(E(TE(0)), x[1], E(TE(1)) * x[0]) + E(TE(0)) * u);
+    const E xt = tracked_q ? x[1] : x[0], xo = tracked_q ? x[0] : x[1];   // tracked / other state: one expression, two selects
+    const E y = fma(E(TE(0)), xo, E(TE(1)) * xt) + E(TE(0)) * u;
     e = ref - y;
     cost = (E(TE(-0.5)) * kappa) * (e * e);                           // env.py:187
     rg0 = kappa * (E(TE(-2)) * e);                                    // env.py:189
