@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "-fmad=false",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared",     # host pass: no contraction either (trim solve / reset)
     "-Xptxas", "-v",
     "--threads", "4",          # the three translation units compile in parallel
 ]

@@ -588,10 +588,25 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
 #undef NF
 }
 
+// Ce500NonLinear.reset (envs/nonlinear/env.py:278-291): the model's built-in initial state, then 1000 + 1 steps at trim
+// input.  Every agent shares the plant and the trim input, and the plant is IEEE-basic-operations only, so the 1001 steps
+// are integrated ONCE on the host (same header, same bits as on the device) and broadcast by the init kernel.
+struct NlTrim { double x[12]; };
+static NlTrim nl_trim_on_host(const rl4_nl_params* p)
+{
+    NlTrim t = {{0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0}};
+    const int n_trim = (int)(10.0 / p->dt) + 1;
+    for (int k = 0; k < n_trim; ++k) {
+        if (p->integrator == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(&p->plant, t.x, p->trim_input, p->dt);
+        else rl4_cit_step_ode5(&p->plant, t.x, p->trim_input, p->dt);
+    }
+    return t;
+}
+
 // Ce500NonLinear.reset + IDHPnonlin prologue
 template <typename TN>
 __global__ void __launch_bounds__(128)
-nl_init_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict__ w1a, const double* __restrict__ w2a,
+nl_init_kernel(const __grid_constant__ rl4_nl_params p, const NlTrim trim, const double* __restrict__ w1a, const double* __restrict__ w2a,
                const double* __restrict__ w1c, const double* __restrict__ w2c, int64_t stride_in, const rl4_nl_state st, int64_t n_agents)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -602,14 +617,8 @@ nl_init_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict
     TN* Nn = (TN*)st.net + i;
     for (int f = 0; f < RL4_NLE_COUNT; ++f) E[(int64_t)f * S] = 0.0;
     for (int f = 0; f < RL4_NLN_COUNT; ++f) Nn[(int64_t)f * S] = TN(0);
-    // reset: the model's built-in initial state, then 1000 + 1 steps at trim input (env.py:278-291)
-    double x[12] = {0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0};
-    const int n_trim = (int)(10.0 / p.dt) + 1;
-    for (int k = 0; k < n_trim; ++k) {
-        if (p.integrator == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(&p.plant, x, p.trim_input, p.dt);
-        else rl4_cit_step_ode5(&p.plant, x, p.trim_input, p.dt);
-    }
-    for (int j = 0; j < 12; ++j) E[(int64_t)(RL4_NLE_XFULL + j) * S] = x[j];
+    // reset (env.py:278-291): the trimmed state is the same for every agent and was integrated once on the host
+    for (int j = 0; j < 12; ++j) E[(int64_t)(RL4_NLE_XFULL + j) * S] = trim.x[j];
     const double c0 = hv.hp(RL4_NHP_RLS_COV0);
     for (int d = 0; d < 4; ++d) E[(int64_t)(RL4_NLE_COV + d * 5) * S] = c0;
     E[(int64_t)RL4_NLE_ETA_A * S] = hv.hp(RL4_NHP_ETA_A_H);
@@ -788,8 +797,9 @@ int rl4_nl_init(int policy, const rl4_nl_params* p, const double* w1a, const dou
     if (n == 0) return 0;
     const unsigned grid = (unsigned)((n + 127) / 128);
     cudaStream_t s = (cudaStream_t)stream;
-    if (policy == RL4_MIXED) nl_init_kernel<float><<<grid, 128, 0, s>>>(*p, w1a, w2a, w1c, w2c, stride_in, st, n);
-    else if (policy == RL4_FP64) nl_init_kernel<double><<<grid, 128, 0, s>>>(*p, w1a, w2a, w1c, w2c, stride_in, st, n);
+    const NlTrim trim = nl_trim_on_host(p);
+    if (policy == RL4_MIXED) nl_init_kernel<float><<<grid, 128, 0, s>>>(*p, trim, w1a, w2a, w1c, w2c, stride_in, st, n);
+    else if (policy == RL4_FP64) nl_init_kernel<double><<<grid, 128, 0, s>>>(*p, trim, w1a, w2a, w1c, w2c, stride_in, st, n);
     else { set_error("rl4_nl_init: policy %d not supported on the nonlinear path (mixed or fp64)", policy); return -1; }
     return check_launch("nl_init_kernel");
 }
