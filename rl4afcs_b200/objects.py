@@ -240,12 +240,15 @@ class IDHPsp:
     Every numeric entry of ``config`` may be a per-agent array (hyper-parameter sweeps).  Extra
     keyword arguments: ``weights`` (dict W1a (B,4), W2a (B,4), W1c (B,4), W2c (B,8); default:
     TruncatedNormal(sigma) drawn on the device from ``seed``), ``log`` ('full' | 'basic' | None),
-    ``log_agents`` (how many leading agents are logged), ``log_every``.
+    ``log_agents`` (how many leading agents are logged), ``log_every``; ``numpy2`` selects how `_adapt_check`'s
+    `eta_a != self.eta_a` (objects.py:819) compares a float32 with a python float: numpy 1.x value-based promotion (the
+    reference's era, default: the comparison is True at k = 1 and a cooldown starts) or NEP 50 (numpy >= 2).
     """
 
     def __init__(self, env, config, verbose=True, seed=1, *, weights=None, log="full", log_agents=None,
-                 log_every: int = 1, ref_amp=None) -> None:
+                 log_every: int = 1, ref_amp=None, numpy2: bool = False) -> None:
         self.seed = seed
+        env._engine.params.q7_numpy1 = 0 if numpy2 else 1   # Q7: float32-vs-python-float compare at k = 1 (numpy 1.x) or NEP 50
         self.gamma = config["gamma"]
         self.tau = config["tau"]
         self.ms = config["multistep"]
