@@ -144,7 +144,7 @@ def test_idhpsp_train_equals_reference_run(oracle, name):
     B = 2
     env = Ce500ShortPeriod(_env_config(oracle, g["x0"].reshape(2, 1), FAULTS[str(g["fault"])], str(g["tracked"])), batch=B, dtype="mixed")
     w = {k: np.broadcast_to(g[f"w_{k}"], (B,) + g[f"w_{k}"].shape).copy() for k in ("W1a", "W2a", "W1c", "W2c")}
-    idhp = IDHPsp(env, ic, verbose=0, seed=4, weights=w, log="full", log_agents=B)
+    idhp = IDHPsp(env, ic, verbose=0, seed=4, weights=w, log="full", log_agents=B, numpy2=True)   # fixtures ran under numpy >= 2
     steps = int(g["steps"])
     idhp.train(steps)
     for b in range(B):

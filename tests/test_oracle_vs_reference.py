@@ -58,12 +58,13 @@ def test_c_oracle_equals_numpy_loop_on_verbatim_objects(oracle, seed, fault, eli
         assert np.array_equal(lg[k][2:], cl[k][2:], equal_nan=True), k
 
 
-@pytest.mark.parametrize("seed,fault,elig,ms,tanh,steps", [
-    (31, None, (None, None), 2, "t13", 3000),                                   # full default episode: LR switch, RLS reset
-    (32, "damp_elevator", ("accumulating", None), 0, "libm", 1300),
-    (33, "invert_elevator", ("replacing", "accumulating"), 2, "t13", 1300),
+@pytest.mark.parametrize("seed,fault,elig,ms,tanh,steps,warmup", [
+    (31, None, (None, None), 2, "t13", 3000, 3.0),                              # full default episode: LR switch, RLS reset
+    (32, "damp_elevator", ("accumulating", None), 0, "libm", 1300, 3.0),
+    (33, "invert_elevator", ("replacing", "accumulating"), 2, "t13", 1300, 3.0),
+    (34, None, (None, None), 2, "t13", 900, 1.0),       # warm-up shorter than the cooldown: the case where Q7 (numpy 1.x) would matter
 ])
-def test_c_oracle_equals_verbatim_idhpsp_on_tf_standin(oracle, seed, fault, elig, ms, tanh, steps):
+def test_c_oracle_equals_verbatim_idhpsp_on_tf_standin(oracle, seed, fault, elig, ms, tanh, steps, warmup):
     """The reference's OWN agent code -- objects.py's IDHPsp.train(), Actor / Critic call and trace code, RLS,
     _adapt_check, _log -- executed unmodified on the TensorFlow stand-in (oracle/tf_shim.py supplies only the arithmetic
     of the TF ops) around the verbatim Ce500ShortPeriod, against the C oracle: every logged quantity
@@ -71,7 +72,7 @@ def test_c_oracle_equals_verbatim_idhpsp_on_tf_standin(oracle, seed, fault, elig
     O, tf = ref_loader.load_reference_objects()
     Env = ref_loader.load_reference_linear_env()
     base, amp = oracle.default_reference()
-    ic = oracle.default_idhp_config(); ic["multistep"] = ms
+    ic = oracle.default_idhp_config(); ic["multistep"] = ms; ic["warmup_time"] = warmup
     ic["actor_config"]["elig"], ic["critic_config"]["elig"] = elig
     rng = np.random.default_rng(seed)
     x0 = np.deg2rad(rng.uniform(-2, 2, size=2))
