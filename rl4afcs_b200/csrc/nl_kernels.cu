@@ -688,11 +688,8 @@ static int nl_launch_one(const rl4_nl_params* p, const double* theta_ref, const 
                          int n_steps, rl4_nl_state st, int64_t n, rl4_sp_log lg, unsigned grid, cudaStream_t s)
 {
     const size_t smem = (sizeof(double) * kNlSmemDoubles + sizeof(TN) * kNlSmemNet) * RL4_NL_BLOCK;
-    static bool configured = false;
-    if (!configured) {
-        RL4_CUDA(cudaFuncSetAttribute(nl_run_kernel<TN, INTEG, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // per launch: the attribute is per device and per function, and setting it costs microseconds
+    RL4_CUDA(cudaFuncSetAttribute(nl_run_kernel<TN, INTEG, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nl_run_kernel<TN, INTEG, LOG><<<grid, RL4_NL_BLOCK, smem, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg);
     return 0;
 }

@@ -21,6 +21,7 @@ void set_error(const char* fmt, ...)
 int cuda_fail(cudaError_t e, const char* what)
 {
     set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    (void)cudaGetLastError();        // a non-sticky error (e.g. out of memory) must not be reported again by the next launch check
     return (int)e;
 }
 

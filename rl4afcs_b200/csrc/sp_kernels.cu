@@ -548,6 +548,8 @@ struct rl4_ctx {
     size_t te, tn;
 };
 
+int rl4_ctx_destroy(rl4_ctx* c);
+
 int rl4_ctx_create(int device, int policy, int64_t max_agents, int32_t max_steps, rl4_ctx** out)
 {
     RL4_REQUIRE(out != nullptr, "out is NULL");
@@ -556,17 +558,25 @@ int rl4_ctx_create(int device, int policy, int64_t max_agents, int32_t max_steps
     int rc = rl4_device_check(device);
     if (rc) return rc;
     RL4_CUDA(cudaSetDevice(device));
-    rl4_ctx* c = new rl4_ctx();
+    rl4_ctx* c = new rl4_ctx();                        // value-initialised: every handle / pointer starts as null
     c->device = device; c->policy = policy; c->max_agents = max_agents; c->max_steps = max_steps;
     c->te = (policy == RL4_FP32) ? 4 : 8;
     c->tn = (policy == RL4_FP64) ? 8 : 4;
-    for (int i = 0; i < rl4_ctx::kStreams; ++i) RL4_CUDA(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking));
-    RL4_CUDA(cudaEventCreateWithFlags(&c->ref_ready, cudaEventDisableTiming));
-    RL4_CUDA(cudaMalloc(&c->d_in, sizeof(double) * 22 * max_agents));
-    RL4_CUDA(cudaMalloc(&c->d_ref, sizeof(double) * max_steps));
-    RL4_CUDA(cudaMalloc(&c->d_env, c->te * RL4_SPE_COUNT * max_agents));
-    RL4_CUDA(cudaMalloc(&c->d_net, c->tn * RL4_SPN_COUNT * max_agents));
-    RL4_CUDA(cudaMalloc(&c->d_ints, sizeof(int32_t) * RL4_SPI_COUNT * max_agents));
+    // a failing allocation must not leak the handles created before it: collect the first error, then destroy
+    cudaError_t err = cudaSuccess;
+    const char* what = "";
+    auto step = [&](cudaError_t e, const char* w) { if (err == cudaSuccess && e != cudaSuccess) { err = e; what = w; } };
+    for (int i = 0; i < rl4_ctx::kStreams; ++i) step(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking), "cudaStreamCreateWithFlags");
+    step(cudaEventCreateWithFlags(&c->ref_ready, cudaEventDisableTiming), "cudaEventCreateWithFlags");
+    if (err == cudaSuccess) step(cudaMalloc(&c->d_in, sizeof(double) * 22 * max_agents), "cudaMalloc(d_in)");
+    if (err == cudaSuccess) step(cudaMalloc(&c->d_ref, sizeof(double) * max_steps), "cudaMalloc(d_ref)");
+    if (err == cudaSuccess) step(cudaMalloc(&c->d_env, c->te * RL4_SPE_COUNT * max_agents), "cudaMalloc(d_env)");
+    if (err == cudaSuccess) step(cudaMalloc(&c->d_net, c->tn * RL4_SPN_COUNT * max_agents), "cudaMalloc(d_net)");
+    if (err == cudaSuccess) step(cudaMalloc(&c->d_ints, sizeof(int32_t) * RL4_SPI_COUNT * max_agents), "cudaMalloc(d_ints)");
+    if (err != cudaSuccess) {
+        rl4_ctx_destroy(c);
+        return rl4::cuda_fail(err, what);
+    }
     *out = c;
     return 0;
 }
@@ -576,8 +586,8 @@ int rl4_ctx_destroy(rl4_ctx* c)
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaFree(c->d_in); cudaFree(c->d_ref); cudaFree(c->d_env); cudaFree(c->d_net); cudaFree(c->d_ints);
-    for (int i = 0; i < rl4_ctx::kStreams; ++i) cudaStreamDestroy(c->streams[i]);
-    cudaEventDestroy(c->ref_ready);
+    for (int i = 0; i < rl4_ctx::kStreams; ++i) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
+    if (c->ref_ready) cudaEventDestroy(c->ref_ready);
     delete c;
     return 0;
 }

@@ -127,3 +127,22 @@ def test_host_buffer_episode_equals_device_path(oracle, n):
         L.rl4_ctx_destroy(ctx)
     eq = lambda u, v: bool(((u == v) | (torch.isnan(u) & torch.isnan(v))).all())   # noqa: E731
     assert eq(oenv, eng.env[:, :n].cpu()) and eq(onet, eng.net[:, :n].cpu()) and torch.equal(oint, eng.ints[:, :n].cpu())
+
+
+def test_ctx_create_reports_allocation_failure_and_cleans_up():
+    """A capacity no GPU can hold: rl4_ctx_create returns the CUDA error (positive code, text in rl4_last_error),
+    leaves *out NULL, frees whatever it had created, and the library keeps working afterwards."""
+    from rl4afcs_b200 import _lib
+
+    L = _lib.load()
+    free0 = torch.cuda.mem_get_info()[0]
+    ctx = ctypes.c_void_p()
+    rc = L.rl4_ctx_create(0, _lib.FP64, 1 << 36, 3000, ctypes.byref(ctx))
+    assert rc > 0 and not ctx.value
+    assert b"cudaMalloc" in L.rl4_last_error()
+    torch.cuda.synchronize()
+    assert torch.cuda.mem_get_info()[0] >= free0 - (64 << 20)                 # nothing of the failed context is left behind
+    ok = ctypes.c_void_p()
+    _lib.check(L.rl4_ctx_create(0, _lib.FP64, 1024, 100, ctypes.byref(ok)), "ctx")
+    assert ok.value
+    L.rl4_ctx_destroy(ok)
