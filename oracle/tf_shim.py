@@ -136,7 +136,6 @@ class Tensor:
         assert p == 2, "only squaring is used by objects.py"
         return Tensor(self.v * self.v, [(self, lambda g: (np.asarray(g, dtype=F32) * F32(2)) * self.v)])
 
-    # comparisons used by the reference (`np.isnan(c)` goes through __array__)
     # ---- matmul
     def __matmul__(self, o):
         return matmul(self, o)
@@ -163,22 +162,24 @@ class Variable(Tensor):
         self._parents = ()
 
     def assign(self, value):
-        v = value.v if isinstance(value, Tensor) else np.asarray(value, dtype=np.float64).astype(F32) if not (isinstance(value, np.ndarray) and value.dtype == F32) else value
-        self.v = np.array(v, dtype=F32).reshape(self.v.shape)
+        self.v = np.array(_as_tensor(value).v, dtype=F32).reshape(self.v.shape)
         return self
 
     def assign_sub(self, value):
-        v = value.v if isinstance(value, Tensor) else np.asarray(value, dtype=F32)
-        self.v = (self.v - v).astype(F32)
+        self.v = (self.v - _as_tensor(value).v).astype(F32)
         return self
 
 
 def _as_tensor(x):
+    """TensorFlow's convert_to_tensor(x, dtype_hint=float32): tensors pass through, float32 arrays are taken as they are,
+    everything else (python floats, float64 arrays / scalars) is rounded to float32 once."""
     if isinstance(x, Tensor):
         return x
-    if isinstance(x, (list, tuple)) and any(isinstance(e, Tensor) for e in np.ravel(np.array(x, dtype=object))):
+    if isinstance(x, (list, tuple)) and any(isinstance(e, Tensor) for e in x):
         return Tensor(np.array([np.asarray(e.v if isinstance(e, Tensor) else e) for e in x], dtype=F32))
-    return Tensor(np.asarray(x, dtype=np.float64).astype(F32) if not (isinstance(x, np.ndarray) and x.dtype == F32) else x)
+    if isinstance(x, np.ndarray) and x.dtype == F32:
+        return Tensor(x)
+    return Tensor(np.asarray(x, dtype=np.float64).astype(F32))
 
 
 def matmul(a, b):
