@@ -305,3 +305,35 @@ def test_free_run_bit_exact(nl, policy, case):
                         ("RLS_PARAMS", "theta"), ("RLS_COV", "cov"), ("RSE", "rse_step"), ("ETA_A", "eta_a")):
         off, w = _lib.NLF_FIELDS[name]
         assert np.array_equal(np.transpose(lg[:, off:off + w, :], (2, 0, 1)), olog[oname].reshape(n, steps, w), equal_nan=True), name
+
+
+def test_log_levels_and_stride_are_consistent(nl):
+    """The three log layouts (compact / full / MC row) and a log stride > 1 describe the same run: common quantities agree
+    bit for bit at the common rows, and logging never changes the trajectory."""
+    from rl4afcs_b200 import _lib
+
+    n, steps, every = 40, 210, 7
+    rng = np.random.default_rng(6)
+    noise = rng.standard_normal((steps, n)).astype(np.float32)
+    runs = {}
+    for level, ev in ((0, 1), (1, 1), (2, 1), (3, every)):
+        eng, st, cfg, th = _setup(nl, n, "mixed", seed=13, fault="damp_all", fault_time=1.0)
+        lg = eng.run(steps, noise, log_agents=(n if level else 0), log_every=ev, log_level=max(level, 1))
+        runs[level] = (eng, None if lg is None else lg.cpu().numpy())
+    base = runs[0][0]
+    for level in (1, 2, 3):
+        e = runs[level][0]
+        same = lambda u, v: bool(((u == v) | (torch.isnan(u) & torch.isnan(v))).all())   # noqa: E731
+        assert same(base.env, e.env) and same(base.net, e.net) and torch.equal(base.ints, e.ints), level
+    l1, l2, l3 = runs[1][1], runs[2][1], runs[3][1]
+    F, M, L = _lib.NLF_FIELDS, _lib.NLM, _lib.NLL
+    assert l3.shape == (steps // every, M["COUNT"], n) and l2.shape == (steps, _lib.NLF["COUNT"], n)
+    rows = np.arange(0, steps, every)
+    xf = F["XFULL"][0]
+    assert np.array_equal(l1[:, L["XFULL"]:L["XFULL"] + 12], l2[:, xf:xf + 12])
+    assert np.array_equal(l1[:, L["E_THETA"]], l2[:, F["E"][0]]) and np.array_equal(l1[:, L["SURF"]], l2[:, F["A_CMD"][0]])
+    for mname, col in (("E", F["E"][0]), ("THETA", xf + 7), ("ALPHA", xf + 4), ("Q", xf + 1), ("V", xf + 3), ("H", xf + 9),
+                       ("A_CMD", F["A_CMD"][0]), ("A_EFF", F["A_EFF"][0]), ("RLS_EPS", F["RLS_EPS_NORM"][0])):
+        assert np.array_equal(l3[:, M[mname]], l2[rows, col]), mname
+    o, w = F["A_W1"]
+    assert np.allclose(l3[:, M["WA_NORM"]], np.sqrt((l2[rows, o:o + w] ** 2).sum(axis=1)), rtol=1e-14)
