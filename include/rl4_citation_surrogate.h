@@ -72,6 +72,9 @@ typedef struct rl4_cit_params {
 } rl4_cit_params;
 
 #define RL4_FMA(a, b, c) fma((a), (b), (c))
+#ifndef RL4_DERIV_OUT_OF_LINE
+#define RL4_DERIV_OUT_OF_LINE 0
+#endif
 #ifndef RL4_SINCOS_OUT_OF_LINE
 #define RL4_SINCOS_OUT_OF_LINE 1   /* measured: fp64 kernel +27 %, mixed kernel -0.7 % against the inlined form */
 #endif
@@ -253,6 +256,32 @@ RL4_HD_NOINLINE void rl4_cit_deriv(const rl4_cit_params* P, const rl4_cit_air ai
     }
 }
 
+#if defined(__CUDA_ARCH__) && RL4_DERIV_OUT_OF_LINE
+/* ONE out-of-line copy of the derivative for the 4-6 stage evaluations of a step: scalars in, a 12-double struct out,
+ * everything in registers (no pointers, so nothing is forced into local memory).  The fused kernel executes ~8 000
+ * straight-line instructions per step, right at the instruction-cache capacity; sharing this code keeps it below. */
+typedef struct rl4_cit_vec12 { double v[12]; } rl4_cit_vec12;
+static __device__ __noinline__ rl4_cit_vec12 rl4_cit_deriv_ool(const rl4_cit_params* P, double rho, double lapse,
+                                                                double x0, double x1, double x2, double x3, double x4, double x5,
+                                                                double x6, double x7, double x8,
+                                                                double u0, double u1, double u2, double u3, double u4, double u5,
+                                                                double u6, double u7, double u8, double u9, double u10)
+{
+    const double x[12] = {x0, x1, x2, x3, x4, x5, x6, x7, x8, 0.0, 0.0, 0.0};
+    const double u[11] = {u0, u1, u2, u3, u4, u5, u6, u7, u8, u9, u10};
+    rl4_cit_air air; air.rho = rho; air.thrust_lapse = lapse;
+    rl4_cit_vec12 d;
+    rl4_cit_deriv(P, air, x, u, d.v);
+    return d;
+}
+#define RL4_CIT_DERIV(P, air, x, u, dx) do { const rl4_cit_vec12 d_ = rl4_cit_deriv_ool((P), (air).rho, (air).thrust_lapse, \
+    (x)[0], (x)[1], (x)[2], (x)[3], (x)[4], (x)[5], (x)[6], (x)[7], (x)[8], \
+    (u)[0], (u)[1], (u)[2], (u)[3], (u)[4], (u)[5], (u)[6], (u)[7], (u)[8], (u)[9], (u)[10]); \
+    RL4_UNROLL for (int i_ = 0; i_ < 12; ++i_) (dx)[i_] = d_.v[i_]; } while (0)
+#else
+#define RL4_CIT_DERIV(P, air, x, u, dx) rl4_cit_deriv((P), (air), (x), (u), (dx))
+#endif
+
 /* one fixed step, input held constant over the step (zero-order hold, like Simulink's fixed-step solvers);
  * stage combinations are explicit FMA chains (one rounding per term) */
 RL4_HD void rl4_cit_step_rk4(const rl4_cit_params* P, double* x, const double* u, double dt)
@@ -261,16 +290,16 @@ RL4_HD void rl4_cit_step_rk4(const rl4_cit_params* P, double* x, const double* u
     int i;
     const rl4_cit_air air = rl4_cit_airdata(P, x[RL4_CIT_H]);
     const double hdt = 0.5 * dt, dt6 = dt / 6.0;
-    rl4_cit_deriv(P, air, x, u, k1);
+    RL4_CIT_DERIV(P, air, x, u, k1);
     RL4_UNROLL
     for (i = 0; i < 12; ++i) y[i] = RL4_FMA(hdt, k1[i], x[i]);
-    rl4_cit_deriv(P, air, y, u, k2);
+    RL4_CIT_DERIV(P, air, y, u, k2);
     RL4_UNROLL
     for (i = 0; i < 12; ++i) y[i] = RL4_FMA(hdt, k2[i], x[i]);
-    rl4_cit_deriv(P, air, y, u, k3);
+    RL4_CIT_DERIV(P, air, y, u, k3);
     RL4_UNROLL
     for (i = 0; i < 12; ++i) y[i] = RL4_FMA(dt, k3[i], x[i]);
-    rl4_cit_deriv(P, air, y, u, k4);
+    RL4_CIT_DERIV(P, air, y, u, k4);
     RL4_UNROLL
     for (i = 0; i < 12; ++i) x[i] = RL4_FMA(dt6, RL4_FMA(2.0, k2[i] + k3[i], k1[i] + k4[i]), x[i]);
 }
@@ -282,27 +311,27 @@ RL4_HD void rl4_cit_step_ode5(const rl4_cit_params* P, double* x, const double* 
     int i;
     const rl4_cit_air air = rl4_cit_airdata(P, x[RL4_CIT_H]);
     const double dt5 = dt * (1.0 / 5.0);
-    rl4_cit_deriv(P, air, x, u, k1);
+    RL4_CIT_DERIV(P, air, x, u, k1);
     RL4_UNROLL
     for (i = 0; i < 12; ++i) y[i] = RL4_FMA(dt5, k1[i], x[i]);
-    rl4_cit_deriv(P, air, y, u, k2);
+    RL4_CIT_DERIV(P, air, y, u, k2);
     RL4_UNROLL
     for (i = 0; i < 12; ++i) y[i] = RL4_FMA(dt, RL4_FMA(9.0 / 40.0, k2[i], (3.0 / 40.0) * k1[i]), x[i]);
-    rl4_cit_deriv(P, air, y, u, k3);
+    RL4_CIT_DERIV(P, air, y, u, k3);
     RL4_UNROLL
     for (i = 0; i < 12; ++i)
         y[i] = RL4_FMA(dt, RL4_FMA(32.0 / 9.0, k3[i], RL4_FMA(-56.0 / 15.0, k2[i], (44.0 / 45.0) * k1[i])), x[i]);
-    rl4_cit_deriv(P, air, y, u, k4);
+    RL4_CIT_DERIV(P, air, y, u, k4);
     RL4_UNROLL
     for (i = 0; i < 12; ++i)
         y[i] = RL4_FMA(dt, RL4_FMA(-212.0 / 729.0, k4[i], RL4_FMA(64448.0 / 6561.0, k3[i],
                            RL4_FMA(-25360.0 / 2187.0, k2[i], (19372.0 / 6561.0) * k1[i]))), x[i]);
-    rl4_cit_deriv(P, air, y, u, k5);
+    RL4_CIT_DERIV(P, air, y, u, k5);
     RL4_UNROLL
     for (i = 0; i < 12; ++i)
         y[i] = RL4_FMA(dt, RL4_FMA(-5103.0 / 18656.0, k5[i], RL4_FMA(49.0 / 176.0, k4[i], RL4_FMA(46732.0 / 5247.0, k3[i],
                            RL4_FMA(-355.0 / 33.0, k2[i], (9017.0 / 3168.0) * k1[i])))), x[i]);
-    rl4_cit_deriv(P, air, y, u, k6);
+    RL4_CIT_DERIV(P, air, y, u, k6);
     RL4_UNROLL
     for (i = 0; i < 12; ++i)
         x[i] = RL4_FMA(dt, RL4_FMA(11.0 / 84.0, k6[i], RL4_FMA(-2187.0 / 6784.0, k5[i], RL4_FMA(125.0 / 192.0, k4[i],

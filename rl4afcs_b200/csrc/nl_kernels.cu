@@ -4,7 +4,7 @@
 // The per-agent state (~1.7 KB mixed / 2.6 KB fp64: 4-10-{1,3} nets, traces, 4x4 RLS covariance, 12 plant states)
 // exceeds the 255-register budget: the actor trace and the target critic live in shared memory, ptxas keeps the rest
 // in registers + ~1.3 KB of local memory.  256 agents per SM fill the register file and 174 KB of shared memory;
-// DESIGN.md section 9 has the capacity analysis and the measured alternatives (RL4_NL_SMEM_* / RL4_NL_BLOCK below).
+// DESIGN.md section 9 has the capacity analysis and the measured alternatives (RL4_NL_SMEM_* / RL4_NL_BLOCK_* / RL4_NL_STEP_BARRIER below).
 //
 // Arithmetic: built with -fmad=false, FMAs explicit; numpy-side `@` orders as measured for these
 // shapes, TensorFlow-side `@` in-order chains, tanh = t13.
@@ -36,11 +36,22 @@ template <> __device__ __forceinline__ double nfma<double>(double a, double b, d
 __device__ __forceinline__ float nsqrt(float a) { return sqrt_rn(Rn<float>(a)).v; }
 __device__ __forceinline__ double nsqrt(double a) { return sqrt_rn(Rn<double>(a)).v; }
 
-#ifndef RL4_NL_BLOCK
-#define RL4_NL_BLOCK 128
+// CTA size: 256 threads (one CTA per SM: 255 registers x 256 threads fill the register file, 174 KB of shared memory) for
+// float32 networks, so that ONE barrier per step re-aligns all eight resident warps; 128 for float64 networks (their
+// shared-memory share allows only 128 threads per SM)
+#ifndef RL4_NL_BLOCK_F32
+#define RL4_NL_BLOCK_F32 256
 #endif
+#ifndef RL4_NL_BLOCK_F64
+#define RL4_NL_BLOCK_F64 128
+#endif
+template <typename TN> struct NlBlock { static constexpr int v = RL4_NL_BLOCK_F64; };
+template <> struct NlBlock<float> { static constexpr int v = RL4_NL_BLOCK_F32; };
 #ifndef RL4_NL_MINB
 #define RL4_NL_MINB 1
+#endif
+#ifndef RL4_NL_STEP_BARRIER
+#define RL4_NL_STEP_BARRIER 1
 #endif
 #ifndef RL4_NL_SMEM_RLS
 #define RL4_NL_SMEM_RLS 0       // RLS parameters (12) and covariance (16) in shared memory instead of registers
@@ -54,9 +65,9 @@ constexpr int kNlSmemNet = 70 + (RL4_NL_SMEM_ACTOR ? 50 : 0);
 // per-thread arrays kept in shared memory, laid out [element][thread] (conflict-free, no indexing cost):
 // the actor trace E (50 doubles) and the target-critic weights (70 values) are touched once or twice per
 // step, so they are the cheapest state to move out of the 255-register budget
-template <typename T> struct Strided {
+template <typename T, int BLOCK> struct Strided {
     T* p;
-    __device__ __forceinline__ T& operator[](int j) const { return p[j * RL4_NL_BLOCK]; }
+    __device__ __forceinline__ T& operator[](int j) const { return p[j * BLOCK]; }
 };
 
 // element j of a per-agent array stored in a global SoA plane (step-API kernels)
@@ -219,7 +230,8 @@ __device__ __forceinline__ void nl_env_step(const rl4_nl_params& p, const NlHp<P
     rg2 = (-Q) * e_th;                                                             // env.py:219-220 (q slot)
 }
 
-__device__ __forceinline__ double nl_decay(double a, double b, double c, bool f32)
+// (one out-of-line copy each: three call sites per step, four IEEE divisions per call)
+static __device__ __noinline__ double nl_decay(double a, double b, double c, bool f32)
 {   // objects.py:1235-1243, numpy-1.x promotion: float64 intermediates, network-dtype result
     double r = b / a;
     r = c + (1.0 - c) * r;
@@ -229,7 +241,7 @@ __device__ __forceinline__ double nl_decay(double a, double b, double c, bool f3
 }
 // the same under NEP 50 (numpy >= 2): once `a` is a 0-d float32 array the python-float operands are weak -> float32
 // arithmetic with the constants rounded to float32 first; while `a` is still a python float it is float64 arithmetic
-__device__ __forceinline__ double nl_decay_np2(double a, double b, double c, bool a_is_pyfloat)
+static __device__ __noinline__ double nl_decay_np2(double a, double b, double c, bool a_is_pyfloat)
 {
     if (a_is_pyfloat) {
         double r = b / a;
@@ -247,7 +259,7 @@ __device__ __forceinline__ double nl_decay_np2(double a, double b, double c, boo
 __device__ __forceinline__ bool nl_isclose(double a, double b) { return fabs(a - b) <= (1e-8 + 1e-5 * fabs(b)); }
 
 template <typename TN, int INTEG, bool LOG>
-__global__ void __launch_bounds__(RL4_NL_BLOCK, RL4_NL_MINB)
+__global__ void __launch_bounds__(NlBlock<TN>::v, RL4_NL_MINB)
 nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict__ theta_ref, const float* __restrict__ noise,
               int64_t noise_stride, int k0, int n_steps, const rl4_nl_state st, int64_t n_agents, const rl4_sp_log lg)
 {
@@ -266,20 +278,21 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
     extern __shared__ __align__(16) unsigned char nl_smem[];
     // layout: doubles first ([Ea 50][th 12 + cv 16 when RL4_NL_SMEM_RLS]), then TN ([W1t 40][W2t 30][W1a 40 + W2a 10 when RL4_NL_SMEM_ACTOR])
     double* const sm_d = reinterpret_cast<double*>(nl_smem) + threadIdx.x;
-    TN* const sm_n = reinterpret_cast<TN*>(nl_smem + sizeof(double) * kNlSmemDoubles * RL4_NL_BLOCK) + threadIdx.x;
-    const Strided<double> Ea{sm_d};
-    const Strided<TN> W1t{sm_n};
-    const Strided<TN> W2t{sm_n + 40 * RL4_NL_BLOCK};
+    constexpr int BLK = NlBlock<TN>::v;
+    TN* const sm_n = reinterpret_cast<TN*>(nl_smem + sizeof(double) * kNlSmemDoubles * BLK) + threadIdx.x;
+    const Strided<double, BLK> Ea{sm_d};
+    const Strided<TN, BLK> W1t{sm_n};
+    const Strided<TN, BLK> W2t{sm_n + 40 * BLK};
 #if RL4_NL_SMEM_RLS
-    const Strided<double> th{sm_d + 50 * RL4_NL_BLOCK};
-    const Strided<double> cv{sm_d + 62 * RL4_NL_BLOCK};
+    const Strided<double, BLK> th{sm_d + 50 * BLK};
+    const Strided<double, BLK> cv{sm_d + 62 * BLK};
     double x[12], x_act[3], x_lon[3], x_prev_lon[3], eps[3];
 #else
     double x[12], x_act[3], x_lon[3], x_prev_lon[3], th[12], cv[16], eps[3];
 #endif
 #if RL4_NL_SMEM_ACTOR
-    const Strided<TN> W1a{sm_n + 70 * RL4_NL_BLOCK};
-    const Strided<TN> W2a{sm_n + 110 * RL4_NL_BLOCK};
+    const Strided<TN, BLK> W1a{sm_n + 70 * BLK};
+    const Strided<TN, BLK> W2a{sm_n + 110 * BLK};
     TN s[4], s_prev[4], W1c[40], W2c[30], Mp[9];
 #else
     TN s[4], s_prev[4], W1a[40], W2a[10], W1c[40], W2c[30], Mp[9];
@@ -305,7 +318,24 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
     const bool f32 = sizeof(TN) == 4;
     int k = k0;
     for (; k < k0 + n_steps; ++k) {
+#if RL4_NL_STEP_BARRIER
+        // Re-align the warps of the CTA once per step: the step is ~8 000 straight-line instructions (~128 KB), as large
+        // as the instruction cache; warps that drift apart each stream the whole loop through it, warps that walk it
+        // together share the fetched lines.  Frozen (diverged) agents keep arriving at the barrier and skip the body.
+        __syncthreads();
+        if (diverged_step >= 0) {                                                  // objects.py:1557 (break) + :1168-1175 (NaN rows)
+            if (LOG) {
+                if (logged && (k - k0) % lg.every == 0) {
+                    const int nf = lg.level >= 3 ? RL4_NLM_COUNT : (lg.level == 2 ? RL4_NLF_COUNT : RL4_NLL_COUNT);
+                    double* b = lg.buf + ((int64_t)((k - k0) / lg.every) * nf) * lg.n_agents_logged + i;
+                    for (int f = 0; f < nf; ++f) b[(int64_t)f * lg.n_agents_logged] = __longlong_as_double(0x7ff8000000000000LL);
+                }
+            }
+            continue;
+        }
+#else
         if (diverged_step >= 0) break;                                             // objects.py:1557
+#endif
         const TN a_k = a;
         // ---- env.step(self._get_action(a))  (objects.py:1497, 1448-1455)
         const double act[3] = {(double)a_k, 0.0, 0.0};
@@ -687,10 +717,12 @@ template <typename TN, int INTEG, bool LOG>
 static int nl_launch_one(const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride, int k0,
                          int n_steps, rl4_nl_state st, int64_t n, rl4_sp_log lg, unsigned grid, cudaStream_t s)
 {
-    const size_t smem = (sizeof(double) * kNlSmemDoubles + sizeof(TN) * kNlSmemNet) * RL4_NL_BLOCK;
+    constexpr int BLK = NlBlock<TN>::v;
+    const size_t smem = (sizeof(double) * kNlSmemDoubles + sizeof(TN) * kNlSmemNet) * BLK;
+    grid = (unsigned)((n + BLK - 1) / BLK);
     // per launch: the attribute is per device and per function, and setting it costs microseconds
     RL4_CUDA(cudaFuncSetAttribute(nl_run_kernel<TN, INTEG, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nl_run_kernel<TN, INTEG, LOG><<<grid, RL4_NL_BLOCK, smem, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg);
+    nl_run_kernel<TN, INTEG, LOG><<<grid, BLK, smem, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg);
     return 0;
 }
 
@@ -811,7 +843,7 @@ int rl4_nl_run(int policy, const rl4_nl_params* p, const double* theta_ref, cons
     bool per_agent = false;
     for (int j = 0; j < RL4_NHP_COUNT; ++j) per_agent |= (p->hp_agent[j] != nullptr);
     for (int j = 0; j < RL4_NHPI_COUNT; ++j) per_agent |= (p->hpi_agent[j] != nullptr);
-    const unsigned grid = (unsigned)((n + RL4_NL_BLOCK - 1) / RL4_NL_BLOCK);
+    const unsigned grid = 0;                                  // set per network dtype in nl_launch_one
     cudaStream_t s = (cudaStream_t)stream;
     const bool log = lg.level != RL4_LOG_NONE;
     int rc = 0;

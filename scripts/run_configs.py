@@ -2,6 +2,7 @@
 
     python scripts/run_configs.py --config sweep   [--agents-total 4194304]     # hyper-parameter sweep grid, linear plant
     python scripts/run_configs.py --config faults  [--agents-total 8388608]     # Monte-Carlo fault study, nonlinear plant
+    python scripts/run_configs.py --config nonlinear [--integrator rk4|ode5]    # configs[2]: 256K agents, 90 s flights
     torchrun --nproc-per-node 8 scripts/run_configs.py --config sweep
 
 sweep  (SURVEY 8d config 4): grid over eta_a_h in [2.5,4.7] x eta_c_h in [0.45,0.55] x rls_gamma in [0.99,1.0] x reference
@@ -23,7 +24,8 @@ import torch.distributed as dist  # noqa: E402
 from rl4afcs_b200 import _lib, dist as rdist, nl_engine, sp_engine  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--config", required=True, choices=["sweep", "faults"])
+ap.add_argument("--config", required=True, choices=["sweep", "faults", "nonlinear"])
+ap.add_argument("--integrator", default="rk4", choices=["rk4", "ode5"])
 ap.add_argument("--agents-total", type=int, default=None)
 ap.add_argument("--steps", type=int, default=None)
 a = ap.parse_args()
@@ -74,6 +76,46 @@ if a.config == "sweep":
     summary = rdist.gather_episode_summary(eng, world)
     out = {"config": "hyper-parameter sweep grid (BASELINE.json configs[3])", "grid": dims, "agents_total": total, "n_gpus": world,
            "steps": steps, "policy": "mixed", "seconds": ms * 1e-3, "agent_steps_per_s": total * steps / (ms * 1e-3), "stats": summary}
+elif a.config == "nonlinear":
+    # BASELINE.json configs[2]: nonlinear aircraft IDHP attitude tracking, 256K agents, the 90 s flight of idhp_nonlin.py
+    # (hyper-parameters :123-146, no fault), through the reference-shaped objects: Ce500NonLinear + IDHPnonlin.train()
+    from rl4afcs_b200.envs.nonlinear.env import Ce500NonLinear
+    from rl4afcs_b200.objects import IDHPnonlin
+
+    total = a.agents_total or (1 << 18)
+    steps = a.steps or 9000
+    lo, hi = rdist.shard_bounds(total, world, rank)
+    n = hi - lo
+    th = nl_engine.theta_reference()
+    trim_input = np.array([-0.02855, 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.55, 0.55, 0])
+    trim_state = np.array([0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0])
+    env_config = {"state_dim": 4, "action_dim": 3, "trim_input": trim_input, "trim_state": trim_state, "dt": 0.01, "t_end": steps * 0.01,
+                  "total_steps": steps, "fault_time": 60, "fault_scenario": "none",
+                  "reference": {"tracked_state": ["phi", "theta", "psi"], "signal": [0 * th, th, 0 * th]}}
+    idhp_config = {"gamma": 0.6, "multistep": 0, "lr_decay": 0.998, "lambda_h": 0.95, "lambda_l": 0.95, "kappa": [1, 2, 1],
+                   "cooldown_time": 2.0, "sigma": 0.1, "warmup_time": 4.0, "error_thresh": 1, "tau": 0.02, "in_dims": 4,
+                   "actor_config": {"layers": {10: "tanh", 1: "tanh"}, "eta_h": 35.0, "eta_l": 5.0, "elig": "accumulating"},
+                   "critic_config": {"layers": {10: "tanh", 3: "linear"}, "eta_h": 1.4, "eta_l": 0.7, "elig": 1233},
+                   "rls_config": {"state_dim": 3, "action_dim": 1, "rls_gamma": 1, "rls_cov": 10 ** 6}}
+    env = Ce500NonLinear(env_config, batch=n, device=dev, dtype="mixed", integrator=a.integrator)
+    idhp = IDHPnonlin(env, idhp_config, seed=8 + rank, verbose=0, log=None, chunk=1000)
+    ms = timed(lambda: idhp.train(steps))                     # reset (trim) + prologue + the fused launches + noise draws
+    st = idhp.stats()
+    alive = ~st["diverged"]
+    rse = st["rse"][:, 0][alive]
+    flight = st["rse_flight"][:, 0][alive]
+    part = torch.stack([torch.tensor(float(n), device=dev, dtype=torch.float64), st["diverged"].sum().double(), rse.sum(), flight.sum(),
+                        st["nz_peak"][alive].max(), rse.median(), flight.median()])
+    parts = rdist.gather_per_agent(part[None], world)
+    ok = parts[:, 0].sum() - parts[:, 1].sum()
+    out = {"config": "nonlinear aircraft IDHP attitude tracking (BASELINE.json configs[2])", "agents_total": total, "n_gpus": world,
+           "steps": steps, "policy": "mixed", "integrator": a.integrator, "seconds": ms * 1e-3,
+           "agent_steps_per_s": total * steps / (ms * 1e-3),
+           "stats": {"agents": int(parts[:, 0].sum()), "diverged": int(parts[:, 1].sum()),
+                     "mean_RSE_theta_per_step_deg": float(np.rad2deg(float(parts[:, 2].sum() / ok) / steps)),
+                     "mean_RSE_theta_per_step_flight_deg": float(np.rad2deg(float(parts[:, 3].sum() / ok) / max(1, steps - 5500))),
+                     "median_RSE_theta_per_step_deg_rank0": float(np.rad2deg(float(parts[0, 5]) / steps)),
+                     "peak_nz": float(parts[:, 4].max())}}
 else:
     total = a.agents_total or (1 << 20)
     steps = a.steps or 9000
