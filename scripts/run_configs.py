@@ -99,6 +99,7 @@ elif a.config == "nonlinear":
                    "rls_config": {"state_dim": 3, "action_dim": 1, "rls_gamma": 1, "rls_cov": 10 ** 6}}
     env = Ce500NonLinear(env_config, batch=n, device=dev, dtype="mixed", integrator=a.integrator)
     idhp = IDHPnonlin(env, idhp_config, seed=8 + rank, verbose=0, log=None, chunk=1000)
+    idhp.train(2)                                             # loads the kernels (lazy module loading) outside the timed region
     ms = timed(lambda: idhp.train(steps))                     # reset (trim) + prologue + the fused launches + noise draws
     st = idhp.stats()
     alive = ~st["diverged"]
