@@ -7,5 +7,5 @@ if [[ "$1" == *.py ]]; then script=$1; shift; fi
 for so in build_variants/librl4_*.so; do
   echo "== $so"
   if [ "$script" = scripts/prof_nl.py ] && [ $# -eq 0 ]; then set -- --steps 300 --warmup 50; fi
-  RL4AFCS_LIB=$PWD/$so timeout 300 python $script "$@" 2>&1 | tail -6
+  RL4AFCS_LIB=$PWD/$so timeout 90 python $script "$@" 2>&1 | tail -6
 done
