@@ -258,12 +258,14 @@ static __device__ __noinline__ double nl_decay_np2(double a, double b, double c,
 }
 __device__ __forceinline__ bool nl_isclose(double a, double b) { return fabs(a - b) <= (1e-8 + 1e-5 * fabs(b)); }
 
-template <typename TN, int INTEG, bool LOG>
+template <typename TN, int INTEG, bool LOG, bool PER_AGENT>
 __global__ void __launch_bounds__(NlBlock<TN>::v, RL4_NL_MINB)
 nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict__ theta_ref, const float* __restrict__ noise,
               int64_t noise_stride, int k0, int n_steps, const rl4_nl_state st, int64_t n_agents, const rl4_sp_log lg)
 {
-    constexpr bool PER_AGENT = true;     // per-agent overrides are a pointer test + load; negligible next to the plant
+    // PER_AGENT = false (no per-agent override array at all, the common case): every hyper-parameter read is a constant-
+    // bank operand; true: a pointer test + load per read (about 150 instructions and the reloads of the spilled agent
+    // index per step -- 10 % of the step time, so the uniform case gets its own instantiation)
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_agents) return;
     const NlHp<PER_AGENT> hv{p, i};
@@ -713,7 +715,7 @@ nl_rls_update_kernel(double rgam, const double* __restrict__ rgam_agent, double*
     out_eps_norm[i] = eps_norm;
 }
 
-template <typename TN, int INTEG, bool LOG>
+template <typename TN, int INTEG, bool LOG, bool PER_AGENT>
 static int nl_launch_one(const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride, int k0,
                          int n_steps, rl4_nl_state st, int64_t n, rl4_sp_log lg, unsigned grid, cudaStream_t s)
 {
@@ -721,20 +723,23 @@ static int nl_launch_one(const rl4_nl_params* p, const double* theta_ref, const 
     const size_t smem = (sizeof(double) * kNlSmemDoubles + sizeof(TN) * kNlSmemNet) * BLK;
     grid = (unsigned)((n + BLK - 1) / BLK);
     // per launch: the attribute is per device and per function, and setting it costs microseconds
-    RL4_CUDA(cudaFuncSetAttribute(nl_run_kernel<TN, INTEG, LOG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nl_run_kernel<TN, INTEG, LOG><<<grid, BLK, smem, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg);
+    RL4_CUDA(cudaFuncSetAttribute(nl_run_kernel<TN, INTEG, LOG, PER_AGENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nl_run_kernel<TN, INTEG, LOG, PER_AGENT><<<grid, BLK, smem, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg);
     return 0;
 }
 
 template <typename TN>
 static int nl_launch(const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride, int k0, int n_steps,
-                     rl4_nl_state st, int64_t n, rl4_sp_log lg, bool log, bool /*per_agent*/, unsigned grid, cudaStream_t s)
+                     rl4_nl_state st, int64_t n, rl4_sp_log lg, bool log, bool per_agent, unsigned grid, cudaStream_t s)
 {
     const bool rk4 = (p->integrator == RL4_CIT_INTEGRATOR_RK4);
-    if (log) return rk4 ? nl_launch_one<TN, RL4_CIT_INTEGRATOR_RK4, true>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s)
-                        : nl_launch_one<TN, RL4_CIT_INTEGRATOR_ODE5, true>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s);
-    return rk4 ? nl_launch_one<TN, RL4_CIT_INTEGRATOR_RK4, false>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s)
-               : nl_launch_one<TN, RL4_CIT_INTEGRATOR_ODE5, false>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s);
+    // logging launches always take the general (per-agent capable) instantiation; the log-free hot path is specialised
+    if (log) return rk4 ? nl_launch_one<TN, RL4_CIT_INTEGRATOR_RK4, true, true>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s)
+                        : nl_launch_one<TN, RL4_CIT_INTEGRATOR_ODE5, true, true>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s);
+    if (per_agent) return rk4 ? nl_launch_one<TN, RL4_CIT_INTEGRATOR_RK4, false, true>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s)
+                              : nl_launch_one<TN, RL4_CIT_INTEGRATOR_ODE5, false, true>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s);
+    return rk4 ? nl_launch_one<TN, RL4_CIT_INTEGRATOR_RK4, false, false>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s)
+               : nl_launch_one<TN, RL4_CIT_INTEGRATOR_ODE5, false, false>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s);
 }
 
 // Critic_big.call (objects.py:294-339): forward of the 4-10-3 critic (its trace is never formed, :304-305)

@@ -337,3 +337,44 @@ def test_log_levels_and_stride_are_consistent(nl):
         assert np.array_equal(l3[:, M[mname]], l2[rows, col]), mname
     o, w = F["A_W1"]
     assert np.allclose(l3[:, M["WA_NORM"]], np.sqrt((l2[rows, o:o + w] ** 2).sum(axis=1)), rtol=1e-14)
+
+
+def test_per_agent_configuration_bit_exact(nl):
+    """Every agent with its own hyper-parameters, trace mode, multistep switch and fault (family, time, severity): the
+    kernel's per-agent instantiation against the oracle run with one configuration record per agent, free run, bit for
+    bit; and the same batch with the overrides removed equals the uniform instantiation's result for agent 0's settings."""
+    from rl4afcs_b200 import _lib, nl_engine
+
+    n, steps = 96, 700
+    rng = np.random.default_rng(17)
+    names = ["none", "damp_elevator", "damp_all", "shift_cg", "slow_all", "saturate_elevator", "damp_elevator_and_saturate_elevator"]
+    cfg = nl.make_cfg(n)
+    per = dict(eta_a_h=rng.uniform(20, 40, n), eta_a_l=rng.uniform(3, 8, n), eta_c_h=rng.uniform(0.8, 1.6, n), eta_c_l=rng.uniform(0.4, 0.8, n),
+               lambda_h=rng.uniform(0.85, 0.98, n), lambda_l=rng.uniform(0.6, 0.9, n), damp_factor=rng.uniform(0.2, 0.5, n),
+               cg_shift=rng.uniform(-0.5, 0.0, n), lr_decay=rng.uniform(0.99, 0.999, n))
+    for k, v in per.items():
+        cfg[k] = v
+    picks = rng.integers(0, len(names), n)
+    ds = np.asarray([nl_engine.split_fault(names[p]) for p in picks], dtype=np.int32)
+    cfg["fault_damp"], cfg["fault_sat"] = ds[:, 0], ds[:, 1]
+    cfg["fault_step"] = np.where((ds[:, 0] == 0) & (ds[:, 1] == 0), -1, rng.integers(100, 500, n)).astype(np.int32)
+    cfg["multistep"] = rng.integers(0, 2, n)
+    cfg["elig_a"] = rng.integers(0, 3, n)
+    cfg["warmup_steps"] = rng.integers(100, 300, n)
+    cfg["cooldown_steps"] = rng.integers(50, 250, n)
+    w = nl.init_weights(n, 23)
+    st = nl.init_states("mixed", cfg, w, n)
+    th = nl.theta_reference()
+    noise = rng.standard_normal((steps, n)).astype(np.float32)
+    nl.run("mixed", cfg, th, noise, st, 0, steps, tanh="t13")
+    eng = nl_engine.NlEngine(n, policy="mixed")
+    for k, v in per.items():
+        eng.set_hp(k.upper(), v)
+    for k in ("fault_damp", "fault_sat", "fault_step", "multistep", "elig_a", "warmup_steps", "cooldown_steps"):
+        eng.set_hpi(k.upper(), cfg[k])
+    eng.set_reference(th)
+    eng.init(w["W1a"], w["W2a"], w["W1c"], w["W2c"])
+    eng.run(steps, noise)
+    got = _util_nl.engine_to_oracle(eng, nl)
+    for f in _EXACT_FIELDS:
+        assert np.array_equal(got[f], st[f], equal_nan=(got[f].dtype.kind == "f")), f
