@@ -338,6 +338,141 @@ RL4_HD void rl4_cit_step_ode5(const rl4_cit_params* P, double* x, const double* 
                            RL4_FMA(500.0 / 1113.0, k3[i], (35.0 / 384.0) * k1[i])))), x[i]);
 }
 
+/* ---- symmetric flight --------------------------------------------------------------------------------------------------
+ * With p = r = beta = phi = psi = 0 and da = dr = 0 (the pitch-tracking task: IDHPnonlin commands the elevator only,
+ * objects.py:1448-1455) every lateral term of rl4_cit_deriv is an exact zero: products with a zero factor are +-0, an FMA
+ * whose product is +-0 returns its addend, cos(0) = 1 and 1/1 = 1 are exact.  The functions below are rl4_cit_deriv /
+ * rl4_cit_step_* with those terms dropped: for finite symmetric states they return the SAME values for
+ * z = [q, V, alpha, theta, h, xe] (the lateral derivatives are +-0, so the lateral states stay zero) with ~40 % fewer
+ * operations and half the stage storage.  tests/test_oracle_math.py compares them with the full model on the host,
+ * the GPU parity tests compare the kernel (which takes this path when it applies) with the oracle (which never does). */
+RL4_HD int rl4_cit_lon_in_range(const double* x)
+{   /* far from overflow / division by zero: inside this box no intermediate of the step can become inf or nan, which is
+     * what makes "zero times finite = zero" hold for every dropped lateral term (NaN compares false) */
+    const double big = 1.0e30, tiny = 1.0e-30;
+    return fabs(x[RL4_CIT_Q]) < big && fabs(x[RL4_CIT_V]) < big && fabs(x[RL4_CIT_V]) > tiny && fabs(x[RL4_CIT_ALPHA]) < big &&
+           fabs(x[RL4_CIT_THETA]) < big && fabs(x[RL4_CIT_H]) < big && fabs(x[RL4_CIT_XE]) < big;
+}
+RL4_HD int rl4_cit_is_symmetric(const double* x, const double* u)
+{
+    return x[RL4_CIT_P] == 0.0 && x[RL4_CIT_R] == 0.0 && x[RL4_CIT_BETA] == 0.0 && x[RL4_CIT_PHI] == 0.0 && x[RL4_CIT_PSI] == 0.0 &&
+           (u[1] + u[4]) == 0.0 && (u[2] + u[5]) == 0.0 && rl4_cit_lon_in_range(x);
+}
+
+/* z = [q, V, alpha, theta, h, xe];  c = [de, flap, gear, thr, dxcg] */
+RL4_HD void rl4_cit_deriv_lon(const rl4_cit_params* P, const rl4_cit_air air, const double* z, const double* c, double* dz)
+{
+    const double q = z[0], V = z[1], al = z[2], th = z[3];
+    const double de = c[0], flap = c[1], gear = c[2], thr = c[3], dxcg = c[4];
+    double sa, ca, sth, cth;
+    RL4_SINCOS(al, sa, ca); RL4_SINCOS(th, sth, cth);
+    const double invV = 1.0 / V;
+    const double qS = (0.5 * air.rho * P->S) * (V * V);
+    const double ch = (0.5 * P->c) * invV;
+    const double qh = q * ch;
+    const double an = al * P->inv_al_stall;
+    const double al_e = al / sqrt(RL4_FMA(an, an, 1.0));
+    const double al_x = al - al_e;
+    const double CL = RL4_FMA(P->CLflap, flap, RL4_FMA(P->CLde, de, RL4_FMA(P->CLq, qh, RL4_FMA(P->CLa, al_e, P->CL0))));
+    const double CD = RL4_FMA(P->CDstall * al_x, al_x, RL4_FMA(P->CDflap, flap, RL4_FMA(P->CDgear, gear, RL4_FMA(P->CDk * CL, CL, P->CD0))));
+    const double CX = RL4_FMA(CL, sa, -CD * ca);
+    const double CZ = -RL4_FMA(CL, ca, CD * sa);
+    const double Cm = RL4_FMA(CZ * dxcg, P->inv_c, RL4_FMA(P->Cmflap, flap, RL4_FMA(P->Cmde, de, RL4_FMA(P->Cmq, qh,
+                      RL4_FMA(P->Cmstall, al_x, RL4_FMA(P->Cma, al, P->Cm0))))));
+    const double T = P->Tstatic * air.thrust_lapse * thr;
+    const double ax = RL4_FMA(qS, CX, T) * P->inv_m, az = (qS * CZ) * P->inv_m;
+    const double M = (qS * P->c) * Cm;
+    const double ub = V * ca, wb = V * sa;                              /* cb = 1 */
+    const double ud = RL4_FMA(-q, wb, RL4_FMA(-P->g, sth, ax));
+    const double wd = RL4_FMA(q, ub, RL4_FMA(P->g, cth, az));           /* g * cos(phi) = g */
+    const double Vd = RL4_FMA(ub, ud, wb * wd) * invV;
+    dz[0] = M * P->inv_Iyy;
+    dz[1] = Vd;
+    dz[2] = RL4_FMA(ub, wd, -wb * ud) * (invV * invV);
+    dz[3] = q;
+    dz[4] = RL4_FMA(ub, sth, -(wb * cth));
+    dz[5] = (ub * cth) + (wb * sth);
+}
+
+#define RL4_CIT_LON_PACK(x, u, z, c) do { \
+    (z)[0] = (x)[RL4_CIT_Q]; (z)[1] = (x)[RL4_CIT_V]; (z)[2] = (x)[RL4_CIT_ALPHA]; (z)[3] = (x)[RL4_CIT_THETA]; \
+    (z)[4] = (x)[RL4_CIT_H]; (z)[5] = (x)[RL4_CIT_XE]; \
+    (c)[0] = (u)[0] + (u)[3]; (c)[1] = (u)[6]; (c)[2] = (u)[7]; (c)[3] = 0.5 * ((u)[8] + (u)[9]); (c)[4] = (u)[10]; } while (0)
+#define RL4_CIT_LON_UNPACK(x, z) do { \
+    (x)[RL4_CIT_Q] = (z)[0]; (x)[RL4_CIT_V] = (z)[1]; (x)[RL4_CIT_ALPHA] = (z)[2]; (x)[RL4_CIT_THETA] = (z)[3]; \
+    (x)[RL4_CIT_H] = (z)[4]; (x)[RL4_CIT_XE] = (z)[5]; } while (0)
+
+RL4_HD void rl4_cit_step_rk4_lon(const rl4_cit_params* P, double* x, const double* u, double dt)
+{
+    double z[6], c[5], k1[6], k2[6], k3[6], k4[6], y[6];
+    int i;
+    const rl4_cit_air air = rl4_cit_airdata(P, x[RL4_CIT_H]);
+    const double hdt = 0.5 * dt, dt6 = dt / 6.0;
+    RL4_CIT_LON_PACK(x, u, z, c);
+    rl4_cit_deriv_lon(P, air, z, c, k1);
+    RL4_UNROLL
+    for (i = 0; i < 6; ++i) y[i] = RL4_FMA(hdt, k1[i], z[i]);
+    rl4_cit_deriv_lon(P, air, y, c, k2);
+    RL4_UNROLL
+    for (i = 0; i < 6; ++i) y[i] = RL4_FMA(hdt, k2[i], z[i]);
+    rl4_cit_deriv_lon(P, air, y, c, k3);
+    RL4_UNROLL
+    for (i = 0; i < 6; ++i) y[i] = RL4_FMA(dt, k3[i], z[i]);
+    rl4_cit_deriv_lon(P, air, y, c, k4);
+    RL4_UNROLL
+    for (i = 0; i < 6; ++i) z[i] = RL4_FMA(dt6, RL4_FMA(2.0, k2[i] + k3[i], k1[i] + k4[i]), z[i]);
+    RL4_CIT_LON_UNPACK(x, z);
+}
+
+RL4_HD void rl4_cit_step_ode5_lon(const rl4_cit_params* P, double* x, const double* u, double dt)
+{
+    double z[6], c[5], k1[6], k2[6], k3[6], k4[6], k5[6], k6[6], y[6];
+    int i;
+    const rl4_cit_air air = rl4_cit_airdata(P, x[RL4_CIT_H]);
+    const double dt5 = dt * (1.0 / 5.0);
+    RL4_CIT_LON_PACK(x, u, z, c);
+    rl4_cit_deriv_lon(P, air, z, c, k1);
+    RL4_UNROLL
+    for (i = 0; i < 6; ++i) y[i] = RL4_FMA(dt5, k1[i], z[i]);
+    rl4_cit_deriv_lon(P, air, y, c, k2);
+    RL4_UNROLL
+    for (i = 0; i < 6; ++i) y[i] = RL4_FMA(dt, RL4_FMA(9.0 / 40.0, k2[i], (3.0 / 40.0) * k1[i]), z[i]);
+    rl4_cit_deriv_lon(P, air, y, c, k3);
+    RL4_UNROLL
+    for (i = 0; i < 6; ++i)
+        y[i] = RL4_FMA(dt, RL4_FMA(32.0 / 9.0, k3[i], RL4_FMA(-56.0 / 15.0, k2[i], (44.0 / 45.0) * k1[i])), z[i]);
+    rl4_cit_deriv_lon(P, air, y, c, k4);
+    RL4_UNROLL
+    for (i = 0; i < 6; ++i)
+        y[i] = RL4_FMA(dt, RL4_FMA(-212.0 / 729.0, k4[i], RL4_FMA(64448.0 / 6561.0, k3[i],
+                           RL4_FMA(-25360.0 / 2187.0, k2[i], (19372.0 / 6561.0) * k1[i]))), z[i]);
+    rl4_cit_deriv_lon(P, air, y, c, k5);
+    RL4_UNROLL
+    for (i = 0; i < 6; ++i)
+        y[i] = RL4_FMA(dt, RL4_FMA(-5103.0 / 18656.0, k5[i], RL4_FMA(49.0 / 176.0, k4[i], RL4_FMA(46732.0 / 5247.0, k3[i],
+                           RL4_FMA(-355.0 / 33.0, k2[i], (9017.0 / 3168.0) * k1[i])))), z[i]);
+    rl4_cit_deriv_lon(P, air, y, c, k6);
+    RL4_UNROLL
+    for (i = 0; i < 6; ++i)
+        z[i] = RL4_FMA(dt, RL4_FMA(11.0 / 84.0, k6[i], RL4_FMA(-2187.0 / 6784.0, k5[i], RL4_FMA(125.0 / 192.0, k4[i],
+                           RL4_FMA(500.0 / 1113.0, k3[i], (35.0 / 384.0) * k1[i])))), z[i]);
+    RL4_CIT_LON_UNPACK(x, z);
+}
+
+/* One plant step that takes the symmetric-flight form when it provably equals the full model: symmetric, in-range state
+ * before the step AND an in-range result (a step that blows up is redone with the full equations, whose lateral terms
+ * then turn into NaN exactly as the oracle's do). */
+RL4_HD void rl4_cit_step_auto(const rl4_cit_params* P, double* x, const double* u, double dt, int integrator)
+{
+    if (rl4_cit_is_symmetric(x, u)) {
+        const double s0 = x[RL4_CIT_Q], s1 = x[RL4_CIT_V], s2 = x[RL4_CIT_ALPHA], s3 = x[RL4_CIT_THETA], s4 = x[RL4_CIT_H], s5 = x[RL4_CIT_XE];
+        if (integrator == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4_lon(P, x, u, dt); else rl4_cit_step_ode5_lon(P, x, u, dt);
+        if (rl4_cit_lon_in_range(x)) return;
+        x[RL4_CIT_Q] = s0; x[RL4_CIT_V] = s1; x[RL4_CIT_ALPHA] = s2; x[RL4_CIT_THETA] = s3; x[RL4_CIT_H] = s4; x[RL4_CIT_XE] = s5;
+    }
+    if (integrator == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(P, x, u, dt); else rl4_cit_step_ode5(P, x, u, dt);
+}
+
 /* Default parameter set: Ce500 Citation derivatives, with CL0 / Cm0 / Tstatic solved for the trim point
  * (V, h, alpha = theta, de, throttle) = (90, 2000, 0.0576, -0.02855, 0.55) of idhp_nonlin.py:53-54. */
 RL4_HD void rl4_cit_default_params(rl4_cit_params* P)

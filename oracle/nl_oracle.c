@@ -178,6 +178,13 @@ int orc_nl_run(int policy, int tanh_mode, const orc_nl_cfg* cfgs, int cfg_stride
 
 int orc_nl_sizeof_cfg(void)    { return (int)sizeof(orc_nl_cfg); }
 int orc_nl_sizeof_state(void)  { return (int)sizeof(orc_nl_state); }
+/* the symmetric-flight variant of the plant step (what the CUDA kernel uses when it applies); returns 0 when the state is not symmetric */
+int orc_cit_plant_step_lon(const rl4_cit_params* P, double* x, const double* u, double dt, int integrator)
+{
+    if (!rl4_cit_is_symmetric(x, u)) return 0;
+    rl4_cit_step_auto(P, x, u, dt, integrator);
+    return 1;
+}
 /* element-wise probes of the plant's deterministic elementary functions (tests) */
 void orc_cit_sincos(const double* a, double* s, double* c, int64_t n) { for (int64_t i = 0; i < n; ++i) rl4_sincos(a[i], s + i, c + i); }
 void orc_cit_air(const rl4_cit_params* P, const double* h, double* rho, double* lapse, int64_t n)

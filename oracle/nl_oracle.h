@@ -94,6 +94,7 @@ void orc_nl_rls_update(double gamma, double* theta, double* cov, const double* d
 void orc_nl_env_step(const orc_nl_cfg* c, double theta_ref_k, const double* act, double* x_full, double* x_act, int32_t stepp,
                      double* surf, double* u, double* e, double* reward);
 void orc_cit_plant_step(const rl4_cit_params* P, double* x, const double* u, double dt, int integrator);
+int orc_cit_plant_step_lon(const rl4_cit_params* P, double* x, const double* u, double dt, int integrator);
 void orc_cit_sincos(const double* a, double* s, double* c, int64_t n);
 void orc_cit_air(const rl4_cit_params* P, const double* h, double* rho, double* lapse, int64_t n);
 int orc_nl_sizeof_cfg(void);

@@ -222,8 +222,10 @@ __device__ __forceinline__ void nl_env_step(const rl4_nl_params& p, const NlHp<P
 #pragma unroll
     for (int i = 0; i < 11; ++i) u[i] = p.trim_input[i] + eff[i];                  // env.py:207-208
     ueff[0] = u[0]; ueff[1] = u[1]; ueff[2] = u[2];
-    if (INTEG == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(&p.plant, x, u, p.dt);   // compile-time: one integrator's code per kernel
-    else rl4_cit_step_ode5(&p.plant, x, u, p.dt);                                  // env.py:210
+    // env.py:210.  Symmetric flight (elevator-only commands from a trimmed start: always, in IDHPnonlin's task) takes the
+    // longitudinal form of the same equations -- identical values, ~40 % less work and half the stage storage; INTEG is
+    // a compile-time constant, so one integrator's code per kernel
+    rl4_cit_step_auto(&p.plant, x, u, p.dt, INTEG);
     const double Q = hv.hp(RL4_NHP_Q_SYM);
     e_phi = x[6] - 0.0; e_th = x[7] - theta_ref_k; e_psi = x[8] - 0.0;            // env.py:215 (state - ref)
     reward = (-0.5 * Q) * (e_th * e_th);                                           // env.py:218

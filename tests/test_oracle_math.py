@@ -93,3 +93,54 @@ def test_quirk_flags_change_what_they_should(oracle):
         oracle.run("mixed", cfg, base, st, 0, 2, tanh="t13")
         cd[q7] = int(st["cooldown"][0])
     assert cd == {0: 0, 1: 100}                             # Q7: cooldown starts at k = 1 under numpy 1.x
+
+
+def test_symmetric_flight_plant_equals_full_model(oracle):
+    """include/rl4_citation_surrogate.h: the longitudinal form of the plant step (taken by the CUDA kernel in symmetric
+    flight) returns the same values as the full 6-DOF step for symmetric states -- both integrators, random states,
+    controls, flap / gear / c.g. settings, several consecutive steps; a non-symmetric state is refused."""
+    import ctypes
+
+    from oracle import nl_c
+
+    L = nl_c.lib()
+    vp = ctypes.c_void_p
+    L.orc_cit_plant_step.argtypes = [vp, vp, vp, ctypes.c_double, ctypes.c_int]
+    L.orc_cit_plant_step_lon.argtypes = [vp, vp, vp, ctypes.c_double, ctypes.c_int]
+    L.orc_cit_plant_step_lon.restype = ctypes.c_int
+    plant = np.ascontiguousarray(nl_c.make_cfg()["plant"][:1])
+    rng = np.random.default_rng(0)
+    for integ in (0, 1):
+        for _ in range(1500):
+            x = np.zeros(12)
+            x[1], x[3], x[4], x[7] = rng.normal(0, 0.3), rng.uniform(40, 160), rng.normal(0.06, 0.2), rng.normal(0.06, 0.4)
+            x[9], x[10], x[11] = rng.uniform(0, 6000), rng.uniform(0, 1e4), rng.choice([0.0, 3.5])
+            u = np.array([rng.uniform(-0.3, 0.3), 0, 0, -0.02855, 0, 0, rng.choice([0, 0.2]), rng.choice([0, 1.0]), rng.uniform(0, 1),
+                          rng.uniform(0, 1), rng.choice([0, -0.5])])
+            a, b = x.copy(), x.copy()
+            for _step in range(4):
+                L.orc_cit_plant_step(plant.ctypes.data, a.ctypes.data, u.ctypes.data, 0.01, integ)
+                assert L.orc_cit_plant_step_lon(plant.ctypes.data, b.ctypes.data, u.ctypes.data, 0.01, integ) == 1
+            assert np.array_equal(a, b)
+    # degenerate states (huge / tiny airspeed, huge rates and angles, i.e. agents about to diverge): the guarded step
+    # (in-range check before and after, else the full equations) reproduces the full model including its inf / nan pattern
+    rng = np.random.default_rng(1)
+    for integ in (0, 1):
+        for _ in range(2500):
+            x = np.zeros(12)
+            x[1] = rng.normal(0, 0.3) * 10.0 ** rng.choice([0, 0, 3, 8, 20, 40, 80, 150, 300])
+            x[3] = rng.uniform(40, 160) * 10.0 ** rng.choice([0, 0, -5, -20, -40, 5, 20, 60, 160])
+            x[4] = rng.normal(0.06, 0.2) * rng.choice([1, 1, 50, 1e5]); x[7] = rng.normal(0.06, 0.4) * rng.choice([1, 1, 50, 1e5])
+            x[9] = rng.uniform(0, 6000)
+            u = np.array([rng.uniform(-0.3, 0.3), 0, 0, -0.02855, 0, 0, 0, 0, 0.55, 0.55, rng.choice([0, -0.5])])
+            a, b = x.copy(), x.copy()
+            for _step in range(5):
+                L.orc_cit_plant_step(plant.ctypes.data, a.ctypes.data, u.ctypes.data, 0.01, integ)
+                if L.orc_cit_plant_step_lon(plant.ctypes.data, b.ctypes.data, u.ctypes.data, 0.01, integ) == 0:
+                    L.orc_cit_plant_step(plant.ctypes.data, b.ctypes.data, u.ctypes.data, 0.01, integ)
+                assert np.array_equal(a, b, equal_nan=True)
+    x = np.zeros(12); x[3] = 90.0; x[5] = 1e-9                                   # a sideslip: not symmetric
+    u = np.zeros(11)
+    assert L.orc_cit_plant_step_lon(plant.ctypes.data, x.ctypes.data, u.ctypes.data, 0.01, 1) == 0
+    x[5] = 0.0; u[1] = 0.01                                                      # an aileron input: not symmetric
+    assert L.orc_cit_plant_step_lon(plant.ctypes.data, x.ctypes.data, u.ctypes.data, 0.01, 1) == 0
