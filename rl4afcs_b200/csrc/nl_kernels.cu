@@ -35,6 +35,19 @@ template <> __device__ __forceinline__ float nfma<float>(float a, float b, float
 template <> __device__ __forceinline__ double nfma<double>(double a, double b, double c) { return __fma_rn(a, b, c); }
 __device__ __forceinline__ float nsqrt(float a) { return sqrt_rn(Rn<float>(a)).v; }
 __device__ __forceinline__ double nsqrt(double a) { return sqrt_rn(Rn<double>(a)).v; }
+// sqrt(d * d) as the reference writes |d| (objects.py:1379-1380, envs/nonlinear/env.py:251).  In binary floating point with
+// round-to-nearest sqrt(fl(d*d)) == |d| whenever d*d neither underflows nor overflows (checked exhaustively for every
+// float32 in [2^-60, 2^60) and by sampling for float64); outside that range the literal expression is evaluated.
+__device__ __forceinline__ float sqrt_of_square(float d)
+{
+    const float a = fabsf(d);
+    return (a < 1.152921504606846976e18f && (a >= 8.673617379884035e-19f || a == 0.0f)) ? a : nsqrt(d * d);
+}
+__device__ __forceinline__ double sqrt_of_square(double d)
+{
+    const double a = fabs(d);
+    return (a < 3.273390607896142e150 && (a >= 3.054936363499605e-151 || a == 0.0)) ? a : nsqrt(d * d);   // 2^+-500
+}
 
 // CTA size: 256 threads (one CTA per SM: 255 registers x 256 threads fill the register file, 174 KB of shared memory) for
 // float32 networks, so that ONE barrier per step re-aligns all eight resident warps; 128 for float64 networks (their
@@ -351,7 +364,7 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
         bool nans = false;
 #pragma unroll
         for (int j = 0; j < 12; ++j) nans |= (x[j] != x[j]);
-        const double rse_k0 = nsqrt(e_th * e_th), rse_k1 = nsqrt(e_phi * e_phi + e_psi * e_psi);   // env.py:251
+        const double rse_k0 = sqrt_of_square(e_th), rse_k1 = nsqrt(e_phi * e_phi + e_psi * e_psi);   // env.py:251
         rse0 += rse_k0;                                                            // objects.py:1503-1504
         rse1 += rse_k1;
         if (k >= flight_step) { rse_f0 += rse_k0; rse_f1 += rse_k1; }              // functions.py:917,1039
@@ -484,7 +497,7 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
             }
             {   // actor (objects.py:1379-1388): smoothness terms, loss, update (the s_random pass ran above)
                 const TN dT = a_k - a_next, dS = a_k - a_random;
-                const TN L_T = nsqrt(dT * dT), L_S = nsqrt(dS * dS);
+                const TN L_T = sqrt_of_square(dT), L_S = sqrt_of_square(dS);
                 TN v[3];
 #pragma unroll
                 for (int j = 0; j < 3; ++j) v[j] = -((TN)rg[j] + gam * lt[j]);
