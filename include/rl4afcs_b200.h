@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RL4_ABI_VERSION 1
+#define RL4_ABI_VERSION 2      /* bumped whenever a struct, enum or signature below changes; _lib.load() checks it */
 
 enum rl4_policy { RL4_FP64 = 0, RL4_FP32 = 1, RL4_MIXED = 2 };
 enum rl4_elig   { RL4_ELIG_NONE = 0, RL4_ELIG_ACCUMULATING = 1, RL4_ELIG_REPLACING = 2 };
@@ -116,7 +116,9 @@ typedef struct rl4_sp_params {
     double hp[RL4_HP_COUNT];        /* shared scalars, indexed by rl4_sp_hp */
     int32_t hpi[RL4_HPI_COUNT];     /* shared ints, indexed by rl4_sp_hpi (fault_step < 0: no fault) */
     int32_t q3_alias;               /* reproduce the x aliasing at k == 1 (reference: 1) */
-    int32_t q7_numpy1;              /* numpy-1.x float32-vs-python-float compare (reference: 1) */
+    int32_t q7_numpy1;              /* 0 (default) = NEP 50 float32-vs-python-float compare, the behaviour OBSERVED when the
+                                     * verbatim agent runs under numpy >= 2; 1 = numpy-1.x value-based compare (derived from the promotion
+                                     * rules, never observed: opt-in, unverified) */
     const double*  hp_agent[RL4_HP_COUNT];    /* optional per-agent overrides, length n_agents */
     const int32_t* hpi_agent[RL4_HPI_COUNT];
 } rl4_sp_params;
@@ -144,6 +146,10 @@ typedef struct rl4_sp_log {
 
 /* ---- library ---- */
 int         rl4_abi_version(void);
+/* sizeof(rl4_sp_params) / sizeof(rl4_nl_params) as this library was compiled: the binding compares them with its own
+ * struct layouts before the first by-value call */
+int64_t     rl4_sizeof_sp_params(void);
+int64_t     rl4_sizeof_nl_params(void);
 const char* rl4_last_error(void);
 /* 0 if `device` is an sm_100 GPU this library can run on */
 int         rl4_device_check(int device);
@@ -259,9 +265,10 @@ enum rl4_nl_hpi {
     RL4_NHPI_MULTISTEP = 0, RL4_NHPI_WARMUP_STEPS, RL4_NHPI_COOLDOWN_STEPS, RL4_NHPI_FAULT_STEP,
     RL4_NHPI_FAULT_DAMP, RL4_NHPI_FAULT_SAT, RL4_NHPI_ELIG_A,
     RL4_NHPI_FLIGHT_STEP,      /* first step of the 'flight' phase of the RSE split (5500)      functions.py:916-917 */
-    RL4_NHPI_NUMPY2,           /* _adapt_check promotion rules (objects.py:1235-1284): 0 = numpy 1.x value-based casting (the
-                                * reference's era: float64 intermediates), 1 = NEP 50 / numpy >= 2 (python floats are weak:
-                                * float32 arithmetic once eta / lambda have become float32 arrays) */
+    RL4_NHPI_NUMPY2,           /* _adapt_check promotion rules (objects.py:1235-1284): 1 (default) = NEP 50 / numpy >= 2 (python
+                                * floats are weak: float32 arithmetic once eta / lambda have become float32 arrays) -- the mode
+                                * observed against the verbatim agent; 0 = numpy 1.x value-based casting (float64 intermediates),
+                                * derived from the promotion rules, never observed: opt-in, unverified */
     RL4_NHPI_COUNT
 };
 enum rl4_nl_fault_damp { RL4_NL_DAMP_NONE = 0, RL4_NL_DAMP_ELEVATOR, RL4_NL_DAMP_AILERON, RL4_NL_DAMP_RUDDER,
@@ -365,12 +372,62 @@ int rl4_nl_env_step(const rl4_nl_params* p, const double* theta_ref, int32_t ste
                     const double* action, double* out_mdp, double* out_reward, double* out_e_theta, double* out_surf,
                     double* out_eff, int64_t stride, int64_t n_agents, void* stream);
 
-/* ---- host-buffer episode (what a reference user calls: IDHPsp(...).train() for a batch) ----
- * Copies x0 / weights from host memory, runs rl4_sp_init + rl4_sp_run for n_steps on the GPU
- * and copies the final state planes and statistics back.  Host buffers may be pageable or pinned. */
+/* ---- step-API arithmetic that the reference does in TensorFlow / numpy one-liners ---- */
+/* Critic / Actor / Critic_big.soft_update (objects.py:207-215, 273-281, 353-361): target <- (1 - tau) target + tau source,
+ * three separately rounded operations per weight in the network dtype TN; target, source: [n_rows][stride] planes. */
+int rl4_soft_update(int policy, void* target, const void* source, double tau, int32_t n_rows, int64_t stride,
+                    int64_t n_agents, void* stream);
+/* Actor / Actor_big.get_weight_update (objects.py:261-271, 417-427): out[r] = loss * (TN) E[r]; loss [stride] (TN),
+ * E [n_rows][stride] (TE: the trace dtype of the policy, double on the nonlinear path), out [n_rows][stride] (TN). */
+int rl4_actor_weight_update(int policy, const void* loss, const void* E, void* out, int32_t n_rows, int64_t stride,
+                            int64_t n_agents, void* stream);
+
+/* ---- episode statistics ---- */
+/* Per-agent numbers of MC_run_seed (functions.py:53,57; utils.py:350-369) from the state planes after n_steps steps,
+ * out [RL4_SPS_COUNT][out_stride] doubles.  nMAE = mean|e| / (max ref - min ref) is an addition of this repo
+ * (BASELINE.json asks for it; the reference has no such statistic): ref = hp[REF_AMP] * ref_base, so the caller passes
+ * the extremes of ref_base over the episode. */
+enum rl4_sp_stat_field {
+    RL4_SPS_SUM_C = 0,      /* sum(c) / kappa                                  functions.py:53 */
+    RL4_SPS_CONV_TIME,      /* dt * last step with |alpha error| > 0.5 deg     utils.py:350-369 */
+    RL4_SPS_DIVERGED,       /* 1.0 if the run diverged (NaN state / reward)    functions.py:162; objects.py:991 */
+    RL4_SPS_UNSTEADY,       /* 1.0 if CONV_TIME > 30 s                         functions.py:165 */
+    RL4_SPS_MEAN_ABS_E,     /* sum|e| / n_steps */
+    RL4_SPS_NMAE,           /* MEAN_ABS_E / |amp * ref_base_max - amp * ref_base_min| */
+    RL4_SPS_COUNT
+};
+int rl4_sp_agent_stats(int policy, const rl4_sp_params* p, rl4_sp_state st, int64_t n_agents, int32_t n_steps,
+                       double ref_base_min, double ref_base_max, double* out, int64_t out_stride, void* stream);
+/* Per-agent numbers MC_test_hparam keeps (functions.py:916-917, 1036-1039, 1050-1055), out [RL4_NLS_COUNT][out_stride]. */
+enum rl4_nl_stat_field { RL4_NLS_RSE_WARMUP = 0, RL4_NLS_RSE_FLIGHT, RL4_NLS_RSE_LAT, RL4_NLS_NZ_PEAK, RL4_NLS_DIVERGED,
+                         RL4_NLS_COUNT };
+int rl4_nl_agent_stats(rl4_nl_state st, int64_t n_agents, double* out, int64_t out_stride, void* stream);
+/* MC_run's reduction over runs (functions.py:161-182): sums of n_fields (<= 8) per-agent planes [n_fields][stride] over
+ * n_agents agents.  `exclude` (may be NULL): a plane; agents with exclude != 0 (diverged runs, functions.py:176-178)
+ * are left out of the "kept" sums.  out [2 * n_fields + 2] (device) = for each field: sum over kept agents, sum over
+ * all agents; then the number of kept and of excluded agents.  Deterministic (fixed summation order, no atomics).
+ * `work`: device scratch of at least rl4_stats_reduce_work_doubles() doubles. */
+int64_t rl4_stats_reduce_work_doubles(void);
+int rl4_stats_reduce(const double* planes, int64_t stride, int32_t n_fields, const double* exclude, int64_t n_agents,
+                     double* out, double* work, int64_t work_doubles, void* stream);
+
+/* ---- host-buffer episodes (what a reference user calls: IDHPsp(...).train() / IDHPnonlin(...).train() for a batch) ----
+ * Copy the inputs from host memory, run init + the fused loop for n_steps on the GPU, copy the selected results back.
+ * Host buffers may be pageable or pinned (pinned: the agent chunks pipeline H2D / kernel / D2H over four streams). */
 typedef struct rl4_ctx rl4_ctx;
+/* `max_steps` bounds n_steps of the episodes run through this context; a context serves both paths (the nonlinear
+ * buffers are allocated by the first rl4_nl_episode_host call). */
 int rl4_ctx_create(int device, int policy, int64_t max_agents, int32_t max_steps, rl4_ctx** out);
 int rl4_ctx_destroy(rl4_ctx* ctx);
+/* which groups of final-state fields travel back (rows of the same full-plane host layout; unselected rows are not written) */
+enum rl4_out_mask {
+    RL4_OUT_STATS = 1,      /* SP: SUM_C, SUM_ABS_E + the int plane;  NL: RSE, NZ_PEAK, RSE_FLIGHT, ETA / LAMBDA + the int plane */
+    RL4_OUT_WEIGHTS = 2,    /* actor, critic, target-critic weights (IDHPsp.actor / critic / target_critic.trainable_weights) */
+    RL4_OUT_RLS = 4,        /* THETA, COV, EPS, EPS_NORM (IDHPsp.model) */
+    RL4_OUT_STATE = 8,      /* plant state, actions, M_prev, previous reward gradient, learning rates: what a resume needs */
+    RL4_OUT_TRACES = 16,    /* eligibility / Jacobian traces */
+    RL4_OUT_ALL = 31
+};
 typedef struct rl4_sp_host_io {
     const double* x0;           /* [2][n] */
     const double* w1a;          /* [4][n] */
@@ -381,9 +438,33 @@ typedef struct rl4_sp_host_io {
     void*    out_env;           /* [RL4_SPE_COUNT][n] of TE */
     void*    out_net;           /* [RL4_SPN_COUNT][n] of TN */
     int32_t* out_ints;          /* [RL4_SPI_COUNT][n] */
+    int32_t  out_mask;          /* rl4_out_mask bits; 0 = RL4_OUT_ALL */
+    int32_t  reserved;
 } rl4_sp_host_io;
 int rl4_sp_episode_host(rl4_ctx* ctx, const rl4_sp_params* p, const rl4_sp_host_io* io,
                         int64_t n_agents, int32_t n_steps, int32_t use_traces);
+
+/* N(0,1) float32 draws for the nonlinear agent's policy-smoothing term (tf.random.normal, objects.py:1375): Philox4x32-10
+ * keyed by `seed`, counter = (step, agent), Box-Muller; out[(k - k0) * stride + agent] for k in [k0, k0 + n_steps).
+ * TensorFlow's stream is not reproducible, so this is a stream of this repo; tests read it back and feed the oracle. */
+int rl4_nl_noise_fill(uint64_t seed, int32_t k0, int32_t n_steps, int64_t n_agents, float* out, int64_t stride, void* stream);
+typedef struct rl4_nl_host_io {
+    const double* w1a;          /* [40][n] (4,10) row-major */
+    const double* w2a;          /* [10][n] */
+    const double* w1c;          /* [40][n] */
+    const double* w2c;          /* [30][n] (10,3) row-major */
+    const double* theta_ref;    /* [n_steps] */
+    const float*  noise;        /* [n_steps][n] host N(0,1) draws, or NULL: generated on the device by rl4_nl_noise_fill(noise_seed) */
+    uint64_t      noise_seed;
+    double*  out_env;           /* [RL4_NLE_COUNT][n] */
+    void*    out_net;           /* [RL4_NLN_COUNT][n] of TN */
+    int32_t* out_ints;          /* [RL4_NLI_COUNT][n] */
+    int32_t  out_mask;          /* rl4_out_mask bits; 0 = RL4_OUT_ALL */
+    int32_t  reserved;
+} rl4_nl_host_io;
+/* IDHPnonlin(...).train() for a batch from host buffers (objects.py:1457-1564): rl4_nl_init + rl4_nl_run in chunks of
+ * agents x steps.  The context's policy must be RL4_MIXED or RL4_FP64. */
+int rl4_nl_episode_host(rl4_ctx* ctx, const rl4_nl_params* p, const rl4_nl_host_io* io, int64_t n_agents, int32_t n_steps);
 
 /* ---- measurement helpers (bench.py roofline denominators) ---- */
 /* Runs a dependent-FMA micro-kernel (is_double ? DFMA : FFMA) and returns achieved FLOP/s. */

@@ -150,6 +150,7 @@ int orc_nl_default_cfg(orc_nl_cfg* c)
     c->multistep = 0; c->warmup_steps = 400; c->cooldown_steps = 200; c->fault_step = -1;
     c->elig_a = 1; c->fault_damp = 0; c->fault_sat = 0; c->integrator = RL4_CIT_INTEGRATOR_ODE5;
     c->flight_step = 5500;
+    c->numpy2 = 1;                 /* NEP 50: the mode the verbatim agent was OBSERVED in (numpy 2.3); 0 = numpy 1.x, derived only */
     return 0;
 }
 

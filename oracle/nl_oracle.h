@@ -45,8 +45,9 @@ typedef struct {
     int32_t elig_a;             /* 0 none, 1 accumulating, 2 replacing */
     int32_t fault_damp, fault_sat, integrator;
     int32_t flight_step;        /* 5500: RSE split of functions.py:916-917,1038-1039 */
-    int32_t numpy2;             /* 0: numpy 1.x value-based promotion in _adapt_check (the reference's era, what the kernels
-                                 * implement); 1: NEP 50 (numpy >= 2, what the verbatim code does in this container) */
+    int32_t numpy2;             /* 1 (default): NEP 50 (numpy >= 2) -- what the verbatim code was OBSERVED to do in this container,
+                                 * the mode every golden fixture was generated in; 0: numpy 1.x value-based promotion in
+                                 * _adapt_check, derived from the promotion rules, never observed (opt-in, unverified) */
 } orc_nl_cfg;
 
 typedef struct {

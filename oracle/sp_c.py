@@ -192,7 +192,7 @@ def default_idhp_config() -> dict:
 
 
 def make_cfg(idhp_config=None, *, dt=0.02, fault_time=20, fault_scenario=None, ref_amp=None,
-             q3_alias=1, q7_numpy1=1, tracked_q=0, n=1) -> np.ndarray:
+             q3_alias=1, q7_numpy1=0, tracked_q=0, n=1) -> np.ndarray:
     """Build ``n`` identical orc_sp_cfg records from reference-style config dicts."""
     ic = default_idhp_config() if idhp_config is None else idhp_config
     k = ce500_coeffs()
@@ -324,3 +324,18 @@ def tanh_t13(x: np.ndarray) -> np.ndarray:
     y = np.empty_like(x)
     L.orc_tanh_t13_f64_array(_ptr(x), _ptr(y), x.size)
     return y
+
+
+def episode_stats(states: np.ndarray, cfg: np.ndarray, ref_base, n_steps: int) -> dict:
+    """Per-agent episode statistics from the oracle's final states: ``sum_c`` = sum(c)/kappa (functions.py:53),
+    ``converged_time`` (utils.py:350-369), ``diverged`` (functions.py:162; objects.py:991), ``mean_abs_e`` and
+    ``nmae`` = mean|e| / (max ref - min ref) with ref = ref_amp * ref_base[:n_steps] (an addition of the new repo:
+    BASELINE.json names the statistic, the reference has none -- SURVEY.md section 5.5)."""
+    base = np.asarray(ref_base, dtype=np.float64)[: max(int(n_steps), 1)]
+    kappa, amp = cfg["kappa"].astype(np.float64), cfg["ref_amp"].astype(np.float64)
+    mean_abs_e = states["sum_abs_e"] / float(max(int(n_steps), 1))
+    rng = np.abs(amp * base.max() - amp * base.min())
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return {"sum_c": states["sum_c"] / kappa, "converged_time": states["conv_step"].astype(np.float64) * cfg["dt"],
+                "diverged": (states["diverged_step"] >= 0) | (states["x_nan"] != 0),
+                "mean_abs_e": mean_abs_e, "nmae": mean_abs_e / rng}

@@ -55,7 +55,8 @@ typedef struct {
     int32_t fault_step;     /* int(fault_time/dt), <0 = no fault   envs/linear/env.py:128 */
     int32_t elig_a, elig_c; /* ORC_ELIG_* */
     int32_t q3_alias;       /* x aliasing at k == 1 (reference behaviour = 1) */
-    int32_t q7_numpy1;      /* numpy-1.x value-based compare of f32 lr vs python float */
+    int32_t q7_numpy1;      /* 0 (default) = NEP 50 compare, as observed with the verbatim agent under numpy 2.3;
+                             * 1 = numpy-1.x value-based compare of f32 lr vs python float (derived, unverified) */
     int32_t tracked_q;      /* 0: tracked_state 'alpha', 1: 'q'   envs/linear/env.py:180-184 */
     int32_t pad;
 } orc_sp_cfg;

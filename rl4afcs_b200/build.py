@@ -16,7 +16,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "librl4afcs_b200.so")
-SOURCES = ["runtime.cu", "sp_kernels.cu", "nl_kernels.cu"]
+SOURCES = ["runtime.cu", "sp_kernels.cu", "nl_kernels.cu", "step_kernels.cu", "host_episode.cu"]
 HEADERS = ["rl4_math.cuh", "sp_core.cuh", "rl4_runtime.h", os.path.join("..", "..", "include", "rl4afcs_b200.h"),
            os.path.join("..", "..", "include", "rl4_citation_surrogate.h")]
 

@@ -281,8 +281,11 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
     // PER_AGENT = false (no per-agent override array at all, the common case): every hyper-parameter read is a constant-
     // bank operand; true: a pointer test + load per read (about 150 instructions and the reloads of the spilled agent
     // index per step -- 10 % of the step time, so the uniform case gets its own instantiation)
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_agents) return;
+    // Tail threads of the last CTA do not exit: every thread of the CTA must reach the per-step barrier.  They shadow the
+    // last agent (loads only), are frozen like a diverged agent, and skip the store.
+    const int64_t i_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i_raw < n_agents;
+    const int64_t i = active ? i_raw : n_agents - 1;
     const NlHp<PER_AGENT> hv{p, i};
     const int64_t S = st.stride;
     double* __restrict__ E = st.env + i;
@@ -330,8 +333,9 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
     for (int j = 0; j < 9; ++j) Mp[j] = NF(RL4_NLN_MPREV + j);
     int cooldown = I[(int64_t)RL4_NLI_COOLDOWN * S], diverged_step = I[(int64_t)RL4_NLI_DIVERGED_STEP * S], stepp = I[(int64_t)RL4_NLI_STEPP * S];
     int pyfloat_mask = I[(int64_t)RL4_NLI_PYFLOAT_MASK * S];
+    if (!active) diverged_step = 0;
 
-    const bool logged = LOG && i < lg.n_agents_logged;
+    const bool logged = LOG && active && i < lg.n_agents_logged;
     const bool f32 = sizeof(TN) == 4;
     int k = k0;
     for (; k < k0 + n_steps; ++k) {
@@ -616,6 +620,7 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
     }
 
     // ---- store ----
+    if (!active) return;
     for (int j = 0; j < 12; ++j) { EF(RL4_NLE_XFULL + j) = x[j]; EF(RL4_NLE_THETA + j) = th[j]; }
     for (int j = 0; j < 3; ++j) { EF(RL4_NLE_XACT + j) = x_act[j]; EF(RL4_NLE_XLON + j) = x_lon[j]; EF(RL4_NLE_XPREVLON + j) = x_prev_lon[j]; EF(RL4_NLE_EPS + j) = eps[j]; }
     for (int j = 0; j < 16; ++j) EF(RL4_NLE_COV + j) = cv[j];
@@ -833,7 +838,7 @@ int rl4_nl_default_params(rl4_nl_params* p)
     p->hpi[RL4_NHPI_FAULT_STEP] = -1; p->hpi[RL4_NHPI_FAULT_DAMP] = 0; p->hpi[RL4_NHPI_FAULT_SAT] = 0;
     p->hpi[RL4_NHPI_ELIG_A] = RL4_ELIG_ACCUMULATING;
     p->hpi[RL4_NHPI_FLIGHT_STEP] = 5500;
-    p->hpi[RL4_NHPI_NUMPY2] = 0;
+    p->hpi[RL4_NHPI_NUMPY2] = 1;          // NEP 50: the mode observed against the verbatim agent (numpy 2.3); 0 = numpy 1.x, unverified
     p->integrator = RL4_CIT_INTEGRATOR_ODE5;
     return 0;
 }

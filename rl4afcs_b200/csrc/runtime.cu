@@ -50,29 +50,32 @@ static int run_peak(double* out_flops, cudaStream_t stream)
     RL4_CUDA(cudaGetDevice(&dev));
     RL4_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     T* d = nullptr;
-    RL4_CUDA(cudaMalloc(&d, sizeof(T)));
-    cudaEvent_t e0, e1;
-    RL4_CUDA(cudaEventCreate(&e0));
-    RL4_CUDA(cudaEventCreate(&e1));
-    const int blocks = sms * 8, threads = 256, iters = 4096;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = 0;
     double best = 0.0;
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    // single cleanup path: the buffer and both events are released on every exit
+    auto fail = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && rc == 0) rc = cuda_fail(e, what); return rc != 0; };
+    if (fail(cudaMalloc(&d, sizeof(T)), "cudaMalloc") || fail(cudaEventCreate(&e0), "cudaEventCreate") ||
+        fail(cudaEventCreate(&e1), "cudaEventCreate"))
+        goto done;
     for (int rep = 0; rep < 6; ++rep) {
-        RL4_CUDA(cudaEventRecord(e0, stream));
+        if (fail(cudaEventRecord(e0, stream), "cudaEventRecord")) goto done;
         fma_peak_kernel<T><<<blocks, threads, 0, stream>>>(d, iters, (T)0.999, (T)1e-3);
-        int rc = check_launch("fma_peak_kernel");
-        if (rc) return rc;
-        RL4_CUDA(cudaEventRecord(e1, stream));
-        RL4_CUDA(cudaEventSynchronize(e1));
+        rc = check_launch("fma_peak_kernel");
+        if (rc) goto done;
+        if (fail(cudaEventRecord(e1, stream), "cudaEventRecord") || fail(cudaEventSynchronize(e1), "cudaEventSynchronize")) goto done;
         float ms = 0.f;
-        RL4_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (fail(cudaEventElapsedTime(&ms, e0, e1), "cudaEventElapsedTime")) goto done;
         const double flops = 2.0 * 16.0 * iters * (double)blocks * threads / (ms * 1e-3);
         if (rep > 0 && flops > best) best = flops;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(d);
     *out_flops = best;
-    return 0;
+done:
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(d);
+    return rc;
 }
 
 // element-wise probes of the arithmetic primitives (tests/test_gpu_math.py)

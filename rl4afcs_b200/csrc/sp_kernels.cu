@@ -531,115 +531,4 @@ int rl4_sp_critic_weight_update(int policy, const void* td, const void* E, void*
     return check_launch("sp_critic_weight_update_kernel");
 }
 
-// ---- host-buffer episode -----------------------------------------------------------------
-struct rl4_ctx {
-    int device;
-    int policy;
-    int64_t max_agents;
-    int32_t max_steps;
-    static constexpr int kStreams = 4;
-    cudaStream_t streams[kStreams];
-    cudaEvent_t ref_ready;
-    double* d_in;        // [22][max_agents] x0(2) w1a(4) w2a(4) w1c(4) w2c(8)
-    double* d_ref;       // [max_steps]
-    void* d_env;
-    void* d_net;
-    int32_t* d_ints;
-    size_t te, tn;
-};
-
-int rl4_ctx_destroy(rl4_ctx* c);
-
-int rl4_ctx_create(int device, int policy, int64_t max_agents, int32_t max_steps, rl4_ctx** out)
-{
-    RL4_REQUIRE(out != nullptr, "out is NULL");
-    RL4_REQUIRE(max_agents > 0 && max_steps > 0, "bad capacity");
-    RL4_REQUIRE(policy == RL4_FP64 || policy == RL4_FP32 || policy == RL4_MIXED, "unknown policy");
-    int rc = rl4_device_check(device);
-    if (rc) return rc;
-    RL4_CUDA(cudaSetDevice(device));
-    rl4_ctx* c = new rl4_ctx();                        // value-initialised: every handle / pointer starts as null
-    c->device = device; c->policy = policy; c->max_agents = max_agents; c->max_steps = max_steps;
-    c->te = (policy == RL4_FP32) ? 4 : 8;
-    c->tn = (policy == RL4_FP64) ? 8 : 4;
-    // a failing allocation must not leak the handles created before it: collect the first error, then destroy
-    cudaError_t err = cudaSuccess;
-    const char* what = "";
-    auto step = [&](cudaError_t e, const char* w) { if (err == cudaSuccess && e != cudaSuccess) { err = e; what = w; } };
-    for (int i = 0; i < rl4_ctx::kStreams; ++i) step(cudaStreamCreateWithFlags(&c->streams[i], cudaStreamNonBlocking), "cudaStreamCreateWithFlags");
-    step(cudaEventCreateWithFlags(&c->ref_ready, cudaEventDisableTiming), "cudaEventCreateWithFlags");
-    if (err == cudaSuccess) step(cudaMalloc(&c->d_in, sizeof(double) * 22 * max_agents), "cudaMalloc(d_in)");
-    if (err == cudaSuccess) step(cudaMalloc(&c->d_ref, sizeof(double) * max_steps), "cudaMalloc(d_ref)");
-    if (err == cudaSuccess) step(cudaMalloc(&c->d_env, c->te * RL4_SPE_COUNT * max_agents), "cudaMalloc(d_env)");
-    if (err == cudaSuccess) step(cudaMalloc(&c->d_net, c->tn * RL4_SPN_COUNT * max_agents), "cudaMalloc(d_net)");
-    if (err == cudaSuccess) step(cudaMalloc(&c->d_ints, sizeof(int32_t) * RL4_SPI_COUNT * max_agents), "cudaMalloc(d_ints)");
-    if (err != cudaSuccess) {
-        rl4_ctx_destroy(c);
-        return rl4::cuda_fail(err, what);
-    }
-    *out = c;
-    return 0;
-}
-
-int rl4_ctx_destroy(rl4_ctx* c)
-{
-    if (!c) return 0;
-    cudaSetDevice(c->device);
-    cudaFree(c->d_in); cudaFree(c->d_ref); cudaFree(c->d_env); cudaFree(c->d_net); cudaFree(c->d_ints);
-    for (int i = 0; i < rl4_ctx::kStreams; ++i) if (c->streams[i]) cudaStreamDestroy(c->streams[i]);
-    if (c->ref_ready) cudaEventDestroy(c->ref_ready);
-    delete c;
-    return 0;
-}
-
-// The batch is cut into chunks of agents that flow through kStreams streams, so that the H2D copy of chunk
-// c+1, the fused kernel of chunk c and the D2H copy of chunk c-1 overlap (agents are independent; a chunk is just a
-// column range of the SoA planes).  With pinned host buffers the copies are fully asynchronous.
-int rl4_sp_episode_host(rl4_ctx* c, const rl4_sp_params* p, const rl4_sp_host_io* io, int64_t n, int32_t n_steps,
-                        int32_t use_traces)
-{
-    RL4_REQUIRE(c && p && io, "NULL argument");
-    RL4_REQUIRE(n > 0 && n <= c->max_agents && n_steps > 0 && n_steps <= c->max_steps, "size exceeds the context capacity");
-    RL4_REQUIRE(io->x0 && io->w1a && io->w2a && io->w1c && io->w2c && io->ref_base, "NULL input buffer");
-    RL4_CUDA(cudaSetDevice(c->device));
-    const int64_t S = c->max_agents;
-    RL4_CUDA(cudaMemcpyAsync(c->d_ref, io->ref_base, sizeof(double) * n_steps, cudaMemcpyHostToDevice, c->streams[0]));
-    RL4_CUDA(cudaEventRecord(c->ref_ready, c->streams[0]));
-    int64_t n_chunks = n / 65536;
-    if (n_chunks < 1) n_chunks = 1;
-    if (n_chunks > 8) n_chunks = 8;
-    const int64_t per = ((n + n_chunks - 1) / n_chunks + 127) / 128 * 128;
-    const struct { const double* host; int rows; int64_t dev_row; } ins[5] = {
-        {io->x0, 2, 0}, {io->w1a, 4, 2}, {io->w2a, 4, 6}, {io->w1c, 4, 10}, {io->w2c, 8, 14}};
-    int ci = 0;
-    for (int64_t off = 0; off < n; off += per, ++ci) {
-        const int64_t m = (n - off < per) ? (n - off) : per;
-        cudaStream_t s = c->streams[ci % rl4_ctx::kStreams];
-        if (ci % rl4_ctx::kStreams != 0 || ci >= rl4_ctx::kStreams) RL4_CUDA(cudaStreamWaitEvent(s, c->ref_ready, 0));
-        for (const auto& in : ins)   // host planes are [rows][n]; device planes are [rows][S]
-            RL4_CUDA(cudaMemcpy2DAsync(c->d_in + in.dev_row * S + off, S * 8, in.host + off, n * 8, m * 8, in.rows,
-                                       cudaMemcpyHostToDevice, s));
-        rl4_sp_params pc = *p;       // per-agent override arrays follow the chunk
-        for (int j = 0; j < RL4_HP_COUNT; ++j) if (pc.hp_agent[j]) pc.hp_agent[j] += off;
-        for (int j = 0; j < RL4_HPI_COUNT; ++j) if (pc.hpi_agent[j]) pc.hpi_agent[j] += off;
-        rl4_sp_state st{(char*)c->d_env + off * c->te, (char*)c->d_net + off * c->tn, c->d_ints + off, S};
-        int rc = rl4_sp_init(c->policy, &pc, c->d_in + off, c->d_in + 2 * S + off, c->d_in + 6 * S + off, c->d_in + 10 * S + off,
-                             c->d_in + 14 * S + off, S, st, m, s);
-        if (rc) return rc;
-        rl4_sp_log lg{nullptr, RL4_LOG_NONE, 1, 0};
-        rc = rl4_sp_run(c->policy, &pc, c->d_ref, 0, n_steps, st, m, use_traces, lg, s);
-        if (rc) return rc;
-        if (io->out_env)
-            RL4_CUDA(cudaMemcpy2DAsync((char*)io->out_env + off * c->te, n * c->te, st.env, S * c->te, m * c->te, RL4_SPE_COUNT,
-                                       cudaMemcpyDeviceToHost, s));
-        if (io->out_net)
-            RL4_CUDA(cudaMemcpy2DAsync((char*)io->out_net + off * c->tn, n * c->tn, st.net, S * c->tn, m * c->tn, RL4_SPN_COUNT,
-                                       cudaMemcpyDeviceToHost, s));
-        if (io->out_ints)
-            RL4_CUDA(cudaMemcpy2DAsync(io->out_ints + off, n * 4, st.ints, S * 4, m * 4, RL4_SPI_COUNT, cudaMemcpyDeviceToHost, s));
-    }
-    for (int i = 0; i < rl4_ctx::kStreams; ++i) RL4_CUDA(cudaStreamSynchronize(c->streams[i]));
-    return 0;
-}
-
 }  // extern "C"

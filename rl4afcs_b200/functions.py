@@ -41,7 +41,8 @@ def MC_run_seed(idhp: IDHPsp) -> dict:
 def MC_run(n_configs, configs, env_config, seeds, *, device="cuda", dtype="mixed", base_seed=0, log_agents=0, weights=None):
     """Monte-Carlo over ``n_configs`` hyper-parameter sets x ``seeds`` seeds in ONE batch (functions.py:62-232 ran
     a process pool of 10).  ``configs`` has the reference's keys (lambda_hs, lambda_ls, kappas, cooldown_times, sigmas,
-    warmup_times, elig_a, lr_a_hs, lr_a_ls, lr_c_hs, lr_c_ls, multistep), each None or a list per config.
+    warmup_times, elig_a, lr_a_hs, lr_a_ls, lr_c_hs, lr_c_ls, multistep), each None or a list per config (``sigmas`` is
+    honoured per config: seed s of every config starts from the same standard-normal draw scaled by that config's sigma).
     Returns (metrics per config, idhp): metrics = dict(avg_PSD_err?, avg_c, avg_t, diverged, unsteady_convergence)
     as functions.py:223-227 (PSD error only when trajectories are logged).  ``weights``: optional dict of (B, w) initial
     weights (agent index = config * seeds + seed).  Like the reference, ``avg_c`` averages the non-diverged runs while
@@ -59,7 +60,7 @@ def MC_run(n_configs, configs, env_config, seeds, *, device="cuda", dtype="mixed
     idhp_config = {"multistep": col("multistep").astype(np.int64), "gamma": 0.6, "gamma_rls": 1.0,
                    "lambda_h": col("lambda_hs").astype(np.float64), "lambda_l": col("lambda_ls").astype(np.float64),
                    "kappa": col("kappas").astype(np.float64), "cooldown_time": col("cooldown_times").astype(np.float64),
-                   "sigma": float(sig[0]), "warmup_time": col("warmup_times").astype(np.float64), "error_thresh": 1,
+                   "sigma": sig, "warmup_time": col("warmup_times").astype(np.float64), "error_thresh": 1,
                    "tau": 0.01, "in_dims": 1,
                    "actor_config": {"layers": {4: "tanh", env_config["action_dim"]: "tanh"},
                                     "eta_h": col("lr_a_hs").astype(np.float64), "eta_l": col("lr_a_ls").astype(np.float64),
@@ -70,6 +71,11 @@ def MC_run(n_configs, configs, env_config, seeds, *, device="cuda", dtype="mixed
                    "rls_config": {"state_dim": env_config["state_dim"], "action_dim": env_config["action_dim"],
                                   "rls_gamma": 1, "rls_cov": 10 ** 6}}
     env = Ce500ShortPeriod(env_config, batch=B, device=device, dtype=dtype)
+    if weights is None:
+        # functions.py:80,97,131-139: every config runs seeds 0..seeds-1, so seed s starts every config from the same
+        # standard-normal draw, scaled by that config's own sigma
+        from . import sp_engine
+        weights = sp_engine.truncated_normal_weights(seeds, base_seed, sig, env._engine.device, repeat=n_configs)
     idhp = IDHPsp(env, idhp_config, verbose=0, seed=base_seed, weights=weights, log="full" if log_agents else None,
                   log_agents=log_agents)
     idhp.train()
@@ -103,7 +109,7 @@ _ALGOS = {(0, None): "idhp", (0, "replacing"): "idhprt", (0, "accumulating"): "i
 
 
 def MC_test_hparam(configs, directory, env, N, repetitions, save=0, show=0, transparency=0.2, *, noise=None, weights=None,
-                   flight_step=5500, numpy2=False):
+                   flight_step=5500, numpy2=True):
     """Nonlinear-task Monte-Carlo of functions.py:931-1060: ``N`` hyper-parameter sets (``configs`` = dict of lists with
     the reference's keys etaah, etaal, etach, etacl, lambda_hs, lambda_ls, seeds, ms, elig) x ``repetitions`` seeds, run
     as ONE batch of N * repetitions agents (agent index = config * repetitions + seed).

@@ -136,6 +136,14 @@ class NlEngine:
         self.k += n_steps
         return log_t
 
+    def stats_planes(self) -> torch.Tensor:
+        """(NLS.COUNT, n) float64 per-agent statistics computed by ``rl4_nl_agent_stats`` (rows: _lib.NLS)."""
+        out = torch.empty((_lib.NLS["COUNT"], self.stride), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.rl4_nl_agent_stats(self.state_struct(), self.n, out.data_ptr(), self.stride, self._stream()),
+                       "rl4_nl_agent_stats")
+        return out[:, : self.n]
+
     def stats(self):
         return {"rse": self.env_field("RSE", 2).t().clone(), "rse_flight": self.env_field("RSE_FLIGHT", 2).t().clone(),
                 "nz_peak": self.env_field("NZ_PEAK")[0].clone(),

@@ -148,12 +148,8 @@ class _Net:
 
     def soft_update(self, source_weights, tau):
         """target <- (1 - tau) * target + tau * source, three separately rounded float ops per weight
-        (objects.py:207-215)."""
-        for tgt, src in zip(self.trainable_weights, source_weights):
-            src = torch.as_tensor(src, device=tgt.device).to(tgt.dtype).reshape(tgt.shape)
-            omt = torch.tensor(1.0 - tau, dtype=torch.float64).to(tgt.dtype)
-            tt = torch.tensor(float(tau), dtype=torch.float64).to(tgt.dtype)
-            tgt.copy_(tgt.mul(omt).add_(src.mul(tt)))
+        (objects.py:207-215), computed by ``rl4_soft_update``."""
+        _soft_update(self._eng, [(self._w1, 4), (self._w2, 4 * self._n_out)], source_weights, tau, self.batch)
 
 
 class Critic(_Net):
@@ -225,9 +221,8 @@ class Actor(_Net):
 
     def get_weight_update(self, loss):
         """loss (B,1,1) -> [W1_update (B,1,4), W2_update (B,4,1)] = loss * E (objects.py:261-271)."""
-        e = self._eng
-        g = torch.as_tensor(loss, device=e.device).to(e.tn).reshape(self.batch, 1) * self.E.reshape(self.batch, 8).to(e.tn)
-        return [g[:, 4:8].reshape(self.batch, 1, 4), g[:, 0:4].reshape(self.batch, 4, 1)]
+        g = _actor_weight_update(self._eng, loss, 8, self.batch)          # (8, B): rows = E's columns
+        return [g[4:8].t().reshape(self.batch, 1, 4), g[0:4].t().reshape(self.batch, 4, 1)]
 
 
 # ------------------------------------------------------------------------------------------
@@ -241,12 +236,13 @@ class IDHPsp:
     keyword arguments: ``weights`` (dict W1a (B,4), W2a (B,4), W1c (B,4), W2c (B,8); default:
     TruncatedNormal(sigma) drawn on the device from ``seed``), ``log`` ('full' | 'basic' | None),
     ``log_agents`` (how many leading agents are logged), ``log_every``; ``numpy2`` selects how `_adapt_check`'s
-    `eta_a != self.eta_a` (objects.py:819) compares a float32 with a python float: numpy 1.x value-based promotion (the
-    reference's era, default: the comparison is True at k = 1 and a cooldown starts) or NEP 50 (numpy >= 2).
+    `eta_a != self.eta_a` (objects.py:819) compares a float32 with a python float: True (default) = NEP 50 (numpy >= 2), the
+    behaviour OBSERVED by running the verbatim agent (every golden fixture); False = numpy 1.x value-based promotion (the
+    comparison is True at k = 1 and a cooldown starts) -- derived from the promotion rules, never observed: unverified.
     """
 
     def __init__(self, env, config, verbose=True, seed=1, *, weights=None, log="full", log_agents=None,
-                 log_every: int = 1, ref_amp=None, numpy2: bool = False) -> None:
+                 log_every: int = 1, ref_amp=None, numpy2: bool = True) -> None:
         self.seed = seed
         env._engine.params.q7_numpy1 = 0 if numpy2 else 1   # Q7: float32-vs-python-float compare at k = 1 (numpy 1.x) or NEP 50
         self.gamma = config["gamma"]
@@ -291,7 +287,7 @@ class IDHPsp:
         self.model = RLS(config["rls_config"], _engine=eng)
         self.n, self.m = self.model.state_dim, self.model.action_dim
         if weights is None:
-            weights = sp_engine.truncated_normal_weights(self.batch, seed, float(np.ravel(config["sigma"])[0]), eng.device)
+            weights = sp_engine.truncated_normal_weights(self.batch, seed, config["sigma"], eng.device)   # scalar or per-agent sigma
         self._init_weights = weights
 
     # ---- the hot path ---------------------------------------------------------------------
@@ -403,12 +399,8 @@ class Critic_big(_BigNetView):
     call = __call__
 
     def soft_update(self, source_weights, tau):
-        """target <- (1 - tau) target + tau source (objects.py:353-361), separately rounded."""
-        for tgt, src in zip(self.trainable_weights, source_weights):
-            src = torch.as_tensor(src, device=tgt.device).to(tgt.dtype).reshape(tgt.shape)
-            omt = torch.tensor(1.0 - tau, dtype=torch.float64).to(tgt.dtype)
-            tt = torch.tensor(float(tau), dtype=torch.float64).to(tgt.dtype)
-            tgt.copy_(tgt.mul(omt).add_(src.mul(tt)))
+        """target <- (1 - tau) target + tau source (objects.py:353-361), separately rounded, by ``rl4_soft_update``."""
+        _soft_update(self._eng, [(self._w1, 40), (self._w2, 10 * self._n_out)], source_weights, tau, self.batch)
 
 
 class Actor_big(_BigNetView):
@@ -439,8 +431,7 @@ class Actor_big(_BigNetView):
 
     def get_weight_update(self, loss):
         """loss (B,1,1) -> [W1_update (B,4,10), W2_update (B,10,1)] = loss * E (objects.py:417-427)."""
-        e = self._eng
-        g = torch.as_tensor(loss, device=e.device).to(e.tn).reshape(self.batch, 1) * self.E.reshape(self.batch, 50).to(e.tn)
+        g = _actor_weight_update(self._eng, loss, 50, self.batch).t()     # (B, 50)
         return [g[:, 10:].reshape(self.batch, 10, 4).transpose(1, 2), g[:, 0:10].reshape(self.batch, 10, 1)]
 
 
@@ -522,8 +513,9 @@ class IDHPnonlin:
     generator (or supplied: ``noise=`` (steps, B) float32), the initial weights are TruncatedNormal(sigma) from
     ``seed`` or ``weights=`` (W1a (B,40), W2a (B,10), W1c (B,40), W2c (B,30)).
 
-    ``numpy2``: the float32 / float64 promotion rules `_adapt_check` (objects.py:1235-1284) runs under -- False = numpy 1.x
-    value-based casting (the reference's era, default), True = NEP 50 (what the verbatim code does under numpy >= 2).
+    ``numpy2``: the float32 / float64 promotion rules `_adapt_check` (objects.py:1235-1284) runs under -- True (default) = NEP 50,
+    what the verbatim code was OBSERVED to do under numpy >= 2 (every golden fixture); False = numpy 1.x value-based casting,
+    derived from the promotion rules and never observed (opt-in, unverified).
 
     ``log``: "full" = the reference's log dict (objects.py:1083-1176) for the first ``log_agents`` agents, every array
     with a leading agent axis; "compact" = x_full / a / e / reward / a_cmd only; "mc" = the per-step quantities
@@ -531,7 +523,7 @@ class IDHPnonlin:
     """
 
     def __init__(self, env, config, verbose=True, seed=1, *, weights=None, log="full", log_agents=None,
-                 chunk: int = 1000, numpy2: bool = False) -> None:
+                 chunk: int = 1000, numpy2: bool = True) -> None:
         from . import nl_engine  # noqa: F401
 
         assert log in ("full", "compact", "mc", None)
@@ -656,6 +648,29 @@ class IDHPnonlin:
 
     def stats(self) -> dict:
         return self._eng.stats()
+
+
+def _soft_update(e, fields, source_weights, tau, batch):
+    """Polyak update of the weight planes ``fields`` = [(net-plane field, rows), ...] from reference-shaped source arrays
+    [W1 (B,in,h), W2 (B,h,out)] through the C-ABI (objects.py:207-215, 353-361)."""
+    for (name, rows), src in zip(fields, source_weights):
+        sp = torch.as_tensor(src, device=e.device).to(e.tn).reshape(batch, rows).t().contiguous()     # (rows, B) plane
+        assert e.stride == batch
+        with torch.cuda.device(e.device):
+            rc = e.lib.rl4_soft_update(e.policy_id, e.net_field(name, rows).data_ptr(), sp.data_ptr(), float(tau), rows,
+                                       e.stride, batch, e._stream())
+            _lib.check(rc, "rl4_soft_update")
+
+
+def _actor_weight_update(e, loss, rows, batch):
+    """loss * E (E stored in the trace dtype, cast to the tensor dtype: objects.py:261-271, 417-427) -> (rows, B) planes."""
+    lp = torch.as_tensor(loss, device=e.device).to(e.tn).reshape(batch).contiguous()
+    out = torch.empty((rows, e.stride), dtype=e.tn, device=e.device)
+    with torch.cuda.device(e.device):
+        rc = e.lib.rl4_actor_weight_update(e.policy_id, lp.data_ptr(), e.env_field("EA", rows).data_ptr(), out.data_ptr(), rows,
+                                           e.stride, batch, e._stream())
+        _lib.check(rc, "rl4_actor_weight_update")
+    return out[:, :batch]
 
 
 def _first(v):

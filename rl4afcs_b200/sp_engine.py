@@ -96,7 +96,7 @@ class SpEngine:
             for j in range(2):
                 self.params.B[v][j] = float(B.reshape(-1)[j])
         self.params.q3_alias = 1
-        self.params.q7_numpy1 = 1
+        self.params.q7_numpy1 = 0     # NEP 50 compare (the mode observed against the verbatim agent); 1 = numpy 1.x, unverified
         self._keep = {}          # per-agent override tensors kept alive
         self.use_traces = False
         self.ref_base = None
@@ -144,7 +144,8 @@ class SpEngine:
         return False
 
     def set_reference(self, ref_base) -> None:
-        self.ref_base = torch.as_tensor(np.asarray(ref_base, dtype=np.float64)).to(self.device).contiguous()
+        self._ref_host = np.ascontiguousarray(np.asarray(ref_base, dtype=np.float64))
+        self.ref_base = torch.as_tensor(self._ref_host).to(self.device).contiguous()
 
     # ---- state views -------------------------------------------------------------------
     def state_struct(self) -> _lib.SpState:
@@ -204,20 +205,26 @@ class SpEngine:
         return log_t
 
     # ---- episode statistics (functions.py:39-60; utils.py:350-369) --------------------------
+    def stats_planes(self, n_steps=None) -> torch.Tensor:
+        """(SPS.COUNT, n) float64 per-agent statistics computed by ``rl4_sp_agent_stats`` (rows: _lib.SPS)."""
+        n_steps = self.k if n_steps is None else int(n_steps)
+        out = torch.empty((_lib.SPS["COUNT"], self.stride), dtype=torch.float64, device=self.device)
+        ref = getattr(self, "_ref_host", None)
+        seg = ref[: max(n_steps, 1)] if ref is not None and ref.size else np.zeros(1)
+        with torch.cuda.device(self.device):
+            rc = self.lib.rl4_sp_agent_stats(self.policy_id, ctypes.byref(self.params), self.state_struct(), self.n, n_steps,
+                                             float(seg.min()), float(seg.max()), out.data_ptr(), self.stride, self._stream())
+            _lib.check(rc, "rl4_sp_agent_stats")
+        return out[:, : self.n]
+
     def stats(self, n_steps=None) -> dict:
-        n_steps = self.k if n_steps is None else n_steps
-        kappa = self._keep.get(("hp", HP["KAPPA"]))
-        kappa = kappa if kappa is not None else self.params.hp[HP["KAPPA"]]
-        sum_c = self.env_field("SUM_C")[0].to(torch.float64)
-        conv = self.int_field("CONV_STEP")
-        div_step = self.int_field("DIVERGED_STEP")
-        flags = self.int_field("FLAGS")
-        return {
-            "sum_c": sum_c / kappa,                                    # functions.py:53
-            "converged_time": conv.to(torch.float64) * self.params.dt,  # utils.py:366-368
-            "diverged": (div_step >= 0) | ((flags & _lib.SPF["X_NAN"]) != 0),   # functions.py:162
-            "mean_abs_e": self.env_field("SUM_ABS_E")[0].to(torch.float64) / max(n_steps, 1),
-        }
+        """Per-agent episode statistics: ``sum_c`` (functions.py:53), ``converged_time`` (utils.py:350-369), ``diverged``
+        (functions.py:162), ``mean_abs_e`` and ``nmae`` = mean|e| / (max ref - min ref) -- the normalised tracking error
+        BASELINE.json names (the reference has no such statistic; it is an addition of this repo)."""
+        S = _lib.SPS
+        pl = self.stats_planes(n_steps)
+        return {"sum_c": pl[S["SUM_C"]], "converged_time": pl[S["CONV_TIME"]], "diverged": pl[S["DIVERGED"]] != 0,
+                "unsteady": pl[S["UNSTEADY"]] != 0, "mean_abs_e": pl[S["MEAN_ABS_E"]], "nmae": pl[S["NMAE"]]}
 
 
 def default_reference(t_end=60, dt=0.02, period=10):
@@ -259,12 +266,22 @@ def apply_idhp_config(eng: SpEngine, cfg: dict, *, dt: float) -> None:
     eng.set_hpi("ELIG_C", elig(cfg["critic_config"]["elig"]))
 
 
-def truncated_normal_weights(n: int, seed: int, sigma: float, device) -> dict:
+def truncated_normal_weights(n: int, seed: int, sigma, device, *, repeat: int = 1) -> dict:
     """TruncatedNormal(0, sigma), re-drawn beyond 2 sigma (the keras initializer of
     objects.py:74), from torch's Philox generator on the device.  TensorFlow's own stream is not
-    reproducible outside TF, so weights are always explicit data here."""
+    reproducible outside TF, so weights are always explicit data here.
+
+    ``sigma`` may be a per-agent array (length n * repeat).  ``repeat`` > 1 draws the standard-normal numbers for ``n``
+    agents once and tiles them ``repeat`` times before scaling: a Monte-Carlo over ``repeat`` hyper-parameter sets x ``n``
+    seeds in which seed s starts every set from the same draw, scaled by that set's sigma (functions.py:80,97: the
+    reference re-uses seeds 0..seeds-1 for every config)."""
     g = torch.Generator(device=device)
     g.manual_seed(int(seed))
+    if np.ndim(sigma) == 0:
+        sig = float(sigma)
+    else:
+        sig = torch.as_tensor(np.asarray(sigma, dtype=np.float64)).to(device=device, dtype=torch.float32).reshape(-1, 1)
+        assert sig.shape[0] == n * repeat, f"sigma: expected {n * repeat} values"
 
     def draw(width):
         out = torch.randn((n, width), generator=g, device=device, dtype=torch.float32)
@@ -272,7 +289,9 @@ def truncated_normal_weights(n: int, seed: int, sigma: float, device) -> dict:
         while bool(bad.any()):
             out = torch.where(bad, torch.randn((n, width), generator=g, device=device, dtype=torch.float32), out)
             bad = out.abs() > 2.0
-        return (out * sigma).to(torch.float64)
+        if repeat > 1:
+            out = out.repeat(repeat, 1)
+        return (out * sig).to(torch.float64)
 
     return {"W1a": draw(4), "W2a": draw(4), "W1c": draw(4), "W2c": draw(8)}
 

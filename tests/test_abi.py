@@ -25,7 +25,22 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), n
     assert sorted(_lib.EXPORTS) == names
-    assert L.rl4_abi_version() == 1
+    hdr = open(os.path.join(ROOT, "include", "rl4afcs_b200.h")).read()
+    assert L.rl4_abi_version() == _lib.ABI_VERSION == int(re.search(r"#define RL4_ABI_VERSION (\d+)", hdr).group(1))
+    # load() refuses a library whose struct layouts differ from the binding's
+    assert L.rl4_sizeof_sp_params() == ctypes.sizeof(_lib.SpParams) and L.rl4_sizeof_nl_params() == ctypes.sizeof(_lib.NlParams)
+
+
+def test_load_rejects_a_stale_library(monkeypatch):
+    """A library built from an older header (other ABI version / struct sizes) must not load silently (by-value structs
+    of another layout would corrupt kernel parameters)."""
+    from rl4afcs_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "ABI_VERSION", _lib.ABI_VERSION + 1)
+    with pytest.raises(_lib.Rl4Error, match="rebuild"):
+        _lib.load()
+    monkeypatch.setattr(_lib, "_lib", None)
 
 
 def test_struct_layouts_match_header_constants():
@@ -33,7 +48,7 @@ def test_struct_layouts_match_header_constants():
 
     hdr = open(os.path.join(ROOT, "include", "rl4afcs_b200.h")).read()
     for table, prefix in ((_lib.SPE, "RL4_SPE_"), (_lib.SPN, "RL4_SPN_"), (_lib.SPI, "RL4_SPI_"), (_lib.LF, "RL4_LF_"), (_lib.LB, "RL4_LB_"),
-                          (_lib.NLL, "RL4_NLL_"), (_lib.NLF, "RL4_NLF_")):
+                          (_lib.NLL, "RL4_NLL_"), (_lib.NLF, "RL4_NLF_"), (_lib.OUT, "RL4_OUT_")):
         for k, v in table.items():
             m = re.search(prefix + k + r"\s*=\s*(\d+)", hdr)
             assert m and int(m.group(1)) == v, (prefix, k)
@@ -45,6 +60,12 @@ def test_struct_layouts_match_header_constants():
             key = nm.replace("RL4_HPI_", "").replace("RL4_HP_", "")
             assert table[key] == i, nm
     assert ctypes.sizeof(_lib.SpParams) == 8 * (16 + 8 + 1 + 14) + 4 * (8 + 2) + 8 * (14 + 8)
+    for table, enum, prefix in ((_lib.SPS, "rl4_sp_stat_field", "RL4_SPS_"), (_lib.NLS, "rl4_nl_stat_field", "RL4_NLS_")):
+        body = re.search(r"enum " + enum + r"\s*\{(.*?)\}", hdr, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = [t.strip().split("=")[0].strip() for t in body.split(",") if t.strip()]
+        assert [table[nm.replace(prefix, "")] for nm in names] == list(range(len(names))), enum
+    assert ctypes.sizeof(_lib.SpHostIO) == 8 * 9 + 8 and ctypes.sizeof(_lib.NlHostIO) == 8 * 10 + 8
 
 
 def test_no_cpu_fallback():
@@ -93,4 +114,4 @@ def test_nl_default_params_equal_oracle_defaults(oracle):
     hi = _lib.NHPI
     assert p.hpi[hi["WARMUP_STEPS"]] == cfg["warmup_steps"] and p.hpi[hi["COOLDOWN_STEPS"]] == cfg["cooldown_steps"]
     assert p.hpi[hi["MULTISTEP"]] == cfg["multistep"] and p.hpi[hi["ELIG_A"]] == cfg["elig_a"] and p.hpi[hi["FAULT_STEP"]] == cfg["fault_step"]
-    assert p.hpi[hi["FLIGHT_STEP"]] == cfg["flight_step"] == 5500 and p.hpi[hi["NUMPY2"]] == 0 and p.integrator == cfg["integrator"]
+    assert p.hpi[hi["FLIGHT_STEP"]] == cfg["flight_step"] == 5500 and p.hpi[hi["NUMPY2"]] == cfg["numpy2"] == 1 and p.integrator == cfg["integrator"]

@@ -7,6 +7,25 @@ import pytest
 torch = pytest.importorskip("torch")
 
 
+def _summary_part(n, n_div, conv_time, sum_c, mean_abs_e, nmae):
+    """What rl4_stats_reduce writes for one rank (rl4afcs_b200/dist.py layout): per SPS field the sum over the
+    non-diverged agents and over all agents, then n_kept, n_excluded."""
+    from rl4afcs_b200 import _lib
+    from rl4afcs_b200 import dist as rdist
+
+    S = _lib.SPS
+    part = torch.zeros(rdist.SUMMARY_LEN, dtype=torch.float64)
+    kept = n - n_div
+    for f, v in (("SUM_C", sum_c), ("CONV_TIME", conv_time), ("MEAN_ABS_E", mean_abs_e), ("NMAE", nmae),
+                 ("UNSTEADY", 1.0 if conv_time > 30 else 0.0)):
+        part[2 * S[f]] = kept * v
+        part[2 * S[f] + 1] = n * v
+    part[2 * S["DIVERGED"] + 1] = n_div
+    part[2 * S["COUNT"]] = kept
+    part[2 * S["COUNT"] + 1] = n_div
+    return part
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
 
@@ -15,19 +34,15 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    lo, hi = rdist.shard_bounds(10, world, rank)
+    lo, hi = rdist.shard_bounds(11, world, rank)          # 6 + 5 agents: unequal shards
     n = hi - lo
-    stats = {"diverged": torch.tensor([False] * (n - 1) + [rank == 1]),
-             "converged_time": torch.full((n,), 10.0 + 25.0 * rank, dtype=torch.float64),
-             "sum_c": torch.full((n,), -1.0 - rank, dtype=torch.float64),
-             "mean_abs_e": torch.full((n,), 0.01, dtype=torch.float64)}
-    part = rdist.episode_summary_tensor(stats)
-    parts = [torch.empty_like(part) for _ in range(world)]
-    dist.all_gather(parts, part)
-    out = rdist.reduce_summary(torch.stack(parts))
-    per_agent = rdist.gather_per_agent(torch.arange(lo, hi, dtype=torch.float64)[:, None], world) if n * world == 10 else None
+    part = _summary_part(n, 1 if rank == 1 else 0, 10.0 + 25.0 * rank, -1.0 - rank, 0.01, 0.05)
+    out = rdist.gather_episode_summary(None, world, part=part)          # the function bench.py calls, under a process group
+    mine = torch.arange(lo, hi, dtype=torch.float64)[:, None]
+    per_agent = rdist.gather_per_agent(mine, world, n_total=11)
+    per_agent2 = rdist.gather_per_agent(mine, world)                     # sizes exchanged first
     if rank == 0:
-        q.put((out, None if per_agent is None else per_agent.ravel().tolist()))
+        q.put((out, per_agent.ravel().tolist(), per_agent2.ravel().tolist()))
     dist.destroy_process_group()
 
 
@@ -51,10 +66,12 @@ def test_episode_summary_gather_gloo_world2():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    out, per_agent = q.get(timeout=120)
+    out, per_agent, per_agent2 = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert out["agents"] == 10 and out["diverged"] == 1 and out["unsteady_convergence"] == 5
-    assert abs(out["avg_c"] - (5 * -1.0 + 4 * -2.0) / 9) < 1e-12
-    assert per_agent == [float(i) for i in range(10)]
+    assert out["agents"] == 11 and out["diverged"] == 1 and out["unsteady_convergence"] == 5
+    assert abs(out["avg_c"] - (6 * -1.0 + 4 * -2.0) / 10) < 1e-12
+    assert abs(out["avg_t"] - (6 * 10.0 + 4 * 35.0) / 10) < 1e-12 and abs(out["avg_t_all"] - (6 * 10.0 + 5 * 35.0) / 11) < 1e-12
+    assert abs(out["avg_nmae"] - 0.05) < 1e-15 and abs(out["avg_abs_e"] - 0.01) < 1e-15
+    assert per_agent == [float(i) for i in range(11)] and per_agent2 == per_agent

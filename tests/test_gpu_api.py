@@ -144,7 +144,7 @@ def test_idhpsp_train_equals_reference_run(oracle, name):
     B = 2
     env = Ce500ShortPeriod(_env_config(oracle, g["x0"].reshape(2, 1), FAULTS[str(g["fault"])], str(g["tracked"])), batch=B, dtype="mixed")
     w = {k: np.broadcast_to(g[f"w_{k}"], (B,) + g[f"w_{k}"].shape).copy() for k in ("W1a", "W2a", "W1c", "W2c")}
-    idhp = IDHPsp(env, ic, verbose=0, seed=4, weights=w, log="full", log_agents=B, numpy2=True)   # fixtures ran under numpy >= 2
+    idhp = IDHPsp(env, ic, verbose=0, seed=4, weights=w, log="full", log_agents=B)   # DEFAULT mode = the fixtures' (NEP 50, numpy >= 2)
     steps = int(g["steps"])
     idhp.train(steps)
     for b in range(B):
@@ -403,7 +403,7 @@ def test_idhpnonlin_train_equals_verbatim_reference_run(name):
                    "critic_config": {"layers": {10: "tanh", 3: "linear"}, "eta_h": 1.4, "eta_l": 0.7, "elig": 1233},
                    "rls_config": {"state_dim": 3, "action_dim": 1, "rls_gamma": 1, "rls_cov": 10 ** 6}}
     w = {k: np.broadcast_to(g[f"w_{k}"], (B,) + g[f"w_{k}"].shape).copy() for k in ("W1a", "W2a", "W1c", "W2c")}
-    idhp = IDHPnonlin(env, idhp_config, seed=1, verbose=0, weights=w, log="full", log_agents=B, chunk=250, numpy2=True)
+    idhp = IDHPnonlin(env, idhp_config, seed=1, verbose=0, weights=w, log="full", log_agents=B, chunk=250)   # DEFAULT mode = the fixtures'
     idhp.train(steps, noise=np.repeat(g["noise"][:, None], B, axis=1))
     lg = {k: v.cpu().numpy() for k, v in idhp.log.items()}
     for b in range(B):
@@ -469,7 +469,7 @@ def test_mc_test_hparam_equals_verbatim_reference():
     configs["elig"] = elig
     w = {k: np.stack([g[f"w{r}_{k}"] for _ in range(N) for r in range(reps)]) for k in ("W1a", "W2a", "W1c", "W2c")}
     noise = np.stack([g["noise"][r] for _ in range(N) for r in range(reps)], axis=1)           # (9000, B)
-    out = F.MC_test_hparam(configs, "unused/", env, N, reps, noise=noise, weights=w, numpy2=True)
+    out = F.MC_test_hparam(configs, "unused/", env, N, reps, noise=noise, weights=w)          # DEFAULT mode = the fixtures'
     assert [o[0] for o in out] == ["idhpat", "midhp"]
     for i, (algo, cfg, log) in enumerate(out):
         lg = {k: v.cpu().numpy() for k, v in log.items()}
@@ -513,3 +513,75 @@ def test_mc_run_metrics_equal_verbatim_reference(oracle):
         assert np.array_equal(st["converged_time"][sl].cpu().numpy(), g[f"arrays{c}_converged_time"])
         ok = ~st["diverged"][sl].cpu().numpy()
         assert np.allclose(st["sum_c"][sl].cpu().numpy()[ok], g[f"arrays{c}_sum_c"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("policy", ["fp64", "mixed", "fp32"])
+def test_episode_statistics_and_nmae_equal_oracle(oracle, policy):
+    """SpEngine.stats() (rl4_sp_agent_stats) against the oracle's episode statistics -- sum(c)/kappa, convergence time,
+    divergence, mean|e| and the normalised tracking error nMAE = mean|e| / (max ref - min ref) BASELINE.json names -- bit
+    for bit, with per-agent kappa / reference amplitude and a few diverging agents; and the rank summary of
+    rl4_stats_reduce (dist.episode_summary_tensor) against a float64 torch reduction of the same planes."""
+    from rl4afcs_b200 import _lib, sp_engine
+    from rl4afcs_b200 import dist as rdist
+
+    n, steps = 700, 450
+    ic = oracle.default_idhp_config()
+    base, _ = oracle.default_reference()
+    rng = np.random.default_rng(5)
+    x0 = np.deg2rad(rng.uniform(-2, 2, size=(n, 2)))
+    w = oracle.init_weights(n, 6)
+    cfg = oracle.make_cfg(ic, n=n)
+    cfg["kappa"] = rng.uniform(800, 1500, n)
+    cfg["ref_amp"] = np.deg2rad(rng.uniform(1, 10, n)) * rng.choice([-1.0, 1.0], n)
+    cfg["eta_a_h"] = np.where(np.arange(n) % 9 == 0, 400.0, cfg["eta_a_h"])     # these agents blow up
+    st = oracle.init_states(policy, cfg, x0, w)
+    oracle.run(policy, cfg, base, st, 0, steps, tanh="t13")
+    want = oracle.episode_stats(st, cfg, base, steps)
+    eng = sp_engine.SpEngine(n, policy=policy)
+    sp_engine.apply_idhp_config(eng, ic, dt=0.02)
+    eng.set_hp("KAPPA", cfg["kappa"]); eng.set_hp("REF_AMP", cfg["ref_amp"]); eng.set_hp("ETA_A_H", cfg["eta_a_h"])
+    eng.set_hpi("FAULT_STEP", -1); eng.set_hpi("FAULT_KIND", 0)
+    eng.set_reference(base)
+    eng.init(x0, w["W1a"], w["W2a"], w["W1c"], w["W2c"])
+    eng.run(steps)
+    got = {k: v.cpu().numpy() for k, v in eng.stats().items()}
+    assert want["diverged"].any() and not want["diverged"].all()
+    for k in ("sum_c", "converged_time", "diverged", "mean_abs_e", "nmae"):
+        assert np.array_equal(got[k], want[k], equal_nan=True), k
+    ok = ~want["diverged"]
+    assert np.all(got["nmae"][ok] > 0) and np.all(np.isfinite(got["nmae"][ok]))
+    # the per-rank summary: deterministic device reduction == float64 reduction of the same per-agent planes
+    part = rdist.episode_summary_tensor(eng).cpu().numpy()
+    planes = eng.stats_planes().cpu().numpy()
+    S = _lib.SPS
+    for f in range(S["COUNT"]):
+        kept, every = planes[f][ok].sum(), planes[f].sum()
+        assert np.isclose(part[2 * f], kept, rtol=1e-12, atol=0), f
+        assert np.isclose(part[2 * f + 1], every, rtol=1e-12, atol=0, equal_nan=True), f
+    assert part[2 * S["COUNT"]] == ok.sum() and part[2 * S["COUNT"] + 1] == (~ok).sum()
+    assert np.array_equal(part, rdist.episode_summary_tensor(eng).cpu().numpy(), equal_nan=True)      # run-to-run identical
+    summ = rdist.gather_episode_summary(eng, 1)
+    assert summ["agents"] == n and summ["diverged"] == int((~ok).sum())
+    assert np.isclose(summ["avg_nmae"], got["nmae"][ok].mean(), rtol=1e-12)
+
+
+def test_mc_run_sigma_sweep_pairs_seeds_across_configs():
+    """functions.MC_run honours `sigmas` per config (functions.py:80,97) and, like the reference's seeds 0..seeds-1 per config,
+    starts seed s of every config from the same standard-normal draw, scaled by that config's sigma."""
+    from rl4afcs_b200 import functions as F
+    from rl4afcs_b200 import sp_engine
+
+    seeds, n_cfg = 6, 3
+    t = np.linspace(0, 4, 200)
+    env_config = {"state_dim": 2, "action_dim": 1, "x0": np.zeros((2, 1)), "dt": 0.02, "t_end": 4, "fault_time": 20,
+                  "fault_scenario": None, "reference": {"tracked_state": ["alpha"], "signal": [np.deg2rad(5) * np.sin(2 * np.pi * t / 10)]}}
+    configs = {"sigmas": [0.05, 0.1, 0.2]}
+    _, idhp = F.MC_run(n_cfg, configs, env_config, seeds, dtype="mixed", base_seed=3)
+    w0 = idhp._init_weights
+    std = sp_engine.truncated_normal_weights(seeds, 3, 1.0, "cuda:0")
+    for key in ("W1a", "W2a", "W1c", "W2c"):
+        W = w0[key].reshape(n_cfg, seeds, -1)
+        for c, sig in enumerate(configs["sigmas"]):
+            want = (std[key].float() * torch.tensor(sig, dtype=torch.float32)).double()
+            assert torch.equal(W[c], want), (key, c)
+    assert float(w0["W1a"].abs().max()) <= 0.4 + 1e-7

@@ -217,7 +217,7 @@ def test_fp32_single_step_within_1e4_of_fp64_oracle(oracle):
     assert worst < 1e-4, worst
 
 
-@pytest.mark.parametrize("policy", ["fp64", "mixed"])
+@pytest.mark.parametrize("policy", ["fp64", "mixed", "fp32"])
 def test_full_size_batch_by_replication_property(oracle, policy):
     """BASELINE.json configs[1] size (2^20 agents): agents are independent, so a batch that replicates a 1024-agent
     block 1024 times must reproduce that block bit for bit at every position (no cross-agent leakage, no
