@@ -422,11 +422,12 @@ int rl4_ctx_destroy(rl4_ctx* ctx);
 /* which groups of final-state fields travel back (rows of the same full-plane host layout; unselected rows are not written) */
 enum rl4_out_mask {
     RL4_OUT_STATS = 1,      /* SP: SUM_C, SUM_ABS_E + the int plane;  NL: RSE, NZ_PEAK, RSE_FLIGHT, ETA / LAMBDA + the int plane */
-    RL4_OUT_WEIGHTS = 2,    /* actor, critic, target-critic weights (IDHPsp.actor / critic / target_critic.trainable_weights) */
+    RL4_OUT_WEIGHTS = 2,    /* actor and critic weights (IDHPsp.actor / critic.trainable_weights) */
     RL4_OUT_RLS = 4,        /* THETA, COV, EPS, EPS_NORM (IDHPsp.model) */
     RL4_OUT_STATE = 8,      /* plant state, actions, M_prev, previous reward gradient, learning rates: what a resume needs */
     RL4_OUT_TRACES = 16,    /* eligibility / Jacobian traces */
-    RL4_OUT_ALL = 31
+    RL4_OUT_TARGET = 32,    /* target-critic weights (IDHPsp.target_critic.trainable_weights) */
+    RL4_OUT_ALL = 63
 };
 typedef struct rl4_sp_host_io {
     const double* x0;           /* [2][n] */
@@ -445,17 +446,21 @@ int rl4_sp_episode_host(rl4_ctx* ctx, const rl4_sp_params* p, const rl4_sp_host_
                         int64_t n_agents, int32_t n_steps, int32_t use_traces);
 
 /* N(0,1) float32 draws for the nonlinear agent's policy-smoothing term (tf.random.normal, objects.py:1375): Philox4x32-10
- * keyed by `seed`, counter = (step, agent), Box-Muller; out[(k - k0) * stride + agent] for k in [k0, k0 + n_steps).
- * TensorFlow's stream is not reproducible, so this is a stream of this repo; tests read it back and feed the oracle. */
-int rl4_nl_noise_fill(uint64_t seed, int32_t k0, int32_t n_steps, int64_t n_agents, float* out, int64_t stride, void* stream);
+ * keyed by `seed`, counter = (agent0 + i, step), Box-Muller; out[(k - k0) * stride + i] for k in [k0, k0 + n_steps),
+ * i in [0, n_agents): a pure function of (seed, global agent index, step), so any split over chunks, launches or GPUs
+ * draws the same numbers.  TensorFlow's stream is not reproducible, so this is a stream of this repo; tests read it back
+ * and feed the oracle. */
+int rl4_nl_noise_fill(uint64_t seed, int64_t agent0, int32_t k0, int32_t n_steps, int64_t n_agents, float* out, int64_t stride,
+                      void* stream);
 typedef struct rl4_nl_host_io {
     const double* w1a;          /* [40][n] (4,10) row-major */
     const double* w2a;          /* [10][n] */
     const double* w1c;          /* [40][n] */
     const double* w2c;          /* [30][n] (10,3) row-major */
     const double* theta_ref;    /* [n_steps] */
-    const float*  noise;        /* [n_steps][n] host N(0,1) draws, or NULL: generated on the device by rl4_nl_noise_fill(noise_seed) */
+    const float*  noise;        /* [n_steps][n] host N(0,1) draws, or NULL: generated on the device by rl4_nl_noise_fill(noise_seed, ...) */
     uint64_t      noise_seed;
+    int64_t       noise_agent0; /* global index of this batch's first agent in the device-drawn stream (multi-GPU shards) */
     double*  out_env;           /* [RL4_NLE_COUNT][n] */
     void*    out_net;           /* [RL4_NLN_COUNT][n] of TN */
     int32_t* out_ints;          /* [RL4_NLI_COUNT][n] */
@@ -470,13 +475,16 @@ int rl4_nl_episode_host(rl4_ctx* ctx, const rl4_nl_params* p, const rl4_nl_host_
 /* Runs a dependent-FMA micro-kernel (is_double ? DFMA : FFMA) and returns achieved FLOP/s. */
 int rl4_peak_fma(int is_double, double* out_flops_per_s, void* stream);
 /* Test hook: element-wise probe of the arithmetic primitives on device arrays.
- * op 0: tanh t13 (double)  1: tanh t13 (float)  2: shared-reciprocal division a/b (double)
+ * op 0: tanh t13 (double)  1: tanh t13 (float)  2: shared-reciprocal division a/b (double; RLS gain / covariance)
  * 3: __ddiv_rn(a, b)  4 / 5: rl4_sincos sine / cosine  6 / 7: ISA density / thrust lapse at altitude a (b = device copy
  * of an rl4_cit_params).  Used by tests/test_gpu_math.py only. */
 int rl4_test_math(int op, const void* a, const void* b, void* out, int64_t n, void* stream);
 /* Test hook: exhaustive comparison of the float t13 quotient em/(em+2) with __fdiv_rn over the float
  * bit patterns [lo_bits, hi_bits); adds the number of mismatches to *device_mismatch_counter. */
 int rl4_test_t13_div_f32(uint32_t lo_bits, uint32_t hi_bits, unsigned long long* device_mismatch_counter, void* stream);
+/* Test hook: exhaustive comparison of the float32 reciprocal that seeds the double t13 quotient (MUFU.RCP + one Newton
+ * step) with __frcp_rn (IEEE 1/d) over the float bit patterns [lo_bits, hi_bits); adds the mismatches to the counter. */
+int rl4_test_rcp_f32(uint32_t lo_bits, uint32_t hi_bits, unsigned long long* device_mismatch_counter, void* stream);
 /* number of kernel launches issued by this library since load (bench.py "gpu_launches") */
 int64_t rl4_launch_count(void);
 

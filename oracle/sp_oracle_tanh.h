@@ -14,7 +14,14 @@
  *   q  = Horner(1/D!, ..., 1/2!) in r        (D = 13 for f64, 8 for f32)
  *   p  = fma(r*r, q, r)                      (= expm1(r))
  *   s  = 2^n ; em = fma(s, p, s - 1)         (= expm1(2|x|))
- *   y  = em / (em + 2) ; return copysign(y, x)
+ *   f32:  y = em / (em + 2)                  (IEEE division)
+ *   f64:  y = em (/) (em + 2), a fixed sequence of IEEE operations:
+ *           d  = em + 2 ; r0 = (double)(1.0f / (float)d)           (float32 reciprocal of the float32-rounded d)
+ *           e  = fma(-d, r0, 1) ; e = fma(e, e, e) ; rc = fma(r0, e, r0)      (one cubic Newton step)
+ *           q0 = em * rc ; y = fma(rc, fma(-d, q0, em), q0)                   (quotient, remainder, correction)
+ *   return copysign(y, x)
+ * The kernels evaluate the f64 polynomial on r/2 with power-of-two-scaled coefficients; scaling by powers of two
+ * commutes with rounding, so that is the same function bit for bit -- this file keeps the textbook form.
  */
 #ifndef RL4_SP_ORACLE_TANH_H
 #define RL4_SP_ORACLE_TANH_H
@@ -52,7 +59,15 @@ static inline double orc_t13_f64(double x)
     const uint64_t sb = (uint64_t)(1023 + (int64_t)(int32_t)(uint32_t)kb) << 52;
     double s; memcpy(&s, &sb, 8);
     const double em = fma(s, p, s - 1.0);
-    const double y = em / (em + 2.0);
+    const double d = em + 2.0;
+    const volatile float df = (float)d;      /* volatile: no excess precision, no reciprocal tricks */
+    const volatile float rf = 1.0f / df;
+    const double r0 = (double)rf;
+    double e = fma(-d, r0, 1.0);
+    e = fma(e, e, e);
+    const double rc = fma(r0, e, r0);
+    const double q0 = em * rc;
+    const double y = fma(rc, fma(-d, q0, em), q0);
     return copysign(y, x);
 }
 

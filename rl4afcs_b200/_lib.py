@@ -119,13 +119,13 @@ class SpHostIO(ctypes.Structure):
 
 class NlHostIO(ctypes.Structure):
     _fields_ = [("w1a", ctypes.c_void_p), ("w2a", ctypes.c_void_p), ("w1c", ctypes.c_void_p), ("w2c", ctypes.c_void_p),
-                ("theta_ref", ctypes.c_void_p), ("noise", ctypes.c_void_p), ("noise_seed", ctypes.c_uint64),
+                ("theta_ref", ctypes.c_void_p), ("noise", ctypes.c_void_p), ("noise_seed", ctypes.c_uint64), ("noise_agent0", ctypes.c_int64),
                 ("out_env", ctypes.c_void_p), ("out_net", ctypes.c_void_p), ("out_ints", ctypes.c_void_p),
                 ("out_mask", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 ABI_VERSION = 2          # RL4_ABI_VERSION of include/rl4afcs_b200.h these struct layouts were written against
-OUT = dict(STATS=1, WEIGHTS=2, RLS=4, STATE=8, TRACES=16, ALL=31)
+OUT = dict(STATS=1, WEIGHTS=2, RLS=4, STATE=8, TRACES=16, TARGET=32, ALL=63)
 SPS = dict(SUM_C=0, CONV_TIME=1, DIVERGED=2, UNSTEADY=3, MEAN_ABS_E=4, NMAE=5, COUNT=6)
 NLS = dict(RSE_WARMUP=0, RSE_FLIGHT=1, RSE_LAT=2, NZ_PEAK=3, DIVERGED=4, COUNT=5)
 
@@ -138,7 +138,7 @@ EXPORTS = [
     "rl4_nl_rls_update", "rl4_peak_fma", "rl4_launch_count", "rl4_test_math", "rl4_test_t13_div_f32",
     "rl4_nl_init", "rl4_nl_run", "rl4_nl_env_step", "rl4_nl_default_params", "rl4_nl_critic_forward", "rl4_nl_actor_forward",
     "rl4_sizeof_sp_params", "rl4_sizeof_nl_params", "rl4_soft_update", "rl4_actor_weight_update", "rl4_sp_agent_stats",
-    "rl4_nl_agent_stats", "rl4_stats_reduce_work_doubles", "rl4_stats_reduce", "rl4_nl_noise_fill", "rl4_nl_episode_host",
+    "rl4_nl_agent_stats", "rl4_stats_reduce_work_doubles", "rl4_stats_reduce", "rl4_nl_noise_fill", "rl4_nl_episode_host", "rl4_test_rcp_f32",
 ]
 _NOT_STATUS = ("rl4_last_error", "rl4_launch_count", "rl4_abi_version", "rl4_sizeof_sp_params", "rl4_sizeof_nl_params",
                "rl4_stats_reduce_work_doubles")
@@ -196,13 +196,14 @@ def load() -> ctypes.CDLL:
     L.rl4_nl_critic_forward.argtypes = [ctypes.c_int, vp, vp, vp, vp, i64, i64, vp]
     L.rl4_nl_actor_forward.argtypes = [ctypes.c_int, vp, vp, vp, vp, vp, vp, dbl, i32, i32, i64, i64, vp]
     L.rl4_test_t13_div_f32.argtypes = [ctypes.c_uint32, ctypes.c_uint32, vp, vp]
+    L.rl4_test_rcp_f32.argtypes = [ctypes.c_uint32, ctypes.c_uint32, vp, vp]
     L.rl4_soft_update.argtypes = [ctypes.c_int, vp, vp, dbl, i32, i64, i64, vp]
     L.rl4_actor_weight_update.argtypes = [ctypes.c_int, vp, vp, vp, i32, i64, i64, vp]
     L.rl4_sp_agent_stats.argtypes = [ctypes.c_int, ctypes.POINTER(SpParams), SpState, i64, i32, dbl, dbl, vp, i64, vp]
     L.rl4_nl_agent_stats.argtypes = [NlState, i64, vp, i64, vp]
     L.rl4_stats_reduce_work_doubles.restype = i64
     L.rl4_stats_reduce.argtypes = [vp, i64, i32, vp, i64, vp, vp, i64, vp]
-    L.rl4_nl_noise_fill.argtypes = [ctypes.c_uint64, i32, i32, i64, vp, i64, vp]
+    L.rl4_nl_noise_fill.argtypes = [ctypes.c_uint64, i64, i32, i32, i64, vp, i64, vp]
     L.rl4_nl_episode_host.argtypes = [vp, ctypes.POINTER(NlParams), ctypes.POINTER(NlHostIO), i64, i32]
     for name in EXPORTS:
         fn = getattr(L, name)

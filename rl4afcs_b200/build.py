@@ -37,6 +37,28 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; rl4afcs_b200 has no prebuilt or CPU fallback")
 
 
+# headers each translation unit depends on (a stale object is rebuilt, the others are reused: the nonlinear kernels take
+# over a minute to compile, the rest seconds)
+_COMMON = ["rl4_math.cuh", "rl4_runtime.h", os.path.join("..", "..", "include", "rl4afcs_b200.h"),
+           os.path.join("..", "..", "include", "rl4_citation_surrogate.h")]
+DEPS = {"runtime.cu": _COMMON, "sp_kernels.cu": _COMMON + ["sp_core.cuh"], "nl_kernels.cu": _COMMON,
+        "step_kernels.cu": _COMMON, "host_episode.cu": _COMMON}
+OBJ_DIR = os.path.join(_HERE, "build")
+
+
+def _obj(src: str) -> str:
+    return os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+
+
+def _src_stale(src: str) -> bool:
+    o = _obj(src)
+    if not os.path.isfile(o):
+        return True
+    t = os.path.getmtime(o)
+    deps = [os.path.join(CSRC, d) for d in [src] + DEPS[src]] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
 def _stale() -> bool:
     if not os.path.isfile(LIB_PATH):
         return True
@@ -46,19 +68,57 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = None) -> str:
-    """Build the library.  ``extra_flags`` / ``out`` exist for tuning experiments (scripts/)."""
+    """Build the library: every stale translation unit is compiled to rl4afcs_b200/build/*.o (in parallel), then linked.
+    ``extra_flags`` / ``out`` exist for tuning experiments (scripts/): they compile everything into one private library."""
     out = out or LIB_PATH
     if not force and out == LIB_PATH and not _stale():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
     log = os.path.join(_HERE, "build.log")
+    if extra_flags or out != LIB_PATH:
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        text = " ".join(cmd) + "\n" + res.stdout + res.stderr
+        rc = res.returncode
+    else:
+        os.makedirs(OBJ_DIR, exist_ok=True)
+        todo = [s for s in SOURCES if force or _src_stale(s)]
+        compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+        procs = []
+        for s in todo:
+            cmd = [_nvcc()] + compile_flags + ["-c", "-o", _obj(s), os.path.join(CSRC, s)]
+            procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        text, rc = "", 0
+        for cmd, pr in procs:
+            o, _ = pr.communicate()
+            text += " ".join(cmd) + "\n" + o
+            rc = rc or pr.returncode
+        if rc == 0:
+            cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out] + [_obj(s) for s in SOURCES]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            text += " ".join(cmd) + "\n" + res.stdout + res.stderr
+            rc = res.returncode
+        # keep the ptxas summaries of the units that were NOT recompiled in the log
+        old = {}
+        if os.path.isfile(log) and todo != SOURCES:
+            try:
+                cur = None
+                for line in open(log):
+                    if line.startswith(_nvcc()) and " -c " in line:
+                        cur = line.rsplit("/", 1)[-1].strip()
+                        old[cur] = line
+                    elif cur is not None:
+                        old[cur] += line
+            except OSError:
+                old = {}
+        for s in SOURCES:
+            if s not in todo and s in old:
+                text += old[s]
     with open(log, "w") as fh:
-        fh.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+        fh.write(text)
     if verbose:
-        print(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed ({res.returncode}); see {log}\n{res.stderr[-4000:]}")
+        print(text)
+    if rc != 0:
+        raise RuntimeError(f"nvcc failed ({rc}); see {log}\n{text[-4000:]}")
     return out
 
 

@@ -19,12 +19,13 @@ __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint
 }
 
 __global__ void __launch_bounds__(256)
-nl_noise_kernel(uint64_t seed, int k0, int n_steps, int64_t n, float* __restrict__ out, int64_t stride)
+nl_noise_kernel(uint64_t seed, int64_t agent0, int k0, int n_steps, int64_t n, float* __restrict__ out, int64_t stride)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
     if (i >= n || r >= n_steps) return;
-    uint32_t c[4] = {(uint32_t)i, (uint32_t)((uint64_t)i >> 32), (uint32_t)(k0 + r), 0u};
+    const uint64_t g = (uint64_t)(agent0 + i);
+    uint32_t c[4] = {(uint32_t)g, (uint32_t)(g >> 32), (uint32_t)(k0 + r), 0u};
     uint32_t ka = (uint32_t)seed, kb = (uint32_t)(seed >> 32);
 #pragma unroll
     for (int round = 0; round < 10; ++round) {
@@ -167,7 +168,8 @@ int rl4_sp_episode_host(rl4_ctx* c, const rl4_sp_params* p, const rl4_sp_host_io
     if (mask & RL4_OUT_RLS) { mark(env_rows, RL4_SPE_THETA, RL4_SPE_CGRAD_PREV); mark(env_rows, RL4_SPE_EPS, RL4_SPE_SUM_C); }
     if (mask & RL4_OUT_STATS) mark(env_rows, RL4_SPE_SUM_C, RL4_SPE_EA);
     if (mask & RL4_OUT_TRACES) mark(env_rows, RL4_SPE_EA, RL4_SPE_COUNT);
-    if (mask & RL4_OUT_WEIGHTS) mark(net_rows, RL4_SPN_W1A, RL4_SPN_MPREV);
+    if (mask & RL4_OUT_WEIGHTS) mark(net_rows, RL4_SPN_W1A, RL4_SPN_W1T);
+    if (mask & RL4_OUT_TARGET) mark(net_rows, RL4_SPN_W1T, RL4_SPN_MPREV);
     RowRange er[RL4_SPE_COUNT], nr[RL4_SPN_COUNT];
     const int n_er = io->out_env ? ranges_from_rows(env_rows, RL4_SPE_COUNT, er) : 0;
     const int n_nr = io->out_net ? ranges_from_rows(net_rows, RL4_SPN_COUNT, nr) : 0;
@@ -214,13 +216,13 @@ done:
     return drain(c, rc);
 }
 
-int rl4_nl_noise_fill(uint64_t seed, int32_t k0, int32_t n_steps, int64_t n, float* out, int64_t stride, void* stream)
+int rl4_nl_noise_fill(uint64_t seed, int64_t agent0, int32_t k0, int32_t n_steps, int64_t n, float* out, int64_t stride, void* stream)
 {
     RL4_REQUIRE(out != nullptr, "out is NULL");
-    RL4_REQUIRE(n >= 0 && stride >= n && k0 >= 0 && n_steps >= 0 && n_steps <= 65535, "bad size (n_steps <= 65535 per call)");
+    RL4_REQUIRE(n >= 0 && stride >= n && k0 >= 0 && agent0 >= 0 && n_steps >= 0 && n_steps <= 65535, "bad size (n_steps <= 65535 per call)");
     if (n == 0 || n_steps == 0) return 0;
     const dim3 grid((unsigned)((n + 255) / 256), (unsigned)n_steps);
-    nl_noise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, k0, n_steps, n, out, stride);
+    nl_noise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, agent0, k0, n_steps, n, out, stride);
     return check_launch("nl_noise_kernel");
 }
 
@@ -252,7 +254,8 @@ int rl4_nl_episode_host(rl4_ctx* c, const rl4_nl_params* p, const rl4_nl_host_io
     if (mask & RL4_OUT_RLS) { mark(env_rows, RL4_NLE_THETA, RL4_NLE_CGRAD_PREV); mark(env_rows, RL4_NLE_EPS, RL4_NLE_RSE); }
     if (mask & RL4_OUT_STATS) { mark(env_rows, RL4_NLE_RSE, RL4_NLE_EA); mark(env_rows, RL4_NLE_RSE_FLIGHT, RL4_NLE_COUNT); }
     if (mask & RL4_OUT_TRACES) mark(env_rows, RL4_NLE_EA, RL4_NLE_RSE_FLIGHT);
-    if (mask & RL4_OUT_WEIGHTS) mark(net_rows, RL4_NLN_W1A, RL4_NLN_MPREV);
+    if (mask & RL4_OUT_WEIGHTS) mark(net_rows, RL4_NLN_W1A, RL4_NLN_W1T);
+    if (mask & RL4_OUT_TARGET) mark(net_rows, RL4_NLN_W1T, RL4_NLN_MPREV);
     RowRange er[RL4_NLE_COUNT], nr[RL4_NLN_COUNT];
     const int n_er = io->out_env ? ranges_from_rows(env_rows, RL4_NLE_COUNT, er) : 0;
     const int n_nr = io->out_net ? ranges_from_rows(net_rows, RL4_NLN_COUNT, nr) : 0;
@@ -287,7 +290,7 @@ int rl4_nl_episode_host(rl4_ctx* c, const rl4_nl_params* p, const rl4_nl_host_io
             if (io->noise)
                 EP_CUDA(cudaMemcpy2DAsync(nz, S * 4, io->noise + (int64_t)k * n + off, n * 4, m * 4, ks, cudaMemcpyHostToDevice, s));
             else {
-                rc = rl4_nl_noise_fill(io->noise_seed, k, ks, m, nz, S, s);
+                rc = rl4_nl_noise_fill(io->noise_seed, io->noise_agent0 + off, k, ks, m, nz, S, s);
                 if (rc) goto done;
             }
             rc = rl4_nl_run(c->policy, &pc, c->d_ref, nz, S, k, ks, st, m, lg, s);

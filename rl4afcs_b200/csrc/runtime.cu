@@ -122,6 +122,20 @@ __global__ void t13_div_f32_exhaustive_kernel(unsigned lo, unsigned hi, unsigned
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// exhaustive check of the seed of the double t13 quotient: rcp_rn_f32_normal(d) against __frcp_rn(d) (IEEE 1/d) for every
+// float bit pattern in [lo, hi)
+__global__ void rcp_f32_exhaustive_kernel(unsigned lo, unsigned hi, unsigned long long* mismatches)
+{
+    unsigned long long bad = 0;
+    const unsigned long long n = (unsigned long long)hi - lo;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float d = __uint_as_float(lo + (unsigned)i);
+        if (__float_as_uint(rcp_rn_f32_normal(d)) != __float_as_uint(__frcp_rn(d))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace rl4
 
 extern "C" {
@@ -163,6 +177,13 @@ int rl4_test_t13_div_f32(uint32_t lo_bits, uint32_t hi_bits, unsigned long long*
     RL4_REQUIRE(device_mismatch_counter && hi_bits >= lo_bits, "bad argument");
     rl4::t13_div_f32_exhaustive_kernel<<<148 * 16, 256, 0, (cudaStream_t)stream>>>(lo_bits, hi_bits, device_mismatch_counter);
     return rl4::check_launch("t13_div_f32_exhaustive_kernel");
+}
+
+int rl4_test_rcp_f32(uint32_t lo_bits, uint32_t hi_bits, unsigned long long* device_mismatch_counter, void* stream)
+{
+    RL4_REQUIRE(device_mismatch_counter && hi_bits >= lo_bits, "bad argument");
+    rl4::rcp_f32_exhaustive_kernel<<<148 * 16, 256, 0, (cudaStream_t)stream>>>(lo_bits, hi_bits, device_mismatch_counter);
+    return rl4::check_launch("rcp_f32_exhaustive_kernel");
 }
 
 int64_t rl4_launch_count(void) { return rl4::g_launch_count.load(); }

@@ -46,6 +46,10 @@ template <typename T, int N> struct Arr<T, N, true> {
     __device__ __forceinline__ Rn<T>& operator[](int j) const { return p[j * RL4_SP_BLOCK]; }
 };
 
+// ||eps||^2 as np.linalg.norm forms it before the square root (ddot: in-order FMA chain; objects.py:539)
+template <typename TE>
+__device__ __forceinline__ Rn<TE> sp_eps_sq(const Rn<TE> (&eps)[2]) { return fma(eps[1], eps[1], eps[0] * eps[0]); }
+
 template <typename TN, typename TE, bool SM = false>
 struct SpAgent {
     using N = Rn<TN>;
@@ -61,6 +65,8 @@ struct SpAgent {
     Arr<TN, 8, SM> W2t;
     // int plane
     int cooldown, flags, diverged_step, conv_step;
+    bool eps_fresh;                 // eps was updated since epsn was last formed (the square root is taken lazily)
+    __device__ __forceinline__ void refresh_epsn() { if (eps_fresh) { epsn = sqrt_rn(sp_eps_sq<TE>(eps)); eps_fresh = false; } }
 };
 
 // per-step scratch that the log and the step-API kernels want to see
@@ -237,7 +243,7 @@ __device__ __forceinline__ void sp_actor_forward(Rn<TN> z, const Rn<TN> (&h)[4],
 // RLS.update (objects.py:492-543).  X = [dx0; da0], Y = dx1.
 template <typename TE, typename TH, typename CV>
 __device__ __forceinline__ void sp_rls_update(TH& th, CV& cv, const Rn<TE> (&X)[3], const Rn<TE> (&Y)[2],
-                                              Rn<TE> rls_gamma, Rn<TE> (&eps)[2], Rn<TE>& eps_norm)
+                                              Rn<TE> rls_gamma, Rn<TE> (&eps)[2])
 {
     using E = Rn<TE>;
     E CX[3], K[3];
@@ -281,7 +287,22 @@ __device__ __forceinline__ void sp_rls_update(TH& th, CV& cv, const Rn<TE> (&X)[
 #pragma unroll
         for (int j = 0; j < 9; ++j) cv[j] = quo[j];
     }
-    eps_norm = sqrt_rn(fma(eps[1], eps[1], eps[0] * eps[0]));    // objects.py:539
+    // objects.py:539: eps_norm = sqrt(sp_eps_sq(eps)) is formed by the callers, only where its value is needed
+}
+
+// Predicate `sqrt(v) > c` (c > 0) without the square root: sqrt is monotone and rounds once (relative error 2^-53 /
+// 2^-24), so outside a guard band of 1e-12 (double) / 1e-5 (float) around c^2 the comparison of v with c^2 decides;
+// inside the band the literal expression is evaluated.  Same truth value as the literal predicate for every input.
+template <typename TE> struct Guard;
+template <> struct Guard<double> { static __device__ __forceinline__ double lo() { return 1.0 - 1e-12; } static __device__ __forceinline__ double hi() { return 1.0 + 1e-12; } };
+template <> struct Guard<float>  { static __device__ __forceinline__ float lo() { return 1.0f - 1e-5f; } static __device__ __forceinline__ float hi() { return 1.0f + 1e-5f; } };
+template <typename TE>
+__device__ __forceinline__ bool sqrt_gt(Rn<TE> v, TE c)
+{
+    const TE c2 = c * c;
+    if (v.v > c2 * Guard<TE>::hi()) return true;
+    if (!(v.v >= c2 * Guard<TE>::lo())) return false;        // below the band, or NaN (NaN > c is false)
+    return sqrt_rn(v).v > c;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -407,14 +428,15 @@ __device__ __forceinline__ void sp_agent_step(SpAgent<TN, TE, SM>& s, const rl4_
             }
             X[2] = cvt<TE>(a_k - s.ap);                                 // objects.py:973 (tensor dtype)
             Y[0] = xn[0] - s.x[0]; Y[1] = xn[1] - s.x[1];
-            sp_rls_update<TE>(s.th, s.cv, X, Y, E(TE(hv.hp(RL4_HP_RLS_GAMMA))), s.eps, s.epsn);
+            sp_rls_update<TE>(s.th, s.cv, X, Y, E(TE(hv.hp(RL4_HP_RLS_GAMMA))), s.eps);
+            s.eps_fresh = true;                                         // s.epsn is re-formed from s.eps when it is read
         }
         // ---- _adapt_check (objects.py:783-841)
         {
             const E thr = E(TE(hv.hp(RL4_HP_ERROR_THRESH_DEG))) * E(Consts<TE>::deg2rad());
             const bool cond1 = k < hv.hpi(RL4_HPI_WARMUP_STEPS);
             const bool cond2 = abs_rn(o.e).v > thr.v;
-            const bool cond3 = s.epsn.v > TE(5e-5);
+            const bool cond3 = sqrt_gt<TE>(sp_eps_sq<TE>(s.eps), TE(5e-5));    // rls.eps_norm > 5e-5 (objects.py:539,797)
             if (s.cooldown > 0) s.cooldown -= 1;
             const bool high = cond1 || cond2;
             const double eta_a_h = hv.hp(RL4_HP_ETA_A_H);
@@ -451,10 +473,22 @@ __device__ __forceinline__ void sp_agent_step(SpAgent<TN, TE, SM>& s, const rl4_
     s.sumc = s.sumc + o.cost;
     s.sumabse = s.sumabse + abs_rn(o.e);
     {
-        E cq[1] = {o.cost}, cdk[1];
-        div_group<1>(cq, kappa, cdk);
-        const E aoa_err_deg = sqrt_rn(E(TE(-2)) * cdk[0]) * E(Consts<TE>::rad2deg());
-        if (aoa_err_deg.v > TE(0.5)) s.conv_step = k;
+        // utils.py:350-369 on this step's reward: sqrt(-2 c / kappa) * rad2deg > 0.5.  The literal expression is |e| * rad2deg
+        // up to five roundings (c = (-0.5 kappa)(e e)), so outside a guard band around 0.5 deg the comparison of |e| with
+        // the threshold in radians decides; inside the band (and for a kappa outside the range in which that error
+        // analysis holds) the literal expression is evaluated.  Same truth value as the literal predicate.
+        const TE ae = abs_rn(o.e).v;
+        const TE thr = TE(0.5) / Consts<TE>::rad2deg();
+        const TE kk = fabs(kappa.v);
+        bool late;
+        if (kk >= TE(1e-3) && kk <= TE(1e9) && (ae > thr * Guard<TE>::hi() || ae < thr * Guard<TE>::lo())) {
+            late = ae > thr;
+        } else {
+            E cq[1] = {o.cost}, cdk[1];
+            div_group<1>(cq, kappa, cdk);
+            late = (sqrt_rn(E(TE(-2)) * cdk[0]) * E(Consts<TE>::rad2deg())).v > TE(0.5);
+        }
+        if (late) s.conv_step = k;
     }
     if (is_nan(xn[0]) || is_nan(xn[1])) s.flags |= RL4_SPF_X_NAN;
     if (is_nan(o.cost)) s.diverged_step = k;                            // objects.py:991 (Q19)

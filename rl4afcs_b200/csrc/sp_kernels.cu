@@ -58,6 +58,7 @@ __device__ __forceinline__ void sp_load(SpAgent<TN, TE, SM>& s, const rl4_sp_sta
     for (int j = 0; j < 9; ++j) s.cv[j] = e.ld(RL4_SPE_COV + j, i);
     s.cgp = e.ld(RL4_SPE_CGRAD_PREV, i);
     s.epsn = e.ld(RL4_SPE_EPS_NORM, i);
+    s.eps_fresh = false;
     s.sumc = e.ld(RL4_SPE_SUM_C, i);
     s.sumabse = e.ld(RL4_SPE_SUM_ABS_E, i);
     if (traces) {
@@ -190,7 +191,7 @@ sp_run_kernel(const __grid_constant__ rl4_sp_params p, const double* __restrict_
         if (s.diverged_step >= 0) break;            // the reference left its loop (objects.py:991)
         sp_agent_step<TN, TE, TRACES, PER_AGENT, SM>(s, p, hv, k, __ldg(ref_base + k), o);
         if (LOG != RL4_LOG_NONE) {
-            if (logged && (k - k0) % lg.every == 0) sp_write_log<TN, TE, LOG, SM>(lg, (k - k0) / lg.every, i, k, s, o);
+            if (logged && (k - k0) % lg.every == 0) { s.refresh_epsn(); sp_write_log<TN, TE, LOG, SM>(lg, (k - k0) / lg.every, i, k, s, o); }
         }
     }
     if (LOG != RL4_LOG_NONE) {                      // NaN-fill the rows after a divergence (objects.py:656-679)
@@ -203,6 +204,7 @@ sp_run_kernel(const __grid_constant__ rl4_sp_params p, const double* __restrict_
             }
         }
     }
+    s.refresh_epsn();
     sp_store<TN, TE, SM>(s, st, i);
 }
 
@@ -228,7 +230,7 @@ sp_init_kernel(const __grid_constant__ rl4_sp_params p, const double* __restrict
     const E c0 = E(TE(hv.hp(RL4_HP_RLS_COV0)));
 #pragma unroll
     for (int j = 0; j < 9; ++j) s.cv[j] = (j % 4 == 0) ? c0 : ze;        // objects.py:470
-    s.cgp = ze; s.epsn = ze; s.sumc = ze; s.sumabse = ze;
+    s.cgp = ze; s.epsn = ze; s.eps_fresh = false; s.sumc = ze; s.sumabse = ze;
 #pragma unroll
     for (int j = 0; j < 8; ++j) s.Ea[j] = ze;
 #pragma unroll
@@ -281,14 +283,15 @@ sp_rls_update_kernel(const __grid_constant__ rl4_sp_params p, TE* __restrict__ t
     if (i >= n_agents) return;
     const HpView<true> hv{p, i};
     using E = Rn<TE>;
-    E th[6], cv[9], X[3], Y[2], eps[2], epsn;
+    E th[6], cv[9], X[3], Y[2], eps[2];
 #pragma unroll
     for (int j = 0; j < 6; ++j) th[j] = E(theta[j * stride + i]);
 #pragma unroll
     for (int j = 0; j < 9; ++j) cv[j] = E(cov[j * stride + i]);
     X[0] = E(dx0[i]); X[1] = E(dx0[stride + i]); X[2] = E(da0[i]);
     Y[0] = E(dx1[i]); Y[1] = E(dx1[stride + i]);
-    sp_rls_update<TE>(th, cv, X, Y, E(TE(hv.hp(RL4_HP_RLS_GAMMA))), eps, epsn);
+    sp_rls_update<TE>(th, cv, X, Y, E(TE(hv.hp(RL4_HP_RLS_GAMMA))), eps);
+    const E epsn = sqrt_rn(sp_eps_sq<TE>(eps));                         // objects.py:539
 #pragma unroll
     for (int j = 0; j < 6; ++j) theta[j * stride + i] = th[j].v;
 #pragma unroll

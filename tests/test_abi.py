@@ -65,7 +65,7 @@ def test_struct_layouts_match_header_constants():
         body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
         names = [t.strip().split("=")[0].strip() for t in body.split(",") if t.strip()]
         assert [table[nm.replace(prefix, "")] for nm in names] == list(range(len(names))), enum
-    assert ctypes.sizeof(_lib.SpHostIO) == 8 * 9 + 8 and ctypes.sizeof(_lib.NlHostIO) == 8 * 10 + 8
+    assert ctypes.sizeof(_lib.SpHostIO) == 8 * 9 + 8 and ctypes.sizeof(_lib.NlHostIO) == 8 * 11 + 8
 
 
 def test_no_cpu_fallback():

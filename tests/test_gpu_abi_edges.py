@@ -146,3 +146,121 @@ def test_ctx_create_reports_allocation_failure_and_cleans_up():
     _lib.check(L.rl4_ctx_create(0, _lib.FP64, 1024, 100, ctypes.byref(ok)), "ctx")
     assert ok.value
     L.rl4_ctx_destroy(ok)
+
+
+def test_host_buffer_episode_output_mask(oracle):
+    """rl4_sp_host_io.out_mask: only the selected field groups travel back (same full-plane host layout, unselected rows
+    untouched); the default selection of bench.py's end-to-end leg is statistics + weights + RLS model."""
+    from rl4afcs_b200 import _lib
+    from rl4afcs_b200._lib import OUT, SPE, SPI, SPN
+
+    n, steps = 70000, 60
+    eng, ic, base, amp = _engine(oracle, n, "fp64")
+    L = eng.lib
+    rng = np.random.default_rng(4)
+    x0 = np.deg2rad(rng.uniform(-2, 2, size=(n, 2)))
+    w = oracle.init_weights(n, 6)
+    eng.init(x0, w["W1a"], w["W2a"], w["W1c"], w["W2c"])
+    eng.run(steps)
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a.T)).pin_memory()     # noqa: E731
+    hx0, h1, h2, h3, h4 = pin(x0), pin(w["W1a"]), pin(w["W2a"]), pin(w["W1c"]), pin(w["W2c"])
+    href = torch.as_tensor(base[:steps].copy()).pin_memory()
+    ctx = ctypes.c_void_p()
+    _lib.check(L.rl4_ctx_create(0, _lib.FP64, n, steps, ctypes.byref(ctx)), "ctx")
+    sel = {"STATS": ([("SUM_C", 2)], [], True), "WEIGHTS": ([], [("W1A", 20)], False), "TARGET": ([], [("W1T", 12)], False),
+           "RLS": ([("THETA", 15), ("EPS", 3)], [], False), "STATE": ([("X", 4), ("CGRAD_PREV", 1)], [("A", 2), ("MPREV", 6)], True),
+           "TRACES": ([("EA", 20)], [], False)}
+    try:
+        for groups in (("STATS",), ("STATS", "WEIGHTS", "RLS"), ("STATE", "TRACES", "TARGET"), tuple(sel)):
+            oenv = torch.full((SPE["COUNT"], n), -7.0, dtype=torch.float64).pin_memory()
+            onet = torch.full((SPN["COUNT"], n), -7.0, dtype=torch.float64).pin_memory()
+            oint = torch.full((SPI["COUNT"], n), -7, dtype=torch.int32).pin_memory()
+            mask = sum(OUT[g] for g in groups)
+            io = _lib.SpHostIO(hx0.data_ptr(), h1.data_ptr(), h2.data_ptr(), h3.data_ptr(), h4.data_ptr(), href.data_ptr(),
+                               oenv.data_ptr(), onet.data_ptr(), oint.data_ptr(), mask, 0)
+            _lib.check(L.rl4_sp_episode_host(ctx, ctypes.byref(eng.params), ctypes.byref(io), n, steps, 0), "episode")
+            env_rows = np.zeros(SPE["COUNT"], bool); net_rows = np.zeros(SPN["COUNT"], bool); ints = False
+            for g in groups:
+                for f, c in sel[g][0]:
+                    env_rows[SPE[f]:SPE[f] + c] = True
+                for f, c in sel[g][1]:
+                    net_rows[SPN[f]:SPN[f] + c] = True
+                ints |= sel[g][2]
+            eq = lambda u, v: bool(((u == v) | (torch.isnan(u) & torch.isnan(v))).all())   # noqa: E731
+            er, nr = torch.as_tensor(env_rows), torch.as_tensor(net_rows)
+            assert eq(oenv[er], eng.env[:, :n].cpu()[er]) and bool((oenv[~er] == -7.0).all()), groups
+            assert eq(onet[nr], eng.net[:, :n].cpu()[nr]) and bool((onet[~nr] == -7.0).all()), groups
+            assert torch.equal(oint, eng.ints[:, :n].cpu()) if ints else bool((oint == -7).all()), groups
+    finally:
+        L.rl4_ctx_destroy(ctx)
+
+
+def test_nonlinear_noise_stream_is_deterministic_standard_normal():
+    """rl4_nl_noise_fill: the Philox / Box-Muller N(0,1) stream is a pure function of (seed, step, agent) -- any split
+    of the steps or the agents reproduces the same numbers -- with the moments of a standard normal."""
+    from rl4afcs_b200 import _lib
+
+    L = _lib.load()
+    n, steps = 5000, 64
+    full = torch.empty((steps, n), dtype=torch.float32, device="cuda")
+    _lib.check(L.rl4_nl_noise_fill(1234, 0, 0, steps, n, full.data_ptr(), n, None), "noise")
+    part = torch.empty((24, n - 1000), dtype=torch.float32, device="cuda")
+    _lib.check(L.rl4_nl_noise_fill(1234, 1000, 40, 24, n - 1000, part.data_ptr(), n - 1000, None), "noise")   # agents 1000.., steps 40..
+    other = torch.empty((steps, n), dtype=torch.float32, device="cuda")
+    _lib.check(L.rl4_nl_noise_fill(1235, 0, 0, steps, n, other.data_ptr(), n, None), "noise")
+    torch.cuda.synchronize()
+    assert torch.equal(part, full[40:, 1000:]) and not torch.equal(other, full)
+    assert bool(torch.isfinite(full).all())
+    assert abs(float(full.mean())) < 0.01 and abs(float(full.std()) - 1.0) < 0.01
+    assert abs(float((full.abs() < 1.0).float().mean()) - 0.6827) < 0.01 and float(full.abs().max()) > 3.5
+    assert abs(float((full[1:] * full[:-1]).mean())) < 0.01 and abs(float((full[:, 1:] * full[:, :-1]).mean())) < 0.01
+
+
+@pytest.mark.parametrize("noise_on_host", [True, False])
+def test_nonlinear_host_buffer_episode_equals_device_path(noise_on_host):
+    """rl4_nl_episode_host (IDHPnonlin(...).train() for a batch from HOST buffers: chunked over agents and steps, noise
+    either supplied as a host plane or drawn on the device by rl4_nl_noise_fill) returns exactly what rl4_nl_init +
+    rl4_nl_run produce on device buffers with the same noise."""
+    from oracle import nl_c
+    from rl4afcs_b200 import _lib, nl_engine
+    from rl4afcs_b200._lib import NLE, NLI, NLN, OUT
+
+    n, steps, seed = 70000, 320, 99
+    eng = nl_engine.NlEngine(n, policy="mixed", device="cuda:0")
+    L = eng.lib
+    th = nl_engine.theta_reference()
+    eng.set_reference(th)
+    w = nl_c.init_weights(n, 8)
+    noise = torch.empty((steps, n), dtype=torch.float32, device="cuda")
+    if noise_on_host:
+        noise.copy_(torch.as_tensor(np.random.default_rng(2).standard_normal((steps, n)).astype(np.float32)))
+    else:
+        _lib.check(L.rl4_nl_noise_fill(seed, 0, 0, steps, n, noise.data_ptr(), n, None), "noise")
+    eng.init(w["W1a"], w["W2a"], w["W1c"], w["W2c"])
+    eng.run(steps, noise)
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a.T)).pin_memory()     # noqa: E731
+    h = [pin(w[k]) for k in ("W1a", "W2a", "W1c", "W2c")]
+    href = torch.as_tensor(th[:steps].copy()).pin_memory()
+    hnoise = noise.cpu().pin_memory() if noise_on_host else None
+    oenv = torch.full((NLE["COUNT"], n), -7.0, dtype=torch.float64).pin_memory()
+    onet = torch.full((NLN["COUNT"], n), -7.0, dtype=torch.float32).pin_memory()
+    oint = torch.full((NLI["COUNT"], n), -7, dtype=torch.int32).pin_memory()
+    ctx = ctypes.c_void_p()
+    _lib.check(L.rl4_ctx_create(0, _lib.MIXED, n, steps, ctypes.byref(ctx)), "ctx")
+    eq = lambda u, v: bool(((u == v) | (torch.isnan(u) & torch.isnan(v))).all())   # noqa: E731
+    try:
+        io = _lib.NlHostIO(h[0].data_ptr(), h[1].data_ptr(), h[2].data_ptr(), h[3].data_ptr(), href.data_ptr(),
+                           hnoise.data_ptr() if noise_on_host else None, seed, 0, oenv.data_ptr(), onet.data_ptr(), oint.data_ptr(), 0, 0)
+        _lib.check(L.rl4_nl_episode_host(ctx, ctypes.byref(eng.params), ctypes.byref(io), n, steps), "nl episode")
+        assert eq(oenv, eng.env[:, :n].cpu()) and eq(onet, eng.net[:, :n].cpu()) and torch.equal(oint, eng.ints[:, :n].cpu())
+        # statistics only: RSE / n_z / learning rates + the int plane
+        oenv.fill_(-7.0); onet.fill_(-7.0); oint.fill_(-7)
+        io.out_mask = OUT["STATS"]
+        _lib.check(L.rl4_nl_episode_host(ctx, ctypes.byref(eng.params), ctypes.byref(io), n, steps), "nl episode (stats)")
+        rows = np.zeros(NLE["COUNT"], bool); rows[NLE["RSE"]:NLE["EA"]] = True; rows[NLE["RSE_FLIGHT"]:] = True
+        r = torch.as_tensor(rows)
+        assert eq(oenv[r], eng.env[:, :n].cpu()[r]) and bool((oenv[~r] == -7.0).all()) and bool((onet == -7.0).all())
+        assert torch.equal(oint, eng.ints[:, :n].cpu())
+    finally:
+        L.rl4_ctx_destroy(ctx)
+    assert int((eng.int_field("DIVERGED_STEP") >= 0).sum()) < n // 2

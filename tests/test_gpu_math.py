@@ -80,6 +80,21 @@ def test_float_t13_quotient_equals_ieee_for_every_float():
     assert int(cnt.item()) == 0
 
 
+def test_double_t13_quotient_seed_is_the_ieee_float_reciprocal_for_every_float():
+    """The double t13 quotient starts from the float32 reciprocal of the float32-rounded denominator; the kernel forms it as
+    MUFU.RCP + one Newton step and the oracle as `1.0f / d`.  They must agree for EVERY float the denominator em + 2 can
+    round to (2 <= d < 2^60; em < 2^56)."""
+    from rl4afcs_b200 import _lib
+
+    L = _lib.load()
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    lo = int(np.float32(2.0).view(np.uint32))
+    hi = int(np.float32(2.0 ** 60).view(np.uint32))
+    _lib.check(L.rl4_test_rcp_f32(lo, hi, cnt.data_ptr(), None), "rl4_test_rcp_f32")
+    torch.cuda.synchronize()
+    assert int(cnt.item()) == 0
+
+
 def test_plant_sincos_and_atmosphere_equal_oracle_bitwise(oracle):
     """The surrogate plant's sine / cosine and ISA series (include/rl4_citation_surrogate.h) are IEEE basic operations
     only: device == host bit for bit, and accurate (sin / cos < 2 ulp of libm; density == ISA power law to 1e-15)."""
