@@ -555,6 +555,8 @@ def sp_roofline(policy, n, K, ms, eng, counters, L):
     peak = ctypes.c_double(0.0)
     from rl4afcs_b200 import _lib
     _lib.check(L.rl4_peak_fma(1 if is_double else 0, ctypes.byref(peak), None), "rl4_peak_fma")
+    peak3 = ctypes.c_double(0.0)
+    _lib.check(L.rl4_peak_fma(3 if is_double else 2, ctypes.byref(peak3), None), "rl4_peak_fma")
     rate = n * K / (ms * 1e-3)                                     # rank 0's kernel; per GPU
     achieved = SURVEY_FLOP_PER_AGENT_STEP * rate
     state_bytes = eng.env.element_size() * 45 + eng.net.element_size() * 40 + 16
@@ -565,6 +567,9 @@ def sp_roofline(policy, n, K, ms, eng, counters, L):
             "flop_per_agent_step": SURVEY_FLOP_PER_AGENT_STEP,
             "special_ops_per_s": {k: v * rate for k, v in SURVEY_SPECIAL_PER_AGENT_STEP.items()},
             "peak_source": "rl4_peak_fma measured live on this GPU (MEASURED_PEAKS.json has no FP64/FP32 vector peak)",
+            "fma_rate_distinct_operands_tflops": peak3.value / 1e12,
+            "fma_rate_note": "the same micro-benchmark with three distinct register operands per FMA (the agent kernels' operand pattern); "
+                             "context only, the fraction above uses the shared-operand peak",
             "hbm_algorithmic_bytes_per_launch": 2 * state_bytes * n,
             "hbm_bytes_per_agent_step": 2 * state_bytes / K}
     prof = counters.get(f"sp_run_kernel_{policy}")

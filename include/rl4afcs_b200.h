@@ -472,7 +472,9 @@ typedef struct rl4_nl_host_io {
 int rl4_nl_episode_host(rl4_ctx* ctx, const rl4_nl_params* p, const rl4_nl_host_io* io, int64_t n_agents, int32_t n_steps);
 
 /* ---- measurement helpers (bench.py roofline denominators) ---- */
-/* Runs a dependent-FMA micro-kernel (is_double ? DFMA : FFMA) and returns achieved FLOP/s. */
+/* Runs an FMA micro-kernel and returns achieved FLOP/s.  is_double: 0 = FFMA, 1 = DFMA with 16 independent chains per thread
+ * whose multiplier and addend are shared (the pipe's peak, the roofline denominator); 2 / 3 = FFMA / DFMA whose three
+ * operands are distinct registers (what the pipe sustains on the agent kernels' operand pattern; reported beside it). */
 int rl4_peak_fma(int is_double, double* out_flops_per_s, void* stream);
 /* Test hook: element-wise probe of the arithmetic primitives on device arrays.
  * op 0: tanh t13 (double)  1: tanh t13 (float)  2: shared-reciprocal division a/b (double; RLS gain / covariance)

@@ -43,7 +43,27 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(T* out, int iters, T a, T
     if (s == (T)123456789) out[0] = s;   // never true; keeps the chains alive
 }
 
+// The same with three DISTINCT register operands per FMA (two ping-pong sets of 16 values): what the pipe sustains when
+// no operand is shared between instructions, as in the agent kernels (64-bit operands: six register reads per DFMA).
 template <typename T>
+__global__ void __launch_bounds__(256) fma3_peak_kernel(T* out, int iters)
+{
+    T a[16], b[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = (T)(threadIdx.x + j) * (T)1e-4;
+    for (int it = 0; it < iters; it += 2) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) b[j] = ::fma(a[j], a[(j + 5) & 15], a[(j + 11) & 15]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = ::fma(b[j], b[(j + 3) & 15], b[(j + 9) & 15]);
+    }
+    T s = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += a[j];
+    if (s == (T)123456789) out[0] = s;
+}
+
+template <typename T, bool DISTINCT = false>
 static int run_peak(double* out_flops, cudaStream_t stream)
 {
     int dev = 0, sms = 0;
@@ -61,7 +81,8 @@ static int run_peak(double* out_flops, cudaStream_t stream)
         goto done;
     for (int rep = 0; rep < 6; ++rep) {
         if (fail(cudaEventRecord(e0, stream), "cudaEventRecord")) goto done;
-        fma_peak_kernel<T><<<blocks, threads, 0, stream>>>(d, iters, (T)0.999, (T)1e-3);
+        if (DISTINCT) fma3_peak_kernel<T><<<blocks, threads, 0, stream>>>(d, iters);
+        else fma_peak_kernel<T><<<blocks, threads, 0, stream>>>(d, iters, (T)0.999, (T)1e-3);
         rc = check_launch("fma_peak_kernel");
         if (rc) goto done;
         if (fail(cudaEventRecord(e1, stream), "cudaEventRecord") || fail(cudaEventSynchronize(e1), "cudaEventSynchronize")) goto done;
@@ -159,8 +180,13 @@ int rl4_device_check(int device)
 int rl4_peak_fma(int is_double, double* out_flops_per_s, void* stream)
 {
     RL4_REQUIRE(out_flops_per_s != nullptr, "out_flops_per_s is NULL");
-    return is_double ? rl4::run_peak<double>(out_flops_per_s, (cudaStream_t)stream)
-                     : rl4::run_peak<float>(out_flops_per_s, (cudaStream_t)stream);
+    switch (is_double) {
+    case 0: return rl4::run_peak<float>(out_flops_per_s, (cudaStream_t)stream);
+    case 1: return rl4::run_peak<double>(out_flops_per_s, (cudaStream_t)stream);
+    case 2: return rl4::run_peak<float, true>(out_flops_per_s, (cudaStream_t)stream);
+    case 3: return rl4::run_peak<double, true>(out_flops_per_s, (cudaStream_t)stream);
+    default: rl4::set_error("rl4_peak_fma: mode %d (0 float, 1 double, 2 / 3 the same with three distinct register operands)", is_double); return -1;
+    }
 }
 
 int rl4_test_math(int op, const void* a, const void* b, void* out, int64_t n, void* stream)

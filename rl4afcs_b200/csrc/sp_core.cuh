@@ -92,7 +92,7 @@ __device__ __forceinline__ void sp_env_step(Rn<TE> (&x)[2], Rn<TN> action_deg, R
     const E u = cvt<TE>(u_n);
     // env.py:179  y = C@x + D*action with C = I, D = 0; env.py:180-184: error = ref - y[0] ('alpha') or ref - y[1] ('q')
     const E xt = tracked_q ? x[1] : x[0], xo = tracked_q ? x[0] : x[1];   // tracked / other state: one expression, two selects
-    const E y = fma(E(TE(0)), xo, E(TE(1)) * xt) + E(TE(0)) * u;
+    const E y = fma(E(TE(0)), xo, xt) + E(TE(0)) * u;                 // 1 * xt == xt bit for bit (the product by one is exact)
     e = ref - y;
     cost = (E(TE(-0.5)) * kappa) * (e * e);                           // env.py:187
     rg0 = kappa * (E(TE(-2)) * e);                                    // env.py:189
@@ -111,10 +111,26 @@ template <typename TN, typename W1T>
 __device__ __forceinline__ void sp_hidden3(Rn<TN> z, const Rn<TN> (&W1c)[4], const W1T& W1t, const Rn<TN> (&W1a)[4],
                                            Rn<TN> (&hc)[4], Rn<TN> (&ht)[4], Rn<TN> (&ha)[4])
 {
+#ifndef RL4_SP_TANH_GROUP
+#define RL4_SP_TANH_GROUP 12
+#endif
     Rn<TN> pre[12], h[12];
 #pragma unroll
     for (int j = 0; j < 4; ++j) { pre[j] = z * W1c[j]; pre[4 + j] = z * W1t[j]; pre[8 + j] = z * W1a[j]; }
+#if RL4_SP_TANH_GROUP == 12
     tanh_t13_n<12>(pre, h);
+#else
+    // smaller groups: fewer interleaved chains, fewer live temporaries
+#pragma unroll
+    for (int g = 0; g < 12; g += RL4_SP_TANH_GROUP) {
+        Rn<TN> pg[RL4_SP_TANH_GROUP], hg[RL4_SP_TANH_GROUP];
+#pragma unroll
+        for (int j = 0; j < RL4_SP_TANH_GROUP; ++j) pg[j] = pre[g + j];
+        tanh_t13_n<RL4_SP_TANH_GROUP>(pg, hg);
+#pragma unroll
+        for (int j = 0; j < RL4_SP_TANH_GROUP; ++j) h[g + j] = hg[j];
+    }
+#endif
 #pragma unroll
     for (int j = 0; j < 4; ++j) { hc[j] = h[j]; ht[j] = h[4 + j]; ha[j] = h[8 + j]; }
 }
@@ -233,7 +249,7 @@ __device__ __forceinline__ void sp_actor_forward(Rn<TN> z, const Rn<TN> (&h)[4],
 #pragma unroll
         for (int j = 0; j < 8; ++j) Ea[j] = trace_none_or_acc(elig, Ea[j], g[j], gl);
     }
-    const N g_o = N(TN(1)) * ai1;
+    const N g_o = ai1;                                            // dy = 1: 1 * ai1 == ai1 bit for bit
     N acc = ((g_o * W2[0]) * ai0[0]) * W1[0];
 #pragma unroll
     for (int j = 1; j < 4; ++j) acc = fma((g_o * W2[j]) * ai0[j], W1[j], acc);

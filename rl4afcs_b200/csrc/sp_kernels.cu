@@ -88,7 +88,18 @@ __device__ __forceinline__ void sp_load(SpAgent<TN, TE, SM>& s, const rl4_sp_sta
     s.conv_step = st.ints[(int64_t)RL4_SPI_CONV_STEP * st.stride + i];
 }
 
+// the Jacobian traces (actor E (1,8), critic E: 12 unique of 24)
 template <typename TN, typename TE, bool SM>
+__device__ __forceinline__ void sp_store_traces(const SpAgent<TN, TE, SM>& s, const rl4_sp_state& st, int64_t i)
+{
+    const Plane<TE> e{(TE*)st.env, st.stride};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) e.st(RL4_SPE_EA + j, i, s.Ea[j]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { e.st(RL4_SPE_EC_H + j, i, s.EcH[j]); e.st(RL4_SPE_EC_W1R0 + j, i, s.EcR0[j]); e.st(RL4_SPE_EC_W1R1 + j, i, s.EcR1[j]); }
+}
+
+template <typename TN, typename TE, bool SM, bool WITH_TRACES = true>
 __device__ __forceinline__ void sp_store(const SpAgent<TN, TE, SM>& s, const rl4_sp_state& st, int64_t i)
 {
     const Plane<TE> e{(TE*)st.env, st.stride};
@@ -103,10 +114,7 @@ __device__ __forceinline__ void sp_store(const SpAgent<TN, TE, SM>& s, const rl4
     e.st(RL4_SPE_EPS_NORM, i, s.epsn);
     e.st(RL4_SPE_SUM_C, i, s.sumc);
     e.st(RL4_SPE_SUM_ABS_E, i, s.sumabse);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) e.st(RL4_SPE_EA + j, i, s.Ea[j]);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { e.st(RL4_SPE_EC_H + j, i, s.EcH[j]); e.st(RL4_SPE_EC_W1R0 + j, i, s.EcR0[j]); e.st(RL4_SPE_EC_W1R1 + j, i, s.EcR1[j]); }
+    if (WITH_TRACES) sp_store_traces<TN, TE, SM>(s, st, i);
     n.st(RL4_SPN_A, i, s.a); n.st(RL4_SPN_APREV, i, s.ap);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -190,6 +198,12 @@ sp_run_kernel(const __grid_constant__ rl4_sp_params p, const double* __restrict_
     for (; k < k0 + n_steps; ++k) {
         if (s.diverged_step >= 0) break;            // the reference left its loop (objects.py:991)
         sp_agent_step<TN, TE, TRACES, PER_AGENT, SM>(s, p, hv, k, __ldg(ref_base + k), o);
+        if (!TRACES) {
+            // Without eligibility traces E is this step's Jacobian, overwritten by every step and read only inside it: it
+            // goes to the state planes from the last step an agent executes and is NOT carried across iterations
+            // (20 values = 40 registers that would otherwise stay live for the store after the loop).
+            if (k == k0 + n_steps - 1 || s.diverged_step >= 0) sp_store_traces<TN, TE, SM>(s, st, i);
+        }
         if (LOG != RL4_LOG_NONE) {
             if (logged && (k - k0) % lg.every == 0) { s.refresh_epsn(); sp_write_log<TN, TE, LOG, SM>(lg, (k - k0) / lg.every, i, k, s, o); }
         }
@@ -205,7 +219,7 @@ sp_run_kernel(const __grid_constant__ rl4_sp_params p, const double* __restrict_
         }
     }
     s.refresh_epsn();
-    sp_store<TN, TE, SM>(s, st, i);
+    sp_store<TN, TE, SM, TRACES>(s, st, i);
 }
 
 // IDHPsp.__init__ + train() prologue (objects.py:552-615, 843-851, 911-948); env.reset (env.py:222-258)

@@ -9,6 +9,7 @@ import torch
 
 from . import _lib
 from ._lib import NHP, NHPI, NLE, NLI, NLN
+from .sp_engine import _collapse
 
 
 def theta_reference(t_end=90, dt=0.01):
@@ -67,6 +68,7 @@ class NlEngine:
 
     def set_hp(self, name, value):
         j = NHP[name]
+        value = _collapse(value)
         if np.ndim(value) == 0:
             self.params.hp[j] = float(value); self.params.hp_agent[j] = None; self._keep.pop(("hp", j), None)
         else:
@@ -76,6 +78,7 @@ class NlEngine:
 
     def set_hpi(self, name, value):
         j = NHPI[name]
+        value = _collapse(value)
         if np.ndim(value) == 0:
             self.params.hpi[j] = int(value); self.params.hpi_agent[j] = None; self._keep.pop(("hpi", j), None)
         else:

@@ -63,6 +63,17 @@ def plant_variants():
 _TORCH_DT = {"f8": torch.float64, "f4": torch.float32}
 
 
+def _collapse(value):
+    """A per-agent array whose entries are all equal is the shared scalar (the kernels then read it from the constant bank
+    and the trace-free / uniform instantiations stay available)."""
+    if np.ndim(value) == 0:
+        return value
+    a = np.asarray(value)
+    if a.size and (a == a.flat[0]).all():
+        return a.flat[0]
+    return value
+
+
 def policy_dtypes(policy: str):
     """(network dtype, env dtype) of a dtype policy."""
     return {"fp64": (torch.float64, torch.float64), "fp32": (torch.float32, torch.float32),
@@ -106,6 +117,7 @@ class SpEngine:
     def set_hp(self, name: str, value) -> None:
         """Shared scalar or per-agent array (length n_agents) for a float hyper-parameter."""
         j = HP[name]
+        value = _collapse(value)
         if np.ndim(value) == 0:
             self.params.hp[j] = float(value)
             self.params.hp_agent[j] = None
@@ -119,6 +131,7 @@ class SpEngine:
 
     def set_hpi(self, name: str, value) -> None:
         j = HPI[name]
+        value = _collapse(value)
         if np.ndim(value) == 0:
             self.params.hpi[j] = int(value)
             self.params.hpi_agent[j] = None
