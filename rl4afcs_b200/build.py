@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "librl4afcs_b200.so")
 SOURCES = ["runtime.cu", "sp_kernels.cu", "nl_kernels.cu", "step_kernels.cu", "host_episode.cu"]
-HEADERS = ["rl4_math.cuh", "sp_core.cuh", "rl4_runtime.h", os.path.join("..", "..", "include", "rl4afcs_b200.h"),
+HEADERS = ["rl4_math.cuh", "sp_core.cuh", "nl_pipeline.cuh", "rl4_runtime.h", os.path.join("..", "..", "include", "rl4afcs_b200.h"),
            os.path.join("..", "..", "include", "rl4_citation_surrogate.h")]
 
 NVCC_FLAGS = [
@@ -41,7 +41,7 @@ def _nvcc() -> str:
 # over a minute to compile, the rest seconds)
 _COMMON = ["rl4_math.cuh", "rl4_runtime.h", os.path.join("..", "..", "include", "rl4afcs_b200.h"),
            os.path.join("..", "..", "include", "rl4_citation_surrogate.h")]
-DEPS = {"runtime.cu": _COMMON, "sp_kernels.cu": _COMMON + ["sp_core.cuh"], "nl_kernels.cu": _COMMON,
+DEPS = {"runtime.cu": _COMMON, "sp_kernels.cu": _COMMON + ["sp_core.cuh"], "nl_kernels.cu": _COMMON + ["nl_pipeline.cuh"],
         "step_kernels.cu": _COMMON, "host_episode.cu": _COMMON}
 OBJ_DIR = os.path.join(_HERE, "build")
 

@@ -640,6 +640,10 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
 #undef NF
 }
 
+}  // namespace rl4
+#include "nl_pipeline.cuh"
+namespace rl4 {
+
 // Ce500NonLinear.reset (envs/nonlinear/env.py:278-291): the model's built-in initial state, then 1000 + 1 steps at trim
 // input.  Every agent shares the plant and the trim input, and the plant is IEEE-basic-operations only, so the 1001 steps
 // are integrated ONCE on the host (same header, same bits as on the device) and broadcast by the init kernel.
@@ -748,11 +752,36 @@ static int nl_launch_one(const rl4_nl_params* p, const double* theta_ref, const 
     return 0;
 }
 
+#ifndef RL4_NL_PIPELINE
+#define RL4_NL_PIPELINE 1       // log-free launches take the two-role pipeline kernel (nl_pipeline.cuh); 0: always the one-thread kernel
+#endif
+
+template <typename TN, int INTEG, bool PER_AGENT>
+static int nl_launch_pipe(const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride, int k0,
+                          int n_steps, rl4_nl_state st, int64_t n, cudaStream_t s)
+{
+    const size_t smem = PipeSmem<TN>::bytes;
+    RL4_CUDA(cudaFuncSetAttribute(nl_pipe_kernel<TN, INTEG, PER_AGENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((n + kPipeAgents - 1) / kPipeAgents);
+    nl_pipe_kernel<TN, INTEG, PER_AGENT><<<grid, kPipeThreads, smem, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n);
+    return 0;
+}
+
 template <typename TN>
 static int nl_launch(const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride, int k0, int n_steps,
                      rl4_nl_state st, int64_t n, rl4_sp_log lg, bool log, bool per_agent, unsigned grid, cudaStream_t s)
 {
     const bool rk4 = (p->integrator == RL4_CIT_INTEGRATOR_RK4);
+#if RL4_NL_PIPELINE
+    // the pipeline kernel covers log-free launches in the 'none' / 'accumulating' trace modes (the 'replacing' mode needs a
+    // norm over all 50 trace elements in a fixed order; a per-agent mode array may contain it)
+    if (!log && p->hpi[RL4_NHPI_ELIG_A] != RL4_ELIG_REPLACING && !p->hpi_agent[RL4_NHPI_ELIG_A]) {
+        if (per_agent) return rk4 ? nl_launch_pipe<TN, RL4_CIT_INTEGRATOR_RK4, true>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, s)
+                                  : nl_launch_pipe<TN, RL4_CIT_INTEGRATOR_ODE5, true>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, s);
+        return rk4 ? nl_launch_pipe<TN, RL4_CIT_INTEGRATOR_RK4, false>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, s)
+                   : nl_launch_pipe<TN, RL4_CIT_INTEGRATOR_ODE5, false>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, s);
+    }
+#endif
     // logging launches always take the general (per-agent capable) instantiation; the log-free hot path is specialised
     if (log) return rk4 ? nl_launch_one<TN, RL4_CIT_INTEGRATOR_RK4, true, true>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s)
                         : nl_launch_one<TN, RL4_CIT_INTEGRATOR_ODE5, true, true>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, grid, s);
