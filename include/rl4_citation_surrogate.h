@@ -365,7 +365,11 @@ RL4_HD void rl4_cit_deriv_lon(const rl4_cit_params* P, const rl4_cit_air air, co
     const double q = z[0], V = z[1], al = z[2], th = z[3];
     const double de = c[0], flap = c[1], gear = c[2], thr = c[3], dxcg = c[4];
     double sa, ca, sth, cth;
-    RL4_SINCOS(al, sa, ca); RL4_SINCOS(th, sth, cth);
+    /* The exact-zero shortcut of RL4_SINCOS as a select instead of a branch: rl4_sincos(+-0) = (+0, 1), the shortcut returns
+     * (+-0, 1), so only the sign of a zero sine needs restoring.  The whole stage is then one branch-free block and the two
+     * evaluations interleave (alpha and theta are never zero in flight). */
+    rl4_sincos(al, &sa, &ca); rl4_sincos(th, &sth, &cth);
+    sa = (al == 0.0) ? al : sa; sth = (th == 0.0) ? th : sth;
     const double invV = 1.0 / V;
     const double qS = (0.5 * air.rho * P->S) * (V * V);
     const double ch = (0.5 * P->c) * invV;

@@ -27,7 +27,14 @@
 
 namespace rl4 {
 
-constexpr int kPipeAgents = 128;                       // agents per CTA: 4 P-warps (1 thread each) + 8 N-warps (2 lanes each)
+#ifndef RL4_PIPE_REGS_P
+#define RL4_PIPE_REGS_P 0        // 0: one register budget for both roles; else setmaxnreg values for the P / N warpgroups
+#define RL4_PIPE_REGS_N 0
+#endif
+#ifndef RL4_PIPE_AGENTS
+#define RL4_PIPE_AGENTS 64       // agents per CTA (a multiple of 32): 192 threads, two CTAs per SM (measured: 32 = 64 > 128 by 2 %)
+#endif
+constexpr int kPipeAgents = RL4_PIPE_AGENTS;                       // agents per CTA: 4 P-warps (1 thread each) + 8 N-warps (2 lanes each)
 constexpr int kPipeThreads = 3 * kPipeAgents;
 constexpr int kPipeNLanes = 2 * kPipeAgents;
 
@@ -141,7 +148,7 @@ __device__ __forceinline__ void pipe_plant_step(const rl4_cit_params& P, double 
 }
 
 template <typename TN, int INTEG, bool PER_AGENT>
-__global__ void __launch_bounds__(kPipeThreads, 1)
+__global__ void __launch_bounds__(kPipeThreads, 128 / kPipeAgents)
 nl_pipe_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict__ theta_ref, const float* __restrict__ noise,
                int64_t noise_stride, int k0, int n_steps, const rl4_nl_state st, int64_t n_agents)
 {
@@ -163,6 +170,12 @@ nl_pipe_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict
     const int k_end = k0 + n_steps;
     const bool f32 = sizeof(TN) == 4;
 
+#if RL4_PIPE_REGS_P
+    // warpgroup-level register re-allocation: the plant role keeps 12 states + six Runge-Kutta stage vectors in flight, the
+    // network role holds 60 weights and little else.  128 x P + 256 x N registers must not exceed the CTA's allocation.
+    if (roleP) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RL4_PIPE_REGS_P));
+    else       asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RL4_PIPE_REGS_N));
+#endif
     if (roleP) {
         // =========================== role P: plant + env wrapper + RLS + statistics ===========================
         const int la = tid;                                                    // agent slot inside the CTA
