@@ -50,6 +50,22 @@ enum { RL4_CIT_P = 0, RL4_CIT_Q, RL4_CIT_R, RL4_CIT_V, RL4_CIT_ALPHA, RL4_CIT_BE
        RL4_CIT_PSI, RL4_CIT_H, RL4_CIT_XE, RL4_CIT_YE };
 enum { RL4_CIT_INTEGRATOR_RK4 = 0, RL4_CIT_INTEGRATOR_ODE5 = 1 };
 
+/* Longitudinal slopes identified against the reference's own plant binary (oracle/pe_probe/fit_surrogate.py --trajectories:
+ * stage 1, least squares on the binary's one-step map over 20 000 states of the task envelope for the force slopes and
+ * the thrust-speed slope; stage 2, trajectory match on four open-loop elevator manoeuvres for the three pitch-moment
+ * slopes).  The AE3202 table values used in round 1 are quoted beside them: that table's aeroplane had 1.8x the elevator
+ * power and a third of the pitch damping of the reference's. */
+#define RL4_FIT_CLA  6.6284758345693255     /* AE3202: 5.16   */
+#define RL4_FIT_CLQ  13.059503256533402     /* AE3202: 3.86   */
+#define RL4_FIT_CLDE 0.41340524505785026    /* AE3202: 0.6238 */
+#define RL4_FIT_CD0  0.015                  /* AE3202: 0.04   (lower bound of the fit) */
+#define RL4_FIT_CDK  0.07643021209086866    /* AE3202: 0.052  */
+#define RL4_FIT_CMA  -0.6634444312074602    /* AE3202: -0.43  */
+#define RL4_FIT_CMQ  -25.0                  /* AE3202: -7.04  (bound of the fit: the binary's alpha-dot moments are lumped in) */
+#define RL4_FIT_CMDE -1.3524530096077292    /* AE3202: -1.553 */
+#define RL4_FIT_TV   -0.011411097863068305  /* relative thrust change per m/s of airspeed; round 1: 0 */
+#define RL4_FIT_XCG  -0.8155089190491744    /* c.g. displacement per unit of input[10] (regression on the one-step map, r = -0.985); round 1: +1 */
+
 typedef struct rl4_cit_params {
     /* mass and geometry */
     double m, S, c, b, Ixx, Iyy, Izz, Ixz, g;
@@ -61,8 +77,12 @@ typedef struct rl4_cit_params {
     double CYb, CYp, CYr, CYda, CYdr;
     double Clb, Clp, Clr, Clda, Cldr;
     double Cnb, Cnp, Cnr, Cnda, Cndr;
-    /* propulsion: T = Tstatic * (rho/rho0)^0.7 * (thr1 + thr2)/2, along body x through the c.g. */
-    double Tstatic;
+    /* propulsion: T = Tstatic * (rho/rho0)^0.7 * (thr1 + thr2)/2 * (1 + TV (V - Vref)), along body x through the c.g.
+     * (a turbofan's thrust falls with airspeed; TV is the relative slope per m/s) */
+    double Tstatic, TV, Vref;
+    /* input[10] (the reference's `shift_cg` fault sets it to -0.5, envs/nonlinear/env.py:141-143) -> c.g. displacement [m]:
+     * sign and size identified against the binary (a NEGATIVE input pitches the reference's aircraft DOWN) */
+    double xcg_gain;
     /* reciprocals used by rl4_cit_deriv, filled by rl4_cit_finalize() */
     double inv_m, inv_Iyy, inv_gam, inv_al_stall, inv_c, inv_b;
     /* ISA troposphere as binomial series in zeta = lapse h / T0, filled by rl4_cit_finalize():
@@ -193,7 +213,7 @@ RL4_HD_NOINLINE void rl4_cit_deriv(const rl4_cit_params* P, const rl4_cit_air ai
     const double V = x[RL4_CIT_V], al = x[RL4_CIT_ALPHA], be = x[RL4_CIT_BETA];
     const double phi = x[RL4_CIT_PHI], th = x[RL4_CIT_THETA], psi = x[RL4_CIT_PSI];
     const double de = u[0] + u[3], da = u[1] + u[4], dr = u[2] + u[5];
-    const double flap = u[6], gear = u[7], thr = 0.5 * (u[8] + u[9]), dxcg = u[10];
+    const double flap = u[6], gear = u[7], thr = 0.5 * (u[8] + u[9]), dxcg = P->xcg_gain * u[10];
 
     double sa, ca, sb, cb, sphi, cphi, sth, cth, spsi, cpsi;
     RL4_SINCOS(al, sa, ca); RL4_SINCOS(be, sb, cb); RL4_SINCOS(phi, sphi, cphi); RL4_SINCOS(th, sth, cth); RL4_SINCOS(psi, spsi, cpsi);
@@ -221,7 +241,7 @@ RL4_HD_NOINLINE void rl4_cit_deriv(const rl4_cit_params* P, const rl4_cit_air ai
     const double Cn = RL4_FMA(-CY * dxcg, P->inv_b, RL4_FMA(P->Cndr, dr, RL4_FMA(P->Cnda, da, RL4_FMA(P->Cnr, rh,
                       RL4_FMA(P->Cnp, ph, P->Cnb * be)))));
 
-    const double T = P->Tstatic * air.thrust_lapse * thr;
+    const double T = (P->Tstatic * air.thrust_lapse * thr) * RL4_FMA(P->TV, V - P->Vref, 1.0);
     const double ax = RL4_FMA(qS, CX, T) * P->inv_m, ay = (qS * CY) * P->inv_m, az = (qS * CZ) * P->inv_m;   /* specific forces */
     const double L = (qS * P->b) * Cl, M = (qS * P->c) * Cm, N = (qS * P->b) * Cn;
 
@@ -363,7 +383,7 @@ RL4_HD int rl4_cit_is_symmetric(const double* x, const double* u)
 RL4_HD void rl4_cit_deriv_lon(const rl4_cit_params* P, const rl4_cit_air air, const double* z, const double* c, double* dz)
 {
     const double q = z[0], V = z[1], al = z[2], th = z[3];
-    const double de = c[0], flap = c[1], gear = c[2], thr = c[3], dxcg = c[4];
+    const double de = c[0], flap = c[1], gear = c[2], thr = c[3], dxcg = P->xcg_gain * c[4];
     double sa, ca, sth, cth;
     /* The exact-zero shortcut of RL4_SINCOS as a select instead of a branch: rl4_sincos(+-0) = (+0, 1), the shortcut returns
      * (+-0, 1), so only the sign of a zero sine needs restoring.  The whole stage is then one branch-free block and the two
@@ -383,7 +403,7 @@ RL4_HD void rl4_cit_deriv_lon(const rl4_cit_params* P, const rl4_cit_air air, co
     const double CZ = -RL4_FMA(CL, ca, CD * sa);
     const double Cm = RL4_FMA(CZ * dxcg, P->inv_c, RL4_FMA(P->Cmflap, flap, RL4_FMA(P->Cmde, de, RL4_FMA(P->Cmq, qh,
                       RL4_FMA(P->Cmstall, al_x, RL4_FMA(P->Cma, al, P->Cm0))))));
-    const double T = P->Tstatic * air.thrust_lapse * thr;
+    const double T = (P->Tstatic * air.thrust_lapse * thr) * RL4_FMA(P->TV, V - P->Vref, 1.0);
     const double ax = RL4_FMA(qS, CX, T) * P->inv_m, az = (qS * CZ) * P->inv_m;
     const double M = (qS * P->c) * Cm;
     const double ub = V * ca, wb = V * sa;                              /* cb = 1 */
@@ -477,23 +497,14 @@ RL4_HD void rl4_cit_step_auto(const rl4_cit_params* P, double* x, const double* 
     if (integrator == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(P, x, u, dt); else rl4_cit_step_ode5(P, x, u, dt);
 }
 
-/* Default parameter set: Ce500 Citation derivatives, with CL0 / Cm0 / Tstatic solved for the trim point
- * (V, h, alpha = theta, de, throttle) = (90, 2000, 0.0576, -0.02855, 0.55) of idhp_nonlin.py:53-54. */
-RL4_HD void rl4_cit_default_params(rl4_cit_params* P)
+/* CL0, Cm0 and the static thrust for which (V, h, alpha = theta, de, throttle) = (90, 2000, 0.0576, -0.02855, 0.55) -- the
+ * trim point of idhp_nonlin.py:53-54 -- is an exact equilibrium of the model with the slopes currently in *P:
+ * T cos(al) = D, L + T sin(al) = W with D = qS (CD0 + k CL^2 + ...), L = qS CL:
+ * k/qS (W - T sa)^2 + qS CD0 - T ca = 0  ->  quadratic in T, smaller root. */
+RL4_HD void rl4_cit_solve_trim(rl4_cit_params* P)
 {
     const double V = 90.0, h = 2000.0, al = 0.0576, de = -0.02855, thr = 0.55;
     double rho, lapse, qS, sa, ca, W, T, CLt, A, B, C, al_e, al_x;
-    P->m = 4547.8; P->S = 24.2; P->c = 2.022; P->b = 13.36; P->g = 9.80665;
-    P->Ixx = P->m * P->b * P->b * 0.012; P->Izz = P->m * P->b * P->b * 0.037; P->Ixz = P->m * P->b * P->b * 0.002;
-    P->Iyy = P->m * P->c * P->c * 0.980;       /* K_Y^2 = Iyy / (m c^2) */
-    P->CLa = 5.16; P->CLq = 3.86; P->CLde = 0.6238; P->CLflap = 0.6; P->al_stall = 0.28;
-    P->CD0 = 0.04; P->CDk = 0.052; P->CDgear = 0.02; P->CDflap = 0.04; P->CDstall = 8.0;
-    P->Cma = -0.43; P->Cmq = -7.04; P->Cmde = -1.553; P->Cmflap = -0.05; P->Cmstall = -6.0;
-    P->CYb = -0.9896; P->CYp = -0.087; P->CYr = 0.43; P->CYda = 0.0; P->CYdr = 0.3037;
-    P->Clb = -0.0772; P->Clp = -0.3444; P->Clr = 0.28; P->Clda = -0.2349; P->Cldr = 0.0286;
-    P->Cnb = 0.1638; P->Cnp = -0.0108; P->Cnr = -0.193; P->Cnda = 0.0286; P->Cndr = -0.1261;
-    /* level trim: T cos(al) = D, L + T sin(al) = W with D = qS (CD0 + k CL^2), L = qS CL:
-     * k/qS * (W - T sa)^2 + qS CD0 - T ca = 0  ->  quadratic in T, smaller root */
     rl4_cit_finalize(P);                                   /* atmosphere tables are needed by the trim solve */
     {
         const rl4_cit_air air = rl4_cit_airdata(P, h);
@@ -507,8 +518,29 @@ RL4_HD void rl4_cit_default_params(rl4_cit_params* P)
     CLt = (W - T * sa) / qS;
     P->CL0 = CLt - P->CLa * al_e - P->CLde * de;
     P->Cm0 = -(P->Cma * al + P->Cmstall * al_x + P->Cmde * de);
-    P->Tstatic = T / (lapse * thr);
+    P->Vref = V;
+    P->Tstatic = T / (lapse * thr);                        /* the speed factor 1 + TV (V - Vref) is one at the trim speed */
     rl4_cit_finalize(P);
+}
+
+/* Default parameter set.  Geometry, mass and the lateral-directional derivatives are the Cessna Ce500 Citation table of the
+ * TU Delft AE3202 lecture notes (the table envs/linear/env.py:68-87 quotes).  The LONGITUDINAL slopes and the thrust-speed
+ * slope are identified against the one-step map of the reference's own plant binary, run in-process by oracle/pe_probe
+ * (fit_surrogate.py: 20 000 samples over the envelope of the pitch-tracking task, least squares inside a physically
+ * plausible box); CL0, Cm0 and the static thrust then follow from the reference's trim point. */
+RL4_HD void rl4_cit_default_params(rl4_cit_params* P)
+{
+    P->m = 4547.8; P->S = 24.2; P->c = 2.022; P->b = 13.36; P->g = 9.80665;
+    P->Ixx = P->m * P->b * P->b * 0.012; P->Izz = P->m * P->b * P->b * 0.037; P->Ixz = P->m * P->b * P->b * 0.002;
+    P->Iyy = P->m * P->c * P->c * 0.980;       /* K_Y^2 = Iyy / (m c^2) */
+    P->CLa = RL4_FIT_CLA; P->CLq = RL4_FIT_CLQ; P->CLde = RL4_FIT_CLDE; P->CLflap = 0.6; P->al_stall = 0.28;
+    P->CD0 = RL4_FIT_CD0; P->CDk = RL4_FIT_CDK; P->CDgear = 0.02; P->CDflap = 0.04; P->CDstall = 8.0;
+    P->Cma = RL4_FIT_CMA; P->Cmq = RL4_FIT_CMQ; P->Cmde = RL4_FIT_CMDE; P->Cmflap = -0.05; P->Cmstall = -6.0;
+    P->CYb = -0.9896; P->CYp = -0.087; P->CYr = 0.43; P->CYda = 0.0; P->CYdr = 0.3037;
+    P->Clb = -0.0772; P->Clp = -0.3444; P->Clr = 0.28; P->Clda = -0.2349; P->Cldr = 0.0286;
+    P->Cnb = 0.1638; P->Cnp = -0.0108; P->Cnr = -0.193; P->Cnda = 0.0286; P->Cndr = -0.1261;
+    P->TV = RL4_FIT_TV; P->xcg_gain = RL4_FIT_XCG;
+    rl4_cit_solve_trim(P);
 }
 
 #endif

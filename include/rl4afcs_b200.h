@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RL4_ABI_VERSION 2      /* bumped whenever a struct, enum or signature below changes; _lib.load() checks it */
+#define RL4_ABI_VERSION 3      /* bumped whenever a struct, enum or signature below changes; _lib.load() checks it */
 
 enum rl4_policy { RL4_FP64 = 0, RL4_FP32 = 1, RL4_MIXED = 2 };
 enum rl4_elig   { RL4_ELIG_NONE = 0, RL4_ELIG_ACCUMULATING = 1, RL4_ELIG_REPLACING = 2 };
@@ -336,6 +336,11 @@ enum rl4_nl_mclog_field {
 
 /* Fills *p with the configuration of idhp_nonlin.py:36-54,107-146 and the default surrogate plant (host only). */
 int rl4_nl_default_params(rl4_nl_params* p);
+/* Host only: the plant state Ce500NonLinear.reset leaves behind (envs/nonlinear/env.py:278-291: initialize, 1000 + 1
+ * model.step calls at the trim input).  out_state [12] = the state the plant carries into the episode (1001 integrations),
+ * out_observed [12] = what the last model.step call returned = env.state after reset (the plant returns the state BEFORE
+ * each step: 1000 integrations).  Either may be NULL. */
+int rl4_nl_trim_state(const rl4_nl_params* p, double* out_state, double* out_observed);
 /* Ce500NonLinear.reset (envs/nonlinear/env.py:258-311: 1000 + 1 plant steps at trim input) and the
  * IDHPnonlin.train() prologue (objects.py:1466-1488).  Weights: planes of double, W1a [40][stride_in]
  * ((4,10) row-major), W2a [10], W1c [40], W2c [30] ((10,3) row-major). */
@@ -365,12 +370,15 @@ int rl4_nl_critic_forward(int policy, const void* s, void* w1, void* w2, void* o
 int rl4_nl_actor_forward(int policy, const void* s, void* w1, void* w2, double* E, void* out_a, void* out_dads,
                          double gamma_lambda, int32_t elig, int32_t trace, int64_t stride, int64_t n_agents, void* stream);
 /* Ce500NonLinear.step alone (envs/nonlinear/env.py:182-256): action [3][stride] normalised commands (double),
- * x_full [12][stride], x_act [3][stride] in/out; out_mdp [4][stride], out_reward (longitudinal), out_e_theta [stride];
- * out_surf [3][stride] = info['action_commanded'] (surface positions after saturation), out_eff [3][stride] =
- * info['action_effective'] (model_input[:3]); either may be NULL. */
+ * x_full [12][stride] (the plant's carried state), x_act [3][stride] in/out; out_mdp [4][stride], out_reward
+ * (longitudinal), out_e_theta [stride]; out_surf [3][stride] = info['action_commanded'] (surface positions after
+ * saturation), out_eff [3][stride] = info['action_effective'] (model_input[:3]), out_x_obs [12][stride] =
+ * info['x_full'] = what model.step returned -- the reference's plant is an output-then-update block, step() returns
+ * the state BEFORE the step (oracle/pe_probe); the MDP state, errors and rewards are functions of it.  The three
+ * optional outputs may be NULL. */
 int rl4_nl_env_step(const rl4_nl_params* p, const double* theta_ref, int32_t stepp, double* x_full, double* x_act,
                     const double* action, double* out_mdp, double* out_reward, double* out_e_theta, double* out_surf,
-                    double* out_eff, int64_t stride, int64_t n_agents, void* stream);
+                    double* out_eff, double* out_x_obs, int64_t stride, int64_t n_agents, void* stream);
 
 /* ---- step-API arithmetic that the reference does in TensorFlow / numpy one-liners ---- */
 /* Critic / Actor / Critic_big.soft_update (objects.py:207-215, 273-281, 353-361): target <- (1 - tau) target + tau source,

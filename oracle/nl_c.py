@@ -12,7 +12,7 @@ from . import sp_c
 PLANT_FIELDS = ["m", "S", "c", "b", "Ixx", "Iyy", "Izz", "Ixz", "g", "CL0", "CLa", "CLq", "CLde", "CLflap", "al_stall",
                 "CD0", "CDk", "CDgear", "CDflap", "CDstall", "Cm0", "Cma", "Cmq", "Cmde", "Cmflap", "Cmstall",
                 "CYb", "CYp", "CYr", "CYda", "CYdr", "Clb", "Clp", "Clr", "Clda", "Cldr",
-                "Cnb", "Cnp", "Cnr", "Cnda", "Cndr", "Tstatic",
+                "Cnb", "Cnp", "Cnr", "Cnda", "Cndr", "Tstatic", "TV", "Vref", "xcg_gain",
                 "inv_m", "inv_Iyy", "inv_gam", "inv_al_stall", "inv_c", "inv_b"]
 PLANT_DTYPE = np.dtype([(f, "f8") for f in PLANT_FIELDS] + [("zeta_per_m", "f8"), ("rho_poly", "f8", (21,)),
                         ("lapse_poly", "f8", (21,))], align=True)
@@ -167,12 +167,13 @@ def rls_update(gamma, theta, cov, dx0, da0, dx1):
 
 def env_step(cfg, theta_ref_k, act, x_full, x_act, stepp):
     """One Ce500NonLinear.step without the agent (envs/nonlinear/env.py:182-256) for ONE aircraft; x_full (12,) and
-    x_act (3,) are updated in place.  Returns dict(surf, u, e, reward)."""
+    x_act (3,) are updated in place (x_full is the plant's carried state).  Returns dict(surf, u, e, reward, x_obs) with
+    x_obs = what model.step returned, i.e. the state before this step (output-then-update)."""
     L = lib()
     L.orc_nl_env_step.argtypes = [ctypes.c_void_p, ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                  ctypes.c_int32] + [ctypes.c_void_p] * 4
+                                  ctypes.c_int32] + [ctypes.c_void_p] * 5
     act = np.ascontiguousarray(act, dtype=np.float64)
-    surf, u, e, r = np.zeros(3), np.zeros(11), np.zeros(3), np.zeros(1)
+    surf, u, e, r, xo = np.zeros(3), np.zeros(11), np.zeros(3), np.zeros(1), np.zeros(12)
     L.orc_nl_env_step(_ptr(cfg), float(theta_ref_k), _ptr(act), _ptr(x_full), _ptr(x_act), int(stepp), _ptr(surf), _ptr(u),
-                      _ptr(e), _ptr(r))
-    return dict(surf=surf, u=u, e=e, reward=float(r[0]))
+                      _ptr(e), _ptr(r), _ptr(xo))
+    return dict(surf=surf, u=u, e=e, reward=float(r[0]), x_obs=xo)

@@ -46,7 +46,7 @@ void orc_nl_rls_update(double gamma, double* theta, double* cov, const double* d
 /* Ce500NonLinear.step without the agent (envs/nonlinear/env.py:182-256): action scaling (:111-124), rate-limited
  * actuators (:161-180), saturation faults (:150-159), damping / c.g. / slow-actuator faults (:127-148), plant step (:210),
  * errors and the longitudinal reward (:215-220).  stepp is the env's counter BEFORE the step. */
-typedef struct { double surf[3], u[11], e[3], reward, rg2; } orc_nl_envout;
+typedef struct { double surf[3], u[11], e[3], reward, rg2, x_obs[12]; } orc_nl_envout;
 static void orc_nl_env_core(const orc_nl_cfg* c, double theta_ref_k, const double* act, double* x_full, double* x_act,
                             int32_t stepp, orc_nl_envout* o)
 {
@@ -86,25 +86,38 @@ static void orc_nl_env_core(const orc_nl_cfg* c, double theta_ref_k, const doubl
         }
     }
     for (int i = 0; i < 11; ++i) o->u[i] = c->trim_input[i] + eff[i];             /* env.py:207-208 */
+    /* env.py:210  x_full = model.step(input).  The reference's plant binary is an output-then-update block: step() RETURNS
+     * the state before the step and then integrates (oracle/pe_probe/README.md), so the wrapper observes the aircraft one
+     * sample late.  x_full (the carried state) is advanced; everything the wrapper computes uses the returned x_obs. */
+    memcpy(o->x_obs, x_full, sizeof o->x_obs);
     if (c->integrator == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(&c->plant, x_full, o->u, dt);
-    else rl4_cit_step_ode5(&c->plant, x_full, o->u, dt);                           /* env.py:210 */
-    o->e[0] = x_full[6] - 0.0; o->e[1] = x_full[7] - theta_ref_k; o->e[2] = x_full[8] - 0.0;   /* env.py:215 (state - ref) */
+    else rl4_cit_step_ode5(&c->plant, x_full, o->u, dt);
+    o->e[0] = o->x_obs[6] - 0.0; o->e[1] = o->x_obs[7] - theta_ref_k; o->e[2] = o->x_obs[8] - 0.0;   /* env.py:215 (state - ref) */
     o->reward = (-0.5 * c->Q_sym) * (o->e[1] * o->e[1]);                           /* env.py:218 */
     o->rg2 = (-c->Q_sym) * o->e[1];
 }
 
 /* test exports: one env step / one bare plant step / the plant's built-in initial state */
 void orc_nl_env_step(const orc_nl_cfg* c, double theta_ref_k, const double* act, double* x_full, double* x_act, int32_t stepp,
-                     double* surf, double* u, double* e, double* reward)
+                     double* surf, double* u, double* e, double* reward, double* x_obs)
 {
     orc_nl_envout o;
     orc_nl_env_core(c, theta_ref_k, act, x_full, x_act, stepp, &o);
     memcpy(surf, o.surf, sizeof o.surf); memcpy(u, o.u, sizeof o.u); memcpy(e, o.e, sizeof o.e); *reward = o.reward;
+    memcpy(x_obs, o.x_obs, sizeof o.x_obs);
 }
 void orc_cit_plant_step(const rl4_cit_params* P, double* x, const double* u, double dt, int integrator)
 {
     if (integrator == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(P, x, u, dt); else rl4_cit_step_ode5(P, x, u, dt);
 }
+
+/* the one-step map of the surrogate for n samples (oracle/pe_probe/fit_surrogate.py compares it with the real binary's) */
+void orc_cit_plant_step_batch(const rl4_cit_params* P, double* x, const double* u, double dt, int integrator, int64_t n)
+{
+    for (int64_t i = 0; i < n; ++i) orc_cit_plant_step(P, x + 12 * i, u + 11 * i, dt, integrator);
+}
+void orc_cit_finalize(rl4_cit_params* P) { rl4_cit_finalize(P); }
+void orc_cit_solve_trim(rl4_cit_params* P) { rl4_cit_solve_trim(P); }
 
 #define TE double
 

@@ -93,7 +93,7 @@ int orc_nl_run(int policy, int tanh_mode, const orc_nl_cfg* cfgs, int cfg_stride
 void orc_nl_rls_update(double gamma, double* theta, double* cov, const double* dx0, const double* da0, const double* dx1,
                        double* eps, double* eps_norm, int64_t n);
 void orc_nl_env_step(const orc_nl_cfg* c, double theta_ref_k, const double* act, double* x_full, double* x_act, int32_t stepp,
-                     double* surf, double* u, double* e, double* reward);
+                     double* surf, double* u, double* e, double* reward, double* x_obs);
 void orc_cit_plant_step(const rl4_cit_params* P, double* x, const double* u, double dt, int integrator);
 int orc_cit_plant_step_lon(const rl4_cit_params* P, double* x, const double* u, double dt, int integrator);
 void orc_cit_sincos(const double* a, double* s, double* c, int64_t n);

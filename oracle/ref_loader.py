@@ -121,12 +121,14 @@ def load_reference_utils():
     return mod
 
 
-def load_reference_nonlinear_env(integrator: str = "ode5"):
+def load_reference_nonlinear_env(integrator: str = "ode5", plant: str = "surrogate"):
     """Return (verbatim ``Ce500NonLinear`` class, plant stand-in module).  envs/nonlinear/env.py:5-9 imports
     ``extended_input.citation`` -- a SWIG wrapper of a Windows DLL -- so a stand-in module with the same three functions
     (envs/nonlinear/citation.py:62-69: ``initialize()``, ``step(cmd) -> state[12]``, ``terminate()``; process-global
-    state like the original) is registered first; it integrates the surrogate plant of
-    include/rl4_citation_surrogate.h with the C oracle."""
+    state like the original) is registered first.  ``plant="surrogate"`` integrates the surrogate of
+    include/rl4_citation_surrogate.h with the C oracle, with the binary's output-then-update timing (``step`` returns
+    the state BEFORE the step); ``plant="binary"`` runs the reference's REAL plant binary in-process
+    (oracle/pe_probe/pe_citation.py) -- the aircraft the reference actually flies."""
     if not reference_available():
         raise FileNotFoundError(f"reference tree not found at {REFERENCE_ROOT}")
     _install_stubs()
@@ -139,6 +141,7 @@ def load_reference_nonlinear_env(integrator: str = "ode5"):
 
     L = nl_c.lib()
     L.orc_cit_plant_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, ctypes.c_int]
+    plant_name = plant
     plant = np.ascontiguousarray(nl_c.make_cfg()["plant"][:1])
     stub = types.ModuleType("extended_input.citation")
     stub._x = None
@@ -151,13 +154,19 @@ def load_reference_nonlinear_env(integrator: str = "ode5"):
     def step(cmd):
         u = np.ascontiguousarray(cmd, dtype=np.float64)
         assert u.shape == (11,)
+        out = stub._x.copy()                      # output-then-update, like the binary (oracle/pe_probe/README.md)
         L.orc_cit_plant_step(plant.ctypes.data, stub._x.ctypes.data, u.ctypes.data, stub.dt, stub._integrator)
-        return stub._x.copy()
+        return out
 
     def terminate():
         stub._x = None
 
     stub.initialize, stub.step, stub.terminate = initialize, step, terminate
+    if plant_name == "binary":
+        from .pe_probe import pe_citation
+
+        pe_citation.open_variant("extended_input")
+        stub.initialize, stub.step, stub.terminate = pe_citation.initialize, pe_citation.step, pe_citation.terminate
     pkg = types.ModuleType("extended_input")
     pkg.citation = stub
     pkg.__path__ = []

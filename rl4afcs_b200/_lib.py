@@ -77,7 +77,7 @@ INTEGRATOR = {"rk4": 0, "ode5": 1}
 CIT_FIELDS = ["m", "S", "c", "b", "Ixx", "Iyy", "Izz", "Ixz", "g", "CL0", "CLa", "CLq", "CLde", "CLflap", "al_stall",
               "CD0", "CDk", "CDgear", "CDflap", "CDstall", "Cm0", "Cma", "Cmq", "Cmde", "Cmflap", "Cmstall",
               "CYb", "CYp", "CYr", "CYda", "CYdr", "Clb", "Clp", "Clr", "Clda", "Cldr",
-              "Cnb", "Cnp", "Cnr", "Cnda", "Cndr", "Tstatic",
+              "Cnb", "Cnp", "Cnr", "Cnda", "Cndr", "Tstatic", "TV", "Vref", "xcg_gain",
               "inv_m", "inv_Iyy", "inv_gam", "inv_al_stall", "inv_c", "inv_b"]
 
 
@@ -124,7 +124,7 @@ class NlHostIO(ctypes.Structure):
                 ("out_mask", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
-ABI_VERSION = 2          # RL4_ABI_VERSION of include/rl4afcs_b200.h these struct layouts were written against
+ABI_VERSION = 3          # RL4_ABI_VERSION of include/rl4afcs_b200.h these struct layouts were written against
 OUT = dict(STATS=1, WEIGHTS=2, RLS=4, STATE=8, TRACES=16, TARGET=32, ALL=63)
 SPS = dict(SUM_C=0, CONV_TIME=1, DIVERGED=2, UNSTEADY=3, MEAN_ABS_E=4, NMAE=5, COUNT=6)
 NLS = dict(RSE_WARMUP=0, RSE_FLIGHT=1, RSE_LAT=2, NZ_PEAK=3, DIVERGED=4, COUNT=5)
@@ -139,6 +139,7 @@ EXPORTS = [
     "rl4_nl_init", "rl4_nl_run", "rl4_nl_env_step", "rl4_nl_default_params", "rl4_nl_critic_forward", "rl4_nl_actor_forward",
     "rl4_sizeof_sp_params", "rl4_sizeof_nl_params", "rl4_soft_update", "rl4_actor_weight_update", "rl4_sp_agent_stats",
     "rl4_nl_agent_stats", "rl4_stats_reduce_work_doubles", "rl4_stats_reduce", "rl4_nl_noise_fill", "rl4_nl_episode_host", "rl4_test_rcp_f32",
+    "rl4_nl_trim_state",
 ]
 _NOT_STATUS = ("rl4_last_error", "rl4_launch_count", "rl4_abi_version", "rl4_sizeof_sp_params", "rl4_sizeof_nl_params",
                "rl4_stats_reduce_work_doubles")
@@ -190,8 +191,9 @@ def load() -> ctypes.CDLL:
     L.rl4_test_math.argtypes = [ctypes.c_int, vp, vp, vp, i64, vp]
     L.rl4_nl_init.argtypes = [ctypes.c_int, ctypes.POINTER(NlParams), vp, vp, vp, vp, i64, NlState, i64, vp]
     L.rl4_nl_run.argtypes = [ctypes.c_int, ctypes.POINTER(NlParams), vp, vp, i64, i32, i32, NlState, i64, SpLog, vp]
-    L.rl4_nl_env_step.argtypes = [ctypes.POINTER(NlParams), vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]
+    L.rl4_nl_env_step.argtypes = [ctypes.POINTER(NlParams), vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]
     L.rl4_nl_default_params.argtypes = [ctypes.POINTER(NlParams)]
+    L.rl4_nl_trim_state.argtypes = [ctypes.POINTER(NlParams), vp, vp]
     L.rl4_nl_rls_update.argtypes = [ctypes.POINTER(NlParams), vp, vp, vp, vp, vp, vp, vp, i64, i64, vp]
     L.rl4_nl_critic_forward.argtypes = [ctypes.c_int, vp, vp, vp, vp, i64, i64, vp]
     L.rl4_nl_actor_forward.argtypes = [ctypes.c_int, vp, vp, vp, vp, vp, vp, dbl, i32, i32, i64, i64, vp]

@@ -196,7 +196,8 @@ __device__ __forceinline__ void nl_rls_update(TH& th, CV& cv, const double (&Xr)
 template <bool PER_AGENT, int INTEG>
 __device__ __forceinline__ void nl_env_step(const rl4_nl_params& p, const NlHp<PER_AGENT>& hv, int stepp, double theta_ref_k,
                                             const double (&act)[3], double (&x)[12], double (&x_act)[3], double (&surf)[3],
-                                            double& e_phi, double& e_th, double& e_psi, double& reward, double& rg2, double (&ueff)[3])
+                                            double& e_phi, double& e_th, double& e_psi, double& reward, double& rg2, double (&ueff)[3],
+                                            double (&xo)[12])
 {
     const int fault_step = hv.hpi(RL4_NHPI_FAULT_STEP);
     const bool faulted = (fault_step >= 0 && stepp >= fault_step);                 // env.py:132,151
@@ -235,12 +236,17 @@ __device__ __forceinline__ void nl_env_step(const rl4_nl_params& p, const NlHp<P
 #pragma unroll
     for (int i = 0; i < 11; ++i) u[i] = p.trim_input[i] + eff[i];                  // env.py:207-208
     ueff[0] = u[0]; ueff[1] = u[1]; ueff[2] = u[2];
-    // env.py:210.  Symmetric flight (elevator-only commands from a trimmed start: always, in IDHPnonlin's task) takes the
+    // env.py:210  x_full = model.step(input).  The reference's plant is an output-then-update block: step() returns the state
+    // BEFORE the step and then integrates (found by running the binary in-process: DESIGN.md section 9), so the wrapper observes the
+    // aircraft one sample late: xo is what model.step returned, x the carried state.
+    // Symmetric flight (elevator-only commands from a trimmed start: always, in IDHPnonlin's task) takes the
     // longitudinal form of the same equations -- identical values, ~40 % less work and half the stage storage; INTEG is
     // a compile-time constant, so one integrator's code per kernel
+#pragma unroll
+    for (int j = 0; j < 12; ++j) xo[j] = x[j];
     rl4_cit_step_auto(&p.plant, x, u, p.dt, INTEG);
     const double Q = hv.hp(RL4_NHP_Q_SYM);
-    e_phi = x[6] - 0.0; e_th = x[7] - theta_ref_k; e_psi = x[8] - 0.0;            // env.py:215 (state - ref)
+    e_phi = xo[6] - 0.0; e_th = xo[7] - theta_ref_k; e_psi = xo[8] - 0.0;         // env.py:215 (state - ref)
     reward = (-0.5 * Q) * (e_th * e_th);                                           // env.py:218
     rg2 = (-Q) * e_th;                                                             // env.py:219-220 (q slot)
 }
@@ -362,12 +368,13 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
         const double act[3] = {(double)a_k, 0.0, 0.0};
         double surf[3], ueff[3], e_phi, e_th, e_psi, reward, rg2;
         const double yref_k = __ldg(theta_ref + k);
-        nl_env_step<PER_AGENT, INTEG>(p, hv, stepp, yref_k, act, x, x_act, surf, e_phi, e_th, e_psi, reward, rg2, ueff);
+        double xo[12];                                                             // what model.step returned (the state before this step)
+        nl_env_step<PER_AGENT, INTEG>(p, hv, stepp, yref_k, act, x, x_act, surf, e_phi, e_th, e_psi, reward, rg2, ueff, xo);
         stepp += 1;
-        const double x_next_lon[3] = {x[4], x[7], x[1]};                           // env.py:231
+        const double x_next_lon[3] = {xo[4], xo[7], xo[1]};                           // env.py:231
         bool nans = false;
 #pragma unroll
-        for (int j = 0; j < 12; ++j) nans |= (x[j] != x[j]);
+        for (int j = 0; j < 12; ++j) nans |= (xo[j] != xo[j]);
         const double rse_k0 = sqrt_of_square(e_th), rse_k1 = nsqrt(e_phi * e_phi + e_psi * e_psi);   // env.py:251
         rse0 += rse_k0;                                                            // objects.py:1503-1504
         rse1 += rse_k1;
@@ -375,8 +382,8 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
         // full-log row of this step (level 2): the two loss gradients are written where they are formed
         double* const fb = (LOG && logged && lg.level == 2 && (k - k0) % lg.every == 0)
                                ? lg.buf + ((int64_t)((k - k0) / lg.every) * RL4_NLF_COUNT) * lg.n_agents_logged + i : nullptr;
-        { const double nz = fabs(x[3] * x[1] / 9.80665); if (nz > nz_peak) nz_peak = nz; }   // functions.py:774,1055
-        TN s_next[4] = {(TN)x[4], (TN)x[7], (TN)x[1], (TN)e_th};                   // env.py:236-238; objects.py:1499
+        { const double nz = fabs(xo[3] * xo[1] / 9.80665); if (nz > nz_peak) nz_peak = nz; }   // functions.py:774,1055
+        TN s_next[4] = {(TN)xo[4], (TN)xo[7], (TN)xo[1], (TN)e_th};                   // env.py:236-238; objects.py:1499
 
         // ---- _step_networks (objects.py:1292-1348)
         TN hc[10], ht[10], lam[3], lt[3];
@@ -577,8 +584,8 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
                 if (nans) {                                                        // objects.py:1168-1175: this row and all later ones
                     for (int f = 0; f < nf; ++f) b[(int64_t)f * L] = __longlong_as_double(0x7ff8000000000000LL);
                 } else if (lg.level >= 3) {                                        // functions.py:1040-1052
-                    b[(int64_t)RL4_NLM_E * L] = e_th; b[(int64_t)RL4_NLM_THETA * L] = x[7]; b[(int64_t)RL4_NLM_ALPHA * L] = x[4];
-                    b[(int64_t)RL4_NLM_Q * L] = x[1]; b[(int64_t)RL4_NLM_V * L] = x[3]; b[(int64_t)RL4_NLM_H * L] = x[9];
+                    b[(int64_t)RL4_NLM_E * L] = e_th; b[(int64_t)RL4_NLM_THETA * L] = xo[7]; b[(int64_t)RL4_NLM_ALPHA * L] = xo[4];
+                    b[(int64_t)RL4_NLM_Q * L] = xo[1]; b[(int64_t)RL4_NLM_V * L] = xo[3]; b[(int64_t)RL4_NLM_H * L] = xo[9];
                     b[(int64_t)RL4_NLM_A_CMD * L] = surf[0]; b[(int64_t)RL4_NLM_A_EFF * L] = ueff[0];
                     double na = 0.0, nc = 0.0;
                     for (int j = 0; j < 40; ++j) { na = __fma_rn((double)W1a[j], (double)W1a[j], na); nc = __fma_rn((double)W1c[j], (double)W1c[j], nc); }
@@ -586,11 +593,11 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
                     b[(int64_t)RL4_NLM_RLS_EPS * L] = eps_norm;
                 } else if (lg.level == 2) {
                     b[(int64_t)RL4_NLF_ETA_A * L] = eta_a;
-                    for (int j = 0; j < 12; ++j) b[(int64_t)(RL4_NLF_XFULL + j) * L] = x[j];
+                    for (int j = 0; j < 12; ++j) b[(int64_t)(RL4_NLF_XFULL + j) * L] = xo[j];
                     b[(int64_t)RL4_NLF_RSE * L] = rse_k0; b[(int64_t)(RL4_NLF_RSE + 1) * L] = rse_k1;
                     for (int j = 0; j < 3; ++j) b[(int64_t)(RL4_NLF_X + j) * L] = x_next_lon[j];
                     b[(int64_t)RL4_NLF_A_CMD * L] = surf[0]; b[(int64_t)RL4_NLF_A_EFF * L] = ueff[0];
-                    b[(int64_t)RL4_NLF_S * L] = x[4]; b[(int64_t)RL4_NLF_YREF * L] = yref_k; b[(int64_t)RL4_NLF_E * L] = e_th;
+                    b[(int64_t)RL4_NLF_S * L] = xo[4]; b[(int64_t)RL4_NLF_YREF * L] = yref_k; b[(int64_t)RL4_NLF_E * L] = e_th;
                     for (int j = 0; j < 40; ++j) { b[(int64_t)(RL4_NLF_A_W1 + j) * L] = (double)W1a[j]; b[(int64_t)(RL4_NLF_C_W1 + j) * L] = (double)W1c[j]; }
                     for (int j = 0; j < 10; ++j) b[(int64_t)(RL4_NLF_A_W2 + j) * L] = (double)W2a[j];
                     for (int j = 0; j < 30; ++j) b[(int64_t)(RL4_NLF_C_W2 + j) * L] = (double)W2c[j];
@@ -601,7 +608,7 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
                     b[(int64_t)RL4_NLF_RLS_EPS_NORM * L] = eps_norm;
                     b[(int64_t)RL4_NLF_A * L] = (double)a_next; b[(int64_t)RL4_NLF_REWARD * L] = reward;
                 } else {
-                    for (int j = 0; j < 12; ++j) b[(int64_t)(RL4_NLL_XFULL + j) * L] = x[j];
+                    for (int j = 0; j < 12; ++j) b[(int64_t)(RL4_NLL_XFULL + j) * L] = xo[j];
                     b[(int64_t)RL4_NLL_A * L] = (double)a_next; b[(int64_t)RL4_NLL_E_THETA * L] = e_th; b[(int64_t)RL4_NLL_REWARD * L] = reward;
                     for (int j = 0; j < 3; ++j) b[(int64_t)(RL4_NLL_SURF + j) * L] = surf[j];
                 }
@@ -647,12 +654,15 @@ namespace rl4 {
 // Ce500NonLinear.reset (envs/nonlinear/env.py:278-291): the model's built-in initial state, then 1000 + 1 steps at trim
 // input.  Every agent shares the plant and the trim input, and the plant is IEEE-basic-operations only, so the 1001 steps
 // are integrated ONCE on the host (same header, same bits as on the device) and broadcast by the init kernel.
-struct NlTrim { double x[12]; };
+// The plant is an output-then-update block (model.step returns the state before the step): the 1001 calls of reset leave
+// the carried state at 1001 integrations (x) and return the state after 1000 of them (x_obs = env.state after reset).
+struct NlTrim { double x[12]; double x_obs[12]; };
 static NlTrim nl_trim_on_host(const rl4_nl_params* p)
 {
-    NlTrim t = {{0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0}};
+    NlTrim t = {{0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0}, {0}};
     const int n_trim = (int)(10.0 / p->dt) + 1;
     for (int k = 0; k < n_trim; ++k) {
+        memcpy(t.x_obs, t.x, sizeof t.x_obs);
         if (p->integrator == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(&p->plant, t.x, p->trim_input, p->dt);
         else rl4_cit_step_ode5(&p->plant, t.x, p->trim_input, p->dt);
     }
@@ -699,21 +709,22 @@ __global__ void __launch_bounds__(128)
 nl_env_step_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict__ theta_ref, int stepp, double* __restrict__ x_full,
                    double* __restrict__ x_act_p, const double* __restrict__ action, double* __restrict__ out_mdp,
                    double* __restrict__ out_reward, double* __restrict__ out_e, double* __restrict__ out_surf,
-                   double* __restrict__ out_eff, int64_t S, int64_t n_agents)
+                   double* __restrict__ out_eff, double* __restrict__ out_x_obs, int64_t S, int64_t n_agents)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_agents) return;
     const NlHp<true> hv{p, i};
-    double x[12], xa[3], act[3], surf[3], ueff[3], e_phi, e_th, e_psi, reward, rg2;
+    double x[12], xo[12], xa[3], act[3], surf[3], ueff[3], e_phi, e_th, e_psi, reward, rg2;
     for (int j = 0; j < 12; ++j) x[j] = x_full[j * S + i];
     for (int j = 0; j < 3; ++j) { xa[j] = x_act_p[j * S + i]; act[j] = action[j * S + i]; }
     if (p.integrator == RL4_CIT_INTEGRATOR_RK4)
-        nl_env_step<true, RL4_CIT_INTEGRATOR_RK4>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2, ueff);
+        nl_env_step<true, RL4_CIT_INTEGRATOR_RK4>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2, ueff, xo);
     else
-        nl_env_step<true, RL4_CIT_INTEGRATOR_ODE5>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2, ueff);
+        nl_env_step<true, RL4_CIT_INTEGRATOR_ODE5>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2, ueff, xo);
     for (int j = 0; j < 12; ++j) x_full[j * S + i] = x[j];
     for (int j = 0; j < 3; ++j) x_act_p[j * S + i] = xa[j];
-    out_mdp[i] = x[4]; out_mdp[S + i] = x[7]; out_mdp[2 * S + i] = x[1]; out_mdp[3 * S + i] = e_th;
+    if (out_x_obs) for (int j = 0; j < 12; ++j) out_x_obs[j * S + i] = xo[j];     // info['x_full'] = what model.step returned
+    out_mdp[i] = xo[4]; out_mdp[S + i] = xo[7]; out_mdp[2 * S + i] = xo[1]; out_mdp[3 * S + i] = e_th;
     out_reward[i] = reward; out_e[i] = e_th;
     if (out_surf) for (int j = 0; j < 3; ++j) out_surf[j * S + i] = surf[j];          // action_commanded (env.py:244)
     if (out_eff) for (int j = 0; j < 3; ++j) out_eff[j * S + i] = ueff[j];            // action_effective = model_input[:3] (:245)
@@ -872,6 +883,15 @@ int rl4_nl_default_params(rl4_nl_params* p)
     return 0;
 }
 
+int rl4_nl_trim_state(const rl4_nl_params* p, double* out_state, double* out_observed)
+{
+    RL4_REQUIRE(p != nullptr, "p is NULL");
+    const NlTrim t = nl_trim_on_host(p);
+    if (out_state) memcpy(out_state, t.x, sizeof t.x);
+    if (out_observed) memcpy(out_observed, t.x_obs, sizeof t.x_obs);
+    return 0;
+}
+
 int rl4_nl_init(int policy, const rl4_nl_params* p, const double* w1a, const double* w2a, const double* w1c, const double* w2c,
                 int64_t stride_in, rl4_nl_state st, int64_t n, void* stream)
 {
@@ -949,13 +969,13 @@ int rl4_nl_actor_forward(int policy, const void* s, void* w1, void* w2, double* 
 
 int rl4_nl_env_step(const rl4_nl_params* p, const double* theta_ref, int32_t stepp, double* x_full, double* x_act,
                     const double* action, double* out_mdp, double* out_reward, double* out_e_theta, double* out_surf,
-                    double* out_eff, int64_t stride, int64_t n, void* stream)
+                    double* out_eff, double* out_x_obs, int64_t stride, int64_t n, void* stream)
 {
     RL4_REQUIRE(p && theta_ref && x_full && x_act && action && out_mdp && out_reward && out_e_theta, "NULL argument");
     RL4_REQUIRE(n >= 0 && stride >= n && stepp >= 0, "bad size");
     if (n == 0) return 0;
     nl_env_step_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(*p, theta_ref, stepp, x_full, x_act, action,
-                                                                                        out_mdp, out_reward, out_e_theta, out_surf, out_eff, stride, n);
+                                                                                        out_mdp, out_reward, out_e_theta, out_surf, out_eff, out_x_obs, stride, n);
     return check_launch("nl_env_step_kernel");
 }
 

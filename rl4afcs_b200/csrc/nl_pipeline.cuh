@@ -221,7 +221,7 @@ nl_pipe_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict
             if (k < k_end && div < 0) {
                 if (k > k0) { a_old = a_cur; a_cur = mb_a[((k - 1) & 1) * kPipeAgents + la]; }      // a_k = actor forward of step k-1
                 const double act[3] = {(double)a_cur, 0.0, 0.0};
-                double surf[3], ueff[3], e_phi, e_th, e_psi, reward, rg2;
+                double surf[3], ueff[3], xo[12], e_phi, e_th, e_psi, reward, rg2;
                 const double yref_k = __ldg(theta_ref + k);
                 {   // nl_env_step with the rare full-model plant path out of line
                     const int fault_step = hv.hpi(RL4_NHPI_FAULT_STEP);
@@ -261,26 +261,30 @@ nl_pipe_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict
 #pragma unroll
                     for (int j = 0; j < 11; ++j) u[j] = p.trim_input[j] + eff[j];                  // env.py:207-208
                     ueff[0] = u[0]; ueff[1] = u[1]; ueff[2] = u[2];
-                    pipe_plant_step<INTEG>(p.plant, x, u, p.dt);                                   // env.py:210
+                    // env.py:210  x_full = model.step(input): the plant returns the state BEFORE the step (xo) and then
+                    // integrates the carried state (x) -- output-then-update, as the reference's binary does
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) xo[j] = x[j];
+                    pipe_plant_step<INTEG>(p.plant, x, u, p.dt);
                     const double Q = hv.hp(RL4_NHP_Q_SYM);
-                    e_phi = x[6] - 0.0; e_th = x[7] - yref_k; e_psi = x[8] - 0.0;                  // env.py:215 (state - ref)
+                    e_phi = xo[6] - 0.0; e_th = xo[7] - yref_k; e_psi = xo[8] - 0.0;               // env.py:215 (state - ref)
                     reward = (-0.5 * Q) * (e_th * e_th);                                           // env.py:218
                     rg2 = (-Q) * e_th;                                                             // env.py:219-220 (q slot)
                     (void)reward; (void)ueff;
                 }
                 stepp += 1;
-                xn_prev[0] = x[4]; xn_prev[1] = x[7]; xn_prev[2] = x[1];                           // env.py:231
+                xn_prev[0] = xo[4]; xn_prev[1] = xo[7]; xn_prev[2] = xo[1];                        // env.py:231
                 bool nans = false;
 #pragma unroll
-                for (int j = 0; j < 12; ++j) nans |= (x[j] != x[j]);
+                for (int j = 0; j < 12; ++j) nans |= (xo[j] != xo[j]);
                 const double rse_k0 = sqrt_of_square(e_th), rse_k1 = nsqrt(e_phi * e_phi + e_psi * e_psi);   // env.py:251
                 rse0 += rse_k0;                                                                    // objects.py:1503-1504
                 rse1 += rse_k1;
                 if (k >= flight_step) { rse_f0 += rse_k0; rse_f1 += rse_k1; }                      // functions.py:917,1039
-                { const double nz = fabs(x[3] * x[1] / 9.80665); if (nz > nz_peak) nz_peak = nz; } // functions.py:774,1055
+                { const double nz = fabs(xo[3] * xo[1] / 9.80665); if (nz > nz_peak) nz_peak = nz; } // functions.py:774,1055
                 // ---- mailbox for role N's work on step k (read in the next iteration)
                 TN* mb = mb_pn + (size_t)(k & 1) * 16 * kPipeAgents + la;
-                mb[0 * kPipeAgents] = (TN)x[4]; mb[1 * kPipeAgents] = (TN)x[7]; mb[2 * kPipeAgents] = (TN)x[1]; mb[3 * kPipeAgents] = (TN)e_th;   // env.py:236-238
+                mb[0 * kPipeAgents] = (TN)xo[4]; mb[1 * kPipeAgents] = (TN)xo[7]; mb[2 * kPipeAgents] = (TN)xo[1]; mb[3 * kPipeAgents] = (TN)e_th;   // env.py:236-238
 #pragma unroll
                 for (int j = 0; j < 12; ++j) mb[(4 + j) * kPipeAgents] = (TN)th[j];                // F, G BEFORE this step's RLS update (objects.py:1327; Q18)
                 mb_rg2[(k & 1) * kPipeAgents + la] = rg2;

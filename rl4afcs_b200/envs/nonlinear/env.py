@@ -91,7 +91,14 @@ class Ce500NonLinear:
 
     @property
     def state(self) -> torch.Tensor:
-        """(B, 12) plant state p q r V alpha beta phi theta psi h xe ye."""
+        """(B, 12) p q r V alpha beta phi theta psi h xe ye as ``model.step`` last RETURNED it (envs/nonlinear/env.py:210,291).
+        The reference's plant returns the state before the step it then takes, so this is one sample behind the state
+        the plant carries (``plant_state``)."""
+        return self._obs
+
+    @property
+    def plant_state(self) -> torch.Tensor:
+        """(B, 12) the state the plant carries into its next step."""
         return self._engine.env_field("XFULL", 12).t()
 
     # ---- gymnasium-style API ----
@@ -102,6 +109,9 @@ class Ce500NonLinear:
         self.initialized = True
         self.stepp = 0
         self.t = 0
+        obs = (ctypes.c_double * 12)()
+        _lib.check(eng.lib.rl4_nl_trim_state(ctypes.byref(eng.params), None, obs), "rl4_nl_trim_state")
+        self._obs = torch.tensor(list(obs), dtype=torch.float64, device=self.device).repeat(self.batch, 1)   # env.py:291
         MDP_state = torch.zeros((self.batch, self.mdp_s_dim), dtype=torch.float64, device=self.device)
         info = {"nans": False, "s": MDP_state, "yref": np.zeros(3), "action": np.zeros(3), "rates": np.zeros(3), "t": self.t,
                 "x_full": self.state, "x": [torch.zeros((self.batch, 3, 1), dtype=torch.float64, device=self.device),
@@ -125,12 +135,14 @@ class Ce500NonLinear:
         e_th = torch.empty_like(reward_lon)
         surf = torch.empty((3, B), dtype=torch.float64, device=dev)
         eff = torch.empty((3, B), dtype=torch.float64, device=dev)
+        xobs = torch.empty((12, B), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
             rc = eng.lib.rl4_nl_env_step(ctypes.byref(eng.params), eng.theta_ref.data_ptr(), self.stepp,
                                          eng.env_field("XFULL", 12).data_ptr(), eng.env_field("XACT", 3).data_ptr(),
                                          act_p.data_ptr(), mdp.data_ptr(), reward_lon.data_ptr(), e_th.data_ptr(),
-                                         surf.data_ptr(), eff.data_ptr(), eng.stride, B, eng._stream())
+                                         surf.data_ptr(), eff.data_ptr(), xobs.data_ptr(), eng.stride, B, eng._stream())
             _lib.check(rc, "rl4_nl_env_step")
+        self._obs = xobs.t()                                                            # self.state = model.step(input) (env.py:210)
         ref = [r[self.stepp] for r in self.state_reference]
         self.stepp += 1
         self.t += self.dt
