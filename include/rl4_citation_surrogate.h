@@ -3,8 +3,10 @@
  * The reference's plant is `_citation.cp39-win_amd64.pyd` (envs/nonlinear/extended_input/, called at
  * envs/nonlinear/env.py:210,289-291 through envs/nonlinear/citation.py:62-69): a Simulink-Coder build
  * of the DASMAT Cessna Citation 500 model, Windows x64, CPython-3.9 ABI, NO source, fixed-step solver
- * string "ode5".  It cannot be loaded, disassembled into tables, or re-derived here, so NUMERICAL PARITY
- * WITH THE REFERENCE PLANT IS UNPINNED.  What IS reproduced is its contract:
+ * string "ode5".  It cannot be IMPORTED here, but its model code runs in-process (oracle/pe_probe/): that
+ * run is the truth this surrogate is calibrated against (tests/golden/citation_*.npz, profiles/citation_fidelity_r02.json).
+ * The surrogate is NOT a restatement of the DASMAT model: parity with the reference plant is tolerance-level on the
+ * identified envelope, not bit-level.  What IS reproduced exactly is its contract:
  *
  *   step(u[11]) -> x[12], one fixed step of dt seconds, process-global state in the reference /
  *   per-agent state here;
