@@ -1,0 +1,691 @@
+"""TEST / BUILD INFRASTRUCTURE -- static translation of the reference's plant binary into portable C.
+
+The reference's nonlinear aircraft (`envs/nonlinear/<variant>/_citation.cp39-win_amd64.pyd`, called at
+/root/reference/envs/nonlinear/env.py:210,288-291 through envs/nonlinear/citation.py:62-69) exists only as x86-64 machine
+code.  `pe_citation.c` runs it in-process on an x86 host; this script goes one step further and TRANSLATES the model
+code (Simulink entry points initialize 0x96f0, step 0x3720, terminate 0xe620 and everything they reach) instruction by
+instruction into C: every x86 function becomes a C function over an explicit machine state (16 integer registers, 16 SSE
+registers, 5 flags) and a flat byte image of the DLL's sections + heap + stack.  Nothing of the model is interpreted or
+approximated -- each instruction is replaced by its architectural semantics -- so the translation computes what the binary
+computes, and it compiles for any target: gcc (oracle/_ref/libcitation_lifted.so, checked bit for bit against the binary
+itself by tests/test_citation_lifted.py) and nvcc (the `dasmat` plant of the CUDA kernels).
+
+Nothing derived from the binary is committed: the generated sources and the image land in a git-ignored directory and are
+produced at build time where /root/reference exists (the build container); the GPU box receives the compiled libraries.
+
+Usage: python oracle/pe_probe/lift.py [--variant extended_input] [--out DIR]
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import re
+import struct
+import subprocess
+import sys
+
+BASE = 0x180000000
+REF_DIR = "/root/reference/envs/nonlinear"
+ENTRY = {"initialize": 0x96f0, "step": 0x3720, "terminate": 0xe620}
+MODEL_END = 0xe840      # RVA below which .text is Simulink-generated model code (above: rt helpers, SWIG wrappers, CRT)
+
+R64 = ["rax", "rcx", "rdx", "rbx", "rsp", "rbp", "rsi", "rdi", "r8", "r9", "r10", "r11", "r12", "r13", "r14", "r15"]
+R32 = ["eax", "ecx", "edx", "ebx", "esp", "ebp", "esi", "edi"] + [f"r{i}d" for i in range(8, 16)]
+R16 = ["ax", "cx", "dx", "bx", "sp", "bp", "si", "di"] + [f"r{i}w" for i in range(8, 16)]
+R8 = ["al", "cl", "dl", "bl", "spl", "bpl", "sil", "dil"] + [f"r{i}b" for i in range(8, 16)]
+R8H = {"ah": 0, "ch": 1, "dh": 2, "bh": 3}
+REG = {}
+for i in range(16):
+    REG[R64[i]] = (i, 64)
+    REG[R32[i]] = (i, 32)
+    REG[R16[i]] = (i, 16)
+    REG[R8[i]] = (i, 8)
+SIZES = {"BYTE": 8, "WORD": 16, "DWORD": 32, "QWORD": 64, "XMMWORD": 128}
+CC = {"e": "ZF", "z": "ZF", "ne": "!ZF", "nz": "!ZF", "a": "(!CF&&!ZF)", "nbe": "(!CF&&!ZF)", "ae": "!CF", "nb": "!CF", "nc": "!CF",
+      "b": "CF", "c": "CF", "nae": "CF", "be": "(CF||ZF)", "na": "(CF||ZF)", "l": "(SF!=OF)", "nge": "(SF!=OF)", "ge": "(SF==OF)",
+      "nl": "(SF==OF)", "le": "(ZF||SF!=OF)", "ng": "(ZF||SF!=OF)", "g": "(!ZF&&SF==OF)", "nle": "(!ZF&&SF==OF)", "s": "SF", "ns": "!SF",
+      "p": "PF", "pe": "PF", "np": "!PF", "po": "!PF", "o": "OF", "no": "!OF"}
+# C-runtime imports the model code may reach, with their argument shape
+IMPORTS = {"cos": "d_d", "sin": "d_d", "tan": "d_d", "exp": "d_d", "floor": "d_d", "log10": "d_d", "sqrt": "d_d", "pow": "d_dd",
+           "memcpy": "mem", "memset": "mem", "malloc": "mem", "free": "mem"}
+
+
+class Ins:
+    __slots__ = ("addr", "size", "mn", "ops", "raw")
+
+    def __init__(self, addr, size, mn, ops, raw):
+        self.addr, self.size, self.mn, self.ops, self.raw = addr, size, mn, ops, raw
+
+
+def disassemble(path):
+    txt = subprocess.run(["objdump", "-d", "-M", "intel", "--no-show-raw-insn", path], check=True, capture_output=True, text=True).stdout
+    raw = subprocess.run(["objdump", "-d", "-M", "intel", path], check=True, capture_output=True, text=True).stdout
+    # sizes from the raw listing (continuation lines carry only bytes)
+    size = {}
+    last = None
+    for line in raw.splitlines():
+        m = re.match(r"\s*([0-9a-f]+):\t([0-9a-f ]+?)\s*(\t.*)?$", line)
+        if not m:
+            continue
+        a = int(m.group(1), 16)
+        nb = len(m.group(2).split())
+        if m.group(3) is not None and m.group(3).strip():
+            size[a] = nb
+            last = a
+        elif last is not None:
+            size[last] += nb
+    ins = {}
+    for line in txt.splitlines():
+        m = re.match(r"\s*([0-9a-f]+):\t(.*)$", line)
+        if not m:
+            continue
+        a = int(m.group(1), 16)
+        body = m.group(2).strip()
+        if not body or a not in size:
+            continue
+        body = re.sub(r"\s+#.*$", "", body)          # objdump's resolved-address comment (recomputed below)
+        body = re.sub(r"<[^>]*>", "", body).strip()
+        parts = body.split(None, 1)
+        mn = parts[0]
+        while mn in ("rex", "rex.W", "rex.WB", "rex.R", "rex.X", "rex.B", "rex.WR", "rex.WX", "rex.RB", "rex.XB", "rex.RX",
+                     "data16", "lock", "bnd", "notrack", "cs", "ds", "es", "ss") and len(parts) > 1:
+            parts = parts[1].split(None, 1)
+            mn = parts[0]
+        if mn == "rep" or mn == "repz" or mn == "repnz":
+            mn = mn + " " + (parts[1] if len(parts) > 1 else "")
+            ops = []
+        else:
+            ops = split_ops(parts[1]) if len(parts) > 1 else []
+        ins[a] = Ins(a, size[a], mn, ops, body)
+    return ins
+
+
+def split_ops(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch == "[":
+            depth += 1
+        elif ch == "]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+class PE:
+    def __init__(self, path):
+        b = open(path, "rb").read()
+        self.file = b
+        nt = struct.unpack_from("<I", b, 0x3c)[0]
+        assert b[nt:nt + 4] == b"PE\0\0"
+        nsec = struct.unpack_from("<H", b, nt + 6)[0]
+        optsz = struct.unpack_from("<H", b, nt + 20)[0]
+        opt = nt + 24
+        assert struct.unpack_from("<H", b, opt)[0] == 0x20b
+        assert struct.unpack_from("<Q", b, opt + 24)[0] == BASE
+        self.image_size = struct.unpack_from("<I", b, opt + 56)[0]
+        hdr = struct.unpack_from("<I", b, opt + 60)[0]
+        dirs = opt + 112
+        img = bytearray(self.image_size)
+        img[:hdr] = b[:hdr]
+        self.sections = []
+        sec = opt + optsz
+        for i in range(nsec):
+            name = b[sec:sec + 8].rstrip(b"\0").decode()
+            vsz, va, rsz, ro = struct.unpack_from("<IIII", b, sec + 8)
+            n = min(rsz, vsz)
+            img[va:va + n] = b[ro:ro + n]
+            self.sections.append((name, va, vsz))
+            sec += 40
+        self.img = img
+        # imports: IAT slot VA -> name
+        self.iat = {}
+        irva = struct.unpack_from("<I", b, dirs + 8)[0]
+        d = irva
+        while struct.unpack_from("<I", img, d + 12)[0]:
+            oft = struct.unpack_from("<I", img, d)[0] or struct.unpack_from("<I", img, d + 16)[0]
+            ft = struct.unpack_from("<I", img, d + 16)[0]
+            k = 0
+            while True:
+                ent = struct.unpack_from("<Q", img, oft + k)[0]
+                if not ent:
+                    break
+                name = "?ordinal"
+                if not ent >> 63:
+                    p = (ent & 0xffffffff) + 2
+                    name = bytes(img[p:img.index(b"\0", p)]).decode()
+                self.iat[BASE + ft + k] = name
+                k += 8
+            d += 20
+        # absolute pointers in the image (base relocation table): candidates for function pointers
+        self.abs_ptrs = []
+        rrva, rsz = struct.unpack_from("<II", b, dirs + 5 * 8)
+        o = 0
+        while o + 8 <= rsz:
+            page, blk = struct.unpack_from("<II", img, rrva + o)
+            if blk < 8:
+                break
+            for k in range(8, blk, 2):
+                e = struct.unpack_from("<H", img, rrva + o + k)[0]
+                if e >> 12 == 10:
+                    self.abs_ptrs.append(page + (e & 0xfff))
+            o += blk
+        self.text = next((va, vsz) for n, va, vsz in self.sections if n == ".text")
+
+    def in_text(self, va):
+        return BASE + self.text[0] <= va < BASE + self.text[0] + self.text[1]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+class Lifter:
+    def __init__(self, pe, ins):
+        self.pe, self.ins = pe, ins
+        self.funcs = {}          # entry VA -> sorted list of instruction addresses
+        self.unknown = {}
+
+    # ---- operands
+    def mem_addr(self, s, ins):
+        """C expression of the effective address of a memory operand 'SIZE PTR [..]' or '[..]'."""
+        inner = s[s.index("[") + 1:s.rindex("]")]
+        terms = re.findall(r"([+-]?)\s*([^+-]+)", inner)
+        parts = []
+        for sign, t in terms:
+            t = t.strip()
+            if t == "rip":
+                parts.append(f"0x{ins.addr + ins.size:x}ULL")
+            elif "*" in t:
+                r, sc = t.split("*")
+                parts.append(f"{sign}(R[{REG[r][0]}]*{sc}ULL)" if sign == "-" else f"R[{REG[r][0]}]*{sc}ULL")
+            elif t in REG:
+                assert REG[t][1] == 64, s
+                parts.append(f"{sign}R[{REG[t][0]}]" if sign == "-" else f"R[{REG[t][0]}]")
+            else:
+                v = int(t, 16)
+                parts.append(f"-0x{v:x}ULL" if sign == "-" else f"0x{v:x}ULL")
+        expr = parts[0]
+        for p in parts[1:]:
+            expr += p if p.startswith("-") else "+" + p
+        return "(" + expr + ")"
+
+    def const_addr(self, s, ins):
+        """VA if the operand is rip-relative, else None."""
+        if "[rip" not in s:
+            return None
+        inner = s[s.index("[") + 1:s.rindex("]")]
+        m = re.match(r"rip([+-])0x([0-9a-f]+)$", inner)
+        v = int(m.group(2), 16)
+        return (ins.addr + ins.size + (v if m.group(1) == "+" else -v)) & 0xffffffffffffffff
+
+    def op_size(self, s, default=None):
+        if "PTR" in s:
+            return SIZES[s.split()[0]]
+        if s in REG:
+            return REG[s][1]
+        if s in R8H:
+            return 8
+        if s.startswith("xmm"):
+            return 128
+        return default
+
+    def rd(self, s, ins, size=None):
+        """C expression reading an integer operand (zero-extended into uint64_t)."""
+        if s in REG:
+            i, w = REG[s]
+            return f"R[{i}]" if w == 64 else f"(uint64_t)(uint{w}_t)R[{i}]"
+        if s in R8H:
+            return f"((R[{R8H[s]}]>>8)&0xff)"
+        if "[" in s:
+            w = SIZES[s.split()[0]] if "PTR" in s else size
+            return f"LD{w}({self.mem_addr(s, ins)})"
+        v = int(s, 16) if s.startswith(("0x", "-0x")) else int(s)
+        # objdump prints immediates as the sign-extended value at operand size
+        return f"0x{v & 0xffffffffffffffff:x}ULL"
+
+    def wr(self, s, ins, val, size=None):
+        """C statement writing integer `val` (a uint64_t expression) to an operand."""
+        if s in REG:
+            i, w = REG[s]
+            if w == 64:
+                return f"R[{i}]=({val});"
+            if w == 32:
+                return f"R[{i}]=(uint32_t)({val});"
+            mask = (1 << w) - 1
+            return f"R[{i}]=(R[{i}]&~0x{mask:x}ULL)|(({val})&0x{mask:x}ULL);"
+        if s in R8H:
+            i = R8H[s]
+            return f"R[{i}]=(R[{i}]&~0xff00ULL)|((({val})&0xff)<<8);"
+        w = SIZES[s.split()[0]] if "PTR" in s else size
+        return f"ST{w}({self.mem_addr(s, ins)},({val}));"
+
+    def xr(self, s):
+        return int(s[3:])
+
+    # ---- discovery
+    def flow(self, entry):
+        seen, work = set(), [entry]
+        while work:
+            a = work.pop()
+            while a not in seen:
+                if a not in self.ins:
+                    self.unknown.setdefault(entry, []).append(a)
+                    break
+                seen.add(a)
+                i = self.ins[a]
+                mn = i.mn
+                if mn == "ret" or mn == "int3" or mn == "ud2":
+                    break
+                if mn == "jmp":
+                    t = self.direct_target(i)
+                    if t is not None and t not in self.entries and not self.is_import_thunk(t):
+                        work.append(t)
+                    break
+                if mn.startswith("j"):
+                    t = self.direct_target(i)
+                    if t is not None:
+                        work.append(t)
+                a += i.size
+        return sorted(seen)
+
+    def direct_target(self, i):
+        if len(i.ops) == 1 and re.match(r"0x[0-9a-f]+$", i.ops[0]):
+            return int(i.ops[0], 16)
+        return None
+
+    def is_import_thunk(self, a):
+        i = self.ins.get(a)
+        return i is not None and i.mn == "jmp" and i.ops and "[rip" in i.ops[0] and self.const_addr(i.ops[0], i) in self.pe.iat
+
+    def discover(self, roots):
+        self.entries = set(roots)
+        # address-taken code: lea reg,[rip+X] into .text, and relocated absolute pointers into .text
+        self.addr_taken = set()
+        for off in self.pe.abs_ptrs:
+            v = struct.unpack_from("<Q", self.pe.img, off)[0]
+            if self.pe.in_text(v) and v in self.ins:
+                self.addr_taken.add(v)
+                if v < BASE + MODEL_END:        # function pointers of the model (S-function methods); the CRT's stay untranslated
+                    self.entries.add(v)
+        done = set()
+        while True:
+            todo = [e for e in self.entries if e not in done]
+            if not todo:
+                break
+            for e in todo:
+                done.add(e)
+                if self.is_import_thunk(e):
+                    continue
+                body = self.flow(e)
+                self.funcs[e] = body
+                for a in body:
+                    i = self.ins[a]
+                    if i.mn == "call" or i.mn == "jmp":
+                        t = self.direct_target(i)
+                        if t is not None and (i.mn == "call" or t in self.entries or self.is_import_thunk(t)):
+                            self.entries.add(t)
+                    if i.mn == "lea" and "[rip" in i.ops[1]:
+                        t = self.const_addr(i.ops[1], i)
+                        if self.pe.in_text(t) and t in self.ins:
+                            self.addr_taken.add(t)
+                            self.entries.add(t)
+        # a jump into the middle of another discovered function stays a local jump (blocks are duplicated); a jump to an entry
+        # that was discovered later than the function containing the jump must become a tail call: redo the flows once
+        for e in list(self.funcs):
+            self.funcs[e] = self.flow(e)
+
+    # ---- emission
+    def emit_all(self):
+        out = []
+        names = sorted(self.funcs)
+        thunks = sorted(e for e in self.entries if self.is_import_thunk(e))
+        for e in names + thunks:
+            out.append(f"LIFT_FN void f_{e:x}(cpu_t* c);")
+        out.append("")
+        for e in thunks:
+            i = self.ins[e]
+            name = self.pe.iat[self.const_addr(i.ops[0], i)]
+            out.append(f"LIFT_FN void f_{e:x}(cpu_t* c) {{ {self.import_call(name)} R[4]+=8; }}")
+        # indirect-call dispatcher over address-taken functions
+        out.append("LIFT_FN void lift_dispatch(cpu_t* c, uint64_t target) {")
+        out.append("  switch (target) {")
+        for e in sorted(self.addr_taken & set(self.funcs)):
+            out.append(f"  case 0x{e:x}ULL: f_{e:x}(c); return;")
+        out.append("  default: LIFT_TRAP(\"indirect call to an address that is not a translated function\", target);")
+        out.append("  }\n}\n")
+        for e in names:
+            out.extend(self.emit_func(e))
+        return "\n".join(out)
+
+    def import_call(self, name):
+        kind = IMPORTS.get(name)
+        if kind == "d_d":
+            return f"X[0].d[0]=lift_{name}(X[0].d[0]);"
+        if kind == "d_dd":
+            return f"X[0].d[0]=lift_{name}(X[0].d[0],X[1].d[0]);"
+        if name == "memcpy":
+            return "lift_memcpy(c,R[1],R[2],R[8]); R[0]=R[1];"
+        if name == "memset":
+            return "lift_memset(c,R[1],(int)R[2],R[8]); R[0]=R[1];"
+        if name == "malloc":
+            return "R[0]=lift_malloc(c,R[1]);"
+        if name == "free":
+            return ";"
+        return f"LIFT_TRAP(\"unbound import {name}\", 0);"
+
+    def emit_func(self, e):
+        body = self.funcs[e]
+        inside = set(body)
+        targets = set()
+        for a in body:
+            i = self.ins[a]
+            if i.mn.startswith("j"):
+                t = self.direct_target(i)
+                if t in inside:
+                    targets.add(t)
+        out = [f"LIFT_FN void f_{e:x}(cpu_t* c) {{"]
+        prev_end = None
+        for a in body:
+            i = self.ins[a]
+            if prev_end is not None and prev_end != a:
+                pass            # a gap: the previous instruction did not fall through (jmp / ret / int3) or flows elsewhere
+            if a in targets or (prev_end is not None and prev_end != a):
+                out.append(f"L_{a:x}: ;")
+            try:
+                code = self.emit_ins(i, inside, e)
+            except Exception as ex:  # noqa: BLE001 - report the instruction and keep going: unreachable CRT code may be odd
+                code = f"LIFT_TRAP(\"untranslated instruction\", 0x{a:x}ULL); /* {i.raw} : {ex!r} */"
+                self.unknown.setdefault(e, []).append((a, i.raw))
+            out.append(f"  {code}   /* {a:x}: {i.raw} */")
+            prev_end = a + i.size
+            nxt = prev_end
+            if not self.ends_flow(i) and nxt not in inside:
+                out.append(f"  LIFT_TRAP(\"fell off the translated code\", 0x{nxt:x}ULL);")
+        out.append("}\n")
+        # labels that are only reached by fallthrough gaps but never jumped to produce 'unused label' warnings: harmless
+        return out
+
+    def ends_flow(self, i):
+        return i.mn in ("ret", "jmp", "int3", "ud2")
+
+    def goto(self, t, inside):
+        if t in inside:
+            return f"goto L_{t:x};"
+        if t in self.funcs or self.is_import_thunk(t):
+            return f"{{ f_{t:x}(c); return; }}"
+        return f"LIFT_TRAP(\"jump out of the translated code\", 0x{t:x}ULL);"
+
+    def emit_ins(self, i, inside, fentry):
+        mn, ops = i.mn, i.ops
+        rd, wr = self.rd, self.wr
+        if mn in ("nop", "int3", "ud2") or mn.startswith("nop"):
+            return ";" if mn.startswith("nop") else f"LIFT_TRAP(\"{mn}\", 0x{i.addr:x}ULL);"
+        if mn == "ret":
+            return "R[4]+=8; return;"
+        if mn == "call":
+            t = self.direct_target(i)
+            if t is not None:
+                if t in self.funcs or self.is_import_thunk(t):
+                    return f"R[4]-=8; f_{t:x}(c);"
+                return f"LIFT_TRAP(\"call to untranslated code\", 0x{t:x}ULL);"
+            if "[rip" in ops[0]:
+                slot = self.const_addr(ops[0], i)
+                if slot in self.pe.iat:
+                    return self.import_call(self.pe.iat[slot])
+            return f"{{ uint64_t t_={rd(ops[0], i, 64)}; R[4]-=8; lift_dispatch(c,t_); }}"
+        if mn == "jmp":
+            t = self.direct_target(i)
+            if t is not None:
+                return self.goto(t, inside)
+            if "[rip" in ops[0]:
+                slot = self.const_addr(ops[0], i)
+                if slot in self.pe.iat:
+                    return f"{self.import_call(self.pe.iat[slot])} R[4]+=8; return;"
+            return f"{{ uint64_t t_={rd(ops[0], i, 64)}; lift_dispatch(c,t_); return; }}"
+        if mn.startswith("j") and mn[1:] in CC:
+            return f"if ({CC[mn[1:]]}) {self.goto(self.direct_target(i), inside)}"
+        if mn.startswith("set") and mn[3:] in CC:
+            return wr(ops[0], i, f"({CC[mn[3:]]})?1:0", 8)
+        if mn.startswith("cmov") and mn[4:] in CC:
+            w = self.op_size(ops[0])
+            # a 32-bit cmov zero-extends the destination even when the condition is false
+            return f"if ({CC[mn[4:]]}) {{ {wr(ops[0], i, rd(ops[1], i, w))} }} else {{ {wr(ops[0], i, rd(ops[0], i, w))} }}"
+        if mn in ("mov", "movabs"):
+            w = self.op_size(ops[0]) or self.op_size(ops[1])
+            return wr(ops[0], i, rd(ops[1], i, w), w)
+        if mn == "movzx":
+            return wr(ops[0], i, rd(ops[1], i))
+        if mn in ("movsx", "movsxd"):
+            ws = self.op_size(ops[1])
+            return wr(ops[0], i, f"(uint64_t)(int64_t)(int{ws}_t)({rd(ops[1], i)})")
+        if mn == "lea":
+            return wr(ops[0], i, self.mem_addr(ops[1], i))
+        if mn == "cdqe":
+            return "R[0]=(uint64_t)(int64_t)(int32_t)R[0];"
+        if mn == "cdq":
+            return "R[2]=(uint32_t)(((int32_t)R[0])>>31);"
+        if mn == "cqo":
+            return "R[2]=(uint64_t)(((int64_t)R[0])>>63);"
+        if mn == "push":
+            return f"R[4]-=8; ST64(R[4],{rd(ops[0], i, 64)});"
+        if mn == "pop":
+            return f"{{ uint64_t t_=LD64(R[4]); R[4]+=8; {wr(ops[0], i, 't_')} }}"
+        if mn == "xchg":
+            w = self.op_size(ops[0]) or self.op_size(ops[1])
+            return f"{{ uint64_t a_={rd(ops[0], i, w)}, b_={rd(ops[1], i, w)}; {wr(ops[0], i, 'b_', w)} {wr(ops[1], i, 'a_', w)} }}"
+        if mn in ("add", "sub", "and", "or", "xor", "cmp", "test", "adc", "sbb"):
+            w = self.op_size(ops[0]) or self.op_size(ops[1])
+            a, b = rd(ops[0], i, w), rd(ops[1], i, w)
+            if mn == "xor" and ops[0] == ops[1] and ops[0] in REG:
+                return f"R[{REG[ops[0]][0]}]=0; ZF=1; SF=0; CF=0; OF=0; PF=1;" if REG[ops[0]][1] >= 32 else wr(ops[0], i, "0") + " ZF=1; SF=0; CF=0; OF=0; PF=1;"
+            fn = {"add": "ADD", "sub": "SUB", "and": "AND", "or": "OR", "xor": "XOR", "cmp": "SUB", "test": "AND", "adc": "ADC", "sbb": "SBB"}[mn]
+            call = f"lift_{fn}{w}(c,{a},{b})"
+            if mn in ("cmp", "test"):
+                return f"(void){call};"
+            return wr(ops[0], i, call, w)
+        if mn in ("inc", "dec", "neg", "not"):
+            w = self.op_size(ops[0])
+            a = rd(ops[0], i, w)
+            if mn == "not":
+                return wr(ops[0], i, f"~({a})", w)
+            return wr(ops[0], i, f"lift_{mn.upper()}{w}(c,{a})", w)
+        if mn in ("shl", "sal", "shr", "sar", "rol", "ror"):
+            w = self.op_size(ops[0])
+            cnt = rd(ops[1], i, 8) if len(ops) > 1 else "1"
+            fn = {"shl": "SHL", "sal": "SHL", "shr": "SHR", "sar": "SAR", "rol": "ROL", "ror": "ROR"}[mn]
+            return wr(ops[0], i, f"lift_{fn}{w}(c,{rd(ops[0], i, w)},{cnt})", w)
+        if mn == "imul":
+            w = self.op_size(ops[0])
+            if len(ops) == 1:
+                raise NotImplementedError("one-operand imul")
+            a = rd(ops[1] if len(ops) == 3 else ops[0], i, w)
+            b = rd(ops[2] if len(ops) == 3 else ops[1], i, w)
+            return wr(ops[0], i, f"lift_IMUL{w}(c,{a},{b})", w)
+        if mn == "bt":
+            w = self.op_size(ops[0])
+            return f"CF=(({rd(ops[0], i, w)})>>(({rd(ops[1], i, 8)})&{w - 1}))&1;"
+        if mn in ("btr", "bts", "btc"):
+            w = self.op_size(ops[0])
+            op = {"btr": "&~", "bts": "|", "btc": "^"}[mn]
+            return (f"{{ uint64_t v_={rd(ops[0], i, w)}; unsigned n_=(unsigned)({rd(ops[1], i, 8)})&{w - 1}; CF=(v_>>n_)&1; "
+                    f"v_=v_{op}(1ULL<<n_); {wr(ops[0], i, 'v_', w)} }}")
+        # ---- SSE
+        if mn in ("movsd", "movq"):
+            d, s = ops
+            if d.startswith("xmm") and s.startswith("xmm"):
+                if mn == "movq":
+                    return f"X[{self.xr(d)}].u[0]=X[{self.xr(s)}].u[0]; X[{self.xr(d)}].u[1]=0;"
+                return f"X[{self.xr(d)}].u[0]=X[{self.xr(s)}].u[0];"
+            if d.startswith("xmm"):
+                if s in REG:
+                    return f"X[{self.xr(d)}].u[0]={rd(s, i)}; X[{self.xr(d)}].u[1]=0;"
+                return f"X[{self.xr(d)}].u[0]=LD64({self.mem_addr(s, i)}); X[{self.xr(d)}].u[1]=0;"
+            if d in REG:
+                return wr(d, i, f"X[{self.xr(s)}].u[0]")
+            return f"ST64({self.mem_addr(d, i)},X[{self.xr(s)}].u[0]);"
+        if mn == "movd":
+            d, s = ops
+            if d.startswith("xmm"):
+                return f"X[{self.xr(d)}].u[0]=(uint32_t)({rd(s, i, 32)}); X[{self.xr(d)}].u[1]=0;"
+            return wr(d, i, f"(uint32_t)X[{self.xr(s)}].u[0]", 32)
+        if mn in ("movaps", "movups", "movapd", "movupd", "movdqa", "movdqu"):
+            d, s = ops
+            if d.startswith("xmm") and s.startswith("xmm"):
+                return f"X[{self.xr(d)}]=X[{self.xr(s)}];"
+            if d.startswith("xmm"):
+                return f"{{ uint64_t a_={self.mem_addr(s, i)}; X[{self.xr(d)}].u[0]=LD64(a_); X[{self.xr(d)}].u[1]=LD64(a_+8); }}"
+            return f"{{ uint64_t a_={self.mem_addr(d, i)}; ST64(a_,X[{self.xr(s)}].u[0]); ST64(a_+8,X[{self.xr(s)}].u[1]); }}"
+        if mn in ("movlpd", "movhpd", "movlps", "movhps"):
+            k = 0 if mn[3] == "l" else 1
+            d, s = ops
+            if d.startswith("xmm"):
+                return f"X[{self.xr(d)}].u[{k}]=LD64({self.mem_addr(s, i)});"
+            return f"ST64({self.mem_addr(d, i)},X[{self.xr(s)}].u[{k}]);"
+        sc = {"addsd": "F_ADD", "subsd": "F_SUB", "mulsd": "F_MUL", "divsd": "F_DIV", "maxsd": "F_MAX", "minsd": "F_MIN"}
+        if mn in sc:
+            d, s = ops
+            src = f"X[{self.xr(s)}].d[0]" if s.startswith("xmm") else f"LDD({self.mem_addr(s, i)})"
+            return f"X[{self.xr(d)}].d[0]={sc[mn]}(X[{self.xr(d)}].d[0],{src});"
+        if mn == "sqrtsd":
+            d, s = ops
+            src = f"X[{self.xr(s)}].d[0]" if s.startswith("xmm") else f"LDD({self.mem_addr(s, i)})"
+            return f"X[{self.xr(d)}].d[0]=F_SQRT({src});"
+        pk = {"addpd": "F_ADD", "subpd": "F_SUB", "mulpd": "F_MUL", "divpd": "F_DIV", "maxpd": "F_MAX", "minpd": "F_MIN"}
+        if mn in pk or mn == "sqrtpd":
+            d, s = ops
+            pre = ""
+            if s.startswith("xmm"):
+                s0, s1 = f"X[{self.xr(s)}].d[0]", f"X[{self.xr(s)}].d[1]"
+                if self.xr(s) == self.xr(d) and mn != "sqrtpd":
+                    pass
+            else:
+                pre = f"uint64_t a_={self.mem_addr(s, i)}; "
+                s0, s1 = "LDD(a_)", "LDD(a_+8)"
+            dx = f"X[{self.xr(d)}]"
+            if mn == "sqrtpd":
+                return f"{{ {pre}double p_=F_SQRT({s0}), q_=F_SQRT({s1}); {dx}.d[0]=p_; {dx}.d[1]=q_; }}"
+            return f"{{ {pre}double p_={pk[mn]}({dx}.d[0],{s0}), q_={pk[mn]}({dx}.d[1],{s1}); {dx}.d[0]=p_; {dx}.d[1]=q_; }}"
+        if mn in ("unpcklpd", "unpckhpd", "movlhps", "movhlps"):
+            d, s = ops
+            dx = f"X[{self.xr(d)}]"
+            if s.startswith("xmm"):
+                s0, s1 = f"X[{self.xr(s)}].u[0]", f"X[{self.xr(s)}].u[1]"
+                pre = ""
+            else:
+                pre = f"uint64_t a_={self.mem_addr(s, i)}; "
+                s0, s1 = "LD64(a_)", "LD64(a_+8)"
+            if mn == "unpcklpd" or mn == "movlhps":
+                return f"{{ {pre}uint64_t v_={s0}; {dx}.u[1]=v_; }}"
+            if mn == "unpckhpd":
+                return f"{{ {pre}uint64_t v_={s1}; {dx}.u[0]={dx}.u[1]; {dx}.u[1]=v_; }}"
+            return f"{{ {pre}uint64_t v_={s1}; {dx}.u[0]=v_; }}"           # movhlps
+        if mn == "shufpd":
+            d, s, imm = ops
+            k = int(imm, 16)
+            dx, sx = f"X[{self.xr(d)}]", f"X[{self.xr(s)}]"
+            return f"{{ uint64_t p_={dx}.u[{k & 1}], q_={sx}.u[{(k >> 1) & 1}]; {dx}.u[0]=p_; {dx}.u[1]=q_; }}"
+        bw = {"xorps": "^", "xorpd": "^", "pxor": "^", "andps": "&", "andpd": "&", "pand": "&", "orps": "|", "orpd": "|", "por": "|"}
+        if mn in bw:
+            d, s = ops
+            dx = f"X[{self.xr(d)}]"
+            if s.startswith("xmm"):
+                if self.xr(s) == self.xr(d) and bw[mn] == "^":
+                    return f"{dx}.u[0]=0; {dx}.u[1]=0;"
+                return f"{dx}.u[0]{bw[mn]}=X[{self.xr(s)}].u[0]; {dx}.u[1]{bw[mn]}=X[{self.xr(s)}].u[1];"
+            return f"{{ uint64_t a_={self.mem_addr(s, i)}; {dx}.u[0]{bw[mn]}=LD64(a_); {dx}.u[1]{bw[mn]}=LD64(a_+8); }}"
+        if mn in ("andnps", "andnpd", "pandn"):
+            d, s = ops
+            dx = f"X[{self.xr(d)}]"
+            if s.startswith("xmm"):
+                return f"{dx}.u[0]=~{dx}.u[0]&X[{self.xr(s)}].u[0]; {dx}.u[1]=~{dx}.u[1]&X[{self.xr(s)}].u[1];"
+            return f"{{ uint64_t a_={self.mem_addr(s, i)}; {dx}.u[0]=~{dx}.u[0]&LD64(a_); {dx}.u[1]=~{dx}.u[1]&LD64(a_+8); }}"
+        if mn in ("comisd", "ucomisd"):
+            d, s = ops
+            src = f"X[{self.xr(s)}].d[0]" if s.startswith("xmm") else f"LDD({self.mem_addr(s, i)})"
+            return f"lift_COMISD(c,X[{self.xr(d)}].d[0],{src});"
+        if mn == "cvtsi2sd":
+            d, s = ops
+            w = self.op_size(s)
+            return f"X[{self.xr(d)}].d[0]=(double)(int{w}_t)({rd(s, i, w)});"
+        if mn in ("cvttsd2si", "cvtsd2si"):
+            d, s = ops
+            w = self.op_size(d)
+            src = f"X[{self.xr(s)}].d[0]" if s.startswith("xmm") else f"LDD({self.mem_addr(s, i)})"
+            fn = "lift_CVTT" if mn == "cvttsd2si" else "lift_CVTR"
+            return wr(d, i, f"{fn}{w}({src})", w)
+        if mn == "cvtdq2pd":
+            d, s = ops
+            dx = f"X[{self.xr(d)}]"
+            src = f"X[{self.xr(s)}].u[0]" if s.startswith("xmm") else f"LD64({self.mem_addr(s, i)})"
+            return f"{{ uint64_t v_={src}; {dx}.d[0]=(double)(int32_t)(uint32_t)v_; {dx}.d[1]=(double)(int32_t)(uint32_t)(v_>>32); }}"
+        if mn in ("cvtps2pd", "cvtss2sd"):
+            d, s = ops
+            dx = f"X[{self.xr(d)}]"
+            src = f"X[{self.xr(s)}].u[0]" if s.startswith("xmm") else (f"LD64({self.mem_addr(s, i)})" if mn == "cvtps2pd" else f"LD32({self.mem_addr(s, i)})")
+            if mn == "cvtss2sd":
+                return f"{{ uint32_t v_=(uint32_t)({src}); {dx}.d[0]=(double)lift_u2f(v_); }}"
+            return f"{{ uint64_t v_={src}; {dx}.d[0]=(double)lift_u2f((uint32_t)v_); {dx}.d[1]=(double)lift_u2f((uint32_t)(v_>>32)); }}"
+        if mn == "cvtsd2ss":
+            d, s = ops
+            src = f"X[{self.xr(s)}].d[0]" if s.startswith("xmm") else f"LDD({self.mem_addr(s, i)})"
+            return f"X[{self.xr(d)}].u[0]=(X[{self.xr(d)}].u[0]&~0xffffffffULL)|lift_f2u((float)({src}));"
+        if mn == "movss":
+            d, s = ops
+            if d.startswith("xmm") and s.startswith("xmm"):
+                return f"X[{self.xr(d)}].u[0]=(X[{self.xr(d)}].u[0]&~0xffffffffULL)|(X[{self.xr(s)}].u[0]&0xffffffffULL);"
+            if d.startswith("xmm"):
+                return f"X[{self.xr(d)}].u[0]=LD32({self.mem_addr(s, i)}); X[{self.xr(d)}].u[1]=0;"
+            return f"ST32({self.mem_addr(d, i)},X[{self.xr(s)}].u[0]);"
+        if mn.startswith("rep stos"):
+            w = SIZES[mn.split()[2]]
+            return f"lift_REPSTOS(c,{w // 8});"
+        if mn.startswith("rep movs"):
+            w = SIZES[mn.split()[2]]
+            return f"lift_REPMOVS(c,{w // 8});"
+        raise NotImplementedError(mn)
+
+
+PRELUDE = r"""/* GENERATED by oracle/pe_probe/lift.py from the reference's plant binary -- do not edit, do not commit. */
+#ifndef LIFT_FN
+#define LIFT_FN static
+#endif
+#define R  (c->r)
+#define X  (c->x)
+#define ZF (c->zf)
+#define SF (c->sf)
+#define CF (c->cf)
+#define OF (c->of)
+#define PF (c->pf)
+"""
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--variant", default="extended_input")
+    ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "_ref", "lifted"))
+    args = ap.parse_args()
+    path = os.path.join(REF_DIR, args.variant, "_citation.cp39-win_amd64.pyd")
+    pe = PE(path)
+    ins = disassemble(path)
+    L = Lifter(pe, ins)
+    L.discover([BASE + v for v in ENTRY.values()])
+    code = L.emit_all()
+    os.makedirs(args.out, exist_ok=True)
+    with open(os.path.join(args.out, f"citation_{args.variant}_code.inc"), "w") as f:
+        f.write(PRELUDE)
+        f.write(code)
+        f.write("\n#undef R\n#undef X\n#undef ZF\n#undef SF\n#undef CF\n#undef OF\n#undef PF\n")
+    with open(os.path.join(args.out, f"citation_{args.variant}_image.bin"), "wb") as f:
+        f.write(bytes(pe.img))
+    n_ins = sum(len(v) for v in L.funcs.values())
+    print(f"{args.variant}: {len(L.funcs)} functions, {n_ins} instructions translated, image {pe.image_size} bytes")
+    for e, u in sorted(L.unknown.items()):
+        print(f"  f_{e:x}: {len(u)} untranslated:", [(hex(a), r) if isinstance(x, tuple) else hex(x) for x in u[:6] for a, r in [x if isinstance(x, tuple) else (x, '')]])
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
