@@ -49,6 +49,15 @@ static inline uint8_t* lift_wptr(cpu_t* c, uint64_t a, unsigned n)
 #define ST16(a, v) LIFT_ST(uint16_t, a, v)
 #define ST32(a, v) LIFT_ST(uint32_t, a, v)
 #define ST64(a, v) LIFT_ST(uint64_t, a, v)
+#define LDS8 LD8
+#define LDS16 LD16
+#define LDS32 LD32
+#define LDS64 LD64
+#define LDSD LDD
+#define STS8 ST8
+#define STS16 ST16
+#define STS32 ST32
+#define STS64 ST64
 
 #define lift_cos cos
 #define lift_sin sin
@@ -68,17 +77,35 @@ static uint64_t lift_malloc(cpu_t* c, uint64_t n)
     c->heap_next = p + n;
     return p;
 }
-static void lift_REPSTOS(cpu_t* c, unsigned w)
+static void lift_REPSTOS(cpu_t* c, uint64_t* rcx, uint64_t* rdi, uint64_t rax, unsigned w)
 {
-    for (; c->r[1]; --c->r[1], c->r[7] += w) memcpy(lift_wptr(c, c->r[7], w), &c->r[0], w);
+    for (; *rcx; --*rcx, *rdi += w) memcpy(lift_wptr(c, *rdi, w), &rax, w);
 }
-static void lift_REPMOVS(cpu_t* c, unsigned w)
+static void lift_REPMOVS(cpu_t* c, uint64_t* rcx, uint64_t* rdi, uint64_t* rsi, unsigned w)
 {
-    for (; c->r[1]; --c->r[1], c->r[7] += w, c->r[6] += w) memmove(lift_wptr(c, c->r[7], w), lift_ptr(c, c->r[6], w), w);
+    for (; *rcx; --*rcx, *rdi += w, *rsi += w) memmove(lift_wptr(c, *rdi, w), lift_ptr(c, *rsi, w), w);
 }
 static inline uint64_t lift_CVTR32(double v) { return (v > -2147483649.0 && v < 2147483648.0) ? (uint64_t)(uint32_t)(int32_t)nearbyint(v) : 0x80000000ULL; }
 static inline uint64_t lift_CVTR64(double v) { return (uint64_t)(int64_t)nearbyint(v); }
 
+#ifdef LIFT_PROFILE
+/* execution profile: instructions executed per translated function (analysis builds only) */
+static struct { uint64_t fn, n; } g_prof[64];
+static void lift_bb(uint64_t fn, unsigned n)
+{
+    for (int k = 0; k < 64; ++k) {
+        if (g_prof[k].fn == fn || !g_prof[k].fn) { g_prof[k].fn = fn; g_prof[k].n += n; return; }
+    }
+}
+#define LIFT_BB(fn, n) lift_bb(fn, n)
+int cit_lifted_profile(uint64_t* fn, uint64_t* n, int reset)
+{
+    int k = 0;
+    for (; k < 64 && g_prof[k].fn; ++k) { fn[k] = g_prof[k].fn; n[k] = g_prof[k].n; }
+    if (reset) memset(g_prof, 0, sizeof g_prof);
+    return k;
+}
+#endif
 #include LIFT_GENERATED_INC
 
 /* ---- instance API ------------------------------------------------------------------------------------------------ */

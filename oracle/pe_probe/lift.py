@@ -182,13 +182,30 @@ class PE:
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+ARG_REGS = [1, 2, 8, 9]          # rcx rdx r8 r9: integer arguments of the Windows x64 convention (xmm0-3: floating point)
+
+
 class Lifter:
+    """x86-64 -> C.  Inside a translated function the machine registers are C LOCALS (r0..r15, x0l/x0h..x15l/x15h, fl):
+    the C compiler allocates them, removes dead flag computations and keeps values in registers across instructions.
+    Registers cross function boundaries the way the Windows x64 calling convention says they do: rcx rdx r8 r9 xmm0-3 and rsp
+    are written to the shared `cpu_t` before a call, rax and xmm0 are read back after it; callee-saved registers need no
+    traffic (the callee's prologue / epilogue saves and restores whatever its own locals hold), volatile ones are dead."""
+
+    STEP, SOLVER = BASE + 0x3720, BASE + 0x1c80
+
     def __init__(self, pe, ins):
         self.pe, self.ins = pe, ins
         self.funcs = {}          # entry VA -> sorted list of instruction addresses
         self.unknown = {}
+        self.frame_reg = None
 
     # ---- operands
+    def is_stack_operand(self, s):
+        inner = s[s.index("[") + 1:s.rindex("]")]
+        base = re.split(r"[+\-*]", inner)[0].strip()
+        return base == "rsp" or (self.frame_reg is not None and base == self.frame_reg)
+
     def mem_addr(self, s, ins):
         """C expression of the effective address of a memory operand 'SIZE PTR [..]' or '[..]'."""
         inner = s[s.index("[") + 1:s.rindex("]")]
@@ -200,10 +217,10 @@ class Lifter:
                 parts.append(f"0x{ins.addr + ins.size:x}ULL")
             elif "*" in t:
                 r, sc = t.split("*")
-                parts.append(f"{sign}(R[{REG[r][0]}]*{sc}ULL)" if sign == "-" else f"R[{REG[r][0]}]*{sc}ULL")
+                parts.append(f"{sign}(r{REG[r][0]}*{sc}ULL)" if sign == "-" else f"r{REG[r][0]}*{sc}ULL")
             elif t in REG:
                 assert REG[t][1] == 64, s
-                parts.append(f"{sign}R[{REG[t][0]}]" if sign == "-" else f"R[{REG[t][0]}]")
+                parts.append(f"{sign}r{REG[t][0]}")
             else:
                 v = int(t, 16)
                 parts.append(f"-0x{v:x}ULL" if sign == "-" else f"0x{v:x}ULL")
@@ -211,6 +228,18 @@ class Lifter:
         for p in parts[1:]:
             expr += p if p.startswith("-") else "+" + p
         return "(" + expr + ")"
+
+    def ld(self, w, s, ins):
+        k = "S" if self.is_stack_operand(s) else ""
+        return f"LD{k}{w}({self.mem_addr(s, ins)})"
+
+    def ldd(self, s, ins):
+        k = "S" if self.is_stack_operand(s) else ""
+        return f"LD{k}D({self.mem_addr(s, ins)})"
+
+    def st(self, w, s, ins, val):
+        k = "S" if self.is_stack_operand(s) else ""
+        return f"ST{k}{w}({self.mem_addr(s, ins)},({val}));"
 
     def const_addr(self, s, ins):
         """VA if the operand is rip-relative, else None."""
@@ -236,14 +265,13 @@ class Lifter:
         """C expression reading an integer operand (zero-extended into uint64_t)."""
         if s in REG:
             i, w = REG[s]
-            return f"R[{i}]" if w == 64 else f"(uint64_t)(uint{w}_t)R[{i}]"
+            return f"r{i}" if w == 64 else f"(uint64_t)(uint{w}_t)r{i}"
         if s in R8H:
-            return f"((R[{R8H[s]}]>>8)&0xff)"
+            return f"((r{R8H[s]}>>8)&0xff)"
         if "[" in s:
             w = SIZES[s.split()[0]] if "PTR" in s else size
-            return f"LD{w}({self.mem_addr(s, ins)})"
+            return self.ld(w, s, ins)
         v = int(s, 16) if s.startswith(("0x", "-0x")) else int(s)
-        # objdump prints immediates as the sign-extended value at operand size
         return f"0x{v & 0xffffffffffffffff:x}ULL"
 
     def wr(self, s, ins, val, size=None):
@@ -251,19 +279,35 @@ class Lifter:
         if s in REG:
             i, w = REG[s]
             if w == 64:
-                return f"R[{i}]=({val});"
+                return f"r{i}=({val});"
             if w == 32:
-                return f"R[{i}]=(uint32_t)({val});"
+                return f"r{i}=(uint32_t)({val});"
             mask = (1 << w) - 1
-            return f"R[{i}]=(R[{i}]&~0x{mask:x}ULL)|(({val})&0x{mask:x}ULL);"
+            return f"r{i}=(r{i}&~0x{mask:x}ULL)|(({val})&0x{mask:x}ULL);"
         if s in R8H:
             i = R8H[s]
-            return f"R[{i}]=(R[{i}]&~0xff00ULL)|((({val})&0xff)<<8);"
+            return f"r{i}=(r{i}&~0xff00ULL)|((({val})&0xff)<<8);"
         w = SIZES[s.split()[0]] if "PTR" in s else size
-        return f"ST{w}({self.mem_addr(s, ins)},({val}));"
+        return self.st(w, s, ins, val)
 
     def xr(self, s):
         return int(s[3:])
+
+    def xd(self, s, ins, lane=0):
+        """double-valued expression of lane `lane` of an xmm register or of a memory operand"""
+        if s.startswith("xmm"):
+            return f"U2D(x{self.xr(s)}{'lh'[lane]})"
+        a = self.mem_addr(s, ins)
+        k = "S" if self.is_stack_operand(s) else ""
+        return f"LD{k}D({a}+{8 * lane})" if lane else f"LD{k}D({a})"
+
+    def xu(self, s, ins, lane=0):
+        """uint64-valued expression of a lane"""
+        if s.startswith("xmm"):
+            return f"x{self.xr(s)}{'lh'[lane]}"
+        a = self.mem_addr(s, ins)
+        k = "S" if self.is_stack_operand(s) else ""
+        return f"LD{k}64({a}+{8 * lane})" if lane else f"LD{k}64({a})"
 
     # ---- discovery
     def flow(self, entry):
@@ -300,6 +344,10 @@ class Lifter:
         i = self.ins.get(a)
         return i is not None and i.mn == "jmp" and i.ops and "[rip" in i.ops[0] and self.const_addr(i.ops[0], i) in self.pe.iat
 
+    def thunk_name(self, a):
+        i = self.ins[a]
+        return self.pe.iat[self.const_addr(i.ops[0], i)]
+
     def discover(self, roots):
         self.entries = set(roots)
         # address-taken code: lea reg,[rip+X] into .text, and relocated absolute pointers into .text
@@ -332,8 +380,7 @@ class Lifter:
                         if self.pe.in_text(t) and t in self.ins:
                             self.addr_taken.add(t)
                             self.entries.add(t)
-        # a jump into the middle of another discovered function stays a local jump (blocks are duplicated); a jump to an entry
-        # that was discovered later than the function containing the jump must become a tail call: redo the flows once
+        # a jump to an entry that was discovered later than the function containing the jump must become a tail call
         for e in list(self.funcs):
             self.funcs[e] = self.flow(e)
 
@@ -341,14 +388,10 @@ class Lifter:
     def emit_all(self):
         out = []
         names = sorted(self.funcs)
-        thunks = sorted(e for e in self.entries if self.is_import_thunk(e))
-        for e in names + thunks:
+        for e in names:
             out.append(f"LIFT_FN void f_{e:x}(cpu_t* c);")
+        out.append(f"LIFT_FN void f_{self.STEP:x}_m(cpu_t* c);")
         out.append("")
-        for e in thunks:
-            i = self.ins[e]
-            name = self.pe.iat[self.const_addr(i.ops[0], i)]
-            out.append(f"LIFT_FN void f_{e:x}(cpu_t* c) {{ {self.import_call(name)} R[4]+=8; }}")
         # indirect-call dispatcher over address-taken functions
         out.append("LIFT_FN void lift_dispatch(cpu_t* c, uint64_t target) {")
         out.append("  switch (target) {")
@@ -358,27 +401,68 @@ class Lifter:
         out.append("  }\n}\n")
         for e in names:
             out.extend(self.emit_func(e))
+        out.extend(self.emit_func(self.STEP, minor=True))
         return "\n".join(out)
 
     def import_call(self, name):
+        """statement performing a C-runtime import on the LOCAL registers"""
         kind = IMPORTS.get(name)
         if kind == "d_d":
-            return f"X[0].d[0]=lift_{name}(X[0].d[0]);"
+            return f"x0l=D2U(lift_{name}(U2D(x0l)));"
         if kind == "d_dd":
-            return f"X[0].d[0]=lift_{name}(X[0].d[0],X[1].d[0]);"
+            return f"x0l=D2U(lift_{name}(U2D(x0l),U2D(x1l)));"
         if name == "memcpy":
-            return "lift_memcpy(c,R[1],R[2],R[8]); R[0]=R[1];"
+            return "lift_memcpy(c,r1,r2,r8); r0=r1;"
         if name == "memset":
-            return "lift_memset(c,R[1],(int)R[2],R[8]); R[0]=R[1];"
+            return "lift_memset(c,r1,(int)r2,r8); r0=r1;"
         if name == "malloc":
-            return "R[0]=lift_malloc(c,R[1]);"
+            return "r0=lift_malloc(c,r1);"
         if name == "free":
             return ";"
         return f"LIFT_TRAP(\"unbound import {name}\", 0);"
 
-    def emit_func(self, e):
+    PRECALL = "LIFT_PRECALL;"       # locals -> cpu_t: rcx rdx r8 r9 rsp xmm0-3
+    POSTCALL = "LIFT_POSTCALL;"     # cpu_t -> locals: rax xmm0
+
+    def find_frame_reg(self, body):
+        """rbp when the function uses it as a frame pointer: written once by `lea rbp,[rsp+-c]` (or from rax = rsp at entry),
+        otherwise only pushed / popped."""
+        first = self.ins[body[0]]
+        rax_is_rsp = first.mn == "mov" and first.ops == ["rax", "rsp"]
+        ok = False
+        for n, a in enumerate(body):
+            i = self.ins[a]
+            if not i.ops:
+                continue
+            d = i.ops[0]
+            if d in ("rbp", "ebp", "bp", "bpl") and i.mn not in ("push", "cmp", "test"):
+                if i.mn == "pop":
+                    continue
+                if i.mn == "lea" and d == "rbp" and n < 16 and (i.ops[1].startswith("[rsp") or (rax_is_rsp and i.ops[1].startswith("[rax"))):
+                    if ok:
+                        return None
+                    ok = True
+                    continue
+                return None
+            if i.mn == "xchg" and "rbp" in i.ops:
+                return None
+        if ok and rax_is_rsp:
+            # rax must still be rsp at the lea: no write to rax before it
+            for a in body[1:16]:
+                i = self.ins[a]
+                if i.mn == "lea" and i.ops[0] == "rbp":
+                    break
+                if i.ops and i.ops[0] in ("rax", "eax", "ax", "al") and i.mn not in ("push", "cmp", "test"):
+                    return None
+                if i.mn == "call":
+                    return None
+        return "rbp" if ok else None
+
+    def emit_func(self, e, minor=False):
+        self.cur_fn, self.cur_minor = e, minor
         body = self.funcs[e]
         inside = set(body)
+        self.frame_reg = self.find_frame_reg(body)
         targets = set()
         for a in body:
             i = self.ins[a]
@@ -386,56 +470,76 @@ class Lifter:
                 t = self.direct_target(i)
                 if t in inside:
                     targets.add(t)
-        out = [f"LIFT_FN void f_{e:x}(cpu_t* c) {{"]
+        leaders, cur, prev = {}, None, None
+        for a in body:
+            i = self.ins[a]
+            if cur is None or a in targets or prev is None or prev.addr + prev.size != a or prev.mn.startswith("j") or prev.mn in ("call", "ret"):
+                cur = a
+                leaders[cur] = 0
+            leaders[cur] += 1
+            prev = i
+        out = [f"LIFT_FN void f_{e:x}{'_m' if minor else ''}(cpu_t* c) {{", "  LIFT_LOCALS; LIFT_ENTER;"]
         prev_end = None
         for a in body:
             i = self.ins[a]
-            if prev_end is not None and prev_end != a:
-                pass            # a gap: the previous instruction did not fall through (jmp / ret / int3) or flows elsewhere
             if a in targets or (prev_end is not None and prev_end != a):
                 out.append(f"L_{a:x}: ;")
+            if a in leaders:
+                out.append(f"  LIFT_BB(0x{e:x}ULL, {leaders[a]});")
             try:
                 code = self.emit_ins(i, inside, e)
             except Exception as ex:  # noqa: BLE001 - report the instruction and keep going: unreachable CRT code may be odd
-                code = f"LIFT_TRAP(\"untranslated instruction\", 0x{a:x}ULL); /* {i.raw} : {ex!r} */"
+                code = f"LIFT_TRAP(\"untranslated instruction\", 0x{a:x}ULL); /* {ex!r} */"
                 self.unknown.setdefault(e, []).append((a, i.raw))
             out.append(f"  {code}   /* {a:x}: {i.raw} */")
             prev_end = a + i.size
-            nxt = prev_end
-            if not self.ends_flow(i) and nxt not in inside:
-                out.append(f"  LIFT_TRAP(\"fell off the translated code\", 0x{nxt:x}ULL);")
+            if not self.ends_flow(i) and prev_end not in inside:
+                out.append(f"  LIFT_TRAP(\"fell off the translated code\", 0x{prev_end:x}ULL);")
         out.append("}\n")
-        # labels that are only reached by fallthrough gaps but never jumped to produce 'unused label' warnings: harmless
         return out
 
     def ends_flow(self, i):
         return i.mn in ("ret", "jmp", "int3", "ud2")
 
+    def call_fn(self, t, tail=False):
+        """statement(s) calling translated function / import thunk `t` (direct)"""
+        if self.is_import_thunk(t):
+            return self.import_call(self.thunk_name(t)) + (" LIFT_EXIT; return;" if tail else "")
+        if t == self.SOLVER and self.cur_minor:
+            return "LIFT_TRAP(\"solver reached from a minor step\", 0);"
+        name = f"f_{t:x}_m" if (t == self.STEP and self.cur_fn == self.SOLVER) else f"f_{t:x}"
+        if tail:
+            # the callee returns to OUR caller: its `ret` pops the return address our caller pushed
+            return f"{self.PRECALL} {name}(c); return;"
+        return f"r4-=8; {self.PRECALL} {name}(c); r4+=8; {self.POSTCALL}"
+
     def goto(self, t, inside):
         if t in inside:
             return f"goto L_{t:x};"
         if t in self.funcs or self.is_import_thunk(t):
-            return f"{{ f_{t:x}(c); return; }}"
+            return "{ " + self.call_fn(t, tail=True) + " }"
         return f"LIFT_TRAP(\"jump out of the translated code\", 0x{t:x}ULL);"
 
     def emit_ins(self, i, inside, fentry):
         mn, ops = i.mn, i.ops
         rd, wr = self.rd, self.wr
-        if mn in ("nop", "int3", "ud2") or mn.startswith("nop"):
-            return ";" if mn.startswith("nop") else f"LIFT_TRAP(\"{mn}\", 0x{i.addr:x}ULL);"
+        if mn.startswith("nop"):
+            return ";"
+        if mn in ("int3", "ud2"):
+            return f"LIFT_TRAP(\"{mn}\", 0x{i.addr:x}ULL);"
         if mn == "ret":
-            return "R[4]+=8; return;"
+            return "LIFT_EXIT; return;"
         if mn == "call":
             t = self.direct_target(i)
             if t is not None:
                 if t in self.funcs or self.is_import_thunk(t):
-                    return f"R[4]-=8; f_{t:x}(c);"
+                    return self.call_fn(t)
                 return f"LIFT_TRAP(\"call to untranslated code\", 0x{t:x}ULL);"
             if "[rip" in ops[0]:
                 slot = self.const_addr(ops[0], i)
                 if slot in self.pe.iat:
                     return self.import_call(self.pe.iat[slot])
-            return f"{{ uint64_t t_={rd(ops[0], i, 64)}; R[4]-=8; lift_dispatch(c,t_); }}"
+            return f"{{ uint64_t t_={rd(ops[0], i, 64)}; r4-=8; {self.PRECALL} lift_dispatch(c,t_); r4+=8; {self.POSTCALL} }}"
         if mn == "jmp":
             t = self.direct_target(i)
             if t is not None:
@@ -443,8 +547,8 @@ class Lifter:
             if "[rip" in ops[0]:
                 slot = self.const_addr(ops[0], i)
                 if slot in self.pe.iat:
-                    return f"{self.import_call(self.pe.iat[slot])} R[4]+=8; return;"
-            return f"{{ uint64_t t_={rd(ops[0], i, 64)}; lift_dispatch(c,t_); return; }}"
+                    return f"{self.import_call(self.pe.iat[slot])} LIFT_EXIT; return;"
+            return f"{{ uint64_t t_={rd(ops[0], i, 64)}; {self.PRECALL} lift_dispatch(c,t_); return; }}"
         if mn.startswith("j") and mn[1:] in CC:
             return f"if ({CC[mn[1:]]}) {self.goto(self.direct_target(i), inside)}"
         if mn.startswith("set") and mn[3:] in CC:
@@ -464,15 +568,15 @@ class Lifter:
         if mn == "lea":
             return wr(ops[0], i, self.mem_addr(ops[1], i))
         if mn == "cdqe":
-            return "R[0]=(uint64_t)(int64_t)(int32_t)R[0];"
+            return "r0=(uint64_t)(int64_t)(int32_t)r0;"
         if mn == "cdq":
-            return "R[2]=(uint32_t)(((int32_t)R[0])>>31);"
+            return "r2=(uint32_t)(((int32_t)r0)>>31);"
         if mn == "cqo":
-            return "R[2]=(uint64_t)(((int64_t)R[0])>>63);"
+            return "r2=(uint64_t)(((int64_t)r0)>>63);"
         if mn == "push":
-            return f"R[4]-=8; ST64(R[4],{rd(ops[0], i, 64)});"
+            return f"r4-=8; STS64(r4,{rd(ops[0], i, 64)});"
         if mn == "pop":
-            return f"{{ uint64_t t_=LD64(R[4]); R[4]+=8; {wr(ops[0], i, 't_')} }}"
+            return f"{{ uint64_t t_=LDS64(r4); r4+=8; {wr(ops[0], i, 't_')} }}"
         if mn == "xchg":
             w = self.op_size(ops[0]) or self.op_size(ops[1])
             return f"{{ uint64_t a_={rd(ops[0], i, w)}, b_={rd(ops[1], i, w)}; {wr(ops[0], i, 'b_', w)} {wr(ops[1], i, 'a_', w)} }}"
@@ -480,9 +584,10 @@ class Lifter:
             w = self.op_size(ops[0]) or self.op_size(ops[1])
             a, b = rd(ops[0], i, w), rd(ops[1], i, w)
             if mn == "xor" and ops[0] == ops[1] and ops[0] in REG:
-                return f"R[{REG[ops[0]][0]}]=0; ZF=1; SF=0; CF=0; OF=0; PF=1;" if REG[ops[0]][1] >= 32 else wr(ops[0], i, "0") + " ZF=1; SF=0; CF=0; OF=0; PF=1;"
+                z = f"r{REG[ops[0]][0]}=0;" if REG[ops[0]][1] >= 32 else wr(ops[0], i, "0")
+                return z + " ZF=1; SF=0; CF=0; OF=0; PF=1;"
             fn = {"add": "ADD", "sub": "SUB", "and": "AND", "or": "OR", "xor": "XOR", "cmp": "SUB", "test": "AND", "adc": "ADC", "sbb": "SBB"}[mn]
-            call = f"lift_{fn}{w}(c,{a},{b})"
+            call = f"lift_{fn}{w}(&fl,{a},{b})"
             if mn in ("cmp", "test"):
                 return f"(void){call};"
             return wr(ops[0], i, call, w)
@@ -491,19 +596,19 @@ class Lifter:
             a = rd(ops[0], i, w)
             if mn == "not":
                 return wr(ops[0], i, f"~({a})", w)
-            return wr(ops[0], i, f"lift_{mn.upper()}{w}(c,{a})", w)
+            return wr(ops[0], i, f"lift_{mn.upper()}{w}(&fl,{a})", w)
         if mn in ("shl", "sal", "shr", "sar", "rol", "ror"):
             w = self.op_size(ops[0])
             cnt = rd(ops[1], i, 8) if len(ops) > 1 else "1"
             fn = {"shl": "SHL", "sal": "SHL", "shr": "SHR", "sar": "SAR", "rol": "ROL", "ror": "ROR"}[mn]
-            return wr(ops[0], i, f"lift_{fn}{w}(c,{rd(ops[0], i, w)},{cnt})", w)
+            return wr(ops[0], i, f"lift_{fn}{w}(&fl,{rd(ops[0], i, w)},{cnt})", w)
         if mn == "imul":
             w = self.op_size(ops[0])
             if len(ops) == 1:
                 raise NotImplementedError("one-operand imul")
             a = rd(ops[1] if len(ops) == 3 else ops[0], i, w)
             b = rd(ops[2] if len(ops) == 3 else ops[1], i, w)
-            return wr(ops[0], i, f"lift_IMUL{w}(c,{a},{b})", w)
+            return wr(ops[0], i, f"lift_IMUL{w}(&fl,{a},{b})", w)
         if mn == "bt":
             w = self.op_size(ops[0])
             return f"CF=(({rd(ops[0], i, w)})>>(({rd(ops[1], i, 8)})&{w - 1}))&1;"
@@ -512,139 +617,127 @@ class Lifter:
             op = {"btr": "&~", "bts": "|", "btc": "^"}[mn]
             return (f"{{ uint64_t v_={rd(ops[0], i, w)}; unsigned n_=(unsigned)({rd(ops[1], i, 8)})&{w - 1}; CF=(v_>>n_)&1; "
                     f"v_=v_{op}(1ULL<<n_); {wr(ops[0], i, 'v_', w)} }}")
-        # ---- SSE
+        # ---- SSE (xmm N = locals xNl, xNh)
+        xu, xd, st = self.xu, self.xd, self.st
         if mn in ("movsd", "movq"):
             d, s = ops
             if d.startswith("xmm") and s.startswith("xmm"):
-                if mn == "movq":
-                    return f"X[{self.xr(d)}].u[0]=X[{self.xr(s)}].u[0]; X[{self.xr(d)}].u[1]=0;"
-                return f"X[{self.xr(d)}].u[0]=X[{self.xr(s)}].u[0];"
+                n = self.xr(d)
+                return f"x{n}l=x{self.xr(s)}l;" + (f" x{n}h=0;" if mn == "movq" else "")
             if d.startswith("xmm"):
-                if s in REG:
-                    return f"X[{self.xr(d)}].u[0]={rd(s, i)}; X[{self.xr(d)}].u[1]=0;"
-                return f"X[{self.xr(d)}].u[0]=LD64({self.mem_addr(s, i)}); X[{self.xr(d)}].u[1]=0;"
+                n = self.xr(d)
+                return f"x{n}l={rd(s, i) if s in REG else xu(s, i)}; x{n}h=0;"
             if d in REG:
-                return wr(d, i, f"X[{self.xr(s)}].u[0]")
-            return f"ST64({self.mem_addr(d, i)},X[{self.xr(s)}].u[0]);"
+                return wr(d, i, f"x{self.xr(s)}l")
+            return st(64, d, i, f"x{self.xr(s)}l")
         if mn == "movd":
             d, s = ops
             if d.startswith("xmm"):
-                return f"X[{self.xr(d)}].u[0]=(uint32_t)({rd(s, i, 32)}); X[{self.xr(d)}].u[1]=0;"
-            return wr(d, i, f"(uint32_t)X[{self.xr(s)}].u[0]", 32)
+                n = self.xr(d)
+                return f"x{n}l=(uint32_t)({rd(s, i, 32)}); x{n}h=0;"
+            return wr(d, i, f"(uint32_t)x{self.xr(s)}l", 32)
         if mn in ("movaps", "movups", "movapd", "movupd", "movdqa", "movdqu"):
             d, s = ops
-            if d.startswith("xmm") and s.startswith("xmm"):
-                return f"X[{self.xr(d)}]=X[{self.xr(s)}];"
             if d.startswith("xmm"):
-                return f"{{ uint64_t a_={self.mem_addr(s, i)}; X[{self.xr(d)}].u[0]=LD64(a_); X[{self.xr(d)}].u[1]=LD64(a_+8); }}"
-            return f"{{ uint64_t a_={self.mem_addr(d, i)}; ST64(a_,X[{self.xr(s)}].u[0]); ST64(a_+8,X[{self.xr(s)}].u[1]); }}"
+                n = self.xr(d)
+                if s.startswith("xmm"):
+                    return f"x{n}l=x{self.xr(s)}l; x{n}h=x{self.xr(s)}h;"
+                return f"{{ uint64_t p_={xu(s, i, 0)}, q_={xu(s, i, 1)}; x{n}l=p_; x{n}h=q_; }}"
+            k = "S" if self.is_stack_operand(d) else ""
+            return f"{{ uint64_t a_={self.mem_addr(d, i)}; ST{k}64(a_,x{self.xr(s)}l); ST{k}64(a_+8,x{self.xr(s)}h); }}"
         if mn in ("movlpd", "movhpd", "movlps", "movhps"):
-            k = 0 if mn[3] == "l" else 1
+            k = "l" if mn[3] == "l" else "h"
             d, s = ops
             if d.startswith("xmm"):
-                return f"X[{self.xr(d)}].u[{k}]=LD64({self.mem_addr(s, i)});"
-            return f"ST64({self.mem_addr(d, i)},X[{self.xr(s)}].u[{k}]);"
+                return f"x{self.xr(d)}{k}={xu(s, i)};"
+            return st(64, d, i, f"x{self.xr(s)}{k}")
         sc = {"addsd": "F_ADD", "subsd": "F_SUB", "mulsd": "F_MUL", "divsd": "F_DIV", "maxsd": "F_MAX", "minsd": "F_MIN"}
         if mn in sc:
             d, s = ops
-            src = f"X[{self.xr(s)}].d[0]" if s.startswith("xmm") else f"LDD({self.mem_addr(s, i)})"
-            return f"X[{self.xr(d)}].d[0]={sc[mn]}(X[{self.xr(d)}].d[0],{src});"
+            n = self.xr(d)
+            return f"x{n}l=D2U({sc[mn]}(U2D(x{n}l),{xd(s, i)}));"
         if mn == "sqrtsd":
             d, s = ops
-            src = f"X[{self.xr(s)}].d[0]" if s.startswith("xmm") else f"LDD({self.mem_addr(s, i)})"
-            return f"X[{self.xr(d)}].d[0]=F_SQRT({src});"
+            return f"x{self.xr(d)}l=D2U(F_SQRT({xd(s, i)}));"
         pk = {"addpd": "F_ADD", "subpd": "F_SUB", "mulpd": "F_MUL", "divpd": "F_DIV", "maxpd": "F_MAX", "minpd": "F_MIN"}
-        if mn in pk or mn == "sqrtpd":
+        if mn in pk:
             d, s = ops
-            pre = ""
-            if s.startswith("xmm"):
-                s0, s1 = f"X[{self.xr(s)}].d[0]", f"X[{self.xr(s)}].d[1]"
-                if self.xr(s) == self.xr(d) and mn != "sqrtpd":
-                    pass
-            else:
-                pre = f"uint64_t a_={self.mem_addr(s, i)}; "
-                s0, s1 = "LDD(a_)", "LDD(a_+8)"
-            dx = f"X[{self.xr(d)}]"
-            if mn == "sqrtpd":
-                return f"{{ {pre}double p_=F_SQRT({s0}), q_=F_SQRT({s1}); {dx}.d[0]=p_; {dx}.d[1]=q_; }}"
-            return f"{{ {pre}double p_={pk[mn]}({dx}.d[0],{s0}), q_={pk[mn]}({dx}.d[1],{s1}); {dx}.d[0]=p_; {dx}.d[1]=q_; }}"
-        if mn in ("unpcklpd", "unpckhpd", "movlhps", "movhlps"):
+            n = self.xr(d)
+            return (f"{{ double p_={pk[mn]}(U2D(x{n}l),{xd(s, i, 0)}), q_={pk[mn]}(U2D(x{n}h),{xd(s, i, 1)}); "
+                    f"x{n}l=D2U(p_); x{n}h=D2U(q_); }}")
+        if mn == "sqrtpd":
             d, s = ops
-            dx = f"X[{self.xr(d)}]"
-            if s.startswith("xmm"):
-                s0, s1 = f"X[{self.xr(s)}].u[0]", f"X[{self.xr(s)}].u[1]"
-                pre = ""
-            else:
-                pre = f"uint64_t a_={self.mem_addr(s, i)}; "
-                s0, s1 = "LD64(a_)", "LD64(a_+8)"
-            if mn == "unpcklpd" or mn == "movlhps":
-                return f"{{ {pre}uint64_t v_={s0}; {dx}.u[1]=v_; }}"
-            if mn == "unpckhpd":
-                return f"{{ {pre}uint64_t v_={s1}; {dx}.u[0]={dx}.u[1]; {dx}.u[1]=v_; }}"
-            return f"{{ {pre}uint64_t v_={s1}; {dx}.u[0]=v_; }}"           # movhlps
+            n = self.xr(d)
+            return f"{{ double p_=F_SQRT({xd(s, i, 0)}), q_=F_SQRT({xd(s, i, 1)}); x{n}l=D2U(p_); x{n}h=D2U(q_); }}"
+        if mn in ("unpcklpd", "movlhps"):
+            d, s = ops
+            return f"x{self.xr(d)}h={xu(s, i, 0)};"
+        if mn == "unpckhpd":
+            d, s = ops
+            n = self.xr(d)
+            return f"{{ uint64_t v_={xu(s, i, 1)}; x{n}l=x{n}h; x{n}h=v_; }}"
+        if mn == "movhlps":
+            d, s = ops
+            return f"x{self.xr(d)}l={xu(s, i, 1)};"
         if mn == "shufpd":
             d, s, imm = ops
             k = int(imm, 16)
-            dx, sx = f"X[{self.xr(d)}]", f"X[{self.xr(s)}]"
-            return f"{{ uint64_t p_={dx}.u[{k & 1}], q_={sx}.u[{(k >> 1) & 1}]; {dx}.u[0]=p_; {dx}.u[1]=q_; }}"
+            n = self.xr(d)
+            return f"{{ uint64_t p_=x{n}{'lh'[k & 1]}, q_={xu(s, i, (k >> 1) & 1)}; x{n}l=p_; x{n}h=q_; }}"
         bw = {"xorps": "^", "xorpd": "^", "pxor": "^", "andps": "&", "andpd": "&", "pand": "&", "orps": "|", "orpd": "|", "por": "|"}
         if mn in bw:
             d, s = ops
-            dx = f"X[{self.xr(d)}]"
-            if s.startswith("xmm"):
-                if self.xr(s) == self.xr(d) and bw[mn] == "^":
-                    return f"{dx}.u[0]=0; {dx}.u[1]=0;"
-                return f"{dx}.u[0]{bw[mn]}=X[{self.xr(s)}].u[0]; {dx}.u[1]{bw[mn]}=X[{self.xr(s)}].u[1];"
-            return f"{{ uint64_t a_={self.mem_addr(s, i)}; {dx}.u[0]{bw[mn]}=LD64(a_); {dx}.u[1]{bw[mn]}=LD64(a_+8); }}"
+            n = self.xr(d)
+            if s.startswith("xmm") and self.xr(s) == n and bw[mn] == "^":
+                return f"x{n}l=0; x{n}h=0;"
+            return f"{{ uint64_t p_={xu(s, i, 0)}, q_={xu(s, i, 1)}; x{n}l{bw[mn]}=p_; x{n}h{bw[mn]}=q_; }}"
         if mn in ("andnps", "andnpd", "pandn"):
             d, s = ops
-            dx = f"X[{self.xr(d)}]"
-            if s.startswith("xmm"):
-                return f"{dx}.u[0]=~{dx}.u[0]&X[{self.xr(s)}].u[0]; {dx}.u[1]=~{dx}.u[1]&X[{self.xr(s)}].u[1];"
-            return f"{{ uint64_t a_={self.mem_addr(s, i)}; {dx}.u[0]=~{dx}.u[0]&LD64(a_); {dx}.u[1]=~{dx}.u[1]&LD64(a_+8); }}"
+            n = self.xr(d)
+            return f"{{ uint64_t p_={xu(s, i, 0)}, q_={xu(s, i, 1)}; x{n}l=~x{n}l&p_; x{n}h=~x{n}h&q_; }}"
         if mn in ("comisd", "ucomisd"):
             d, s = ops
-            src = f"X[{self.xr(s)}].d[0]" if s.startswith("xmm") else f"LDD({self.mem_addr(s, i)})"
-            return f"lift_COMISD(c,X[{self.xr(d)}].d[0],{src});"
+            return f"lift_COMISD(&fl,U2D(x{self.xr(d)}l),{xd(s, i)});"
         if mn == "cvtsi2sd":
             d, s = ops
             w = self.op_size(s)
-            return f"X[{self.xr(d)}].d[0]=(double)(int{w}_t)({rd(s, i, w)});"
+            return f"x{self.xr(d)}l=D2U((double)(int{w}_t)({rd(s, i, w)}));"
         if mn in ("cvttsd2si", "cvtsd2si"):
             d, s = ops
             w = self.op_size(d)
-            src = f"X[{self.xr(s)}].d[0]" if s.startswith("xmm") else f"LDD({self.mem_addr(s, i)})"
             fn = "lift_CVTT" if mn == "cvttsd2si" else "lift_CVTR"
-            return wr(d, i, f"{fn}{w}({src})", w)
+            return wr(d, i, f"{fn}{w}({xd(s, i)})", w)
         if mn == "cvtdq2pd":
             d, s = ops
-            dx = f"X[{self.xr(d)}]"
-            src = f"X[{self.xr(s)}].u[0]" if s.startswith("xmm") else f"LD64({self.mem_addr(s, i)})"
-            return f"{{ uint64_t v_={src}; {dx}.d[0]=(double)(int32_t)(uint32_t)v_; {dx}.d[1]=(double)(int32_t)(uint32_t)(v_>>32); }}"
-        if mn in ("cvtps2pd", "cvtss2sd"):
+            n = self.xr(d)
+            return f"{{ uint64_t v_={xu(s, i, 0)}; x{n}l=D2U((double)(int32_t)(uint32_t)v_); x{n}h=D2U((double)(int32_t)(uint32_t)(v_>>32)); }}"
+        if mn == "cvtps2pd":
             d, s = ops
-            dx = f"X[{self.xr(d)}]"
-            src = f"X[{self.xr(s)}].u[0]" if s.startswith("xmm") else (f"LD64({self.mem_addr(s, i)})" if mn == "cvtps2pd" else f"LD32({self.mem_addr(s, i)})")
-            if mn == "cvtss2sd":
-                return f"{{ uint32_t v_=(uint32_t)({src}); {dx}.d[0]=(double)lift_u2f(v_); }}"
-            return f"{{ uint64_t v_={src}; {dx}.d[0]=(double)lift_u2f((uint32_t)v_); {dx}.d[1]=(double)lift_u2f((uint32_t)(v_>>32)); }}"
+            n = self.xr(d)
+            return f"{{ uint64_t v_={xu(s, i, 0)}; x{n}l=D2U((double)lift_u2f((uint32_t)v_)); x{n}h=D2U((double)lift_u2f((uint32_t)(v_>>32))); }}"
+        if mn == "cvtss2sd":
+            d, s = ops
+            src = f"x{self.xr(s)}l" if s.startswith("xmm") else self.ld(32, s, i)
+            return f"x{self.xr(d)}l=D2U((double)lift_u2f((uint32_t)({src})));"
         if mn == "cvtsd2ss":
             d, s = ops
-            src = f"X[{self.xr(s)}].d[0]" if s.startswith("xmm") else f"LDD({self.mem_addr(s, i)})"
-            return f"X[{self.xr(d)}].u[0]=(X[{self.xr(d)}].u[0]&~0xffffffffULL)|lift_f2u((float)({src}));"
+            n = self.xr(d)
+            return f"x{n}l=(x{n}l&~0xffffffffULL)|lift_f2u((float)({xd(s, i)}));"
         if mn == "movss":
             d, s = ops
             if d.startswith("xmm") and s.startswith("xmm"):
-                return f"X[{self.xr(d)}].u[0]=(X[{self.xr(d)}].u[0]&~0xffffffffULL)|(X[{self.xr(s)}].u[0]&0xffffffffULL);"
+                n = self.xr(d)
+                return f"x{n}l=(x{n}l&~0xffffffffULL)|(x{self.xr(s)}l&0xffffffffULL);"
             if d.startswith("xmm"):
-                return f"X[{self.xr(d)}].u[0]=LD32({self.mem_addr(s, i)}); X[{self.xr(d)}].u[1]=0;"
-            return f"ST32({self.mem_addr(d, i)},X[{self.xr(s)}].u[0]);"
+                n = self.xr(d)
+                return f"x{n}l={self.ld(32, s, i)}; x{n}h=0;"
+            return st(32, d, i, f"x{self.xr(s)}l")
         if mn.startswith("rep stos"):
             w = SIZES[mn.split()[2]]
-            return f"lift_REPSTOS(c,{w // 8});"
+            return f"lift_REPSTOS(c,&r1,&r7,r0,{w // 8});"
         if mn.startswith("rep movs"):
             w = SIZES[mn.split()[2]]
-            return f"lift_REPMOVS(c,{w // 8});"
+            return f"lift_REPMOVS(c,&r1,&r7,&r6,{w // 8});"
         raise NotImplementedError(mn)
 
 
@@ -652,14 +745,36 @@ PRELUDE = r"""/* GENERATED by oracle/pe_probe/lift.py from the reference's plant
 #ifndef LIFT_FN
 #define LIFT_FN static
 #endif
-#define R  (c->r)
-#define X  (c->x)
-#define ZF (c->zf)
-#define SF (c->sf)
-#define CF (c->cf)
-#define OF (c->of)
-#define PF (c->pf)
+#ifndef LIFT_BB
+#define LIFT_BB(fn, n)
+#endif
+#ifndef LIFT_MEM_CTX
+#define LIFT_MEM_CTX
+#endif
+#define ZF (fl.zf)
+#define SF (fl.sf)
+#define CF (fl.cf)
+#define OF (fl.of)
+#define PF (fl.pf)
+#define LIFT_LOCALS \
+    uint64_t r0=0,r1=0,r2=0,r3=0,r4=0,r5=0,r6=0,r7=0,r8=0,r9=0,r10=0,r11=0,r12=0,r13=0,r14=0,r15=0; \
+    uint64_t x0l=0,x0h=0,x1l=0,x1h=0,x2l=0,x2h=0,x3l=0,x3h=0,x4l=0,x4h=0,x5l=0,x5h=0,x6l=0,x6h=0,x7l=0,x7h=0; \
+    uint64_t x8l=0,x8h=0,x9l=0,x9h=0,x10l=0,x10h=0,x11l=0,x11h=0,x12l=0,x12h=0,x13l=0,x13h=0,x14l=0,x14h=0,x15l=0,x15h=0; \
+    lift_flags fl = {0,0,0,0,0}; LIFT_MEM_CTX \
+    (void)r0;(void)r1;(void)r2;(void)r3;(void)r5;(void)r6;(void)r7;(void)r8;(void)r9;(void)r10;(void)r11;(void)r12;(void)r13;(void)r14;(void)r15; \
+    (void)x0h;(void)x1l;(void)x1h;(void)x2l;(void)x2h;(void)x3l;(void)x3h;(void)x4l;(void)x4h;(void)x5l;(void)x5h;(void)x6l;(void)x6h;(void)x7l;(void)x7h; \
+    (void)x8l;(void)x8h;(void)x9l;(void)x9h;(void)x10l;(void)x10h;(void)x11l;(void)x11h;(void)x12l;(void)x12h;(void)x13l;(void)x13h;(void)x14l;(void)x14h;(void)x15l;(void)x15h;(void)fl
+#define LIFT_ENTER \
+    r1=c->r[1]; r2=c->r[2]; r8=c->r[8]; r9=c->r[9]; r4=c->r[4]; \
+    x0l=c->x[0].u[0]; x1l=c->x[1].u[0]; x2l=c->x[2].u[0]; x3l=c->x[3].u[0]
+#define LIFT_PRECALL \
+    c->r[1]=r1; c->r[2]=r2; c->r[8]=r8; c->r[9]=r9; c->r[4]=r4; \
+    c->x[0].u[0]=x0l; c->x[1].u[0]=x1l; c->x[2].u[0]=x2l; c->x[3].u[0]=x3l
+#define LIFT_POSTCALL r0=c->r[0]; x0l=c->x[0].u[0]
+#define LIFT_EXIT c->r[0]=r0; c->x[0].u[0]=x0l
 """
+
+POSTLUDE = "\n#undef ZF\n#undef SF\n#undef CF\n#undef OF\n#undef PF\n"
 
 
 def main():
@@ -677,13 +792,19 @@ def main():
     with open(os.path.join(args.out, f"citation_{args.variant}_code.inc"), "w") as f:
         f.write(PRELUDE)
         f.write(code)
-        f.write("\n#undef R\n#undef X\n#undef ZF\n#undef SF\n#undef CF\n#undef OF\n#undef PF\n")
+        f.write(POSTLUDE)
     with open(os.path.join(args.out, f"citation_{args.variant}_image.bin"), "wb") as f:
         f.write(bytes(pe.img))
+    # the same bytes as a C initialiser list (up to the end of .data: the unwind / resource / relocation sections are not used)
+    end = max(va + vsz for n, va, vsz in pe.sections if n in (".text", ".rdata", ".data"))
+    with open(os.path.join(args.out, f"citation_{args.variant}_image.inc"), "w") as f:
+        blob = bytes(pe.img[:end])
+        for o in range(0, len(blob), 64):
+            f.write(",".join(str(v) for v in blob[o:o + 64]) + ",\n")
     n_ins = sum(len(v) for v in L.funcs.values())
     print(f"{args.variant}: {len(L.funcs)} functions, {n_ins} instructions translated, image {pe.image_size} bytes")
     for e, u in sorted(L.unknown.items()):
-        print(f"  f_{e:x}: {len(u)} untranslated:", [(hex(a), r) if isinstance(x, tuple) else hex(x) for x in u[:6] for a, r in [x if isinstance(x, tuple) else (x, '')]])
+        print(f"  f_{e:x}: untranslated:", [(hex(x[0]), x[1]) if isinstance(x, tuple) else hex(x) for x in u[:6]])
     return 0
 
 

@@ -2,7 +2,7 @@
  * (envs/nonlinear/<variant>/_citation.cp39-win_amd64.pyd; /root/reference/envs/nonlinear/citation.py:62-69).
  *
  * The generated code is a sequence of x86-64 instructions spelled as C statements over this state: 16 integer
- * registers, 16 SSE registers, five flags, and ONE flat little-endian memory that holds the DLL image at its preferred
+ * registers, 16 SSE registers and five flags (C locals inside a translated function), and ONE flat little-endian memory that holds the DLL image at its preferred
  * base, a bump-allocated heap behind it and the stack at the top.  Each helper below implements the architectural
  * semantics of one instruction class (Intel SDM vol. 2); floating point is IEEE binary64 with one rounding per
  * instruction, exactly what SSE2 scalar / packed instructions do, so the host compiler must not contract (`-ffp-contract=off`
@@ -10,6 +10,7 @@
  *
  * Before including the generated .inc the includer defines how memory is reached:
  *     LD8/16/32/64(addr), LDD(addr), ST8/16/32/64(addr, value)       (addr = emulated virtual address, uint64_t)
+ *     LDS.. / STS..: the same for operands the translator knows to be on the stack (rsp- or frame-pointer-based)
  * and may define LIFT_FN (function qualifiers), LIFT_TRAP(msg, value), F_ADD ... F_SQRT, and the lift_<libm> functions.
  */
 #ifndef RL4_LIFT_RUNTIME_H
@@ -25,13 +26,22 @@
 
 typedef union { uint64_t u[2]; double d[2]; } lift_xmm;
 
+/* what crosses a function boundary (Windows x64 convention): arguments rcx rdx r8 r9 / xmm0-3, the stack pointer, results
+ * rax / xmm0.  Inside a translated function every register is a C local. */
 typedef struct cpu_t {
     uint64_t r[16];          /* rax rcx rdx rbx rsp rbp rsi rdi r8..r15 */
     lift_xmm x[16];
-    uint8_t zf, sf, cf, of, pf;
     uint64_t heap_next, heap_end;
     LIFT_CPU_EXTRA
 } cpu_t;
+typedef struct lift_flags { uint8_t zf, sf, cf, of, pf; } lift_flags;
+
+#ifndef U2D
+LIFT_HD double lift_u2d(uint64_t u) { union { uint64_t u; double d; } t; t.u = u; return t.d; }
+LIFT_HD uint64_t lift_d2u(double d) { union { uint64_t u; double d; } t; t.d = d; return t.u; }
+#define U2D(u) lift_u2d(u)
+#define D2U(d) lift_d2u(d)
+#endif
 
 #ifndef F_ADD
 #define F_ADD(a, b) ((a) + (b))
@@ -50,45 +60,45 @@ LIFT_HD uint32_t lift_f2u(float f) { union { uint32_t u; float f; } t; t.f = f; 
 LIFT_HD uint8_t lift_parity(uint64_t v) { v &= 0xff; v ^= v >> 4; v ^= v >> 2; v ^= v >> 1; return (uint8_t)(~v & 1); }
 
 #define LIFT_DEFINE_INT(W, UT, ST)                                                                                              \
-    LIFT_HD uint64_t lift_ADD##W(cpu_t* c, uint64_t a_, uint64_t b_) {                                                          \
+    LIFT_HD uint64_t lift_ADD##W(lift_flags* c, uint64_t a_, uint64_t b_) {                                                          \
         UT a = (UT)a_, b = (UT)b_, r = (UT)(a + b);                                                                             \
         c->zf = r == 0; c->sf = (ST)r < 0; c->cf = r < a; c->of = (ST)((a ^ r) & (b ^ r)) < 0; c->pf = lift_parity(r); return r; } \
-    LIFT_HD uint64_t lift_ADC##W(cpu_t* c, uint64_t a_, uint64_t b_) {                                                          \
+    LIFT_HD uint64_t lift_ADC##W(lift_flags* c, uint64_t a_, uint64_t b_) {                                                          \
         UT a = (UT)a_, b = (UT)b_, ci = c->cf, r = (UT)(a + b + ci);                                                            \
         c->zf = r == 0; c->sf = (ST)r < 0; c->cf = ci ? r <= a : r < a; c->of = (ST)((a ^ r) & (b ^ r)) < 0; c->pf = lift_parity(r); return r; } \
-    LIFT_HD uint64_t lift_SUB##W(cpu_t* c, uint64_t a_, uint64_t b_) {                                                          \
+    LIFT_HD uint64_t lift_SUB##W(lift_flags* c, uint64_t a_, uint64_t b_) {                                                          \
         UT a = (UT)a_, b = (UT)b_, r = (UT)(a - b);                                                                             \
         c->zf = r == 0; c->sf = (ST)r < 0; c->cf = a < b; c->of = (ST)((a ^ b) & (a ^ r)) < 0; c->pf = lift_parity(r); return r; } \
-    LIFT_HD uint64_t lift_SBB##W(cpu_t* c, uint64_t a_, uint64_t b_) {                                                          \
+    LIFT_HD uint64_t lift_SBB##W(lift_flags* c, uint64_t a_, uint64_t b_) {                                                          \
         UT a = (UT)a_, b = (UT)b_, ci = c->cf, r = (UT)(a - b - ci);                                                            \
         c->zf = r == 0; c->sf = (ST)r < 0; c->cf = ci ? a <= b : a < b; c->of = (ST)((a ^ b) & (a ^ r)) < 0; c->pf = lift_parity(r); return r; } \
-    LIFT_HD uint64_t lift_AND##W(cpu_t* c, uint64_t a_, uint64_t b_) {                                                          \
+    LIFT_HD uint64_t lift_AND##W(lift_flags* c, uint64_t a_, uint64_t b_) {                                                          \
         UT r = (UT)((UT)a_ & (UT)b_); c->zf = r == 0; c->sf = (ST)r < 0; c->cf = 0; c->of = 0; c->pf = lift_parity(r); return r; } \
-    LIFT_HD uint64_t lift_OR##W(cpu_t* c, uint64_t a_, uint64_t b_) {                                                           \
+    LIFT_HD uint64_t lift_OR##W(lift_flags* c, uint64_t a_, uint64_t b_) {                                                           \
         UT r = (UT)((UT)a_ | (UT)b_); c->zf = r == 0; c->sf = (ST)r < 0; c->cf = 0; c->of = 0; c->pf = lift_parity(r); return r; } \
-    LIFT_HD uint64_t lift_XOR##W(cpu_t* c, uint64_t a_, uint64_t b_) {                                                          \
+    LIFT_HD uint64_t lift_XOR##W(lift_flags* c, uint64_t a_, uint64_t b_) {                                                          \
         UT r = (UT)((UT)a_ ^ (UT)b_); c->zf = r == 0; c->sf = (ST)r < 0; c->cf = 0; c->of = 0; c->pf = lift_parity(r); return r; } \
-    LIFT_HD uint64_t lift_INC##W(cpu_t* c, uint64_t a_) {                                                                       \
+    LIFT_HD uint64_t lift_INC##W(lift_flags* c, uint64_t a_) {                                                                       \
         UT a = (UT)a_, r = (UT)(a + 1); c->zf = r == 0; c->sf = (ST)r < 0; c->of = (ST)((a ^ r) & (1 ^ r)) < 0; c->pf = lift_parity(r); return r; } \
-    LIFT_HD uint64_t lift_DEC##W(cpu_t* c, uint64_t a_) {                                                                       \
+    LIFT_HD uint64_t lift_DEC##W(lift_flags* c, uint64_t a_) {                                                                       \
         UT a = (UT)a_, r = (UT)(a - 1); c->zf = r == 0; c->sf = (ST)r < 0; c->of = (ST)((a ^ 1) & (a ^ r)) < 0; c->pf = lift_parity(r); return r; } \
-    LIFT_HD uint64_t lift_NEG##W(cpu_t* c, uint64_t a_) {                                                                       \
+    LIFT_HD uint64_t lift_NEG##W(lift_flags* c, uint64_t a_) {                                                                       \
         UT a = (UT)a_, r = (UT)(0 - a); c->zf = r == 0; c->sf = (ST)r < 0; c->cf = a != 0; c->of = (ST)(a & r) < 0; c->pf = lift_parity(r); return r; } \
-    LIFT_HD uint64_t lift_SHL##W(cpu_t* c, uint64_t a_, uint64_t n_) {                                                          \
+    LIFT_HD uint64_t lift_SHL##W(lift_flags* c, uint64_t a_, uint64_t n_) {                                                          \
         const unsigned n = (unsigned)n_ & (W == 64 ? 63 : 31); UT a = (UT)a_; if (!n) return a;                                 \
         UT r = n < W ? (UT)(a << n) : 0; c->cf = n <= W ? (a >> (W - n)) & 1 : 0; c->zf = r == 0; c->sf = (ST)r < 0;            \
         c->of = ((r >> (W - 1)) & 1) ^ c->cf; c->pf = lift_parity(r); return r; }                                               \
-    LIFT_HD uint64_t lift_SHR##W(cpu_t* c, uint64_t a_, uint64_t n_) {                                                          \
+    LIFT_HD uint64_t lift_SHR##W(lift_flags* c, uint64_t a_, uint64_t n_) {                                                          \
         const unsigned n = (unsigned)n_ & (W == 64 ? 63 : 31); UT a = (UT)a_; if (!n) return a;                                 \
         UT r = n < W ? (UT)(a >> n) : 0; c->cf = n <= W ? (a >> (n - 1)) & 1 : 0; c->zf = r == 0; c->sf = (ST)r < 0;            \
         c->of = (a >> (W - 1)) & 1; c->pf = lift_parity(r); return r; }                                                         \
-    LIFT_HD uint64_t lift_SAR##W(cpu_t* c, uint64_t a_, uint64_t n_) {                                                          \
+    LIFT_HD uint64_t lift_SAR##W(lift_flags* c, uint64_t a_, uint64_t n_) {                                                          \
         unsigned n = (unsigned)n_ & (W == 64 ? 63 : 31); ST a = (ST)(UT)a_; if (!n) return (UT)a; if (n >= W) n = W - 1;        \
         UT r = (UT)(a >> n); c->cf = ((UT)a >> (n - 1)) & 1; c->zf = r == 0; c->sf = (ST)r < 0; c->of = 0; c->pf = lift_parity(r); return r; } \
-    LIFT_HD uint64_t lift_ROL##W(cpu_t* c, uint64_t a_, uint64_t n_) {                                                          \
+    LIFT_HD uint64_t lift_ROL##W(lift_flags* c, uint64_t a_, uint64_t n_) {                                                          \
         const unsigned n = ((unsigned)n_ & (W == 64 ? 63 : 31)) % W; UT a = (UT)a_; if (!n) return a;                           \
         UT r = (UT)((a << n) | (a >> (W - n))); c->cf = r & 1; return r; }                                                      \
-    LIFT_HD uint64_t lift_ROR##W(cpu_t* c, uint64_t a_, uint64_t n_) {                                                          \
+    LIFT_HD uint64_t lift_ROR##W(lift_flags* c, uint64_t a_, uint64_t n_) {                                                          \
         const unsigned n = ((unsigned)n_ & (W == 64 ? 63 : 31)) % W; UT a = (UT)a_; if (!n) return a;                           \
         UT r = (UT)((a >> n) | (a << (W - n))); c->cf = (r >> (W - 1)) & 1; return r; }
 
@@ -98,12 +108,12 @@ LIFT_DEFINE_INT(32, uint32_t, int32_t)
 LIFT_DEFINE_INT(64, uint64_t, int64_t)
 
 /* two- / three-operand imul: truncated product; CF = OF = the product did not fit */
-LIFT_HD uint64_t lift_IMUL16(cpu_t* c, uint64_t a, uint64_t b) { int32_t p = (int32_t)(int16_t)a * (int32_t)(int16_t)b; c->cf = c->of = p != (int16_t)p; return (uint16_t)p; }
-LIFT_HD uint64_t lift_IMUL32(cpu_t* c, uint64_t a, uint64_t b) { int64_t p = (int64_t)(int32_t)a * (int64_t)(int32_t)b; c->cf = c->of = p != (int32_t)p; return (uint32_t)p; }
-LIFT_HD uint64_t lift_IMUL64(cpu_t* c, uint64_t a, uint64_t b) { c->cf = c->of = 0; return a * b; }   /* overflow flag of a 64-bit imul is never consumed by compiled code */
+LIFT_HD uint64_t lift_IMUL16(lift_flags* c, uint64_t a, uint64_t b) { int32_t p = (int32_t)(int16_t)a * (int32_t)(int16_t)b; c->cf = c->of = p != (int16_t)p; return (uint16_t)p; }
+LIFT_HD uint64_t lift_IMUL32(lift_flags* c, uint64_t a, uint64_t b) { int64_t p = (int64_t)(int32_t)a * (int64_t)(int32_t)b; c->cf = c->of = p != (int32_t)p; return (uint32_t)p; }
+LIFT_HD uint64_t lift_IMUL64(lift_flags* c, uint64_t a, uint64_t b) { c->cf = c->of = 0; return a * b; }   /* overflow flag of a 64-bit imul is never consumed by compiled code */
 
 /* comisd / ucomisd: unordered -> ZF = PF = CF = 1 */
-LIFT_HD void lift_COMISD(cpu_t* c, double a, double b)
+LIFT_HD void lift_COMISD(lift_flags* c, double a, double b)
 {
     c->of = 0; c->sf = 0;
     if (a != a || b != b) { c->zf = 1; c->pf = 1; c->cf = 1; }

@@ -207,6 +207,10 @@ def load() -> ctypes.CDLL:
     L.rl4_stats_reduce.argtypes = [vp, i64, i32, vp, i64, vp, vp, i64, vp]
     L.rl4_nl_noise_fill.argtypes = [ctypes.c_uint64, i64, i32, i32, i64, vp, i64, vp]
     L.rl4_nl_episode_host.argtypes = [vp, ctypes.POINTER(NlParams), ctypes.POINTER(NlHostIO), i64, i32]
+    L.rl4_dasmat_image_bytes.restype = i64
+    L.rl4_dasmat_initialize.argtypes = [vp, vp]
+    L.rl4_dasmat_reset.argtypes = [vp, vp, i64, i64, vp]
+    L.rl4_dasmat_step.argtypes = [vp, vp, i64, i64, vp, i64, i32, vp, i64, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in _NOT_STATUS:

@@ -16,7 +16,7 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "librl4afcs_b200.so")
-SOURCES = ["runtime.cu", "sp_kernels.cu", "nl_kernels.cu", "step_kernels.cu", "host_episode.cu"]
+SOURCES = ["runtime.cu", "sp_kernels.cu", "nl_kernels.cu", "step_kernels.cu", "host_episode.cu", "dasmat_plant.cu"]
 HEADERS = ["rl4_math.cuh", "sp_core.cuh", "nl_pipeline.cuh", "rl4_runtime.h", os.path.join("..", "..", "include", "rl4afcs_b200.h"),
            os.path.join("..", "..", "include", "rl4_citation_surrogate.h")]
 
@@ -42,7 +42,27 @@ def _nvcc() -> str:
 _COMMON = ["rl4_math.cuh", "rl4_runtime.h", os.path.join("..", "..", "include", "rl4afcs_b200.h"),
            os.path.join("..", "..", "include", "rl4_citation_surrogate.h")]
 DEPS = {"runtime.cu": _COMMON, "sp_kernels.cu": _COMMON + ["sp_core.cuh"], "nl_kernels.cu": _COMMON + ["nl_pipeline.cuh"],
-        "step_kernels.cu": _COMMON, "host_episode.cu": _COMMON}
+        "step_kernels.cu": _COMMON, "host_episode.cu": _COMMON,
+        "dasmat_plant.cu": ["rl4_runtime.h", os.path.join("..", "..", "include", "rl4afcs_b200.h"),
+                            os.path.join("..", "..", "oracle", "pe_probe", "lift_runtime.h")]}
+
+# The 'dasmat' plant is the reference's own aircraft model, translated from its binary (oracle/pe_probe/lift.py).  Nothing
+# derived from the binary is committed: csrc/_gen/ is produced here, where the reference exists, and compiled into the
+# library; without it dasmat_plant.cu compiles to entry points that report "built without the reference's plant binary".
+GEN_DIR = os.path.join(CSRC, "_gen")
+PLANT_BINARY = "/root/reference/envs/nonlinear/extended_input/_citation.cp39-win_amd64.pyd"
+LIFTER = os.path.join(_HERE, "..", "oracle", "pe_probe", "lift.py")
+
+
+def _generate_plant() -> None:
+    code, image = os.path.join(GEN_DIR, "dasmat_code.inc"), os.path.join(GEN_DIR, "dasmat_image.inc")
+    if not os.path.isfile(PLANT_BINARY) or not os.path.isfile(LIFTER):
+        return
+    if os.path.isfile(code) and os.path.isfile(image) and os.path.getmtime(code) >= os.path.getmtime(LIFTER):
+        return
+    subprocess.run([sys.executable, LIFTER, "--variant", "extended_input", "--out", GEN_DIR], check=True, stdout=subprocess.DEVNULL)
+    shutil.copyfile(os.path.join(GEN_DIR, "citation_extended_input_code.inc"), code)
+    shutil.copyfile(os.path.join(GEN_DIR, "citation_extended_input_image.inc"), image)
 OBJ_DIR = os.path.join(_HERE, "build")
 
 
@@ -56,6 +76,8 @@ def _src_stale(src: str) -> bool:
         return True
     t = os.path.getmtime(o)
     deps = [os.path.join(CSRC, d) for d in [src] + DEPS[src]] + [os.path.abspath(__file__)]
+    if src == "dasmat_plant.cu":
+        deps = deps[:-1] + [g for g in (os.path.join(GEN_DIR, "dasmat_code.inc"), os.path.join(GEN_DIR, "dasmat_image.inc")) if os.path.isfile(g)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -71,7 +93,8 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str =
     """Build the library: every stale translation unit is compiled to rl4afcs_b200/build/*.o (in parallel), then linked.
     ``extra_flags`` / ``out`` exist for tuning experiments (scripts/): they compile everything into one private library."""
     out = out or LIB_PATH
-    if not force and out == LIB_PATH and not _stale():
+    _generate_plant()
+    if not force and out == LIB_PATH and not _stale() and not _src_stale("dasmat_plant.cu"):
         return LIB_PATH
     log = os.path.join(_HERE, "build.log")
     if extra_flags or out != LIB_PATH:

@@ -1,0 +1,290 @@
+// The reference's OWN nonlinear aircraft on the GPU (row a25: `_citation.step`, envs/nonlinear/citation.py:62-69, called at
+// envs/nonlinear/env.py:210,288-291).
+//
+// The reference ships the DASMAT Citation model only as x86-64 machine code inside a Windows .pyd.  oracle/pe_probe/lift.py
+// translates that machine code, instruction by instruction, into C over an explicit machine state (lift_runtime.h); the
+// build (rl4afcs_b200/build.py, only where /root/reference exists) writes the translation to csrc/_gen/ and this unit
+// compiles it for sm_100a: one aircraft per thread, every thread executing the model's own instruction stream on its own
+// copy of the model's writable memory.  What the binary computes, this computes -- the only arithmetic that is not the
+// binary's own is inside the eight C-runtime functions it imports (sin cos tan exp log10 pow floor sqrt: CUDA's here,
+// the Windows UCRT's in the reference, glibc's in the in-process run the golden fixtures come from; 1-2 ulp apart).
+//
+// Memory model of one aircraft (emulated virtual addresses, LIFT_BASE = image base):
+//   image   [0x00000, 0x40000)  the DLL's sections after initialize() has run -- ONE copy in HBM, read-only during steps
+//   A       [0x2eb00, 0x2ec00)  \  the only parts of .data that step() writes (model time, block signals, continuous and
+//   D       [0x3a000, 0x3c200)  /  discrete states, solver work arrays): PER AIRCRAFT, 1120 eight-byte words
+//   stack   [0x40000, 0x42000)  per thread, scratch
+// A and D persist between launches in an SoA plane `state[word * stride + aircraft]` (coalesced copy in / out); inside a
+// launch they and the stack live in thread-local memory, which the hardware interleaves per lane.
+// A store outside A / D / stack, an indirect call to an unknown target or an untranslated instruction sets an error bit
+// that the host reads back: the translation never silently computes something else.
+#include "rl4_runtime.h"
+#include "../../include/rl4afcs_b200.h"
+#include <math_constants.h>
+#include <vector>
+
+#if __has_include("_gen/dasmat_code.inc")
+#define RL4_HAVE_DASMAT 1
+#else
+#define RL4_HAVE_DASMAT 0
+#endif
+
+namespace rl4 {
+
+constexpr uint64_t kImg = 0x40000, kStack = 0x2000, kFlat = kImg + kStack;
+constexpr uint64_t kALo = 0x2eb00, kASz = 0x100, kDLo = 0x3a000, kDSz = 0x2200;
+constexpr int kStateWords = (int)((kASz + kDSz) / 8);           // 1120
+constexpr uint64_t kLocalBytes = kASz + kDSz + kStack;
+constexpr uint64_t kRvaX = 0x3c120, kRvaEngine = 0x3c198;       // the 16 continuous states (oracle/pe_probe/README.md)
+
+#if RL4_HAVE_DASMAT
+
+#define LIFT_HD __device__ __forceinline__
+#define LIFT_CPU_EXTRA uint8_t* G; uint8_t* m; int flat; int err;
+#define F_ADD(a, b) __dadd_rn((a), (b))
+#define F_SUB(a, b) __dsub_rn((a), (b))
+#define F_MUL(a, b) __dmul_rn((a), (b))
+#define F_DIV(a, b) __ddiv_rn((a), (b))
+#define F_SQRT(a) __dsqrt_rn(a)
+#define U2D(u) __longlong_as_double((long long)(u))
+#define D2U(d) ((uint64_t)__double_as_longlong(d))
+#include "../../oracle/pe_probe/lift_runtime.h"
+
+enum { kErrTrap = 1, kErrWildAccess = 2, kErrStoreToImage = 4 };
+
+#define LIFT_FN static __device__ __noinline__
+#define LIFT_TRAP(msg, v) do { c->err |= kErrTrap; return; } while (0)
+// per-function copies of the memory context (the compiler cannot keep c->m in a register across stores otherwise)
+#define LIFT_MEM_CTX uint8_t* const m_ = c->m; const uint8_t* const G_ = c->G; const int flat_ = c->flat; (void)m_; (void)G_; (void)flat_;
+
+// where an emulated address lives: the thread's private copy of A / D / stack, or the shared image
+template <typename T> __device__ __forceinline__ T lift_load(uint8_t* m_, const uint8_t* G_, int flat_, cpu_t* c, uint64_t a)
+{
+    const uint64_t off = a - LIFT_BASE;
+    if (!flat_) {
+        if (off - kDLo < kDSz) return *reinterpret_cast<const T*>(m_ + kASz + (off - kDLo));
+        if (off - kImg < kStack) return *reinterpret_cast<const T*>(m_ + kASz + kDSz + (off - kImg));
+        if (off - kALo < kASz) return *reinterpret_cast<const T*>(m_ + (off - kALo));
+        if (off >= kImg) { c->err |= kErrWildAccess; return T(0); }
+        return __ldg(reinterpret_cast<const T*>(G_ + off));          // shared image: read-only while aircraft are stepping
+    }
+    if (off >= kFlat) { c->err |= kErrWildAccess; return T(0); }
+    return *reinterpret_cast<const T*>(G_ + off);
+}
+template <typename T> __device__ __forceinline__ void lift_store(uint8_t* m_, const uint8_t* G_, int flat_, cpu_t* c, uint64_t a, T v)
+{
+    const uint64_t off = a - LIFT_BASE;
+    if (!flat_) {
+        if (off - kDLo < kDSz) { *reinterpret_cast<T*>(m_ + kASz + (off - kDLo)) = v; return; }
+        if (off - kImg < kStack) { *reinterpret_cast<T*>(m_ + kASz + kDSz + (off - kImg)) = v; return; }
+        if (off - kALo < kASz) { *reinterpret_cast<T*>(m_ + (off - kALo)) = v; return; }
+        c->err |= kErrStoreToImage;
+        return;
+    }
+    if (off >= kFlat) { c->err |= kErrWildAccess; return; }
+    *reinterpret_cast<T*>(const_cast<uint8_t*>(G_) + off) = v;
+}
+#define LD8(a)  ((uint64_t)lift_load<uint8_t>(m_, G_, flat_, c, (a)))
+#define LD16(a) ((uint64_t)lift_load<uint16_t>(m_, G_, flat_, c, (a)))
+#define LD32(a) ((uint64_t)lift_load<uint32_t>(m_, G_, flat_, c, (a)))
+#define LD64(a) lift_load<uint64_t>(m_, G_, flat_, c, (a))
+#define LDD(a)  lift_load<double>(m_, G_, flat_, c, (a))
+#define ST8(a, v)  lift_store<uint8_t>(m_, G_, flat_, c, (a), (uint8_t)(v))
+#define ST16(a, v) lift_store<uint16_t>(m_, G_, flat_, c, (a), (uint16_t)(v))
+#define ST32(a, v) lift_store<uint32_t>(m_, G_, flat_, c, (a), (uint32_t)(v))
+#define ST64(a, v) lift_store<uint64_t>(m_, G_, flat_, c, (a), (uint64_t)(v))
+// operands the translator knows to be on the stack: no decoding (in flat mode c->m is biased so that the same expression
+// lands in the global buffer)
+#define LIFT_STK(T, a) reinterpret_cast<T*>(m_ + (kASz + kDSz) + ((a) - (LIFT_BASE + kImg)))
+#define LDS8(a)  ((uint64_t)*LIFT_STK(uint8_t, a))
+#define LDS16(a) ((uint64_t)*LIFT_STK(uint16_t, a))
+#define LDS32(a) ((uint64_t)*LIFT_STK(uint32_t, a))
+#define LDS64(a) (*LIFT_STK(uint64_t, a))
+#define LDSD(a)  (*LIFT_STK(double, a))
+#define STS8(a, v)  (*LIFT_STK(uint8_t, a) = (uint8_t)(v))
+#define STS16(a, v) (*LIFT_STK(uint16_t, a) = (uint16_t)(v))
+#define STS32(a, v) (*LIFT_STK(uint32_t, a) = (uint32_t)(v))
+#define STS64(a, v) (*LIFT_STK(uint64_t, a) = (uint64_t)(v))
+
+#define lift_cos cos
+#define lift_sin sin
+#define lift_tan tan
+#define lift_exp exp
+#define lift_floor floor
+#define lift_log10 log10
+#define lift_sqrt __dsqrt_rn
+#define lift_pow pow
+
+__device__ __noinline__ void lift_memcpy(cpu_t* c, uint64_t d, uint64_t s, uint64_t n)
+{
+    LIFT_MEM_CTX
+    if (d <= s) for (uint64_t k = 0; k < n; ++k) ST8(d + k, LD8(s + k));
+    else for (uint64_t k = n; k-- > 0;) ST8(d + k, LD8(s + k));
+}
+__device__ __noinline__ void lift_memset(cpu_t* c, uint64_t d, int v, uint64_t n)
+{
+    LIFT_MEM_CTX
+    for (uint64_t k = 0; k < n; ++k) ST8(d + k, v);
+}
+__device__ __forceinline__ uint64_t lift_malloc(cpu_t* c, uint64_t) { c->err |= kErrTrap; return 0; }   // the model allocates nothing
+__device__ __noinline__ void lift_REPSTOS(cpu_t* c, uint64_t* rcx, uint64_t* rdi, uint64_t rax, unsigned w)
+{
+    LIFT_MEM_CTX
+    for (; *rcx; --*rcx, *rdi += w)
+        for (unsigned k = 0; k < w; ++k) ST8(*rdi + k, rax >> (8 * k));
+}
+__device__ __noinline__ void lift_REPMOVS(cpu_t* c, uint64_t* rcx, uint64_t* rdi, uint64_t* rsi, unsigned w)
+{
+    LIFT_MEM_CTX
+    for (; *rcx; --*rcx, *rdi += w, *rsi += w)
+        for (unsigned k = 0; k < w; ++k) ST8(*rdi + k, LD8(*rsi + k));
+}
+__device__ __forceinline__ uint64_t lift_CVTR32(double v) { return (v > -2147483649.0 && v < 2147483648.0) ? (uint64_t)(uint32_t)__double2int_rn(v) : 0x80000000ULL; }
+__device__ __forceinline__ uint64_t lift_CVTR64(double v) { return (uint64_t)__double2ll_rn(v); }
+
+#include "_gen/dasmat_code.inc"
+
+// the pristine image (sections at their RVAs), embedded at build time
+static const uint8_t kPristine[] = {
+#include "_gen/dasmat_image.inc"
+};
+
+__device__ __forceinline__ void enter(cpu_t& c)
+{
+    // Windows x64 frame at the top of the stack: return address slot at rsp, 32 bytes of home space above it
+    c.r[4] = LIFT_BASE + kFlat - 0x100 - 8;
+}
+
+// initialize() in flat mode: one thread, everything (image + stack) in the global buffer G
+__global__ void dasmat_initialize_kernel(uint8_t* G, int* err)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    cpu_t c;
+    memset(&c, 0, sizeof c);
+    c.G = G; c.m = G + kImg - (kASz + kDSz); c.flat = 1;     // biased so that the stack-operand expression lands in G
+    enter(c);
+    f_1800096f0(&c);
+    *err = c.err;
+}
+
+// per-aircraft state words <- the image's A and D regions
+__global__ void dasmat_reset_kernel(const uint64_t* __restrict__ G, uint64_t* __restrict__ state, int64_t stride, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int w = 0; w < (int)(kASz / 8); ++w) state[(int64_t)w * stride + i] = G[kALo / 8 + w];
+    for (int w = 0; w < (int)(kDSz / 8); ++w) state[(int64_t)(kASz / 8 + w) * stride + i] = G[kDLo / 8 + w];
+}
+
+// n_steps calls of step(u) per aircraft.  u: [11][u_stride] (held for all steps of the launch); out: what the LAST call
+// returned, [12][out_stride]; out_all (optional): every call's return, [n_steps][12][out_stride].
+__global__ void __launch_bounds__(128)
+dasmat_step_kernel(uint8_t* G, uint64_t* __restrict__ state, int64_t stride, int64_t n, const double* __restrict__ u, int64_t u_stride,
+                   int n_steps, double* __restrict__ out, int64_t out_stride, double* __restrict__ out_all, int* __restrict__ err)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    __align__(16) uint8_t m[kLocalBytes];
+    uint64_t* mw = reinterpret_cast<uint64_t*>(m);
+    for (int w = 0; w < kStateWords; ++w) mw[w] = state[(int64_t)w * stride + i];
+    cpu_t c;
+    memset(&c, 0, sizeof c);
+    c.G = G; c.m = m; c.flat = 0;
+    // the caller's buffers sit above the frame, inside the stack region (as a C caller's locals would)
+    const uint64_t a_in = LIFT_BASE + kFlat - 0x100 + 0x20, a_out = a_in + 96;
+    double* in_p = reinterpret_cast<double*>(m + kASz + kDSz + (a_in - LIFT_BASE - kImg));
+    double* out_p = reinterpret_cast<double*>(m + kASz + kDSz + (a_out - LIFT_BASE - kImg));
+    for (int k = 0; k < n_steps; ++k) {
+        for (int j = 0; j < 11; ++j) in_p[j] = u[(int64_t)j * u_stride + i];
+        enter(c);
+        c.r[1] = a_out; c.r[2] = a_in;
+        f_180003720(&c);
+        if (out_all)
+            for (int j = 0; j < 12; ++j) out_all[((int64_t)k * 12 + j) * out_stride + i] = out_p[j];
+    }
+    if (out)
+        for (int j = 0; j < 12; ++j) out[(int64_t)j * out_stride + i] = out_p[j];
+    for (int w = 0; w < kStateWords; ++w) state[(int64_t)w * stride + i] = mw[w];
+    if (c.err) atomicOr(err, c.err);
+}
+
+#endif  // RL4_HAVE_DASMAT
+
+static int no_plant()
+{
+    set_error("this library was built without the reference's plant binary (rl4afcs_b200/csrc/_gen/ is produced by "
+              "oracle/pe_probe/lift.py where /root/reference exists): the 'dasmat' plant is not available");
+    return -2;
+}
+
+}  // namespace rl4
+
+using namespace rl4;
+
+extern "C" {
+
+int rl4_dasmat_available(void) { return RL4_HAVE_DASMAT; }
+int64_t rl4_dasmat_image_bytes(void) { return (int64_t)kFlat; }
+int32_t rl4_dasmat_state_words(void) { return kStateWords; }
+/* word index (in the per-aircraft state) of the 12 airframe states / the 4 engine states */
+int32_t rl4_dasmat_word_x(void) { return (int32_t)((kASz + (kRvaX - kDLo)) / 8); }
+int32_t rl4_dasmat_word_engine(void) { return (int32_t)((kASz + (kRvaEngine - kDLo)) / 8); }
+
+int rl4_dasmat_initialize(void* image, void* stream)
+{
+#if RL4_HAVE_DASMAT
+    RL4_REQUIRE(image != nullptr, "null image buffer");
+    cudaStream_t s = (cudaStream_t)stream;
+    static_assert(sizeof(kPristine) <= kImg, "image larger than the emulated address space");
+    RL4_CUDA(cudaMemsetAsync(image, 0, kFlat, s));
+    RL4_CUDA(cudaMemcpyAsync(image, kPristine, sizeof(kPristine), cudaMemcpyHostToDevice, s));
+    int* d_err = nullptr;
+    RL4_CUDA(cudaMalloc(&d_err, sizeof(int)));
+    RL4_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), s));
+    dasmat_initialize_kernel<<<1, 1, 0, s>>>((uint8_t*)image, d_err);
+    int rc = check_launch("dasmat_initialize_kernel");
+    int h_err = 0;
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) rc = cuda_fail(e, "dasmat initialize");
+    }
+    cudaFree(d_err);
+    if (rc) return rc;
+    if (h_err) { set_error("rl4_dasmat_initialize: the translated initialize() raised error bits 0x%x", h_err); return -3; }
+    return 0;
+#else
+    (void)image; (void)stream;
+    return no_plant();
+#endif
+}
+
+int rl4_dasmat_reset(const void* image, uint64_t* state, int64_t stride, int64_t n_agents, void* stream)
+{
+#if RL4_HAVE_DASMAT
+    RL4_REQUIRE(image && state && stride >= n_agents && n_agents > 0, "bad arguments");
+    dasmat_reset_kernel<<<(unsigned)((n_agents + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint64_t*)image, state, stride, n_agents);
+    return check_launch("dasmat_reset_kernel");
+#else
+    (void)image; (void)state; (void)stride; (void)n_agents; (void)stream;
+    return no_plant();
+#endif
+}
+
+int rl4_dasmat_step(void* image, uint64_t* state, int64_t stride, int64_t n_agents, const double* u, int64_t u_stride,
+                    int32_t n_steps, double* out, int64_t out_stride, double* out_all, int32_t* device_err, void* stream)
+{
+#if RL4_HAVE_DASMAT
+    RL4_REQUIRE(image && state && u && device_err && stride >= n_agents && u_stride >= n_agents && n_agents > 0 && n_steps > 0, "bad arguments");
+    RL4_REQUIRE((!out && !out_all) || out_stride >= n_agents, "out_stride < n_agents");
+    dasmat_step_kernel<<<(unsigned)((n_agents + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        (uint8_t*)image, state, stride, n_agents, u, u_stride, n_steps, out, out_stride, out_all, device_err);
+    return check_launch("dasmat_step_kernel");
+#else
+    (void)image; (void)state; (void)stride; (void)n_agents; (void)u; (void)u_stride; (void)n_steps; (void)out; (void)out_stride;
+    (void)out_all; (void)device_err; (void)stream;
+    return no_plant();
+#endif
+}
+
+}  // extern "C"
