@@ -26,16 +26,18 @@ static void lift_trap(const char* msg, uint64_t v)
 }
 #define LIFT_TRAP(msg, v) lift_trap(msg, (uint64_t)(v))
 
+/* memory operands arrive as the LOW 32 BITS of the emulated address (lift.py: mem_a32); helpers that take full 64-bit
+ * addresses (memcpy & co.) truncate the same way */
 static inline uint8_t* lift_ptr(cpu_t* c, uint64_t a, unsigned n)
 {
-    const uint64_t off = a - LIFT_BASE;
+    const uint64_t off = (uint32_t)((uint32_t)a - (uint32_t)LIFT_BASE);
     if (off > LIFT_MEM_SIZE - n) lift_trap("memory access outside the emulated address space", a);
     return c->M + off;
 }
 static inline uint8_t* lift_wptr(cpu_t* c, uint64_t a, unsigned n)
 {
     uint8_t* p = lift_ptr(c, a, n);
-    if (c->wmask) memset(c->wmask + (a - LIFT_BASE), 1, n);
+    if (c->wmask) memset(c->wmask + (uint32_t)((uint32_t)a - (uint32_t)LIFT_BASE), 1, n);
     return p;
 }
 #define LIFT_LD(T, a) ({ T v_; memcpy(&v_, lift_ptr(c, (a), sizeof(T)), sizeof(T)); v_; })

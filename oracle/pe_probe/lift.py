@@ -199,6 +199,7 @@ class Lifter:
         self.funcs = {}          # entry VA -> sorted list of instruction addresses
         self.unknown = {}
         self.frame_reg = None
+        self.const_regs = {}
 
     # ---- operands
     def is_stack_operand(self, s):
@@ -229,17 +230,43 @@ class Lifter:
             expr += p if p.startswith("-") else "+" + p
         return "(" + expr + ")"
 
+    def mem_a32(self, s, ins):
+        """The LOW 32 BITS of the effective address, as a uint32_t C expression: every object of the emulated address space
+        lies within 2 GB of the image base, so memory operands are addressed with 32-bit arithmetic (half the integer work
+        on a 32-bit machine like the GPU).  A register the function holds constant (const_regs) contributes its value."""
+        inner = s[s.index("[") + 1:s.rindex("]")]
+        terms = re.findall(r"([+-]?)\s*([^+-]+)", inner)
+        const, parts = 0, []
+        for sign, t in terms:
+            t = t.strip()
+            sg = -1 if sign == "-" else 1
+            if t == "rip":
+                const += ins.addr + ins.size
+            elif "*" in t:
+                r, sc = t.split("*")
+                assert sg == 1
+                if r in self.const_regs:
+                    const += self.const_regs[r] * int(sc)
+                else:
+                    parts.append(f"(uint32_t)r{REG[r][0]}*{sc}u")
+            elif t in REG:
+                assert REG[t][1] == 64 and sg == 1, s
+                if t in self.const_regs:
+                    const += self.const_regs[t]
+                else:
+                    parts.append(f"(uint32_t)r{REG[t][0]}")
+            else:
+                const += sg * int(t, 16)
+        parts.append(f"0x{const & 0xffffffff:x}u")
+        return "(" + "+".join(parts) + ")"
+
     def ld(self, w, s, ins):
         k = "S" if self.is_stack_operand(s) else ""
-        return f"LD{k}{w}({self.mem_addr(s, ins)})"
-
-    def ldd(self, s, ins):
-        k = "S" if self.is_stack_operand(s) else ""
-        return f"LD{k}D({self.mem_addr(s, ins)})"
+        return f"LD{k}{w}({self.mem_a32(s, ins)})"
 
     def st(self, w, s, ins, val):
         k = "S" if self.is_stack_operand(s) else ""
-        return f"ST{k}{w}({self.mem_addr(s, ins)},({val}));"
+        return f"ST{k}{w}({self.mem_a32(s, ins)},({val}));"
 
     def const_addr(self, s, ins):
         """VA if the operand is rip-relative, else None."""
@@ -297,17 +324,17 @@ class Lifter:
         """double-valued expression of lane `lane` of an xmm register or of a memory operand"""
         if s.startswith("xmm"):
             return f"U2D(x{self.xr(s)}{'lh'[lane]})"
-        a = self.mem_addr(s, ins)
+        a = self.mem_a32(s, ins)
         k = "S" if self.is_stack_operand(s) else ""
-        return f"LD{k}D({a}+{8 * lane})" if lane else f"LD{k}D({a})"
+        return f"LD{k}D({a}+{8 * lane}u)" if lane else f"LD{k}D({a})"
 
     def xu(self, s, ins, lane=0):
         """uint64-valued expression of a lane"""
         if s.startswith("xmm"):
             return f"x{self.xr(s)}{'lh'[lane]}"
-        a = self.mem_addr(s, ins)
+        a = self.mem_a32(s, ins)
         k = "S" if self.is_stack_operand(s) else ""
-        return f"LD{k}64({a}+{8 * lane})" if lane else f"LD{k}64({a})"
+        return f"LD{k}64({a}+{8 * lane}u)" if lane else f"LD{k}64({a})"
 
     # ---- discovery
     def flow(self, entry):
@@ -385,23 +412,48 @@ class Lifter:
             self.funcs[e] = self.flow(e)
 
     # ---- emission
-    def emit_all(self):
+    def reachable(self, roots):
+        """functions reachable from `roots` through direct calls / tail calls, plus every address-taken function if any
+        indirect call is reachable"""
+        seen, work, indirect = set(), list(roots), False
+        while work:
+            e = work.pop()
+            if e in seen or e not in self.funcs:
+                continue
+            seen.add(e)
+            for a in self.funcs[e]:
+                i = self.ins[a]
+                if i.mn in ("call", "jmp"):
+                    t = self.direct_target(i)
+                    if t is not None and t in self.funcs:
+                        work.append(t)
+                    elif t is None and not ("[rip" in i.ops[0] and self.const_addr(i.ops[0], i) in self.pe.iat):
+                        if not indirect:
+                            indirect = True
+                            work.extend(self.addr_taken & set(self.funcs))
+        return seen
+
+    def emit_all(self, roots=None):
         out = []
-        names = sorted(self.funcs)
+        names = sorted(self.funcs if roots is None else self.reachable(roots))
+        self.emitting = set(names)
         for e in names:
             out.append(f"LIFT_FN void f_{e:x}(cpu_t* c);")
-        out.append(f"LIFT_FN void f_{self.STEP:x}_m(cpu_t* c);")
+        with_step = self.STEP in self.emitting
+        if with_step:
+            out.append(f"LIFT_FN void f_{self.STEP:x}_m(cpu_t* c);")
         out.append("")
         # indirect-call dispatcher over address-taken functions
         out.append("LIFT_FN void lift_dispatch(cpu_t* c, uint64_t target) {")
         out.append("  switch (target) {")
-        for e in sorted(self.addr_taken & set(self.funcs)):
+        for e in sorted(self.addr_taken & self.emitting):
             out.append(f"  case 0x{e:x}ULL: f_{e:x}(c); return;")
         out.append("  default: LIFT_TRAP(\"indirect call to an address that is not a translated function\", target);")
         out.append("  }\n}\n")
         for e in names:
             out.extend(self.emit_func(e))
-        out.extend(self.emit_func(self.STEP, minor=True))
+        if with_step:
+            out.extend(self.emit_func(self.STEP, minor=True))
         return "\n".join(out)
 
     def import_call(self, name):
@@ -423,6 +475,35 @@ class Lifter:
 
     PRECALL = "LIFT_PRECALL;"       # locals -> cpu_t: rcx rdx r8 r9 rsp xmm0-3
     POSTCALL = "LIFT_POSTCALL;"     # cpu_t -> locals: rax xmm0
+
+    def find_const_regs(self, body):
+        """Callee-saved registers that the function loads ONCE with the address of a global (`lea reg,[rip+X]`) and otherwise
+        only saves / restores: as the base of a memory operand they are a known constant, which turns `[rbx+0x128]` into an
+        absolute address the C compiler resolves at compile time (thread-private signal, shared parameter ...)."""
+        saved = {"rbx": ("rbx", "ebx", "bx", "bl", "bh"), "rsi": ("rsi", "esi", "si", "sil"), "rdi": ("rdi", "edi", "di", "dil"),
+                 "r12": ("r12", "r12d", "r12w", "r12b"), "r13": ("r13", "r13d", "r13w", "r13b"), "r14": ("r14", "r14d", "r14w", "r14b"),
+                 "r15": ("r15", "r15d", "r15w", "r15b")}
+        out = {}
+        for reg, names in saved.items():
+            val, bad, n = None, False, 0
+            for a in body:
+                i = self.ins[a]
+                if not i.ops or i.mn in ("push", "cmp", "test", "comisd", "ucomisd", "call", "jmp") or i.mn.startswith("j"):
+                    continue
+                writes = [i.ops[0]] + ([i.ops[1]] if i.mn == "xchg" else [])
+                if i.mn in ("mov", "movsd", "movaps", "movups", "movdqa", "movdqu", "movss") and "[" in i.ops[0]:
+                    writes = []                      # a store: the register is only read
+                if any(w in names for w in writes):
+                    if i.mn == "pop":
+                        continue
+                    n += 1
+                    if i.mn == "lea" and i.ops[0] == reg and "[rip" in i.ops[1]:
+                        val = self.const_addr(i.ops[1], i)
+                    else:
+                        bad = True
+            if val is not None and n == 1 and not bad:
+                out[reg] = val
+        return out
 
     def find_frame_reg(self, body):
         """rbp when the function uses it as a frame pointer: written once by `lea rbp,[rsp+-c]` (or from rax = rsp at entry),
@@ -463,6 +544,7 @@ class Lifter:
         body = self.funcs[e]
         inside = set(body)
         self.frame_reg = self.find_frame_reg(body)
+        self.const_regs = self.find_const_regs(body)
         targets = set()
         for a in body:
             i = self.ins[a]
@@ -479,6 +561,8 @@ class Lifter:
             leaders[cur] += 1
             prev = i
         out = [f"LIFT_FN void f_{e:x}{'_m' if minor else ''}(cpu_t* c) {{", "  LIFT_LOCALS; LIFT_ENTER;"]
+        if e == self.STEP:
+            out.append("  LIFT_SYNC;        /* every aircraft calls step() the same number of times: a convergent point */")
         prev_end = None
         for a in body:
             i = self.ins[a]
@@ -574,9 +658,9 @@ class Lifter:
         if mn == "cqo":
             return "r2=(uint64_t)(((int64_t)r0)>>63);"
         if mn == "push":
-            return f"r4-=8; STS64(r4,{rd(ops[0], i, 64)});"
+            return f"r4-=8; STS64((uint32_t)r4,{rd(ops[0], i, 64)});"
         if mn == "pop":
-            return f"{{ uint64_t t_=LDS64(r4); r4+=8; {wr(ops[0], i, 't_')} }}"
+            return f"{{ uint64_t t_=LDS64((uint32_t)r4); r4+=8; {wr(ops[0], i, 't_')} }}"
         if mn == "xchg":
             w = self.op_size(ops[0]) or self.op_size(ops[1])
             return f"{{ uint64_t a_={rd(ops[0], i, w)}, b_={rd(ops[1], i, w)}; {wr(ops[0], i, 'b_', w)} {wr(ops[1], i, 'a_', w)} }}"
@@ -644,7 +728,7 @@ class Lifter:
                     return f"x{n}l=x{self.xr(s)}l; x{n}h=x{self.xr(s)}h;"
                 return f"{{ uint64_t p_={xu(s, i, 0)}, q_={xu(s, i, 1)}; x{n}l=p_; x{n}h=q_; }}"
             k = "S" if self.is_stack_operand(d) else ""
-            return f"{{ uint64_t a_={self.mem_addr(d, i)}; ST{k}64(a_,x{self.xr(s)}l); ST{k}64(a_+8,x{self.xr(s)}h); }}"
+            return f"{{ uint32_t a_={self.mem_a32(d, i)}; ST{k}64(a_,x{self.xr(s)}l); ST{k}64(a_+8u,x{self.xr(s)}h); }}"
         if mn in ("movlpd", "movhpd", "movlps", "movhps"):
             k = "l" if mn[3] == "l" else "h"
             d, s = ops
@@ -751,6 +835,9 @@ PRELUDE = r"""/* GENERATED by oracle/pe_probe/lift.py from the reference's plant
 #ifndef LIFT_MEM_CTX
 #define LIFT_MEM_CTX
 #endif
+#ifndef LIFT_SYNC
+#define LIFT_SYNC
+#endif
 #define ZF (fl.zf)
 #define SF (fl.sf)
 #define CF (fl.cf)
@@ -787,12 +874,14 @@ def main():
     ins = disassemble(path)
     L = Lifter(pe, ins)
     L.discover([BASE + v for v in ENTRY.values()])
-    code = L.emit_all()
     os.makedirs(args.out, exist_ok=True)
-    with open(os.path.join(args.out, f"citation_{args.variant}_code.inc"), "w") as f:
-        f.write(PRELUDE)
-        f.write(code)
-        f.write(POSTLUDE)
+    # three files: everything (CPU library), what step() reaches, what initialize() / terminate() reach (the CUDA build
+    # compiles the last two under different memory models)
+    for tag, roots in (("code", None), ("code_step", [BASE + ENTRY["step"]]), ("code_init", [BASE + ENTRY["initialize"], BASE + ENTRY["terminate"]])):
+        with open(os.path.join(args.out, f"citation_{args.variant}_{tag}.inc"), "w") as f:
+            f.write(PRELUDE)
+            f.write(L.emit_all(roots))
+            f.write(POSTLUDE)
     with open(os.path.join(args.out, f"citation_{args.variant}_image.bin"), "wb") as f:
         f.write(bytes(pe.img))
     # the same bytes as a C initialiser list (up to the end of .data: the unwind / resource / relocation sections are not used)

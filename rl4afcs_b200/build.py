@@ -55,14 +55,14 @@ LIFTER = os.path.join(_HERE, "..", "oracle", "pe_probe", "lift.py")
 
 
 def _generate_plant() -> None:
-    code, image = os.path.join(GEN_DIR, "dasmat_code.inc"), os.path.join(GEN_DIR, "dasmat_image.inc")
+    code, image = os.path.join(GEN_DIR, "dasmat_code_step.inc"), os.path.join(GEN_DIR, "dasmat_image.inc")
     if not os.path.isfile(PLANT_BINARY) or not os.path.isfile(LIFTER):
         return
     if os.path.isfile(code) and os.path.isfile(image) and os.path.getmtime(code) >= os.path.getmtime(LIFTER):
         return
     subprocess.run([sys.executable, LIFTER, "--variant", "extended_input", "--out", GEN_DIR], check=True, stdout=subprocess.DEVNULL)
-    shutil.copyfile(os.path.join(GEN_DIR, "citation_extended_input_code.inc"), code)
-    shutil.copyfile(os.path.join(GEN_DIR, "citation_extended_input_image.inc"), image)
+    for tag in ("code_step", "code_init", "image"):
+        shutil.copyfile(os.path.join(GEN_DIR, f"citation_extended_input_{tag}.inc"), os.path.join(GEN_DIR, f"dasmat_{tag}.inc"))
 OBJ_DIR = os.path.join(_HERE, "build")
 
 
@@ -77,7 +77,7 @@ def _src_stale(src: str) -> bool:
     t = os.path.getmtime(o)
     deps = [os.path.join(CSRC, d) for d in [src] + DEPS[src]] + [os.path.abspath(__file__)]
     if src == "dasmat_plant.cu":
-        deps = deps[:-1] + [g for g in (os.path.join(GEN_DIR, "dasmat_code.inc"), os.path.join(GEN_DIR, "dasmat_image.inc")) if os.path.isfile(g)]
+        deps = deps[:-1] + [g for g in (os.path.join(GEN_DIR, "dasmat_code_step.inc"), os.path.join(GEN_DIR, "dasmat_code_init.inc"), os.path.join(GEN_DIR, "dasmat_image.inc")) if os.path.isfile(g)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

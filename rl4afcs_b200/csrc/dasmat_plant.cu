@@ -15,7 +15,9 @@
 //   D       [0x3a000, 0x3c200)  /  discrete states, solver work arrays): PER AIRCRAFT, 1120 eight-byte words
 //   stack   [0x40000, 0x42000)  per thread, scratch
 // A and D persist between launches in an SoA plane `state[word * stride + aircraft]` (coalesced copy in / out); inside a
-// launch they and the stack live in thread-local memory, which the hardware interleaves per lane.
+// launch they and the stack live in thread-local memory, which the hardware interleaves per lane: one window
+// [0x3a000, 0x42000) (D, the never-touched tail of the image, the stack -- a single range check decodes a dynamic address;
+// untouched lines cost no cache) plus A.  Memory operands are addressed with the low 32 bits of the emulated address.
 // A store outside A / D / stack, an indirect call to an unknown target or an untranslated instruction sets an error bit
 // that the host reads back: the translation never silently computes something else.
 #include "rl4_runtime.h"
@@ -23,7 +25,7 @@
 #include <math_constants.h>
 #include <vector>
 
-#if __has_include("_gen/dasmat_code.inc")
+#if __has_include("_gen/dasmat_code_step.inc")
 #define RL4_HAVE_DASMAT 1
 #else
 #define RL4_HAVE_DASMAT 0
@@ -31,16 +33,25 @@
 
 namespace rl4 {
 
-constexpr uint64_t kImg = 0x40000, kStack = 0x2000, kFlat = kImg + kStack;
-constexpr uint64_t kALo = 0x2eb00, kASz = 0x100, kDLo = 0x3a000, kDSz = 0x2200;
+constexpr uint32_t kImg = 0x40000, kStack = 0x2000, kFlat = kImg + kStack;
+constexpr uint32_t kALo = 0x2eb00, kASz = 0x100, kDLo = 0x3a000, kDSz = 0x2200;
+constexpr uint32_t kWLo = kDLo, kWSz = kFlat - kDLo;            // thread-private window: D, the unused tail of the image, the stack
 constexpr int kStateWords = (int)((kASz + kDSz) / 8);           // 1120
-constexpr uint64_t kLocalBytes = kASz + kDSz + kStack;
-constexpr uint64_t kRvaX = 0x3c120, kRvaEngine = 0x3c198;       // the 16 continuous states (oracle/pe_probe/README.md)
+constexpr uint32_t kLocalBytes = kWSz + kASz;                    // window + A; only the touched lines of it ever occupy cache
+constexpr uint32_t kRvaX = 0x3c120, kRvaEngine = 0x3c198;       // the 16 continuous states (oracle/pe_probe/README.md)
+constexpr uint32_t kBase32 = 0x80000000u;                       // low 32 bits of the image base: memory operands arrive as low halves
+
+#ifndef RL4_DASMAT_THREADS
+#define RL4_DASMAT_THREADS 128
+#endif
+#ifndef RL4_DASMAT_MIN_BLOCKS
+#define RL4_DASMAT_MIN_BLOCKS 2
+#endif
 
 #if RL4_HAVE_DASMAT
 
 #define LIFT_HD __device__ __forceinline__
-#define LIFT_CPU_EXTRA uint8_t* G; uint8_t* m; int flat; int err;
+#define LIFT_CPU_EXTRA uint8_t* G; uint8_t* m; int err;
 #define F_ADD(a, b) __dadd_rn((a), (b))
 #define F_SUB(a, b) __dsub_rn((a), (b))
 #define F_MUL(a, b) __dmul_rn((a), (b))
@@ -54,48 +65,130 @@ enum { kErrTrap = 1, kErrWildAccess = 2, kErrStoreToImage = 4 };
 
 #define LIFT_FN static __device__ __noinline__
 #define LIFT_TRAP(msg, v) do { c->err |= kErrTrap; return; } while (0)
-// per-function copies of the memory context (the compiler cannot keep c->m in a register across stores otherwise)
-#define LIFT_MEM_CTX uint8_t* const m_ = c->m; const uint8_t* const G_ = c->G; const int flat_ = c->flat; (void)m_; (void)G_; (void)flat_;
+#define lift_cos cos
+#define lift_sin sin
+#define lift_tan tan
+#define lift_exp exp
+#define lift_floor floor
+#define lift_log10 log10
+#define lift_sqrt __dsqrt_rn
+#define lift_pow pow
+__device__ __forceinline__ uint64_t lift_CVTR32(double v) { return (v > -2147483649.0 && v < 2147483648.0) ? (uint64_t)(uint32_t)__double2int_rn(v) : 0x80000000ULL; }
+__device__ __forceinline__ uint64_t lift_CVTR64(double v) { return (uint64_t)__double2ll_rn(v); }
+__device__ __forceinline__ uint64_t lift_malloc(cpu_t* c, uint64_t) { c->err |= kErrTrap; return 0; }   // the model allocates nothing
 
-// where an emulated address lives: the thread's private copy of A / D / stack, or the shared image
-template <typename T> __device__ __forceinline__ T lift_load(uint8_t* m_, const uint8_t* G_, int flat_, cpu_t* c, uint64_t a)
-{
-    const uint64_t off = a - LIFT_BASE;
-    if (!flat_) {
-        if (off - kDLo < kDSz) return *reinterpret_cast<const T*>(m_ + kASz + (off - kDLo));
-        if (off - kImg < kStack) return *reinterpret_cast<const T*>(m_ + kASz + kDSz + (off - kImg));
-        if (off - kALo < kASz) return *reinterpret_cast<const T*>(m_ + (off - kALo));
-        if (off >= kImg) { c->err |= kErrWildAccess; return T(0); }
-        return __ldg(reinterpret_cast<const T*>(G_ + off));          // shared image: read-only while aircraft are stepping
+// byte-wise helpers over whichever LD8 / ST8 the enclosing namespace defines
+#define LIFT_DEFINE_BULK                                                                                           \
+    __device__ __noinline__ void lift_memcpy(cpu_t* c, uint64_t d64, uint64_t s64, uint64_t n)                      \
+    {                                                                                                               \
+        LIFT_MEM_CTX const uint32_t d = (uint32_t)d64, s = (uint32_t)s64;                                           \
+        if (d <= s) for (uint32_t k = 0; k < n; ++k) ST8(d + k, LD8(s + k));                                        \
+        else for (uint32_t k = (uint32_t)n; k-- > 0;) ST8(d + k, LD8(s + k));                                       \
+    }                                                                                                               \
+    __device__ __noinline__ void lift_memset(cpu_t* c, uint64_t d64, int v, uint64_t n)                             \
+    {                                                                                                               \
+        LIFT_MEM_CTX const uint32_t d = (uint32_t)d64;                                                              \
+        for (uint32_t k = 0; k < n; ++k) ST8(d + k, v);                                                             \
+    }                                                                                                               \
+    __device__ __noinline__ void lift_REPSTOS(cpu_t* c, uint64_t* rcx, uint64_t* rdi, uint64_t rax, unsigned w)    \
+    {                                                                                                               \
+        LIFT_MEM_CTX                                                                                                \
+        for (; *rcx; --*rcx, *rdi += w)                                                                             \
+            for (unsigned k = 0; k < w; ++k) ST8((uint32_t)*rdi + k, rax >> (8 * k));                               \
+    }                                                                                                               \
+    __device__ __noinline__ void lift_REPMOVS(cpu_t* c, uint64_t* rcx, uint64_t* rdi, uint64_t* rsi, unsigned w)   \
+    {                                                                                                               \
+        LIFT_MEM_CTX                                                                                                \
+        for (; *rcx; --*rcx, *rdi += w, *rsi += w)                                                                  \
+            for (unsigned k = 0; k < w; ++k) ST8((uint32_t)*rdi + k, LD8((uint32_t)*rsi + k));                      \
     }
-    if (off >= kFlat) { c->err |= kErrWildAccess; return T(0); }
-    return *reinterpret_cast<const T*>(G_ + off);
-}
-template <typename T> __device__ __forceinline__ void lift_store(uint8_t* m_, const uint8_t* G_, int flat_, cpu_t* c, uint64_t a, T v)
+
+// ---- initialize(): flat model, everything (image + stack) in one global buffer ------------------------------------------
+namespace init_mode {
+#define LIFT_MEM_CTX uint8_t* const G_ = c->G; (void)G_;
+template <typename T> __device__ __forceinline__ T* at(uint8_t* G_, cpu_t* c, uint32_t a32)
 {
-    const uint64_t off = a - LIFT_BASE;
-    if (!flat_) {
-        if (off - kDLo < kDSz) { *reinterpret_cast<T*>(m_ + kASz + (off - kDLo)) = v; return; }
-        if (off - kImg < kStack) { *reinterpret_cast<T*>(m_ + kASz + kDSz + (off - kImg)) = v; return; }
-        if (off - kALo < kASz) { *reinterpret_cast<T*>(m_ + (off - kALo)) = v; return; }
-        c->err |= kErrStoreToImage;
-        return;
-    }
-    if (off >= kFlat) { c->err |= kErrWildAccess; return; }
-    *reinterpret_cast<T*>(const_cast<uint8_t*>(G_) + off) = v;
+    uint32_t off = a32 - kBase32;
+    if (off >= kFlat) { c->err |= kErrWildAccess; off = kImg; }
+    return reinterpret_cast<T*>(G_ + off);
 }
-#define LD8(a)  ((uint64_t)lift_load<uint8_t>(m_, G_, flat_, c, (a)))
-#define LD16(a) ((uint64_t)lift_load<uint16_t>(m_, G_, flat_, c, (a)))
-#define LD32(a) ((uint64_t)lift_load<uint32_t>(m_, G_, flat_, c, (a)))
-#define LD64(a) lift_load<uint64_t>(m_, G_, flat_, c, (a))
-#define LDD(a)  lift_load<double>(m_, G_, flat_, c, (a))
-#define ST8(a, v)  lift_store<uint8_t>(m_, G_, flat_, c, (a), (uint8_t)(v))
-#define ST16(a, v) lift_store<uint16_t>(m_, G_, flat_, c, (a), (uint16_t)(v))
-#define ST32(a, v) lift_store<uint32_t>(m_, G_, flat_, c, (a), (uint32_t)(v))
-#define ST64(a, v) lift_store<uint64_t>(m_, G_, flat_, c, (a), (uint64_t)(v))
-// operands the translator knows to be on the stack: no decoding (in flat mode c->m is biased so that the same expression
-// lands in the global buffer)
-#define LIFT_STK(T, a) reinterpret_cast<T*>(m_ + (kASz + kDSz) + ((a) - (LIFT_BASE + kImg)))
+#define LD8(a)  ((uint64_t)*at<uint8_t>(G_, c, (a)))
+#define LD16(a) ((uint64_t)*at<uint16_t>(G_, c, (a)))
+#define LD32(a) ((uint64_t)*at<uint32_t>(G_, c, (a)))
+#define LD64(a) (*at<uint64_t>(G_, c, (a)))
+#define LDD(a)  (*at<double>(G_, c, (a)))
+#define ST8(a, v)  (*at<uint8_t>(G_, c, (a)) = (uint8_t)(v))
+#define ST16(a, v) (*at<uint16_t>(G_, c, (a)) = (uint16_t)(v))
+#define ST32(a, v) (*at<uint32_t>(G_, c, (a)) = (uint32_t)(v))
+#define ST64(a, v) (*at<uint64_t>(G_, c, (a)) = (uint64_t)(v))
+#define LDS8 LD8
+#define LDS16 LD16
+#define LDS32 LD32
+#define LDS64 LD64
+#define LDSD LDD
+#define STS8 ST8
+#define STS16 ST16
+#define STS32 ST32
+#define STS64 ST64
+LIFT_DEFINE_BULK
+#include "_gen/dasmat_code_init.inc"
+#undef LIFT_MEM_CTX
+#undef LD8
+#undef LD16
+#undef LD32
+#undef LD64
+#undef LDD
+#undef ST8
+#undef ST16
+#undef ST32
+#undef ST64
+#undef LDS8
+#undef LDS16
+#undef LDS32
+#undef LDS64
+#undef LDSD
+#undef STS8
+#undef STS16
+#undef STS32
+#undef STS64
+#undef LIFT_LOCALS
+#undef LIFT_ENTER
+#undef LIFT_PRECALL
+#undef LIFT_POSTCALL
+#undef LIFT_EXIT
+}  // namespace init_mode
+
+// ---- step(): thread-private window (D, stack) + A in local memory, the image shared and read-only ------------------------
+namespace step_mode {
+// m_ is the thread's local array: telling the compiler so turns the accesses into LDL / STL with immediate offsets
+#define LIFT_MEM_CTX uint8_t* const m_ = c->m; const uint8_t* const G_ = c->G; __builtin_assume(__isLocal(m_)); (void)m_; (void)G_;
+#define LIFT_SYNC __syncthreads()      // keeps the warps of a CTA on the same stretch of the (instruction-cache-sized) code
+template <typename T> __device__ __forceinline__ T lift_load(uint8_t* m_, const uint8_t* G_, cpu_t* c, uint32_t a32)
+{
+    const uint32_t off = a32 - kBase32;
+    if (off - kWLo < kWSz) return *reinterpret_cast<const T*>(m_ + (off - kWLo));
+    if (off - kALo < kASz) return *reinterpret_cast<const T*>(m_ + kWSz + (off - kALo));
+    if (off >= kImg) { c->err |= kErrWildAccess; return T(0); }
+    return __ldg(reinterpret_cast<const T*>(G_ + off));              // shared image: read-only while aircraft are stepping
+}
+template <typename T> __device__ __forceinline__ void lift_store(uint8_t* m_, cpu_t* c, uint32_t a32, T v)
+{
+    const uint32_t off = a32 - kBase32;
+    if (off - kWLo < kWSz) { *reinterpret_cast<T*>(m_ + (off - kWLo)) = v; return; }
+    if (off - kALo < kASz) { *reinterpret_cast<T*>(m_ + kWSz + (off - kALo)) = v; return; }
+    c->err |= kErrStoreToImage;
+}
+#define LD8(a)  ((uint64_t)lift_load<uint8_t>(m_, G_, c, (a)))
+#define LD16(a) ((uint64_t)lift_load<uint16_t>(m_, G_, c, (a)))
+#define LD32(a) ((uint64_t)lift_load<uint32_t>(m_, G_, c, (a)))
+#define LD64(a) lift_load<uint64_t>(m_, G_, c, (a))
+#define LDD(a)  lift_load<double>(m_, G_, c, (a))
+#define ST8(a, v)  lift_store<uint8_t>(m_, c, (a), (uint8_t)(v))
+#define ST16(a, v) lift_store<uint16_t>(m_, c, (a), (uint16_t)(v))
+#define ST32(a, v) lift_store<uint32_t>(m_, c, (a), (uint32_t)(v))
+#define ST64(a, v) lift_store<uint64_t>(m_, c, (a), (uint64_t)(v))
+// operands the translator knows to be on the stack: inside the window by construction, no decoding
+#define LIFT_STK(T, a) reinterpret_cast<T*>(m_ + ((a) - (kBase32 + kWLo)))
 #define LDS8(a)  ((uint64_t)*LIFT_STK(uint8_t, a))
 #define LDS16(a) ((uint64_t)*LIFT_STK(uint16_t, a))
 #define LDS32(a) ((uint64_t)*LIFT_STK(uint32_t, a))
@@ -105,44 +198,9 @@ template <typename T> __device__ __forceinline__ void lift_store(uint8_t* m_, co
 #define STS16(a, v) (*LIFT_STK(uint16_t, a) = (uint16_t)(v))
 #define STS32(a, v) (*LIFT_STK(uint32_t, a) = (uint32_t)(v))
 #define STS64(a, v) (*LIFT_STK(uint64_t, a) = (uint64_t)(v))
-
-#define lift_cos cos
-#define lift_sin sin
-#define lift_tan tan
-#define lift_exp exp
-#define lift_floor floor
-#define lift_log10 log10
-#define lift_sqrt __dsqrt_rn
-#define lift_pow pow
-
-__device__ __noinline__ void lift_memcpy(cpu_t* c, uint64_t d, uint64_t s, uint64_t n)
-{
-    LIFT_MEM_CTX
-    if (d <= s) for (uint64_t k = 0; k < n; ++k) ST8(d + k, LD8(s + k));
-    else for (uint64_t k = n; k-- > 0;) ST8(d + k, LD8(s + k));
-}
-__device__ __noinline__ void lift_memset(cpu_t* c, uint64_t d, int v, uint64_t n)
-{
-    LIFT_MEM_CTX
-    for (uint64_t k = 0; k < n; ++k) ST8(d + k, v);
-}
-__device__ __forceinline__ uint64_t lift_malloc(cpu_t* c, uint64_t) { c->err |= kErrTrap; return 0; }   // the model allocates nothing
-__device__ __noinline__ void lift_REPSTOS(cpu_t* c, uint64_t* rcx, uint64_t* rdi, uint64_t rax, unsigned w)
-{
-    LIFT_MEM_CTX
-    for (; *rcx; --*rcx, *rdi += w)
-        for (unsigned k = 0; k < w; ++k) ST8(*rdi + k, rax >> (8 * k));
-}
-__device__ __noinline__ void lift_REPMOVS(cpu_t* c, uint64_t* rcx, uint64_t* rdi, uint64_t* rsi, unsigned w)
-{
-    LIFT_MEM_CTX
-    for (; *rcx; --*rcx, *rdi += w, *rsi += w)
-        for (unsigned k = 0; k < w; ++k) ST8(*rdi + k, LD8(*rsi + k));
-}
-__device__ __forceinline__ uint64_t lift_CVTR32(double v) { return (v > -2147483649.0 && v < 2147483648.0) ? (uint64_t)(uint32_t)__double2int_rn(v) : 0x80000000ULL; }
-__device__ __forceinline__ uint64_t lift_CVTR64(double v) { return (uint64_t)__double2ll_rn(v); }
-
-#include "_gen/dasmat_code.inc"
+LIFT_DEFINE_BULK
+#include "_gen/dasmat_code_step.inc"
+}  // namespace step_mode
 
 // the pristine image (sections at their RVAs), embedded at build time
 static const uint8_t kPristine[] = {
@@ -161,9 +219,9 @@ __global__ void dasmat_initialize_kernel(uint8_t* G, int* err)
     if (blockIdx.x || threadIdx.x) return;
     cpu_t c;
     memset(&c, 0, sizeof c);
-    c.G = G; c.m = G + kImg - (kASz + kDSz); c.flat = 1;     // biased so that the stack-operand expression lands in G
+    c.G = G; c.m = nullptr;
     enter(c);
-    f_1800096f0(&c);
+    init_mode::f_1800096f0(&c);
     *err = c.err;
 }
 
@@ -178,33 +236,40 @@ __global__ void dasmat_reset_kernel(const uint64_t* __restrict__ G, uint64_t* __
 
 // n_steps calls of step(u) per aircraft.  u: [11][u_stride] (held for all steps of the launch); out: what the LAST call
 // returned, [12][out_stride]; out_all (optional): every call's return, [n_steps][12][out_stride].
-__global__ void __launch_bounds__(128)
+// Every thread of the CTA runs the loop (the translated code synchronises the CTA at each step() entry): aircraft beyond
+// n_agents are clamped copies of the last one and store nothing.
+__global__ void __launch_bounds__(RL4_DASMAT_THREADS, RL4_DASMAT_MIN_BLOCKS)
 dasmat_step_kernel(uint8_t* G, uint64_t* __restrict__ state, int64_t stride, int64_t n, const double* __restrict__ u, int64_t u_stride,
                    int n_steps, double* __restrict__ out, int64_t out_stride, double* __restrict__ out_all, int* __restrict__ err)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int64_t i_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i_raw < n;
+    const int64_t i = active ? i_raw : n - 1;
     __align__(16) uint8_t m[kLocalBytes];
-    uint64_t* mw = reinterpret_cast<uint64_t*>(m);
-    for (int w = 0; w < kStateWords; ++w) mw[w] = state[(int64_t)w * stride + i];
+    uint64_t* wd = reinterpret_cast<uint64_t*>(m);                       // D at the bottom of the window
+    uint64_t* wa = reinterpret_cast<uint64_t*>(m + kWSz);                // A behind the window
+    for (int w = 0; w < (int)(kASz / 8); ++w) wa[w] = state[(int64_t)w * stride + i];
+    for (int w = 0; w < (int)(kDSz / 8); ++w) wd[w] = state[(int64_t)(kASz / 8 + w) * stride + i];
     cpu_t c;
     memset(&c, 0, sizeof c);
-    c.G = G; c.m = m; c.flat = 0;
+    c.G = G; c.m = m;
     // the caller's buffers sit above the frame, inside the stack region (as a C caller's locals would)
     const uint64_t a_in = LIFT_BASE + kFlat - 0x100 + 0x20, a_out = a_in + 96;
-    double* in_p = reinterpret_cast<double*>(m + kASz + kDSz + (a_in - LIFT_BASE - kImg));
-    double* out_p = reinterpret_cast<double*>(m + kASz + kDSz + (a_out - LIFT_BASE - kImg));
+    double* in_p = reinterpret_cast<double*>(m + ((uint32_t)a_in - kBase32 - kWLo));
+    double* out_p = reinterpret_cast<double*>(m + ((uint32_t)a_out - kBase32 - kWLo));
     for (int k = 0; k < n_steps; ++k) {
         for (int j = 0; j < 11; ++j) in_p[j] = u[(int64_t)j * u_stride + i];
         enter(c);
         c.r[1] = a_out; c.r[2] = a_in;
-        f_180003720(&c);
-        if (out_all)
+        step_mode::f_180003720(&c);
+        if (out_all && active)
             for (int j = 0; j < 12; ++j) out_all[((int64_t)k * 12 + j) * out_stride + i] = out_p[j];
     }
+    if (!active) return;
     if (out)
         for (int j = 0; j < 12; ++j) out[(int64_t)j * out_stride + i] = out_p[j];
-    for (int w = 0; w < kStateWords; ++w) state[(int64_t)w * stride + i] = mw[w];
+    for (int w = 0; w < (int)(kASz / 8); ++w) state[(int64_t)w * stride + i] = wa[w];
+    for (int w = 0; w < (int)(kDSz / 8); ++w) state[(int64_t)(kASz / 8 + w) * stride + i] = wd[w];
     if (c.err) atomicOr(err, c.err);
 }
 
@@ -277,7 +342,7 @@ int rl4_dasmat_step(void* image, uint64_t* state, int64_t stride, int64_t n_agen
 #if RL4_HAVE_DASMAT
     RL4_REQUIRE(image && state && u && device_err && stride >= n_agents && u_stride >= n_agents && n_agents > 0 && n_steps > 0, "bad arguments");
     RL4_REQUIRE((!out && !out_all) || out_stride >= n_agents, "out_stride < n_agents");
-    dasmat_step_kernel<<<(unsigned)((n_agents + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+    dasmat_step_kernel<<<(unsigned)((n_agents + RL4_DASMAT_THREADS - 1) / RL4_DASMAT_THREADS), RL4_DASMAT_THREADS, 0, (cudaStream_t)stream>>>(
         (uint8_t*)image, state, stride, n_agents, u, u_stride, n_steps, out, out_stride, out_all, device_err);
     return check_launch("dasmat_step_kernel");
 #else

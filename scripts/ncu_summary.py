@@ -17,7 +17,10 @@ ap.add_argument("--agents", type=int, required=True)
 ap.add_argument("--steps", type=int, required=True)
 a = ap.parse_args()
 
-raw = subprocess.run(["ncu", "-i", a.rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+if a.rep.endswith(".csv"):        # raw page already exported on the GPU box (reports of very large kernels do not travel)
+    raw = open(a.rep).read()
+else:
+    raw = subprocess.run(["ncu", "-i", a.rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
 open(a.out + "_raw.csv", "w").write(raw)
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
