@@ -479,6 +479,42 @@ typedef struct rl4_nl_host_io {
  * agents x steps.  The context's policy must be RL4_MIXED or RL4_FP64. */
 int rl4_nl_episode_host(rl4_ctx* ctx, const rl4_nl_params* p, const rl4_nl_host_io* io, int64_t n_agents, int32_t n_steps);
 
+/* ---- the reference's own nonlinear aircraft ("dasmat" plant) -----------------------------------------------------------
+ * Replaces `_citation.initialize / step / terminate` (envs/nonlinear/citation.py:62-69; called at envs/nonlinear/env.py:210,
+ * 288-291): the DASMAT Citation model the reference ships as a Windows binary, translated from that binary's machine code at
+ * build time (oracle/pe_probe/lift.py -> rl4afcs_b200/csrc/_gen/, only where the reference tree exists) and compiled for
+ * sm_100a, one aircraft per thread.  A library built without the binary exports the same symbols; they return -2 and
+ * rl4_last_error() says so.  Buffers (all device memory, caller-owned):
+ *   image        rl4_dasmat_image_bytes() bytes: the model's memory image after initialize(); shared, read-only afterwards
+ *   plant_state  uint64 [rl4_dasmat_state_words()][stride]: the part of the model's memory that step() writes, per aircraft
+ *                (continuous states at words rl4_dasmat_word_x() .. +12 and rl4_dasmat_word_engine() .. +4, as doubles)
+ *   device_err   one int32, OR of error bits raised by any aircraft (1 untranslated path / bad indirect call, 2 access
+ *                outside the model's memory, 4 store into the shared image); 0 after a valid run */
+int     rl4_dasmat_available(void);
+int64_t rl4_dasmat_image_bytes(void);
+int32_t rl4_dasmat_state_words(void);
+int32_t rl4_dasmat_word_x(void);
+int32_t rl4_dasmat_word_engine(void);
+/* citation.initialize(): fills `image` (synchronises the stream: the model's own initialisation code runs on the device) */
+int rl4_dasmat_initialize(void* image, void* stream);
+/* every aircraft <- the initialised model */
+int rl4_dasmat_reset(const void* image, uint64_t* plant_state, int64_t stride, int64_t n_agents, void* stream);
+/* n_steps calls of citation.step(u) per aircraft: u [11][u_stride] held over the launch; out [12][out_stride] = the last
+ * call's return (may be NULL); out_all [n_steps][12][out_stride] = every call's return (may be NULL) */
+int rl4_dasmat_step(void* image, uint64_t* plant_state, int64_t stride, int64_t n_agents, const double* u, int64_t u_stride,
+                    int32_t n_steps, double* out, int64_t out_stride, double* out_all, int32_t* device_err, void* stream);
+/* aircraft `src_index` of one state plane -> every aircraft of another (the trimmed state after Ce500NonLinear.reset) */
+int rl4_dasmat_broadcast(const uint64_t* src, int64_t src_stride, int64_t src_index, uint64_t* dst, int64_t dst_stride, int64_t n_agents,
+                         void* stream);
+/* rl4_nl_env_step / rl4_nl_run with the dasmat plant in place of the surrogate (policy RL4_MIXED; integrator = the model's own) */
+int rl4_nl_env_step_dasmat(const rl4_nl_params* p, const double* theta_ref, int32_t stepp, double* x_full, double* x_act,
+                           const double* action, double* out_mdp, double* out_reward, double* out_e_theta, double* out_surf,
+                           double* out_eff, double* out_x_obs, int64_t stride, int64_t n, void* image, uint64_t* plant_state,
+                           int64_t plant_stride, int32_t* device_err, void* stream);
+int rl4_nl_run_dasmat(int policy, const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride,
+                      int32_t k0, int32_t n_steps, rl4_nl_state st, int64_t n, rl4_sp_log lg, void* image, uint64_t* plant_state,
+                      int64_t plant_stride, int32_t* device_err, void* stream);
+
 /* ---- measurement helpers (bench.py roofline denominators) ---- */
 /* Runs an FMA micro-kernel and returns achieved FLOP/s.  is_double: 0 = FFMA, 1 = DFMA with 16 independent chains per thread
  * whose multiplier and addend are shared (the pipe's peak, the roofline denominator); 2 / 3 = FFMA / DFMA whose three

@@ -72,6 +72,27 @@ def lib():
     return L
 
 
+_ext_keep = []
+
+
+def set_external_plant(n_agents: int, variant: str = "extended_input"):
+    """Runs the oracle's env on the reference's OWN aircraft model (the translated binary, oracle/pe_probe/lifted.py), one
+    instance per agent, instead of the surrogate header; ``set_external_plant(0)`` switches back.  Single-threaded."""
+    L = lib()
+    L.orc_nl_set_external_plant.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    _ext_keep.clear()
+    if not n_agents:
+        L.orc_nl_set_external_plant(None, None, None)
+        return None
+    from oracle.pe_probe import lifted
+    P = lifted.lib(variant)
+    crafts = [lifted.Aircraft(variant) for _ in range(int(n_agents))]
+    arr = (ctypes.c_void_p * len(crafts))(*[c.h.value for c in crafts])
+    _ext_keep.extend([crafts, arr, P])
+    L.orc_nl_set_external_plant(ctypes.cast(P.cit_lifted_step, ctypes.c_void_p), ctypes.cast(P.cit_lifted_initialize, ctypes.c_void_p), arr)
+    return crafts
+
+
 def split_fault(name):
     """The reference matches fault names by substring in an if/elif chain
     (envs/nonlinear/env.py:134-158), e.g. 'damp_elevator_and_saturate_elevator' (idhp_nonlin.py:75)."""

@@ -43,6 +43,19 @@ void orc_nl_rls_update(double gamma, double* theta, double* cov, const double* d
     }
 }
 
+/* Optional external plant: `citation.initialize / step` of the reference's OWN model (the translated binary of
+ * oracle/pe_probe, one instance per agent) in place of the surrogate header.  Single-threaded use only. */
+typedef void (*orc_ext_plant_step_fn)(void* instance, const double* u, double* x_out);
+typedef void (*orc_ext_plant_init_fn)(void* instance);
+static orc_ext_plant_step_fn g_ext_step;
+static orc_ext_plant_init_fn g_ext_init;
+static void** g_ext_inst;
+static int64_t g_cur_agent;
+void orc_nl_set_external_plant(orc_ext_plant_step_fn step, orc_ext_plant_init_fn init, void** instances)
+{
+    g_ext_step = step; g_ext_init = init; g_ext_inst = instances;
+}
+
 /* Ce500NonLinear.step without the agent (envs/nonlinear/env.py:182-256): action scaling (:111-124), rate-limited
  * actuators (:161-180), saturation faults (:150-159), damping / c.g. / slow-actuator faults (:127-148), plant step (:210),
  * errors and the longitudinal reward (:215-220).  stepp is the env's counter BEFORE the step. */
@@ -89,9 +102,14 @@ static void orc_nl_env_core(const orc_nl_cfg* c, double theta_ref_k, const doubl
     /* env.py:210  x_full = model.step(input).  The reference's plant binary is an output-then-update block: step() RETURNS
      * the state before the step and then integrates (oracle/pe_probe/README.md), so the wrapper observes the aircraft one
      * sample late.  x_full (the carried state) is advanced; everything the wrapper computes uses the returned x_obs. */
-    memcpy(o->x_obs, x_full, sizeof o->x_obs);
-    if (c->integrator == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(&c->plant, x_full, o->u, dt);
-    else rl4_cit_step_ode5(&c->plant, x_full, o->u, dt);
+    if (g_ext_step) {               /* external plant (the reference's own model): step(u) returns the state before the step */
+        g_ext_step(g_ext_inst[g_cur_agent], o->u, o->x_obs);
+        memcpy(x_full, o->x_obs, sizeof o->x_obs);
+    } else {
+        memcpy(o->x_obs, x_full, sizeof o->x_obs);
+        if (c->integrator == RL4_CIT_INTEGRATOR_RK4) rl4_cit_step_rk4(&c->plant, x_full, o->u, dt);
+        else rl4_cit_step_ode5(&c->plant, x_full, o->u, dt);
+    }
     o->e[0] = o->x_obs[6] - 0.0; o->e[1] = o->x_obs[7] - theta_ref_k; o->e[2] = o->x_obs[8] - 0.0;   /* env.py:215 (state - ref) */
     o->reward = (-0.5 * c->Q_sym) * (o->e[1] * o->e[1]);                           /* env.py:218 */
     o->rg2 = (-c->Q_sym) * o->e[1];
@@ -173,6 +191,7 @@ int orc_nl_init(int policy, const orc_nl_cfg* cfgs, int cfg_stride, const double
     if (!cfgs || !W1a || !W2a || !W1c || !W2c || !st || n < 0) return -1;
     for (int64_t i = 0; i < n; ++i) {
         const orc_nl_cfg* c = cfgs + (cfg_stride ? i : 0);
+        g_cur_agent = i;
         if (policy == ORC_POLICY_MIXED) nl_init_one_mixed(c, W1a + 40 * i, W2a + 10 * i, W1c + 40 * i, W2c + 30 * i, st + i);
         else if (policy == ORC_POLICY_FP64) nl_init_one_fp64(c, W1a + 40 * i, W2a + 10 * i, W1c + 40 * i, W2c + 30 * i, st + i);
         else return -1;

@@ -211,6 +211,9 @@ def load() -> ctypes.CDLL:
     L.rl4_dasmat_initialize.argtypes = [vp, vp]
     L.rl4_dasmat_reset.argtypes = [vp, vp, i64, i64, vp]
     L.rl4_dasmat_step.argtypes = [vp, vp, i64, i64, vp, i64, i32, vp, i64, vp, vp, vp]
+    L.rl4_dasmat_broadcast.argtypes = [vp, i64, i64, vp, i64, i64, vp]
+    L.rl4_nl_env_step_dasmat.argtypes = [ctypes.POINTER(NlParams), vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp]
+    L.rl4_nl_run_dasmat.argtypes = [ctypes.c_int, ctypes.POINTER(NlParams), vp, vp, i64, i32, i32, NlState, i64, SpLog, vp, vp, i64, vp, vp]
     for name in EXPORTS:
         fn = getattr(L, name)
         if name not in _NOT_STATUS:

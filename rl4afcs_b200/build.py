@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "librl4afcs_b200.so")
 SOURCES = ["runtime.cu", "sp_kernels.cu", "nl_kernels.cu", "step_kernels.cu", "host_episode.cu", "dasmat_plant.cu"]
-HEADERS = ["rl4_math.cuh", "sp_core.cuh", "nl_pipeline.cuh", "rl4_runtime.h", os.path.join("..", "..", "include", "rl4afcs_b200.h"),
+HEADERS = ["rl4_math.cuh", "sp_core.cuh", "nl_pipeline.cuh", "nl_core.cuh", "rl4_runtime.h", os.path.join("..", "..", "include", "rl4afcs_b200.h"),
            os.path.join("..", "..", "include", "rl4_citation_surrogate.h")]
 
 NVCC_FLAGS = [
@@ -41,9 +41,9 @@ def _nvcc() -> str:
 # over a minute to compile, the rest seconds)
 _COMMON = ["rl4_math.cuh", "rl4_runtime.h", os.path.join("..", "..", "include", "rl4afcs_b200.h"),
            os.path.join("..", "..", "include", "rl4_citation_surrogate.h")]
-DEPS = {"runtime.cu": _COMMON, "sp_kernels.cu": _COMMON + ["sp_core.cuh"], "nl_kernels.cu": _COMMON + ["nl_pipeline.cuh"],
+DEPS = {"runtime.cu": _COMMON, "sp_kernels.cu": _COMMON + ["sp_core.cuh"], "nl_kernels.cu": _COMMON + ["nl_pipeline.cuh", "nl_core.cuh"],
         "step_kernels.cu": _COMMON, "host_episode.cu": _COMMON,
-        "dasmat_plant.cu": ["rl4_runtime.h", os.path.join("..", "..", "include", "rl4afcs_b200.h"),
+        "dasmat_plant.cu": _COMMON + ["nl_core.cuh",
                             os.path.join("..", "..", "oracle", "pe_probe", "lift_runtime.h")]}
 
 # The 'dasmat' plant is the reference's own aircraft model, translated from its binary (oracle/pe_probe/lift.py).  Nothing

@@ -51,7 +51,7 @@ constexpr uint32_t kBase32 = 0x80000000u;                       // low 32 bits o
 #if RL4_HAVE_DASMAT
 
 #define LIFT_HD __device__ __forceinline__
-#define LIFT_CPU_EXTRA uint8_t* G; uint8_t* m; int err;
+#define LIFT_CPU_EXTRA uint8_t* G; uint8_t* m; int err; int sync;
 #define F_ADD(a, b) __dadd_rn((a), (b))
 #define F_SUB(a, b) __dsub_rn((a), (b))
 #define F_MUL(a, b) __dmul_rn((a), (b))
@@ -162,7 +162,9 @@ LIFT_DEFINE_BULK
 namespace step_mode {
 // m_ is the thread's local array: telling the compiler so turns the accesses into LDL / STL with immediate offsets
 #define LIFT_MEM_CTX uint8_t* const m_ = c->m; const uint8_t* const G_ = c->G; __builtin_assume(__isLocal(m_)); (void)m_; (void)G_;
-#define LIFT_SYNC __syncthreads()      // keeps the warps of a CTA on the same stretch of the (instruction-cache-sized) code
+// keeps the warps of a CTA on the same stretch of the code (far larger than the instruction cache); c->sync is uniform over
+// the CTA by construction (set by the kernels from a CTA-wide vote)
+#define LIFT_SYNC if (c->sync) __syncthreads()
 template <typename T> __device__ __forceinline__ T lift_load(uint8_t* m_, const uint8_t* G_, cpu_t* c, uint32_t a32)
 {
     const uint32_t off = a32 - kBase32;
@@ -202,16 +204,104 @@ LIFT_DEFINE_BULK
 #include "_gen/dasmat_code_step.inc"
 }  // namespace step_mode
 
-// the pristine image (sections at their RVAs), embedded at build time
-static const uint8_t kPristine[] = {
-#include "_gen/dasmat_image.inc"
+// ---- one aircraft inside the fused env + agent kernel (nl_core.cuh, PLANT = 1) ------------------------------------------------
+struct DasmatThread {
+    cpu_t c;
+    __align__(16) uint8_t m[kLocalBytes];
 };
-
+}  // namespace rl4
+#define RL4_NL_WITH_DASMAT 1
+namespace rl4 {
+struct DasmatIo;
+__device__ __forceinline__ void dasmat_thread_load(DasmatThread* t, const DasmatIo& io, int64_t i);
+__device__ __forceinline__ void dasmat_thread_store(DasmatThread* t, const DasmatIo& io, int64_t i);
+__device__ __forceinline__ void dasmat_thread_set_sync(DasmatThread* t, bool on) { t->c.sync = on ? 1 : 0; }
 __device__ __forceinline__ void enter(cpu_t& c)
 {
     // Windows x64 frame at the top of the stack: return address slot at rsp, 32 bytes of home space above it
     c.r[4] = LIFT_BASE + kFlat - 0x100 - 8;
 }
+constexpr uint64_t kArgIn = LIFT_BASE + kFlat - 0x100 + 0x20, kArgOut = kArgIn + 96;   // the caller's buffers, above the frame
+// citation.step(u) -> xo (envs/nonlinear/citation.py:62-69)
+__device__ __forceinline__ void dasmat_thread_step(DasmatThread* t, const double (&u)[11], double (&xo)[12])
+{
+    double* in_p = reinterpret_cast<double*>(t->m + ((uint32_t)kArgIn - kBase32 - kWLo));
+    const double* out_p = reinterpret_cast<const double*>(t->m + ((uint32_t)kArgOut - kBase32 - kWLo));
+#pragma unroll
+    for (int j = 0; j < 11; ++j) in_p[j] = u[j];
+    enter(t->c);
+    t->c.r[1] = kArgOut; t->c.r[2] = kArgIn;
+    step_mode::f_180003720(&t->c);
+#pragma unroll
+    for (int j = 0; j < 12; ++j) xo[j] = out_p[j];
+}
+}  // namespace rl4
+#include "nl_core.cuh"
+namespace rl4 {
+__device__ __forceinline__ void dasmat_thread_load(DasmatThread* t, const DasmatIo& io, int64_t i)
+{
+    uint64_t* wd = reinterpret_cast<uint64_t*>(t->m);
+    uint64_t* wa = reinterpret_cast<uint64_t*>(t->m + kWSz);
+    for (int w = 0; w < (int)(kASz / 8); ++w) wa[w] = io.state[(int64_t)w * io.stride + i];
+    for (int w = 0; w < (int)(kDSz / 8); ++w) wd[w] = io.state[(int64_t)(kASz / 8 + w) * io.stride + i];
+    memset(&t->c, 0, sizeof t->c);
+    t->c.G = io.image; t->c.m = t->m;
+}
+__device__ __forceinline__ void dasmat_thread_store(DasmatThread* t, const DasmatIo& io, int64_t i)
+{
+    const uint64_t* wd = reinterpret_cast<const uint64_t*>(t->m);
+    const uint64_t* wa = reinterpret_cast<const uint64_t*>(t->m + kWSz);
+    for (int w = 0; w < (int)(kASz / 8); ++w) io.state[(int64_t)w * io.stride + i] = wa[w];
+    for (int w = 0; w < (int)(kDSz / 8); ++w) io.state[(int64_t)(kASz / 8 + w) * io.stride + i] = wd[w];
+    if (t->c.err) atomicOr(io.err, t->c.err);
+}
+
+// fused episode launches with the translated plant: float32 networks (the reference's own mix), general hyper-parameters
+template <bool LOG>
+static int dasmat_launch_fused(const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride, int k0,
+                               int n_steps, rl4_nl_state st, int64_t n, rl4_sp_log lg, DasmatIo dio, cudaStream_t s)
+{
+    constexpr int BLK = NlBlock<float>::v;
+    const size_t smem = (sizeof(double) * kNlSmemDoubles + sizeof(float) * kNlSmemNet) * BLK;
+    auto kern = nl_run_kernel<float, RL4_CIT_INTEGRATOR_ODE5, LOG, true, 1>;
+    RL4_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)((n + BLK - 1) / BLK), BLK, smem, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, dio);
+    return check_launch("nl_run_kernel<dasmat>");
+}
+
+// Ce500NonLinear.step with the translated plant, step-API form (envs/nonlinear/env.py:182-256); same outputs as nl_env_step_kernel
+__global__ void __launch_bounds__(RL4_DASMAT_THREADS, RL4_DASMAT_MIN_BLOCKS)
+dasmat_env_step_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict__ theta_ref, int stepp, double* __restrict__ x_full,
+                       double* __restrict__ x_act_p, const double* __restrict__ action, double* __restrict__ out_mdp,
+                       double* __restrict__ out_reward, double* __restrict__ out_e, double* __restrict__ out_surf,
+                       double* __restrict__ out_eff, double* __restrict__ out_x_obs, int64_t S, int64_t n_agents, const DasmatIo dio)
+{
+    const int64_t i_raw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i_raw < n_agents;
+    const int64_t i = active ? i_raw : n_agents - 1;
+    const NlHp<true> hv{p, i};
+    DasmatThread dz;
+    dasmat_thread_load(&dz, dio, i);
+    dz.c.sync = 1;                                  // every thread of the CTA takes the step (tail threads shadow the last aircraft)
+    double x[12], xo[12], xa[3], act[3], surf[3], ueff[3], e_phi, e_th, e_psi, reward, rg2;
+    for (int j = 0; j < 12; ++j) x[j] = x_full[j * S + i];
+    for (int j = 0; j < 3; ++j) { xa[j] = x_act_p[j * S + i]; act[j] = action[j * S + i]; }
+    nl_env_step<true, RL4_CIT_INTEGRATOR_ODE5, 1>(p, hv, stepp, __ldg(theta_ref + stepp), act, x, xa, surf, e_phi, e_th, e_psi, reward, rg2, ueff, xo, &dz);
+    if (!active) return;
+    dasmat_thread_store(&dz, dio, i);
+    for (int j = 0; j < 12; ++j) x_full[j * S + i] = x[j];
+    for (int j = 0; j < 3; ++j) x_act_p[j * S + i] = xa[j];
+    if (out_x_obs) for (int j = 0; j < 12; ++j) out_x_obs[j * S + i] = xo[j];
+    out_mdp[i] = xo[4]; out_mdp[S + i] = xo[7]; out_mdp[2 * S + i] = xo[1]; out_mdp[3 * S + i] = e_th;
+    out_reward[i] = reward; out_e[i] = e_th;
+    if (out_surf) for (int j = 0; j < 3; ++j) out_surf[j * S + i] = surf[j];
+    if (out_eff) for (int j = 0; j < 3; ++j) out_eff[j * S + i] = ueff[j];
+}
+
+// the pristine image (sections at their RVAs), embedded at build time
+static const uint8_t kPristine[] = {
+#include "_gen/dasmat_image.inc"
+};
 
 // initialize() in flat mode: one thread, everything (image + stack) in the global buffer G
 __global__ void dasmat_initialize_kernel(uint8_t* G, int* err)
@@ -252,7 +342,7 @@ dasmat_step_kernel(uint8_t* G, uint64_t* __restrict__ state, int64_t stride, int
     for (int w = 0; w < (int)(kDSz / 8); ++w) wd[w] = state[(int64_t)(kASz / 8 + w) * stride + i];
     cpu_t c;
     memset(&c, 0, sizeof c);
-    c.G = G; c.m = m;
+    c.G = G; c.m = m; c.sync = 1;
     // the caller's buffers sit above the frame, inside the stack region (as a C caller's locals would)
     const uint64_t a_in = LIFT_BASE + kFlat - 0x100 + 0x20, a_out = a_in + 96;
     double* in_p = reinterpret_cast<double*>(m + ((uint32_t)a_in - kBase32 - kWLo));
@@ -271,6 +361,15 @@ dasmat_step_kernel(uint8_t* G, uint64_t* __restrict__ state, int64_t stride, int
     for (int w = 0; w < (int)(kASz / 8); ++w) state[(int64_t)w * stride + i] = wa[w];
     for (int w = 0; w < (int)(kDSz / 8); ++w) state[(int64_t)(kASz / 8 + w) * stride + i] = wd[w];
     if (c.err) atomicOr(err, c.err);
+}
+
+// aircraft `src_index` of one state plane copied to every aircraft of another (the trimmed state after reset)
+__global__ void dasmat_broadcast_kernel(const uint64_t* __restrict__ src, int64_t src_stride, int64_t src_index, uint64_t* __restrict__ dst,
+                                        int64_t dst_stride, int64_t n)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int w = 0; w < kStateWords; ++w) dst[(int64_t)w * dst_stride + i] = src[(int64_t)w * src_stride + src_index];
 }
 
 #endif  // RL4_HAVE_DASMAT
@@ -348,6 +447,61 @@ int rl4_dasmat_step(void* image, uint64_t* state, int64_t stride, int64_t n_agen
 #else
     (void)image; (void)state; (void)stride; (void)n_agents; (void)u; (void)u_stride; (void)n_steps; (void)out; (void)out_stride;
     (void)out_all; (void)device_err; (void)stream;
+    return no_plant();
+#endif
+}
+
+int rl4_dasmat_broadcast(const uint64_t* src, int64_t src_stride, int64_t src_index, uint64_t* dst, int64_t dst_stride, int64_t n_agents,
+                         void* stream)
+{
+#if RL4_HAVE_DASMAT
+    RL4_REQUIRE(src && dst && src_index >= 0 && src_stride > src_index && dst_stride >= n_agents && n_agents > 0, "bad arguments");
+    dasmat_broadcast_kernel<<<(unsigned)((n_agents + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, src_stride, src_index, dst, dst_stride, n_agents);
+    return check_launch("dasmat_broadcast_kernel");
+#else
+    (void)src; (void)src_stride; (void)src_index; (void)dst; (void)dst_stride; (void)n_agents; (void)stream;
+    return no_plant();
+#endif
+}
+
+int rl4_nl_env_step_dasmat(const rl4_nl_params* p, const double* theta_ref, int32_t stepp, double* x_full, double* x_act,
+                           const double* action, double* out_mdp, double* out_reward, double* out_e_theta, double* out_surf,
+                           double* out_eff, double* out_x_obs, int64_t stride, int64_t n, void* image, uint64_t* plant_state,
+                           int64_t plant_stride, int32_t* device_err, void* stream)
+{
+#if RL4_HAVE_DASMAT
+    RL4_REQUIRE(p && theta_ref && x_full && x_act && action && out_mdp && out_reward && out_e_theta && image && plant_state && device_err, "NULL argument");
+    RL4_REQUIRE(n >= 0 && stride >= n && plant_stride >= n && stepp >= 0, "bad size");
+    if (n == 0) return 0;
+    const DasmatIo dio{(uint8_t*)image, plant_state, plant_stride, device_err};
+    dasmat_env_step_kernel<<<(unsigned)((n + RL4_DASMAT_THREADS - 1) / RL4_DASMAT_THREADS), RL4_DASMAT_THREADS, 0, (cudaStream_t)stream>>>(
+        *p, theta_ref, stepp, x_full, x_act, action, out_mdp, out_reward, out_e_theta, out_surf, out_eff, out_x_obs, stride, n, dio);
+    return check_launch("dasmat_env_step_kernel");
+#else
+    (void)p; (void)theta_ref; (void)stepp; (void)x_full; (void)x_act; (void)action; (void)out_mdp; (void)out_reward; (void)out_e_theta;
+    (void)out_surf; (void)out_eff; (void)out_x_obs; (void)stride; (void)n; (void)image; (void)plant_state; (void)plant_stride;
+    (void)device_err; (void)stream;
+    return no_plant();
+#endif
+}
+
+int rl4_nl_run_dasmat(int policy, const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride,
+                      int32_t k0, int32_t n_steps, rl4_nl_state st, int64_t n, rl4_sp_log lg, void* image, uint64_t* plant_state,
+                      int64_t plant_stride, int32_t* device_err, void* stream)
+{
+#if RL4_HAVE_DASMAT
+    RL4_REQUIRE(p && theta_ref && noise && st.env && st.net && st.ints && image && plant_state && device_err, "NULL argument");
+    RL4_REQUIRE(n >= 0 && st.stride >= n && noise_stride >= n && plant_stride >= n && k0 >= 0 && n_steps >= 0, "bad size");
+    RL4_REQUIRE(policy == RL4_MIXED, "the dasmat plant runs with float32 networks (policy mixed, the reference's own arithmetic)");
+    if (lg.level != RL4_LOG_NONE) RL4_REQUIRE(lg.level >= 1 && lg.level <= 3 && lg.buf && lg.every >= 1 && lg.n_agents_logged >= 0 && lg.n_agents_logged <= n, "bad log descriptor");
+    if (n == 0 || n_steps == 0) return 0;
+    const DasmatIo dio{(uint8_t*)image, plant_state, plant_stride, device_err};
+    cudaStream_t s = (cudaStream_t)stream;
+    return lg.level != RL4_LOG_NONE ? dasmat_launch_fused<true>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, dio, s)
+                                    : dasmat_launch_fused<false>(p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, dio, s);
+#else
+    (void)policy; (void)p; (void)theta_ref; (void)noise; (void)noise_stride; (void)k0; (void)n_steps; (void)st; (void)n; (void)lg;
+    (void)image; (void)plant_state; (void)plant_stride; (void)device_err; (void)stream;
     return no_plant();
 #endif
 }

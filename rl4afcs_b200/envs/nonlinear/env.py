@@ -22,7 +22,7 @@ from ... import _lib, nl_engine
 
 class Ce500NonLinear:
     def __init__(self, env_config, render_mode=None, *, batch: int = 1, device="cuda", dtype: str = "mixed",
-                 integrator: str = "ode5"):
+                 integrator: str = "ode5", plant: str = "surrogate"):
         self.batch = int(batch)
         self.fault_scenario = env_config["fault_scenario"]
         self.initialized = False
@@ -39,7 +39,9 @@ class Ce500NonLinear:
         self.action = None
         self.tracked_state = env_config["reference"]["tracked_state"]
         self.state_reference = env_config["reference"]["signal"]
-        self._engine = nl_engine.NlEngine(self.batch, policy=dtype, device=device)
+        # plant: "surrogate" = the calibrated stand-in (fast), "dasmat" = the reference's own model translated from its binary
+        self.plant = plant
+        self._engine = nl_engine.NlEngine(self.batch, policy=dtype, device=device, plant=plant)
         self.device = self._engine.device
         eng = self._engine
         eng.params.dt = self.dt
@@ -99,6 +101,8 @@ class Ce500NonLinear:
     @property
     def plant_state(self) -> torch.Tensor:
         """(B, 12) the state the plant carries into its next step."""
+        if self._engine.dasmat is not None:
+            return self._engine.dasmat.x
         return self._engine.env_field("XFULL", 12).t()
 
     # ---- gymnasium-style API ----
@@ -109,8 +113,11 @@ class Ce500NonLinear:
         self.initialized = True
         self.stepp = 0
         self.t = 0
-        obs = (ctypes.c_double * 12)()
-        _lib.check(eng.lib.rl4_nl_trim_state(ctypes.byref(eng.params), None, obs), "rl4_nl_trim_state")
+        if eng.dasmat is not None:
+            obs = eng.trim_obs
+        else:
+            obs = (ctypes.c_double * 12)()
+            _lib.check(eng.lib.rl4_nl_trim_state(ctypes.byref(eng.params), None, obs), "rl4_nl_trim_state")
         self._obs = torch.tensor(list(obs), dtype=torch.float64, device=self.device).repeat(self.batch, 1)   # env.py:291
         MDP_state = torch.zeros((self.batch, self.mdp_s_dim), dtype=torch.float64, device=self.device)
         info = {"nans": False, "s": MDP_state, "yref": np.zeros(3), "action": np.zeros(3), "rates": np.zeros(3), "t": self.t,
@@ -137,11 +144,18 @@ class Ce500NonLinear:
         eff = torch.empty((3, B), dtype=torch.float64, device=dev)
         xobs = torch.empty((12, B), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
-            rc = eng.lib.rl4_nl_env_step(ctypes.byref(eng.params), eng.theta_ref.data_ptr(), self.stepp,
-                                         eng.env_field("XFULL", 12).data_ptr(), eng.env_field("XACT", 3).data_ptr(),
-                                         act_p.data_ptr(), mdp.data_ptr(), reward_lon.data_ptr(), e_th.data_ptr(),
-                                         surf.data_ptr(), eff.data_ptr(), xobs.data_ptr(), eng.stride, B, eng._stream())
-            _lib.check(rc, "rl4_nl_env_step")
+            args = (ctypes.byref(eng.params), eng.theta_ref.data_ptr(), self.stepp,
+                    eng.env_field("XFULL", 12).data_ptr(), eng.env_field("XACT", 3).data_ptr(),
+                    act_p.data_ptr(), mdp.data_ptr(), reward_lon.data_ptr(), e_th.data_ptr(),
+                    surf.data_ptr(), eff.data_ptr(), xobs.data_ptr(), eng.stride, B)
+            if eng.dasmat is not None:
+                dz = eng.dasmat
+                rc = eng.lib.rl4_nl_env_step_dasmat(*args, dz.image.data_ptr(), dz.state.data_ptr(), dz.stride, dz.err.data_ptr(), eng._stream())
+                _lib.check(rc, "rl4_nl_env_step_dasmat")
+                dz.check()
+            else:
+                rc = eng.lib.rl4_nl_env_step(*args, eng._stream())
+                _lib.check(rc, "rl4_nl_env_step")
         self._obs = xobs.t()                                                            # self.state = model.step(input) (env.py:210)
         ref = [r[self.stepp] for r in self.state_reference]
         self.stepp += 1

@@ -41,10 +41,81 @@ def split_fault(name):
     return damp, sat
 
 
+_DASMAT_IMAGE = {}      # device index -> the model's memory image after initialize() (shared by every engine on that device)
+_DASMAT_TRIM = {}       # (device index, trim input, steps) -> (state words of one trimmed aircraft, what the last reset call returned)
+
+
+class DasmatPlant:
+    """The reference's own aircraft model on the GPU (`_citation.initialize/step`, envs/nonlinear/citation.py:62-69), translated
+    from its binary at build time (csrc/dasmat_plant.cu).  Holds the per-aircraft model memory of one batch."""
+
+    def __init__(self, lib, device, n, stride):
+        if not lib.rl4_dasmat_available():
+            raise _lib.Rl4Error("plant='dasmat': this librl4afcs_b200.so was built without the reference's plant binary "
+                                "(csrc/_gen/ is produced by oracle/pe_probe/lift.py where /root/reference exists)")
+        self.lib, self.device, self.n, self.stride = lib, device, n, stride
+        self.words = lib.rl4_dasmat_state_words()
+        self.word_x, self.word_engine = lib.rl4_dasmat_word_x(), lib.rl4_dasmat_word_engine()
+        if device.index not in _DASMAT_IMAGE:
+            img = torch.zeros(lib.rl4_dasmat_image_bytes(), dtype=torch.uint8, device=device)
+            with torch.cuda.device(device):
+                _lib.check(lib.rl4_dasmat_initialize(img.data_ptr(), self._stream()), "rl4_dasmat_initialize")
+            _DASMAT_IMAGE[device.index] = img
+        self.image = _DASMAT_IMAGE[device.index]
+        self.state = torch.zeros((self.words, stride), dtype=torch.int64, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self, trim_input, n_steps):
+        """Ce500NonLinear.reset (envs/nonlinear/env.py:278-291): initialize(), then `n_steps` calls of step(trim input).  Every
+        aircraft starts identically, so one warp flies the settling phase once per process and the result is broadcast.
+        Returns what the last call returned (12 doubles on the host)."""
+        key = (self.device.index, tuple(float(v) for v in trim_input), int(n_steps))
+        if key not in _DASMAT_TRIM:
+            nb = 32
+            st = torch.zeros((self.words, nb), dtype=torch.int64, device=self.device)
+            u = torch.tensor(key[1], dtype=torch.float64, device=self.device).reshape(11, 1).repeat(1, nb).contiguous()
+            out = torch.zeros((12, nb), dtype=torch.float64, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.rl4_dasmat_reset(self.image.data_ptr(), st.data_ptr(), nb, nb, self._stream()), "rl4_dasmat_reset")
+                _lib.check(self.lib.rl4_dasmat_step(self.image.data_ptr(), st.data_ptr(), nb, nb, u.data_ptr(), nb, int(n_steps),
+                                                    out.data_ptr(), nb, None, self.err.data_ptr(), self._stream()), "rl4_dasmat_step")
+            self.check()
+            _DASMAT_TRIM[key] = (st, out[:, 0].cpu().numpy().copy())
+        st, x_obs = _DASMAT_TRIM[key]
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.rl4_dasmat_broadcast(st.data_ptr(), st.shape[1], 0, self.state.data_ptr(), self.stride, self.n,
+                                                     self._stream()), "rl4_dasmat_broadcast")
+        return x_obs
+
+    def check(self):
+        e = int(self.err.item())
+        if e:
+            self.err.zero_()
+            raise _lib.Rl4Error(f"dasmat plant: the translated model raised error bits {e:#x} (1 untranslated path, 2 wild access, "
+                                "4 store into the shared image)")
+
+    @property
+    def x(self) -> torch.Tensor:
+        """(n, 12) the continuous airframe states the model carries [p q r V alpha beta phi theta psi h xe ye]"""
+        return self.state[self.word_x:self.word_x + 12, : self.n].view(torch.float64).t()
+
+    @property
+    def engine(self) -> torch.Tensor:
+        """(n, 4) the engine states (two per engine)"""
+        return self.state[self.word_engine:self.word_engine + 4, : self.n].view(torch.float64).t()
+
+
 class NlEngine:
-    def __init__(self, n_agents: int, *, policy: str = "mixed", device="cuda"):
+    def __init__(self, n_agents: int, *, policy: str = "mixed", device="cuda", plant: str = "surrogate"):
         if policy not in ("mixed", "fp64"):
             raise _lib.Rl4Error("the nonlinear path supports the 'mixed' and 'fp64' policies")
+        if plant not in ("surrogate", "dasmat"):
+            raise _lib.Rl4Error("plant must be 'surrogate' (calibrated stand-in, fast) or 'dasmat' (the reference's own model)")
+        if plant == "dasmat" and policy != "mixed":
+            raise _lib.Rl4Error("plant='dasmat' runs with the 'mixed' policy (float32 networks, the reference's own arithmetic)")
         self.lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -65,6 +136,9 @@ class NlEngine:
         self._keep = {}
         self.theta_ref = None
         self.k = 0
+        self.plant = plant
+        self.dasmat = DasmatPlant(self.lib, self.device, self.n, self.stride) if plant == "dasmat" else None
+        self.trim_obs = None
 
     def set_hp(self, name, value):
         j = NHP[name]
@@ -116,6 +190,11 @@ class NlEngine:
             rc = self.lib.rl4_nl_init(self.policy_id, ctypes.byref(self.params), a1.data_ptr(), a2.data_ptr(), c1.data_ptr(),
                                       c2.data_ptr(), self.n, self.state_struct(), self.n, self._stream())
             _lib.check(rc, "rl4_nl_init")
+            if self.dasmat is not None:
+                # reset on the reference's own model: initialize() + 1001 trim calls (envs/nonlinear/env.py:288-291)
+                n_trim = int(10.0 / self.params.dt) + 1
+                self.trim_obs = self.dasmat.reset([self.params.trim_input[j] for j in range(11)], n_trim)
+                self.env_field("XFULL", 12).copy_(torch.as_tensor(self.trim_obs, device=self.device).reshape(12, 1).expand(12, self.n))
         self.k = 0
 
     def run(self, n_steps, noise, *, log_agents=0, log_every=1, log_level=1):
@@ -133,9 +212,17 @@ class NlEngine:
             log_t = torch.empty((rows, nf, log_agents), dtype=torch.float64, device=self.device)
             lg = _lib.SpLog(log_t.data_ptr(), int(log_level), log_every, log_agents)
         with torch.cuda.device(self.device):
-            rc = self.lib.rl4_nl_run(self.policy_id, ctypes.byref(self.params), self.theta_ref.data_ptr(), noise.data_ptr(),
-                                     self.n, self.k, n_steps, self.state_struct(), self.n, lg, self._stream())
-            _lib.check(rc, "rl4_nl_run")
+            if self.dasmat is not None:
+                dz = self.dasmat
+                rc = self.lib.rl4_nl_run_dasmat(self.policy_id, ctypes.byref(self.params), self.theta_ref.data_ptr(), noise.data_ptr(),
+                                                self.n, self.k, n_steps, self.state_struct(), self.n, lg, dz.image.data_ptr(),
+                                                dz.state.data_ptr(), dz.stride, dz.err.data_ptr(), self._stream())
+                _lib.check(rc, "rl4_nl_run_dasmat")
+                dz.check()
+            else:
+                rc = self.lib.rl4_nl_run(self.policy_id, ctypes.byref(self.params), self.theta_ref.data_ptr(), noise.data_ptr(),
+                                         self.n, self.k, n_steps, self.state_struct(), self.n, lg, self._stream())
+                _lib.check(rc, "rl4_nl_run")
         self.k += n_steps
         return log_t
 

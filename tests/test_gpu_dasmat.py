@@ -1,0 +1,190 @@
+"""GPU: the reference's OWN nonlinear aircraft (plant='dasmat': the `_citation` binary translated at build time, csrc/dasmat_plant.cu)
+against (1) the golden trajectories of the binary itself (tests/golden/citation_*.npz, produced by the .pyd executing natively),
+(2) the CPU build of the same translation (bit-identical to the binary, tests/test_citation_lifted.py) on fresh inputs, and
+(3) the CPU oracle's wrapper + agent running on that CPU plant.
+
+Tolerance, not bit parity, and why: the model code is executed instruction for instruction, but the eight C-runtime functions
+it imports (sin cos tan exp log10 pow floor sqrt) are CUDA's on the device, glibc's in the fixtures, the Windows UCRT's on the
+reference's own platform -- 1-2 ulp apart per call.  Per step that is ~1e-15 relative; bounds below are 1e-11 open loop."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+TRIM = np.array([-0.02855, 0, 0, 0, 0, 0, 0, 0, 0.55, 0.55, 0])
+SCALE = np.array([0.1, 0.1, 0.1, 90, 0.06, 0.05, 0.1, 0.06, 0.1, 2000, 1000, 100.0])     # state magnitudes for relative errors
+
+
+@pytest.fixture(scope="module")
+def plant():
+    from rl4afcs_b200 import _lib
+
+    L = _lib.load()
+    if not L.rl4_dasmat_available():
+        pytest.fail("librl4afcs_b200.so was built without the reference's plant binary (rl4afcs_b200/csrc/_gen/ missing at build time)")
+    dev = torch.device("cuda:0")
+    img = torch.zeros(L.rl4_dasmat_image_bytes(), dtype=torch.uint8, device=dev)
+    _lib.check(L.rl4_dasmat_initialize(img.data_ptr(), None), "rl4_dasmat_initialize")
+    return L, _lib, dev, img
+
+
+def _fresh(plant, n):
+    L, _lib, dev, img = plant
+    st = torch.zeros((L.rl4_dasmat_state_words(), n), dtype=torch.int64, device=dev)
+    _lib.check(L.rl4_dasmat_reset(img.data_ptr(), st.data_ptr(), n, n, None), "rl4_dasmat_reset")
+    return st, torch.zeros(1, dtype=torch.int32, device=dev)
+
+
+@pytest.mark.parametrize("name", ["trim", "elevator_doublet_large", "aileron_rudder", "shift_cg"])
+def test_translated_plant_replays_the_binarys_golden_trajectories(plant, name):
+    L, _lib, dev, img = plant
+    g = np.load(os.path.join(GOLD, f"citation_{name}.npz"))
+    u, x = g["u"], g["x"]
+    n = 32
+    st, err = _fresh(plant, n)
+    ud = torch.tensor(u.T.copy(), device=dev)
+    out = torch.zeros((u.shape[0], 12, n), dtype=torch.float64, device=dev)
+    ucol = torch.zeros((11, n), dtype=torch.float64, device=dev)
+    for k in range(u.shape[0]):
+        ucol.copy_(ud[:, k:k + 1].expand(11, n))
+        _lib.check(L.rl4_dasmat_step(img.data_ptr(), st.data_ptr(), n, n, ucol.data_ptr(), n, 1, out[k].data_ptr(), n, None, err.data_ptr(), None), "rl4_dasmat_step")
+    o = out.cpu().numpy()
+    assert int(err.item()) == 0
+    assert np.array_equal(o[:, :, 0], o[:, :, n - 1])                          # every lane flies the same aircraft
+    assert np.array_equal(o[0, :, 0], x[0])                                     # the initial condition is returned first, exactly
+    rel = np.abs(o[:, :, 0] - x) / SCALE
+    assert rel.max() < 1e-11, rel.max(axis=0)
+    # the engine states the model carries at the end (two per engine)
+    eng = st[L.rl4_dasmat_word_engine():L.rl4_dasmat_word_engine() + 4, 0].view(torch.float64).cpu().numpy()
+    assert np.allclose(eng, g["engine_final"], rtol=1e-11, atol=0)
+
+
+def test_translated_plant_equals_its_cpu_build_on_distinct_aircraft(plant):
+    """64 aircraft, each with its own piecewise-constant command on every input channel (surfaces, flap, gear, throttles,
+    c.g. shift): one launch per command segment, every returned state against the CPU build of the same translation."""
+    from oracle.pe_probe import lifted
+
+    if not lifted.available():
+        pytest.skip("the compiled CPU translation is not present")
+    L, _lib, dev, img = plant
+    n, seg, n_seg = 64, 25, 8
+    rng = np.random.default_rng(3)
+    st, err = _fresh(plant, n)
+    crafts = [lifted.Aircraft() for _ in range(n)]
+    for c in crafts:
+        c.initialize()
+    worst = 0.0
+    for s in range(n_seg):
+        u = np.tile(TRIM, (n, 1))
+        u[:, 0:3] += rng.uniform(-0.06, 0.06, (n, 3))
+        u[:, 6] = rng.choice([0.0, 0.3, 1.0], n); u[:, 7] = rng.choice([0.0, 1.0], n)
+        u[:, 8:10] = rng.uniform(0.3, 0.9, (n, 2)); u[:, 10] = rng.choice([0.0, -0.5, 0.3], n)
+        ud = torch.tensor(u.T.copy(), device=dev)
+        out_all = torch.zeros((seg, 12, n), dtype=torch.float64, device=dev)
+        _lib.check(L.rl4_dasmat_step(img.data_ptr(), st.data_ptr(), n, n, ud.data_ptr(), n, seg, None, n, out_all.data_ptr(), err.data_ptr(), None), "rl4_dasmat_step")
+        got = out_all.cpu().numpy()
+        for i, c in enumerate(crafts):
+            ref = c.run(u[i], seg)
+            worst = max(worst, float((np.abs(got[:, :, i] - ref) / SCALE).max()))
+    assert int(err.item()) == 0
+    assert worst < 1e-10, worst
+
+
+def _cfg():
+    from rl4afcs_b200 import nl_engine
+
+    th = nl_engine.theta_reference()
+    z = np.zeros_like(th)
+    return {"fault_scenario": None, "dt": 0.01, "t_end": 90, "total_steps": 9000, "fault_time": 60,
+            "trim_state": [0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0], "trim_input": TRIM.tolist(), "state_dim": 4,
+            "reference": {"tracked_state": [6, 7, 8], "signal": [z, th, z]}}
+
+
+def test_env_reset_and_step_run_on_the_reference_model(plant):
+    """Ce500NonLinear(plant='dasmat'): reset() = initialize() + 1001 trim calls, step() = wrapper + citation.step, against the CPU
+    translation flown with the same commands (zero action: the actuators stay at rest, the command is the trim input)."""
+    from oracle.pe_probe import lifted
+    from rl4afcs_b200.envs.nonlinear.env import Ce500NonLinear
+
+    if not lifted.available():
+        pytest.skip("the compiled CPU translation is not present")
+    env = Ce500NonLinear(_cfg(), batch=5, plant="dasmat")
+    env.reset()
+    ac = lifted.Aircraft(); ac.initialize()
+    ref = ac.run(TRIM, 1001 + 40)
+    assert np.abs(env.state.cpu().numpy() - ref[1000]).max() < 1e-9 * 2000          # what the 1001st call returned (env.py:291)
+    for k in range(40):
+        s, r, _, _, info = env.step(np.zeros(3))
+        got = info["x_full"].cpu().numpy()
+        assert (np.abs(got - ref[1001 + k]) / SCALE).max() < 1e-10, k
+        assert np.allclose(s.cpu().numpy()[:, :3], ref[1001 + k][[4, 7, 1]], rtol=0, atol=1e-12)
+    assert (np.abs(env.plant_state.cpu().numpy() - ac.get_state()[0]) / SCALE).max() < 1e-10
+
+
+def test_idhpnonlin_on_the_reference_model_tracks_the_oracle(oracle):
+    """The fused env + agent kernel with the translated plant against the CPU oracle's wrapper + agent running on the CPU
+    translation: free-running from the same weights and noise.  The two plants differ by ulps in libm, the closed loop amplifies
+    that, so the comparison is tight early and statistical later."""
+    from oracle import nl_c
+    from oracle.pe_probe import lifted
+    from rl4afcs_b200 import _lib, nl_engine
+    from tests import _util_nl
+
+    if not lifted.available():
+        pytest.skip("the compiled CPU translation is not present")
+    n, steps = 6, 400
+    nl_c.lib()
+    cfg = nl_c.make_cfg()
+    w = nl_c.init_weights(n, 7)
+    nl_c.set_external_plant(n)
+    try:
+        st = nl_c.init_states("mixed", cfg, w, n)
+        eng = nl_engine.NlEngine(n, policy="mixed", plant="dasmat")
+        eng.set_hpi("FAULT_STEP", int(cfg["fault_step"][0]))
+        th = nl_c.theta_reference()
+        eng.set_reference(th)
+        eng.init(w["W1a"], w["W2a"], w["W1c"], w["W2c"])
+        noise = np.random.default_rng(2).standard_normal((steps, n)).astype(np.float32)
+        olog = nl_c.run("mixed", cfg, th, noise, st, 0, steps, tanh="t13", n_log=n)
+        lg = eng.run(steps, noise, log_agents=n).cpu().numpy()
+    finally:
+        nl_c.set_external_plant(0)
+    x_gpu = np.transpose(lg[:, _lib.NLL["XFULL"]:_lib.NLL["XFULL"] + 12, :], (2, 0, 1))
+    assert (np.abs(x_gpu[:, 0] - olog["x_full"][:, 0]) / SCALE).max() < 1e-9          # the trimmed state after reset
+    assert _util_nl.max_rel(x_gpu[:, :150, :9], olog["x_full"][:, :150, :9], 1e-2) < 1e-5
+    got = _util_nl.engine_to_oracle(eng, nl_c)
+    assert np.array_equal(got["diverged_step"] >= 0, st["diverged_step"] >= 0)
+    assert np.array_equal(got["stepp"], st["stepp"])
+
+
+def test_agents_learn_to_track_on_the_reference_model():
+    """With the reference's hyper-parameters (idhp_nonlin.py:123-146) IDHP agents learn to track the pitch reference on the
+    reference's own aircraft (what profiles/citation_closed_loop_r02.json reports for the verbatim agent on the binary)."""
+    from rl4afcs_b200 import nl_engine
+    from oracle import nl_c
+
+    n, steps = 192, 3000
+    eng = nl_engine.NlEngine(n, policy="mixed", plant="dasmat")
+    eng.set_hpi("FAULT_STEP", -1)
+    th = nl_engine.theta_reference()
+    eng.set_reference(th)
+    w = nl_c.init_weights(n, 1)
+    eng.init(w["W1a"], w["W2a"], w["W1c"], w["W2c"])
+    g = torch.Generator(device="cuda").manual_seed(0)
+    from rl4afcs_b200 import _lib
+    e_all = []
+    for k0 in range(0, steps, 1000):
+        noise = torch.randn((1000, n), generator=g, device="cuda", dtype=torch.float32)
+        lg = eng.run(1000, noise, log_agents=n)
+        e_all.append(lg[:, _lib.NLL["E_THETA"], :])
+    e = torch.cat(e_all).abs().cpu().numpy()                                       # (steps, n)
+    alive = ~eng.stats()["diverged"].cpu().numpy()
+    assert alive.mean() > 0.9, alive.mean()
+    late = np.degrees(e[2000:, alive].mean(axis=0))
+    assert np.median(late) < 1.5, np.median(late)
