@@ -1,4 +1,4 @@
-/* lift_runtime.h -- machine model under the code that oracle/pe_probe/lift.py generates from the reference's plant binary
+/* rl4_lift_runtime.h -- machine model under the code that rl4afcs_b200/tools/lift_plant.py generates from the reference's plant binary
  * (envs/nonlinear/<variant>/_citation.cp39-win_amd64.pyd; /root/reference/envs/nonlinear/citation.py:62-69).
  *
  * The generated code is a sequence of x86-64 instructions spelled as C statements over this state: 16 integer

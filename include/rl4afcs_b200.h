@@ -482,7 +482,7 @@ int rl4_nl_episode_host(rl4_ctx* ctx, const rl4_nl_params* p, const rl4_nl_host_
 /* ---- the reference's own nonlinear aircraft ("dasmat" plant) -----------------------------------------------------------
  * Replaces `_citation.initialize / step / terminate` (envs/nonlinear/citation.py:62-69; called at envs/nonlinear/env.py:210,
  * 288-291): the DASMAT Citation model the reference ships as a Windows binary, translated from that binary's machine code at
- * build time (oracle/pe_probe/lift.py -> rl4afcs_b200/csrc/_gen/, only where the reference tree exists) and compiled for
+ * build time (rl4afcs_b200/tools/lift_plant.py -> rl4afcs_b200/csrc/_gen/, only where the reference tree exists) and compiled for
  * sm_100a, one aircraft per thread.  A library built without the binary exports the same symbols; they return -2 and
  * rl4_last_error() says so.  Buffers (all device memory, caller-owned):
  *   image        rl4_dasmat_image_bytes() bytes: the model's memory image after initialize(); shared, read-only afterwards

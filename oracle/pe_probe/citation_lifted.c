@@ -1,8 +1,8 @@
-/* TEST INFRASTRUCTURE -- CPU build of the translated plant binary (oracle/pe_probe/lift.py) -> oracle/_ref/libcitation_lifted.so.
+/* TEST INFRASTRUCTURE -- CPU build of the translated plant binary (rl4afcs_b200/tools/lift_plant.py) -> oracle/_ref/libcitation_lifted.so.
  *
  * Same three entry points as the reference's `citation` module (envs/nonlinear/citation.py:62-69), but re-entrant: every
  * instance owns its flat memory (DLL image + heap + stack), so any number of aircraft can be stepped side by side and the
- * library runs where the .pyd cannot (no x86 / no Windows ABI needed -- only this file, lift_runtime.h and the generated
+ * library runs where the .pyd cannot (no x86 / no Windows ABI needed -- only this file, include/rl4_lift_runtime.h and the generated
  * .inc).  Checked bit for bit against the binary executing natively (pe_citation.c) by tests/test_citation_lifted.py.
  */
 #include <math.h>
@@ -17,7 +17,7 @@
 #define LIFT_MEM_SIZE   (LIFT_IMAGE_SIZE + LIFT_HEAP_SIZE + LIFT_STACK_SIZE)
 
 #define LIFT_CPU_EXTRA uint8_t* M; uint64_t n_ins; uint8_t* wmask;
-#include "lift_runtime.h"
+#include "../../include/rl4_lift_runtime.h"
 
 static void lift_trap(const char* msg, uint64_t v)
 {
@@ -51,6 +51,30 @@ static inline uint8_t* lift_wptr(cpu_t* c, uint64_t a, unsigned n)
 #define ST16(a, v) LIFT_ST(uint16_t, a, v)
 #define ST32(a, v) LIFT_ST(uint32_t, a, v)
 #define ST64(a, v) LIFT_ST(uint64_t, a, v)
+/* region hints of the translator (W: writable window of .data, I: read-only image): same flat memory here, but every hinted
+ * access is CHECKED against the region it claims -- the CUDA build trusts the hints */
+static inline uint32_t lift_chk(cpu_t* c, uint32_t a32, int window)
+{
+    const uint32_t off = a32 - (uint32_t)LIFT_BASE;
+    (void)c;
+    if (window ? !(off - 0x3a000u < 0x2200u) : !(off - 0x13000u < 0x27000u && !(off - 0x2eb00u < 0x100u)))
+        lift_trap(window ? "an access hinted as 'window' left the window" : "an access hinted as 'read-only image' left it", a32);
+    return a32;
+}
+#define LDW8(a) LD8(lift_chk(c, (a), 1))
+#define LDW16(a) LD16(lift_chk(c, (a), 1))
+#define LDW32(a) LD32(lift_chk(c, (a), 1))
+#define LDW64(a) LD64(lift_chk(c, (a), 1))
+#define LDWD(a) LDD(lift_chk(c, (a), 1))
+#define STW8(a, v) ST8(lift_chk(c, (a), 1), v)
+#define STW16(a, v) ST16(lift_chk(c, (a), 1), v)
+#define STW32(a, v) ST32(lift_chk(c, (a), 1), v)
+#define STW64(a, v) ST64(lift_chk(c, (a), 1), v)
+#define LDI8(a) LD8(lift_chk(c, (a), 0))
+#define LDI16(a) LD16(lift_chk(c, (a), 0))
+#define LDI32(a) LD32(lift_chk(c, (a), 0))
+#define LDI64(a) LD64(lift_chk(c, (a), 0))
+#define LDID(a) LDD(lift_chk(c, (a), 0))
 #define LDS8 LD8
 #define LDS16 LD16
 #define LDS32 LD32

@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE ONLY -- ctypes front-end of the TRANSLATED plant binary (oracle/_ref/libcitation_lifted_<variant>.so,
-built by oracle/pe_probe/build_lifted.sh from the reference's .pyd where /root/reference exists; the compiled library and the
+built by oracle/pe_probe/build_lifted.sh (translator: rl4afcs_b200/tools/lift_plant.py) from the reference's .pyd where /root/reference exists; the compiled library and the
 image file travel to the GPU box with oracle/_ref/).  Unlike pe_citation (the binary executing natively, one process-global
 model) this is re-entrant: any number of aircraft, any host architecture."""
 from __future__ import annotations

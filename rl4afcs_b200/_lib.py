@@ -140,9 +140,12 @@ EXPORTS = [
     "rl4_sizeof_sp_params", "rl4_sizeof_nl_params", "rl4_soft_update", "rl4_actor_weight_update", "rl4_sp_agent_stats",
     "rl4_nl_agent_stats", "rl4_stats_reduce_work_doubles", "rl4_stats_reduce", "rl4_nl_noise_fill", "rl4_nl_episode_host", "rl4_test_rcp_f32",
     "rl4_nl_trim_state",
+    "rl4_dasmat_available", "rl4_dasmat_image_bytes", "rl4_dasmat_state_words", "rl4_dasmat_word_x", "rl4_dasmat_word_engine",
+    "rl4_dasmat_initialize", "rl4_dasmat_reset", "rl4_dasmat_step", "rl4_dasmat_broadcast", "rl4_nl_env_step_dasmat", "rl4_nl_run_dasmat",
 ]
 _NOT_STATUS = ("rl4_last_error", "rl4_launch_count", "rl4_abi_version", "rl4_sizeof_sp_params", "rl4_sizeof_nl_params",
-               "rl4_stats_reduce_work_doubles")
+               "rl4_stats_reduce_work_doubles", "rl4_dasmat_available", "rl4_dasmat_image_bytes", "rl4_dasmat_state_words",
+               "rl4_dasmat_word_x", "rl4_dasmat_word_engine")
 
 _lib = None
 

@@ -44,14 +44,14 @@ _COMMON = ["rl4_math.cuh", "rl4_runtime.h", os.path.join("..", "..", "include", 
 DEPS = {"runtime.cu": _COMMON, "sp_kernels.cu": _COMMON + ["sp_core.cuh"], "nl_kernels.cu": _COMMON + ["nl_pipeline.cuh", "nl_core.cuh"],
         "step_kernels.cu": _COMMON, "host_episode.cu": _COMMON,
         "dasmat_plant.cu": _COMMON + ["nl_core.cuh",
-                            os.path.join("..", "..", "oracle", "pe_probe", "lift_runtime.h")]}
+                            os.path.join("..", "..", "include", "rl4_lift_runtime.h")]}
 
-# The 'dasmat' plant is the reference's own aircraft model, translated from its binary (oracle/pe_probe/lift.py).  Nothing
+# The 'dasmat' plant is the reference's own aircraft model, translated from its binary (tools/lift_plant.py).  Nothing
 # derived from the binary is committed: csrc/_gen/ is produced here, where the reference exists, and compiled into the
 # library; without it dasmat_plant.cu compiles to entry points that report "built without the reference's plant binary".
 GEN_DIR = os.path.join(CSRC, "_gen")
 PLANT_BINARY = "/root/reference/envs/nonlinear/extended_input/_citation.cp39-win_amd64.pyd"
-LIFTER = os.path.join(_HERE, "..", "oracle", "pe_probe", "lift.py")
+LIFTER = os.path.join(_HERE, "tools", "lift_plant.py")
 
 
 def _generate_plant() -> None:

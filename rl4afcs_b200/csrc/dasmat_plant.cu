@@ -1,8 +1,8 @@
 // The reference's OWN nonlinear aircraft on the GPU (row a25: `_citation.step`, envs/nonlinear/citation.py:62-69, called at
 // envs/nonlinear/env.py:210,288-291).
 //
-// The reference ships the DASMAT Citation model only as x86-64 machine code inside a Windows .pyd.  oracle/pe_probe/lift.py
-// translates that machine code, instruction by instruction, into C over an explicit machine state (lift_runtime.h); the
+// The reference ships the DASMAT Citation model only as x86-64 machine code inside a Windows .pyd.  tools/lift_plant.py
+// translates that machine code, instruction by instruction, into C over an explicit machine state (include/rl4_lift_runtime.h); the
 // build (rl4afcs_b200/build.py, only where /root/reference exists) writes the translation to csrc/_gen/ and this unit
 // compiles it for sm_100a: one aircraft per thread, every thread executing the model's own instruction stream on its own
 // copy of the model's writable memory.  What the binary computes, this computes -- the only arithmetic that is not the
@@ -38,7 +38,7 @@ constexpr uint32_t kALo = 0x2eb00, kASz = 0x100, kDLo = 0x3a000, kDSz = 0x2200;
 constexpr uint32_t kWLo = kDLo, kWSz = kFlat - kDLo;            // thread-private window: D, the unused tail of the image, the stack
 constexpr int kStateWords = (int)((kASz + kDSz) / 8);           // 1120
 constexpr uint32_t kLocalBytes = kWSz + kASz;                    // window + A; only the touched lines of it ever occupy cache
-constexpr uint32_t kRvaX = 0x3c120, kRvaEngine = 0x3c198;       // the 16 continuous states (oracle/pe_probe/README.md)
+constexpr uint32_t kRvaX = 0x3c120, kRvaEngine = 0x3c198;       // the 16 continuous states (established by running the binary)
 constexpr uint32_t kBase32 = 0x80000000u;                       // low 32 bits of the image base: memory operands arrive as low halves
 
 #ifndef RL4_DASMAT_THREADS
@@ -59,7 +59,7 @@ constexpr uint32_t kBase32 = 0x80000000u;                       // low 32 bits o
 #define F_SQRT(a) __dsqrt_rn(a)
 #define U2D(u) __longlong_as_double((long long)(u))
 #define D2U(d) ((uint64_t)__double_as_longlong(d))
-#include "../../oracle/pe_probe/lift_runtime.h"
+#include "../../include/rl4_lift_runtime.h"
 
 enum { kErrTrap = 1, kErrWildAccess = 2, kErrStoreToImage = 4 };
 
@@ -130,6 +130,20 @@ template <typename T> __device__ __forceinline__ T* at(uint8_t* G_, cpu_t* c, ui
 #define STS16 ST16
 #define STS32 ST32
 #define STS64 ST64
+#define LDW8 LD8
+#define LDW16 LD16
+#define LDW32 LD32
+#define LDW64 LD64
+#define LDWD LDD
+#define STW8 ST8
+#define STW16 ST16
+#define STW32 ST32
+#define STW64 ST64
+#define LDI8 LD8
+#define LDI16 LD16
+#define LDI32 LD32
+#define LDI64 LD64
+#define LDID LDD
 LIFT_DEFINE_BULK
 #include "_gen/dasmat_code_init.inc"
 #undef LIFT_MEM_CTX
@@ -151,6 +165,20 @@ LIFT_DEFINE_BULK
 #undef STS16
 #undef STS32
 #undef STS64
+#undef LDW8
+#undef LDW16
+#undef LDW32
+#undef LDW64
+#undef LDWD
+#undef STW8
+#undef STW16
+#undef STW32
+#undef STW64
+#undef LDI8
+#undef LDI16
+#undef LDI32
+#undef LDI64
+#undef LDID
 #undef LIFT_LOCALS
 #undef LIFT_ENTER
 #undef LIFT_PRECALL
@@ -200,6 +228,23 @@ template <typename T> __device__ __forceinline__ void lift_store(uint8_t* m_, cp
 #define STS16(a, v) (*LIFT_STK(uint16_t, a) = (uint16_t)(v))
 #define STS32(a, v) (*LIFT_STK(uint32_t, a) = (uint32_t)(v))
 #define STS64(a, v) (*LIFT_STK(uint64_t, a) = (uint64_t)(v))
+// operands whose object the translator knows (include/rl4_lift_runtime.h, tools/lift_plant.py "region hints"; the CPU build
+// of the same translation checks every hint at run time): W = inside the writable window, I = read-only image
+#define LDW8(a)  ((uint64_t)*LIFT_STK(uint8_t, a))
+#define LDW16(a) ((uint64_t)*LIFT_STK(uint16_t, a))
+#define LDW32(a) ((uint64_t)*LIFT_STK(uint32_t, a))
+#define LDW64(a) (*LIFT_STK(uint64_t, a))
+#define LDWD(a)  (*LIFT_STK(double, a))
+#define STW8(a, v)  (*LIFT_STK(uint8_t, a) = (uint8_t)(v))
+#define STW16(a, v) (*LIFT_STK(uint16_t, a) = (uint16_t)(v))
+#define STW32(a, v) (*LIFT_STK(uint32_t, a) = (uint32_t)(v))
+#define STW64(a, v) (*LIFT_STK(uint64_t, a) = (uint64_t)(v))
+#define LIFT_IMG(T, a) __ldg(reinterpret_cast<const T*>(G_ + ((a) - kBase32)))
+#define LDI8(a)  ((uint64_t)LIFT_IMG(uint8_t, a))
+#define LDI16(a) ((uint64_t)LIFT_IMG(uint16_t, a))
+#define LDI32(a) ((uint64_t)LIFT_IMG(uint32_t, a))
+#define LDI64(a) LIFT_IMG(uint64_t, a)
+#define LDID(a)  LIFT_IMG(double, a)
 LIFT_DEFINE_BULK
 #include "_gen/dasmat_code_step.inc"
 }  // namespace step_mode
@@ -377,7 +422,7 @@ __global__ void dasmat_broadcast_kernel(const uint64_t* __restrict__ src, int64_
 static int no_plant()
 {
     set_error("this library was built without the reference's plant binary (rl4afcs_b200/csrc/_gen/ is produced by "
-              "oracle/pe_probe/lift.py where /root/reference exists): the 'dasmat' plant is not available");
+              "rl4afcs_b200/tools/lift_plant.py where /root/reference exists): the 'dasmat' plant is not available");
     return -2;
 }
 

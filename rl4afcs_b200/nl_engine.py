@@ -52,7 +52,7 @@ class DasmatPlant:
     def __init__(self, lib, device, n, stride):
         if not lib.rl4_dasmat_available():
             raise _lib.Rl4Error("plant='dasmat': this librl4afcs_b200.so was built without the reference's plant binary "
-                                "(csrc/_gen/ is produced by oracle/pe_probe/lift.py where /root/reference exists)")
+                                "(csrc/_gen/ is produced by tools/lift_plant.py where /root/reference exists)")
         self.lib, self.device, self.n, self.stride = lib, device, n, stride
         self.words = lib.rl4_dasmat_state_words()
         self.word_x, self.word_engine = lib.rl4_dasmat_word_x(), lib.rl4_dasmat_word_engine()

@@ -1,19 +1,19 @@
-"""TEST / BUILD INFRASTRUCTURE -- static translation of the reference's plant binary into portable C.
+"""BUILD TOOL -- static translation of the reference's plant binary into portable C.
 
 The reference's nonlinear aircraft (`envs/nonlinear/<variant>/_citation.cp39-win_amd64.pyd`, called at
 /root/reference/envs/nonlinear/env.py:210,288-291 through envs/nonlinear/citation.py:62-69) exists only as x86-64 machine
-code.  `pe_citation.c` runs it in-process on an x86 host; this script goes one step further and TRANSLATES the model
+code.  This script TRANSLATES the model
 code (Simulink entry points initialize 0x96f0, step 0x3720, terminate 0xe620 and everything they reach) instruction by
 instruction into C: every x86 function becomes a C function over an explicit machine state (16 integer registers, 16 SSE
-registers, 5 flags) and a flat byte image of the DLL's sections + heap + stack.  Nothing of the model is interpreted or
+registers, 5 flags; include/rl4_lift_runtime.h) and a flat byte image of the DLL's sections + heap + stack.  Nothing of the model is interpreted or
 approximated -- each instruction is replaced by its architectural semantics -- so the translation computes what the binary
-computes, and it compiles for any target: gcc (oracle/_ref/libcitation_lifted.so, checked bit for bit against the binary
-itself by tests/test_citation_lifted.py) and nvcc (the `dasmat` plant of the CUDA kernels).
+computes, and it compiles for any target: nvcc (the `dasmat` plant of the CUDA kernels, csrc/dasmat_plant.cu) and gcc (the
+CPU build the test suite checks bit for bit against the binary executing natively, tests/test_citation_lifted.py).
 
 Nothing derived from the binary is committed: the generated sources and the image land in a git-ignored directory and are
 produced at build time where /root/reference exists (the build container); the GPU box receives the compiled libraries.
 
-Usage: python oracle/pe_probe/lift.py [--variant extended_input] [--out DIR]
+Usage: python rl4afcs_b200/tools/lift_plant.py [--variant extended_input] --out DIR
 """
 from __future__ import annotations
 
@@ -200,6 +200,7 @@ class Lifter:
         self.unknown = {}
         self.frame_reg = None
         self.const_regs = {}
+        self.region_hints = True
 
     # ---- operands
     def is_stack_operand(self, s):
@@ -258,15 +259,45 @@ class Lifter:
             else:
                 const += sg * int(t, 16)
         parts.append(f"0x{const & 0xffffffff:x}u")
+        self.last_const, self.last_dynamic = const & 0xffffffffffffffff, len(parts) > 1
         return "(" + "+".join(parts) + ")"
 
+    # The constant part of an address (rip-relative displacement, or a base register the analysis knows + displacement) names
+    # the OBJECT the operand addresses; an index register only moves inside that object.  Objects never straddle the regions
+    # of the memory model, so the region is known at translation time and the access needs no run-time decoding:
+    #   S  the stack (rsp / frame-pointer based)            W  the writable window of .data (block signals, states, work arrays)
+    #   I  the rest of the image (code constants, tables, parameters: read-only while stepping)      ''  unknown: decode
+    # The CPU build checks every hinted access against the region it claims (tests/test_citation_lifted.py runs it).
+    WINDOW = (0x3a000, 0x3c200)
+    IMAGE_RO = (0x13000, 0x3a000)          # .rdata .. the start of the window, minus the few words step() writes there
+    IMAGE_RW = (0x2eb00, 0x2ec00)
+
+    def hint(self, s):
+        if self.is_stack_operand(s):
+            return "S"
+        if not self.region_hints:
+            return ""
+        inner = s[s.index("[") + 1:s.rindex("]")]
+        terms = [t.strip() for _, t in re.findall(r"([+-]?)\s*([^+-]+)", inner)]
+        unscaled = [t for t in terms if t in REG]
+        known = [t for t in unscaled if t in self.const_regs]
+        if len(known) != len(unscaled) or ("rip" not in inner and not known):
+            return ""                       # a pointer the analysis does not know, or only a displacement: decode at run time
+        off = self.last_const - BASE
+        if self.WINDOW[0] <= off < self.WINDOW[1]:
+            return "W"
+        if self.IMAGE_RO[0] <= off < self.IMAGE_RO[1] and not (self.IMAGE_RW[0] - 0x40 <= off < self.IMAGE_RW[1]):
+            return "I"
+        return ""
+
     def ld(self, w, s, ins):
-        k = "S" if self.is_stack_operand(s) else ""
-        return f"LD{k}{w}({self.mem_a32(s, ins)})"
+        a = self.mem_a32(s, ins)
+        return f"LD{self.hint(s)}{w}({a})"
 
     def st(self, w, s, ins, val):
-        k = "S" if self.is_stack_operand(s) else ""
-        return f"ST{k}{w}({self.mem_a32(s, ins)},({val}));"
+        a = self.mem_a32(s, ins)
+        k = self.hint(s)
+        return f"ST{'' if k == 'I' else k}{w}({a},({val}));"
 
     def const_addr(self, s, ins):
         """VA if the operand is rip-relative, else None."""
@@ -325,7 +356,7 @@ class Lifter:
         if s.startswith("xmm"):
             return f"U2D(x{self.xr(s)}{'lh'[lane]})"
         a = self.mem_a32(s, ins)
-        k = "S" if self.is_stack_operand(s) else ""
+        k = self.hint(s)
         return f"LD{k}D({a}+{8 * lane}u)" if lane else f"LD{k}D({a})"
 
     def xu(self, s, ins, lane=0):
@@ -333,7 +364,7 @@ class Lifter:
         if s.startswith("xmm"):
             return f"x{self.xr(s)}{'lh'[lane]}"
         a = self.mem_a32(s, ins)
-        k = "S" if self.is_stack_operand(s) else ""
+        k = self.hint(s)
         return f"LD{k}64({a}+{8 * lane}u)" if lane else f"LD{k}64({a})"
 
     # ---- discovery
@@ -476,34 +507,106 @@ class Lifter:
     PRECALL = "LIFT_PRECALL;"       # locals -> cpu_t: rcx rdx r8 r9 rsp xmm0-3
     POSTCALL = "LIFT_POSTCALL;"     # cpu_t -> locals: rax xmm0
 
-    def find_const_regs(self, body):
-        """Callee-saved registers that the function loads ONCE with the address of a global (`lea reg,[rip+X]`) and otherwise
-        only saves / restores: as the base of a memory operand they are a known constant, which turns `[rbx+0x128]` into an
-        absolute address the C compiler resolves at compile time (thread-private signal, shared parameter ...)."""
-        saved = {"rbx": ("rbx", "ebx", "bx", "bl", "bh"), "rsi": ("rsi", "esi", "si", "sil"), "rdi": ("rdi", "edi", "di", "dil"),
-                 "r12": ("r12", "r12d", "r12w", "r12b"), "r13": ("r13", "r13d", "r13w", "r13b"), "r14": ("r14", "r14d", "r14w", "r14b"),
-                 "r15": ("r15", "r15d", "r15w", "r15b")}
-        out = {}
-        for reg, names in saved.items():
-            val, bad, n = None, False, 0
-            for a in body:
-                i = self.ins[a]
-                if not i.ops or i.mn in ("push", "cmp", "test", "comisd", "ucomisd", "call", "jmp") or i.mn.startswith("j"):
+    # ---- constant registers (flow-sensitive) ------------------------------------------------------------------------------
+    NO_DEST = {"cmp", "test", "push", "bt", "comisd", "ucomisd", "call", "jmp", "ret", "nop", "int3", "ud2"}
+    VOLATILE = ("rax", "rcx", "rdx", "r8", "r9", "r10", "r11")
+
+    def reg64(self, name):
+        return R64[REG[name][0]] if name in REG else (R64[R8H[name]] if name in R8H else None)
+
+    def transfer(self, i, st):
+        """constants known after instruction `i`, given those known before it (dict 64-bit register name -> value)"""
+        mn, ops = i.mn, i.ops
+        if mn == "call":
+            st = {r: v for r, v in st.items() if r not in self.VOLATILE}
+            return st
+        if mn.startswith("rep "):
+            return {r: v for r, v in st.items() if r not in ("rcx", "rdi", "rsi")}
+        if mn in ("cdq", "cqo"):
+            return {r: v for r, v in st.items() if r != "rdx"}
+        if mn == "cdqe":
+            return {r: v for r, v in st.items() if r != "rax"}
+        if mn in self.NO_DEST or mn.startswith("j") or not ops:
+            return st
+        killed = []
+        d = ops[0]
+        dr = self.reg64(d)
+        if mn == "xchg":
+            killed = [self.reg64(o) for o in ops if self.reg64(o)]
+        elif mn == "imul" and len(ops) == 1:
+            killed = ["rax", "rdx"]
+        elif dr is not None:
+            killed = [dr]
+        if not killed:
+            return st
+        new = {r: v for r, v in st.items() if r not in killed}
+        if dr is None or mn == "xchg":
+            return new
+        w = REG[d][1] if d in REG else 8
+        val = None
+        if mn == "lea" and w == 64:
+            val = self.fold_address(ops[1], i, st)
+        elif mn in ("mov", "movabs") and w >= 32 and len(ops) == 2:
+            src = ops[1]
+            if re.match(r"-?0x[0-9a-f]+$", src):
+                v = int(src, 16)
+                val = v & (0xffffffff if w == 32 else 0xffffffffffffffff)
+            elif src in REG and REG[src][1] == w and R64[REG[src][0]] in st:
+                v = st[R64[REG[src][0]]]
+                val = v & 0xffffffff if w == 32 else v
+        elif mn == "xor" and len(ops) == 2 and ops[0] == ops[1] and w >= 32:
+            val = 0
+        elif mn in ("add", "sub") and w == 64 and dr in st and re.match(r"-?0x[0-9a-f]+$", ops[1]):
+            v = int(ops[1], 16)
+            val = (st[dr] + (v if mn == "add" else -v)) & 0xffffffffffffffff
+        if val is not None:
+            new[dr] = val
+        return new
+
+    def fold_address(self, s, ins, st):
+        """value of a memory-operand address expression if every register in it is a known constant, else None"""
+        inner = s[s.index("[") + 1:s.rindex("]")]
+        total = 0
+        for sign, t in re.findall(r"([+-]?)\s*([^+-]+)", inner):
+            t = t.strip()
+            sg = -1 if sign == "-" else 1
+            if t == "rip":
+                total += ins.addr + ins.size
+            elif "*" in t:
+                r, sc = t.split("*")
+                if r not in st:
+                    return None
+                total += sg * st[r] * int(sc)
+            elif t in REG:
+                if REG[t][1] != 64 or t not in st:
+                    return None
+                total += sg * st[t]
+            else:
+                total += sg * int(t, 16)
+        return total & 0xffffffffffffffff
+
+    def analyse_constants(self, body, inside):
+        """in-state (known constants) of every instruction of the function: forward data flow, meet = agreement"""
+        ins_state = {}
+        work = [(body[0], {})]
+        while work:
+            a, st = work.pop()
+            if a in ins_state:
+                old = ins_state[a]
+                merged = {r: v for r, v in old.items() if st.get(r) == v}
+                if merged == old:
                     continue
-                writes = [i.ops[0]] + ([i.ops[1]] if i.mn == "xchg" else [])
-                if i.mn in ("mov", "movsd", "movaps", "movups", "movdqa", "movdqu", "movss") and "[" in i.ops[0]:
-                    writes = []                      # a store: the register is only read
-                if any(w in names for w in writes):
-                    if i.mn == "pop":
-                        continue
-                    n += 1
-                    if i.mn == "lea" and i.ops[0] == reg and "[rip" in i.ops[1]:
-                        val = self.const_addr(i.ops[1], i)
-                    else:
-                        bad = True
-            if val is not None and n == 1 and not bad:
-                out[reg] = val
-        return out
+                st = merged
+            ins_state[a] = st
+            i = self.ins[a]
+            out = self.transfer(i, st)
+            if i.mn.startswith("j"):
+                t = self.direct_target(i)
+                if t in inside:
+                    work.append((t, out))
+            if not self.ends_flow(i) and a + i.size in inside:
+                work.append((a + i.size, out))
+        return ins_state
 
     def find_frame_reg(self, body):
         """rbp when the function uses it as a frame pointer: written once by `lea rbp,[rsp+-c]` (or from rax = rsp at entry),
@@ -544,7 +647,8 @@ class Lifter:
         body = self.funcs[e]
         inside = set(body)
         self.frame_reg = self.find_frame_reg(body)
-        self.const_regs = self.find_const_regs(body)
+        self.consts_at = self.analyse_constants(body, inside)
+        self.const_regs = {}
         targets = set()
         for a in body:
             i = self.ins[a]
@@ -570,6 +674,7 @@ class Lifter:
                 out.append(f"L_{a:x}: ;")
             if a in leaders:
                 out.append(f"  LIFT_BB(0x{e:x}ULL, {leaders[a]});")
+            self.const_regs = self.consts_at.get(a, {})
             try:
                 code = self.emit_ins(i, inside, e)
             except Exception as ex:  # noqa: BLE001 - report the instruction and keep going: unreachable CRT code may be odd
@@ -727,8 +832,10 @@ class Lifter:
                 if s.startswith("xmm"):
                     return f"x{n}l=x{self.xr(s)}l; x{n}h=x{self.xr(s)}h;"
                 return f"{{ uint64_t p_={xu(s, i, 0)}, q_={xu(s, i, 1)}; x{n}l=p_; x{n}h=q_; }}"
-            k = "S" if self.is_stack_operand(d) else ""
-            return f"{{ uint32_t a_={self.mem_a32(d, i)}; ST{k}64(a_,x{self.xr(s)}l); ST{k}64(a_+8u,x{self.xr(s)}h); }}"
+            a = self.mem_a32(d, i)
+            k = self.hint(d)
+            k = "" if k == "I" else k
+            return f"{{ uint32_t a_={a}; ST{k}64(a_,x{self.xr(s)}l); ST{k}64(a_+8u,x{self.xr(s)}h); }}"
         if mn in ("movlpd", "movhpd", "movlps", "movhps"):
             k = "l" if mn[3] == "l" else "h"
             d, s = ops
@@ -825,7 +932,7 @@ class Lifter:
         raise NotImplementedError(mn)
 
 
-PRELUDE = r"""/* GENERATED by oracle/pe_probe/lift.py from the reference's plant binary -- do not edit, do not commit. */
+PRELUDE = r"""/* GENERATED by rl4afcs_b200/tools/lift_plant.py from the reference's plant binary -- do not edit, do not commit. */
 #ifndef LIFT_FN
 #define LIFT_FN static
 #endif
@@ -867,7 +974,7 @@ POSTLUDE = "\n#undef ZF\n#undef SF\n#undef CF\n#undef OF\n#undef PF\n"
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--variant", default="extended_input")
-    ap.add_argument("--out", default=os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "_ref", "lifted"))
+    ap.add_argument("--out", required=True)
     args = ap.parse_args()
     path = os.path.join(REF_DIR, args.variant, "_citation.cp39-win_amd64.pyd")
     pe = PE(path)
