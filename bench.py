@@ -539,6 +539,7 @@ def nonlinear_workload(device, counters, n=1 << 18, steps=300, warmup=700, e2e=T
         torch.cuda.empty_cache()
     ret = {"workload": "nonlinear aircraft IDHP attitude tracking (BASELINE.json configs[2]), surrogate 6-DOF plant",
            "agents": n, "steps": steps, "warmup": warmup, "results": out}
+    ret["dasmat"] = dasmat_workload(device, counters, issue_peak)
     if e2e:
         idx = torch.device(device).index or 0
         r = e2e_nl(n, steps, idx, 0)
@@ -547,6 +548,60 @@ def nonlinear_workload(device, counters, n=1 << 18, steps=300, warmup=700, e2e=T
                       "note": "rl4_nl_episode_host (mixed, ode5): pinned host weights / reference -> GPU, reset + K fused steps from the "
                               "start of the episode with device-drawn noise, statistics + weights + RLS -> host"}
     return ret
+
+
+def dasmat_workload(device, counters, issue_peak, n=37888, steps=12, warmup=4) -> dict:
+    """The same task on the reference's OWN aircraft model (plant='dasmat': the `_citation` binary translated at build time,
+    csrc/dasmat_plant.cu) -- exact plant, ~270x heavier than the surrogate (113 712 x86 instructions per step).  Reported
+    beside the surrogate numbers; n = one resident wave of 256 aircraft per SM."""
+    import torch
+
+    from rl4afcs_b200 import _lib, nl_engine
+
+    L = _lib.load()
+    if not L.rl4_dasmat_available():
+        return {"unavailable": "library built without the reference's plant binary"}
+    prof = counters.get("dasmat_step_kernel", {})
+    out = {"agents": n, "steps": steps, "warmup": warmup,
+           "x86_instructions_per_plant_step": 113712, "note": "translated from envs/nonlinear/extended_input/_citation.cp39-win_amd64.pyd"}
+    # (1) the plant alone: citation.step for every aircraft
+    dz = nl_engine.DasmatPlant(L, torch.device(device), n, n)
+    trim = [-0.02855, 0, 0, 0, 0, 0, 0, 0, 0.55, 0.55, 0]
+    dz.reset(trim, 1001)
+    g = torch.Generator(device=device); g.manual_seed(3)
+    u = torch.tensor(trim, dtype=torch.float64, device=device).reshape(11, 1).repeat(1, n)
+    u[0:3] += 0.01 * torch.randn((3, n), generator=g, device=device, dtype=torch.float64)
+    u = u.contiguous()
+    xo = torch.zeros((12, n), dtype=torch.float64, device=device)
+    run = lambda k: _lib.check(L.rl4_dasmat_step(dz.image.data_ptr(), dz.state.data_ptr(), n, n, u.data_ptr(), n, k, xo.data_ptr(), n,  # noqa: E731
+                                                 None, dz.err.data_ptr(), None), "rl4_dasmat_step")
+    run(warmup); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); run(steps); e1.record(); torch.cuda.synchronize()
+    dz.check()
+    ms = e0.elapsed_time(e1)
+    rate = n * steps / (ms * 1e-3)
+    roof = {"bound": "issue", "unit": "Ginstr/s", "peak": issue_peak / 1e9, "from_profile": prof or None}
+    if prof.get("instr_per_plant_step"):
+        roof["achieved"] = prof["instr_per_plant_step"] * rate / 1e9
+        roof["frac"] = prof["instr_per_plant_step"] * rate / issue_peak
+    out["plant_only"] = {"value": rate, "unit": "plant-steps/s", "ms_per_step": ms / steps, "roofline": roof,
+                         "native_binary_one_host_core_steps_per_s": 3.2e4}
+    del dz
+    # (2) fused env + agent on it
+    eng = nl_engine.NlEngine(n, policy="mixed", device=device, plant="dasmat")
+    eng.set_reference(nl_engine.theta_reference())
+    w = lambda k: (torch.randn((n, k), generator=g, device=device).clamp_(-2, 2) * 0.1).double()  # noqa: E731
+    eng.init(w(40), w(10), w(40), w(30))
+    nz = torch.randn((warmup + steps, n), generator=g, device=device)
+    eng.run(warmup, nz[:warmup]); torch.cuda.synchronize()
+    e0.record(); eng.run(steps, nz[warmup:]); e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    out["fused_mixed"] = {"value": n * steps / (ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": ms / steps,
+                          "diverged": int(eng.stats()["diverged"].sum())}
+    del eng, nz
+    torch.cuda.empty_cache()
+    return out
 
 
 def sp_roofline(policy, n, K, ms, eng, counters, L):

@@ -42,10 +42,10 @@ constexpr uint32_t kRvaX = 0x3c120, kRvaEngine = 0x3c198;       // the 16 contin
 constexpr uint32_t kBase32 = 0x80000000u;                       // low 32 bits of the image base: memory operands arrive as low halves
 
 #ifndef RL4_DASMAT_THREADS
-#define RL4_DASMAT_THREADS 128
+#define RL4_DASMAT_THREADS 512
 #endif
 #ifndef RL4_DASMAT_MIN_BLOCKS
-#define RL4_DASMAT_MIN_BLOCKS 2
+#define RL4_DASMAT_MIN_BLOCKS 1
 #endif
 
 #if RL4_HAVE_DASMAT
@@ -193,6 +193,19 @@ namespace step_mode {
 // keeps the warps of a CTA on the same stretch of the code (far larger than the instruction cache); c->sync is uniform over
 // the CTA by construction (set by the kernels from a CTA-wide vote)
 #define LIFT_SYNC if (c->sync) __syncthreads()
+// the same inside step(), in front of calls that every execution passes exactly once (tools/lift_plant.py: spine_calls)
+#ifndef RL4_DASMAT_SYNC_SFUN
+#define RL4_DASMAT_SYNC_SFUN 0   // measured: 1.33e7 (entry only) -> 1.22e7 (+ S-function calls) -> 1.17e7 (+ helper calls) plant steps/s
+#endif
+#ifndef RL4_DASMAT_SYNC_HELPER
+#define RL4_DASMAT_SYNC_HELPER 0
+#endif
+#if RL4_DASMAT_SYNC_SFUN
+#define LIFT_SYNC_SFUN if (c->sync) __syncthreads()
+#endif
+#if RL4_DASMAT_SYNC_HELPER
+#define LIFT_SYNC_HELPER if (c->sync) __syncthreads()
+#endif
 template <typename T> __device__ __forceinline__ T lift_load(uint8_t* m_, const uint8_t* G_, cpu_t* c, uint32_t a32)
 {
     const uint32_t off = a32 - kBase32;
@@ -306,11 +319,9 @@ template <bool LOG>
 static int dasmat_launch_fused(const rl4_nl_params* p, const double* theta_ref, const float* noise, int64_t noise_stride, int k0,
                                int n_steps, rl4_nl_state st, int64_t n, rl4_sp_log lg, DasmatIo dio, cudaStream_t s)
 {
-    constexpr int BLK = NlBlock<float>::v;
-    const size_t smem = (sizeof(double) * kNlSmemDoubles + sizeof(float) * kNlSmemNet) * BLK;
-    auto kern = nl_run_kernel<float, RL4_CIT_INTEGRATOR_ODE5, LOG, true, 1>;
-    RL4_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)((n + BLK - 1) / BLK), BLK, smem, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, dio);
+    constexpr int BLK = kNlBlockDasmat;
+    auto kern = nl_run_kernel<float, RL4_CIT_INTEGRATOR_ODE5, LOG, true, 1>;      // no shared memory: see nl_core.cuh
+    kern<<<(unsigned)((n + BLK - 1) / BLK), BLK, 0, s>>>(*p, theta_ref, noise, noise_stride, k0, n_steps, st, n, lg, dio);
     return check_launch("nl_run_kernel<dasmat>");
 }
 

@@ -55,6 +55,13 @@ __device__ __forceinline__ double sqrt_of_square(double d)
 #endif
 template <typename TN> struct NlBlock { static constexpr int v = RL4_NL_BLOCK_F64; };
 template <> struct NlBlock<float> { static constexpr int v = RL4_NL_BLOCK_F32; };
+// with the translated plant (PLANT = 1) the step is ~660 000 instructions of code far larger than the instruction cache: the
+// more warps of an SM walk it together the better (measured on the plant alone: 128 x 2 -> 8.6e6, 256 x 1 -> 9.6e6,
+// 512 x 1 -> 1.33e7 plant steps/s), so one 512-thread CTA per SM
+#ifndef RL4_NL_BLOCK_DASMAT
+#define RL4_NL_BLOCK_DASMAT 512
+#endif
+constexpr int kNlBlockDasmat = RL4_NL_BLOCK_DASMAT;
 #ifndef RL4_NL_MINB
 #define RL4_NL_MINB 1
 #endif
@@ -83,6 +90,17 @@ template <typename T> struct PlaneCol {
     T* p;
     int64_t stride;
     __device__ __forceinline__ T& operator[](int j) const { return p[(int64_t)j * stride]; }
+};
+
+// picks the local-array form (PlaneCol with stride 1) or the shared-memory form of a per-thread array
+template <bool LOCAL, typename L, typename S> struct DasmatPick;
+template <typename L, typename S> struct DasmatPick<true, L, S> {
+    using type = L;
+    template <typename T> static __device__ __forceinline__ L make(T* local, T*) { return L{local, 1}; }
+};
+template <typename L, typename S> struct DasmatPick<false, L, S> {
+    using type = S;
+    template <typename T> static __device__ __forceinline__ S make(T*, T* shared) { return S{shared}; }
 };
 
 // hidden layer of a 4-10-k net (Network.base_call, objects.py:111-139)
@@ -290,7 +308,7 @@ static __device__ __noinline__ double nl_decay_np2(double a, double b, double c,
 __device__ __forceinline__ bool nl_isclose(double a, double b) { return fabs(a - b) <= (1e-8 + 1e-5 * fabs(b)); }
 
 template <typename TN, int INTEG, bool LOG, bool PER_AGENT, int PLANT = 0>
-__global__ void __launch_bounds__(NlBlock<TN>::v, RL4_NL_MINB)
+__global__ void __launch_bounds__((PLANT == 1 ? kNlBlockDasmat : NlBlock<TN>::v), RL4_NL_MINB)
 nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict__ theta_ref, const float* __restrict__ noise,
               int64_t noise_stride, int k0, int n_steps, const rl4_nl_state st, int64_t n_agents, const rl4_sp_log lg,
               const DasmatIo dio = DasmatIo{})
@@ -315,11 +333,23 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
     extern __shared__ __align__(16) unsigned char nl_smem[];
     // layout: doubles first ([Ea 50][th 12 + cv 16 when RL4_NL_SMEM_RLS]), then TN ([W1t 40][W2t 30][W1a 40 + W2a 10 when RL4_NL_SMEM_ACTOR])
     double* const sm_d = reinterpret_cast<double*>(nl_smem) + threadIdx.x;
-    constexpr int BLK = NlBlock<TN>::v;
+    constexpr int BLK = PLANT == 1 ? kNlBlockDasmat : NlBlock<TN>::v;
     TN* const sm_n = reinterpret_cast<TN*>(nl_smem + sizeof(double) * kNlSmemDoubles * BLK) + threadIdx.x;
+#ifdef RL4_NL_WITH_DASMAT
+    // PLANT = 1: 512-thread CTAs would need 348 KB of shared memory for these; the plant is >99 % of the step there, so the
+    // trace and the target critic simply live in thread-local memory (same element order, same arithmetic)
+    double ea_loc[PLANT == 1 ? 50 : 1];
+    TN w1t_loc[PLANT == 1 ? 40 : 1], w2t_loc[PLANT == 1 ? 30 : 1];
+    using EaT = typename DasmatPick<PLANT == 1, PlaneCol<double>, Strided<double, BLK>>::type;
+    using WtT = typename DasmatPick<PLANT == 1, PlaneCol<TN>, Strided<TN, BLK>>::type;
+    const EaT Ea = DasmatPick<PLANT == 1, PlaneCol<double>, Strided<double, BLK>>::make(ea_loc, sm_d);
+    const WtT W1t = DasmatPick<PLANT == 1, PlaneCol<TN>, Strided<TN, BLK>>::make(w1t_loc, sm_n);
+    const WtT W2t = DasmatPick<PLANT == 1, PlaneCol<TN>, Strided<TN, BLK>>::make(w2t_loc, sm_n + 40 * BLK);
+#else
     const Strided<double, BLK> Ea{sm_d};
     const Strided<TN, BLK> W1t{sm_n};
     const Strided<TN, BLK> W2t{sm_n + 40 * BLK};
+#endif
 #if RL4_NL_SMEM_RLS
     const Strided<double, BLK> th{sm_d + 50 * BLK};
     const Strided<double, BLK> cv{sm_d + 62 * BLK};

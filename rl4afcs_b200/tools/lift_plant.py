@@ -585,6 +585,77 @@ class Lifter:
                 total += sg * int(t, 16)
         return total & 0xffffffffffffffff
 
+    def spine_calls(self, body, inside):
+        """Call instructions of the function that EVERY execution passes exactly once: they dominate every `ret` and lie in
+        no loop.  All aircraft of a CTA reach them the same number of times whatever their data, so the CUDA build may put a
+        CTA barrier in front of them (LIFT_SYNC) to keep the warps on the same stretch of the code."""
+        idx = {a: k for k, a in enumerate(body)}
+        succ = [[] for _ in body]
+        for a in body:
+            i = self.ins[a]
+            if i.mn.startswith("j"):
+                t = self.direct_target(i)
+                if t in inside:
+                    succ[idx[a]].append(idx[t])
+            if not self.ends_flow(i) and a + i.size in inside:
+                succ[idx[a]].append(idx[a + i.size])
+        n = len(body)
+        pred = [[] for _ in body]
+        for u, vs in enumerate(succ):
+            for v in vs:
+                pred[v].append(u)
+        # dominators (bit sets), reverse-post-order iteration
+        order, seen, stack = [], [False] * n, [(0, 0)]
+        seen[0] = True
+        while stack:
+            u, k = stack.pop()
+            if k < len(succ[u]):
+                stack.append((u, k + 1))
+                v = succ[u][k]
+                if not seen[v]:
+                    seen[v] = True
+                    stack.append((v, 0))
+            else:
+                order.append(u)
+        order.reverse()
+        full = (1 << n) - 1
+        dom = [full] * n
+        dom[0] = 1
+        changed = True
+        while changed:
+            changed = False
+            for u in order[1:]:
+                d = full
+                for q in pred[u]:
+                    if seen[q]:
+                        d &= dom[q]
+                d |= 1 << u
+                if d != dom[u]:
+                    dom[u] = d
+                    changed = True
+        exits = [idx[a] for a in body if self.ins[a].mn == "ret" and seen[idx[a]]]
+        if not exits:
+            return set()
+        spine = full
+        for e in exits:
+            spine &= dom[e]
+        # instructions on a cycle: reachable from one of their own successors
+        on_cycle = set()
+        for u in range(n):
+            if not (spine >> u) & 1 or self.ins[body[u]].mn != "call":
+                continue
+            st, vis = list(succ[u]), set()
+            while st:
+                v = st.pop()
+                if v == u:
+                    on_cycle.add(u)
+                    break
+                if v in vis:
+                    continue
+                vis.add(v)
+                st.extend(succ[v])
+        return {body[u] for u in range(n) if (spine >> u) & 1 and self.ins[body[u]].mn == "call" and u not in on_cycle}
+
     def analyse_constants(self, body, inside):
         """in-state (known constants) of every instruction of the function: forward data flow, meet = agreement"""
         ins_state = {}
@@ -665,8 +736,11 @@ class Lifter:
             leaders[cur] += 1
             prev = i
         out = [f"LIFT_FN void f_{e:x}{'_m' if minor else ''}(cpu_t* c) {{", "  LIFT_LOCALS; LIFT_ENTER;"]
+        sync_at = set()
         if e == self.STEP:
             out.append("  LIFT_SYNC;        /* every aircraft calls step() the same number of times: a convergent point */")
+            sync_at = self.spine_calls(body, inside)
+            self.n_spine = len(sync_at)
         prev_end = None
         for a in body:
             i = self.ins[a]
@@ -675,6 +749,11 @@ class Lifter:
             if a in leaders:
                 out.append(f"  LIFT_BB(0x{e:x}ULL, {leaders[a]});")
             self.const_regs = self.consts_at.get(a, {})
+            if a in sync_at:
+                # two classes, so that the build can choose the barrier density: calls through a function pointer (the
+                # model's S-function blocks, ~25 per evaluation) and direct calls of the table-lookup helpers (~90)
+                kind = "LIFT_SYNC_SFUN" if self.direct_target(i) is None else "LIFT_SYNC_HELPER"
+                out.append(f"  {kind};        /* a call every execution of step() passes exactly once */")
             try:
                 code = self.emit_ins(i, inside, e)
             except Exception as ex:  # noqa: BLE001 - report the instruction and keep going: unreachable CRT code may be odd
@@ -945,6 +1024,12 @@ PRELUDE = r"""/* GENERATED by rl4afcs_b200/tools/lift_plant.py from the referenc
 #ifndef LIFT_SYNC
 #define LIFT_SYNC
 #endif
+#ifndef LIFT_SYNC_SFUN
+#define LIFT_SYNC_SFUN
+#endif
+#ifndef LIFT_SYNC_HELPER
+#define LIFT_SYNC_HELPER
+#endif
 #define ZF (fl.zf)
 #define SF (fl.sf)
 #define CF (fl.cf)
@@ -998,7 +1083,8 @@ def main():
         for o in range(0, len(blob), 64):
             f.write(",".join(str(v) for v in blob[o:o + 64]) + ",\n")
     n_ins = sum(len(v) for v in L.funcs.values())
-    print(f"{args.variant}: {len(L.funcs)} functions, {n_ins} instructions translated, image {pe.image_size} bytes")
+    print(f"{args.variant}: {len(L.funcs)} functions, {n_ins} instructions translated, image {pe.image_size} bytes, "
+          f"{getattr(L, 'n_spine', 0)} convergent call sites in step()")
     for e, u in sorted(L.unknown.items()):
         print(f"  f_{e:x}: untranslated:", [(hex(x[0]), x[1]) if isinstance(x, tuple) else hex(x) for x in u[:6]])
     return 0
