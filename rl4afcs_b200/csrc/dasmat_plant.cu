@@ -206,20 +206,43 @@ namespace step_mode {
 #if RL4_DASMAT_SYNC_HELPER
 #define LIFT_SYNC_HELPER if (c->sync) __syncthreads()
 #endif
+// Run-time decode of an address the translator could not place (a pointer through the Simulink SimStruct): BRANCH-FREE --
+// the pointer is selected, then ONE generic load / store follows.  (A branchy decode made ptxas duplicate the code behind
+// every access per region: the 59-instruction table-interpolation helper at RVA 0xe8d0 became 5 268 SASS instructions.)
+#ifndef RL4_DASMAT_BRANCHFREE
+#define RL4_DASMAT_BRANCHFREE 1
+#endif
 template <typename T> __device__ __forceinline__ T lift_load(uint8_t* m_, const uint8_t* G_, cpu_t* c, uint32_t a32)
 {
     const uint32_t off = a32 - kBase32;
+#if RL4_DASMAT_BRANCHFREE
+    (void)c;
+    const uint32_t ow = off - kWLo, oa = off - kALo;
+    const uint8_t* p = G_ + (off < kImg ? off : 0u);                  // a wild address reads the image header: garbage in, flagged on stores
+    p = oa < kASz ? m_ + kWSz + oa : p;
+    p = ow < kWSz ? m_ + ow : p;
+    return *reinterpret_cast<const T*>(p);
+#else
     if (off - kWLo < kWSz) return *reinterpret_cast<const T*>(m_ + (off - kWLo));
     if (off - kALo < kASz) return *reinterpret_cast<const T*>(m_ + kWSz + (off - kALo));
     if (off >= kImg) { c->err |= kErrWildAccess; return T(0); }
     return __ldg(reinterpret_cast<const T*>(G_ + off));              // shared image: read-only while aircraft are stepping
+#endif
 }
 template <typename T> __device__ __forceinline__ void lift_store(uint8_t* m_, cpu_t* c, uint32_t a32, T v)
 {
     const uint32_t off = a32 - kBase32;
+#if RL4_DASMAT_BRANCHFREE
+    const uint32_t ow = off - kWLo, oa = off - kALo;
+    const bool bad = !(ow < kWSz) && !(oa < kASz);
+    uint8_t* p = m_ + (oa < kASz ? kWSz + oa : (ow < kWSz ? ow : kDSz));     // a store outside A / D / stack lands in the window's unused gap
+    *reinterpret_cast<T*>(p) = v;
+    if (bad) c->err |= kErrStoreToImage;
+#else
     if (off - kWLo < kWSz) { *reinterpret_cast<T*>(m_ + (off - kWLo)) = v; return; }
     if (off - kALo < kASz) { *reinterpret_cast<T*>(m_ + kWSz + (off - kALo)) = v; return; }
     c->err |= kErrStoreToImage;
+#endif
 }
 #define LD8(a)  ((uint64_t)lift_load<uint8_t>(m_, G_, c, (a)))
 #define LD16(a) ((uint64_t)lift_load<uint16_t>(m_, G_, c, (a)))
