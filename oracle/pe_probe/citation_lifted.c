@@ -75,15 +75,20 @@ static inline uint32_t lift_chk(cpu_t* c, uint32_t a32, int window)
 #define LDI32(a) LD32(lift_chk(c, (a), 0))
 #define LDI64(a) LD64(lift_chk(c, (a), 0))
 #define LDID(a) LDD(lift_chk(c, (a), 0))
-#define LDS8 LD8
-#define LDS16 LD16
-#define LDS32 LD32
-#define LDS64 LD64
-#define LDSD LDD
-#define STS8 ST8
-#define STS16 ST16
-#define STS32 ST32
-#define STS64 ST64
+static inline uint32_t lift_chk_stack(uint32_t a32)
+{
+    if (a32 - (uint32_t)LIFT_BASE < LIFT_IMAGE_SIZE + LIFT_HEAP_SIZE) lift_trap("an access hinted as 'stack' is not on the stack", a32);
+    return a32;
+}
+#define LDS8(a) LD8(lift_chk_stack(a))
+#define LDS16(a) LD16(lift_chk_stack(a))
+#define LDS32(a) LD32(lift_chk_stack(a))
+#define LDS64(a) LD64(lift_chk_stack(a))
+#define LDSD(a) LDD(lift_chk_stack(a))
+#define STS8(a, v) ST8(lift_chk_stack(a), v)
+#define STS16(a, v) ST16(lift_chk_stack(a), v)
+#define STS32(a, v) ST32(lift_chk_stack(a), v)
+#define STS64(a, v) ST64(lift_chk_stack(a), v)
 
 #define lift_cos cos
 #define lift_sin sin

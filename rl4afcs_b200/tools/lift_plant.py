@@ -201,12 +201,17 @@ class Lifter:
         self.frame_reg = None
         self.const_regs = {}
         self.region_hints = True
+        self.frozen = None          # second pass: the image after initialize() (bytes); loads from its constant part are folded
+        self.clones = {}            # (function, rcx) -> name of the copy specialised for that first argument
+        self.clone_work = []
 
     # ---- operands
     def is_stack_operand(self, s):
         inner = s[s.index("[") + 1:s.rindex("]")]
         base = re.split(r"[+\-*]", inner)[0].strip()
-        return base == "rsp" or (self.frame_reg is not None and base == self.frame_reg)
+        if "*" in re.split(r"[+\-]", inner)[0]:
+            return False
+        return base == "rsp" or (self.frame_reg is not None and base == self.frame_reg) or self.const_regs.get(base) == "stk"
 
     def mem_addr(self, s, ins):
         """C expression of the effective address of a memory operand 'SIZE PTR [..]' or '[..]'."""
@@ -246,13 +251,13 @@ class Lifter:
             elif "*" in t:
                 r, sc = t.split("*")
                 assert sg == 1
-                if r in self.const_regs:
+                if isinstance(self.const_regs.get(r), int):
                     const += self.const_regs[r] * int(sc)
                 else:
                     parts.append(f"(uint32_t)r{REG[r][0]}*{sc}u")
             elif t in REG:
                 assert REG[t][1] == 64 and sg == 1, s
-                if t in self.const_regs:
+                if isinstance(self.const_regs.get(t), int):
                     const += self.const_regs[t]
                 else:
                     parts.append(f"(uint32_t)r{REG[t][0]}")
@@ -271,6 +276,25 @@ class Lifter:
     WINDOW = (0x3a000, 0x3c200)
     IMAGE_RO = (0x13000, 0x3a000)          # .rdata .. the start of the window, minus the few words step() writes there
     IMAGE_RW = (0x2eb00, 0x2ec00)
+    FROZEN_HOLE = (0x2eb48, 0x2eb60)       # the model time inside the rtModel structure: the only word of that region step() writes
+
+    def frozen_value(self, addr, nbytes):
+        """the value at `addr` if it lies in the part of the image that nothing writes after initialize(), else None"""
+        if self.frozen is None:
+            return None
+        off = (addr & 0xffffffffffffffff) - BASE
+        if not (self.IMAGE_RO[0] <= off and off + nbytes <= self.IMAGE_RO[1]):
+            return None
+        if off + nbytes > self.FROZEN_HOLE[0] and off < self.FROZEN_HOLE[1]:
+            return None
+        return int.from_bytes(self.frozen[off:off + nbytes], "little")
+
+    def frozen_operand(self, s, ins, nbytes):
+        """value of a memory operand whose address is a translation-time constant inside the frozen image, else None"""
+        if self.frozen is None or "[" not in s:
+            return None
+        a = self.fold_address(s, ins, self.const_regs)
+        return None if a is None else self.frozen_value(a, nbytes)
 
     def hint(self, s):
         if self.is_stack_operand(s):
@@ -280,7 +304,7 @@ class Lifter:
         inner = s[s.index("[") + 1:s.rindex("]")]
         terms = [t.strip() for _, t in re.findall(r"([+-]?)\s*([^+-]+)", inner)]
         unscaled = [t for t in terms if t in REG]
-        known = [t for t in unscaled if t in self.const_regs]
+        known = [t for t in unscaled if isinstance(self.const_regs.get(t), int)]
         if len(known) != len(unscaled) or ("rip" not in inner and not known):
             return ""                       # a pointer the analysis does not know, or only a displacement: decode at run time
         off = self.last_const - BASE
@@ -328,6 +352,9 @@ class Lifter:
             return f"((r{R8H[s]}>>8)&0xff)"
         if "[" in s:
             w = SIZES[s.split()[0]] if "PTR" in s else size
+            fv = self.frozen_operand(s, ins, w // 8)
+            if fv is not None:
+                return f"0x{fv:x}ULL"
             return self.ld(w, s, ins)
         v = int(s, 16) if s.startswith(("0x", "-0x")) else int(s)
         return f"0x{v & 0xffffffffffffffff:x}ULL"
@@ -351,10 +378,19 @@ class Lifter:
     def xr(self, s):
         return int(s[3:])
 
+    def frozen_lane(self, s, ins, lane):
+        if self.frozen is None or "[" not in s:
+            return None
+        a = self.fold_address(s, ins, self.const_regs)
+        return None if a is None else self.frozen_value(a + 8 * lane, 8)
+
     def xd(self, s, ins, lane=0):
         """double-valued expression of lane `lane` of an xmm register or of a memory operand"""
         if s.startswith("xmm"):
             return f"U2D(x{self.xr(s)}{'lh'[lane]})"
+        fv = self.frozen_lane(s, ins, lane)
+        if fv is not None:
+            return f"U2D(0x{fv:x}ULL)"
         a = self.mem_a32(s, ins)
         k = self.hint(s)
         return f"LD{k}D({a}+{8 * lane}u)" if lane else f"LD{k}D({a})"
@@ -363,6 +399,9 @@ class Lifter:
         """uint64-valued expression of a lane"""
         if s.startswith("xmm"):
             return f"x{self.xr(s)}{'lh'[lane]}"
+        fv = self.frozen_lane(s, ins, lane)
+        if fv is not None:
+            return f"0x{fv:x}ULL"
         a = self.mem_a32(s, ins)
         k = self.hint(s)
         return f"LD{k}64({a}+{8 * lane}u)" if lane else f"LD{k}64({a})"
@@ -481,10 +520,18 @@ class Lifter:
             out.append(f"  case 0x{e:x}ULL: f_{e:x}(c); return;")
         out.append("  default: LIFT_TRAP(\"indirect call to an address that is not a translated function\", target);")
         out.append("  }\n}\n")
+        self.clones, self.clone_work = {}, []
+        bodies = []
         for e in names:
-            out.extend(self.emit_func(e))
+            bodies.extend(self.emit_func(e))
         if with_step:
-            out.extend(self.emit_func(self.STEP, minor=True))
+            bodies.extend(self.emit_func(self.STEP, minor=True))
+        while self.clone_work:
+            t, rcx = self.clone_work.pop()
+            bodies.extend(self.emit_func(t, entry_consts={"rcx": rcx}, name=self.clones[(t, rcx)]))
+        self.n_clones = len(self.clones)
+        out.extend(f"LIFT_FN void {n}(cpu_t* c);" for n in sorted(self.clones.values()))
+        out.extend(bodies)
         return "\n".join(out)
 
     def import_call(self, name):
@@ -546,19 +593,38 @@ class Lifter:
         val = None
         if mn == "lea" and w == 64:
             val = self.fold_address(ops[1], i, st)
+            if val is None:
+                # an address formed from the stack pointer (or a register that already holds one) points into the stack
+                inner = ops[1][ops[1].index("[") + 1:ops[1].rindex("]")]
+                first = re.split(r"[+\-]", inner)[0].strip()
+                if first == "rsp" or st.get(first) == "stk":
+                    val = "stk"
         elif mn in ("mov", "movabs") and w >= 32 and len(ops) == 2:
             src = ops[1]
             if re.match(r"-?0x[0-9a-f]+$", src):
                 v = int(src, 16)
                 val = v & (0xffffffff if w == 32 else 0xffffffffffffffff)
+            elif src == "rsp" and w == 64:
+                val = "stk"
             elif src in REG and REG[src][1] == w and R64[REG[src][0]] in st:
                 v = st[R64[REG[src][0]]]
-                val = v & 0xffffffff if w == 32 else v
+                val = v if v == "stk" else (v & 0xffffffff if w == 32 else v)
+                if val == "stk" and w != 64:
+                    val = None
+            elif "[" in src and self.frozen is not None:
+                a = self.fold_address(src, i, st)
+                if a is not None:
+                    val = self.frozen_value(a, w // 8)
+        elif mn == "movsxd" and w == 64 and "[" in ops[1] and self.frozen is not None:
+            a = self.fold_address(ops[1], i, st)
+            v = None if a is None else self.frozen_value(a, 4)
+            if v is not None:
+                val = (v - (1 << 32) if v >> 31 else v) & 0xffffffffffffffff
         elif mn == "xor" and len(ops) == 2 and ops[0] == ops[1] and w >= 32:
             val = 0
         elif mn in ("add", "sub") and w == 64 and dr in st and re.match(r"-?0x[0-9a-f]+$", ops[1]):
             v = int(ops[1], 16)
-            val = (st[dr] + (v if mn == "add" else -v)) & 0xffffffffffffffff
+            val = "stk" if st[dr] == "stk" else (st[dr] + (v if mn == "add" else -v)) & 0xffffffffffffffff
         if val is not None:
             new[dr] = val
         return new
@@ -574,11 +640,11 @@ class Lifter:
                 total += ins.addr + ins.size
             elif "*" in t:
                 r, sc = t.split("*")
-                if r not in st:
+                if not isinstance(st.get(r), int):
                     return None
                 total += sg * st[r] * int(sc)
             elif t in REG:
-                if REG[t][1] != 64 or t not in st:
+                if REG[t][1] != 64 or not isinstance(st.get(t), int):
                     return None
                 total += sg * st[t]
             else:
@@ -656,10 +722,10 @@ class Lifter:
                 st.extend(succ[v])
         return {body[u] for u in range(n) if (spine >> u) & 1 and self.ins[body[u]].mn == "call" and u not in on_cycle}
 
-    def analyse_constants(self, body, inside):
+    def analyse_constants(self, body, inside, entry=None):
         """in-state (known constants) of every instruction of the function: forward data flow, meet = agreement"""
         ins_state = {}
-        work = [(body[0], {})]
+        work = [(body[0], dict(entry or {}))]
         while work:
             a, st = work.pop()
             if a in ins_state:
@@ -713,12 +779,12 @@ class Lifter:
                     return None
         return "rbp" if ok else None
 
-    def emit_func(self, e, minor=False):
+    def emit_func(self, e, minor=False, entry_consts=None, name=None):
         self.cur_fn, self.cur_minor = e, minor
         body = self.funcs[e]
         inside = set(body)
         self.frame_reg = self.find_frame_reg(body)
-        self.consts_at = self.analyse_constants(body, inside)
+        self.consts_at = self.analyse_constants(body, inside, entry_consts or {})
         self.const_regs = {}
         targets = set()
         for a in body:
@@ -735,7 +801,7 @@ class Lifter:
                 leaders[cur] = 0
             leaders[cur] += 1
             prev = i
-        out = [f"LIFT_FN void f_{e:x}{'_m' if minor else ''}(cpu_t* c) {{", "  LIFT_LOCALS; LIFT_ENTER;"]
+        out = [f"LIFT_FN void {name or f'f_{e:x}' + ('_m' if minor else '')}(cpu_t* c) {{", "  LIFT_LOCALS; LIFT_ENTER;"]
         sync_at = set()
         if e == self.STEP:
             out.append("  LIFT_SYNC;        /* every aircraft calls step() the same number of times: a convergent point */")
@@ -769,13 +835,28 @@ class Lifter:
     def ends_flow(self, i):
         return i.mn in ("ret", "jmp", "int3", "ud2")
 
-    def call_fn(self, t, tail=False):
+    def operand_const(self, s, ins):
+        """translation-time value of an integer operand (a register the analysis knows, or a frozen memory location)"""
+        if s in REG and REG[s][1] == 64:
+            v = self.const_regs.get(s)
+            return v if isinstance(v, int) else None
+        if "[" in s:
+            return self.frozen_operand(s, ins, 8)
+        return None
+
+    def call_fn(self, t, tail=False, rcx=None):
         """statement(s) calling translated function / import thunk `t` (direct)"""
         if self.is_import_thunk(t):
             return self.import_call(self.thunk_name(t)) + (" LIFT_EXIT; return;" if tail else "")
         if t == self.SOLVER and self.cur_minor:
             return "LIFT_TRAP(\"solver reached from a minor step\", 0);"
         name = f"f_{t:x}_m" if (t == self.STEP and self.cur_fn == self.SOLVER) else f"f_{t:x}"
+        if rcx is not None and self.frozen is not None and t not in (self.STEP, self.SOLVER):
+            key = (t, rcx)
+            if key not in self.clones:
+                self.clones[key] = f"f_{t:x}_s{rcx & 0xffffffff:x}"
+                self.clone_work.append(key)
+            name = self.clones[key]
         if tail:
             # the callee returns to OUR caller: its `ret` pops the return address our caller pushed
             return f"{self.PRECALL} {name}(c); return;"
@@ -807,6 +888,12 @@ class Lifter:
                 slot = self.const_addr(ops[0], i)
                 if slot in self.pe.iat:
                     return self.import_call(self.pe.iat[slot])
+            tv = self.operand_const(ops[0], i)
+            if tv is not None and tv in self.funcs:
+                # the target is a constant of the initialised model (an S-function method pointer); when the first argument
+                # (the block's SimStruct) is constant too, call a copy of the method specialised for it
+                rcx = self.const_regs.get("rcx")
+                return self.call_fn(tv, rcx=rcx if isinstance(rcx, int) else None)
             return f"{{ uint64_t t_={rd(ops[0], i, 64)}; r4-=8; {self.PRECALL} lift_dispatch(c,t_); r4+=8; {self.POSTCALL} }}"
         if mn == "jmp":
             t = self.direct_target(i)
@@ -1060,6 +1147,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--variant", default="extended_input")
     ap.add_argument("--out", required=True)
+    ap.add_argument("--no-fold", action="store_true", help="single pass: do not fold loads from the initialised image")
     args = ap.parse_args()
     path = os.path.join(REF_DIR, args.variant, "_citation.cp39-win_amd64.pyd")
     pe = PE(path)
@@ -1067,6 +1155,22 @@ def main():
     L = Lifter(pe, ins)
     L.discover([BASE + v for v in ENTRY.values()])
     os.makedirs(args.out, exist_ok=True)
+    # pass 1 -> run the translated initialize() on the host -> pass 2 folds loads from the part of the image that is constant
+    # from then on (everything outside the regions step() writes)
+    if not args.no_fold:
+        import tempfile
+
+        here = os.path.dirname(os.path.abspath(__file__))
+        with tempfile.TemporaryDirectory() as tmp:
+            inc, img, exe = os.path.join(tmp, "init.inc"), os.path.join(tmp, "image.bin"), os.path.join(tmp, "init_host")
+            with open(inc, "w") as f:
+                f.write(PRELUDE + L.emit_all([BASE + ENTRY["initialize"]]) + POSTLUDE)
+            with open(img, "wb") as f:
+                f.write(bytes(pe.img))
+            subprocess.run(["gcc", "-O1", "-ffp-contract=off", "-w", f"-DLIFT_GENERATED_INC=\"{inc}\"", "-o", exe,
+                            os.path.join(here, "lift_init_host.c"), "-lm"], check=True)
+            L.frozen = subprocess.run([exe, img], check=True, capture_output=True).stdout
+            assert len(L.frozen) == 0x40000
     # three files: everything (CPU library), what step() reaches, what initialize() / terminate() reach (the CUDA build
     # compiles the last two under different memory models)
     for tag, roots in (("code", None), ("code_step", [BASE + ENTRY["step"]]), ("code_init", [BASE + ENTRY["initialize"], BASE + ENTRY["terminate"]])):
@@ -1084,7 +1188,7 @@ def main():
             f.write(",".join(str(v) for v in blob[o:o + 64]) + ",\n")
     n_ins = sum(len(v) for v in L.funcs.values())
     print(f"{args.variant}: {len(L.funcs)} functions, {n_ins} instructions translated, image {pe.image_size} bytes, "
-          f"{getattr(L, 'n_spine', 0)} convergent call sites in step()")
+          f"{getattr(L, 'n_spine', 0)} convergent call sites in step(), {getattr(L, 'n_clones', 0)} specialised S-function copies")
     for e, u in sorted(L.unknown.items()):
         print(f"  f_{e:x}: untranslated:", [(hex(x[0]), x[1]) if isinstance(x, tuple) else hex(x) for x in u[:6]])
     return 0
