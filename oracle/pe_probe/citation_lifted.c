@@ -32,6 +32,9 @@ static inline uint8_t* lift_ptr(cpu_t* c, uint64_t a, unsigned n)
 {
     const uint64_t off = (uint32_t)((uint32_t)a - (uint32_t)LIFT_BASE);
     if (off > LIFT_MEM_SIZE - n) lift_trap("memory access outside the emulated address space", a);
+    /* [0x40000, 0x40800) is the virtual range of the private frames of leaf functions (LIFT_LEAF_LO32): they live in C arrays,
+     * so nothing may reach that range through memory -- a pointer into such a frame that the analysis missed would */
+    if (off - 0x40000u < 0x800u) lift_trap("access to the virtual range of a private leaf frame through memory", a);
     return c->M + off;
 }
 static inline uint8_t* lift_wptr(cpu_t* c, uint64_t a, unsigned n)

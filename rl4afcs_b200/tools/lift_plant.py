@@ -193,6 +193,12 @@ class Lifter:
     traffic (the callee's prologue / epilogue saves and restores whatever its own locals hold), volatile ones are dead."""
 
     STEP, SOLVER = BASE + 0x3720, BASE + 0x1c80
+    COOKIE_CHECK = BASE + 0x11870          # MSVC's __security_check_cookie(rcx): compares with a constant of the image, no effect
+    # Specialised S-function copies that call nothing but C-runtime imports run on a PRIVATE frame: a C array local to the
+    # translated function, addressed from a compile-time-constant stack pointer.  The C compiler then sees every frame access
+    # at a constant offset of a non-escaping array (after unrolling the 3-trip matrix loops) and keeps the x86 spill slots and
+    # the 3x3 work matrices in registers instead of thread-local memory.  Virtual range: the never-used bottom of the stack region.
+    LEAF_LO, LEAF_SIZE, LEAF_ENTRY_RSP = BASE + 0x40000, 0x800, BASE + 0x40800 - 0x48
 
     def __init__(self, pe, ins):
         self.pe, self.ins = pe, ins
@@ -201,6 +207,7 @@ class Lifter:
         self.frame_reg = None
         self.const_regs = {}
         self.region_hints = True
+        self.leaf_private = False
         self.frozen = None          # second pass: the image after initialize() (bytes); loads from its constant part are folded
         self.clones = {}            # (function, rcx) -> name of the copy specialised for that first argument
         self.clone_work = []
@@ -296,9 +303,34 @@ class Lifter:
         a = self.fold_address(s, ins, self.const_regs)
         return None if a is None else self.frozen_value(a, nbytes)
 
+    def leaf_eligible(self, body):
+        depth = 0
+        for a in body:
+            i = self.ins[a]
+            if i.mn == "call":
+                t = self.direct_target(i)
+                if t is None:
+                    if not ("[rip" in i.ops[0] and self.const_addr(i.ops[0], i) in self.pe.iat):
+                        return False
+                elif not (self.is_import_thunk(t) or t == self.COOKIE_CHECK):
+                    return False
+            elif i.mn == "jmp":
+                t = self.direct_target(i)
+                if t is None or t not in set(body):
+                    return False
+            elif i.mn == "push":
+                depth += 8
+            elif i.mn == "sub" and i.ops[0] == "rsp":
+                if not re.match(r"0x[0-9a-f]+$", i.ops[1]):
+                    return False
+                depth += int(i.ops[1], 16)
+            elif i.mn.startswith("rep "):
+                return False
+        return depth + 0x100 < self.LEAF_SIZE - 0x48
+
     def hint(self, s):
         if self.is_stack_operand(s):
-            return "S"
+            return "F" if self.leaf_private else "S"
         if not self.region_hints:
             return ""
         inner = s[s.index("[") + 1:s.rindex("]")]
@@ -801,7 +833,12 @@ class Lifter:
                 leaders[cur] = 0
             leaders[cur] += 1
             prev = i
-        out = [f"LIFT_FN void {name or f'f_{e:x}' + ('_m' if minor else '')}(cpu_t* c) {{", "  LIFT_LOCALS; LIFT_ENTER;"]
+        self.leaf_private = bool(name) and self.frozen is not None and self.leaf_eligible(body)
+        if self.leaf_private:
+            self.n_leaf = getattr(self, "n_leaf", 0) + 1
+            # the private frame changes which operands are 'stack' operands of THIS function only; constants were analysed above
+        out = [f"LIFT_FN void {name or f'f_{e:x}' + ('_m' if minor else '')}(cpu_t* c) {{",
+               "  LIFT_LOCALS; LIFT_ENTER_LEAF;" if self.leaf_private else "  LIFT_LOCALS; LIFT_ENTER;"]
         sync_at = set()
         if e == self.STEP:
             out.append("  LIFT_SYNC;        /* every aircraft calls step() the same number of times: a convergent point */")
@@ -881,6 +918,8 @@ class Lifter:
         if mn == "call":
             t = self.direct_target(i)
             if t is not None:
+                if t == self.COOKIE_CHECK:
+                    return ";   /* __security_check_cookie: compares rcx with a constant of the image; no effect on a correct run */"
                 if t in self.funcs or self.is_import_thunk(t):
                     return self.call_fn(t)
                 return f"LIFT_TRAP(\"call to untranslated code\", 0x{t:x}ULL);"
@@ -929,9 +968,9 @@ class Lifter:
         if mn == "cqo":
             return "r2=(uint64_t)(((int64_t)r0)>>63);"
         if mn == "push":
-            return f"r4-=8; STS64((uint32_t)r4,{rd(ops[0], i, 64)});"
+            return f"r4-=8; ST{'F' if self.leaf_private else 'S'}64((uint32_t)r4,{rd(ops[0], i, 64)});"
         if mn == "pop":
-            return f"{{ uint64_t t_=LDS64((uint32_t)r4); r4+=8; {wr(ops[0], i, 't_')} }}"
+            return f"{{ uint64_t t_=LD{'F' if self.leaf_private else 'S'}64((uint32_t)r4); r4+=8; {wr(ops[0], i, 't_')} }}"
         if mn == "xchg":
             w = self.op_size(ops[0]) or self.op_size(ops[1])
             return f"{{ uint64_t a_={rd(ops[0], i, w)}, b_={rd(ops[1], i, w)}; {wr(ops[0], i, 'b_', w)} {wr(ops[1], i, 'a_', w)} }}"
@@ -1133,6 +1172,22 @@ PRELUDE = r"""/* GENERATED by rl4afcs_b200/tools/lift_plant.py from the referenc
 #define LIFT_ENTER \
     r1=c->r[1]; r2=c->r[2]; r8=c->r[8]; r9=c->r[9]; r4=c->r[4]; \
     x0l=c->x[0].u[0]; x1l=c->x[1].u[0]; x2l=c->x[2].u[0]; x3l=c->x[3].u[0]
+/* private frame of a leaf function: a local array addressed from a constant stack pointer (tools/lift_plant.py: LEAF_*) */
+#define LIFT_LEAF_LO32 0x80040000u
+#define LIFT_ENTER_LEAF \
+    uint8_t lf_[0x800] __attribute__((aligned(16))); \
+    r1=c->r[1]; r2=c->r[2]; r8=c->r[8]; r9=c->r[9]; r4=0x1800407b8ULL; \
+    x0l=c->x[0].u[0]; x1l=c->x[1].u[0]; x2l=c->x[2].u[0]; x3l=c->x[3].u[0]
+#define LIFT_LF(T, a) (*(T*)(lf_ + (uint32_t)((a) - LIFT_LEAF_LO32)))
+#define LDF8(a) ((uint64_t)LIFT_LF(uint8_t, a))
+#define LDF16(a) ((uint64_t)LIFT_LF(uint16_t, a))
+#define LDF32(a) ((uint64_t)LIFT_LF(uint32_t, a))
+#define LDF64(a) LIFT_LF(uint64_t, a)
+#define LDFD(a) LIFT_LF(double, a)
+#define STF8(a, v) (LIFT_LF(uint8_t, a) = (uint8_t)(v))
+#define STF16(a, v) (LIFT_LF(uint16_t, a) = (uint16_t)(v))
+#define STF32(a, v) (LIFT_LF(uint32_t, a) = (uint32_t)(v))
+#define STF64(a, v) (LIFT_LF(uint64_t, a) = (uint64_t)(v))
 #define LIFT_PRECALL \
     c->r[1]=r1; c->r[2]=r2; c->r[8]=r8; c->r[9]=r9; c->r[4]=r4; \
     c->x[0].u[0]=x0l; c->x[1].u[0]=x1l; c->x[2].u[0]=x2l; c->x[3].u[0]=x3l
@@ -1188,7 +1243,8 @@ def main():
             f.write(",".join(str(v) for v in blob[o:o + 64]) + ",\n")
     n_ins = sum(len(v) for v in L.funcs.values())
     print(f"{args.variant}: {len(L.funcs)} functions, {n_ins} instructions translated, image {pe.image_size} bytes, "
-          f"{getattr(L, 'n_spine', 0)} convergent call sites in step(), {getattr(L, 'n_clones', 0)} specialised S-function copies")
+          f"{getattr(L, 'n_spine', 0)} convergent call sites in step(), {getattr(L, 'n_clones', 0)} specialised S-function copies, "
+          f"{getattr(L, 'n_leaf', 0)} emitted with a private frame")
     for e, u in sorted(L.unknown.items()):
         print(f"  f_{e:x}: untranslated:", [(hex(x[0]), x[1]) if isinstance(x, tuple) else hex(x) for x in u[:6]])
     return 0
