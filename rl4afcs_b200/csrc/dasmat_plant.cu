@@ -64,6 +64,7 @@ constexpr uint32_t kBase32 = 0x80000000u;                       // low 32 bits o
 enum { kErrTrap = 1, kErrWildAccess = 2, kErrStoreToImage = 4 };
 
 #define LIFT_FN static __device__ __noinline__
+#define LIFT_FN_INLINE static __device__ __forceinline__
 #define LIFT_TRAP(msg, v) do { c->err |= kErrTrap; return; } while (0)
 #define lift_cos cos
 #define lift_sin sin

@@ -535,15 +535,37 @@ class Lifter:
                             work.extend(self.addr_taken & set(self.funcs))
         return seen
 
+    INLINE_MAX = 0          # measured: inlining the two table-lookup helpers (99 sites) 1.81e7 -> 1.74e7 plant steps/s: code growth costs more than the call protocol
+
+    def inlinable(self, e, depth=0):
+        """small helpers (the table-lookup routines at RVA 0xe840 / 0xe8d0: ~770 calls per step) are emitted `inline`: the call
+        protocol through cpu_t disappears, and their pointer arguments are often constants of the call site"""
+        body = self.funcs.get(e)
+        if body is None or len(body) > self.INLINE_MAX or depth > 2 or e in (self.STEP, self.SOLVER) or e in self.addr_taken:
+            return False
+        for a in body:
+            i = self.ins[a]
+            if i.mn in ("call", "jmp"):
+                t = self.direct_target(i)
+                if t is None:
+                    if not ("[rip" in i.ops[0] and self.const_addr(i.ops[0], i) in self.pe.iat):
+                        return False
+                elif t not in set(body) and not self.is_import_thunk(t) and not (t in self.funcs and t != e and self.inlinable(t, depth + 1)):
+                    return False
+        return True
+
+    def qual(self, e):
+        return "LIFT_FN_INLINE" if self.inlinable(e) else "LIFT_FN"
+
     def emit_all(self, roots=None):
         out = []
         names = sorted(self.funcs if roots is None else self.reachable(roots))
         self.emitting = set(names)
         for e in names:
-            out.append(f"LIFT_FN void f_{e:x}(cpu_t* c);")
+            out.append(f"{self.qual(e)} void f_{e:x}(cpu_t* LIFT_RESTRICT c);")
         with_step = self.STEP in self.emitting
         if with_step:
-            out.append(f"LIFT_FN void f_{self.STEP:x}_m(cpu_t* c);")
+            out.append(f"LIFT_FN void f_{self.STEP:x}_m(cpu_t* LIFT_RESTRICT c);")
         out.append("")
         # indirect-call dispatcher over address-taken functions
         out.append("LIFT_FN void lift_dispatch(cpu_t* c, uint64_t target) {")
@@ -562,7 +584,7 @@ class Lifter:
             t, rcx = self.clone_work.pop()
             bodies.extend(self.emit_func(t, entry_consts={"rcx": rcx}, name=self.clones[(t, rcx)]))
         self.n_clones = len(self.clones)
-        out.extend(f"LIFT_FN void {n}(cpu_t* c);" for n in sorted(self.clones.values()))
+        out.extend(f"LIFT_FN void {n}(cpu_t* LIFT_RESTRICT c);" for n in sorted(self.clones.values()))
         out.extend(bodies)
         return "\n".join(out)
 
@@ -837,7 +859,7 @@ class Lifter:
         if self.leaf_private:
             self.n_leaf = getattr(self, "n_leaf", 0) + 1
             # the private frame changes which operands are 'stack' operands of THIS function only; constants were analysed above
-        out = [f"LIFT_FN void {name or f'f_{e:x}' + ('_m' if minor else '')}(cpu_t* c) {{",
+        out = [f"{'LIFT_FN' if (name or minor) else self.qual(e)} void {name or f'f_{e:x}' + ('_m' if minor else '')}(cpu_t* LIFT_RESTRICT c) {{",
                "  LIFT_LOCALS; LIFT_ENTER_LEAF;" if self.leaf_private else "  LIFT_LOCALS; LIFT_ENTER;"]
         sync_at = set()
         if e == self.STEP:
@@ -1140,6 +1162,12 @@ class Lifter:
 PRELUDE = r"""/* GENERATED by rl4afcs_b200/tools/lift_plant.py from the reference's plant binary -- do not edit, do not commit. */
 #ifndef LIFT_FN
 #define LIFT_FN static
+#endif
+#ifndef LIFT_FN_INLINE
+#define LIFT_FN_INLINE static inline
+#endif
+#ifndef LIFT_RESTRICT
+#define LIFT_RESTRICT __restrict__
 #endif
 #ifndef LIFT_BB
 #define LIFT_BB(fn, n)
