@@ -6,9 +6,13 @@ fault_scenario, reference{tracked_state, signal}``), same ``reset(seed) -> (MDP_
 and ``step(action) -> (MDP_state, reward, None, False, info)`` with the reference's info keys (``nans, s, yref,
 action_commanded, action_effective, rates, t, x_full, x, e, RSE, reward_grad``).  The wrapper logic (action scaling,
 rate-limited first-order actuators, fault / saturation injection, rewards, MDP state) follows the reference line by
-line inside ``rl4_nl_env_step``; the aircraft itself is the documented surrogate of
-``include/rl4_citation_surrogate.h`` because the reference's ``_citation`` model is a source-less Windows binary
-(plant parity unpinned).
+line inside ``rl4_nl_env_step``.  The aircraft itself (``_citation.step``, envs/nonlinear/env.py:210) is selectable:
+
+* ``plant="surrogate"`` (default): the stand-in of ``include/rl4_citation_surrogate.h``, calibrated against the reference's
+  binary (fast: the throughput configurations run on it; tolerance-level fidelity, DESIGN.md section 9);
+* ``plant="dasmat"``: the reference's OWN model -- its ``_citation`` Windows binary translated to C at build time and compiled
+  for the GPU (csrc/dasmat_plant.cu; every step within ~1e-15 relative of the binary; ~150x heavier).
+  ``reset()`` then runs the model's own ``initialize()`` and the 1001 trim calls of envs/nonlinear/env.py:288-291.
 """
 from __future__ import annotations
 
