@@ -35,6 +35,11 @@ typedef struct cpu_t {
     LIFT_CPU_EXTRA
 } cpu_t;
 typedef struct lift_flags { uint8_t zf, sf, cf, of, pf; } lift_flags;
+typedef struct lift_ret { uint64_t rax, x0; } lift_ret;          /* what a translated function returns: rax and the low half of xmm0 */
+LIFT_HD lift_ret lift_mkret(uint64_t rax, uint64_t x0) { lift_ret r; r.rax = rax; r.x0 = x0; return r; }
+/* calls a translated entry point with the arguments held in cpu_t (the includer's glue: kernels, host harnesses) */
+#define LIFT_INVOKE(f, c) do { const lift_ret t__ = f((c), (c)->r[1], (c)->r[2], (c)->r[8], (c)->r[9], (c)->x[0].u[0], (c)->x[1].u[0], \
+                                                      (c)->x[2].u[0], (c)->x[3].u[0], (c)->r[4]); (c)->r[0] = t__.rax; (c)->x[0].u[0] = t__.x0; } while (0)
 
 #ifndef U2D
 LIFT_HD double lift_u2d(uint64_t u) { union { uint64_t u; double d; } t; t.u = u; return t.d; }

@@ -24,7 +24,7 @@ static void lift_trap(const char* msg, uint64_t v)
     fprintf(stderr, "citation_lifted: %s (0x%llx)\n", msg, (unsigned long long)v);
     abort();
 }
-#define LIFT_TRAP(msg, v) lift_trap(msg, (uint64_t)(v))
+#define LIFT_TRAP(msg, v) do { lift_trap(msg, (uint64_t)(v)); LIFT_TRAP_RETURN; } while (0)
 
 /* memory operands arrive as the LOW 32 BITS of the emulated address (lift.py: mem_a32); helpers that take full 64-bit
  * addresses (memcpy & co.) truncate the same way */
@@ -180,8 +180,8 @@ static void enter(cit_lifted* m)
      * shadow space above it as the Windows x64 convention requires */
     m->cpu.r[4] = LIFT_BASE + LIFT_MEM_SIZE - 0x100 - 8;
 }
-void cit_lifted_initialize(cit_lifted* m) { enter(m); f_1800096f0(&m->cpu); }
-void cit_lifted_terminate(cit_lifted* m) { enter(m); f_18000e620(&m->cpu); }
+void cit_lifted_initialize(cit_lifted* m) { enter(m); LIFT_INVOKE(f_1800096f0, &m->cpu); }
+void cit_lifted_terminate(cit_lifted* m) { enter(m); LIFT_INVOKE(f_18000e620, &m->cpu); }
 /* step(out[12], in[11]): the buffers live in the emulated stack region above the frame */
 void cit_lifted_step(cit_lifted* m, const double* in, double* out)
 {
@@ -189,7 +189,7 @@ void cit_lifted_step(cit_lifted* m, const double* in, double* out)
     memcpy(m->mem + (a_in - LIFT_BASE), in, 11 * sizeof(double));
     enter(m);
     m->cpu.r[1] = a_out; m->cpu.r[2] = a_in;
-    f_180003720(&m->cpu);
+    LIFT_INVOKE(f_180003720, &m->cpu);
     memcpy(out, m->mem + (a_out - LIFT_BASE), 12 * sizeof(double));
 }
 void cit_lifted_run(cit_lifted* m, const double* in, int n_steps, double* out)

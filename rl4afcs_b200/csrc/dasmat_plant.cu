@@ -65,7 +65,7 @@ enum { kErrTrap = 1, kErrWildAccess = 2, kErrStoreToImage = 4 };
 
 #define LIFT_FN static __device__ __noinline__
 #define LIFT_FN_INLINE static __device__ __forceinline__
-#define LIFT_TRAP(msg, v) do { c->err |= kErrTrap; return; } while (0)
+#define LIFT_TRAP(msg, v) do { c->err |= kErrTrap; LIFT_TRAP_RETURN; } while (0)
 #define lift_cos cos
 #define lift_sin sin
 #define lift_tan tan
@@ -313,7 +313,7 @@ __device__ __forceinline__ void dasmat_thread_step(DasmatThread* t, const double
     for (int j = 0; j < 11; ++j) in_p[j] = u[j];
     enter(t->c);
     t->c.r[1] = kArgOut; t->c.r[2] = kArgIn;
-    step_mode::f_180003720(&t->c);
+    LIFT_INVOKE(step_mode::f_180003720, &t->c);
 #pragma unroll
     for (int j = 0; j < 12; ++j) xo[j] = out_p[j];
 }
@@ -391,7 +391,7 @@ __global__ void dasmat_initialize_kernel(uint8_t* G, int* err)
     memset(&c, 0, sizeof c);
     c.G = G; c.m = nullptr;
     enter(c);
-    init_mode::f_1800096f0(&c);
+    LIFT_INVOKE(init_mode::f_1800096f0, &c);
     *err = c.err;
 }
 
@@ -431,7 +431,7 @@ dasmat_step_kernel(uint8_t* G, uint64_t* __restrict__ state, int64_t stride, int
         for (int j = 0; j < 11; ++j) in_p[j] = u[(int64_t)j * u_stride + i];
         enter(c);
         c.r[1] = a_out; c.r[2] = a_in;
-        step_mode::f_180003720(&c);
+        LIFT_INVOKE(step_mode::f_180003720, &c);
         if (out_all && active)
             for (int j = 0; j < 12; ++j) out_all[((int64_t)k * 12 + j) * out_stride + i] = out_p[j];
     }

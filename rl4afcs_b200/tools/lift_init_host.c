@@ -16,7 +16,7 @@
 #include "../../include/rl4_lift_runtime.h"
 
 static void trap(const char* msg, uint64_t v) { fprintf(stderr, "lift_init_host: %s (0x%llx)\n", msg, (unsigned long long)v); exit(3); }
-#define LIFT_TRAP(msg, v) trap(msg, (uint64_t)(v))
+#define LIFT_TRAP(msg, v) do { trap(msg, (uint64_t)(v)); LIFT_TRAP_RETURN; } while (0)
 static inline uint8_t* at(cpu_t* c, uint32_t a32, unsigned n)
 {
     const uint32_t off = a32 - (uint32_t)LIFT_BASE;
@@ -94,7 +94,7 @@ int main(int argc, char** argv)
     memset(&c, 0, sizeof c);
     c.M = mem;
     c.r[4] = LIFT_BASE + MEM_SIZE - 0x100 - 8;
-    f_1800096f0(&c);
+    LIFT_INVOKE(f_1800096f0, &c);
     fwrite(mem, 1, 0x40000, stdout);
     return 0;
 }

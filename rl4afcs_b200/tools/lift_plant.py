@@ -562,16 +562,16 @@ class Lifter:
         names = sorted(self.funcs if roots is None else self.reachable(roots))
         self.emitting = set(names)
         for e in names:
-            out.append(f"{self.qual(e)} void f_{e:x}(cpu_t* LIFT_RESTRICT c);")
+            out.append(f"{self.qual(e)} LIFT_RET f_{e:x}(LIFT_PARAMS);")
         with_step = self.STEP in self.emitting
         if with_step:
-            out.append(f"LIFT_FN void f_{self.STEP:x}_m(cpu_t* LIFT_RESTRICT c);")
+            out.append(f"LIFT_FN LIFT_RET f_{self.STEP:x}_m(LIFT_PARAMS);")
         out.append("")
         # indirect-call dispatcher over address-taken functions
-        out.append("LIFT_FN void lift_dispatch(cpu_t* c, uint64_t target) {")
+        out.append("LIFT_FN LIFT_RET lift_dispatch(LIFT_PARAMS, uint64_t target) {")
         out.append("  switch (target) {")
         for e in sorted(self.addr_taken & self.emitting):
-            out.append(f"  case 0x{e:x}ULL: f_{e:x}(c); return;")
+            out.append(f"  case 0x{e:x}ULL: LIFT_FORWARD(f_{e:x});")
         out.append("  default: LIFT_TRAP(\"indirect call to an address that is not a translated function\", target);")
         out.append("  }\n}\n")
         self.clones, self.clone_work = {}, []
@@ -584,7 +584,7 @@ class Lifter:
             t, rcx = self.clone_work.pop()
             bodies.extend(self.emit_func(t, entry_consts={"rcx": rcx}, name=self.clones[(t, rcx)]))
         self.n_clones = len(self.clones)
-        out.extend(f"LIFT_FN void {n}(cpu_t* LIFT_RESTRICT c);" for n in sorted(self.clones.values()))
+        out.extend(f"LIFT_FN LIFT_RET {n}(LIFT_PARAMS);" for n in sorted(self.clones.values()))
         out.extend(bodies)
         return "\n".join(out)
 
@@ -859,7 +859,7 @@ class Lifter:
         if self.leaf_private:
             self.n_leaf = getattr(self, "n_leaf", 0) + 1
             # the private frame changes which operands are 'stack' operands of THIS function only; constants were analysed above
-        out = [f"{'LIFT_FN' if (name or minor) else self.qual(e)} void {name or f'f_{e:x}' + ('_m' if minor else '')}(cpu_t* LIFT_RESTRICT c) {{",
+        out = [f"{'LIFT_FN' if (name or minor) else self.qual(e)} LIFT_RET {name or f'f_{e:x}' + ('_m' if minor else '')}(LIFT_PARAMS) {{",
                "  LIFT_LOCALS; LIFT_ENTER_LEAF;" if self.leaf_private else "  LIFT_LOCALS; LIFT_ENTER;"]
         sync_at = set()
         if e == self.STEP:
@@ -906,7 +906,7 @@ class Lifter:
     def call_fn(self, t, tail=False, rcx=None):
         """statement(s) calling translated function / import thunk `t` (direct)"""
         if self.is_import_thunk(t):
-            return self.import_call(self.thunk_name(t)) + (" LIFT_EXIT; return;" if tail else "")
+            return self.import_call(self.thunk_name(t)) + (" LIFT_RETURN;" if tail else "")
         if t == self.SOLVER and self.cur_minor:
             return "LIFT_TRAP(\"solver reached from a minor step\", 0);"
         name = f"f_{t:x}_m" if (t == self.STEP and self.cur_fn == self.SOLVER) else f"f_{t:x}"
@@ -918,8 +918,8 @@ class Lifter:
             name = self.clones[key]
         if tail:
             # the callee returns to OUR caller: its `ret` pops the return address our caller pushed
-            return f"{self.PRECALL} {name}(c); return;"
-        return f"r4-=8; {self.PRECALL} {name}(c); r4+=8; {self.POSTCALL}"
+            return f"LIFT_TAILCALL({name});"
+        return f"r4-=8; LIFT_CALL({name}); r4+=8;"
 
     def goto(self, t, inside):
         if t in inside:
@@ -936,7 +936,7 @@ class Lifter:
         if mn in ("int3", "ud2"):
             return f"LIFT_TRAP(\"{mn}\", 0x{i.addr:x}ULL);"
         if mn == "ret":
-            return "LIFT_EXIT; return;"
+            return "LIFT_RETURN;"
         if mn == "call":
             t = self.direct_target(i)
             if t is not None:
@@ -955,7 +955,7 @@ class Lifter:
                 # (the block's SimStruct) is constant too, call a copy of the method specialised for it
                 rcx = self.const_regs.get("rcx")
                 return self.call_fn(tv, rcx=rcx if isinstance(rcx, int) else None)
-            return f"{{ uint64_t t_={rd(ops[0], i, 64)}; r4-=8; {self.PRECALL} lift_dispatch(c,t_); r4+=8; {self.POSTCALL} }}"
+            return f"{{ uint64_t t_={rd(ops[0], i, 64)}; r4-=8; LIFT_CALL_DISPATCH(t_); r4+=8; }}"
         if mn == "jmp":
             t = self.direct_target(i)
             if t is not None:
@@ -963,8 +963,8 @@ class Lifter:
             if "[rip" in ops[0]:
                 slot = self.const_addr(ops[0], i)
                 if slot in self.pe.iat:
-                    return f"{self.import_call(self.pe.iat[slot])} LIFT_EXIT; return;"
-            return f"{{ uint64_t t_={rd(ops[0], i, 64)}; {self.PRECALL} lift_dispatch(c,t_); return; }}"
+                    return f"{self.import_call(self.pe.iat[slot])} LIFT_RETURN;"
+            return f"{{ uint64_t t_={rd(ops[0], i, 64)}; LIFT_TAILCALL_DISPATCH(t_); }}"
         if mn.startswith("j") and mn[1:] in CC:
             return f"if ({CC[mn[1:]]}) {self.goto(self.direct_target(i), inside)}"
         if mn.startswith("set") and mn[3:] in CC:
@@ -1197,15 +1197,49 @@ PRELUDE = r"""/* GENERATED by rl4afcs_b200/tools/lift_plant.py from the referenc
     (void)r0;(void)r1;(void)r2;(void)r3;(void)r5;(void)r6;(void)r7;(void)r8;(void)r9;(void)r10;(void)r11;(void)r12;(void)r13;(void)r14;(void)r15; \
     (void)x0h;(void)x1l;(void)x1h;(void)x2l;(void)x2h;(void)x3l;(void)x3h;(void)x4l;(void)x4h;(void)x5l;(void)x5h;(void)x6l;(void)x6h;(void)x7l;(void)x7h; \
     (void)x8l;(void)x8h;(void)x9l;(void)x9h;(void)x10l;(void)x10h;(void)x11l;(void)x11h;(void)x12l;(void)x12h;(void)x13l;(void)x13h;(void)x14l;(void)x14h;(void)x15l;(void)x15h;(void)fl
+/* How registers cross a function boundary (Windows x64 convention: rcx rdx r8 r9 xmm0-3 rsp in, rax xmm0 out):
+ * LIFT_REG_PROTOCOL 1 -- as C parameters / a two-word return value (they travel in machine registers);
+ * LIFT_REG_PROTOCOL 0 -- through the shared cpu_t (memory). */
+#ifndef LIFT_REG_PROTOCOL
+#define LIFT_REG_PROTOCOL 1
+#endif
+/* private frame of a leaf function: a local array addressed from a constant stack pointer (tools/lift_plant.py: LEAF_*) */
+#define LIFT_LEAF_LO32 0x80040000u
+#define LIFT_LEAF_RSP 0x1800407b8ULL
+#define LIFT_LEAF_DECL uint8_t lf_[0x800] __attribute__((aligned(16)))
+#if LIFT_REG_PROTOCOL
+#define LIFT_RET lift_ret
+#define LIFT_PARAMS cpu_t* LIFT_RESTRICT c, uint64_t a1_, uint64_t a2_, uint64_t a8_, uint64_t a9_, uint64_t ax0_, uint64_t ax1_, uint64_t ax2_, uint64_t ax3_, uint64_t a4_
+#define LIFT_ARGS c, r1, r2, r8, r9, x0l, x1l, x2l, x3l, r4
+#define LIFT_ENTER r1=a1_; r2=a2_; r8=a8_; r9=a9_; r4=a4_; x0l=ax0_; x1l=ax1_; x2l=ax2_; x3l=ax3_
+#define LIFT_ENTER_LEAF LIFT_LEAF_DECL; r1=a1_; r2=a2_; r8=a8_; r9=a9_; r4=LIFT_LEAF_RSP; (void)a4_; x0l=ax0_; x1l=ax1_; x2l=ax2_; x3l=ax3_
+#define LIFT_CALL(f) do { const lift_ret t__ = f(LIFT_ARGS); r0 = t__.rax; x0l = t__.x0; } while (0)
+#define LIFT_TAILCALL(f) return f(LIFT_ARGS)
+#define LIFT_FORWARD(f) return f(c, a1_, a2_, a8_, a9_, ax0_, ax1_, ax2_, ax3_, a4_)
+#define LIFT_CALL_DISPATCH(t) do { const lift_ret t__ = lift_dispatch(LIFT_ARGS, (t)); r0 = t__.rax; x0l = t__.x0; } while (0)
+#define LIFT_TAILCALL_DISPATCH(t) return lift_dispatch(LIFT_ARGS, (t))
+#define LIFT_RETURN return lift_mkret(r0, x0l)
+#define LIFT_TRAP_RETURN return lift_mkret(0, 0)
+#else
+#define LIFT_RET void
+#define LIFT_PARAMS cpu_t* LIFT_RESTRICT c
 #define LIFT_ENTER \
     r1=c->r[1]; r2=c->r[2]; r8=c->r[8]; r9=c->r[9]; r4=c->r[4]; \
     x0l=c->x[0].u[0]; x1l=c->x[1].u[0]; x2l=c->x[2].u[0]; x3l=c->x[3].u[0]
-/* private frame of a leaf function: a local array addressed from a constant stack pointer (tools/lift_plant.py: LEAF_*) */
-#define LIFT_LEAF_LO32 0x80040000u
 #define LIFT_ENTER_LEAF \
-    uint8_t lf_[0x800] __attribute__((aligned(16))); \
-    r1=c->r[1]; r2=c->r[2]; r8=c->r[8]; r9=c->r[9]; r4=0x1800407b8ULL; \
+    LIFT_LEAF_DECL; r1=c->r[1]; r2=c->r[2]; r8=c->r[8]; r9=c->r[9]; r4=LIFT_LEAF_RSP; \
     x0l=c->x[0].u[0]; x1l=c->x[1].u[0]; x2l=c->x[2].u[0]; x3l=c->x[3].u[0]
+#define LIFT_PRECALL \
+    c->r[1]=r1; c->r[2]=r2; c->r[8]=r8; c->r[9]=r9; c->r[4]=r4; \
+    c->x[0].u[0]=x0l; c->x[1].u[0]=x1l; c->x[2].u[0]=x2l; c->x[3].u[0]=x3l
+#define LIFT_CALL(f) do { LIFT_PRECALL; f(c); r0=c->r[0]; x0l=c->x[0].u[0]; } while (0)
+#define LIFT_TAILCALL(f) do { LIFT_PRECALL; f(c); return; } while (0)
+#define LIFT_FORWARD(f) do { f(c); return; } while (0)
+#define LIFT_CALL_DISPATCH(t) do { LIFT_PRECALL; lift_dispatch(c, (t)); r0=c->r[0]; x0l=c->x[0].u[0]; } while (0)
+#define LIFT_TAILCALL_DISPATCH(t) do { LIFT_PRECALL; lift_dispatch(c, (t)); return; } while (0)
+#define LIFT_RETURN do { c->r[0]=r0; c->x[0].u[0]=x0l; return; } while (0)
+#define LIFT_TRAP_RETURN return
+#endif
 #define LIFT_LF(T, a) (*(T*)(lf_ + (uint32_t)((a) - LIFT_LEAF_LO32)))
 #define LDF8(a) ((uint64_t)LIFT_LF(uint8_t, a))
 #define LDF16(a) ((uint64_t)LIFT_LF(uint16_t, a))
@@ -1216,14 +1250,12 @@ PRELUDE = r"""/* GENERATED by rl4afcs_b200/tools/lift_plant.py from the referenc
 #define STF16(a, v) (LIFT_LF(uint16_t, a) = (uint16_t)(v))
 #define STF32(a, v) (LIFT_LF(uint32_t, a) = (uint32_t)(v))
 #define STF64(a, v) (LIFT_LF(uint64_t, a) = (uint64_t)(v))
-#define LIFT_PRECALL \
-    c->r[1]=r1; c->r[2]=r2; c->r[8]=r8; c->r[9]=r9; c->r[4]=r4; \
-    c->x[0].u[0]=x0l; c->x[1].u[0]=x1l; c->x[2].u[0]=x2l; c->x[3].u[0]=x3l
-#define LIFT_POSTCALL r0=c->r[0]; x0l=c->x[0].u[0]
-#define LIFT_EXIT c->r[0]=r0; c->x[0].u[0]=x0l
 """
 
-POSTLUDE = "\n#undef ZF\n#undef SF\n#undef CF\n#undef OF\n#undef PF\n"
+POSTLUDE = "\n" + "".join(f"#undef {m}\n" for m in (
+    "ZF SF CF OF PF LIFT_LOCALS LIFT_LEAF_LO32 LIFT_LEAF_RSP LIFT_LEAF_DECL LIFT_RET LIFT_PARAMS LIFT_ARGS LIFT_ENTER LIFT_ENTER_LEAF "
+    "LIFT_PRECALL LIFT_CALL LIFT_TAILCALL LIFT_FORWARD LIFT_CALL_DISPATCH LIFT_TAILCALL_DISPATCH LIFT_RETURN LIFT_TRAP_RETURN LIFT_LF "
+    "LDF8 LDF16 LDF32 LDF64 LDFD STF8 STF16 STF32 STF64").split())
 
 
 def main():
