@@ -16,7 +16,7 @@
 #define LIFT_STACK_SIZE 0x10000ULL
 #define LIFT_MEM_SIZE   (LIFT_IMAGE_SIZE + LIFT_HEAP_SIZE + LIFT_STACK_SIZE)
 
-#define LIFT_CPU_EXTRA uint8_t* M; uint64_t n_ins; uint8_t* wmask;
+#define LIFT_CPU_EXTRA uint8_t* M; uint64_t n_ins; uint8_t* wmask; int guard;
 #include "../../include/rl4_lift_runtime.h"
 
 static void lift_trap(const char* msg, uint64_t v)
@@ -40,6 +40,13 @@ static inline uint8_t* lift_ptr(cpu_t* c, uint64_t a, unsigned n)
 static inline uint8_t* lift_wptr(cpu_t* c, uint64_t a, unsigned n)
 {
     uint8_t* p = lift_ptr(c, a, n);
+    if (c->guard) {
+        /* after initialize(): the translator folded loads from these parts of the writable window (lift_plant.py FROZEN_GAPS) and
+         * from the image outside the regions step() writes -- a store there would invalidate the folded code */
+        const uint32_t off = (uint32_t)a - (uint32_t)LIFT_BASE;
+        if (off < 0x3a078u ? !(off - 0x2eb00u < 0x100u) : (off - 0x3a4b8u < 0x88u || off - 0x3a574u < 0x74u || off - 0x3a5f0u < 0x590u))
+            lift_trap("store into memory the translation assumes constant after initialize()", a);
+    }
     if (c->wmask) memset(c->wmask + (uint32_t)((uint32_t)a - (uint32_t)LIFT_BASE), 1, n);
     return p;
 }
@@ -180,8 +187,9 @@ static void enter(cit_lifted* m)
      * shadow space above it as the Windows x64 convention requires */
     m->cpu.r[4] = LIFT_BASE + LIFT_MEM_SIZE - 0x100 - 8;
 }
-void cit_lifted_initialize(cit_lifted* m) { enter(m); LIFT_INVOKE(f_1800096f0, &m->cpu); }
-void cit_lifted_terminate(cit_lifted* m) { enter(m); LIFT_INVOKE(f_18000e620, &m->cpu); }
+void cit_lifted_initialize(cit_lifted* m) { m->cpu.guard = 0; enter(m); LIFT_INVOKE(f_1800096f0, &m->cpu); m->cpu.guard = 1; }
+void cit_lifted_terminate_unguarded(cit_lifted* m) { m->cpu.guard = 0; }
+void cit_lifted_terminate(cit_lifted* m) { m->cpu.guard = 0; enter(m); LIFT_INVOKE(f_18000e620, &m->cpu); }
 /* step(out[12], in[11]): the buffers live in the emulated stack region above the frame */
 void cit_lifted_step(cit_lifted* m, const double* in, double* out)
 {

@@ -235,7 +235,9 @@ template <typename T> __device__ __forceinline__ void lift_store(uint8_t* m_, cp
     const uint32_t off = a32 - kBase32;
 #if RL4_DASMAT_BRANCHFREE
     const uint32_t ow = off - kWLo, oa = off - kALo;
-    const bool bad = !(ow < kWSz) && !(oa < kASz);
+    // gaps of the window that step() never writes: the translator folded loads from them (lift_plant.py FROZEN_GAPS)
+    const bool gap = off - 0x3a000u < 0x78u || off - 0x3a4b8u < 0x88u || off - 0x3a574u < 0x74u || off - 0x3a5f0u < 0x590u;
+    const bool bad = (!(ow < kWSz) && !(oa < kASz)) || gap;
     uint8_t* p = m_ + (oa < kASz ? kWSz + oa : (ow < kWSz ? ow : kDSz));     // a store outside A / D / stack lands in the window's unused gap
     *reinterpret_cast<T*>(p) = v;
     if (bad) c->err |= kErrStoreToImage;

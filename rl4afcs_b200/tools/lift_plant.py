@@ -284,12 +284,19 @@ class Lifter:
     IMAGE_RO = (0x13000, 0x3a000)          # .rdata .. the start of the window, minus the few words step() writes there
     IMAGE_RW = (0x2eb00, 0x2ec00)
     FROZEN_HOLE = (0x2eb48, 0x2eb60)       # the model time inside the rtModel structure: the only word of that region step() writes
+    # parts of the writable window that step() never writes (write tracking on the CPU build, all test scenarios): they hold the
+    # port-pointer arrays of the S-function blocks, set by initialize().  Folding them makes the specialised S-function copies
+    # fully static.  The memory models enforce the assumption: a store into a gap raises an error (CUDA) / traps (CPU build).
+    FROZEN_GAPS = ((0x3a000, 0x3a078), (0x3a4b8, 0x3a540), (0x3a574, 0x3a5e8), (0x3a5f0, 0x3ab80))
 
     def frozen_value(self, addr, nbytes):
         """the value at `addr` if it lies in the part of the image that nothing writes after initialize(), else None"""
         if self.frozen is None:
             return None
         off = (addr & 0xffffffffffffffff) - BASE
+        for lo, hi in self.FROZEN_GAPS:
+            if lo <= off and off + nbytes <= hi:
+                return int.from_bytes(self.frozen[off:off + nbytes], "little")
         if not (self.IMAGE_RO[0] <= off and off + nbytes <= self.IMAGE_RO[1]):
             return None
         if off + nbytes > self.FROZEN_HOLE[0] and off < self.FROZEN_HOLE[1]:
@@ -350,8 +357,22 @@ class Lifter:
         a = self.mem_a32(s, ins)
         return f"LD{self.hint(s)}{w}({a})"
 
+    def step_reach(self):
+        if not hasattr(self, "_step_reach"):
+            self._step_reach = self.reachable([self.STEP])
+        return self._step_reach
+
+    def check_store(self, s, ins):
+        if self.frozen is None or self.last_dynamic:
+            return
+        off = self.last_const - BASE
+        for lo, hi in self.FROZEN_GAPS:
+            if lo <= off < hi and self.cur_fn in self.step_reach():
+                raise RuntimeError(f"store at {ins.addr:#x} into a region assumed constant after initialize(): {ins.raw}")
+
     def st(self, w, s, ins, val):
         a = self.mem_a32(s, ins)
+        self.check_store(s, ins)
         k = self.hint(s)
         return f"ST{'' if k == 'I' else k}{w}({a},({val}));"
 
