@@ -550,10 +550,10 @@ def nonlinear_workload(device, counters, n=1 << 18, steps=300, warmup=700, e2e=T
     return ret
 
 
-def dasmat_workload(device, counters, issue_peak, n=75776, steps=12, warmup=4) -> dict:
+def dasmat_workload(device, counters, issue_peak, n=151552, steps=12, warmup=4) -> dict:
     """The same task on the reference's OWN aircraft model (plant='dasmat': the `_citation` binary translated at build time,
     csrc/dasmat_plant.cu) -- exact plant, ~270x heavier than the surrogate (113 712 x86 instructions per step).  Reported
-    beside the surrogate numbers; n = one resident wave of 512 aircraft per SM (one 512-thread CTA each)."""
+    beside the surrogate numbers; n = one resident wave of 1024 aircraft per SM (one 1024-thread CTA each)."""
     import torch
 
     from rl4afcs_b200 import _lib, nl_engine

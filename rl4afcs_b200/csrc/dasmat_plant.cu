@@ -42,7 +42,7 @@ constexpr uint32_t kRvaX = 0x3c120, kRvaEngine = 0x3c198;       // the 16 contin
 constexpr uint32_t kBase32 = 0x80000000u;                       // low 32 bits of the image base: memory operands arrive as low halves
 
 #ifndef RL4_DASMAT_THREADS
-#define RL4_DASMAT_THREADS 512
+#define RL4_DASMAT_THREADS 1024
 #endif
 #ifndef RL4_DASMAT_MIN_BLOCKS
 #define RL4_DASMAT_MIN_BLOCKS 1

@@ -55,11 +55,11 @@ __device__ __forceinline__ double sqrt_of_square(double d)
 #endif
 template <typename TN> struct NlBlock { static constexpr int v = RL4_NL_BLOCK_F64; };
 template <> struct NlBlock<float> { static constexpr int v = RL4_NL_BLOCK_F32; };
-// with the translated plant (PLANT = 1) the step is ~660 000 instructions of code far larger than the instruction cache: the
-// more warps of an SM walk it together the better (measured on the plant alone: 128 x 2 -> 8.6e6, 256 x 1 -> 9.6e6,
-// 512 x 1 -> 1.33e7 plant steps/s), so one 512-thread CTA per SM
+// with the translated plant (PLANT = 1) the step is ~430 000 instructions of code far larger than the instruction cache and
+// it waits on thread-local memory: one CTA per SM whose warps walk the code together, as many warps as the register file
+// allows (measured on the plant alone, final translation: 512 x 1 -> 2.02e7, 768 x 1 -> 2.13e7, 1024 x 1 -> 2.33e7 plant steps/s)
 #ifndef RL4_NL_BLOCK_DASMAT
-#define RL4_NL_BLOCK_DASMAT 512
+#define RL4_NL_BLOCK_DASMAT 1024
 #endif
 constexpr int kNlBlockDasmat = RL4_NL_BLOCK_DASMAT;
 #ifndef RL4_NL_MINB
