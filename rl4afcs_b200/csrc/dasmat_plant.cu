@@ -63,6 +63,7 @@ constexpr uint32_t kBase32 = 0x80000000u;                       // low 32 bits o
 
 enum { kErrTrap = 1, kErrWildAccess = 2, kErrStoreToImage = 4 };
 
+#define LIFT_LF_OFF(o) min((o), 0x7f8u)
 #define LIFT_FN static __device__ __noinline__
 #define LIFT_FN_INLINE static __device__ __forceinline__
 #define LIFT_TRAP(msg, v) do { c->err |= kErrTrap; LIFT_TRAP_RETURN; } while (0)
@@ -257,7 +258,9 @@ template <typename T> __device__ __forceinline__ void lift_store(uint8_t* m_, cp
 #define ST32(a, v) lift_store<uint32_t>(m_, c, (a), (uint32_t)(v))
 #define ST64(a, v) lift_store<uint64_t>(m_, c, (a), (uint64_t)(v))
 // operands the translator knows to be on the stack: inside the window by construction, no decoding
-#define LIFT_STK(T, a) reinterpret_cast<T*>(m_ + ((a) - (kBase32 + kWLo)))
+// (offsets are clamped: a NaN that reaches an index computation of a diverging aircraft must not become an out-of-bounds access;
+// for the constant addresses -- nearly all of them -- the compiler folds the clamp away)
+#define LIFT_STK(T, a) reinterpret_cast<T*>(m_ + min((uint32_t)((a) - (kBase32 + kWLo)), kWSz - 8u))
 #define LDS8(a)  ((uint64_t)*LIFT_STK(uint8_t, a))
 #define LDS16(a) ((uint64_t)*LIFT_STK(uint16_t, a))
 #define LDS32(a) ((uint64_t)*LIFT_STK(uint32_t, a))
@@ -278,7 +281,7 @@ template <typename T> __device__ __forceinline__ void lift_store(uint8_t* m_, cp
 #define STW16(a, v) (*LIFT_STK(uint16_t, a) = (uint16_t)(v))
 #define STW32(a, v) (*LIFT_STK(uint32_t, a) = (uint32_t)(v))
 #define STW64(a, v) (*LIFT_STK(uint64_t, a) = (uint64_t)(v))
-#define LIFT_IMG(T, a) __ldg(reinterpret_cast<const T*>(G_ + ((a) - kBase32)))
+#define LIFT_IMG(T, a) __ldg(reinterpret_cast<const T*>(G_ + min((uint32_t)((a) - kBase32), kImg - 8u)))
 #define LDI8(a)  ((uint64_t)LIFT_IMG(uint8_t, a))
 #define LDI16(a) ((uint64_t)LIFT_IMG(uint16_t, a))
 #define LDI32(a) ((uint64_t)LIFT_IMG(uint32_t, a))

@@ -1261,7 +1261,10 @@ PRELUDE = r"""/* GENERATED by rl4afcs_b200/tools/lift_plant.py from the referenc
 #define LIFT_RETURN do { c->r[0]=r0; c->x[0].u[0]=x0l; return; } while (0)
 #define LIFT_TRAP_RETURN return
 #endif
-#define LIFT_LF(T, a) (*(T*)(lf_ + (uint32_t)((a) - LIFT_LEAF_LO32)))
+#define LIFT_LF(T, a) (*(T*)(lf_ + LIFT_LF_OFF((uint32_t)((a) - LIFT_LEAF_LO32))))
+#ifndef LIFT_LF_OFF
+#define LIFT_LF_OFF(o) (o)          /* the CUDA build clamps (a NaN-driven index of a diverging aircraft must stay in bounds) */
+#endif
 #define LDF8(a) ((uint64_t)LIFT_LF(uint8_t, a))
 #define LDF16(a) ((uint64_t)LIFT_LF(uint16_t, a))
 #define LDF32(a) ((uint64_t)LIFT_LF(uint32_t, a))
