@@ -96,6 +96,39 @@ def test_translated_plant_equals_its_cpu_build_on_distinct_aircraft(plant):
     assert worst < 1e-10, worst
 
 
+def test_translated_plant_survives_departure_from_the_envelope(plant):
+    """Hard-over surfaces, throttle chops, c.g. shifts until states blow up (about half of the aircraft end in NaN): the kernel
+    neither hangs nor touches memory outside the model's (error bits stay 0), and agrees with the CPU translation while finite."""
+    from oracle.pe_probe import lifted
+
+    L, _lib, dev, img = plant
+    n, seg, n_seg = 512, 50, 60
+    rng = np.random.default_rng(0)
+    st, err = _fresh(plant, n)
+    crafts = [lifted.Aircraft() for _ in range(4)] if lifted.available() else []
+    for c in crafts:
+        c.initialize()
+    worst, nans = 0.0, 0
+    for s in range(n_seg):
+        u = np.tile(TRIM, (n, 1))
+        u[:, 0] += rng.uniform(-0.5, 0.5, n); u[:, 1] += rng.uniform(-0.6, 0.6, n); u[:, 2] += rng.uniform(-0.4, 0.4, n)
+        u[:, 6] = rng.choice([0.0, 0.3, 1.0], n); u[:, 7] = rng.choice([0.0, 1.0], n)
+        u[:, 8:10] = rng.uniform(0.0, 1.0, (n, 2)); u[:, 10] = rng.uniform(-1.0, 1.0, n)
+        ud = torch.tensor(u.T.copy(), device=dev)
+        out_all = torch.zeros((seg, 12, n), dtype=torch.float64, device=dev)
+        _lib.check(L.rl4_dasmat_step(img.data_ptr(), st.data_ptr(), n, n, ud.data_ptr(), n, seg, None, n, out_all.data_ptr(), err.data_ptr(), None), "rl4_dasmat_step")
+        got = out_all.cpu().numpy()
+        nans = int(np.isnan(got[-1]).any(axis=0).sum())
+        for i, c in enumerate(crafts):
+            ref = c.run(u[i], seg)
+            ok = np.isfinite(ref).all(axis=1) & np.isfinite(got[:, :, i]).all(axis=1) & (np.abs(ref).max(axis=1) < 1e6)
+            if ok.any():
+                worst = max(worst, float((np.abs(got[ok, :, i] - ref[ok]) / np.maximum(SCALE, np.abs(ref[ok]))).max()))
+    assert int(err.item()) == 0
+    assert nans > n // 10                     # the stress did drive a good part of the fleet out of the model's domain
+    assert worst < 1e-6, worst                # violent manoeuvres amplify the ulp-level libm differences; still the same flight
+
+
 def _cfg():
     from rl4afcs_b200 import nl_engine
 
