@@ -6,7 +6,8 @@
  *   RLS (n = 3, m = 1)     objects.py:439-549
  *   IDHPnonlin loop        objects.py:1006-1564 (_step_networks :1292, _update_networks :1350, _adapt_check :1212)
  * around the documented surrogate plant of include/rl4_citation_surrogate.h (the reference's plant is a
- * source-less Windows binary: PLANT PARITY UNPINNED; TensorFlow parts unpinned as in sp_oracle.h).
+ * source-less Windows binary: with the surrogate header plant parity is calibrated, not pinned; `orc_nl_set_external_plant` runs
+ * the wrapper + agent on the translated binary itself (oracle/pe_probe); TensorFlow parts unpinned as in sp_oracle.h).
  * Two policies: mixed (TF float32 nets + numpy float64 env/RLS, the reference's mix) and fp64.
  * numpy-side `@` orders measured in the build container (oracle/make_golden.py header):
  *   (4,3).T@(4,1) -> fma(a0,b0,a1*b1) + fma(a2,b2,a3*b3);  (4,4)@(4,1) -> (p0+p2)+(p1+p3), products rounded;

@@ -4,7 +4,8 @@ oracle (oracle/nl_oracle.c: restatement of envs/nonlinear/env.py:60-311 and obje
 The surrogate plant is written with IEEE basic operations only (polynomial sin / cos, binomial-series atmosphere,
 explicit FMA chains), the networks use the t13 tanh: kernel == oracle BIT FOR BIT over free-running episodes
 (test_free_run_bit_exact).  The teacher-forced tolerance tests below predate that and stay as a second, looser net.
-The reference's own plant is a source-less binary: plant parity against the reference is unpinned."""
+The surrogate is calibrated against the reference's plant binary, not a restatement of it; the reference's OWN model on the GPU
+(plant='dasmat', translated from the binary) has its tests in tests/test_gpu_dasmat.py."""
 import numpy as np
 import pytest
 
