@@ -67,8 +67,19 @@ enum { kErrTrap = 1, kErrWildAccess = 2, kErrStoreToImage = 4 };
 #define LIFT_FN static __device__ __noinline__
 #define LIFT_FN_INLINE static __device__ __forceinline__
 #define LIFT_TRAP(msg, v) do { c->err |= kErrTrap; LIFT_TRAP_RETURN; } while (0)
+// The axis-transformation S-function takes cos AND sin of the same five angles (ten library calls per block, ~1 200 per plant
+// step, a quarter of all instructions): both go through sincos(), so that the two inlined expansions for one angle are the same
+// computation and the compiler keeps one of them.
+#ifndef RL4_DASMAT_SINCOS
+#define RL4_DASMAT_SINCOS 1
+#endif
+#if RL4_DASMAT_SINCOS
+__device__ __forceinline__ double lift_sin(double x) { double sn, cs; sincos(x, &sn, &cs); return sn; }
+__device__ __forceinline__ double lift_cos(double x) { double sn, cs; sincos(x, &sn, &cs); return cs; }
+#else
 #define lift_cos cos
 #define lift_sin sin
+#endif
 #define lift_tan tan
 #define lift_exp exp
 #define lift_floor floor
