@@ -98,8 +98,9 @@ LIFT_HD uint8_t lift_parity(uint64_t v) { v &= 0xff; v ^= v >> 4; v ^= v >> 2; v
         UT r = n < W ? (UT)(a >> n) : 0; c->cf = n <= W ? (a >> (n - 1)) & 1 : 0; c->zf = r == 0; c->sf = (ST)r < 0;            \
         c->of = (a >> (W - 1)) & 1; c->pf = lift_parity(r); return r; }                                                         \
     LIFT_HD uint64_t lift_SAR##W(lift_flags* c, uint64_t a_, uint64_t n_) {                                                          \
-        unsigned n = (unsigned)n_ & (W == 64 ? 63 : 31); ST a = (ST)(UT)a_; if (!n) return (UT)a; if (n >= W) n = W - 1;        \
-        UT r = (UT)(a >> n); c->cf = ((UT)a >> (n - 1)) & 1; c->zf = r == 0; c->sf = (ST)r < 0; c->of = 0; c->pf = lift_parity(r); return r; } \
+        unsigned n = (unsigned)n_ & (W == 64 ? 63 : 31); ST a = (ST)(UT)a_; if (!n) return (UT)a;                               \
+        c->cf = n >= W ? (UT)(a < 0) : (UT)(((UT)a >> (n - 1)) & 1); if (n >= W) n = W - 1;                                     \
+        UT r = (UT)(a >> n); c->zf = r == 0; c->sf = (ST)r < 0; c->of = 0; c->pf = lift_parity(r); return r; } \
     LIFT_HD uint64_t lift_ROL##W(lift_flags* c, uint64_t a_, uint64_t n_) {                                                          \
         const unsigned n = ((unsigned)n_ & (W == 64 ? 63 : 31)) % W; UT a = (UT)a_; if (!n) return a;                           \
         UT r = (UT)((a << n) | (a >> (W - n))); c->cf = r & 1; return r; }                                                      \
