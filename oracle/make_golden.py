@@ -159,13 +159,15 @@ def nl_env_fixture(fault, seed, steps=700, fault_time=3.0, integrator="ode5"):
 
 
 def nl_loop_fixture(seed, *, fault="none", fault_time=60, integrator="ode5", elig="accumulating", ms=0, steps=600, warmup=1.5,
-                    lambda_l=0.8):
+                    lambda_l=0.8, plant="surrogate"):
     """The VERBATIM nonlinear agent: objects.py's IDHPnonlin / Actor_big / Critic_big / RLS on the TensorFlow stand-in,
     driving the verbatim Ce500NonLinear wrapper around the surrogate plant.  numpy >= 2 here, so `_adapt_check` follows
     NEP 50 (oracle / kernel flag numpy2 = 1).  A short warm-up puts the learning-rate decay inside the run."""
     from oracle import nl_c
     O, tf = ref_loader.load_reference_objects()
-    Env, stub = ref_loader.load_reference_nonlinear_env(integrator)
+    # plant="binary": the wrapper drives the reference's REAL plant binary, executing natively (oracle/pe_probe/pe_citation.py) --
+    # then nothing in the loop is a stand-in except the arithmetic inside TensorFlow ops
+    Env, stub = ref_loader.load_reference_nonlinear_env(integrator, plant=plant)
     th = nl_c.theta_reference()
     trim_input = np.array([-0.02855, 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.55, 0.55, 0])
     trim_state = np.array([0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0])
@@ -191,7 +193,7 @@ def nl_loop_fixture(seed, *, fault="none", fault_time=60, integrator="ode5", eli
     finally:
         tf.set_tanh(None); tf.set_noise(None)
     L = idhp.log
-    out = dict(seed=seed, fault=str(fault), fault_time=fault_time, integrator=integrator, elig=str(elig), multistep=ms, steps=steps,
+    out = dict(seed=seed, plant=plant, fault=str(fault), fault_time=fault_time, integrator=integrator, elig=str(elig), multistep=ms, steps=steps,
                warmup=warmup, lambda_l=lambda_l, noise=noise, theta_ref=th[:steps], **{f"w_{k}": v[0] for k, v in w.items()})
     for k in ("eta_a", "t", "x_full", "RSE", "x", "a_cmd", "a_eff", "s", "yref", "e", "a_weights2", "c_weights2", "a_grad",
               "rls_params", "rls_eps_hist", "rls_eps_norm"):
@@ -404,6 +406,12 @@ def main():
                 "replacing_fault": dict(seed=43, elig="replacing", fault="damp_elevator_and_saturate_elevator", fault_time=3.0)}
     for name, kw in nl_cases.items():
         np.savez_compressed(os.path.join(OUT, f"nl_loop_{name}.npz"), **nl_loop_fixture(**kw))
+    # the same verbatim agent + verbatim wrapper on the reference's REAL plant binary (named nlbin_*: not part of the nl_loop_* glob)
+    from oracle.pe_probe import pe_citation
+    if pe_citation.available():
+        bin_cases = {"default": dict(seed=51), "shiftcg_replacing_ms": dict(seed=52, ms=1, elig="replacing", fault="shift_cg", fault_time=3.0)}
+        for name, kw in bin_cases.items():
+            np.savez_compressed(os.path.join(OUT, f"nlbin_loop_{name}.npz"), **nl_loop_fixture(plant="binary", **kw))
     if "--only-utils" in sys.argv:
         return
     for i, f in enumerate([None, "invert_elevator", "damp_elevator", "shift_cg"]):

@@ -221,3 +221,42 @@ def test_agents_learn_to_track_on_the_reference_model():
     assert alive.mean() > 0.9, alive.mean()
     late = np.degrees(e[2000:, alive].mean(axis=0))
     assert np.median(late) < 1.5, np.median(late)
+
+
+@pytest.mark.parametrize("name", ["default", "shiftcg_replacing_ms"])
+def test_idhpnonlin_on_dasmat_follows_the_verbatim_reference_on_the_binary(name):
+    """IDHPnonlin(Ce500NonLinear(plant="dasmat")).train() against golden runs of the WHOLE reference program: verbatim agent +
+    verbatim wrapper + the reference's real plant binary executing natively (tests/golden/nlbin_loop_*.npz; on the CPU the oracle
+    flying the translation equals them bit for bit, tests/test_oracle_golden.py).  On the GPU the model's libm calls are CUDA's,
+    so the flight agrees to ~1e-15 per step and the learning loop amplifies that: tight early, close throughout."""
+    from rl4afcs_b200.envs.nonlinear.env import Ce500NonLinear
+    from rl4afcs_b200.objects import IDHPnonlin
+
+    g = np.load(os.path.join(GOLD, f"nlbin_loop_{name}.npz"))
+    steps, B = int(g["steps"]), 2
+    th = np.zeros(9000); th[:steps] = g["theta_ref"]
+    z = np.zeros_like(th)
+    elig = {"None": None}.get(str(g["elig"]), str(g["elig"]))
+    env_config = {"fault_scenario": str(g["fault"]), "dt": 0.01, "t_end": steps * 0.01, "total_steps": steps, "fault_time": float(g["fault_time"]),
+                  "trim_state": [0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0], "trim_input": TRIM.tolist(), "state_dim": 4, "action_dim": 3,
+                  "reference": {"tracked_state": ["phi", "theta", "psi"], "signal": [z, th, z]}}
+    env = Ce500NonLinear(env_config, batch=B, dtype="mixed", plant="dasmat")
+    idhp_config = {"gamma": 0.6, "multistep": int(g["multistep"]), "lr_decay": 0.998, "lambda_h": 0.95, "lambda_l": float(g["lambda_l"]),
+                   "kappa": [1, 2, 1], "cooldown_time": 2.0, "sigma": 0.1, "warmup_time": float(g["warmup"]), "error_thresh": 1,
+                   "tau": 0.02, "in_dims": 4,
+                   "actor_config": {"layers": {10: "tanh", 1: "tanh"}, "eta_h": 35.0, "eta_l": 5.0, "elig": elig},
+                   "critic_config": {"layers": {10: "tanh", 3: "linear"}, "eta_h": 1.4, "eta_l": 0.7, "elig": 1233},
+                   "rls_config": {"state_dim": 3, "action_dim": 1, "rls_gamma": 1, "rls_cov": 10 ** 6}}
+    w = {k: np.broadcast_to(g[f"w_{k}"], (B,) + g[f"w_{k}"].shape).copy() for k in ("W1a", "W2a", "W1c", "W2c")}
+    idhp = IDHPnonlin(env, idhp_config, seed=1, verbose=0, weights=w, log="full", log_agents=B, chunk=200)
+    idhp.train(steps, noise=np.repeat(g["noise"][:, None], B, axis=1))
+    lg = {k: v.cpu().numpy() for k, v in idhp.log.items()}
+    x, xr = lg["x_full"][0], g["log_x_full"]
+    assert np.array_equal(lg["x_full"][0], lg["x_full"][1], equal_nan=True)           # both lanes fly the same episode
+    assert (np.abs(x[0] - xr[0]) / SCALE).max() < 1e-9                                # the trimmed state after reset (1001 calls)
+    early = slice(0, 120)
+    assert (np.abs(x[early] - xr[early]) / SCALE).max() < 1e-6, (np.abs(x[early] - xr[early]) / SCALE).max()
+    assert np.abs(lg["a_cmd"][0][early] - g["log_a_cmd"][early]).max() < 1e-7
+    # the whole 6 s: same flight (the fault case includes the c.g. shift at 3 s)
+    assert np.abs(lg["e"][0].ravel() - g["log_e"].ravel()).max() < 2e-3, np.abs(lg["e"][0].ravel() - g["log_e"].ravel()).max()
+    assert abs(float(idhp.RSE[0][0]) - g["RSE_total"][0]) < 0.02 * g["RSE_total"][0]
