@@ -302,7 +302,7 @@ def mc_run_fixture(seeds=10):
     return out
 
 
-def mc_test_hparam_fixture(repetitions=2):
+def mc_test_hparam_fixture(repetitions=2, plant="surrogate"):
     """The per-configuration `log` dict the VERBATIM functions.MC_test_hparam (functions.py:931-1060) hands to its plot
     routine -- two algorithms x `repetitions` full 90 s nonlinear episodes on the TensorFlow stand-in / plant stand-in.
     Summary numbers in full, trajectories every 25th sample.  Takes a few minutes."""
@@ -312,7 +312,7 @@ def mc_test_hparam_fixture(repetitions=2):
     from oracle import nl_c
     Fn = ref_loader.load_reference_functions()
     O, tf = ref_loader.load_reference_objects()
-    Env, stub = ref_loader.load_reference_nonlinear_env("ode5")
+    Env, stub = ref_loader.load_reference_nonlinear_env("ode5", plant=plant)      # plant="binary": the reference's real plant, natively
     th = nl_c.theta_reference()
     trim_input = np.array([-0.02855, 0, 0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.55, 0.55, 0])
     trim_state = np.array([0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0])
@@ -345,7 +345,7 @@ def mc_test_hparam_fixture(repetitions=2):
             Fn.MC_test_hparam(configs, "unused/", env, N, repetitions, save=0, show=0)
     finally:
         tf.set_tanh(None); tf.set_noise(None)
-    out = dict(N=N, repetitions=repetitions, noise=noise, theta_ref=th, fault="shift_cg", fault_time=60,
+    out = dict(N=N, repetitions=repetitions, plant=plant, noise=noise, theta_ref=th, fault="shift_cg", fault_time=60,
                **{f"cfg_{k}": np.array([str(x) for x in v]) if k == "elig" else np.asarray(v) for k, v in configs.items()})
     for r, w in enumerate(weights):
         for k, v in w.items():
@@ -412,6 +412,8 @@ def main():
         bin_cases = {"default": dict(seed=51), "shiftcg_replacing_ms": dict(seed=52, ms=1, elig="replacing", fault="shift_cg", fault_time=3.0)}
         for name, kw in bin_cases.items():
             np.savez_compressed(os.path.join(OUT, f"nlbin_loop_{name}.npz"), **nl_loop_fixture(plant="binary", **kw))
+        if "--skip-slow" not in sys.argv:
+            np.savez_compressed(os.path.join(OUT, "nlbin_mc_test_hparam.npz"), **mc_test_hparam_fixture(plant="binary"))
     if "--only-utils" in sys.argv:
         return
     for i, f in enumerate([None, "invert_elevator", "damp_elevator", "shift_cg"]):

@@ -265,3 +265,38 @@ def test_idhpnonlin_on_dasmat_follows_the_verbatim_reference_on_the_binary(name)
     assert abs(float(idhp.RSE[0][0]) - g["RSE_total"][0]) < 1e-9 * g["RSE_total"][0]
     for k in ("a_weights2", "c_weights2", "rls_params"):
         assert np.allclose(lg[k][0], g[f"log_{k}"], rtol=1e-5, atol=1e-8), k
+
+
+def test_mc_test_hparam_on_dasmat_follows_the_verbatim_reference_on_the_binary():
+    """functions.MC_test_hparam on the reference's own aircraft model (2 algorithms x 2 repetitions of the FULL 90 s flight with
+    the c.g.-shift fault at 60 s, one batch of 4 agents) against the `log` dict the VERBATIM functions.MC_test_hparam produced with
+    the verbatim agent, the verbatim wrapper and the real plant binary executing natively (tests/golden/nlbin_mc_test_hparam.npz)."""
+    from rl4afcs_b200 import functions as F
+    from rl4afcs_b200.envs.nonlinear.env import Ce500NonLinear
+
+    g = np.load(os.path.join(GOLD, "nlbin_mc_test_hparam.npz"))
+    assert str(g["plant"]) == "binary"
+    N, reps = int(g["N"]), int(g["repetitions"])
+    B = N * reps
+    th = g["theta_ref"]
+    env_config = {"fault_scenario": str(g["fault"]), "dt": 0.01, "t_end": 90, "total_steps": 9000, "fault_time": float(g["fault_time"]),
+                  "trim_state": [0, 0, 0, 90, 0.0576, 0, 0, 0.0576, 0, 2000, 0, 0], "trim_input": TRIM.tolist(), "state_dim": 4, "action_dim": 3,
+                  "reference": {"tracked_state": ["phi", "theta", "psi"], "signal": [0 * th, th, 0 * th]}}
+    env = Ce500NonLinear(env_config, batch=B, dtype="mixed", plant="dasmat")
+    elig = [None if e == "None" else str(e) for e in g["cfg_elig"]]
+    configs = {k: list(g[f"cfg_{k}"]) for k in ("etaah", "etaal", "etach", "etacl", "lambda_hs", "lambda_ls", "seeds", "ms")}
+    configs["elig"] = elig
+    w = {k: np.stack([g[f"w{r}_{k}"] for _ in range(N) for r in range(reps)]) for k in ("W1a", "W2a", "W1c", "W2c")}
+    noise = np.stack([g["noise"][r] for _ in range(N) for r in range(reps)], axis=1)           # (9000, B)
+    out = F.MC_test_hparam(configs, "unused/", env, N, reps, noise=noise, weights=w)
+    assert [o[0] for o in out] == ["idhpat", "midhp"]
+    worst = {}
+    for i, (algo, cfg, log) in enumerate(out):
+        lg = {k: v.cpu().numpy() for k, v in log.items()}
+        for k, scale in (("e", 1.0), ("theta", 1.0), ("alpha", 1.0), ("q", 5.0), ("V", 90.0), ("h", 2000.0), ("action_cmd", 1.0), ("n_z", 1.0)):
+            d = np.nanmax(np.abs(lg[k][:, ::25] - g[f"log{i}_{k}"])) / scale              # angles are stored in degrees
+            worst[k] = max(worst.get(k, 0.0), float(d))
+        assert np.allclose(lg["RSE"], g[f"log{i}_RSE"], rtol=1e-10, atol=0), (algo, lg["RSE"], g[f"log{i}_RSE"])
+        assert np.allclose(lg["max_nz"], g[f"log{i}_max_abs_nz"], rtol=1e-10, atol=0), algo
+    print("MC_test_hparam on dasmat vs the verbatim run on the binary, worst deviation per quantity over 4 x 90 s:", worst)
+    assert max(worst.values()) < 1e-10, worst               # measured: 6e-14 deg over the four 90 s flights, commanded action identical
