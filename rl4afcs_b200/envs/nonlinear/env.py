@@ -8,11 +8,12 @@ action_commanded, action_effective, rates, t, x_full, x, e, RSE, reward_grad``).
 rate-limited first-order actuators, fault / saturation injection, rewards, MDP state) follows the reference line by
 line inside ``rl4_nl_env_step``.  The aircraft itself (``_citation.step``, envs/nonlinear/env.py:210) is selectable:
 
-* ``plant="surrogate"`` (default): the stand-in of ``include/rl4_citation_surrogate.h``, calibrated against the reference's
-  binary (fast: the throughput configurations run on it; tolerance-level fidelity, DESIGN.md section 9);
-* ``plant="dasmat"``: the reference's OWN model -- its ``_citation`` Windows binary translated to C at build time and compiled
-  for the GPU (csrc/dasmat_plant.cu; every step within ~1e-15 relative of the binary; ~150x heavier).
-  ``reset()`` then runs the model's own ``initialize()`` and the 1001 trim calls of envs/nonlinear/env.py:288-291.
+* ``plant="dasmat"`` (default): the reference's OWN model -- its ``_citation`` Windows binary translated to C at build time and
+  compiled for the GPU (csrc/dasmat_plant.cu; every step within ~1e-15 relative of the binary).
+  ``reset()`` runs the model's own ``initialize()`` and the 1001 trim calls of envs/nonlinear/env.py:288-291.  Needs a library
+  built where the reference tree exists; otherwise the constructor raises and asks for an explicit choice;
+* ``plant="surrogate"``: the stand-in of ``include/rl4_citation_surrogate.h``, calibrated against the reference's binary --
+  a different (similar) aircraft, ~120x lighter: the plant of the throughput configurations.
 """
 from __future__ import annotations
 
@@ -26,7 +27,7 @@ from ... import _lib, nl_engine
 
 class Ce500NonLinear:
     def __init__(self, env_config, render_mode=None, *, batch: int = 1, device="cuda", dtype: str = "mixed",
-                 integrator: str = "ode5", plant: str = "surrogate"):
+                 integrator: str = "ode5", plant: str = "dasmat"):
         self.batch = int(batch)
         self.fault_scenario = env_config["fault_scenario"]
         self.initialized = False
@@ -43,7 +44,14 @@ class Ce500NonLinear:
         self.action = None
         self.tracked_state = env_config["reference"]["tracked_state"]
         self.state_reference = env_config["reference"]["signal"]
-        # plant: "surrogate" = the calibrated stand-in (fast), "dasmat" = the reference's own model translated from its binary
+        # plant: "dasmat" (default) = the reference's own model translated from its binary -- what the reference flies;
+        # "surrogate" = the calibrated stand-in (fast, ~120x lighter), an explicit choice because it is a different aircraft
+        if plant == "dasmat" and not _lib.load().rl4_dasmat_available():
+            raise _lib.Rl4Error("Ce500NonLinear: this librl4afcs_b200.so was built without the reference's plant binary, so the default "
+                                "plant='dasmat' (the reference's own aircraft model) is not available; pass plant='surrogate' for the "
+                                "calibrated stand-in")
+        if plant == "dasmat" and integrator != "ode5":
+            raise _lib.Rl4Error("plant='dasmat' integrates with the model's own fixed-step ode5; integrator='rk4' exists for plant='surrogate'")
         self.plant = plant
         self._engine = nl_engine.NlEngine(self.batch, policy=dtype, device=device, plant=plant)
         self.device = self._engine.device

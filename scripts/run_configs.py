@@ -97,7 +97,7 @@ elif a.config == "nonlinear":
                    "actor_config": {"layers": {10: "tanh", 1: "tanh"}, "eta_h": 35.0, "eta_l": 5.0, "elig": "accumulating"},
                    "critic_config": {"layers": {10: "tanh", 3: "linear"}, "eta_h": 1.4, "eta_l": 0.7, "elig": 1233},
                    "rls_config": {"state_dim": 3, "action_dim": 1, "rls_gamma": 1, "rls_cov": 10 ** 6}}
-    env = Ce500NonLinear(env_config, batch=n, device=dev, dtype="mixed", integrator=a.integrator)
+    env = Ce500NonLinear(env_config, batch=n, device=dev, dtype="mixed", integrator=a.integrator, plant="surrogate")
     idhp = IDHPnonlin(env, idhp_config, seed=8 + rank, verbose=0, log=None, chunk=1000)
     idhp.train(2)                                             # loads the kernels (lazy module loading) outside the timed region
     ms = timed(lambda: idhp.train(steps))                     # reset (trim) + prologue + the fused launches + noise draws

@@ -192,7 +192,7 @@ def test_nonlinear_env_and_agent_api(oracle):
                    "actor_config": {"layers": {10: "tanh", 1: "tanh"}, "eta_h": 35.0, "eta_l": 5.0, "elig": "accumulating"},
                    "critic_config": {"layers": {10: "tanh", 3: "linear"}, "eta_h": 1.4, "eta_l": 0.7, "elig": 1233},
                    "rls_config": {"state_dim": 3, "action_dim": 1, "rls_gamma": 1, "rls_cov": 10 ** 6}}
-    env = Ce500NonLinear(env_config, batch=B, dtype="mixed")
+    env = Ce500NonLinear(env_config, batch=B, dtype="mixed", plant="surrogate")
     s, r, term, trunc, info = env.reset()
     assert s.shape == (B, 4) and float(s.abs().max()) == 0.0 and info["x_full"].shape == (B, 12)
     assert abs(float(info["x_full"][0, 3]) - 90.0) < 1e-9 and abs(float(info["x_full"][0, 7]) - 0.0576) < 1e-9
@@ -269,7 +269,7 @@ def test_idhpnonlin_full_log_dict(oracle):
                    "actor_config": {"layers": {10: "tanh", 1: "tanh"}, "eta_h": 35.0, "eta_l": 5.0, "elig": "accumulating"},
                    "critic_config": {"layers": {10: "tanh", 3: "linear"}, "eta_h": 1.4, "eta_l": 0.7, "elig": 1233},
                    "rls_config": {"state_dim": 3, "action_dim": 1, "rls_gamma": 1, "rls_cov": 10 ** 6}}
-    env = Ce500NonLinear(_nl_env_config(th), batch=B, dtype="mixed")
+    env = Ce500NonLinear(_nl_env_config(th), batch=B, dtype="mixed", plant="surrogate")
     idhp = IDHPnonlin(env, idhp_config, seed=3, verbose=0, log_agents=B, chunk=100)
     idhp.train(steps)
     widths = {"eta_a": 1, "t": 1, "x_full": 12, "RSE": 2, "x": 3, "a_cmd": 1, "a_eff": 1, "s": 4, "yref": 4, "e": 1,
@@ -306,7 +306,7 @@ def test_mc_test_hparam_front_end(oracle):
 
     N, reps, steps, split = 3, 4, 1200, 700
     th = nl_c.theta_reference()
-    env = Ce500NonLinear(_nl_env_config(th, t_end=steps * 0.01, total_steps=steps), batch=N * reps, dtype="mixed")
+    env = Ce500NonLinear(_nl_env_config(th, t_end=steps * 0.01, total_steps=steps), batch=N * reps, dtype="mixed", plant="surrogate")
     configs = {"etaah": [35.0] * N, "etaal": [5.0] * N, "etach": [1.4] * N, "etacl": [0.7] * N, "lambda_hs": [0.95] * N,
                "lambda_ls": [0.95] * N, "seeds": [0] * N, "ms": [0, 0, 1], "elig": [None, "accumulating", "replacing"]}
     out = F.MC_test_hparam(configs, "unused/", env, N, reps, save=0, show=0, flight_step=split)
@@ -363,7 +363,7 @@ def test_nonlinear_env_equals_verbatim_reference_wrapper(path):
     B = 3
     th_full = np.zeros(9000); th_full[: len(g["theta_ref"])] = g["theta_ref"]
     env = Ce500NonLinear(_nl_env_config(th_full, fault_scenario=str(g["fault"]), fault_time=float(g["fault_time"])), batch=B,
-                         dtype="mixed", integrator=str(g["integrator"]))
+                         dtype="mixed", integrator=str(g["integrator"]), plant="surrogate")
     env._set_weight_matrices([int(k) for k in g["kappa"]])
     s, r, term, trunc, info = env.reset()
     assert np.array_equal(info["x_full"].cpu().numpy(), np.broadcast_to(g["x_reset"], (B, 12)))
@@ -395,7 +395,7 @@ def test_idhpnonlin_train_equals_verbatim_reference_run(name):
     th = np.zeros(9000); th[:steps] = g["theta_ref"]
     elig = {"None": None}.get(str(g["elig"]), str(g["elig"]))
     env = Ce500NonLinear(_nl_env_config(th, fault_scenario=str(g["fault"]), fault_time=float(g["fault_time"]), t_end=steps * 0.01,
-                                        total_steps=steps), batch=B, dtype="mixed", integrator=str(g["integrator"]))
+                                        total_steps=steps), batch=B, dtype="mixed", integrator=str(g["integrator"]), plant="surrogate")
     idhp_config = {"gamma": 0.6, "multistep": int(g["multistep"]), "lr_decay": 0.998, "lambda_h": 0.95, "lambda_l": float(g["lambda_l"]),
                    "kappa": [1, 2, 1], "cooldown_time": 2.0, "sigma": 0.1, "warmup_time": float(g["warmup"]), "error_thresh": 1,
                    "tau": 0.02, "in_dims": 4,
@@ -463,7 +463,7 @@ def test_mc_test_hparam_equals_verbatim_reference():
     N, reps = int(g["N"]), int(g["repetitions"])
     B = N * reps
     env = Ce500NonLinear(_nl_env_config(g["theta_ref"], fault_scenario=str(g["fault"]), fault_time=float(g["fault_time"])), batch=B,
-                         dtype="mixed")
+                         dtype="mixed", plant="surrogate")
     elig = [None if e == "None" else str(e) for e in g["cfg_elig"]]
     configs = {k: list(g[f"cfg_{k}"]) for k in ("etaah", "etaal", "etach", "etacl", "lambda_hs", "lambda_ls", "seeds", "ms")}
     configs["elig"] = elig
