@@ -343,7 +343,7 @@ __device__ __forceinline__ void dasmat_thread_load(DasmatThread* t, const Dasmat
     for (int w = 0; w < (int)(kASz / 8); ++w) wa[w] = io.state[(int64_t)w * io.stride + i];
     for (int w = 0; w < (int)(kDSz / 8); ++w) wd[w] = io.state[(int64_t)(kASz / 8 + w) * io.stride + i];
     memset(&t->c, 0, sizeof t->c);
-    t->c.G = io.image; t->c.m = t->m;
+    t->c.G = io.image; t->c.m = t->m; t->c.sync = 1;       // every thread of the CTA takes every plant step (nl_core.cuh)
 }
 __device__ __forceinline__ void dasmat_thread_store(DasmatThread* t, const DasmatIo& io, int64_t i)
 {

@@ -397,14 +397,14 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
         // Re-align the warps of the CTA once per step: the step is ~8 000 straight-line instructions (~128 KB), as large
         // as the instruction cache; warps that drift apart each stream the whole loop through it, warps that walk it
         // together share the fetched lines.  Frozen (diverged) agents keep arriving at the barrier and skip the body.
-#ifdef RL4_NL_WITH_DASMAT
-        // the translated model synchronises the CTA at every step() entry (it is far larger than the instruction cache): only
-        // possible while every aircraft of the CTA is flying, which this barrier decides for the whole CTA
-        if (PLANT == 1) dasmat_thread_set_sync(dzp, !__syncthreads_or(diverged_step >= 0));
-        else
-#endif
         __syncthreads();
-        if (diverged_step >= 0) {                                                  // objects.py:1557 (break) + :1168-1175 (NaN rows)
+        // PLANT = 1: the translated model synchronises the CTA at every step() entry (it is far larger than the instruction cache),
+        // so EVERY thread of the CTA must take the plant step, through the one call site below: a frozen (diverged) agent flies
+        // it too -- on whatever its model holds, results discarded, its own state restored -- and leaves afterwards.  (Disabling
+        // the barrier for CTAs with a diverged agent instead cost 40 % of the throughput of a 90 s episode: with 1 % of the
+        // agents diverged nearly every 1024-agent CTA holds one.)
+        const bool frozen = diverged_step >= 0;
+        if (PLANT != 1 && frozen) {                                                // objects.py:1557 (break) + :1168-1175 (NaN rows)
             if (LOG) {
                 if (logged && (k - k0) % lg.every == 0) {
                     const int nf = lg.level >= 3 ? RL4_NLM_COUNT : (lg.level == 2 ? RL4_NLF_COUNT : RL4_NLL_COUNT);
@@ -423,7 +423,32 @@ nl_run_kernel(const __grid_constant__ rl4_nl_params p, const double* __restrict_
         double surf[3], ueff[3], e_phi, e_th, e_psi, reward, rg2;
         const double yref_k = __ldg(theta_ref + k);
         double xo[12];                                                             // what model.step returned (the state before this step)
+#ifdef RL4_NL_WITH_DASMAT
+        double x_keep[PLANT == 1 ? 12 : 1], xa_keep[PLANT == 1 ? 3 : 1];
+        if (PLANT == 1 && frozen) {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) x_keep[j] = x[j];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) xa_keep[j] = x_act[j];
+        }
+#endif
         nl_env_step<PER_AGENT, INTEG, PLANT>(p, hv, stepp, yref_k, act, x, x_act, surf, e_phi, e_th, e_psi, reward, rg2, ueff, xo, dzp);
+#ifdef RL4_NL_WITH_DASMAT
+        if (PLANT == 1 && frozen) {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) x[j] = x_keep[j];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) x_act[j] = xa_keep[j];
+            if (LOG) {
+                if (logged && (k - k0) % lg.every == 0) {
+                    const int nf = lg.level >= 3 ? RL4_NLM_COUNT : (lg.level == 2 ? RL4_NLF_COUNT : RL4_NLL_COUNT);
+                    double* b = lg.buf + ((int64_t)((k - k0) / lg.every) * nf) * lg.n_agents_logged + i;
+                    for (int f = 0; f < nf; ++f) b[(int64_t)f * lg.n_agents_logged] = __longlong_as_double(0x7ff8000000000000LL);
+                }
+            }
+            continue;
+        }
+#endif
         stepp += 1;
         const double x_next_lon[3] = {xo[4], xo[7], xo[1]};                           // env.py:231
         bool nans = false;
