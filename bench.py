@@ -596,7 +596,17 @@ def dasmat_workload(device, counters, issue_peak, n=151552, steps=12, warmup=4) 
         roof["hbm"] = {"achieved_gbps": prof["dram_bytes_per_plant_step"] * rate / 1e9, "peak_gbps": hbm_peak / 1e9,
                        "frac": prof["dram_bytes_per_plant_step"] * rate / hbm_peak}
     out["plant_only"] = {"value": rate, "unit": "plant-steps/s", "ms_per_step": ms / steps, "roofline": roof,
-                         "native_binary_one_host_core_steps_per_s": 3.2e4}
+                         "native_binary_one_host_core_steps_per_s": 3.2e4,
+                         "native_note": "the reference's .pyd executing natively on one core of the build container (it cannot run on this box)"}
+    try:        # CPU yardstick measured HERE: the gcc build of the same translation (test infrastructure, oracle/pe_probe), one core
+        from oracle.pe_probe import lifted
+        if lifted.available():
+            ac = lifted.Aircraft(); ac.initialize()
+            ac.run(np.asarray(trim), 200)
+            t0 = time.perf_counter(); ac.run(np.asarray(trim), 4000); dt = time.perf_counter() - t0
+            out["plant_only"]["cpu_translation_one_core_steps_per_s"] = 4000 / dt
+    except Exception as e:  # noqa: BLE001 - a missing checker library must not fail the bench
+        out["plant_only"]["cpu_translation_error"] = str(e)[:120]
     del dz
     # (2) fused env + agent on it
     eng = nl_engine.NlEngine(n, policy="mixed", device=device, plant="dasmat")
