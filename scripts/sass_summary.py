@@ -42,5 +42,15 @@ demangle = subprocess.run(["c++filt"], input="\n".join(counts), capture_output=T
 print("static SASS instruction counts per kernel of rl4afcs_b200/librl4afcs_b200.so (sm_100a), by class")
 print("  ".join(f"{n:>11}" for n in names) + "  kernel")
 for (k, c), d in zip(counts.items(), demangle):
-    d = re.sub(r"\(.*", "", d)
+    # drop the parameter list (the LAST top-level parenthesis group; template arguments like `(int)1` stay)
+    depth, cut = 0, len(d)
+    for pos in range(len(d) - 1, -1, -1):
+        if d[pos] == ")":
+            depth += 1
+        elif d[pos] == "(":
+            depth -= 1
+            if depth == 0:
+                cut = pos
+                break
+    d = d[:cut]
     print("  ".join(f"{c[n]:>11}" for n in names) + "  " + d)
